@@ -1,0 +1,100 @@
+// Shared host/device helpers for the dclip_b200 C-ABI library (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/dclip_b200.h"
+
+namespace dclip {
+
+// ---- error reporting (thread-local message, negative status codes) -------------------------
+char* last_error_buffer();  // defined in api.cu
+inline int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(last_error_buffer(), 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define DCLIP_CUDA_OK(expr)                                                                        \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return ::dclip::fail(DCLIP_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                                 __FILE__, __LINE__);                                              \
+    } while (0)
+
+#define DCLIP_LAUNCH_OK(name)                                                                      \
+    do {                                                                                           \
+        cudaError_t _e = cudaGetLastError();                                                       \
+        if (_e != cudaSuccess)                                                                     \
+            return ::dclip::fail(DCLIP_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(_e)); \
+    } while (0)
+
+#define DCLIP_REQUIRE(cond, ...)                                       \
+    do {                                                               \
+        if (!(cond)) return ::dclip::fail(DCLIP_ERR_INVALID, __VA_ARGS__); \
+    } while (0)
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline size_t dtype_size(int dt) { return dt == DCLIP_F32 ? 4 : 2; }
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int sm_count();           // cached multiprocessor count of the current device
+bool device_is_sm100();   // compute capability 10.x
+
+// bump allocator over the caller's workspace
+struct Workspace {
+    char* base;
+    size_t size;
+    size_t used = 0;
+    Workspace(void* p, size_t n) : base(static_cast<char*>(p)), size(n) {}
+    void* take(size_t bytes) {
+        size_t off = align_up(used, 256);
+        used = off + bytes;
+        return (base != nullptr && used <= size) ? base + off : nullptr;
+    }
+    bool ok() const { return base != nullptr && used <= size; }
+};
+
+// ---- device helpers -------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+}  // namespace dclip
+
+// dtype dispatch: calls BODY with `T` bound to the element type
+#define DCLIP_DISPATCH_DTYPE(dt, BODY)                                                \
+    switch (dt) {                                                                     \
+        case DCLIP_F32: { using T = float; BODY; } break;                              \
+        case DCLIP_BF16: { using T = __nv_bfloat16; BODY; } break;                     \
+        case DCLIP_F16: { using T = __half; BODY; } break;                             \
+        default: return ::dclip::fail(DCLIP_ERR_INVALID, "unknown dtype %d", (int)(dt)); \
+    }

@@ -1,0 +1,201 @@
+// C-ABI of the distillation objective: argument checking, workspace carving, path choice.
+#include "common.cuh"
+#include "loss_internal.h"
+
+using namespace dclip;
+
+namespace {
+
+int resolve_loss_path(int path, int op_dtype_hint) {
+    (void)op_dtype_hint;
+    if (path == DCLIP_PATH_AUTO) return DCLIP_PATH_FP32;
+    return path;
+}
+
+int check_common(int64_t m, int64_t d) {
+    DCLIP_REQUIRE(m >= 0 && d > 0, "bad shape m=%lld d=%lld", (long long)m, (long long)d);
+    DCLIP_REQUIRE(d % 8 == 0, "d must be a multiple of 8 (got %lld)", (long long)d);
+    return DCLIP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dclip_loss_prep(const void* x, const void* teacher, int64_t m, int64_t d, int dtype, void* x_hat, int op_dtype,
+                    float* inv_norm, float* cos, void* stream) {
+    if (int e = check_common(m, d)) return e;
+    DCLIP_REQUIRE(x && x_hat && inv_norm, "loss_prep: null pointer");
+    DCLIP_REQUIRE(aligned16(x) && aligned16(x_hat) && (!teacher || aligned16(teacher)), "loss_prep: pointers must be 16-byte aligned");
+    PrepArgs a{};
+    a.s[0] = PrepSide{x, teacher, x_hat, inv_norm, cos};
+    a.m = m; a.d = d;
+    return launch_loss_prep(a, 1, dtype, op_dtype, static_cast<cudaStream_t>(stream));
+}
+
+size_t dclip_infonce_rowlse_workspace_bytes(int64_t m, int64_t n, int64_t d, int path) {
+    (void)path;
+    int ns = simt_rowlse_nsplit(m, n, d);
+    if (ns < 1) ns = 1;
+    return 2 * align_up((size_t)ns * m * sizeof(float), 256) + 256;
+}
+
+int dclip_infonce_rowlse(const void* x_hat, int64_t m, const void* y_hat, int64_t n, int64_t d, int op_dtype,
+                         float temperature, int64_t row_offset, float* lse, float* diag, void* workspace,
+                         size_t workspace_bytes, int path, void* stream) {
+    if (int e = check_common(m, d)) return e;
+    DCLIP_REQUIRE(x_hat && y_hat && lse && n > 0, "rowlse: null pointer or empty n");
+    DCLIP_REQUIRE(temperature > 0.f, "rowlse: temperature must be > 0");
+    path = resolve_loss_path(path, op_dtype);
+    if (path == DCLIP_PATH_FP32) {
+        DCLIP_REQUIRE(op_dtype == DCLIP_F32, "rowlse: FP32 path needs float32 operands");
+        LseArgs a{};
+        a.nsplit = simt_rowlse_nsplit(m, n, d);
+        if (a.nsplit == 0) return fail(DCLIP_ERR_UNSUPPORTED, "FP32 loss path supports d <= 1024 (got %lld)", (long long)d);
+        Workspace ws(workspace, workspace_bytes);
+        float* pm = static_cast<float*>(ws.take((size_t)a.nsplit * m * sizeof(float)));
+        float* pl = static_cast<float*>(ws.take((size_t)a.nsplit * m * sizeof(float)));
+        if (!ws.ok()) return fail(DCLIP_ERR_WORKSPACE, "rowlse: workspace too small (%zu < %zu)", workspace_bytes, ws.used);
+        a.s[0] = LseSide{static_cast<const float*>(x_hat), static_cast<const float*>(y_hat), pm, pl, lse, diag};
+        a.m = m; a.n = n; a.d = d; a.temperature = temperature; a.row_offset = row_offset;
+        return launch_rowlse_simt(a, 1, static_cast<cudaStream_t>(stream));
+    }
+    return fail(DCLIP_ERR_UNSUPPORTED, "rowlse: path %d not available", path);
+}
+
+size_t dclip_infonce_grad_workspace_bytes(int64_t m, int64_t n, int64_t d, int path) {
+    (void)m; (void)n; (void)d; (void)path;
+    return 256;
+}
+
+int dclip_infonce_grad(const void* x_hat, int64_t m, const void* y_hat, int64_t n, int64_t d, int op_dtype,
+                       float temperature, int64_t row_offset, const float* lse_x, const float* lse_y, float coef,
+                       float* dx_hat, void* workspace, size_t workspace_bytes, int path, void* stream) {
+    (void)workspace; (void)workspace_bytes;
+    if (int e = check_common(m, d)) return e;
+    DCLIP_REQUIRE(x_hat && y_hat && lse_x && lse_y && dx_hat && n > 0, "infonce_grad: null pointer or empty n");
+    DCLIP_REQUIRE(temperature > 0.f, "infonce_grad: temperature must be > 0");
+    path = resolve_loss_path(path, op_dtype);
+    if (path == DCLIP_PATH_FP32) {
+        DCLIP_REQUIRE(op_dtype == DCLIP_F32, "infonce_grad: FP32 path needs float32 operands");
+        GradArgs a{};
+        a.s[0] = GradSide{static_cast<const float*>(x_hat), static_cast<const float*>(y_hat), lse_x, lse_y, dx_hat};
+        a.m = m; a.n = n; a.d = d; a.temperature = temperature; a.row_offset = row_offset;
+        a.coef_over_tau = coef / temperature;
+        return launch_grad_simt(a, 1, static_cast<cudaStream_t>(stream));
+    }
+    return fail(DCLIP_ERR_UNSUPPORTED, "infonce_grad: path %d not available", path);
+}
+
+int dclip_loss_grad_tail(const void* x, const void* teacher, const float* inv_norm, const float* dx_hat, int64_t m,
+                         int64_t d, int dtype, float w_cos_over_B, float grad_scale, void* d_x, void* stream) {
+    if (int e = check_common(m, d)) return e;
+    DCLIP_REQUIRE(x && inv_norm && d_x, "loss_grad_tail: null pointer");
+    TailArgs a{};
+    a.s[0] = TailSide{x, teacher, inv_norm, dx_hat, d_x};
+    a.m = m; a.d = d; a.w_cos_over_B = w_cos_over_B; a.grad_scale = grad_scale;
+    return launch_grad_tail(a, 1, dtype, static_cast<cudaStream_t>(stream));
+}
+
+int dclip_loss_partial_sums(const float* lse_u, const float* lse_v, const float* diag, const float* cos_img,
+                            const float* cos_txt, int64_t m, float* out3, void* stream) {
+    DCLIP_REQUIRE(out3 && m >= 0, "loss_partial_sums: null pointer");
+    DCLIP_REQUIRE((lse_u && lse_v && diag) || (!lse_u && !lse_v && !diag), "loss_partial_sums: give lse_u, lse_v and diag together or none");
+    SumsArgs a{lse_u, lse_v, diag, cos_img, cos_txt, m, out3, nullptr, 0.f, 0.f, 0.f};
+    return launch_loss_sums(a, static_cast<cudaStream_t>(stream));
+}
+
+int dclip_tensor_path_ready(void) { return 0; }
+
+int dclip_distill_loss_launch_count(int64_t m, int64_t n, int64_t d, int path, int sharded) {
+    (void)m; (void)n; (void)d;
+    path = resolve_loss_path(path, DCLIP_F32);
+    if (path == DCLIP_PATH_FP32) return sharded ? 11 : 7;   // prep, rowlse+combine, sums, grad, tail (x2 sides when sharded)
+    return sharded ? 11 : 7;
+}
+
+// ---- single-GPU composite -------------------------------------------------------------------
+// workspace: u_hat, v_hat [B,d] operands | inv_u, inv_v, cos_img, cos_txt, lse_u, lse_v, diag [B]
+//            | partials 2 x 2 x [nsplit, B] | du_hat, dv_hat [B,d] fp32
+size_t dclip_distill_loss_workspace_bytes(int64_t B, int64_t d, int path) {
+    (void)path;
+    int ns = simt_rowlse_nsplit(B, B, d);
+    if (ns < 1) ns = 1;
+    size_t total = 0;
+    total += 2 * align_up((size_t)B * d * 4, 256);          // operands (fp32 worst case)
+    total += 8 * align_up((size_t)B * 4, 256);              // per-row vectors
+    total += 4 * align_up((size_t)ns * B * 4, 256);         // partials
+    total += 2 * align_up((size_t)B * d * 4, 256);          // dx_hat
+    return total + 1024;
+}
+
+int dclip_distill_loss_fwd_bwd(const void* s_img, const void* s_txt, const void* t_img, const void* t_txt, int64_t B,
+                               int64_t d, int dtype, float temperature, float w_img, float w_txt, float w_con,
+                               float grad_scale, float* losses, void* d_s_img, void* d_s_txt, float* stats,
+                               void* workspace, size_t workspace_bytes, int path, void* stream) {
+    if (int e = check_common(B, d)) return e;
+    DCLIP_REQUIRE(B > 0, "distill_loss: empty batch");
+    DCLIP_REQUIRE(s_img && s_txt && losses, "distill_loss: null pointer");
+    DCLIP_REQUIRE((t_img == nullptr) == (t_txt == nullptr), "distill_loss: give both teachers or neither");
+    DCLIP_REQUIRE((d_s_img == nullptr) == (d_s_txt == nullptr), "distill_loss: give both gradients or neither");
+    DCLIP_REQUIRE(temperature > 0.f, "distill_loss: temperature must be > 0");
+    DCLIP_REQUIRE(aligned16(s_img) && aligned16(s_txt) && aligned16(workspace), "distill_loss: pointers must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    path = resolve_loss_path(path, dtype);
+    if (path != DCLIP_PATH_FP32) return fail(DCLIP_ERR_UNSUPPORTED, "distill_loss: path %d not available", path);
+
+    const int op_dtype = DCLIP_F32;
+    Workspace ws(workspace, workspace_bytes);
+    void* u_hat = ws.take((size_t)B * d * 4);
+    void* v_hat = ws.take((size_t)B * d * 4);
+    float* vec[8];
+    for (auto& v : vec) v = static_cast<float*>(ws.take((size_t)B * 4));
+    float *inv_u = vec[0], *inv_v = vec[1], *cos_img = vec[2], *cos_txt = vec[3], *lse_u = vec[4], *lse_v = vec[5], *diag = vec[6];
+    const int ns = simt_rowlse_nsplit(B, B, d);
+    if (ns == 0) return fail(DCLIP_ERR_UNSUPPORTED, "FP32 loss path supports d <= 1024 (got %lld)", (long long)d);
+    float* part[4];
+    for (auto& p : part) p = static_cast<float*>(ws.take((size_t)ns * B * 4));
+    float* du_hat = static_cast<float*>(ws.take((size_t)B * d * 4));
+    float* dv_hat = static_cast<float*>(ws.take((size_t)B * d * 4));
+    if (!ws.ok()) return fail(DCLIP_ERR_WORKSPACE, "distill_loss: workspace too small (%zu < %zu)", workspace_bytes, ws.used);
+    if (stats) { lse_u = stats; lse_v = stats + B; }
+
+    PrepArgs pa{};
+    pa.s[0] = PrepSide{s_img, t_img, u_hat, inv_u, cos_img};
+    pa.s[1] = PrepSide{s_txt, t_txt, v_hat, inv_v, cos_txt};
+    pa.m = B; pa.d = d;
+    if (int e = launch_loss_prep(pa, 2, dtype, op_dtype, st)) return e;
+
+    LseArgs la{};
+    la.s[0] = LseSide{(const float*)u_hat, (const float*)v_hat, part[0], part[1], lse_u, diag};
+    la.s[1] = LseSide{(const float*)v_hat, (const float*)u_hat, part[2], part[3], lse_v, nullptr};
+    la.m = B; la.n = B; la.d = d; la.temperature = temperature; la.row_offset = 0; la.nsplit = ns;
+    if (int e = launch_rowlse_simt(la, 2, st)) return e;
+
+    SumsArgs sa{lse_u, lse_v, diag, t_img ? cos_img : nullptr, t_txt ? cos_txt : nullptr, B, nullptr, losses, w_img, w_txt, w_con};
+    if (int e = launch_loss_sums(sa, st)) return e;
+
+    if (d_s_img) {
+        const bool need_con = w_con != 0.f;
+        if (need_con) {
+            GradArgs ga{};
+            ga.s[0] = GradSide{(const float*)u_hat, (const float*)v_hat, lse_u, lse_v, du_hat};
+            ga.s[1] = GradSide{(const float*)v_hat, (const float*)u_hat, lse_v, lse_u, dv_hat};
+            ga.m = B; ga.n = B; ga.d = d; ga.temperature = temperature; ga.row_offset = 0;
+            ga.coef_over_tau = w_con / (2.0f * (float)B) / temperature;
+            if (int e = launch_grad_simt(ga, 2, st)) return e;
+        }
+        // the two sides may carry different cosine weights: one tail launch per side
+        TailArgs ta{};
+        ta.m = B; ta.d = d; ta.grad_scale = grad_scale;
+        ta.s[0] = TailSide{s_img, t_img, inv_u, need_con ? du_hat : nullptr, d_s_img};
+        ta.w_cos_over_B = w_img / (float)B;
+        if (int e = launch_grad_tail(ta, 1, dtype, st)) return e;
+        ta.s[0] = TailSide{s_txt, t_txt, inv_v, need_con ? dv_hat : nullptr, d_s_txt};
+        ta.w_cos_over_B = w_txt / (float)B;
+        if (int e = launch_grad_tail(ta, 1, dtype, st)) return e;
+    }
+    return DCLIP_OK;
+}
+
+}  // extern "C"

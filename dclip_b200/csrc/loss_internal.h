@@ -1,0 +1,54 @@
+// Internal launch-argument structs shared by the loss kernels (FP32 and tensor paths).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dclip {
+
+// A "side" is one direction of the symmetric objective: side 0 = image rows against all text
+// rows, side 1 = text rows against all image rows.  Kernels take both sides in one launch
+// (blockIdx.z / .y selects) so the single-GPU step is 6 launches.
+struct PrepSide { const void* x; const void* t; void* xhat; float* inv_norm; float* cos; };
+struct PrepArgs { PrepSide s[2]; int64_t m, d; };
+
+struct LseSide {
+    const float* x; const float* y;   // FP32 path operands (normalised rows)
+    float* part_m; float* part_l;     // [nsplit, m] online-softmax partials
+    float* lse; float* diag;          // outputs [m]
+};
+struct LseArgs {
+    LseSide s[2];
+    int64_t m, n, d;
+    float temperature;
+    int64_t row_offset;
+    int nsplit, tiles_per_split;
+};
+
+struct GradSide { const float* x; const float* y; const float* lse_x; const float* lse_y; float* dx; };
+struct GradArgs {
+    GradSide s[2];
+    int64_t m, n, d;
+    float temperature;
+    int64_t row_offset;
+    float coef_over_tau;
+};
+
+struct TailSide { const void* x; const void* t; const float* inv_norm; const float* dx_hat; void* d_x; };
+struct TailArgs { TailSide s[2]; int64_t m, d; float w_cos_over_B; float grad_scale; };
+
+struct SumsArgs {
+    const float* lse_u; const float* lse_v; const float* diag; const float* cos_img; const float* cos_txt;
+    int64_t m;
+    float* out3;      // raw partial sums (sharded API) or nullptr
+    float* losses;    // finished {total, img, txt, con} (single-GPU composite) or nullptr
+    float w_img, w_txt, w_con;
+};
+
+int launch_loss_prep(const PrepArgs& a, int nsides, int dtype, int op_dtype, cudaStream_t st);
+int simt_rowlse_nsplit(int64_t m, int64_t n, int64_t d);
+int launch_rowlse_simt(LseArgs a, int nsides, cudaStream_t st);
+int launch_grad_simt(const GradArgs& a, int nsides, cudaStream_t st);
+int launch_grad_tail(const TailArgs& a, int nsides, int dtype, cudaStream_t st);
+int launch_loss_sums(const SumsArgs& a, cudaStream_t st);
+
+}  // namespace dclip

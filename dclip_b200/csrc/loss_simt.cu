@@ -1,0 +1,529 @@
+// Distillation objective — FP32 CUDA-core path (exact tier: 1e-5 vs the fp32 reference).
+//
+// Reference math: training/CLIP_image_distillation.py:532-576 (compute_contrastive_loss,
+// cosine_distillation_loss) and :594-634 (combine).  The B x B logits are never stored: the
+// forward keeps per-row log-sum-exp vectors of S and of S^T (each side computes the row block
+// it owns against all rows of the other side — the same kernel serves both sides and every
+// data-parallel rank), the backward recomputes 32 x TJ score tiles and feeds them straight
+// into the second contraction (dX = G . Y) from shared memory.
+//
+// Layout: X_hat tile (32 rows x d, fp32) stays resident in shared memory for the whole CTA
+// life; Y_hat tiles (TJ rows x d) stream through; row stride d+4 floats keeps 128-bit
+// shared loads conflict-free.  Grid: (row tiles, column splits, sides).
+#include "common.cuh"
+#include "loss_internal.h"
+
+namespace dclip {
+
+constexpr int kTI = 32;          // rows of X per CTA
+constexpr int kThreads = 256;
+constexpr float kNormEps = 1e-12f;  // F.normalize eps
+
+// ---------------------------------------------------------------------------------------------
+// prep: one warp per row.  x_hat = x / max(|x|, eps); cos = x_hat . t_hat
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float (&v)[8]);
+template <>
+__device__ __forceinline__ void load8<float>(const float* p, float (&v)[8]) {
+    float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void load8<__half>(const __half* p, float (&v)[8]) {
+    uint4 r = *reinterpret_cast<const uint4*>(p);
+    const __half2* h = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+template <>
+__device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+    uint4 r = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+template <typename T>
+__device__ __forceinline__ void store8(T* p, const float (&v)[8]);
+template <>
+__device__ __forceinline__ void store8<float>(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <>
+__device__ __forceinline__ void store8<__half>(__half* p, const float (&v)[8]) {
+    uint4 r;
+    __half2* h = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = r;
+}
+template <>
+__device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 r;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = r;
+}
+
+template <typename T, typename OT>
+__global__ void __launch_bounds__(kThreads) k_loss_prep(PrepArgs a) {
+    const PrepSide s = a.s[blockIdx.y];
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    if (row >= a.m) return;
+    const int64_t d = a.d;
+    const T* x = static_cast<const T*>(s.x) + row * d;
+    const T* t = s.t ? static_cast<const T*>(s.t) + row * d : nullptr;
+    float ss = 0.f, tt = 0.f, xt = 0.f;
+    for (int64_t k = lane * 8; k < d; k += 256) {
+        float xv[8];
+        load8<T>(x + k, xv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ss = fmaf(xv[i], xv[i], ss);
+        if (t) {
+            float tv[8];
+            load8<T>(t + k, tv);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { tt = fmaf(tv[i], tv[i], tt); xt = fmaf(xv[i], tv[i], xt); }
+        }
+    }
+    ss = warp_sum(ss);
+    const float nx = fmaxf(sqrtf(ss), kNormEps);
+    if (t) { tt = warp_sum(tt); xt = warp_sum(xt); }
+    if (lane == 0) {
+        s.inv_norm[row] = 1.0f / nx;
+        if (s.cos) s.cos[row] = t ? xt / (nx * fmaxf(sqrtf(tt), kNormEps)) : 0.f;
+    }
+    OT* out = static_cast<OT*>(s.xhat) + row * d;
+    for (int64_t k = lane * 8; k < d; k += 256) {
+        float xv[8];
+        load8<T>(x + k, xv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) xv[i] = xv[i] / nx;
+        store8<OT>(out + k, xv);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// score tile: 2 x CPT micro-tile per thread from smem-resident rows, k ascending (fma chain)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_rows(float* dst, int ld, const float* src, int64_t row0, int64_t nrows,
+                                          int rows, int64_t d) {
+    const int vec_per_row = (int)(d / 4);
+    for (int idx = threadIdx.x; idx < rows * vec_per_row; idx += kThreads) {
+        const int r = idx / vec_per_row, c = idx - r * vec_per_row;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row0 + r < nrows) v = __ldg(reinterpret_cast<const float4*>(src + (row0 + r) * d) + c);
+        *reinterpret_cast<float4*>(dst + r * ld + c * 4) = v;
+    }
+}
+
+template <int CPT>
+__device__ __forceinline__ void score_tile(const float* Xs, const float* Ys, int ld, int d, int ty, int tx,
+                                           float (&acc)[2][CPT]) {
+    const float4* x0 = reinterpret_cast<const float4*>(Xs + ty * ld);
+    const float4* x1 = reinterpret_cast<const float4*>(Xs + (ty + 16) * ld);
+    const float4* y0 = reinterpret_cast<const float4*>(Ys + tx * ld);
+    const float4* y1 = reinterpret_cast<const float4*>(Ys + (tx + 16) * ld);
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) acc[r][c] = 0.f;
+#pragma unroll 2
+    for (int k = 0; k < d / 4; ++k) {
+        const float4 a0 = x0[k], a1 = x1[k], b0 = y0[k];
+        acc[0][0] = fmaf(a0.x, b0.x, acc[0][0]); acc[0][0] = fmaf(a0.y, b0.y, acc[0][0]);
+        acc[0][0] = fmaf(a0.z, b0.z, acc[0][0]); acc[0][0] = fmaf(a0.w, b0.w, acc[0][0]);
+        acc[1][0] = fmaf(a1.x, b0.x, acc[1][0]); acc[1][0] = fmaf(a1.y, b0.y, acc[1][0]);
+        acc[1][0] = fmaf(a1.z, b0.z, acc[1][0]); acc[1][0] = fmaf(a1.w, b0.w, acc[1][0]);
+        if (CPT == 2) {
+            const float4 b1 = y1[k];
+            acc[0][CPT - 1] = fmaf(a0.x, b1.x, acc[0][CPT - 1]); acc[0][CPT - 1] = fmaf(a0.y, b1.y, acc[0][CPT - 1]);
+            acc[0][CPT - 1] = fmaf(a0.z, b1.z, acc[0][CPT - 1]); acc[0][CPT - 1] = fmaf(a0.w, b1.w, acc[0][CPT - 1]);
+            acc[1][CPT - 1] = fmaf(a1.x, b1.x, acc[1][CPT - 1]); acc[1][CPT - 1] = fmaf(a1.y, b1.y, acc[1][CPT - 1]);
+            acc[1][CPT - 1] = fmaf(a1.z, b1.z, acc[1][CPT - 1]); acc[1][CPT - 1] = fmaf(a1.w, b1.w, acc[1][CPT - 1]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward: per-row online (max, sum) over a column split; diag pick
+// ---------------------------------------------------------------------------------------------
+template <int CPT>
+__global__ void __launch_bounds__(kThreads) k_rowlse_partial(LseArgs a) {
+    constexpr int TJ = 16 * CPT;
+    extern __shared__ __align__(16) float smem[];
+    const LseSide s = a.s[blockIdx.z];
+    const int d = (int)a.d, ld = d + 4;
+    float* Xs = smem;
+    float* Ys = smem + kTI * ld;
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    const int64_t row0 = (int64_t)blockIdx.x * kTI;
+    load_rows(Xs, ld, s.x, row0, a.m, kTI, a.d);
+
+    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+    const int64_t ntiles = (a.n + TJ - 1) / TJ;
+    const int64_t t_begin = (int64_t)blockIdx.y * a.tiles_per_split;
+    const int64_t t_end = min(ntiles, t_begin + a.tiles_per_split);
+    for (int64_t jt = t_begin; jt < t_end; ++jt) {
+        const int64_t col0 = jt * TJ;
+        __syncthreads();
+        load_rows(Ys, ld, s.y, col0, a.n, TJ, a.d);
+        __syncthreads();
+        float acc[2][CPT];
+        score_tile<CPT>(Xs, Ys, ld, d, ty, tx, acc);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int64_t grow = row0 + ty + 16 * r;
+            float tmax = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) {
+                const int64_t gcol = col0 + tx + 16 * c;
+                float v = acc[r][c] / a.temperature;
+                if (gcol >= a.n) v = -INFINITY;
+                else if (s.diag && gcol == a.row_offset + grow && grow < a.m) s.diag[grow] = v;
+                acc[r][c] = v;
+                tmax = fmaxf(tmax, v);
+            }
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+            const float m_new = fmaxf(m_run[r], tmax);   // finite: every tile has >= 1 valid column
+            float part = 0.f;
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) part += expf(acc[r][c] - m_new);
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            l_run[r] = l_run[r] * expf(m_run[r] - m_new) + part;
+            m_run[r] = m_new;
+        }
+    }
+    if (tx == 0) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int64_t grow = row0 + ty + 16 * r;
+            if (grow < a.m) {
+                s.part_m[(int64_t)blockIdx.y * a.m + grow] = m_run[r];
+                s.part_l[(int64_t)blockIdx.y * a.m + grow] = l_run[r];
+            }
+        }
+    }
+}
+
+__global__ void k_lse_combine(LseArgs a) {
+    const LseSide s = a.s[blockIdx.y];
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.m) return;
+    float M = -INFINITY;
+    for (int p = 0; p < a.nsplit; ++p) M = fmaxf(M, s.part_m[(int64_t)p * a.m + i]);
+    float L = 0.f;
+    for (int p = 0; p < a.nsplit; ++p) {
+        const float mp = s.part_m[(int64_t)p * a.m + i];
+        if (mp > -INFINITY) L += s.part_l[(int64_t)p * a.m + i] * expf(mp - M);
+    }
+    s.lse[i] = M + logf(L);
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward: dX = coef/tau * G . Y with G recomputed tile by tile
+// ---------------------------------------------------------------------------------------------
+template <int CPT, int NC>
+__global__ void __launch_bounds__(kThreads) k_infonce_grad(GradArgs a) {
+    constexpr int TJ = 16 * CPT;
+    constexpr int GLD = kTI + 4;
+    extern __shared__ __align__(16) float smem[];
+    const GradSide s = a.s[blockIdx.z];
+    const int d = (int)a.d, ld = d + 4;
+    float* Xs = smem;
+    float* Ys = Xs + kTI * ld;
+    float* Gt = Ys + TJ * ld;   // [TJ][GLD]: Gt[j][i]
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    const int64_t row0 = (int64_t)blockIdx.x * kTI;
+    load_rows(Xs, ld, s.x, row0, a.m, kTI, a.d);
+
+    float lx[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int64_t grow = row0 + ty + 16 * r;
+        lx[r] = grow < a.m ? s.lse_x[grow] : 0.f;
+    }
+    float out[kTI][NC];
+#pragma unroll
+    for (int i = 0; i < kTI; ++i)
+#pragma unroll
+        for (int q = 0; q < NC; ++q) out[i][q] = 0.f;
+
+    const int64_t ntiles = (a.n + TJ - 1) / TJ;
+    for (int64_t jt = 0; jt < ntiles; ++jt) {
+        const int64_t col0 = jt * TJ;
+        __syncthreads();   // previous tile's Ys / Gt fully consumed
+        load_rows(Ys, ld, s.y, col0, a.n, TJ, a.d);
+        __syncthreads();
+        float acc[2][CPT];
+        score_tile<CPT>(Xs, Ys, ld, d, ty, tx, acc);
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+            const int64_t gcol = col0 + tx + 16 * c;
+            const float ly = gcol < a.n ? s.lse_y[gcol] : 0.f;
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int64_t grow = row0 + ty + 16 * r;
+                float g = 0.f;
+                if (gcol < a.n && grow < a.m) {
+                    const float v = acc[r][c] / a.temperature;
+                    g = expf(v - lx[r]) + expf(v - ly);
+                    if (gcol == a.row_offset + grow) g -= 2.0f;
+                }
+                Gt[(tx + 16 * c) * GLD + ty + 16 * r] = g;
+            }
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int j = 0; j < TJ; ++j) {
+            float y[NC];
+#pragma unroll
+            for (int q = 0; q < NC; ++q) {
+                const int col = threadIdx.x + kThreads * q;
+                y[q] = col < d ? Ys[j * ld + col] : 0.f;
+            }
+            const float4* g4 = reinterpret_cast<const float4*>(Gt + j * GLD);
+#pragma unroll
+            for (int i4 = 0; i4 < kTI / 4; ++i4) {
+                const float4 g = g4[i4];
+#pragma unroll
+                for (int q = 0; q < NC; ++q) {
+                    out[4 * i4 + 0][q] = fmaf(g.x, y[q], out[4 * i4 + 0][q]);
+                    out[4 * i4 + 1][q] = fmaf(g.y, y[q], out[4 * i4 + 1][q]);
+                    out[4 * i4 + 2][q] = fmaf(g.z, y[q], out[4 * i4 + 2][q]);
+                    out[4 * i4 + 3][q] = fmaf(g.w, y[q], out[4 * i4 + 3][q]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kTI; ++i) {
+        const int64_t grow = row0 + i;
+#pragma unroll
+        for (int q = 0; q < NC; ++q) {
+            const int col = threadIdx.x + kThreads * q;
+            if (grow < a.m && col < d) s.dx[grow * a.d + col] = a.coef_over_tau * out[i][q];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// tail: cosine-term gradient + normalise backward, one warp per row
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_loss_grad_tail(TailArgs a) {
+    const TailSide s = a.s[blockIdx.y];
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    if (row >= a.m) return;
+    const int64_t d = a.d;
+    const T* x = static_cast<const T*>(s.x) + row * d;
+    const T* t = s.t ? static_cast<const T*>(s.t) + row * d : nullptr;
+    const float* g_in = s.dx_hat ? s.dx_hat + row * d : nullptr;
+    const float inv = s.inv_norm[row];
+    float t_scale = 0.f;
+    if (t) {
+        float tt = 0.f;
+        for (int64_t k = lane * 8; k < d; k += 256) {
+            float tv[8];
+            load8<T>(t + k, tv);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) tt = fmaf(tv[i], tv[i], tt);
+        }
+        tt = warp_sum(tt);
+        t_scale = -a.w_cos_over_B / fmaxf(sqrtf(tt), kNormEps);
+    }
+    // pass 1: dot = x_hat . g
+    float dot = 0.f;
+    for (int64_t k = lane * 8; k < d; k += 256) {
+        float xv[8], g[8];
+        load8<T>(x + k, xv);
+        if (g_in) load8<float>(g_in + k, g);
+        else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) g[i] = 0.f;
+        }
+        if (t) {
+            float tv[8];
+            load8<T>(t + k, tv);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) g[i] = fmaf(t_scale, tv[i], g[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dot = fmaf(xv[i] * inv, g[i], dot);
+    }
+    dot = warp_sum(dot);
+    // F.normalize clamps the norm: below eps the denominator is a constant (no projection term)
+    const bool clamped = inv >= 1.0f / kNormEps;
+    if (clamped) dot = 0.f;
+    T* out = static_cast<T*>(s.d_x) + row * d;
+    const float scale = inv * a.grad_scale;
+    for (int64_t k = lane * 8; k < d; k += 256) {
+        float xv[8], g[8];
+        load8<T>(x + k, xv);
+        if (g_in) load8<float>(g_in + k, g);
+        else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) g[i] = 0.f;
+        }
+        if (t) {
+            float tv[8];
+            load8<T>(t + k, tv);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) g[i] = fmaf(t_scale, tv[i], g[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] = (g[i] - xv[i] * inv * dot) * scale;
+        store8<T>(out + k, g);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// loss sums: single CTA, fixed-order tree (deterministic)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_loss_sums(SumsArgs a) {
+    __shared__ float red[3][1024];
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int64_t i = threadIdx.x; i < a.m; i += 1024) {
+        if (a.lse_u) s0 += a.lse_u[i] + a.lse_v[i] - 2.0f * a.diag[i];
+        if (a.cos_img) s1 += 1.0f - a.cos_img[i];
+        if (a.cos_txt) s2 += 1.0f - a.cos_txt[i];
+    }
+    red[0][threadIdx.x] = s0; red[1][threadIdx.x] = s1; red[2][threadIdx.x] = s2;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            red[0][threadIdx.x] += red[0][threadIdx.x + o];
+            red[1][threadIdx.x] += red[1][threadIdx.x + o];
+            red[2][threadIdx.x] += red[2][threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (a.out3) { a.out3[0] = red[0][0]; a.out3[1] = red[1][0]; a.out3[2] = red[2][0]; }
+        if (a.losses) {   // single-GPU composite: finished losses {total, img, txt, con}
+            const float l_con = red[0][0] / (2.0f * (float)a.m);
+            const float l_img = a.cos_img ? red[1][0] / (float)a.m : 0.f;
+            const float l_txt = a.cos_txt ? red[2][0] / (float)a.m : 0.f;
+            a.losses[0] = a.w_img * l_img + a.w_txt * l_txt + a.w_con * l_con;
+            a.losses[1] = l_img; a.losses[2] = l_txt; a.losses[3] = l_con;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------------
+int launch_loss_prep(const PrepArgs& a, int nsides, int dtype, int op_dtype, cudaStream_t st) {
+    if (a.m == 0) return DCLIP_OK;
+    dim3 grid((unsigned)ceil_div(a.m, kThreads / 32), nsides);
+    if (op_dtype == DCLIP_F32) {
+        DCLIP_DISPATCH_DTYPE(dtype, (k_loss_prep<T, float><<<grid, kThreads, 0, st>>>(a)));
+    } else if (op_dtype == DCLIP_F16) {
+        DCLIP_DISPATCH_DTYPE(dtype, (k_loss_prep<T, __half><<<grid, kThreads, 0, st>>>(a)));
+    } else if (op_dtype == DCLIP_BF16) {
+        DCLIP_DISPATCH_DTYPE(dtype, (k_loss_prep<T, __nv_bfloat16><<<grid, kThreads, 0, st>>>(a)));
+    } else {
+        return fail(DCLIP_ERR_INVALID, "loss_prep: bad op_dtype %d", op_dtype);
+    }
+    DCLIP_LAUNCH_OK("k_loss_prep");
+    return DCLIP_OK;
+}
+
+static int simt_cpt(int64_t d) {   // columns per thread of the score tile (TJ = 16*CPT)
+    const size_t need2 = (size_t)(kTI + 32) * (d + 4) * 4 + 32 * (kTI + 4) * 4;
+    const size_t need1 = (size_t)(kTI + 16) * (d + 4) * 4 + 16 * (kTI + 4) * 4;
+    if (need2 <= 220 * 1024) return 2;
+    if (need1 <= 220 * 1024) return 1;
+    return 0;
+}
+
+int simt_rowlse_nsplit(int64_t m, int64_t n, int64_t d) {
+    const int cpt = simt_cpt(d);
+    if (cpt == 0) return 0;
+    const int64_t ntiles = ceil_div(n, 16 * cpt);
+    const int64_t rowtiles = ceil_div(m, kTI);
+    int64_t want = ceil_div(2 * (int64_t)sm_count(), rowtiles);   // aim for >= 2 CTAs per SM overall
+    if (want < 1) want = 1;
+    if (want > ntiles) want = ntiles;
+    if (want > 64) want = 64;
+    return (int)want;
+}
+
+int launch_rowlse_simt(LseArgs a, int nsides, cudaStream_t st) {
+    if (a.m == 0) return DCLIP_OK;
+    const int cpt = simt_cpt(a.d);
+    if (cpt == 0) return fail(DCLIP_ERR_UNSUPPORTED, "FP32 loss path supports d <= 1024 (got %lld)", (long long)a.d);
+    const int TJ = 16 * cpt;
+    const int64_t ntiles = ceil_div(a.n, TJ);
+    a.tiles_per_split = (int)ceil_div(ntiles, a.nsplit);
+    const size_t smem = (size_t)(kTI + TJ) * (a.d + 4) * 4;
+    dim3 grid((unsigned)ceil_div(a.m, kTI), a.nsplit, nsides);
+    if (cpt == 2) {
+        DCLIP_CUDA_OK(cudaFuncSetAttribute(k_rowlse_partial<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_rowlse_partial<2><<<grid, kThreads, smem, st>>>(a);
+    } else {
+        DCLIP_CUDA_OK(cudaFuncSetAttribute(k_rowlse_partial<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_rowlse_partial<1><<<grid, kThreads, smem, st>>>(a);
+    }
+    DCLIP_LAUNCH_OK("k_rowlse_partial");
+    dim3 g2((unsigned)ceil_div(a.m, 256), nsides);
+    k_lse_combine<<<g2, 256, 0, st>>>(a);
+    DCLIP_LAUNCH_OK("k_lse_combine");
+    return DCLIP_OK;
+}
+
+template <int CPT, int NC>
+static int launch_grad_inst(const GradArgs& a, int nsides, cudaStream_t st) {
+    constexpr int TJ = 16 * CPT;
+    const size_t smem = ((size_t)(kTI + TJ) * (a.d + 4) + TJ * (kTI + 4)) * 4;
+    DCLIP_CUDA_OK(cudaFuncSetAttribute(k_infonce_grad<CPT, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)ceil_div(a.m, kTI), 1, nsides);
+    k_infonce_grad<CPT, NC><<<grid, kThreads, smem, st>>>(a);
+    DCLIP_LAUNCH_OK("k_infonce_grad");
+    return DCLIP_OK;
+}
+
+int launch_grad_simt(const GradArgs& a, int nsides, cudaStream_t st) {
+    if (a.m == 0) return DCLIP_OK;
+    const int cpt = simt_cpt(a.d);
+    if (cpt == 0) return fail(DCLIP_ERR_UNSUPPORTED, "FP32 loss path supports d <= 1024 (got %lld)", (long long)a.d);
+    const int nc = (int)ceil_div(a.d, kThreads);
+    if (cpt == 2) {
+        switch (nc) {
+            case 1: return launch_grad_inst<2, 1>(a, nsides, st);
+            case 2: return launch_grad_inst<2, 2>(a, nsides, st);
+            case 3: return launch_grad_inst<2, 3>(a, nsides, st);
+            case 4: return launch_grad_inst<2, 4>(a, nsides, st);
+        }
+    } else {
+        switch (nc) {
+            case 1: return launch_grad_inst<1, 1>(a, nsides, st);
+            case 2: return launch_grad_inst<1, 2>(a, nsides, st);
+            case 3: return launch_grad_inst<1, 3>(a, nsides, st);
+            case 4: return launch_grad_inst<1, 4>(a, nsides, st);
+        }
+    }
+    return fail(DCLIP_ERR_UNSUPPORTED, "FP32 loss path supports d <= 1024 (got %lld)", (long long)a.d);
+}
+
+int launch_grad_tail(const TailArgs& a, int nsides, int dtype, cudaStream_t st) {
+    if (a.m == 0) return DCLIP_OK;
+    dim3 grid((unsigned)ceil_div(a.m, kThreads / 32), nsides);
+    DCLIP_DISPATCH_DTYPE(dtype, (k_loss_grad_tail<T><<<grid, kThreads, 0, st>>>(a)));
+    DCLIP_LAUNCH_OK("k_loss_grad_tail");
+    return DCLIP_OK;
+}
+
+int launch_loss_sums(const SumsArgs& a, cudaStream_t st) {
+    k_loss_sums<<<1, 1024, 0, st>>>(a);
+    DCLIP_LAUNCH_OK("k_loss_sums");
+    return DCLIP_OK;
+}
+
+}  // namespace dclip

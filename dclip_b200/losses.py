@@ -1,0 +1,318 @@
+"""Distillation objective — drop-in for the reference's loss functions.
+
+Mirrors (same names, argument meaning and defaults):
+  compute_contrastive_loss(image_embeddings, text_embeddings, temperature=0.05)
+      training/CLIP_image_distillation.py:532-562 == training/train_contrastive_teacher.py:251-261
+  cosine_distillation_loss(student_embeddings, teacher_embeddings)
+      training/CLIP_image_distillation.py:564-576
+  DistillationLoss          the combine of training_step, CLIP_image_distillation.py:594-634
+
+All arithmetic runs in the CUDA library behind include/dclip_b200.h; the B x B logits are
+never materialised.  `distill_loss_fwd_bwd` is the raw fused call (forward + backward in
+one pass over the library), the autograd wrappers are thin shells around it.
+"""
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import check, dtype_code, path_code, ptr, require_cuda, stream_ptr, workspace
+
+__all__ = [
+    "compute_contrastive_loss", "cosine_distillation_loss", "DistillationLoss", "distill_loss_fwd_bwd",
+    "sharded_distill_loss_fwd_bwd", "ShardedDistillationLoss", "CudaLossOps",
+]
+
+
+def _check_pair(a, b, what):
+    if a.dim() != 2 or a.shape != b.shape or a.dtype != b.dtype:
+        raise ValueError(f"{what}: expected two [B, d] tensors of equal shape and dtype, got "
+                         f"{tuple(a.shape)} {a.dtype} and {tuple(b.shape)} {b.dtype}")
+
+
+def distill_loss_fwd_bwd(s_img, s_txt, t_img=None, t_txt=None, temperature=0.05, w_img=1.0, w_txt=1.0, w_con=1.0,
+                         grad_scale=1.0, need_grad=True, path="auto", return_stats=False):
+    """Fused forward+backward of L = w_img*L_img + w_txt*L_txt + w_con*L_con on one GPU.
+
+    Returns (losses[4] = {total, L_img, L_txt, L_con} (float32, on device), d_s_img, d_s_txt)
+    with the gradients in the input dtype (None when need_grad is False).  No host sync.
+    """
+    _check_pair(s_img, s_txt, "distill_loss")
+    if (t_img is None) != (t_txt is None):
+        raise ValueError("distill_loss: give both teacher tensors or neither")
+    if t_img is not None:
+        _check_pair(s_img, t_img, "distill_loss")
+        _check_pair(s_txt, t_txt, "distill_loss")
+    dev = require_cuda(s_img, s_txt, t_img, t_txt)
+    lib = _lib.load_library()
+    B, d = s_img.shape
+    pc = path_code(path)
+    losses = torch.empty(4, dtype=torch.float32, device=dev)
+    d_img = torch.empty_like(s_img) if need_grad else None
+    d_txt = torch.empty_like(s_txt) if need_grad else None
+    stats = torch.empty(2 * B, dtype=torch.float32, device=dev) if return_stats else None
+    ws = workspace(lib.dclip_distill_loss_workspace_bytes(B, d, pc), dev)
+    with torch.cuda.device(dev):
+        check(lib.dclip_distill_loss_fwd_bwd(ptr(s_img), ptr(s_txt), ptr(t_img), ptr(t_txt), B, d, dtype_code(s_img),
+                                             float(temperature), float(w_img), float(w_txt), float(w_con),
+                                             float(grad_scale), ptr(losses), ptr(d_img), ptr(d_txt), ptr(stats),
+                                             ptr(ws), ws.numel(), pc, stream_ptr(dev)), "distill_loss_fwd_bwd")
+    if return_stats:
+        return losses, d_img, d_txt, stats
+    return losses, d_img, d_txt
+
+
+class _DistillLossFn(torch.autograd.Function):
+    """Autograd shell: the library computes loss and gradients in one call; backward only
+    scales the saved gradients by the upstream scalar."""
+
+    @staticmethod
+    def forward(ctx, s_img, s_txt, t_img, t_txt, temperature, w_img, w_txt, w_con, path):
+        need = s_img.requires_grad or s_txt.requires_grad
+        losses, d_img, d_txt = distill_loss_fwd_bwd(s_img.detach(), s_txt.detach(),
+                                                    None if t_img is None else t_img.detach(),
+                                                    None if t_txt is None else t_txt.detach(),
+                                                    temperature, w_img, w_txt, w_con, 1.0, need, path)
+        if need:
+            ctx.save_for_backward(d_img, d_txt)
+        return losses
+
+    @staticmethod
+    def backward(ctx, grad_losses):
+        d_img, d_txt = ctx.saved_tensors
+        g = grad_losses[0]            # only the total (index 0) carries gradient; components are for logging
+        return (d_img * g.to(d_img.dtype), d_txt * g.to(d_txt.dtype), None, None, None, None, None, None, None)
+
+
+def _contig(t):
+    return t if t is None or t.is_contiguous() else t.contiguous()
+
+
+def compute_contrastive_loss(image_embeddings, text_embeddings, temperature=0.05, path="auto"):
+    """Symmetric InfoNCE over the B x B image-text logits (un-normalised [B, d] inputs).
+    Returns a 0-dim tensor with an autograd graph, like the reference."""
+    losses = _DistillLossFn.apply(_contig(image_embeddings), _contig(text_embeddings), None, None, temperature,
+                                  0.0, 0.0, 1.0, path)
+    return losses[0]
+
+
+class _CosineLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, student, teacher):
+        dev = require_cuda(student, teacher)
+        lib = _lib.load_library()
+        m, d = student.shape
+        xhat = torch.empty((m, d), dtype=torch.float32, device=dev)
+        inv = torch.empty(m, dtype=torch.float32, device=dev)
+        cos = torch.empty(m, dtype=torch.float32, device=dev)
+        out3 = torch.empty(3, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            st = stream_ptr(dev)
+            check(lib.dclip_loss_prep(ptr(student), ptr(teacher), m, d, dtype_code(student), ptr(xhat), _lib.DCLIP_F32,
+                                      ptr(inv), ptr(cos), st), "loss_prep")
+            check(lib.dclip_loss_partial_sums(None, None, None, ptr(cos), None, m, ptr(out3), st), "loss_partial_sums")
+        ctx.save_for_backward(student, teacher, inv)
+        return out3[1] / m
+
+    @staticmethod
+    def backward(ctx, g):
+        student, teacher, inv = ctx.saved_tensors
+        lib = _lib.load_library()
+        m, d = student.shape
+        dx = torch.empty_like(student)
+        with torch.cuda.device(student.device):
+            check(lib.dclip_loss_grad_tail(ptr(student), ptr(teacher), ptr(inv), None, m, d, dtype_code(student),
+                                           1.0 / m, 1.0, ptr(dx), stream_ptr(student.device)), "loss_grad_tail")
+        return dx * g.to(dx.dtype), None
+
+
+def cosine_distillation_loss(student_embeddings, teacher_embeddings):
+    """mean_i (1 - cos(student_i, teacher_i)); gradient flows to the student only (the
+    reference's teacher tensors are built under no_grad, CLIP_image_distillation.py:597-608)."""
+    _check_pair(student_embeddings, teacher_embeddings, "cosine_distillation_loss")
+    return _CosineLossFn.apply(_contig(student_embeddings), _contig(teacher_embeddings.detach()))
+
+
+class DistillationLoss(nn.Module):
+    """loss = L_img + L_txt + contrastive_weight * L_con  (CLIP_image_distillation.py:628).
+
+    forward returns the total (0-dim, differentiable w.r.t. the student embeddings);
+    ``last_components`` holds the device tensor {total, L_img, L_txt, L_con} so callers can log
+    all three terms with one host read instead of the reference's three ``.item()`` syncs."""
+
+    def __init__(self, temperature=0.05, contrastive_weight=1.0, image_weight=1.0, text_weight=1.0, path="auto"):
+        super().__init__()
+        self.temperature = temperature
+        self.contrastive_weight = contrastive_weight
+        self.image_weight = image_weight
+        self.text_weight = text_weight
+        self.path = path
+        self.last_components = None
+
+    def forward(self, student_image_embeddings, student_text_embeddings, teacher_image_embeddings,
+                teacher_text_embeddings):
+        losses = _DistillLossFn.apply(_contig(student_image_embeddings), _contig(student_text_embeddings),
+                                      _contig(teacher_image_embeddings.detach()),
+                                      _contig(teacher_text_embeddings.detach()), self.temperature,
+                                      self.image_weight, self.text_weight, self.contrastive_weight, self.path)
+        self.last_components = losses.detach()
+        return losses[0]
+
+
+# ------------------------------------------------------------------------------------------------
+# data-parallel (sharded global batch) — SURVEY.md §8(e)
+# ------------------------------------------------------------------------------------------------
+class CudaLossOps:
+    """The per-rank compute steps of the sharded objective, bound to the C ABI.  The
+    choreography in `sharded_distill_loss_fwd_bwd` only sees this interface, so the CPU
+    (gloo) tests can drive the same choreography with a stand-in."""
+
+    def __init__(self, path="auto"):
+        self.lib = _lib.load_library()
+        self.path = path_code(path)
+        # operands of the FP32 path are float32; the tensor path uses fp16 normalised rows
+        self.op_torch_dtype = torch.float32 if self.path != _lib.PATH_TENSOR else torch.float16
+        self.op_dtype = _lib.DCLIP_F32 if self.path != _lib.PATH_TENSOR else _lib.DCLIP_F16
+
+    def prep(self, x, teacher, out_hat):
+        dev = require_cuda(x, teacher, out_hat)
+        m, d = x.shape
+        inv = torch.empty(m, dtype=torch.float32, device=dev)
+        cos = torch.empty(m, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(self.lib.dclip_loss_prep(ptr(x), ptr(teacher), m, d, dtype_code(x), ptr(out_hat), self.op_dtype,
+                                           ptr(inv), ptr(cos), stream_ptr(dev)), "loss_prep")
+        return inv, cos
+
+    def rowlse(self, x_hat, y_all, temperature, row_offset, want_diag):
+        dev = require_cuda(x_hat, y_all)
+        m, d = x_hat.shape
+        n = y_all.shape[0]
+        lse = torch.empty(m, dtype=torch.float32, device=dev)
+        diag = torch.empty(m, dtype=torch.float32, device=dev) if want_diag else None
+        ws = workspace(self.lib.dclip_infonce_rowlse_workspace_bytes(m, n, d, self.path), dev)
+        with torch.cuda.device(dev):
+            check(self.lib.dclip_infonce_rowlse(ptr(x_hat), m, ptr(y_all), n, d, self.op_dtype, float(temperature),
+                                                int(row_offset), ptr(lse), ptr(diag), ptr(ws), ws.numel(), self.path,
+                                                stream_ptr(dev)), "infonce_rowlse")
+        return lse, diag
+
+    def grad(self, x_hat, y_all, temperature, row_offset, lse_x, lse_y_all, coef):
+        dev = require_cuda(x_hat, y_all, lse_x, lse_y_all)
+        m, d = x_hat.shape
+        n = y_all.shape[0]
+        dx = torch.empty((m, d), dtype=torch.float32, device=dev)
+        ws = workspace(self.lib.dclip_infonce_grad_workspace_bytes(m, n, d, self.path), dev)
+        with torch.cuda.device(dev):
+            check(self.lib.dclip_infonce_grad(ptr(x_hat), m, ptr(y_all), n, d, self.op_dtype, float(temperature),
+                                              int(row_offset), ptr(lse_x), ptr(lse_y_all), float(coef), ptr(dx),
+                                              ptr(ws), ws.numel(), self.path, stream_ptr(dev)), "infonce_grad")
+        return dx
+
+    def tail(self, x, teacher, inv, dx_hat, w_cos_over_B, grad_scale):
+        dev = require_cuda(x, teacher, inv, dx_hat)
+        m, d = x.shape
+        out = torch.empty_like(x)
+        with torch.cuda.device(dev):
+            check(self.lib.dclip_loss_grad_tail(ptr(x), ptr(teacher), ptr(inv), ptr(dx_hat), m, d, dtype_code(x),
+                                                float(w_cos_over_B), float(grad_scale), ptr(out), stream_ptr(dev)),
+                  "loss_grad_tail")
+        return out
+
+    def partial_sums(self, lse_u, lse_v, diag, cos_img, cos_txt):
+        dev = require_cuda(lse_u, lse_v, diag, cos_img, cos_txt)
+        out = torch.empty(3, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(self.lib.dclip_loss_partial_sums(ptr(lse_u), ptr(lse_v), ptr(diag), ptr(cos_img), ptr(cos_txt),
+                                                   lse_u.shape[0], ptr(out), stream_ptr(dev)), "loss_partial_sums")
+        return out
+
+
+def sharded_distill_loss_fwd_bwd(s_img, s_txt, t_img=None, t_txt=None, temperature=0.05, w_img=1.0, w_txt=1.0,
+                                 w_con=1.0, grad_scale=1.0, need_grad=True, group=None, ops=None, path="auto"):
+    """Global-batch objective with the batch sharded over the ranks of `group`.
+
+    Every rank passes its own [m, d] rows (equal m on all ranks; rank r owns global rows
+    [r*m, (r+1)*m)).  Returns (losses[4] of the GLOBAL batch, d_s_img, d_s_txt for the local
+    rows) — identical on every rank to what one process would compute on the concatenated
+    batch.  Collectives: all-gather of the normalised operands (2 x [m, d]), all-gather of
+    the two log-sum-exp vectors (2 x [m] floats), all-reduce of 3 floats.  Each rank
+    recomputes the column block it owns, so no [B, d] gradient reduce-scatter is needed.
+    """
+    import torch.distributed as dist
+
+    ops = ops or CudaLossOps(path)
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    m, d = s_img.shape
+    B = m * world
+    row_offset = rank * m
+    dev = s_img.device
+
+    # (1) normalise local rows straight into this rank's slot of the gathered operand buffers
+    u_all = torch.empty((B, d), dtype=ops.op_torch_dtype, device=dev)
+    v_all = torch.empty((B, d), dtype=ops.op_torch_dtype, device=dev)
+    u_loc = u_all[row_offset:row_offset + m]
+    v_loc = v_all[row_offset:row_offset + m]
+    inv_u, cos_img = ops.prep(s_img, t_img, u_loc)
+    inv_v, cos_txt = ops.prep(s_txt, t_txt, v_loc)
+    if world > 1:
+        dist.all_gather_into_tensor(u_all, u_loc.clone(), group=group)
+        dist.all_gather_into_tensor(v_all, v_loc.clone(), group=group)
+
+    # (2) forward: log-sum-exp of the local row block of S (image side) and of S^T (text side)
+    lse_u, diag = ops.rowlse(u_loc, v_all, temperature, row_offset, True)
+    lse_v, _ = ops.rowlse(v_loc, u_all, temperature, row_offset, False)
+    sums = ops.partial_sums(lse_u, lse_v, diag, cos_img if t_img is not None else None,
+                            cos_txt if t_txt is not None else None)
+    lse_u_all, lse_v_all = lse_u, lse_v
+    if world > 1:
+        lse_u_all = torch.empty(B, dtype=torch.float32, device=dev)
+        lse_v_all = torch.empty(B, dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(lse_u_all, lse_u, group=group)
+        dist.all_gather_into_tensor(lse_v_all, lse_v, group=group)
+        dist.all_reduce(sums, group=group)
+    l_con = sums[0] / (2.0 * B)
+    l_img = sums[1] / B if t_img is not None else torch.zeros((), device=dev)
+    l_txt = sums[2] / B if t_txt is not None else torch.zeros((), device=dev)
+    losses = torch.stack([w_img * l_img + w_txt * l_txt + w_con * l_con, l_img, l_txt, l_con]).float()
+    if not need_grad:
+        return losses, None, None
+
+    # (3) backward: score tiles recomputed; gradients of the local rows only
+    coef = w_con / (2.0 * B)
+    du_hat = ops.grad(u_loc, v_all, temperature, row_offset, lse_u, lse_v_all, coef) if w_con != 0 else None
+    dv_hat = ops.grad(v_loc, u_all, temperature, row_offset, lse_v, lse_u_all, coef) if w_con != 0 else None
+    d_img = ops.tail(s_img, t_img, inv_u, du_hat, w_img / B, grad_scale)
+    d_txt = ops.tail(s_txt, t_txt, inv_v, dv_hat, w_txt / B, grad_scale)
+    return losses, d_img, d_txt
+
+
+class _ShardedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, s_img, s_txt, t_img, t_txt, temperature, w_img, w_txt, w_con, group, path):
+        need = s_img.requires_grad or s_txt.requires_grad
+        losses, d_img, d_txt = sharded_distill_loss_fwd_bwd(s_img.detach(), s_txt.detach(), t_img, t_txt, temperature,
+                                                            w_img, w_txt, w_con, 1.0, need, group, None, path)
+        if need:
+            ctx.save_for_backward(d_img, d_txt)
+        return losses
+
+    @staticmethod
+    def backward(ctx, g):
+        d_img, d_txt = ctx.saved_tensors
+        return (d_img * g[0].to(d_img.dtype), d_txt * g[0].to(d_txt.dtype)) + (None,) * 8
+
+
+class ShardedDistillationLoss(DistillationLoss):
+    """DistillationLoss over a global batch sharded across the ranks of a process group."""
+
+    def __init__(self, *args, group=None, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.group = group
+
+    def forward(self, s_img, s_txt, t_img, t_txt):
+        losses = _ShardedFn.apply(_contig(s_img), _contig(s_txt), _contig(t_img.detach()), _contig(t_txt.detach()),
+                                  self.temperature, self.image_weight, self.text_weight, self.contrastive_weight,
+                                  self.group, self.path)
+        self.last_components = losses.detach()
+        return losses[0]

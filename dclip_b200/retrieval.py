@@ -1,0 +1,321 @@
+"""Cosine retrieval — drop-in for the reference's evaluation / KNN functions.
+
+Mirrors:
+  calculate_retrieval_metrics(similarity_matrix, image_ids, caption_image_ids)
+      eval_scripts/flickr30k_eval.py:16-88  (kept for compatibility: takes a materialised matrix)
+  retrieval_metrics_from_embeddings(caption_emb, image_emb, image_ids, caption_image_ids)
+      the fused form of flickr30k_eval.py:243-269: normalise -> scores -> ranks -> R@K without
+      ever building the [n_cap, n_img] similarity matrix
+  IndexFlatIP(d).add(x) / .search(q, k) / .ntotal
+      the faiss surface used at training/compute_faiss.py:27,79 and training/image_tokenizer.py:262
+
+Score contract (bit-exact against oracle/retrieval_oracle.c): fp32 fmaf chain over k ascending,
+order (-score, +index).  Rank of a target = #{s_j > s_t} + #{j < t : s_j == s_t}, i.e. the
+position in ``np.argsort(-s, kind="stable")``; partial ranks over gallery shards add up.
+"""
+from collections import defaultdict
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, dtype_code, path_code, ptr, require_cuda, stream_ptr, workspace
+
+__all__ = ["calculate_retrieval_metrics", "retrieval_metrics_from_embeddings", "retrieval_ranks", "normalize_rows",
+           "pair_scores", "rank_counts", "matrix_ranks", "recall_metrics", "topk_ip", "topk_merge", "IndexFlatIP",
+           "build_eval_index", "sharded_topk_ip", "sharded_retrieval_ranks"]
+
+
+def _as_cuda(x, device=None, dtype=None):
+    """numpy / CPU tensors are accepted at this boundary (the reference hands numpy arrays)
+    and moved to the GPU; compute never happens on the host."""
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(np.ascontiguousarray(x))
+    if not isinstance(x, torch.Tensor):
+        x = torch.as_tensor(x)
+    if dtype is not None and x.dtype != dtype:
+        x = x.to(dtype)
+    if not x.is_cuda:
+        if device is None:
+            if not torch.cuda.is_available():
+                raise RuntimeError("dclip_b200.retrieval needs a CUDA device (there is no CPU fallback)")
+            device = torch.device("cuda", torch.cuda.current_device())
+        x = x.to(device, non_blocking=True)
+    return x.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# thin wrappers over the C ABI
+# ------------------------------------------------------------------------------------------------
+def normalize_rows(x):
+    """x / ||x|| per row with the contract's arithmetic (numpy semantics: no eps). -> float32."""
+    dev = require_cuda(x)
+    n, d = x.shape
+    out = torch.empty((n, d), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.load_library().dclip_normalize_rows(ptr(x), n, d, dtype_code(x), ptr(out), stream_ptr(dev)),
+              "normalize_rows")
+    return out
+
+
+def pair_scores(q, g, gidx, qidx=None):
+    dev = require_cuda(q, g, gidx, qidx)
+    n = gidx.shape[0]
+    out = torch.empty(n, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.load_library().dclip_pair_scores(ptr(q), ptr(g), q.shape[1], ptr(qidx), ptr(gidx), n, ptr(out),
+                                                    stream_ptr(dev)), "pair_scores")
+    return out
+
+
+def rank_counts(q, g, target_score, target_index, qidx=None, g_index_offset=0, path="fp32"):
+    """Partial ranks of the targets over gallery shard `g` (int32[npairs])."""
+    dev = require_cuda(q, g, target_score, target_index, qidx)
+    lib = _lib.load_library()
+    npairs = target_index.shape[0]
+    ng, d = g.shape
+    rank = torch.empty(npairs, dtype=torch.int32, device=dev)
+    pc = path_code(path)
+    ws = workspace(lib.dclip_rank_counts_workspace_bytes(npairs, ng, d, pc), dev)
+    with torch.cuda.device(dev):
+        check(lib.dclip_rank_counts(ptr(q), ptr(g), ng, d, ptr(qidx), ptr(target_score), ptr(target_index), npairs,
+                                    int(g_index_offset), ptr(rank), ptr(ws), ws.numel(), pc, stream_ptr(dev)),
+              "rank_counts")
+    return rank
+
+
+def recall_metrics(rank, group=None, n_groups=0):
+    """-> float64[4] device tensor {R@1, R@5, R@10, MRR}."""
+    dev = require_cuda(rank, group)
+    lib = _lib.load_library()
+    out = torch.empty(4, dtype=torch.float64, device=dev)
+    ws = workspace(4 * max(int(n_groups), 1) + 64, dev)
+    with torch.cuda.device(dev):
+        check(lib.dclip_recall_metrics(ptr(rank), ptr(group), rank.shape[0], int(n_groups), ptr(out), ptr(ws),
+                                       ws.numel(), stream_ptr(dev)), "recall_metrics")
+    return out
+
+
+def topk_ip(q, g, k, g_index_offset=0, path="fp32"):
+    """Exact inner-product top-k: (scores float32[nq,k] descending, index int64[nq,k])."""
+    dev = require_cuda(q, g)
+    lib = _lib.load_library()
+    nq, d = q.shape
+    ng = g.shape[0]
+    if g.shape[1] != d:
+        raise ValueError(f"topk_ip: dim mismatch {q.shape} vs {g.shape}")
+    out_s = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    out_i = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    pc = path_code(path)
+    ws = workspace(lib.dclip_topk_ip_workspace_bytes(nq, ng, d, k, dtype_code(q), dtype_code(g), pc), dev)
+    with torch.cuda.device(dev):
+        check(lib.dclip_topk_ip(ptr(q), ptr(g), nq, ng, d, k, dtype_code(q), dtype_code(g), int(g_index_offset),
+                                ptr(out_s), ptr(out_i), ptr(ws), ws.numel(), pc, stream_ptr(dev)), "topk_ip")
+    return out_s, out_i
+
+
+def topk_merge(scores, index):
+    """[nlists, nq, k] per-shard results -> [nq, k] by (-score, +index)."""
+    dev = require_cuda(scores, index)
+    nlists, nq, k = scores.shape
+    out_s = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    out_i = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.load_library().dclip_topk_merge(ptr(scores), ptr(index), nlists, nq, k, ptr(out_s), ptr(out_i),
+                                                   stream_ptr(dev)), "topk_merge")
+    return out_s, out_i
+
+
+# ------------------------------------------------------------------------------------------------
+# Recall@K evaluation
+# ------------------------------------------------------------------------------------------------
+def build_eval_index(image_ids, caption_image_ids):
+    """Host-side bookkeeping of calculate_retrieval_metrics (flickr30k_eval.py:18-21, :33-34, :52-56):
+    gt image index per caption (first match, like list.index) and the (image, caption) pairs of
+    the i2t direction grouped by image."""
+    first = {}
+    for idx, iid in enumerate(image_ids):
+        first.setdefault(iid, idx)
+    try:
+        gt_img = np.fromiter((first[c] for c in caption_image_ids), dtype=np.int64, count=len(caption_image_ids))
+    except KeyError as e:      # the reference raises ValueError from list.index here
+        raise ValueError(f"{e.args[0]!r} is not in list") from None
+    img_to_caps = defaultdict(list)
+    for ci, cid in enumerate(caption_image_ids):
+        img_to_caps[cid].append(ci)
+    pair_img, pair_cap = [], []
+    for ii, iid in enumerate(image_ids):
+        for ci in img_to_caps.get(iid, ()):
+            pair_img.append(ii)
+            pair_cap.append(ci)
+    return gt_img, np.asarray(pair_img, dtype=np.int64), np.asarray(pair_cap, dtype=np.int64)
+
+
+def retrieval_ranks(caption_emb, image_emb, image_ids, caption_image_ids, path="fp32"):
+    """(t2i_rank int32[n_cap], i2t_pair_rank int32[n_pairs], pair_img int64[n_pairs]) on the device.
+    Embeddings are un-normalised [n, d]; normalisation is part of the op (flickr30k_eval.py:249-250)."""
+    cap = _as_cuda(caption_emb)
+    img = _as_cuda(image_emb, cap.device)
+    dev = cap.device
+    gt_img, pair_img, pair_cap = build_eval_index(list(image_ids), list(caption_image_ids))
+    gt_img_d = torch.from_numpy(gt_img).to(dev)
+    pair_img_d = torch.from_numpy(pair_img).to(dev)
+    pair_cap_d = torch.from_numpy(pair_cap).to(dev)
+    c_hat = normalize_rows(cap)
+    i_hat = normalize_rows(img)
+    # text -> image: every caption against all images, target = its ground-truth image
+    ts = pair_scores(c_hat, i_hat, gt_img_d)
+    t2i = rank_counts(c_hat, i_hat, ts, gt_img_d, path=path)
+    # image -> text: one (image, gt caption) pair per caption; best rank per image taken later
+    ts2 = pair_scores(i_hat, c_hat, pair_cap_d, qidx=pair_img_d)
+    i2t_pairs = rank_counts(i_hat, c_hat, ts2, pair_cap_d, qidx=pair_img_d, path=path)
+    return t2i, i2t_pairs, pair_img_d
+
+
+def _metrics_dict(t2i_m, i2t_m):
+    t, i = t2i_m.tolist(), i2t_m.tolist()     # the one device->host read of the evaluation
+    keys = ("R@1", "R@5", "R@10", "MAP")
+    return {"t2i": dict(zip(keys, t)), "i2t": dict(zip(keys, i))}
+
+
+def retrieval_metrics_from_embeddings(caption_emb, image_emb, image_ids, caption_image_ids, path="fp32"):
+    """Fused evaluation: same dict as calculate_retrieval_metrics, S never materialised."""
+    t2i, i2t_pairs, pair_img = retrieval_ranks(caption_emb, image_emb, image_ids, caption_image_ids, path)
+    t2i_m = recall_metrics(t2i)
+    i2t_m = recall_metrics(i2t_pairs, group=pair_img, n_groups=len(image_ids))
+    return _metrics_dict(t2i_m, i2t_m)
+
+
+def matrix_ranks(sim, line_index, target_index, along_rows):
+    """Ranks inside a materialised matrix: pair p looks at row (along_rows) or column
+    `line_index[p]` of `sim` and ranks element `target_index[p]` of that line."""
+    dev = require_cuda(sim, line_index, target_index)
+    n = line_index.shape[0]
+    rank = torch.empty(n, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.load_library().dclip_matrix_ranks(ptr(sim), 1 if sim.dtype == torch.float64 else 0, sim.shape[0],
+                                                     sim.shape[1], ptr(line_index), ptr(target_index), n,
+                                                     1 if along_rows else 0, ptr(rank), stream_ptr(dev)),
+              "matrix_ranks")
+    return rank
+
+
+def calculate_retrieval_metrics(similarity_matrix, image_ids, caption_image_ids):
+    """Signature-compatible with flickr30k_eval.calculate_retrieval_metrics (:16): takes the
+    materialised [n_cap, n_img] matrix (numpy float64/float32 or a tensor).  Ranks are computed
+    on the GPU by comparison counting (stable-argsort semantics), not by sorting.
+
+    The matrix form exists for compatibility with callers that already built S; the eval script
+    should call `retrieval_metrics_from_embeddings` instead, which never builds it."""
+    sim = _as_cuda(similarity_matrix)
+    dev = sim.device
+    if sim.dtype not in (torch.float32, torch.float64):
+        sim = sim.float()
+    gt_img, pair_img, pair_cap = build_eval_index(list(image_ids), list(caption_image_ids))
+    n_cap, n_img = sim.shape
+    # rank counting over a given matrix is an HBM-bound compare-and-count (dclip_matrix_ranks)
+    gt_img_d = torch.from_numpy(gt_img).to(dev)
+    pair_img_d = torch.from_numpy(pair_img).to(dev)
+    pair_cap_d = torch.from_numpy(pair_cap).to(dev)
+    t2i = matrix_ranks(sim, torch.arange(n_cap, device=dev), gt_img_d, along_rows=True)
+    i2t_pairs = matrix_ranks(sim, pair_img_d, pair_cap_d, along_rows=False)
+    t2i_m = recall_metrics(t2i)
+    i2t_m = recall_metrics(i2t_pairs, group=pair_img_d, n_groups=len(image_ids))
+    return _metrics_dict(t2i_m, i2t_m)
+
+
+# ------------------------------------------------------------------------------------------------
+# faiss-style flat inner-product index
+# ------------------------------------------------------------------------------------------------
+class IndexFlatIP:
+    """Exact inner-product index with the faiss surface the reference uses
+    (compute_faiss.py:27 `IndexFlatIP(d)`, :79 `.add`, image_tokenizer.py:262 `.search`).
+
+    Vectors live in HBM (float32, or float16 with ``storage="float16"`` for 10 M-row galleries);
+    `search` returns numpy arrays for numpy queries (faiss convention) and CUDA tensors for CUDA
+    queries.  Results are ordered by (-score, +index); missing slots are (-inf, -1)."""
+
+    def __init__(self, d, device=None, storage="float32", path="fp32"):
+        self.d = int(d)
+        self.device = torch.device(device) if device is not None else None
+        self.storage = torch.float32 if storage == "float32" else torch.float16
+        self.path = path
+        self._chunks = []
+        self._data = None
+        self.index_offset = 0     # global index of row 0 (gallery sharding)
+
+    @property
+    def ntotal(self):
+        return sum(c.shape[0] for c in self._chunks) + (0 if self._data is None else self._data.shape[0])
+
+    def add(self, x):
+        x = _as_cuda(x, self.device, None)
+        if x.dim() != 2 or x.shape[1] != self.d:
+            raise ValueError(f"IndexFlatIP.add: expected [n, {self.d}], got {tuple(x.shape)}")
+        if self.device is None:
+            self.device = x.device
+        self._chunks.append(x.to(self.storage))
+
+    def _matrix(self):
+        if self._chunks:
+            parts = ([self._data] if self._data is not None else []) + self._chunks
+            self._data = parts[0] if len(parts) == 1 else torch.cat(parts, dim=0)
+            self._chunks = []
+        if self._data is None:
+            dev = self.device or torch.device("cuda", torch.cuda.current_device())
+            self._data = torch.empty((0, self.d), dtype=self.storage, device=dev)
+        return self._data
+
+    def search(self, q, k):
+        as_numpy = isinstance(q, np.ndarray)
+        g = self._matrix()
+        qd = _as_cuda(q, g.device)
+        if qd.dtype not in (torch.float32, torch.float16):
+            qd = qd.float()
+        if g.dtype == torch.float32 and qd.dtype != torch.float32:
+            qd = qd.float()
+        scores, index = topk_ip(qd, g, int(k), self.index_offset, self.path)
+        if as_numpy:
+            return scores.cpu().numpy(), index.cpu().numpy()
+        return scores, index
+
+    def reset(self):
+        self._chunks, self._data = [], None
+
+
+# ------------------------------------------------------------------------------------------------
+# gallery sharding across ranks — SURVEY.md §8(e)
+# ------------------------------------------------------------------------------------------------
+def sharded_topk_ip(q, g_shard, k, g_index_offset, group=None, path="fp32", topk_fn=None, merge_fn=None):
+    """Every rank holds all queries and one contiguous gallery shard (global row index =
+    g_index_offset + local row).  Per-rank top-k, all-gather of the [nq, k] (score, index)
+    lists, merge by (-score, +index).  Returns the same global result on every rank."""
+    import torch.distributed as dist
+
+    topk_fn = topk_fn or topk_ip
+    merge_fn = merge_fn or topk_merge
+    s, i = topk_fn(q, g_shard, k, g_index_offset, path)
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return s, i
+    nq = s.shape[0]
+    all_s = torch.empty((world * nq, k), dtype=s.dtype, device=s.device)     # concat along dim 0
+    all_i = torch.empty((world * nq, k), dtype=i.dtype, device=i.device)
+    dist.all_gather_into_tensor(all_s, s.contiguous(), group=group)
+    dist.all_gather_into_tensor(all_i, i.contiguous(), group=group)
+    return merge_fn(all_s.view(world, nq, k), all_i.view(world, nq, k))
+
+
+def sharded_retrieval_ranks(q_hat, g_hat_shard, target_score, target_index, g_index_offset, qidx=None, group=None,
+                            path="fp32", rank_fn=None):
+    """Partial ranks over this rank's gallery shard, summed over ranks (integer all-reduce:
+    exact and order-independent).  `target_score` must be identical on all ranks (computed by
+    the owner of the target row with `pair_scores` and broadcast, or recomputed from replicated
+    rows — the contract's arithmetic is deterministic)."""
+    import torch.distributed as dist
+
+    rank_fn = rank_fn or rank_counts
+    r = rank_fn(q_hat, g_hat_shard, target_score, target_index, qidx, g_index_offset, path)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(r, group=group)
+    return r

@@ -1,0 +1,181 @@
+/* dclip_b200 — C ABI of the B200-native (sm_100a) DCLIP hot path.
+ *
+ * The reference (ChuckDanz/DCLIP) is pure Python and has no FFI layer: its "boundary" is a
+ * set of Python callables that the training / eval scripts import by name.
+ * This header is the C-ABI those callables bind to in the B200 build (via ctypes, see
+ * dclip_b200/_lib.py and INTEGRATION.md).  Each entry point cites the reference code it
+ * replaces (paths relative to the reference tree).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every data pointer is a DEVICE pointer unless noted
+ *  - the library never allocates or frees tensor memory: inputs, outputs and workspace are
+ *    caller-owned; `*_workspace_bytes()` tells how much scratch an op needs
+ *  - every op only enqueues work on `stream` (a cudaStream_t passed as void*); no device sync
+ *  - returns DCLIP_OK (0) or a negative dclip_status; message via dclip_last_error()
+ *  - no CPU fallback: on a machine without an sm_100 device every compute call fails
+ *  - row-major, contiguous tensors; `d` (embedding dim) must be a multiple of 8
+ */
+#ifndef DCLIP_B200_H
+#define DCLIP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCLIP_B200_VERSION 100 /* major*10000 + minor*100 + patch */
+
+typedef enum {
+    DCLIP_OK = 0,
+    DCLIP_ERR_INVALID = -1,     /* bad shape / null pointer / misalignment */
+    DCLIP_ERR_UNSUPPORTED = -2, /* combination not implemented (e.g. d too large for a path) */
+    DCLIP_ERR_WORKSPACE = -3,   /* workspace too small */
+    DCLIP_ERR_CUDA = -4,        /* CUDA runtime error (message has cudaGetErrorString) */
+    DCLIP_ERR_ARCH = -5         /* tensor path requested on a non-sm_100 device */
+} dclip_status;
+
+typedef enum { DCLIP_F32 = 0, DCLIP_BF16 = 1, DCLIP_F16 = 2 } dclip_dtype;
+
+/* Which arithmetic a GEMM-shaped op runs in.
+ *  FP32   : CUDA-core FFMA, fp32 end to end (1e-5 parity tier; bit-exact retrieval contract)
+ *  TENSOR : tcgen05 / TMEM tiles fed by TMA, fp16 operands (normalised rows, |x|<=1) or the
+ *           input 16-bit dtype, fp32 accumulation (1e-3 parity tier); retrieval re-scores
+ *           candidates with the FP32 contract so indices stay bit-exact
+ *  AUTO   : TENSOR for 16-bit inputs on large problems, FP32 otherwise                      */
+typedef enum { DCLIP_PATH_AUTO = 0, DCLIP_PATH_FP32 = 1, DCLIP_PATH_TENSOR = 2 } dclip_path;
+
+int dclip_version(void);
+/* Copies the calling thread's last error message (NUL-terminated) into buf. */
+int dclip_last_error(char* buf, size_t buf_len);
+/* 1 if device `device` is compute capability 10.x (tcgen05 path usable). */
+int dclip_device_supports_tensor_path(int device);
+
+/* ------------------------------------------------------------------------------------------
+ * Distillation objective   (replaces compute_contrastive_loss
+ *   training/CLIP_image_distillation.py:532-562 == training/train_contrastive_teacher.py:251-261,
+ *   cosine_distillation_loss training/CLIP_image_distillation.py:564-576 and the combine in
+ *   training_step :594-634)
+ *
+ *   u_hat = s_img / max(|s_img|, 1e-12), v_hat likewise;  S = u_hat v_hat^T / tau
+ *   L_con = 1/(2B) sum_i (lse_row_i + lse_col_i - 2 S_ii)
+ *   L_img = mean_i (1 - u_hat_i . t_hat_img_i),  L_txt likewise
+ *   L = w_img L_img + w_txt L_txt + w_con L_con ; gradients w.r.t. s_img, s_txt only.
+ *
+ * The B x B logits are never written to memory: forward keeps per-row / per-column
+ * log-sum-exp vectors, backward recomputes score tiles.
+ * ------------------------------------------------------------------------------------------ */
+
+/* Single-GPU, whole objective, forward + backward in one call.
+ *  s_img, s_txt : [B, d] student embeddings, dtype `dtype`
+ *  t_img, t_txt : [B, d] teacher embeddings (same dtype) or NULL (pure InfoNCE: the teacher
+ *                 step's loss, train_contrastive_teacher.py:357)
+ *  losses       : float[4] = {total, L_img, L_txt, L_con}          (device)
+ *  d_s_img/d_s_txt : [B, d] gradients in `dtype`, already multiplied by `grad_scale`
+ *                 (the upstream d(total)); either both NULL (forward only) or both set
+ *  stats        : optional float[2*B] = {lse_row[B], lse_col[B]} for callers that save them */
+size_t dclip_distill_loss_workspace_bytes(int64_t B, int64_t d, int path);
+int dclip_distill_loss_fwd_bwd(const void* s_img, const void* s_txt, const void* t_img, const void* t_txt,
+                               int64_t B, int64_t d, int dtype, float temperature, float w_img, float w_txt,
+                               float w_con, float grad_scale, float* losses, void* d_s_img, void* d_s_txt,
+                               float* stats, void* workspace, size_t workspace_bytes, int path, void* stream);
+
+/* Number of kernels of this library one step launches (single-GPU composite when sharded == 0, the
+ * per-rank building blocks (1)-(5) when sharded != 0); used by bench.py for "gpu_launches". */
+int dclip_distill_loss_launch_count(int64_t m, int64_t n, int64_t d, int path, int sharded);
+/* 1 when the tcgen05 tensor path of the loss is compiled in and validated for use. */
+int dclip_tensor_path_ready(void);
+
+/* Sharded (data-parallel) building blocks — SURVEY.md §8(e).  Rank r owns `m` rows starting at
+ * global row `row_offset` of a global batch of `n` rows.  The host all-gathers the normalised
+ * operands between (1) and (2) and the two lse vectors between (2) and (3); no [B, d]
+ * reduce-scatter is needed because each rank recomputes the column block it owns.
+ *
+ * (1) normalise the local student rows into GEMM operands and compute the row-local cosine
+ *     terms.  x_hat: [m, d] in `op_dtype` (DCLIP_F32 for the FP32 path, DCLIP_F16 for TENSOR);
+ *     inv_norm: float[m] = 1 / max(|x|, 1e-12);  cos: float[m] = x_hat . t_hat (0 if teacher NULL). */
+int dclip_loss_prep(const void* x, const void* teacher, int64_t m, int64_t d, int dtype, void* x_hat,
+                    int op_dtype, float* inv_norm, float* cos, void* stream);
+/* (2) lse[i] = log sum_j exp(x_hat_i . y_hat_j / tau)  over all n rows of y_hat;
+ *     diag[i] = x_hat_i . y_hat_{row_offset+i} / tau  (NULL to skip). */
+size_t dclip_infonce_rowlse_workspace_bytes(int64_t m, int64_t n, int64_t d, int path);
+int dclip_infonce_rowlse(const void* x_hat, int64_t m, const void* y_hat, int64_t n, int64_t d, int op_dtype,
+                         float temperature, int64_t row_offset, float* lse, float* diag, void* workspace,
+                         size_t workspace_bytes, int path, void* stream);
+/* (3) dx_hat[i,:] = coef/tau * sum_j (exp(S_ij - lse_x[i]) + exp(S_ij - lse_y[j]) - 2 [j == row_offset+i]) y_hat[j,:]
+ *     (fp32 [m, d]); lse_x: float[m] (local rows), lse_y: float[n] (all rows of the other side). */
+size_t dclip_infonce_grad_workspace_bytes(int64_t m, int64_t n, int64_t d, int path);
+int dclip_infonce_grad(const void* x_hat, int64_t m, const void* y_hat, int64_t n, int64_t d, int op_dtype,
+                       float temperature, int64_t row_offset, const float* lse_x, const float* lse_y, float coef,
+                       float* dx_hat, void* workspace, size_t workspace_bytes, int path, void* stream);
+/* (4) row-local tail: adds the cosine-distillation gradient (-w_cos/B_global * t_hat), applies the
+ *     normalise backward  dx = (g - x_hat (x_hat . g)) * inv_norm  and writes d_x in `dtype`.
+ *     dx_hat may be NULL (cosine term only).  teacher may be NULL. */
+int dclip_loss_grad_tail(const void* x, const void* teacher, const float* inv_norm, const float* dx_hat, int64_t m,
+                         int64_t d, int dtype, float w_cos_over_B, float grad_scale, void* d_x, void* stream);
+/* (5) local partial sums of the loss terms (host all-reduces them):
+ *     out[0] = sum_i (lse_u[i] + lse_v[i] - 2 diag[i]),  out[1] = sum_i (1 - cos_img[i]),
+ *     out[2] = sum_i (1 - cos_txt[i]).  cos_* may be NULL.  Deterministic (fixed-order) sums. */
+int dclip_loss_partial_sums(const float* lse_u, const float* lse_v, const float* diag, const float* cos_img,
+                            const float* cos_txt, int64_t m, float* out3, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Retrieval   (replaces the similarity build + calculate_retrieval_metrics,
+ *   eval_scripts/flickr30k_eval.py:243-266 and :16-88, and the faiss IndexFlatIP add/search
+ *   used by training/compute_faiss.py:27,79 and training/image_tokenizer.py:262)
+ *
+ * Score contract (bit-exact with oracle/retrieval_oracle.c):
+ *     score(q, g) = fp32 fmaf chain over k = 0..d-1;   order = (-score, +index).
+ * The score matrix is never materialised.
+ * ------------------------------------------------------------------------------------------ */
+
+/* x_hat = x / sqrt(fmaf-chain sum of squares)   (numpy semantics: no eps).  out: float[n, d]. */
+int dclip_normalize_rows(const void* x, int64_t n, int64_t d, int dtype, float* out, void* stream);
+
+/* out[p] = score(q[qidx[p]], g[gidx[p]])  (qidx NULL -> p).  q, g: float32. */
+int dclip_pair_scores(const float* q, const float* g, int64_t d, const int64_t* qidx, const int64_t* gidx,
+                      int64_t npairs, float* out, void* stream);
+
+/* Partial ranks over one gallery shard g[0..ng) whose rows have global indices
+ * g_index_offset + j:   rank[p] = #{ j : s_pj > ts[p]  or (s_pj == ts[p] and g_index_offset + j < tgt[p]) }
+ * with s_pj = score(q[qidx[p]], g[j]), ts = target scores from dclip_pair_scores, tgt = global
+ * target index.  Ranks of shards add up (all-reduce sum) to the stable-argsort rank. */
+size_t dclip_rank_counts_workspace_bytes(int64_t npairs, int64_t ng, int64_t d, int path);
+int dclip_rank_counts(const float* q, const float* g, int64_t ng, int64_t d, const int64_t* qidx,
+                      const float* target_score, const int64_t* target_index, int64_t npairs,
+                      int64_t g_index_offset, int32_t* rank, void* workspace, size_t workspace_bytes, int path,
+                      void* stream);
+
+/* Compatibility form of calculate_retrieval_metrics (flickr30k_eval.py:16), which receives a
+ * MATERIALISED similarity matrix sim[n_rows, n_cols] (float32 if is_f64 == 0 else float64, the
+ * reference stores fp32 products in a float64 buffer, :255).  Pair p ranks element
+ * target_index[p] within row (along_rows = 1) or column (along_rows = 0) line_index[p]:
+ *   rank[p] = #{ j : s_j > s_t  or (s_j == s_t and j < t) }. */
+int dclip_matrix_ranks(const void* sim, int is_f64, int64_t n_rows, int64_t n_cols, const int64_t* line_index,
+                       const int64_t* target_index, int64_t npairs, int along_rows, int32_t* rank, void* stream);
+
+/* R@1, R@5, R@10 and mean reciprocal rank ("MAP" in the reference, :70-71) of `n` ranks.
+ * group (int64[n], values in [0, n_groups)) or NULL: when given, the best (minimum) rank per
+ * group is scored and empty groups are skipped (i2t direction, :48-64).
+ * out: double[4] on the device.  workspace: >= 4 * n_groups + 64 bytes when group != NULL. */
+int dclip_recall_metrics(const int32_t* rank, const int64_t* group, int64_t n, int64_t n_groups, double* out4,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* Exact inner-product top-k of every query against gallery shard g[0..ng):
+ *   out_scores float[nq, k] descending, out_index int64[nq, k] = g_index_offset + row,
+ *   ties by ascending index; unfilled slots (-inf, -1) as in faiss.  k <= 32.
+ *   q: [nq, d] q_dtype, g: [ng, d] g_dtype (DCLIP_F32 or DCLIP_F16). */
+size_t dclip_topk_ip_workspace_bytes(int64_t nq, int64_t ng, int64_t d, int64_t k, int q_dtype, int g_dtype,
+                                     int path);
+int dclip_topk_ip(const void* q, const void* g, int64_t nq, int64_t ng, int64_t d, int64_t k, int q_dtype,
+                  int g_dtype, int64_t g_index_offset, float* out_scores, int64_t* out_index, void* workspace,
+                  size_t workspace_bytes, int path, void* stream);
+/* Merge `nlists` per-shard results ([nlists, nq, k] each) into one [nq, k] by (-score, +index). */
+int dclip_topk_merge(const float* in_scores, const int64_t* in_index, int64_t nlists, int64_t nq, int64_t k,
+                     float* out_scores, int64_t* out_index, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCLIP_B200_H */

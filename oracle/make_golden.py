@@ -1,0 +1,140 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (imported from
+/root/reference with the stub recipe of import_reference.py).  Build-container only.
+
+    python -m oracle.make_golden
+
+The fixtures pin the oracle restatement (tests/test_oracle_golden.py) and, through it, the CUDA
+path.  Each .npz stores inputs (or the seed recipe for the large case) and the reference outputs.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import reference_math as om  # noqa: E402
+from oracle import synthetic  # noqa: E402
+from oracle.import_reference import import_reference  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def xattn_case(pta, dist, name, B, T, R, d, heads, seed, ragged, store_inputs=True):
+    mod = pta.CrossModalAttention(d, heads)
+    mod.load_state_dict(om.perturbed_cross_attention_params(d, heads, seed), strict=True)
+    g = torch.Generator().manual_seed(seed + 1)
+    text, image = synthetic.xattn_inputs(B, T, R, d, seed, ragged)
+    txt_emb = torch.randn(B, d, generator=g)
+    t_out, i_out = mod(text, image)
+    agg_t = pta.PatchTextAggregation.aggregation(None, t_out)
+    agg_i = pta.PatchTextAggregation.aggregation(None, i_out)
+    glob = 0.5 * agg_t + 0.5 * agg_i                                   # patch_text_aggregation.py:647
+    ns = types.SimpleNamespace(device="cpu")
+    loss = dist.CLIPImageDistillation.compute_contrastive_loss(ns, glob, txt_emb)   # == closure :251-261
+    loss.backward()
+    out = {"B": B, "T": T, "R": R, "d": d, "heads": heads, "seed": seed, "ragged": int(ragged),
+           "txt_emb": _np(txt_emb), "global": _np(glob), "loss": _np(loss)}
+    if store_inputs:
+        out.update({"text": _np(text), "image": _np(image), "text_out": _np(t_out), "image_out": _np(i_out),
+                    "agg_text": _np(agg_t), "agg_image": _np(agg_i)})
+    for n, p in mod.named_parameters():
+        if store_inputs:
+            out["param." + n] = _np(p)
+            out["grad." + n] = _np(p.grad)
+        else:
+            out["gradnorm." + n] = np.float64(p.grad.double().norm().item())
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "loss", float(loss))
+
+
+def loss_case(dist, name, B, d, seed, temperature=0.05, zero_row=False, store_inputs=True):
+    s_img, s_txt, t_img, t_txt = synthetic.loss_inputs(B, d, seed)
+    if zero_row:
+        s_img[1] = 0
+        t_txt[2] = 0
+    a = s_img.clone().requires_grad_(True)
+    b = s_txt.clone().requires_grad_(True)
+    ns = types.SimpleNamespace(device="cpu")
+    C = dist.CLIPImageDistillation
+    l_img = C.cosine_distillation_loss(ns, a, t_img)
+    l_txt = C.cosine_distillation_loss(ns, b, t_txt)
+    l_con = C.compute_contrastive_loss(ns, a, b, temperature)
+    total = l_img + l_txt + 1.0 * l_con                                # CLIP_image_distillation.py:628
+    total.backward()
+    out = {"B": B, "d": d, "seed": seed, "temperature": temperature, "zero_row": int(zero_row),
+           "losses": np.array([total.item(), l_img.item(), l_txt.item(), l_con.item()], dtype=np.float64)}
+    if store_inputs:
+        out.update({"s_img": _np(s_img), "s_txt": _np(s_txt), "t_img": _np(t_img), "t_txt": _np(t_txt),
+                    "d_s_img": _np(a.grad), "d_s_txt": _np(b.grad)})
+    else:
+        out.update({"d_s_img_norm": np.float64(a.grad.double().norm().item()),
+                    "d_s_txt_norm": np.float64(b.grad.double().norm().item()),
+                    "d_s_img_head": _np(a.grad[:4]), "d_s_txt_head": _np(b.grad[:4])})
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, out["losses"])
+
+
+def retrieval_case(ev, name, n_img, cpi, d, sigma, seed, drop_images=0):
+    cap, img, image_ids, cap_ids = synthetic.retrieval_inputs(n_img, cpi, d, sigma, seed)
+    if drop_images:   # images without captions are skipped in i2t (flickr30k_eval.py:55-56)
+        keep = [c for c in range(len(cap_ids)) if cap_ids[c] >= drop_images]
+        cap = cap[keep]
+        cap_ids = [cap_ids[c] for c in keep]
+    # the reference's own similarity build, flickr30k_eval.py:249-266 (inlined there; restated verbatim)
+    ie = img / np.linalg.norm(img, axis=1, keepdims=True)
+    ce = cap / np.linalg.norm(cap, axis=1, keepdims=True)
+    sim = np.zeros((len(ce), len(ie)))
+    chunk = 1000
+    for i in range(0, len(ce), chunk):
+        for j in range(0, len(ie), chunk):
+            sim[i:i + chunk, j:j + chunk] = np.matmul(ce[i:i + chunk], ie[j:j + chunk].T)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = ev.calculate_retrieval_metrics(sim, image_ids, cap_ids)
+    flat = np.array([m[dn][k] for dn in ("t2i", "i2t") for k in ("R@1", "R@5", "R@10", "MAP")], dtype=np.float64)
+    # smallest |s_j - s_gt| that any rank decision depends on: ranks are summation-order independent
+    # as long as this is far above fp32 rounding (~1e-7)
+    gt = np.array([image_ids.index(c) for c in cap_ids])
+    sg = sim[np.arange(len(cap_ids)), gt]
+    dif = np.abs(sim - sg[:, None]); dif[np.arange(len(cap_ids)), gt] = np.inf
+    gap = float(dif.min())
+    for c in range(len(cap_ids)):
+        col = np.abs(sim[:, gt[c]] - sim[c, gt[c]]); col[c] = np.inf
+        gap = min(gap, float(col.min()))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), n_img=n_img, cpi=cpi, d=d, sigma=sigma, seed=seed,
+                        drop_images=drop_images, cap=cap, img=img, image_ids=np.array(image_ids),
+                        caption_image_ids=np.array(cap_ids), metrics=flat, min_gap=gap)
+    print(name, flat, "min gap", gap)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    pta, dist, ev = import_reference()
+    xattn_case(pta, dist, "xattn_small", B=3, T=7, R=4, d=64, heads=8, seed=1, ragged=False)
+    xattn_case(pta, dist, "xattn_ragged", B=4, T=9, R=5, d=64, heads=8, seed=2, ragged=True)
+    xattn_case(pta, dist, "xattn_hd96", B=2, T=6, R=3, d=96 * 2, heads=2, seed=3, ragged=False)
+    xattn_case(pta, dist, "xattn_cfg1", B=32, T=77, R=8, d=512, heads=8, seed=42, ragged=True, store_inputs=False)
+    loss_case(dist, "loss_small", B=16, d=64, seed=1)
+    loss_case(dist, "loss_b1", B=1, d=32, seed=2)
+    loss_case(dist, "loss_zero_row", B=8, d=32, seed=3, zero_row=True)
+    loss_case(dist, "loss_temp", B=12, d=48, seed=4, temperature=0.5)
+    loss_case(dist, "loss_cfg1", B=32, d=512, seed=42)
+    loss_case(dist, "loss_b256_d768", B=256, d=768, seed=7, store_inputs=False)
+    retrieval_case(ev, "retrieval_small", n_img=12, cpi=5, d=32, sigma=1.0, seed=1)
+    retrieval_case(ev, "retrieval_mid", n_img=100, cpi=5, d=64, sigma=1.5, seed=2)
+    retrieval_case(ev, "retrieval_dropped", n_img=20, cpi=3, d=32, sigma=1.0, seed=3, drop_images=4)
+
+
+if __name__ == "__main__":
+    main()

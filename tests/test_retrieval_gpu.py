@@ -1,0 +1,124 @@
+"""Parity of the CUDA retrieval path against the C oracle (bit-exact, ties included) and the
+reference's golden metrics."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import retrieval as orc
+from oracle import synthetic
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _d(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+@pytest.mark.parametrize("name", ["retrieval_small", "retrieval_mid", "retrieval_dropped"])
+def test_golden_metrics(built_library, name):
+    from dclip_b200 import retrieval as R
+    g = load_golden(name)
+    image_ids = [int(x) for x in g["image_ids"]]
+    cap_ids = [int(x) for x in g["caption_image_ids"]]
+    m = R.retrieval_metrics_from_embeddings(g["cap"], g["img"], image_ids, cap_ids)
+    got = np.array([m[dn][k] for dn in ("t2i", "i2t") for k in ("R@1", "R@5", "R@10", "MAP")])
+    want = g["metrics"]
+    assert np.array_equal(got[[0, 1, 2, 4, 5, 6]], want[[0, 1, 2, 4, 5, 6]])      # Recall@K bit-exact
+    assert np.allclose(got[[3, 7]], want[[3, 7]], rtol=0, atol=1e-12)
+    # compatibility form on the materialised matrix (float64 buffer of fp32 products, like the reference)
+    sim = orc.numpy_similarity(g["cap"], g["img"])
+    m2 = R.calculate_retrieval_metrics(sim, image_ids, cap_ids)
+    got2 = np.array([m2[dn][k] for dn in ("t2i", "i2t") for k in ("R@1", "R@5", "R@10", "MAP")])
+    assert np.array_equal(got2[[0, 1, 2, 4, 5, 6]], want[[0, 1, 2, 4, 5, 6]])
+    assert np.allclose(got2[[3, 7]], want[[3, 7]], rtol=0, atol=1e-12)
+
+
+def test_normalize_and_scores_bit_exact(built_library):
+    from dclip_b200 import retrieval as R
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((77, 200)).astype(np.float32)
+    xh = R.normalize_rows(_d(x))
+    assert np.array_equal(xh.cpu().numpy(), orc.c_normalize_rows(x))
+    g = rng.standard_normal((301, 200)).astype(np.float32)
+    gi = rng.integers(0, 301, size=77)
+    ps = R.pair_scores(_d(x), _d(g), _d(gi))
+    want = orc.c_scores(x, g)[np.arange(77), gi]
+    assert np.array_equal(ps.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("n_img,cpi,d", [(1000, 5, 512), (37, 3, 40), (130, 1, 768)])
+def test_ranks_bit_exact(built_library, n_img, cpi, d):
+    from dclip_b200 import retrieval as R
+    cap, img, image_ids, cap_ids = synthetic.retrieval_inputs(n_img, cpi, d, 1.0, seed=n_img)
+    t2i, i2t_pairs, pair_img = R.retrieval_ranks(cap, img, image_ids, cap_ids)
+    want_t2i, want_i2t = orc.ranks_from_embeddings_c(cap, img, image_ids, cap_ids)
+    assert t2i.cpu().tolist() == want_t2i
+    best = {}
+    for o, r in zip(pair_img.cpu().tolist(), i2t_pairs.cpu().tolist()):
+        best[o] = min(best.get(o, 1 << 30), r)
+    assert [best[i] for i in range(n_img)] == want_i2t
+
+
+def test_ranks_with_exact_ties(built_library):
+    from dclip_b200 import retrieval as R
+    rng = np.random.default_rng(2)
+    g = rng.integers(-1, 2, size=(150, 8)).astype(np.float32)
+    q = rng.integers(-1, 2, size=(70, 8)).astype(np.float32)
+    tgt = rng.integers(0, 150, size=70)
+    ts = R.pair_scores(_d(q), _d(g), _d(tgt))
+    r = R.rank_counts(_d(q), _d(g), ts, _d(tgt))
+    assert r.cpu().tolist() == orc.c_ranks(q, g, np.arange(70), tgt).tolist()
+    # gallery sharding: partial ranks add up
+    parts = [R.rank_counts(_d(q), _d(g[a:b]), ts, _d(tgt), g_index_offset=a) for a, b in ((0, 64), (64, 65), (65, 150))]
+    assert (parts[0] + parts[1] + parts[2]).cpu().tolist() == r.cpu().tolist()
+
+
+@pytest.mark.parametrize("ng,nq,d,k", [(5000, 33, 128, 10), (64, 1, 512, 3), (100000, 16, 64, 10), (5, 4, 16, 10), (777, 70, 768, 32)])
+def test_topk_bit_exact(built_library, ng, nq, d, k):
+    from dclip_b200 import retrieval as R
+    gal, q, planted = synthetic.gallery_inputs(ng, nq, d, seed=ng + k)
+    s, i = R.topk_ip(_d(q), _d(gal), k)
+    ws, wi = orc.c_topk(q, gal, k)
+    assert np.array_equal(i.cpu().numpy(), wi)
+    assert np.array_equal(s.cpu().numpy(), ws)
+    assert np.array_equal(i[:, 0].cpu().numpy(), planted)
+
+
+def test_topk_ties_and_sharded_merge(built_library):
+    from dclip_b200 import retrieval as R
+    rng = np.random.default_rng(5)
+    g = rng.integers(-1, 2, size=(900, 8)).astype(np.float32)      # heavy exact ties
+    q = rng.integers(-1, 2, size=(20, 8)).astype(np.float32)
+    ws, wi = orc.c_topk(q, g, 10)
+    s, i = R.topk_ip(_d(q), _d(g), 10)
+    assert np.array_equal(i.cpu().numpy(), wi) and np.array_equal(s.cpu().numpy(), ws)
+    bounds = [0, 300, 301, 640, 900]
+    parts = [R.topk_ip(_d(q), _d(g[a:b]), 10, g_index_offset=a) for a, b in zip(bounds[:-1], bounds[1:])]
+    ms, mi = R.topk_merge(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]))
+    assert np.array_equal(mi.cpu().numpy(), wi) and np.array_equal(ms.cpu().numpy(), ws)
+
+
+def test_fp16_gallery(built_library):
+    from dclip_b200 import retrieval as R
+    gal, q, planted = synthetic.gallery_inputs(3000, 12, 96, seed=8)
+    gal16 = gal.astype(np.float16)
+    s, i = R.topk_ip(_d(q), _d(gal16), 10)
+    ws, wi = orc.c_topk(q, gal16.astype(np.float32), 10)     # contract: products of the converted values
+    assert np.array_equal(i.cpu().numpy(), wi) and np.array_equal(s.cpu().numpy(), ws)
+
+
+def test_index_flat_ip_surface(built_library):
+    from dclip_b200 import retrieval as R
+    gal, q, planted = synthetic.gallery_inputs(500, 3, 64, seed=9)
+    index = R.IndexFlatIP(64)
+    for row in gal[:10]:
+        index.add(row[None, :])                 # the reference adds one [1, d] row at a time (compute_faiss.py:79)
+    index.add(gal[10:])
+    assert index.ntotal == 500
+    D, I = index.search(q[:1], 3)               # image_tokenizer.py:262
+    assert isinstance(D, np.ndarray) and D.shape == (1, 3) and I.dtype == np.int64
+    ws, wi = orc.c_topk(q[:1], gal, 3)
+    assert np.array_equal(I, wi) and np.array_equal(D, ws)
+    assert I[0, 0] == planted[0] and D[0, 0] >= 0.85
