@@ -28,6 +28,7 @@ SIGNATURES = {
                                           _vp, _vp, _vp, _sz, _i32, _vp]),
     "dclip_distill_loss_launch_count": (_i32, [_i64, _i64, _i64, _i32, _i32]),
     "dclip_tensor_path_ready": (_i32, []),
+    "dclip_debug_pipeline_error": (_i32, [_vp]),
     "dclip_loss_prep": (_i32, [_vp, _vp, _i64, _i64, _i32, _vp, _i32, _vp, _vp, _vp]),
     "dclip_infonce_rowlse_workspace_bytes": (_sz, [_i64, _i64, _i64, _i32]),
     "dclip_infonce_rowlse": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _f32, _i64, _vp, _vp, _vp, _sz, _i32, _vp]),

@@ -34,8 +34,8 @@ int dclip_loss_prep(const void* x, const void* teacher, int64_t m, int64_t d, in
 }
 
 size_t dclip_infonce_rowlse_workspace_bytes(int64_t m, int64_t n, int64_t d, int path) {
-    (void)path;
     int ns = simt_rowlse_nsplit(m, n, d);
+    if (path == DCLIP_PATH_TENSOR) ns = tc_nsplit(m, n, 1);
     if (ns < 1) ns = 1;
     return 2 * align_up((size_t)ns * m * sizeof(float), 256) + 256;
 }
@@ -60,11 +60,34 @@ int dclip_infonce_rowlse(const void* x_hat, int64_t m, const void* y_hat, int64_
         a.m = m; a.n = n; a.d = d; a.temperature = temperature; a.row_offset = row_offset;
         return launch_rowlse_simt(a, 1, static_cast<cudaStream_t>(stream));
     }
+    if (path == DCLIP_PATH_TENSOR) {
+        DCLIP_REQUIRE(op_dtype == DCLIP_F16, "rowlse: tensor path needs float16 operands (dclip_loss_prep with op_dtype = DCLIP_F16)");
+        if (!tc_loss_shape_ok(d, temperature))
+            return fail(DCLIP_ERR_UNSUPPORTED, "rowlse: tensor path needs d %% 128 == 0, 128 <= d <= 768 and temperature >= 0.025 (d=%lld tau=%g)", (long long)d, temperature);
+        DCLIP_REQUIRE(aligned16(x_hat) && aligned16(y_hat), "rowlse: operands must be 16-byte aligned");
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        const int ns = tc_nsplit(m, n, 1);
+        Workspace ws(workspace, workspace_bytes);
+        float* part = static_cast<float*>(ws.take((size_t)ns * m * sizeof(float)));
+        if (!ws.ok()) return fail(DCLIP_ERR_WORKSPACE, "rowlse: workspace too small (%zu < %zu)", workspace_bytes, ws.used);
+        TcArgs a{};
+        a.s[0] = TcSide{nullptr, nullptr, part};
+        a.m = m; a.n = n; a.d = d; a.inv_tau = 1.0f / temperature; a.row_offset = row_offset;
+        const void* xs[2] = {x_hat, x_hat};
+        const void* ys[2] = {y_hat, y_hat};
+        if (int e = launch_infonce_tc(false, 1, xs, ys, a, ns, st)) return e;
+        if (int e = launch_tc_lse_combine(part, ns, m, a.inv_tau, lse, st)) return e;
+        if (diag) return launch_tc_diag(x_hat, y_hat, m, n, d, a.inv_tau, row_offset, diag, st);
+        return DCLIP_OK;
+    }
     return fail(DCLIP_ERR_UNSUPPORTED, "rowlse: path %d not available", path);
 }
 
 size_t dclip_infonce_grad_workspace_bytes(int64_t m, int64_t n, int64_t d, int path) {
-    (void)m; (void)n; (void)d; (void)path;
+    if (path == DCLIP_PATH_TENSOR) {
+        const int ns = tc_nsplit(m, n, 1);
+        return ns > 1 ? align_up((size_t)ns * m * d * sizeof(float), 256) + 256 : 256;
+    }
     return 256;
 }
 
@@ -83,6 +106,28 @@ int dclip_infonce_grad(const void* x_hat, int64_t m, const void* y_hat, int64_t 
         a.m = m; a.n = n; a.d = d; a.temperature = temperature; a.row_offset = row_offset;
         a.coef_over_tau = coef / temperature;
         return launch_grad_simt(a, 1, static_cast<cudaStream_t>(stream));
+    }
+    if (path == DCLIP_PATH_TENSOR) {
+        DCLIP_REQUIRE(op_dtype == DCLIP_F16, "infonce_grad: tensor path needs float16 operands");
+        if (!tc_loss_shape_ok(d, temperature))
+            return fail(DCLIP_ERR_UNSUPPORTED, "infonce_grad: tensor path needs d %% 128 == 0, 128 <= d <= 768 and temperature >= 0.025 (d=%lld tau=%g)", (long long)d, temperature);
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        const int ns = tc_nsplit(m, n, 1);
+        float* out = dx_hat;
+        if (ns > 1) {
+            Workspace ws(workspace, workspace_bytes);
+            out = static_cast<float*>(ws.take((size_t)ns * m * d * sizeof(float)));
+            if (!ws.ok()) return fail(DCLIP_ERR_WORKSPACE, "infonce_grad: workspace too small (%zu < %zu)", workspace_bytes, ws.used);
+        }
+        TcArgs a{};
+        a.s[0] = TcSide{lse_x, lse_y, out};
+        a.m = m; a.n = n; a.d = d; a.inv_tau = 1.0f / temperature; a.row_offset = row_offset;
+        a.out_scale = coef / temperature * (1.0f / 8192.0f);
+        const void* xs[2] = {x_hat, x_hat};
+        const void* ys[2] = {y_hat, y_hat};
+        if (int e = launch_infonce_tc(true, 1, xs, ys, a, ns, st)) return e;
+        if (ns > 1) return launch_tc_grad_combine(out, ns, m, d, dx_hat, st);
+        return DCLIP_OK;
     }
     return fail(DCLIP_ERR_UNSUPPORTED, "infonce_grad: path %d not available", path);
 }
@@ -105,13 +150,20 @@ int dclip_loss_partial_sums(const float* lse_u, const float* lse_v, const float*
     return launch_loss_sums(a, static_cast<cudaStream_t>(stream));
 }
 
-int dclip_tensor_path_ready(void) { return 0; }
+#ifndef DCLIP_TENSOR_PATH_READY
+#define DCLIP_TENSOR_PATH_READY 0
+#endif
+int dclip_tensor_path_ready(void) { return DCLIP_TENSOR_PATH_READY; }
+
+int dclip_debug_pipeline_error(void* stream) { return tc_check_error_flag(static_cast<cudaStream_t>(stream)); }
 
 int dclip_distill_loss_launch_count(int64_t m, int64_t n, int64_t d, int path, int sharded) {
     (void)m; (void)n; (void)d;
     path = resolve_loss_path(path, DCLIP_F32);
     if (path == DCLIP_PATH_FP32) return sharded ? 11 : 7;   // prep, rowlse+combine, sums, grad, tail (x2 sides when sharded)
-    return sharded ? 11 : 7;
+    // tensor path: prep, fwd tiles, 2 lse combines, diag, sums, bwd tiles, (grad combine), 2 tails
+    if (!sharded) return 10 + (tc_nsplit(m, n, 2) > 1 ? 2 : 0);
+    return 2 + 2 * 3 + 1 + 2 * (1 + (tc_nsplit(m, n, 1) > 1 ? 1 : 0)) + 2;
 }
 
 // ---- single-GPU composite -------------------------------------------------------------------
@@ -126,6 +178,11 @@ size_t dclip_distill_loss_workspace_bytes(int64_t B, int64_t d, int path) {
     total += 8 * align_up((size_t)B * 4, 256);              // per-row vectors
     total += 4 * align_up((size_t)ns * B * 4, 256);         // partials
     total += 2 * align_up((size_t)B * d * 4, 256);          // dx_hat
+    if (path == DCLIP_PATH_TENSOR) {
+        const int tns = tc_nsplit(B, B, 2);
+        total += 4 * align_up((size_t)tns * B * 4, 256);
+        if (tns > 1) total += align_up((size_t)2 * tns * B * d * 4, 256);
+    }
     return total + 1024;
 }
 
@@ -142,21 +199,31 @@ int dclip_distill_loss_fwd_bwd(const void* s_img, const void* s_txt, const void*
     DCLIP_REQUIRE(aligned16(s_img) && aligned16(s_txt) && aligned16(workspace), "distill_loss: pointers must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     path = resolve_loss_path(path, dtype);
-    if (path != DCLIP_PATH_FP32) return fail(DCLIP_ERR_UNSUPPORTED, "distill_loss: path %d not available", path);
+    const bool tensor = path == DCLIP_PATH_TENSOR;
+    if (tensor && !tc_loss_shape_ok(d, temperature))
+        return fail(DCLIP_ERR_UNSUPPORTED, "distill_loss: tensor path needs d %% 128 == 0, 128 <= d <= 768 and temperature >= 0.025 (d=%lld tau=%g)", (long long)d, temperature);
+    if (!tensor && path != DCLIP_PATH_FP32) return fail(DCLIP_ERR_INVALID, "distill_loss: unknown path %d", path);
 
-    const int op_dtype = DCLIP_F32;
+    const int op_dtype = tensor ? DCLIP_F16 : DCLIP_F32;
+    const size_t op_size = tensor ? 2 : 4;
     Workspace ws(workspace, workspace_bytes);
-    void* u_hat = ws.take((size_t)B * d * 4);
-    void* v_hat = ws.take((size_t)B * d * 4);
+    void* u_hat = ws.take((size_t)B * d * op_size);
+    void* v_hat = ws.take((size_t)B * d * op_size);
     float* vec[8];
     for (auto& v : vec) v = static_cast<float*>(ws.take((size_t)B * 4));
     float *inv_u = vec[0], *inv_v = vec[1], *cos_img = vec[2], *cos_txt = vec[3], *lse_u = vec[4], *lse_v = vec[5], *diag = vec[6];
-    const int ns = simt_rowlse_nsplit(B, B, d);
+    const int ns = tensor ? tc_nsplit(B, B, 2) : simt_rowlse_nsplit(B, B, d);
     if (ns == 0) return fail(DCLIP_ERR_UNSUPPORTED, "FP32 loss path supports d <= 1024 (got %lld)", (long long)d);
     float* part[4];
     for (auto& p : part) p = static_cast<float*>(ws.take((size_t)ns * B * 4));
     float* du_hat = static_cast<float*>(ws.take((size_t)B * d * 4));
     float* dv_hat = static_cast<float*>(ws.take((size_t)B * d * 4));
+    float* du_part = du_hat;
+    float* dv_part = dv_hat;
+    if (tensor && ns > 1 && d_s_img) {
+        du_part = static_cast<float*>(ws.take((size_t)2 * ns * B * d * 4));   // [side][split][B][d], sides contiguous
+        dv_part = du_part + (size_t)ns * B * d;
+    }
     if (!ws.ok()) return fail(DCLIP_ERR_WORKSPACE, "distill_loss: workspace too small (%zu < %zu)", workspace_bytes, ws.used);
     if (stats) { lse_u = stats; lse_v = stats + B; }
 
@@ -166,18 +233,42 @@ int dclip_distill_loss_fwd_bwd(const void* s_img, const void* s_txt, const void*
     pa.m = B; pa.d = d;
     if (int e = launch_loss_prep(pa, 2, dtype, op_dtype, st)) return e;
 
-    LseArgs la{};
-    la.s[0] = LseSide{(const float*)u_hat, (const float*)v_hat, part[0], part[1], lse_u, diag};
-    la.s[1] = LseSide{(const float*)v_hat, (const float*)u_hat, part[2], part[3], lse_v, nullptr};
-    la.m = B; la.n = B; la.d = d; la.temperature = temperature; la.row_offset = 0; la.nsplit = ns;
-    if (int e = launch_rowlse_simt(la, 2, st)) return e;
+    const void* xs2[2] = {u_hat, v_hat};
+    const void* ys2[2] = {v_hat, u_hat};
+    if (tensor) {
+        TcArgs fa{};
+        fa.s[0] = TcSide{nullptr, nullptr, part[0]};
+        fa.s[1] = TcSide{nullptr, nullptr, part[2]};
+        fa.m = B; fa.n = B; fa.d = d; fa.inv_tau = 1.0f / temperature; fa.row_offset = 0;
+        if (int e = launch_infonce_tc(false, 2, xs2, ys2, fa, ns, st)) return e;
+        if (int e = launch_tc_lse_combine(part[0], ns, B, fa.inv_tau, lse_u, st)) return e;
+        if (int e = launch_tc_lse_combine(part[2], ns, B, fa.inv_tau, lse_v, st)) return e;
+        if (int e = launch_tc_diag(u_hat, v_hat, B, B, d, fa.inv_tau, 0, diag, st)) return e;
+    } else {
+        LseArgs la{};
+        la.s[0] = LseSide{(const float*)u_hat, (const float*)v_hat, part[0], part[1], lse_u, diag};
+        la.s[1] = LseSide{(const float*)v_hat, (const float*)u_hat, part[2], part[3], lse_v, nullptr};
+        la.m = B; la.n = B; la.d = d; la.temperature = temperature; la.row_offset = 0; la.nsplit = ns;
+        if (int e = launch_rowlse_simt(la, 2, st)) return e;
+    }
 
     SumsArgs sa{lse_u, lse_v, diag, t_img ? cos_img : nullptr, t_txt ? cos_txt : nullptr, B, nullptr, losses, w_img, w_txt, w_con};
     if (int e = launch_loss_sums(sa, st)) return e;
 
     if (d_s_img) {
         const bool need_con = w_con != 0.f;
-        if (need_con) {
+        if (need_con && tensor) {
+            TcArgs ga{};
+            ga.s[0] = TcSide{lse_u, lse_v, du_part};
+            ga.s[1] = TcSide{lse_v, lse_u, dv_part};
+            ga.m = B; ga.n = B; ga.d = d; ga.inv_tau = 1.0f / temperature; ga.row_offset = 0;
+            ga.out_scale = w_con / (2.0f * (float)B) / temperature * (1.0f / 8192.0f);
+            if (int e = launch_infonce_tc(true, 2, xs2, ys2, ga, ns, st)) return e;
+            if (ns > 1) {
+                if (int e = launch_tc_grad_combine(du_part, ns, B, d, du_hat, st)) return e;
+                if (int e = launch_tc_grad_combine(dv_part, ns, B, d, dv_hat, st)) return e;
+            }
+        } else if (need_con) {
             GradArgs ga{};
             ga.s[0] = GradSide{(const float*)u_hat, (const float*)v_hat, lse_u, lse_v, du_hat};
             ga.s[1] = GradSide{(const float*)v_hat, (const float*)u_hat, lse_v, lse_u, dv_hat};

@@ -44,6 +44,33 @@ struct SumsArgs {
     float w_img, w_txt, w_con;
 };
 
+// ---- tensor path (loss_tc.cu) ----
+struct TcSide {
+    const float* lse_x;   // [m]   (bwd)
+    const float* lse_y;   // [n]   (bwd)
+    float* out;           // fwd: partial row sums [nsplit][m];  bwd: partial dx [nsplit][m][d]
+};
+struct TcArgs {
+    TcSide s[2];
+    int64_t m, n, d;
+    float inv_tau;        // 1 / tau
+    int64_t row_offset;   // global index of local row 0 (diagonal)
+    int tiles_per_split;
+    float out_scale;      // bwd: coef / tau * 2^-13
+    int* error_flag;      // set to 1 on a pipeline timeout
+};
+
+
+bool tc_loss_shape_ok(int64_t d, float temperature);
+int tc_nsplit(int64_t m, int64_t n, int nsides);
+int launch_infonce_tc(bool bwd, int nsides, const void* const x[2], const void* const y[2], const TcArgs& args, int nsplit,
+                      cudaStream_t st);
+int launch_tc_lse_combine(const float* part, int nsplit, int64_t m, float inv_tau, float* lse, cudaStream_t st);
+int launch_tc_grad_combine(const float* part, int nsplit, int64_t m, int64_t d, float* dx, cudaStream_t st);
+int launch_tc_diag(const void* x, const void* y, int64_t m, int64_t n, int64_t d, float inv_tau, int64_t row_offset, float* diag,
+                   cudaStream_t st);
+int tc_check_error_flag(cudaStream_t st);
+
 int launch_loss_prep(const PrepArgs& a, int nsides, int dtype, int op_dtype, cudaStream_t st);
 int simt_rowlse_nsplit(int64_t m, int64_t n, int64_t d);
 int launch_rowlse_simt(LseArgs a, int nsides, cudaStream_t st);

@@ -87,6 +87,10 @@ int dclip_distill_loss_launch_count(int64_t m, int64_t n, int64_t d, int path, i
 /* 1 when the tcgen05 tensor path of the loss is compiled in and validated for use. */
 int dclip_tensor_path_ready(void);
 
+/* Test / debug hook: 1 if a tensor-path kernel hit a bounded-wait timeout since the last call
+ * (clears the flag).  Synchronises `stream`; never called on the product path. */
+int dclip_debug_pipeline_error(void* stream);
+
 /* Sharded (data-parallel) building blocks — SURVEY.md §8(e).  Rank r owns `m` rows starting at
  * global row `row_offset` of a global batch of `n` rows.  The host all-gathers the normalised
  * operands between (1) and (2) and the two lse vectors between (2) and (3); no [B, d]

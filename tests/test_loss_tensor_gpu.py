@@ -1,0 +1,82 @@
+"""tcgen05 tensor path of the distillation objective vs the oracle (1e-3 tier, north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import reference_math as om
+from oracle import synthetic
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+def _rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def _pipeline_ok(lib):
+    from dclip_b200 import _lib
+    return lib.dclip_debug_pipeline_error(_lib.stream_ptr(torch.device("cuda:0"))) == 0
+
+
+@pytest.mark.parametrize("B,d,dtype", [(128, 128, torch.float32), (64, 768, torch.bfloat16), (256, 768, torch.bfloat16),
+                                        (1024, 512, torch.float16), (200, 256, torch.bfloat16), (4096, 768, torch.bfloat16)])
+def test_tensor_path_matches_oracle(built_library, B, d, dtype):
+    from dclip_b200 import losses as L
+    dev = torch.device("cuda:0")
+    s_img, s_txt, t_img, t_txt = (t.to(dtype) for t in synthetic.loss_inputs(B, d, seed=B + d))
+    losses, d_img, d_txt = L.distill_loss_fwd_bwd(s_img.to(dev), s_txt.to(dev), t_img.to(dev), t_txt.to(dev), path="tensor")
+    torch.cuda.synchronize()
+    assert _pipeline_ok(built_library), "tensor-path pipeline timed out"
+    (tot, li, lt, lc), g_img, g_txt = om.distill_total_with_grads(s_img.float(), s_txt.float(), t_img.float(), t_txt.float(),
+                                                                   dtype=torch.float64)
+    want = torch.stack([tot, li, lt, lc])
+    got = losses.cpu().double()
+    assert torch.allclose(got, want, rtol=TOL, atol=1e-5), (got, want)
+    out_tol = TOL + (2 ** -8 if dtype == torch.bfloat16 else 2 ** -10 if dtype == torch.float16 else 0)
+    assert _rel(d_img, g_img) < out_tol, _rel(d_img, g_img)
+    assert _rel(d_txt, g_txt) < out_tol, _rel(d_txt, g_txt)
+
+
+def test_tensor_building_blocks_and_splits(built_library):
+    """Sharded building blocks on the tensor path (m < n forces column splits + partial combines)."""
+    from dclip_b200 import losses as L
+    dev = torch.device("cuda:0")
+    P, m, d = 4, 128, 256
+    B = P * m
+    s_img, s_txt, t_img, t_txt = (t.to(dev) for t in synthetic.loss_inputs(B, d, seed=21))
+    ref_losses, ref_di, ref_dt = L.distill_loss_fwd_bwd(s_img, s_txt, t_img, t_txt, path="fp32")
+    ops = L.CudaLossOps("tensor")
+    u_all = torch.empty(B, d, device=dev, dtype=torch.float16)
+    v_all = torch.empty(B, d, device=dev, dtype=torch.float16)
+    inv_u, cos_i = ops.prep(s_img, t_img, u_all)
+    inv_v, cos_t = ops.prep(s_txt, t_txt, v_all)
+    lse_u = torch.empty(B, device=dev)
+    lse_v = torch.empty(B, device=dev)
+    diag = torch.empty(B, device=dev)
+    for r in range(P):
+        sl = slice(r * m, (r + 1) * m)
+        lse_u[sl], diag[sl] = ops.rowlse(u_all[sl], v_all, 0.05, r * m, True)
+        lse_v[sl], _ = ops.rowlse(v_all[sl], u_all, 0.05, r * m, False)
+    sums = ops.partial_sums(lse_u, lse_v, diag, cos_i, cos_t)
+    l_con = sums[0] / (2 * B)
+    assert abs(float(l_con) - float(ref_losses[3])) < TOL * float(ref_losses[3]) + 1e-5
+    for r in range(P):
+        sl = slice(r * m, (r + 1) * m)
+        du = ops.grad(u_all[sl], v_all, 0.05, r * m, lse_u[sl].contiguous(), lse_v, 1.0 / (2 * B))
+        di = ops.tail(s_img[sl].contiguous(), t_img[sl].contiguous(), inv_u[sl].contiguous(), du, 1.0 / B, 1.0)
+        assert _rel(di, ref_di[sl]) < TOL
+    torch.cuda.synchronize()
+    assert _pipeline_ok(built_library)
+
+
+def test_tensor_path_rejects_unsupported(built_library):
+    from dclip_b200 import losses as L
+    dev = torch.device("cuda:0")
+    x = torch.randn(64, 192, device=dev)
+    with pytest.raises(RuntimeError, match="tensor path needs"):
+        L.distill_loss_fwd_bwd(x, x.clone(), path="tensor")
+    y = torch.randn(64, 256, device=dev)
+    with pytest.raises(RuntimeError, match="temperature"):
+        L.distill_loss_fwd_bwd(y, y.clone(), temperature=0.01, path="tensor")
