@@ -6,6 +6,8 @@ using namespace dclip;
 
 namespace {
 
+// AUTO: the exact FP32 path unless the caller asked for the tensor path.  The Python layer picks
+// TENSOR for 16-bit inputs with supported shapes (dclip_b200/losses.py::resolve_path).
 int resolve_loss_path(int path, int op_dtype_hint) {
     (void)op_dtype_hint;
     if (path == DCLIP_PATH_AUTO) return DCLIP_PATH_FP32;
@@ -151,7 +153,7 @@ int dclip_loss_partial_sums(const float* lse_u, const float* lse_v, const float*
 }
 
 #ifndef DCLIP_TENSOR_PATH_READY
-#define DCLIP_TENSOR_PATH_READY 0
+#define DCLIP_TENSOR_PATH_READY 1   // validated on B200 (tests/test_loss_tensor_gpu.py)
 #endif
 int dclip_tensor_path_ready(void) { return DCLIP_TENSOR_PATH_READY; }
 

@@ -50,4 +50,11 @@ if has ncu; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$P.csv $CMD > $OUT/ncu_run.log 2>&1
   echo "ncu exit=$?"; tail -3 $OUT/ncu_run.log
 fi
+if has ncufull; then
+  # one full capture of the dominant kernel (backward contraction), after the plain run passed
+  CMD="python bench.py --steps 1 --warmup 3 --path tensor --no-retrieval --no-cpu-baseline"
+  timeout 600 $CMD > $OUT/ncufull_plain.log 2>&1 && \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_infonce_tc -s 4 -c 2 -f -o $OUT/prof_infonce_tc $CMD > $OUT/ncufull_run.log 2>&1
+  echo "ncufull exit=$?"; tail -3 $OUT/ncufull_run.log
+fi
 echo "gpu_round done"
