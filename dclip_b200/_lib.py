@@ -37,6 +37,15 @@ SIGNATURES = {
                                   _vp]),
     "dclip_loss_grad_tail": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _f32, _f32, _vp, _vp]),
     "dclip_loss_partial_sums": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "dclip_xattn_saved_bytes": (_sz, [_i64, _i64, _i64, _i64, _i32]),
+    "dclip_xattn_bwd_scratch_bytes": (_sz, [_i64, _i64, _i64, _i64, _i32]),
+    "dclip_xattn_fwd": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "dclip_xattn_bwd": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
+                               _vp]),
+    "dclip_aggregate_fwd": (_i32, [_vp, _i64, _i64, _i64, _i32, _f32, _vp, _vp, _vp]),
+    "dclip_aggregate_bwd": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _f32, _vp, _vp]),
+    "dclip_combine_guard_fwd": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
+    "dclip_combine_guard_bwd": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "dclip_normalize_rows": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp]),
     "dclip_pair_scores": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp]),
     "dclip_rank_counts_workspace_bytes": (_sz, [_i64, _i64, _i64, _i32]),

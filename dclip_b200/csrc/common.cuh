@@ -90,11 +90,11 @@ __device__ __forceinline__ float warp_max(float v) {
 
 }  // namespace dclip
 
-// dtype dispatch: calls BODY with `T` bound to the element type
-#define DCLIP_DISPATCH_DTYPE(dt, BODY)                                                \
+// dtype dispatch: runs the statement(s) given after `dt` with `T` bound to the element type
+#define DCLIP_DISPATCH_DTYPE(dt, ...)                                                 \
     switch (dt) {                                                                     \
-        case DCLIP_F32: { using T = float; BODY; } break;                              \
-        case DCLIP_BF16: { using T = __nv_bfloat16; BODY; } break;                     \
-        case DCLIP_F16: { using T = __half; BODY; } break;                             \
+        case DCLIP_F32: { using T = float; __VA_ARGS__; } break;                       \
+        case DCLIP_BF16: { using T = __nv_bfloat16; __VA_ARGS__; } break;              \
+        case DCLIP_F16: { using T = __half; __VA_ARGS__; } break;                      \
         default: return ::dclip::fail(DCLIP_ERR_INVALID, "unknown dtype %d", (int)(dt)); \
     }

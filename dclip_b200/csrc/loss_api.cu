@@ -140,7 +140,7 @@ int dclip_loss_grad_tail(const void* x, const void* teacher, const float* inv_no
     DCLIP_REQUIRE(x && inv_norm && d_x, "loss_grad_tail: null pointer");
     TailArgs a{};
     a.s[0] = TailSide{x, teacher, inv_norm, dx_hat, d_x};
-    a.m = m; a.d = d; a.w_cos_over_B = w_cos_over_B; a.grad_scale = grad_scale;
+    a.m = m; a.d = d; a.w_cos_over_B[0] = w_cos_over_B; a.grad_scale = grad_scale;
     return launch_grad_tail(a, 1, dtype, static_cast<cudaStream_t>(stream));
 }
 
@@ -162,9 +162,9 @@ int dclip_debug_pipeline_error(void* stream) { return tc_check_error_flag(static
 int dclip_distill_loss_launch_count(int64_t m, int64_t n, int64_t d, int path, int sharded) {
     (void)m; (void)n; (void)d;
     path = resolve_loss_path(path, DCLIP_F32);
-    if (path == DCLIP_PATH_FP32) return sharded ? 11 : 7;   // prep, rowlse+combine, sums, grad, tail (x2 sides when sharded)
+    if (path == DCLIP_PATH_FP32) return sharded ? 11 : 6;   // prep, rowlse+combine, sums, grad, tail (x2 sides when sharded)
     // tensor path: prep, fwd tiles, 2 lse combines, diag, sums, bwd tiles, (grad combine), 2 tails
-    if (!sharded) return 10 + (tc_nsplit(m, n, 2) > 1 ? 2 : 0);
+    if (!sharded) return 5 + (tc_nsplit(m, n, 2) > 1 ? 2 : 0);   // prep_pair, fwd tiles, finalize, bwd tiles, tail
     return 2 + 2 * 3 + 1 + 2 * (1 + (tc_nsplit(m, n, 1) > 1 ? 1 : 0)) + 2;
 }
 
@@ -233,7 +233,12 @@ int dclip_distill_loss_fwd_bwd(const void* s_img, const void* s_txt, const void*
     pa.s[0] = PrepSide{s_img, t_img, u_hat, inv_u, cos_img};
     pa.s[1] = PrepSide{s_txt, t_txt, v_hat, inv_v, cos_txt};
     pa.m = B; pa.d = d;
-    if (int e = launch_loss_prep(pa, 2, dtype, op_dtype, st)) return e;
+    if (tensor) {
+        pa.diag = diag; pa.inv_tau = 1.0f / temperature;
+        if (int e = launch_loss_prep_pair(pa, dtype, op_dtype, st)) return e;
+    } else {
+        if (int e = launch_loss_prep(pa, 2, dtype, op_dtype, st)) return e;
+    }
 
     const void* xs2[2] = {u_hat, v_hat};
     const void* ys2[2] = {v_hat, u_hat};
@@ -243,9 +248,9 @@ int dclip_distill_loss_fwd_bwd(const void* s_img, const void* s_txt, const void*
         fa.s[1] = TcSide{nullptr, nullptr, part[2]};
         fa.m = B; fa.n = B; fa.d = d; fa.inv_tau = 1.0f / temperature; fa.row_offset = 0;
         if (int e = launch_infonce_tc(false, 2, xs2, ys2, fa, ns, st)) return e;
-        if (int e = launch_tc_lse_combine(part[0], ns, B, fa.inv_tau, lse_u, st)) return e;
-        if (int e = launch_tc_lse_combine(part[2], ns, B, fa.inv_tau, lse_v, st)) return e;
-        if (int e = launch_tc_diag(u_hat, v_hat, B, B, d, fa.inv_tau, 0, diag, st)) return e;
+        FinalizeArgs fz{part[0], part[2], ns, B, fa.inv_tau, lse_u, lse_v,
+                        SumsArgs{lse_u, lse_v, diag, t_img ? cos_img : nullptr, t_txt ? cos_txt : nullptr, B, nullptr, losses, w_img, w_txt, w_con}};
+        if (int e = launch_tc_finalize(fz, st)) return e;
     } else {
         LseArgs la{};
         la.s[0] = LseSide{(const float*)u_hat, (const float*)v_hat, part[0], part[1], lse_u, diag};
@@ -254,8 +259,10 @@ int dclip_distill_loss_fwd_bwd(const void* s_img, const void* s_txt, const void*
         if (int e = launch_rowlse_simt(la, 2, st)) return e;
     }
 
-    SumsArgs sa{lse_u, lse_v, diag, t_img ? cos_img : nullptr, t_txt ? cos_txt : nullptr, B, nullptr, losses, w_img, w_txt, w_con};
-    if (int e = launch_loss_sums(sa, st)) return e;
+    if (!tensor) {
+        SumsArgs sa{lse_u, lse_v, diag, t_img ? cos_img : nullptr, t_txt ? cos_txt : nullptr, B, nullptr, losses, w_img, w_txt, w_con};
+        if (int e = launch_loss_sums(sa, st)) return e;
+    }
 
     if (d_s_img) {
         const bool need_con = w_con != 0.f;
@@ -278,15 +285,13 @@ int dclip_distill_loss_fwd_bwd(const void* s_img, const void* s_txt, const void*
             ga.coef_over_tau = w_con / (2.0f * (float)B) / temperature;
             if (int e = launch_grad_simt(ga, 2, st)) return e;
         }
-        // the two sides may carry different cosine weights: one tail launch per side
         TailArgs ta{};
         ta.m = B; ta.d = d; ta.grad_scale = grad_scale;
         ta.s[0] = TailSide{s_img, t_img, inv_u, need_con ? du_hat : nullptr, d_s_img};
-        ta.w_cos_over_B = w_img / (float)B;
-        if (int e = launch_grad_tail(ta, 1, dtype, st)) return e;
-        ta.s[0] = TailSide{s_txt, t_txt, inv_v, need_con ? dv_hat : nullptr, d_s_txt};
-        ta.w_cos_over_B = w_txt / (float)B;
-        if (int e = launch_grad_tail(ta, 1, dtype, st)) return e;
+        ta.s[1] = TailSide{s_txt, t_txt, inv_v, need_con ? dv_hat : nullptr, d_s_txt};
+        ta.w_cos_over_B[0] = w_img / (float)B;
+        ta.w_cos_over_B[1] = w_txt / (float)B;
+        if (int e = launch_grad_tail(ta, 2, dtype, st)) return e;
     }
     return DCLIP_OK;
 }

@@ -9,7 +9,7 @@ namespace dclip {
 // rows, side 1 = text rows against all image rows.  Kernels take both sides in one launch
 // (blockIdx.z / .y selects) so the single-GPU step is 6 launches.
 struct PrepSide { const void* x; const void* t; void* xhat; float* inv_norm; float* cos; };
-struct PrepArgs { PrepSide s[2]; int64_t m, d; };
+struct PrepArgs { PrepSide s[2]; int64_t m, d; float* diag; float inv_tau; };   // diag: pair kernel only
 
 struct LseSide {
     const float* x; const float* y;   // FP32 path operands (normalised rows)
@@ -34,7 +34,7 @@ struct GradArgs {
 };
 
 struct TailSide { const void* x; const void* t; const float* inv_norm; const float* dx_hat; void* d_x; };
-struct TailArgs { TailSide s[2]; int64_t m, d; float w_cos_over_B; float grad_scale; };
+struct TailArgs { TailSide s[2]; int64_t m, d; float w_cos_over_B[2]; float grad_scale; };
 
 struct SumsArgs {
     const float* lse_u; const float* lse_v; const float* diag; const float* cos_img; const float* cos_txt;
@@ -72,6 +72,14 @@ int launch_tc_diag(const void* x, const void* y, int64_t m, int64_t n, int64_t d
 int tc_check_error_flag(cudaStream_t st);
 
 int launch_loss_prep(const PrepArgs& a, int nsides, int dtype, int op_dtype, cudaStream_t st);
+// both sides of row i in one warp + diag[i] = u_hat_i . v_hat_i / tau from the rounded operands
+int launch_loss_prep_pair(const PrepArgs& a, int dtype, int op_dtype, cudaStream_t st);
+// tensor path: lse = 1/tau + ln(sum of partial row sums) for both sides + the loss sums, one launch
+struct FinalizeArgs {
+    const float* part_u; const float* part_v; int nsplit; int64_t m; float inv_tau;
+    float* lse_u; float* lse_v; SumsArgs sums;
+};
+int launch_tc_finalize(const FinalizeArgs& a, cudaStream_t st);
 int simt_rowlse_nsplit(int64_t m, int64_t n, int64_t d);
 int launch_rowlse_simt(LseArgs a, int nsides, cudaStream_t st);
 int launch_grad_simt(const GradArgs& a, int nsides, cudaStream_t st);

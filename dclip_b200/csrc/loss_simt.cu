@@ -106,6 +106,97 @@ __global__ void __launch_bounds__(kThreads) k_loss_prep(PrepArgs a) {
     }
 }
 
+// both sides of one row per warp (single-GPU composite): also yields diag[i] = u_hat_i . v_hat_i / tau
+// computed from the operand values as rounded to OT, i.e. the S_ii the tensor tiles see.
+template <typename T, typename OT>
+__global__ void __launch_bounds__(kThreads) k_loss_prep_pair(PrepArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    if (row >= a.m) return;
+    const int64_t d = a.d;
+    float nrm[2];
+#pragma unroll
+    for (int sd = 0; sd < 2; ++sd) {
+        const PrepSide s = a.s[sd];
+        const T* x = static_cast<const T*>(s.x) + row * d;
+        const T* t = s.t ? static_cast<const T*>(s.t) + row * d : nullptr;
+        float ss = 0.f, tt = 0.f, xt = 0.f;
+        for (int64_t k = lane * 8; k < d; k += 256) {
+            float xv[8];
+            load8<T>(x + k, xv);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ss = fmaf(xv[i], xv[i], ss);
+            if (t) {
+                float tv[8];
+                load8<T>(t + k, tv);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { tt = fmaf(tv[i], tv[i], tt); xt = fmaf(xv[i], tv[i], xt); }
+            }
+        }
+        ss = warp_sum(ss);
+        const float nx = fmaxf(sqrtf(ss), kNormEps);
+        nrm[sd] = nx;
+        if (t) { tt = warp_sum(tt); xt = warp_sum(xt); }
+        if (lane == 0) {
+            s.inv_norm[row] = 1.0f / nx;
+            if (s.cos) s.cos[row] = t ? xt / (nx * fmaxf(sqrtf(tt), kNormEps)) : 0.f;
+        }
+    }
+    const T* x0 = static_cast<const T*>(a.s[0].x) + row * d;
+    const T* x1 = static_cast<const T*>(a.s[1].x) + row * d;
+    OT* o0 = static_cast<OT*>(a.s[0].xhat) + row * d;
+    OT* o1 = static_cast<OT*>(a.s[1].xhat) + row * d;
+    float dot = 0.f;
+    for (int64_t k = lane * 8; k < d; k += 256) {
+        float u[8], v[8];
+        load8<T>(x0 + k, u);
+        load8<T>(x1 + k, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            u[i] = to_f32<OT>(from_f32<OT>(u[i] / nrm[0]));
+            v[i] = to_f32<OT>(from_f32<OT>(v[i] / nrm[1]));
+            dot = fmaf(u[i], v[i], dot);
+        }
+        store8<OT>(o0 + k, u);
+        store8<OT>(o1 + k, v);
+    }
+    dot = warp_sum(dot);
+    if (lane == 0 && a.diag) a.diag[row] = dot * a.inv_tau;
+}
+
+// tensor path finalize: both lse vectors from the partial row sums + the loss sums (single CTA)
+__global__ void __launch_bounds__(1024) k_tc_finalize(FinalizeArgs f) {
+    __shared__ float red[3][1024];
+    const SumsArgs& a = f.sums;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int64_t i = threadIdx.x; i < f.m; i += 1024) {
+        float su = 0.f, sv = 0.f;
+        for (int p = 0; p < f.nsplit; ++p) { su += f.part_u[(int64_t)p * f.m + i]; sv += f.part_v[(int64_t)p * f.m + i]; }
+        const float lu = f.inv_tau + logf(su), lv = f.inv_tau + logf(sv);
+        f.lse_u[i] = lu; f.lse_v[i] = lv;
+        s0 += lu + lv - 2.0f * a.diag[i];
+        if (a.cos_img) s1 += 1.0f - a.cos_img[i];
+        if (a.cos_txt) s2 += 1.0f - a.cos_txt[i];
+    }
+    red[0][threadIdx.x] = s0; red[1][threadIdx.x] = s1; red[2][threadIdx.x] = s2;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            red[0][threadIdx.x] += red[0][threadIdx.x + o];
+            red[1][threadIdx.x] += red[1][threadIdx.x + o];
+            red[2][threadIdx.x] += red[2][threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const float l_con = red[0][0] / (2.0f * (float)f.m);
+        const float l_img = a.cos_img ? red[1][0] / (float)f.m : 0.f;
+        const float l_txt = a.cos_txt ? red[2][0] / (float)f.m : 0.f;
+        a.losses[0] = a.w_img * l_img + a.w_txt * l_txt + a.w_con * l_con;
+        a.losses[1] = l_img; a.losses[2] = l_txt; a.losses[3] = l_con;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // score tile: 2 x CPT micro-tile per thread from smem-resident rows, k ascending (fma chain)
 // ---------------------------------------------------------------------------------------------
@@ -336,7 +427,7 @@ __global__ void __launch_bounds__(kThreads) k_loss_grad_tail(TailArgs a) {
             for (int i = 0; i < 8; ++i) tt = fmaf(tv[i], tv[i], tt);
         }
         tt = warp_sum(tt);
-        t_scale = -a.w_cos_over_B / fmaxf(sqrtf(tt), kNormEps);
+        t_scale = -a.w_cos_over_B[blockIdx.y] / fmaxf(sqrtf(tt), kNormEps);
     }
     // pass 1: dot = x_hat . g
     float dot = 0.f;
@@ -432,6 +523,26 @@ int launch_loss_prep(const PrepArgs& a, int nsides, int dtype, int op_dtype, cud
         return fail(DCLIP_ERR_INVALID, "loss_prep: bad op_dtype %d", op_dtype);
     }
     DCLIP_LAUNCH_OK("k_loss_prep");
+    return DCLIP_OK;
+}
+
+int launch_loss_prep_pair(const PrepArgs& a, int dtype, int op_dtype, cudaStream_t st) {
+    if (a.m == 0) return DCLIP_OK;
+    dim3 grid((unsigned)ceil_div(a.m, kThreads / 32));
+    if (op_dtype == DCLIP_F32) {
+        DCLIP_DISPATCH_DTYPE(dtype, (k_loss_prep_pair<T, float><<<grid, kThreads, 0, st>>>(a)));
+    } else if (op_dtype == DCLIP_F16) {
+        DCLIP_DISPATCH_DTYPE(dtype, (k_loss_prep_pair<T, __half><<<grid, kThreads, 0, st>>>(a)));
+    } else {
+        return fail(DCLIP_ERR_INVALID, "loss_prep_pair: bad op_dtype %d", op_dtype);
+    }
+    DCLIP_LAUNCH_OK("k_loss_prep_pair");
+    return DCLIP_OK;
+}
+
+int launch_tc_finalize(const FinalizeArgs& a, cudaStream_t st) {
+    k_tc_finalize<<<1, 1024, 0, st>>>(a);
+    DCLIP_LAUNCH_OK("k_tc_finalize");
     return DCLIP_OK;
 }
 

@@ -49,16 +49,23 @@ struct Pipe {
     }
 };
 
-template <bool kBwd>
+// kC = thread-block cluster size along the row-block axis.  The kC CTAs of a cluster own different
+// row blocks but walk the same Y tiles, so each loads 1/kC of every ring slot and multicasts it to
+// all of them: L2 -> SM traffic per CTA drops by kC (the kernel is otherwise bound by it).
+template <bool kBwd, int kC>
 __global__ void __launch_bounds__(kTcThreads, 1)
 k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CUtensorMap tmy0,
-             const __grid_constant__ CUtensorMap tmx1, const __grid_constant__ CUtensorMap tmy1, const TcArgs a) {
+             const __grid_constant__ CUtensorMap tmx1, const __grid_constant__ CUtensorMap tmy1,
+             const __grid_constant__ CUtensorMap tmh0, const __grid_constant__ CUtensorMap tmh1, const TcArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int side = blockIdx.z;
     const CUtensorMap* tmx = side ? &tmx1 : &tmx0;
     const CUtensorMap* tmy = side ? &tmy1 : &tmy0;
+    const CUtensorMap* tmh = side ? &tmh1 : &tmh0;      // same matrix as tmy, 64-row boxes (kC == 4)
     const TcSide S = a.s[side];
+    const uint32_t crank = kC > 1 ? cluster_ctarank() : 0;
+    constexpr uint16_t kMask = (uint16_t)((1u << kC) - 1);
     const int d = (int)a.d;
     const int nkb = d / 64;            // 64-column boxes along K
     const int NS = d / 128;            // ring slots per phase (= accumulator d-blocks)
@@ -86,7 +93,7 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
     const int T = (int)(t_end - t_begin);
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kSlots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < kSlots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kC); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 128);
             mbar_init(&g_full[i], 128); mbar_init(&g_empty[i], 1);
@@ -97,6 +104,7 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
     if (warp == 1) tmem_alloc(tmem_ptr, 512);
     fence_before_thread_sync();
     __syncthreads();
+    if (kC > 1) cluster_sync_all();      // peers' barriers are initialised before anyone multicasts
     fence_after_thread_sync();
     const uint32_t tmem = *tmem_ptr;
     bool ok = true;
@@ -116,8 +124,16 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
                         ok = mbar_wait(&empty[p.stage], p.phase ^ 1, kSpin);
                         uint8_t* dst = ring + (size_t)p.stage * kSlotBytes;
                         mbar_arrive_expect_tx(&full[p.stage], kSlotBytes);
-                        tma_load_2d(dst, tmy, &full[p.stage], (2 * s) * 64, j0);
-                        tma_load_2d(dst + kBoxBytes, tmy, &full[p.stage], (2 * s + 1) * 64, j0);
+                        if (kC == 1) {
+                            tma_load_2d(dst, tmy, &full[p.stage], (2 * s) * 64, j0);
+                            tma_load_2d(dst + kBoxBytes, tmy, &full[p.stage], (2 * s + 1) * 64, j0);
+                        } else if (kC == 2) {        // CTA r loads box r of the slot for both CTAs
+                            tma_load_2d_mcast(dst + crank * kBoxBytes, tmy, &full[p.stage], (2 * s + (int)crank) * 64, j0, kMask);
+                        } else {                     // kC == 4: CTA r loads rows [64 (r&1), +64) of box r>>1
+                            const int box = (int)(crank >> 1), half = (int)(crank & 1);
+                            tma_load_2d_mcast(dst + box * kBoxBytes + half * (kBoxBytes / 2), tmh, &full[p.stage], (2 * s + box) * 64,
+                                              j0 + half * 64, kMask);
+                        }
                         p.advance();
                     }
                 };
@@ -155,7 +171,7 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
                                 const uint64_t db = smem_desc(hiK, xs_addr + (2 * s + h) * kXBoxBytes + ks * 32);
                                 umma_f16(dcol, da, db, idesc1, (s | h | ks) != 0);
                             }
-                        umma_commit(&empty[p.stage]);
+                        if (kC == 1) umma_commit(&empty[p.stage]); else umma_commit_mcast(&empty[p.stage], kMask);
                         p.advance();
                     }
                     umma_commit(&s_full[b]);
@@ -175,7 +191,7 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
                             const uint64_t db = smem_desc(hiB2, gaddr + ks * 2048);
                             umma_f16(tmem + s * NI, da, db, idesc2, (t | ks) != 0);
                         }
-                        umma_commit(&empty[p.stage]);
+                        if (kC == 1) umma_commit(&empty[p.stage]); else umma_commit_mcast(&empty[p.stage], kMask);
                         p.advance();
                     }
                     umma_commit(&g_empty[b]);
@@ -309,6 +325,7 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
     if (!ok && lane == 0 && a.error_flag) atomicExch(a.error_flag, 1);
     fence_before_thread_sync();
     __syncthreads();
+    if (kC > 1) cluster_sync_all();      // nobody leaves while a peer may still multicast into / signal this CTA
     if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
@@ -361,8 +378,19 @@ bool tc_loss_shape_ok(int64_t d, float temperature) {
     return d % 128 == 0 && d >= 128 && d <= 768 && temperature >= 0.025f;
 }
 
+static int tc_cluster_size() {   // DCLIP_TC_CLUSTER = 1 | 2 | 4 (default 2)
+    static int c = 0;
+    if (!c) {
+        const char* e = getenv("DCLIP_TC_CLUSTER");
+        c = e ? atoi(e) : 2;
+        if (c != 1 && c != 2 && c != 4) c = 2;
+    }
+    return c;
+}
+
 int tc_nsplit(int64_t m, int64_t n, int nsides) {
-    const int64_t row_ctas = ceil_div(m, NI) * nsides;
+    const int C = tc_cluster_size();
+    const int64_t row_ctas = ceil_div(ceil_div(m, NI), C) * C * nsides;
     const int64_t ntiles = ceil_div(n, TJ);
     int64_t want = sm_count() / (row_ctas > 0 ? row_ctas : 1);
     if (want < 1) want = 1;
@@ -391,25 +419,39 @@ int launch_infonce_tc(bool bwd, int nsides, const void* const x[2], const void* 
                       cudaStream_t st) {
     if (!device_is_sm100()) return fail(DCLIP_ERR_ARCH, "tensor path needs an sm_100 device");
     TcArgs a = args_in;
-    CUtensorMap tmx[2], tmy[2];
+    CUtensorMap tmx[2], tmy[2], tmh[2];
     for (int s = 0; s < 2; ++s) {
         const int src = s < nsides ? s : 0;
         if (!make_tmap_2d_sw128(&tmx[s], x[src], (uint64_t)a.m, (uint64_t)a.d, NI, 0) ||
-            !make_tmap_2d_sw128(&tmy[s], y[src], (uint64_t)a.n, (uint64_t)a.d, TJ, 0))
+            !make_tmap_2d_sw128(&tmy[s], y[src], (uint64_t)a.n, (uint64_t)a.d, TJ, 0) ||
+            !make_tmap_2d_sw128(&tmh[s], y[src], (uint64_t)a.n, (uint64_t)a.d, TJ / 2, 0))
             return fail(DCLIP_ERR_CUDA, "cuTensorMapEncodeTiled failed (m=%lld n=%lld d=%lld)", (long long)a.m, (long long)a.n, (long long)a.d);
     }
     const int64_t ntiles = ceil_div(a.n, TJ);
     a.tiles_per_split = (int)ceil_div(ntiles, nsplit);
     a.error_flag = tc_error_flag();
     const size_t smem = tc_smem_bytes(a.d, bwd);
-    dim3 grid((unsigned)ceil_div(a.m, NI), (unsigned)nsplit, (unsigned)nsides);
+    const int C = tc_cluster_size();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(ceil_div(ceil_div(a.m, NI), C) * C), (unsigned)nsplit, (unsigned)nsides);
+    cfg.blockDim = dim3(kTcThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+#define DCLIP_TC_LAUNCH(BWD, CL)                                                                                              \
+    do {                                                                                                                      \
+        DCLIP_CUDA_OK(cudaFuncSetAttribute(k_infonce_tc<BWD, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+        DCLIP_CUDA_OK(cudaLaunchKernelEx(&cfg, k_infonce_tc<BWD, CL>, tmx[0], tmy[0], tmx[1], tmy[1], tmh[0], tmh[1], a));    \
+    } while (0)
     if (bwd) {
-        DCLIP_CUDA_OK(cudaFuncSetAttribute(k_infonce_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_infonce_tc<true><<<grid, kTcThreads, smem, st>>>(tmx[0], tmy[0], tmx[1], tmy[1], a);
+        if (C == 1) DCLIP_TC_LAUNCH(true, 1); else if (C == 2) DCLIP_TC_LAUNCH(true, 2); else DCLIP_TC_LAUNCH(true, 4);
     } else {
-        DCLIP_CUDA_OK(cudaFuncSetAttribute(k_infonce_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_infonce_tc<false><<<grid, kTcThreads, smem, st>>>(tmx[0], tmy[0], tmx[1], tmy[1], a);
+        if (C == 1) DCLIP_TC_LAUNCH(false, 1); else if (C == 2) DCLIP_TC_LAUNCH(false, 2); else DCLIP_TC_LAUNCH(false, 4);
     }
+#undef DCLIP_TC_LAUNCH
     DCLIP_LAUNCH_OK("k_infonce_tc");
     return DCLIP_OK;
 }

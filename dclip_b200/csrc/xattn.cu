@@ -1,0 +1,779 @@
+// Meta-teacher bidirectional cross-attention + aggregation — forward and backward.
+//
+// Replaces (paths relative to the reference tree):
+//   CrossModalAttention.forward              training/patch_text_aggregation.py:21-46
+//     = 2 x nn.MultiheadAttention (packed in-proj, no masks, need_weights path) + residual + LayerNorm
+//   PatchTextAggregation.aggregation         training/patch_text_aggregation.py:243-265
+//   combine + NaN/Inf guard                  training/patch_text_aggregation.py:640-656
+//   and the autograd backward the teacher step runs through them
+//   (training/train_contrastive_teacher.py:347-362).
+//
+// This file is the fp32 CUDA-core implementation (exact tier).  All intermediates are fp32 in a
+// caller-provided `saved` buffer that the backward re-reads (Q, K|V, attention output, pre-LN sums,
+// LN statistics); attention probabilities are never stored — the backward recomputes them per
+// (batch, head) in shared memory.  16-bit inputs/parameters are widened once on entry.
+//
+// Row layout: text rows = b*T + t, image rows = b*R + r (batch-first, as the callers hold them; the
+// reference's transpose to [L, B, d] only permutes rows of the same per-(b, head) problems).
+#include "common.cuh"
+
+namespace dclip {
+
+// ---------------------------------------------------------------------------------------------
+// grouped fp32 GEMM:  C[m,n] (+)= alpha * sum_k A'(m,k) B'(k,n) + bias[n] + residual[m,n]
+// ---------------------------------------------------------------------------------------------
+struct GemmProblem {
+    const float* A; const float* B; float* C; const float* bias; const float* residual;
+    int M, N, K;
+    int lda, ldb, ldc, ldr;
+    int transA, transB;      // A'(m,k) = transA ? A[k*lda+m] : A[m*lda+k];  B'(k,n) = transB ? B[n*ldb+k] : B[k*ldb+n]
+    float alpha;
+    int accumulate;
+};
+struct GemmGroup { GemmProblem p[8]; int count; };
+
+constexpr int GT = 64, GK = 16;
+
+__global__ void __launch_bounds__(256) k_gemm_group(const __grid_constant__ GemmGroup g) {
+    const GemmProblem& P = g.p[blockIdx.z];
+    const int m0 = blockIdx.y * GT, n0 = blockIdx.x * GT;
+    if (m0 >= P.M || n0 >= P.N) return;
+    __shared__ __align__(16) float As[GK][GT + 4];
+    __shared__ __align__(16) float Bs[GK][GT + 4];
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < P.K; k0 += GK) {
+        __syncthreads();
+        // 64x16 elements per operand, 4 per thread; index so that the contiguous dim is the fast one
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int idx = tid + e * 256;
+            int m, k;
+            if (P.transA) { m = idx & 63; k = idx >> 6; } else { k = idx & 15; m = idx >> 4; }
+            float v = 0.f;
+            if (m0 + m < P.M && k0 + k < P.K)
+                v = P.transA ? P.A[(size_t)(k0 + k) * P.lda + m0 + m] : P.A[(size_t)(m0 + m) * P.lda + k0 + k];
+            As[k][m] = v;
+            int n, kb;
+            if (P.transB) { kb = idx & 15; n = idx >> 4; } else { n = idx & 63; kb = idx >> 6; }
+            float w = 0.f;
+            if (n0 + n < P.N && k0 + kb < P.K)
+                w = P.transB ? P.B[(size_t)(n0 + n) * P.ldb + k0 + kb] : P.B[(size_t)(k0 + kb) * P.ldb + n0 + n];
+            Bs[kb][n] = w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < GK; ++k) {
+            const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+            const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            const float ar[4] = {av.x, av.y, av.z, av.w}, br[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= P.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= P.N) continue;
+            float v = P.alpha * acc[i][j];
+            if (P.bias) v += P.bias[n];
+            if (P.residual) v += P.residual[(size_t)m * P.ldr + n];
+            float* c = P.C + (size_t)m * P.ldc + n;
+            *c = P.accumulate ? *c + v : v;
+        }
+    }
+}
+
+static int launch_gemm_group(const GemmGroup& g, cudaStream_t st) {
+    int maxM = 0, maxN = 0;
+    for (int i = 0; i < g.count; ++i) { maxM = max(maxM, g.p[i].M); maxN = max(maxN, g.p[i].N); }
+    if (maxM == 0 || maxN == 0) return DCLIP_OK;
+    dim3 grid((maxN + GT - 1) / GT, (maxM + GT - 1) / GT, g.count);
+    k_gemm_group<<<grid, 256, 0, st>>>(g);
+    DCLIP_LAUNCH_OK("k_gemm_group");
+    return DCLIP_OK;
+}
+
+static GemmProblem gemm(const float* A, int lda, bool tA, const float* B, int ldb, bool tB, float* C, int ldc, int M, int N, int K,
+                        const float* bias = nullptr, const float* residual = nullptr, int ldr = 0, bool accumulate = false) {
+    GemmProblem p{};
+    p.A = A; p.B = B; p.C = C; p.bias = bias; p.residual = residual;
+    p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldb = ldb; p.ldc = ldc; p.ldr = ldr;
+    p.transA = tA; p.transB = tB; p.alpha = 1.f; p.accumulate = accumulate;
+    return p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// casts and column sums
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_to_f32(const T* __restrict__ in, float* __restrict__ out, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = to_f32<T>(in[i]);
+}
+template <typename T>
+__global__ void k_from_f32(const float* __restrict__ in, T* __restrict__ out, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = from_f32<T>(in[i]);
+}
+
+// out[c] = sum_rows M[row, c]   (and optionally out2[c] = sum_rows M[row,c] * W[row,c]); fixed order
+__global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ Mx, const float* __restrict__ W, int rows, int cols, int ld,
+                                                int ldw, float* __restrict__ out, float* __restrict__ out2) {
+    __shared__ float r1[8][33], r2[8][33];
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31), g = threadIdx.x >> 5;
+    float s1 = 0.f, s2 = 0.f;
+    if (c < cols)
+        for (int r = g; r < rows; r += 8) {
+            const float v = Mx[(size_t)r * ld + c];
+            s1 += v;
+            if (W) s2 += v * W[(size_t)r * ldw + c];
+        }
+    r1[g][threadIdx.x & 31] = s1; r2[g][threadIdx.x & 31] = s2;
+    __syncthreads();
+    if (g == 0 && c < cols) {
+        float a = 0.f, b = 0.f;
+        for (int i = 0; i < 8; ++i) { a += r1[i][threadIdx.x]; b += r2[i][threadIdx.x]; }
+        if (out) out[c] = a;
+        if (out2) out2[c] = b;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// attention core, forward: one CTA per (batch, head, direction)
+//   O[q, :] = softmax_j(scale * Q[q] . K[j]) V[j]
+// ---------------------------------------------------------------------------------------------
+struct AttnDir {
+    const float* Q;  int ldq;     // [B*Lq, d] (head h at columns h*hd)
+    const float* KV; int ldkv;    // [B*Lk, 2d]: K at column h*hd, V at column d + h*hd
+    float* O;                     // [B*Lq, d]
+    int Lq, Lk;
+    // backward only
+    const float* dO; float* dQ; float* dKV;
+};
+struct AttnArgs { AttnDir dir[2]; int B, heads, hd, d; float scale; };
+
+__global__ void __launch_bounds__(128) k_attn_fwd(const __grid_constant__ AttnArgs a) {
+    extern __shared__ float sm[];
+    const AttnDir& D = a.dir[blockIdx.y];
+    const int b = blockIdx.x / a.heads, h = blockIdx.x % a.heads, hd = a.hd, ld = hd + 1;
+    float* Ks = sm;                         // [Lk][ld]
+    float* Vs = Ks + D.Lk * ld;             // [Lk][ld]
+    float* qs = Vs + D.Lk * ld;             // [4][hd]
+    float* ps = qs + 4 * hd;                // [4][Lk]
+    for (int idx = threadIdx.x; idx < D.Lk * hd; idx += 128) {
+        const int j = idx / hd, e = idx - j * hd;
+        const float* row = D.KV + (size_t)(b * D.Lk + j) * D.ldkv + h * hd + e;
+        Ks[j * ld + e] = row[0];
+        Vs[j * ld + e] = row[a.d];
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* q = qs + warp * hd;
+    float* p = ps + warp * D.Lk;
+    for (int qi = warp; qi < D.Lq; qi += 4) {
+        const float* qrow = D.Q + (size_t)(b * D.Lq + qi) * D.ldq + h * hd;
+        for (int e = lane; e < hd; e += 32) q[e] = qrow[e];
+        __syncwarp();
+        float mx = -INFINITY;
+        for (int j = lane; j < D.Lk; j += 32) {
+            float s = 0.f;
+            for (int e = 0; e < hd; ++e) s = fmaf(q[e], Ks[j * ld + e], s);
+            s *= a.scale;
+            p[j] = s;
+            mx = fmaxf(mx, s);
+        }
+        mx = warp_max(mx);
+        float sum = 0.f;
+        for (int j = lane; j < D.Lk; j += 32) { const float ev = expf(p[j] - mx); p[j] = ev; sum += ev; }
+        sum = warp_sum(sum);
+        const float inv = 1.0f / sum;
+        __syncwarp();
+        float* orow = D.O + (size_t)(b * D.Lq + qi) * a.d + h * hd;
+        for (int e = lane; e < hd; e += 32) {
+            float o = 0.f;
+            for (int j = 0; j < D.Lk; ++j) o = fmaf(p[j], Vs[j * ld + e], o);
+            orow[e] = o * inv;
+        }
+        __syncwarp();
+    }
+}
+
+// backward: recompute P, then dV = P^T dO, dS = P o (dP - rowsum(dP o P)), dQ = scale dS K, dK = scale dS^T Q
+__global__ void __launch_bounds__(128) k_attn_bwd(const __grid_constant__ AttnArgs a) {
+    extern __shared__ float sm[];
+    const AttnDir& D = a.dir[blockIdx.y];
+    const int b = blockIdx.x / a.heads, h = blockIdx.x % a.heads, hd = a.hd, ld = hd + 1;
+    const int Lq = D.Lq, Lk = D.Lk, lp = Lk + 1;
+    float* Qs = sm;                     // [Lq][ld]
+    float* dOs = Qs + Lq * ld;          // [Lq][ld]
+    float* Ks = dOs + Lq * ld;          // [Lk][ld]
+    float* Vs = Ks + Lk * ld;           // [Lk][ld]
+    float* Ps = Vs + Lk * ld;           // [Lq][lp]
+    float* dSs = Ps + Lq * lp;          // [Lq][lp]
+    for (int idx = threadIdx.x; idx < Lq * hd; idx += 128) {
+        const int qi = idx / hd, e = idx - qi * hd;
+        Qs[qi * ld + e] = D.Q[(size_t)(b * Lq + qi) * D.ldq + h * hd + e];
+        dOs[qi * ld + e] = D.dO[(size_t)(b * Lq + qi) * a.d + h * hd + e];
+    }
+    for (int idx = threadIdx.x; idx < Lk * hd; idx += 128) {
+        const int j = idx / hd, e = idx - j * hd;
+        const float* row = D.KV + (size_t)(b * Lk + j) * D.ldkv + h * hd + e;
+        Ks[j * ld + e] = row[0];
+        Vs[j * ld + e] = row[a.d];
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int qi = warp; qi < Lq; qi += 4) {
+        float mx = -INFINITY;
+        for (int j = lane; j < Lk; j += 32) {
+            float s = 0.f, dp = 0.f;
+            for (int e = 0; e < hd; ++e) {
+                s = fmaf(Qs[qi * ld + e], Ks[j * ld + e], s);
+                dp = fmaf(dOs[qi * ld + e], Vs[j * ld + e], dp);
+            }
+            s *= a.scale;
+            Ps[qi * lp + j] = s;
+            dSs[qi * lp + j] = dp;
+            mx = fmaxf(mx, s);
+        }
+        mx = warp_max(mx);
+        float sum = 0.f;
+        for (int j = lane; j < Lk; j += 32) { const float ev = expf(Ps[qi * lp + j] - mx); Ps[qi * lp + j] = ev; sum += ev; }
+        sum = warp_sum(sum);
+        const float inv = 1.0f / sum;
+        float dot = 0.f;
+        for (int j = lane; j < Lk; j += 32) { const float pv = Ps[qi * lp + j] * inv; Ps[qi * lp + j] = pv; dot = fmaf(pv, dSs[qi * lp + j], dot); }
+        dot = warp_sum(dot);
+        for (int j = lane; j < Lk; j += 32) dSs[qi * lp + j] = Ps[qi * lp + j] * (dSs[qi * lp + j] - dot) * a.scale;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < Lq * hd; idx += 128) {          // dQ
+        const int qi = idx / hd, e = idx - qi * hd;
+        float v = 0.f;
+        for (int j = 0; j < Lk; ++j) v = fmaf(dSs[qi * lp + j], Ks[j * ld + e], v);
+        D.dQ[(size_t)(b * Lq + qi) * a.d + h * hd + e] = v;
+    }
+    for (int idx = threadIdx.x; idx < Lk * hd; idx += 128) {          // dK, dV
+        const int j = idx / hd, e = idx - j * hd;
+        float dk = 0.f, dv = 0.f;
+        for (int qi = 0; qi < Lq; ++qi) {
+            dk = fmaf(dSs[qi * lp + j], Qs[qi * ld + e], dk);
+            dv = fmaf(Ps[qi * lp + j], dOs[qi * ld + e], dv);
+        }
+        float* row = D.dKV + (size_t)(b * Lk + j) * (2 * a.d) + h * hd + e;
+        row[0] = dk;
+        row[a.d] = dv;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm (eps 1e-5, biased variance, affine): one warp per row, d <= 4096
+// ---------------------------------------------------------------------------------------------
+constexpr float kLnEps = 1e-5f;
+__global__ void __launch_bounds__(256) k_ln_fwd(const float* __restrict__ z, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                int rows, int d, float* __restrict__ out, float* __restrict__ stats) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float* zr = z + (size_t)row * d;
+    float s = 0.f;
+    for (int c = lane; c < d; c += 32) s += zr[c];
+    const float mu = warp_sum(s) / d;
+    float v = 0.f;
+    for (int c = lane; c < d; c += 32) { const float t = zr[c] - mu; v = fmaf(t, t, v); }
+    const float rstd = rsqrtf(warp_sum(v) / d + kLnEps);
+    for (int c = lane; c < d; c += 32) out[(size_t)row * d + c] = (zr[c] - mu) * rstd * gamma[c] + beta[c];
+    if (lane == 0) { stats[2 * row] = mu; stats[2 * row + 1] = rstd; }
+}
+// dz = rstd (dy g - mean(dy g) - zhat mean(dy g zhat));  also writes zhat for the dgamma column sums
+__global__ void __launch_bounds__(256) k_ln_bwd(const float* __restrict__ dy, const float* __restrict__ z, const float* __restrict__ gamma,
+                                                const float* __restrict__ stats, int rows, int d, float* __restrict__ dz,
+                                                float* __restrict__ zhat) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float mu = stats[2 * row], rstd = stats[2 * row + 1];
+    const float* zr = z + (size_t)row * d;
+    const float* dyr = dy + (size_t)row * d;
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = lane; c < d; c += 32) {
+        const float zh = (zr[c] - mu) * rstd, g = dyr[c] * gamma[c];
+        s1 += g;
+        s2 = fmaf(g, zh, s2);
+    }
+    s1 = warp_sum(s1) / d;
+    s2 = warp_sum(s2) / d;
+    for (int c = lane; c < d; c += 32) {
+        const float zh = (zr[c] - mu) * rstd, g = dyr[c] * gamma[c];
+        dz[(size_t)row * d + c] = rstd * (g - s1 - zh * s2);
+        zhat[(size_t)row * d + c] = zh;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// aggregation (patch_text_aggregation.py:243-265): one CTA per batch element
+// ---------------------------------------------------------------------------------------------
+constexpr float kCosEps = 1e-8f;
+__device__ __forceinline__ float block_sum(float v, float* red) {   // 256 threads
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    return t;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_aggregate_fwd(const T* __restrict__ x, int L, int d, float temperature, T* __restrict__ out,
+                                                       float* __restrict__ w_saved) {
+    extern __shared__ float sm[];
+    float* mean = sm;            // [d]
+    float* cs = mean + d;        // [L]
+    float* red = cs + L;         // [8]
+    const int b = blockIdx.x;
+    const T* xb = x + (size_t)b * L * d;
+    float part = 0.f;
+    for (int c = threadIdx.x; c < d; c += 256) {
+        float s = 0.f;
+        for (int l = 0; l < L; ++l) s += to_f32<T>(xb[(size_t)l * d + c]);
+        s /= L;
+        mean[c] = s;
+        part = fmaf(s, s, part);
+    }
+    const float nm = fmaxf(sqrtf(block_sum(part, red)), kCosEps);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int l = warp; l < L; l += 8) {
+        float dot = 0.f, nx = 0.f;
+        for (int c = lane; c < d; c += 32) { const float v = to_f32<T>(xb[(size_t)l * d + c]); dot = fmaf(v, mean[c], dot); nx = fmaf(v, v, nx); }
+        dot = warp_sum(dot); nx = warp_sum(nx);
+        if (lane == 0) cs[l] = dot / (fmaxf(sqrtf(nx), kCosEps) * nm) / temperature;
+    }
+    __syncthreads();
+    float mx = -INFINITY;
+    for (int l = 0; l < L; ++l) mx = fmaxf(mx, cs[l]);
+    float den = 0.f;
+    for (int l = 0; l < L; ++l) den += expf(cs[l] - mx);
+    __syncthreads();
+    for (int l = threadIdx.x; l < L; l += 256) {
+        const float w = expf(cs[l] - mx) / den;
+        cs[l] = w;
+        if (w_saved) w_saved[(size_t)b * L + l] = w;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < d; c += 256) {
+        float s = 0.f;
+        for (int l = 0; l < L; ++l) s = fmaf(cs[l], to_f32<T>(xb[(size_t)l * d + c]), s);
+        out[(size_t)b * d + c] = from_f32<T>(s);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_aggregate_bwd(const T* __restrict__ x, const float* __restrict__ w_saved, const T* __restrict__ dout,
+                                                       int L, int d, float temperature, T* __restrict__ dx) {
+    extern __shared__ float sm[];
+    float* mean = sm;            // [d]
+    float* dmean = mean + d;     // [d]
+    float* cosv = dmean + d;     // [L]  cosine similarities
+    float* nxs = cosv + L;       // [L]  clamped row norms
+    float* dcs = nxs + L;        // [L]  d loss / d cos
+    float* red = dcs + L;        // [8]
+    const int b = blockIdx.x;
+    const T* xb = x + (size_t)b * L * d;
+    const T* dg = dout + (size_t)b * d;
+    const float* w = w_saved + (size_t)b * L;
+    float part = 0.f;
+    for (int c = threadIdx.x; c < d; c += 256) {
+        float s = 0.f;
+        for (int l = 0; l < L; ++l) s += to_f32<T>(xb[(size_t)l * d + c]);
+        s /= L;
+        mean[c] = s;
+        part = fmaf(s, s, part);
+    }
+    const float nm_raw = sqrtf(block_sum(part, red));
+    const float nm = fmaxf(nm_raw, kCosEps);
+    const bool m_clamped = nm_raw < kCosEps;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int l = warp; l < L; l += 8) {
+        float dot = 0.f, nx = 0.f, dw = 0.f;
+        for (int c = lane; c < d; c += 32) {
+            const float v = to_f32<T>(xb[(size_t)l * d + c]);
+            dot = fmaf(v, mean[c], dot); nx = fmaf(v, v, nx); dw = fmaf(v, to_f32<T>(dg[c]), dw);
+        }
+        dot = warp_sum(dot); nx = warp_sum(nx); dw = warp_sum(dw);
+        if (lane == 0) {
+            const float nxr = sqrtf(nx);
+            nxs[l] = nxr < kCosEps ? -kCosEps : nxr;     // negative marks "clamped"
+            cosv[l] = dot / (fmaxf(nxr, kCosEps) * nm);
+            dcs[l] = dw;                                  // dw_l for now
+        }
+    }
+    __syncthreads();
+    float sdot = 0.f;
+    for (int l = 0; l < L; ++l) sdot = fmaf(w[l], dcs[l], sdot);
+    __syncthreads();
+    for (int l = threadIdx.x; l < L; l += 256) dcs[l] = w[l] / temperature * (dcs[l] - sdot);
+    __syncthreads();
+    // dmean[c] = sum_l dc_l (x_l[c] / (nx_l nm) - cos_l mean[c] / nm^2)
+    for (int c = threadIdx.x; c < d; c += 256) {
+        float s = 0.f;
+        for (int l = 0; l < L; ++l) {
+            const float nx = fabsf(nxs[l]);
+            float t = to_f32<T>(xb[(size_t)l * d + c]) / (nx * nm);
+            if (!m_clamped) t -= cosv[l] * mean[c] / (nm * nm);
+            s = fmaf(dcs[l], t, s);
+        }
+        dmean[c] = s / L;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < L * d; idx += 256) {
+        const int l = idx / d, c = idx - l * d;
+        const float xv = to_f32<T>(xb[idx]);
+        const float nx = fabsf(nxs[l]);
+        float t = mean[c] / (nx * nm);
+        if (nxs[l] > 0.f) t -= cosv[l] * xv / (nx * nx);
+        dx[(size_t)b * L * d + idx] = from_f32<T>(w[l] * to_f32<T>(dg[c]) + dcs[l] * t + dmean[c]);
+    }
+}
+
+// combine + whole-tensor NaN/Inf guard (patch_text_aggregation.py:647-651)
+template <typename T>
+__global__ void k_combine_fwd(const T* __restrict__ a, const T* __restrict__ b, int64_t n, T* __restrict__ out, int* __restrict__ flag) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = 0.5f * to_f32<T>(a[i]) + 0.5f * to_f32<T>(b[i]);
+    out[i] = from_f32<T>(v);
+    if (!isfinite(v)) atomicOr(flag, 1);
+}
+template <typename T>
+__global__ void k_guard_zero(T* __restrict__ out, int64_t n, const int* __restrict__ flag) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && *flag) out[i] = from_f32<T>(0.f);
+}
+template <typename T>
+__global__ void k_combine_bwd(const T* __restrict__ dout, int64_t n, const int* __restrict__ flag, T* __restrict__ da, T* __restrict__ db) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = *flag ? 0.f : 0.5f * to_f32<T>(dout[i]);
+    da[i] = from_f32<T>(v);
+    db[i] = from_f32<T>(v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// saved-buffer layout (floats)
+// ---------------------------------------------------------------------------------------------
+struct XLayout {
+    size_t Xt, Xi, Qt, KVi, Qi, KVt, Ot, Oi, Zt, Zi, St, Si, W, total;
+    // W: fp32 copies of the 12 parameter tensors (only when dtype != f32)
+};
+static const int kParamCount = 12;
+// order of the params[] / grads[] arrays == state_dict order of the reference module
+//  0 t2i.in_proj_weight [3d,d]  1 t2i.in_proj_bias [3d]  2 t2i.out_proj.weight [d,d]  3 t2i.out_proj.bias [d]
+//  4 i2t.in_proj_weight         5 i2t.in_proj_bias       6 i2t.out_proj.weight        7 i2t.out_proj.bias
+//  8 norm_text.weight [d]  9 norm_text.bias  10 norm_image.weight  11 norm_image.bias
+static size_t param_numel(int i, int64_t d) {
+    switch (i % 4 + (i >= 8 ? 4 : 0)) {
+        case 0: return (size_t)3 * d * d;
+        case 1: return (size_t)3 * d;
+        case 2: return (size_t)d * d;
+        case 3: return (size_t)d;
+        default: return (size_t)d;
+    }
+}
+static XLayout xlayout(int64_t B, int64_t T, int64_t R, int64_t d, bool widen) {
+    XLayout L{};
+    size_t o = 0;
+    auto take = [&](size_t n) { size_t r = o; o += (n + 63) / 64 * 64; return r; };
+    const size_t nt = (size_t)B * T, ni = (size_t)B * R;
+    L.Xt = take(widen ? nt * d : 0); L.Xi = take(widen ? ni * d : 0);
+    L.Qt = take(nt * d); L.KVi = take(ni * 2 * d); L.Qi = take(ni * d); L.KVt = take(nt * 2 * d);
+    L.Ot = take(nt * d); L.Oi = take(ni * d); L.Zt = take(nt * d); L.Zi = take(ni * d);
+    L.St = take(nt * 2); L.Si = take(ni * 2);
+    L.W = o;
+    if (widen) for (int i = 0; i < kParamCount; ++i) take(param_numel(i, d));
+    L.total = o;
+    return L;
+}
+
+template <typename T>
+static int widen(const void* src, float* dst, size_t n, cudaStream_t st) {
+    if (n == 0) return DCLIP_OK;
+    k_to_f32<T><<<(unsigned)ceil_div((int64_t)n, 256), 256, 0, st>>>(static_cast<const T*>(src), dst, (int64_t)n);
+    DCLIP_LAUNCH_OK("k_to_f32");
+    return DCLIP_OK;
+}
+template <typename T>
+static int narrow(const float* src, void* dst, size_t n, cudaStream_t st) {
+    if (n == 0) return DCLIP_OK;
+    k_from_f32<T><<<(unsigned)ceil_div((int64_t)n, 256), 256, 0, st>>>(src, static_cast<T*>(dst), (int64_t)n);
+    DCLIP_LAUNCH_OK("k_from_f32");
+    return DCLIP_OK;
+}
+
+static size_t attn_fwd_smem(int Lk, int hd) { return ((size_t)2 * Lk * (hd + 1) + 4 * hd + 4 * Lk) * 4; }
+static size_t attn_bwd_smem(int Lq, int Lk, int hd) { return ((size_t)(2 * Lq + 2 * Lk) * (hd + 1) + (size_t)2 * Lq * (Lk + 1)) * 4; }
+
+}  // namespace dclip
+
+using namespace dclip;
+
+extern "C" {
+
+size_t dclip_xattn_saved_bytes(int64_t B, int64_t T, int64_t R, int64_t d, int dtype) {
+    return xlayout(B, T, R, d, dtype != DCLIP_F32).total * sizeof(float) + 256;
+}
+// scratch for the backward: dZ, zhat, dO (text+image), dQ, dKV (both) + widened output grads
+size_t dclip_xattn_bwd_scratch_bytes(int64_t B, int64_t T, int64_t R, int64_t d, int dtype) {
+    const size_t nt = (size_t)B * T, ni = (size_t)B * R;
+    size_t f = (nt + ni) * d * 6 + (nt + ni) * 2 * d + 1024;       // dY, dZ, zhat, dO, dQ, dX + dKV
+    if (dtype != DCLIP_F32) { f += (nt + ni) * d; for (int i = 0; i < kParamCount; ++i) f += param_numel(i, d) + 64; }
+    return f * sizeof(float) + 4096;
+}
+
+int dclip_xattn_fwd(const void* text, const void* image, int64_t B, int64_t T, int64_t R, int64_t d, int heads, int dtype,
+                    const void* const* params, void* text_out, void* image_out, void* saved, size_t saved_bytes, void* stream) {
+    DCLIP_REQUIRE(text && image && params && text_out && image_out && saved, "xattn_fwd: null pointer");
+    DCLIP_REQUIRE(B > 0 && T > 0 && R > 0 && d > 0 && heads > 0 && d % heads == 0, "xattn_fwd: bad shape B=%lld T=%lld R=%lld d=%lld heads=%d",
+                  (long long)B, (long long)T, (long long)R, (long long)d, heads);
+    const bool wide = dtype != DCLIP_F32;
+    const XLayout L = xlayout(B, T, R, d, wide);
+    if (saved_bytes < L.total * sizeof(float)) return fail(DCLIP_ERR_WORKSPACE, "xattn_fwd: saved buffer too small (%zu < %zu)", saved_bytes, L.total * sizeof(float));
+    const int hd = (int)(d / heads);
+    const size_t sm_t2i = attn_fwd_smem((int)R, hd), sm_i2t = attn_fwd_smem((int)T, hd);
+    if (max(sm_t2i, sm_i2t) > 220 * 1024) return fail(DCLIP_ERR_UNSUPPORTED, "xattn_fwd: sequence x head_dim too large for shared memory");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float* S = static_cast<float*>(saved);
+    const int nt = (int)(B * T), ni = (int)(B * R), D = (int)d;
+    const float* Xt = static_cast<const float*>(text);
+    const float* Xi = static_cast<const float*>(image);
+    const float* Wp[kParamCount];
+    if (wide) {
+        size_t o = L.W;
+        for (int i = 0; i < kParamCount; ++i) {
+            const size_t n = param_numel(i, d);
+            DCLIP_DISPATCH_DTYPE(dtype, { if (int e = widen<T>(params[i], S + o, n, st)) return e; });
+            Wp[i] = S + o;
+            o += (n + 63) / 64 * 64;
+        }
+        DCLIP_DISPATCH_DTYPE(dtype, { if (int e = widen<T>(text, S + L.Xt, (size_t)nt * d, st)) return e; });
+        DCLIP_DISPATCH_DTYPE(dtype, { if (int e = widen<T>(image, S + L.Xi, (size_t)ni * d, st)) return e; });
+        Xt = S + L.Xt; Xi = S + L.Xi;
+    } else {
+        for (int i = 0; i < kParamCount; ++i) Wp[i] = static_cast<const float*>(params[i]);
+    }
+    // (1) in-projections: Q_t, K|V_i (text_to_image) and Q_i, K|V_t (image_to_text)
+    GemmGroup g{};
+    g.p[0] = gemm(Xt, D, false, Wp[0], D, true, S + L.Qt, D, nt, D, D, Wp[1]);
+    g.p[1] = gemm(Xi, D, false, Wp[0] + (size_t)d * d, D, true, S + L.KVi, 2 * D, ni, 2 * D, D, Wp[1] + d);
+    g.p[2] = gemm(Xi, D, false, Wp[4], D, true, S + L.Qi, D, ni, D, D, Wp[5]);
+    g.p[3] = gemm(Xt, D, false, Wp[4] + (size_t)d * d, D, true, S + L.KVt, 2 * D, nt, 2 * D, D, Wp[5] + d);
+    g.count = 4;
+    if (int e = launch_gemm_group(g, st)) return e;
+    // (2) attention cores
+    AttnArgs a{};
+    a.B = (int)B; a.heads = heads; a.hd = hd; a.d = D; a.scale = 1.0f / sqrtf((float)hd);
+    a.dir[0] = AttnDir{S + L.Qt, D, S + L.KVi, 2 * D, S + L.Ot, (int)T, (int)R, nullptr, nullptr, nullptr};
+    a.dir[1] = AttnDir{S + L.Qi, D, S + L.KVt, 2 * D, S + L.Oi, (int)R, (int)T, nullptr, nullptr, nullptr};
+    const size_t smf = max(sm_t2i, sm_i2t);
+    DCLIP_CUDA_OK(cudaFuncSetAttribute(k_attn_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf));
+    k_attn_fwd<<<dim3((unsigned)(B * heads), 2), 128, smf, st>>>(a);
+    DCLIP_LAUNCH_OK("k_attn_fwd");
+    // (3) out-projection + bias + residual -> Z
+    GemmGroup g2{};
+    g2.p[0] = gemm(S + L.Ot, D, false, Wp[2], D, true, S + L.Zt, D, nt, D, D, Wp[3], Xt, D);
+    g2.p[1] = gemm(S + L.Oi, D, false, Wp[6], D, true, S + L.Zi, D, ni, D, D, Wp[7], Xi, D);
+    g2.count = 2;
+    if (int e = launch_gemm_group(g2, st)) return e;
+    // (4) LayerNorm
+    if (!wide) {
+        k_ln_fwd<<<(unsigned)ceil_div(nt, 8), 256, 0, st>>>(S + L.Zt, Wp[8], Wp[9], nt, D, static_cast<float*>(text_out), S + L.St);
+        k_ln_fwd<<<(unsigned)ceil_div(ni, 8), 256, 0, st>>>(S + L.Zi, Wp[10], Wp[11], ni, D, static_cast<float*>(image_out), S + L.Si);
+        DCLIP_LAUNCH_OK("k_ln_fwd");
+    } else {
+        // fp32 result staged in the widened-input slots (X copies are re-derived in the backward from the originals)
+        k_ln_fwd<<<(unsigned)ceil_div(nt, 8), 256, 0, st>>>(S + L.Zt, Wp[8], Wp[9], nt, D, S + L.Xt, S + L.St);
+        k_ln_fwd<<<(unsigned)ceil_div(ni, 8), 256, 0, st>>>(S + L.Zi, Wp[10], Wp[11], ni, D, S + L.Xi, S + L.Si);
+        DCLIP_LAUNCH_OK("k_ln_fwd");
+        DCLIP_DISPATCH_DTYPE(dtype, { if (int e = narrow<T>(S + L.Xt, text_out, (size_t)nt * d, st)) return e; });
+        DCLIP_DISPATCH_DTYPE(dtype, { if (int e = narrow<T>(S + L.Xi, image_out, (size_t)ni * d, st)) return e; });
+    }
+    return DCLIP_OK;
+}
+
+int dclip_xattn_bwd(const void* text, const void* image, int64_t B, int64_t T, int64_t R, int64_t d, int heads, int dtype,
+                    const void* const* params, const void* saved, const void* d_text_out, const void* d_image_out,
+                    void* const* grads, void* d_text, void* d_image, void* scratch, size_t scratch_bytes, void* stream) {
+    DCLIP_REQUIRE(text && image && params && saved && d_text_out && d_image_out && grads && scratch, "xattn_bwd: null pointer");
+    DCLIP_REQUIRE((d_text == nullptr) == (d_image == nullptr), "xattn_bwd: give both input gradients or neither");
+    if (scratch_bytes < dclip_xattn_bwd_scratch_bytes(B, T, R, d, dtype)) return fail(DCLIP_ERR_WORKSPACE, "xattn_bwd: scratch too small");
+    const bool wide = dtype != DCLIP_F32;
+    const XLayout L = xlayout(B, T, R, d, wide);
+    const int hd = (int)(d / heads);
+    const size_t smb = max(attn_bwd_smem((int)T, (int)R, hd), attn_bwd_smem((int)R, (int)T, hd));
+    if (smb > 220 * 1024) return fail(DCLIP_ERR_UNSUPPORTED, "xattn_bwd: sequence x head_dim too large for shared memory");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const float* S = static_cast<const float*>(saved);
+    const int nt = (int)(B * T), ni = (int)(B * R), D = (int)d;
+    // scratch carve (floats)
+    float* W = static_cast<float*>(scratch);
+    size_t o = 0;
+    auto take = [&](size_t n) { float* r = W + o; o += (n + 63) / 64 * 64; return r; };
+    float* dYt = take((size_t)nt * d); float* dYi = take((size_t)ni * d);     // widened upstream grads
+    float* dZt = take((size_t)nt * d); float* dZi = take((size_t)ni * d);
+    float* zht = take((size_t)nt * d); float* zhi = take((size_t)ni * d);
+    float* dOt = take((size_t)nt * d); float* dOi = take((size_t)ni * d);
+    float* dQt = take((size_t)nt * d); float* dQi = take((size_t)ni * d);
+    float* dKVi = take((size_t)ni * 2 * d); float* dKVt = take((size_t)nt * 2 * d);
+    float* dXt = take((size_t)nt * d); float* dXi = take((size_t)ni * d);
+    float* Xt_w = nullptr; float* Xi_w = nullptr;
+    float* G[kParamCount];
+    const float* Wp[kParamCount];
+    const float* Xt = static_cast<const float*>(text);
+    const float* Xi = static_cast<const float*>(image);
+    const float* dyt = static_cast<const float*>(d_text_out);
+    const float* dyi = static_cast<const float*>(d_image_out);
+    if (wide) {
+        Xt_w = take((size_t)nt * d); Xi_w = take((size_t)ni * d);
+        size_t wo = L.W;
+        for (int i = 0; i < kParamCount; ++i) {
+            G[i] = take(param_numel(i, d));
+            Wp[i] = S + wo;
+            wo += (param_numel(i, d) + 63) / 64 * 64;
+        }
+        DCLIP_DISPATCH_DTYPE(dtype, { if (int e = widen<T>(text, Xt_w, (size_t)nt * d, st)) return e; });
+        DCLIP_DISPATCH_DTYPE(dtype, { if (int e = widen<T>(image, Xi_w, (size_t)ni * d, st)) return e; });
+        DCLIP_DISPATCH_DTYPE(dtype, { if (int e = widen<T>(d_text_out, dYt, (size_t)nt * d, st)) return e; });
+        DCLIP_DISPATCH_DTYPE(dtype, { if (int e = widen<T>(d_image_out, dYi, (size_t)ni * d, st)) return e; });
+        Xt = Xt_w; Xi = Xi_w; dyt = dYt; dyi = dYi;
+    } else {
+        for (int i = 0; i < kParamCount; ++i) { G[i] = static_cast<float*>(grads[i]); Wp[i] = static_cast<const float*>(params[i]); }
+    }
+    if (o * sizeof(float) > scratch_bytes) return fail(DCLIP_ERR_WORKSPACE, "xattn_bwd: scratch too small (%zu < %zu)", scratch_bytes, o * sizeof(float));
+
+    // (4') LayerNorm backward: dZ, zhat; dgamma = colsum(dY * zhat), dbeta = colsum(dY)
+    k_ln_bwd<<<(unsigned)ceil_div(nt, 8), 256, 0, st>>>(dyt, S + L.Zt, Wp[8], S + L.St, nt, D, dZt, zht);
+    k_ln_bwd<<<(unsigned)ceil_div(ni, 8), 256, 0, st>>>(dyi, S + L.Zi, Wp[10], S + L.Si, ni, D, dZi, zhi);
+    DCLIP_LAUNCH_OK("k_ln_bwd");
+    k_colsum<<<(unsigned)ceil_div(D, 32), 256, 0, st>>>(dyt, zht, nt, D, D, D, G[9], G[8]);
+    k_colsum<<<(unsigned)ceil_div(D, 32), 256, 0, st>>>(dyi, zhi, ni, D, D, D, G[11], G[10]);
+    // (3') out-projection backward: dWo = dZ^T O, dbo = colsum(dZ), dO = dZ Wo
+    k_colsum<<<(unsigned)ceil_div(D, 32), 256, 0, st>>>(dZt, nullptr, nt, D, D, 0, G[3], nullptr);
+    k_colsum<<<(unsigned)ceil_div(D, 32), 256, 0, st>>>(dZi, nullptr, ni, D, D, 0, G[7], nullptr);
+    DCLIP_LAUNCH_OK("k_colsum");
+    GemmGroup g{};
+    g.p[0] = gemm(dZt, D, true, S + L.Ot, D, false, G[2], D, D, D, nt);
+    g.p[1] = gemm(dZi, D, true, S + L.Oi, D, false, G[6], D, D, D, ni);
+    g.p[2] = gemm(dZt, D, false, Wp[2], D, false, dOt, D, nt, D, D);
+    g.p[3] = gemm(dZi, D, false, Wp[6], D, false, dOi, D, ni, D, D);
+    g.count = 4;
+    if (int e = launch_gemm_group(g, st)) return e;
+    // (2') attention cores backward
+    AttnArgs a{};
+    a.B = (int)B; a.heads = heads; a.hd = hd; a.d = D; a.scale = 1.0f / sqrtf((float)hd);
+    a.dir[0] = AttnDir{S + L.Qt, D, S + L.KVi, 2 * D, nullptr, (int)T, (int)R, dOt, dQt, dKVi};
+    a.dir[1] = AttnDir{S + L.Qi, D, S + L.KVt, 2 * D, nullptr, (int)R, (int)T, dOi, dQi, dKVt};
+    DCLIP_CUDA_OK(cudaFuncSetAttribute(k_attn_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb));
+    k_attn_bwd<<<dim3((unsigned)(B * heads), 2), 128, smb, st>>>(a);
+    DCLIP_LAUNCH_OK("k_attn_bwd");
+    // (1') in-projection backward: weight grads (rows 0..d = q, d..3d = k|v) and bias grads
+    k_colsum<<<(unsigned)ceil_div(D, 32), 256, 0, st>>>(dQt, nullptr, nt, D, D, 0, G[1], nullptr);
+    k_colsum<<<(unsigned)ceil_div(2 * D, 32), 256, 0, st>>>(dKVi, nullptr, ni, 2 * D, 2 * D, 0, G[1] + d, nullptr);
+    k_colsum<<<(unsigned)ceil_div(D, 32), 256, 0, st>>>(dQi, nullptr, ni, D, D, 0, G[5], nullptr);
+    k_colsum<<<(unsigned)ceil_div(2 * D, 32), 256, 0, st>>>(dKVt, nullptr, nt, 2 * D, 2 * D, 0, G[5] + d, nullptr);
+    DCLIP_LAUNCH_OK("k_colsum");
+    GemmGroup g2{};
+    g2.p[0] = gemm(dQt, D, true, Xt, D, false, G[0], D, D, D, nt);
+    g2.p[1] = gemm(dKVi, 2 * D, true, Xi, D, false, G[0] + (size_t)d * d, D, 2 * D, D, ni);
+    g2.p[2] = gemm(dQi, D, true, Xi, D, false, G[4], D, D, D, ni);
+    g2.p[3] = gemm(dKVt, 2 * D, true, Xt, D, false, G[4] + (size_t)d * d, D, 2 * D, D, nt);
+    g2.count = 4;
+    if (int e = launch_gemm_group(g2, st)) return e;
+    if (d_text) {
+        // input gradients: residual path + query projection + key/value projection of the other direction
+        GemmGroup g3{};
+        g3.p[0] = gemm(dQt, D, false, Wp[0], D, false, dXt, D, nt, D, D, nullptr, dZt, D);
+        g3.p[1] = gemm(dQi, D, false, Wp[4], D, false, dXi, D, ni, D, D, nullptr, dZi, D);
+        g3.count = 2;
+        if (int e = launch_gemm_group(g3, st)) return e;
+        GemmGroup g4{};
+        g4.p[0] = gemm(dKVt, 2 * D, false, Wp[4] + (size_t)d * d, D, false, dXt, D, nt, D, 2 * D, nullptr, nullptr, 0, true);
+        g4.p[1] = gemm(dKVi, 2 * D, false, Wp[0] + (size_t)d * d, D, false, dXi, D, ni, D, 2 * D, nullptr, nullptr, 0, true);
+        g4.count = 2;
+        if (int e = launch_gemm_group(g4, st)) return e;
+        if (wide) {
+            DCLIP_DISPATCH_DTYPE(dtype, { if (int e = narrow<T>(dXt, d_text, (size_t)nt * d, st)) return e; });
+            DCLIP_DISPATCH_DTYPE(dtype, { if (int e = narrow<T>(dXi, d_image, (size_t)ni * d, st)) return e; });
+        } else {
+            DCLIP_CUDA_OK(cudaMemcpyAsync(d_text, dXt, (size_t)nt * d * 4, cudaMemcpyDeviceToDevice, st));
+            DCLIP_CUDA_OK(cudaMemcpyAsync(d_image, dXi, (size_t)ni * d * 4, cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    if (wide)
+        for (int i = 0; i < kParamCount; ++i)
+            DCLIP_DISPATCH_DTYPE(dtype, { if (int e = narrow<T>(G[i], grads[i], param_numel(i, d), st)) return e; });
+    return DCLIP_OK;
+}
+
+int dclip_aggregate_fwd(const void* x, int64_t B, int64_t L, int64_t d, int dtype, float temperature, void* out, float* weights,
+                        void* stream) {
+    DCLIP_REQUIRE(x && out && B > 0 && L > 0 && d > 0 && temperature > 0.f, "aggregate_fwd: bad arguments");
+    const size_t sm = (size_t)(d + L + 8) * 4;
+    if (sm > 200 * 1024) return fail(DCLIP_ERR_UNSUPPORTED, "aggregate_fwd: d + L too large");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    DCLIP_DISPATCH_DTYPE(dtype, {
+        DCLIP_CUDA_OK(cudaFuncSetAttribute(k_aggregate_fwd<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        k_aggregate_fwd<T><<<(unsigned)B, 256, sm, st>>>(static_cast<const T*>(x), (int)L, (int)d, temperature, static_cast<T*>(out), weights);
+    });
+    DCLIP_LAUNCH_OK("k_aggregate_fwd");
+    return DCLIP_OK;
+}
+
+int dclip_aggregate_bwd(const void* x, const float* weights, const void* d_out, int64_t B, int64_t L, int64_t d, int dtype,
+                        float temperature, void* d_x, void* stream) {
+    DCLIP_REQUIRE(x && weights && d_out && d_x && B > 0 && L > 0 && d > 0 && temperature > 0.f, "aggregate_bwd: bad arguments");
+    const size_t sm = (size_t)(2 * d + 3 * L + 8) * 4;
+    if (sm > 200 * 1024) return fail(DCLIP_ERR_UNSUPPORTED, "aggregate_bwd: d + L too large");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    DCLIP_DISPATCH_DTYPE(dtype, {
+        DCLIP_CUDA_OK(cudaFuncSetAttribute(k_aggregate_bwd<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        k_aggregate_bwd<T><<<(unsigned)B, 256, sm, st>>>(static_cast<const T*>(x), weights, static_cast<const T*>(d_out), (int)L, (int)d,
+                                                         temperature, static_cast<T*>(d_x));
+    });
+    DCLIP_LAUNCH_OK("k_aggregate_bwd");
+    return DCLIP_OK;
+}
+
+int dclip_combine_guard_fwd(const void* a, const void* b, int64_t n, int dtype, void* out, int* flag, void* stream) {
+    DCLIP_REQUIRE(a && b && out && flag && n > 0, "combine_guard_fwd: bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    DCLIP_CUDA_OK(cudaMemsetAsync(flag, 0, sizeof(int), st));
+    DCLIP_DISPATCH_DTYPE(dtype, {
+        k_combine_fwd<T><<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(static_cast<const T*>(a), static_cast<const T*>(b), n, static_cast<T*>(out), flag);
+        k_guard_zero<T><<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(static_cast<T*>(out), n, flag);
+    });
+    DCLIP_LAUNCH_OK("k_combine_fwd");
+    return DCLIP_OK;
+}
+
+int dclip_combine_guard_bwd(const void* d_out, int64_t n, int dtype, const int* flag, void* d_a, void* d_b, void* stream) {
+    DCLIP_REQUIRE(d_out && flag && d_a && d_b && n > 0, "combine_guard_bwd: bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    DCLIP_DISPATCH_DTYPE(dtype, {
+        k_combine_bwd<T><<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(static_cast<const T*>(d_out), n, flag, static_cast<T*>(d_a), static_cast<T*>(d_b));
+    });
+    DCLIP_LAUNCH_OK("k_combine_bwd");
+    return DCLIP_OK;
+}
+
+}  // extern "C"

@@ -179,6 +179,42 @@ int dclip_topk_ip(const void* q, const void* g, int64_t nq, int64_t ng, int64_t 
 int dclip_topk_merge(const float* in_scores, const int64_t* in_index, int64_t nlists, int64_t nq, int64_t k,
                      float* out_scores, int64_t* out_index, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Meta-teacher cross-attention   (replaces CrossModalAttention.forward,
+ *   training/patch_text_aggregation.py:13-46 = 2 x nn.MultiheadAttention + residual + LayerNorm,
+ *   PatchTextAggregation.aggregation :243-265, the combine / NaN guard :640-656, and the autograd
+ *   backward of the teacher step, training/train_contrastive_teacher.py:347-362)
+ *
+ * text [B, T, d], image [B, R, d] (batch-first, zero-padded rows are attended: there is no mask in
+ * the reference).  params / grads: 12 pointers in the reference module's state_dict order
+ *   0 text_to_image.in_proj_weight [3d,d]   1 .in_proj_bias [3d]   2 .out_proj.weight [d,d]   3 .out_proj.bias [d]
+ *   4 image_to_text.in_proj_weight          5 .in_proj_bias        6 .out_proj.weight         7 .out_proj.bias
+ *   8 norm_text.weight [d]   9 norm_text.bias   10 norm_image.weight   11 norm_image.bias
+ * all in `dtype`.  `saved` keeps the fp32 intermediates the backward re-reads (Q, K|V, attention
+ * output, pre-LayerNorm sums, LayerNorm statistics); attention probabilities are recomputed.
+ * ------------------------------------------------------------------------------------------ */
+size_t dclip_xattn_saved_bytes(int64_t B, int64_t T, int64_t R, int64_t d, int dtype);
+size_t dclip_xattn_bwd_scratch_bytes(int64_t B, int64_t T, int64_t R, int64_t d, int dtype);
+int dclip_xattn_fwd(const void* text, const void* image, int64_t B, int64_t T, int64_t R, int64_t d, int heads, int dtype,
+                    const void* const* params, void* text_out, void* image_out, void* saved, size_t saved_bytes,
+                    void* stream);
+/* d_text / d_image may both be NULL (the teacher step needs parameter gradients only). */
+int dclip_xattn_bwd(const void* text, const void* image, int64_t B, int64_t T, int64_t R, int64_t d, int heads, int dtype,
+                    const void* const* params, const void* saved, const void* d_text_out, const void* d_image_out,
+                    void* const* grads, void* d_text, void* d_image, void* scratch, size_t scratch_bytes, void* stream);
+
+/* aggregation(attended [B, L, d], temperature = 2.0) -> [B, d]; weights: float[B, L] softmax weights
+ * saved for the backward (may be NULL for inference). */
+int dclip_aggregate_fwd(const void* x, int64_t B, int64_t L, int64_t d, int dtype, float temperature, void* out,
+                        float* weights, void* stream);
+int dclip_aggregate_bwd(const void* x, const float* weights, const void* d_out, int64_t B, int64_t L, int64_t d, int dtype,
+                        float temperature, void* d_x, void* stream);
+
+/* out = 0.5 a + 0.5 b; if any element is NaN/Inf the WHOLE tensor becomes zero (reference :649-651).
+ * flag: int[1] device (1 = guard fired), kept by the caller for the backward.  No host sync. */
+int dclip_combine_guard_fwd(const void* a, const void* b, int64_t n, int dtype, void* out, int* flag, void* stream);
+int dclip_combine_guard_bwd(const void* d_out, int64_t n, int dtype, const int* flag, void* d_a, void* d_b, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

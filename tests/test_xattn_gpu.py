@@ -1,0 +1,127 @@
+"""Cross-attention + aggregation + teacher step on the GPU vs the reference golden outputs and the
+oracle (fp32 tier 1e-5 relative on outputs; gradients 1e-4: they pass through several chained
+fp32 reductions, the CPU reference itself differs from fp64 at that level)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import reference_math as om
+from oracle import synthetic
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def _rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def _module(d, heads, params, dtype=torch.float32):
+    from dclip_b200.patch_text_aggregation import PatchTextAggregation
+    m = PatchTextAggregation(embed_dim=d, num_heads=heads)
+    missing = m.cross_modal_attention.load_state_dict(params, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    return m.to(DEV).to(dtype)
+
+
+@pytest.mark.parametrize("name", ["xattn_small", "xattn_ragged", "xattn_hd96"])
+def test_golden_forward_backward(built_library, name):
+    from dclip_b200 import losses as L
+    g = load_golden(name)
+    d, heads = int(g["d"]), int(g["heads"])
+    params = {k[len("param."):]: _t(v) for k, v in g.items() if k.startswith("param.")}
+    m = _module(d, heads, params)
+    text, image = _t(g["text"]).to(DEV), _t(g["image"]).to(DEV)
+    t_out, i_out = m.cross_attention(text, image)
+    assert _rel(t_out, _t(g["text_out"])) < 1e-5 and _rel(i_out, _t(g["image_out"])) < 1e-5
+    assert _rel(m.aggregation(t_out), _t(g["agg_text"])) < 1e-5
+    assert _rel(m.aggregation(i_out), _t(g["agg_image"])) < 1e-5
+    glob = m.global_embedding(text, image)
+    assert _rel(glob, _t(g["global"])) < 1e-5
+    loss = L.compute_contrastive_loss(glob, _t(g["txt_emb"]).to(DEV), temperature=0.05, path="fp32")
+    loss.backward()
+    assert abs(float(loss) - float(g["loss"])) < 2e-5 * max(1.0, abs(float(g["loss"])))
+    grads = dict(m.cross_modal_attention.named_parameters())
+    for k in om.PARAM_KEYS:
+        assert _rel(grads[k].grad, _t(g["grad." + k])) < 2e-4, k
+
+
+def test_cfg1_teacher_step(built_library):
+    """BASELINE configs[0] shape: B=32, T=77, R=8, d=512, ragged zero padding."""
+    from dclip_b200 import losses as L
+    g = load_golden("xattn_cfg1")
+    B, T, R, d, heads, seed = (int(g[k]) for k in ("B", "T", "R", "d", "heads", "seed"))
+    params = om.perturbed_cross_attention_params(d, heads, seed)
+    m = _module(d, heads, params)
+    text, image = synthetic.xattn_inputs(B, T, R, d, seed, ragged=True)
+    glob = m.global_embedding(text.to(DEV), image.to(DEV))
+    assert _rel(glob, _t(g["global"])) < 1e-5
+    loss = L.compute_contrastive_loss(glob, _t(g["txt_emb"]).to(DEV), path="fp32")
+    loss.backward()
+    assert abs(float(loss) - float(g["loss"])) < 2e-5 * abs(float(g["loss"]))
+    for k, p in m.cross_modal_attention.named_parameters():
+        want = float(g["gradnorm." + k])
+        assert abs(float(p.grad.double().norm()) - want) < 1e-3 * max(want, 1e-6), k
+
+
+def test_input_gradients_and_oracle_fp64(built_library):
+    B, T, R, d, heads = 3, 11, 5, 128, 8
+    params = om.perturbed_cross_attention_params(d, heads, 5)
+    m = _module(d, heads, params)
+    text, image = synthetic.xattn_inputs(B, T, R, d, 5)
+    a = text.to(DEV).requires_grad_(True)
+    b = image.to(DEV).requires_grad_(True)
+    glob = m.global_embedding(a, b)
+    w = torch.randn(B, d, generator=torch.Generator().manual_seed(1))
+    (glob * w.to(DEV)).sum().backward()
+    p64 = {k: v.double().requires_grad_(True) for k, v in params.items()}
+    a64 = text.double().requires_grad_(True)
+    b64 = image.double().requires_grad_(True)
+    ref = om.global_embedding(p64, a64, b64, heads)
+    (ref * w.double()).sum().backward()
+    assert _rel(glob, ref) < 1e-5
+    assert _rel(a.grad, a64.grad) < 1e-4 and _rel(b.grad, b64.grad) < 1e-4
+    for k, p in m.cross_modal_attention.named_parameters():
+        assert _rel(p.grad, p64[k].grad) < 1e-4, k
+
+
+def test_bf16_cfg3_shape(built_library):
+    """BASELINE configs[2] shape (B=32, R=36, T=77, d=768, bf16 params/activations, fp32 statistics)."""
+    B, T, R, d, heads = 32, 77, 36, 768, 8
+    params = om.perturbed_cross_attention_params(d, heads, 3)
+    m = _module(d, heads, params, torch.bfloat16)
+    text, image = synthetic.xattn_inputs(B, T, R, d, 3, ragged=True)
+    tb, ib = text.bfloat16(), image.bfloat16()
+    t_out, i_out = m.cross_attention(tb.to(DEV), ib.to(DEV))
+    pb = {k: v.bfloat16().float() for k, v in params.items()}
+    rt, ri = om.cross_modal_attention(pb, tb.float(), ib.float(), heads)
+    # one bf16 rounding of the outputs (2^-9) on top of fp32 math
+    assert _rel(t_out, rt) < 4e-3 and _rel(i_out, ri) < 4e-3
+
+
+def test_nan_guard_zeroes_whole_tensor(built_library):
+    from dclip_b200.patch_text_aggregation import combine_global
+    a = torch.randn(4, 16, device=DEV, requires_grad=True)
+    b = torch.randn(4, 16, device=DEV)
+    b[2, 3] = float("inf")
+    out = combine_global(a, b)
+    assert torch.count_nonzero(out) == 0
+    out.sum().backward()
+    assert torch.count_nonzero(a.grad) == 0
+    out2 = combine_global(a.detach(), torch.ones_like(a))
+    assert torch.allclose(out2, 0.5 * a.detach() + 0.5)
+
+
+def test_state_dict_is_reference_compatible(built_library):
+    from dclip_b200.patch_text_aggregation import CrossModalAttention
+    m = CrossModalAttention(64, 8)
+    assert list(m.state_dict().keys()) == list(om.PARAM_KEYS)
+    names = [n for n, _ in m.named_parameters()]
+    # the teacher loop unfreezes parameters whose name contains one of these (train_contrastive_teacher.py:130-134)
+    assert all(("attention" in "cross_modal_attention." + n) or ("proj" in n) for n in names)

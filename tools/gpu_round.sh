@@ -50,6 +50,22 @@ if has ncu; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$P.csv $CMD > $OUT/ncu_run.log 2>&1
   echo "ncu exit=$?"; tail -3 $OUT/ncu_run.log
 fi
+if has cluster; then
+  for C in 1 2 4; do
+    DCLIP_TC_CLUSTER=$C timeout 600 python -m pytest tests/test_loss_tensor_gpu.py -q -m gpu > $OUT/pytest_tensor_c$C.log 2>&1
+    echo "cluster=$C pytest exit=$?"; tail -4 $OUT/pytest_tensor_c$C.log
+    DCLIP_TC_CLUSTER=$C timeout 600 python bench.py --steps 20 --warmup 5 --path tensor --no-retrieval --no-cpu-baseline > $OUT/bench_tensor_c$C.json 2> $OUT/bench_tensor_c$C.err
+    echo "cluster=$C bench exit=$?"; tail -2 $OUT/bench_tensor_c$C.err
+    python - <<PY
+import json
+try:
+    d=json.loads(open("$OUT/bench_tensor_c$C.json").read().strip().splitlines()[-1])
+    print("cluster=$C ms_per_step", d["ms_per_step"], "value", d["value"], "e2e", d["e2e"]["value"], "roof", d["roofline"]["frac"], d["roofline"]["avg_launch_us"])
+except Exception as e: print("no bench json", e)
+PY
+  done
+fi
+
 if has ncufull; then
   # one full capture of the dominant kernel (backward contraction), after the plain run passed
   CMD="python bench.py --steps 1 --warmup 3 --path tensor --no-retrieval --no-cpu-baseline"
