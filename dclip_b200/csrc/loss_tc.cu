@@ -85,7 +85,7 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 1);
     float* a_s = reinterpret_cast<float*>(tmem_ptr + 2);  // [NI] (bwd) column factors
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;     // warp-uniform role index
     const int64_t row0 = (int64_t)blockIdx.x * NI;
     const int64_t ntiles = (a.n + TJ - 1) / TJ;
     const int64_t t_begin = (int64_t)blockIdx.y * a.tiles_per_split;
@@ -112,7 +112,7 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
     if (T > 0) {
         if (warp == 0) {
             // ===================== TMA producer =====================
-            if (lane == 0) {
+            if (elect_one()) {
                 tma_prefetch_desc(tmx);
                 tma_prefetch_desc(tmy);
                 mbar_arrive_expect_tx(x_full, (uint32_t)(nkb * kXBoxBytes));
@@ -145,7 +145,7 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
             }
         } else if (warp == 1) {
             // ===================== MMA issuer =====================
-            if (lane == 0) {
+            if (elect_one()) {
                 const uint32_t idesc1 = make_idesc_f16(128, NI, kFmtF16, 0, 0);
                 const uint32_t idesc2 = make_idesc_f16(128, NI, kFmtF16, 1, 1);
                 const uint64_t hiK = make_smem_desc_hi(0, 1024, kSwizzle128B);
@@ -162,15 +162,14 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
                     for (int s = 0; s < NS && ok; ++s) {
                         ok = mbar_wait(&full[p.stage], p.phase, kSpin);
                         fence_after_thread_sync();
-                        const uint32_t slot = ring_addr + p.stage * kSlotBytes;
+                        const uint64_t da0 = smem_desc(hiK, ring_addr + p.stage * kSlotBytes);
+                        const uint64_t db0 = smem_desc(hiK, xs_addr + (2 * s) * kXBoxBytes);
 #pragma unroll
                         for (int h = 0; h < 2; ++h)
 #pragma unroll
-                            for (int ks = 0; ks < 4; ++ks) {
-                                const uint64_t da = smem_desc(hiK, slot + h * kBoxBytes + ks * 32);
-                                const uint64_t db = smem_desc(hiK, xs_addr + (2 * s + h) * kXBoxBytes + ks * 32);
-                                umma_f16(dcol, da, db, idesc1, (s | h | ks) != 0);
-                            }
+                            for (int ks = 0; ks < 4; ++ks)      // +32 B per K step, next box at +16 KB (A) / +8 KB (B); >>4 encoded
+                                umma_f16(dcol, da0 + (uint64_t)(h * (kBoxBytes >> 4) + ks * 2), db0 + (uint64_t)(h * (kXBoxBytes >> 4) + ks * 2), idesc1,
+                                         (s | h | ks) != 0);
                         if (kC == 1) umma_commit(&empty[p.stage]); else umma_commit_mcast(&empty[p.stage], kMask);
                         p.advance();
                     }
@@ -184,13 +183,11 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
                     for (int s = 0; s < NS && ok; ++s) {
                         ok = mbar_wait(&full[p.stage], p.phase, kSpin);
                         fence_after_thread_sync();
-                        const uint32_t slot = ring_addr + p.stage * kSlotBytes;
+                        const uint64_t da0 = smem_desc(hiA2, ring_addr + p.stage * kSlotBytes);
+                        const uint64_t db0 = smem_desc(hiB2, gaddr);
 #pragma unroll
-                        for (int ks = 0; ks < 8; ++ks) {
-                            const uint64_t da = smem_desc(hiA2, slot + ks * 2048);
-                            const uint64_t db = smem_desc(hiB2, gaddr + ks * 2048);
-                            umma_f16(tmem + s * NI, da, db, idesc2, (t | ks) != 0);
-                        }
+                        for (int ks = 0; ks < 8; ++ks)          // 16 j per step = two 8-row groups = +2048 B
+                            umma_f16(tmem + s * NI, da0 + (uint64_t)(ks * 128), db0 + (uint64_t)(ks * 128), idesc2, (t | ks) != 0);
                         if (kC == 1) umma_commit(&empty[p.stage]); else umma_commit_mcast(&empty[p.stage], kMask);
                         p.advance();
                     }

@@ -20,6 +20,22 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
+// Warp-uniform helpers.  tcgen05.mma / TMA take their descriptors from UNIFORM registers: if the
+// issuing code sits behind a per-thread predicate (threadIdx.x == 0) the compiler has to move every
+// descriptor through R2UR inside a convergence loop (~90 cycles per MMA, measured).  Selecting the
+// role with a shuffled (provably uniform) warp index and one elected lane keeps them in the uniform
+// datapath.
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n.reg .b32 rx;\n.reg .pred px;\n"
+        "elect.sync rx|px, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, px;\n}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- mbarrier ---------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

@@ -1,0 +1,170 @@
+// tc_bench — micro-benchmarks of the sm_100a primitives the tensor-path kernels are built from.
+// Development tool: measures (1) tcgen05.mma issue/execute rate from resident shared memory for the
+// tile shapes and operand majors we use, (2) TMA streaming rate through an mbarrier ring.
+// Every wait is bounded.  Usage: tc_bench mma | tc_bench tma
+#include <cuda_fp16.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../dclip_b200/csrc/tcgen05.cuh"
+
+using namespace dclip::tc;
+
+#define CK(x)                                                                              \
+    do {                                                                                   \
+        cudaError_t e_ = (x);                                                              \
+        if (e_ != cudaSuccess) {                                                           \
+            printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+            exit(2);                                                                       \
+        }                                                                                  \
+    } while (0)
+
+// ---- (1) MMA rate: one thread issues `iters` x `per` MMAs on resident (zeroed) operands ---------
+__global__ void __launch_bounds__(128) k_mma_rate(int N, int a_mn, int b_mn, int iters, int per, int spread, long long* cycles) {
+    extern __shared__ uint8_t raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    for (int i = threadIdx.x; i < 160 * 1024 / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+    if (threadIdx.x < 32) tmem_alloc(&tmem_base, 512);
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+    fence_before_thread_sync();
+    __syncthreads();
+    fence_after_thread_sync();
+    const uint32_t tmem = tmem_base;
+    if (uniform_warp_idx() == 0 && elect_one()) {
+        const uint32_t idesc = make_idesc_f16(128, N, kFmtF16, a_mn, b_mn);
+        const uint64_t hiA = make_smem_desc_hi(a_mn ? 16384 : 0, 1024, kSwizzle128B);
+        const uint64_t hiB = make_smem_desc_hi(b_mn ? 16384 : 0, 1024, kSwizzle128B);
+        const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem) + 64 * 1024;
+        uint32_t parity = 0;
+        const long long t0 = clock64();
+        for (int it = 0; it < iters; ++it) {
+            const uint64_t dA = smem_desc(hiA, a0), dB = smem_desc(hiB, b0);
+            const uint32_t stepA = spread ? (a_mn ? 128u : 2u) : 0u, stepB = b_mn ? 128u : 2u;
+            for (int k8 = 0; k8 < per; k8 += 8) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    umma_f16(tmem + (k & 1) * 256, dA + (uint64_t)(k * stepA), dB + (uint64_t)((k & 3) * stepB), idesc, 1);
+            }
+            umma_commit(&bar);
+            if (!mbar_wait(&bar, parity, 1u << 22)) { cycles[blockIdx.x] = -1; break; }
+            parity ^= 1;
+        }
+        const long long t1 = clock64();
+        if (cycles[blockIdx.x] != -1) cycles[blockIdx.x] = t1 - t0;
+    }
+    fence_before_thread_sync();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc(tmem, 512);
+}
+
+static void run_mma() {
+    long long* cyc;
+    CK(cudaMalloc(&cyc, 148 * 8));
+    CK(cudaFuncSetAttribute(k_mma_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    printf("%-6s %-4s %-4s %-7s %-6s | cycles/MMA (ideal M*N/256... 128*N*16/4096)\n", "N", "Amn", "Bmn", "spread", "grid");
+    const int Ns[3] = {64, 128, 256};
+    for (int grid : {1, 148})
+        for (int ni = 0; ni < 3; ++ni)
+            for (int maj = 0; maj < 4; ++maj)
+                for (int spread = 0; spread < 2; ++spread) {
+                    const int N = Ns[ni], a_mn = maj & 1, b_mn = maj >> 1;
+                    if (b_mn && N > 64 && 0) continue;
+                    CK(cudaMemset(cyc, 0, 148 * 8));
+                    const int iters = 20, per = 64;
+                    k_mma_rate<<<grid, 128, 200 * 1024>>>(N, a_mn, b_mn, iters, per, spread, cyc);
+                    cudaError_t e = cudaDeviceSynchronize();
+                    if (e != cudaSuccess) { printf("N=%d maj=%d: CUDA ERROR %s\n", N, maj, cudaGetErrorString(e)); exit(3); }
+                    long long h[148];
+                    CK(cudaMemcpy(h, cyc, grid * 8, cudaMemcpyDeviceToHost));
+                    double avg = 0;
+                    for (int i = 0; i < grid; ++i) avg += (double)h[i];
+                    avg /= grid;
+                    printf("%-6d %-4d %-4d %-7d %-6d | %8.1f   (ideal %d)%s\n", N, a_mn, b_mn, spread, grid, avg / (iters * per), N / 2,
+                           h[0] < 0 ? "  TIMEOUT" : "");
+                }
+}
+
+// ---- (2) TMA streaming rate ---------------------------------------------------------------------
+__global__ void __launch_bounds__(64) k_tma_rate(const __grid_constant__ CUtensorMap tm, int slots, int boxes_per_slot, int jobs, int rows_total,
+                                                 int distinct, long long* cycles) {
+    extern __shared__ uint8_t raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t full[16], empty[16];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < slots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        fence_barrier_init();
+    }
+    __syncthreads();
+    const int slot_bytes = boxes_per_slot * 16384;
+    const int ntiles = rows_total / 128;
+    if (uniform_warp_idx() == 0 && elect_one()) {           // producer
+        uint32_t stage = 0, phase = 0;
+        for (int j = 0; j < jobs; ++j) {
+            if (!mbar_wait(&empty[stage], phase ^ 1, 1u << 22)) break;
+            mbar_arrive_expect_tx(&full[stage], slot_bytes);
+            const int tile = distinct ? (int)((blockIdx.x * 7 + j / 6) % ntiles) : (j / 6) % ntiles;
+            for (int b = 0; b < boxes_per_slot; ++b)
+                tma_load_2d(smem + stage * slot_bytes + b * 16384, &tm, &full[stage], ((j % 6) * boxes_per_slot + b) * 64 % 768, tile * 128);
+            if (++stage == (uint32_t)slots) { stage = 0; phase ^= 1; }
+        }
+    } else if (uniform_warp_idx() == 1 && elect_one()) {   // consumer: wait + release
+        uint32_t stage = 0, phase = 0;
+        const long long t0 = clock64();
+        bool ok = true;
+        for (int j = 0; j < jobs && ok; ++j) {
+            ok = mbar_wait(&full[stage], phase, 1u << 22);
+            mbar_arrive(&empty[stage]);
+            if (++stage == (uint32_t)slots) { stage = 0; phase ^= 1; }
+        }
+        cycles[blockIdx.x] = ok ? clock64() - t0 : -1;
+    }
+}
+
+static void run_tma() {
+    const int rows = 4096, cols = 768;
+    __half* d;
+    CK(cudaMalloc(&d, (size_t)rows * cols * 2));
+    CK(cudaMemset(d, 0, (size_t)rows * cols * 2));
+    CUtensorMap tm;
+    if (!make_tmap_2d_sw128(&tm, d, rows, cols, 128, 0)) { printf("tmap failed\n"); exit(2); }
+    long long* cyc;
+    CK(cudaMalloc(&cyc, 148 * 8));
+    CK(cudaFuncSetAttribute(k_tma_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    printf("%-6s %-6s %-9s %-9s | bytes/clk/SM   aggregate TB/s (at measured SM clock)\n", "grid", "slots", "slotKB", "distinct");
+    int clk_khz = 0;
+    cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, 0);
+    for (int grid : {1, 32, 64, 128, 148})
+        for (int cfg = 0; cfg < 4; ++cfg)
+            for (int distinct = 0; distinct < 2; ++distinct) {
+                const int slots = cfg == 0 ? 3 : cfg == 1 ? 6 : cfg == 2 ? 6 : 12;
+                const int bps = cfg == 0 ? 2 : cfg == 1 ? 2 : 1;
+                if (slots * bps * 16384 > 200 * 1024) continue;
+                const int jobs = 600;
+                CK(cudaMemset(cyc, 0, 148 * 8));
+                k_tma_rate<<<grid, 64, 220 * 1024>>>(tm, slots, bps, jobs, rows, distinct, cyc);
+                cudaError_t e = cudaDeviceSynchronize();
+                if (e != cudaSuccess) { printf("CUDA ERROR %s\n", cudaGetErrorString(e)); exit(3); }
+                long long h[148];
+                CK(cudaMemcpy(h, cyc, grid * 8, cudaMemcpyDeviceToHost));
+                double avg = 0; bool to = false;
+                for (int i = 0; i < grid; ++i) { avg += (double)h[i]; to |= h[i] < 0; }
+                avg /= grid;
+                const double bpc = (double)jobs * bps * 16384 / avg;
+                printf("%-6d %-6d %-9d %-9d | %8.1f        %6.2f%s\n", grid, slots, bps * 16, distinct, bpc, bpc * grid * clk_khz * 1e3 / 1e12,
+                       to ? "  TIMEOUT" : "");
+                fflush(stdout);
+            }
+}
+
+int main(int argc, char** argv) {
+    if (argc >= 2 && !strcmp(argv[1], "mma")) { run_mma(); return 0; }
+    if (argc >= 2 && !strcmp(argv[1], "tma")) { run_tma(); return 0; }
+    printf("usage: tc_bench mma | tma\n");
+    return 64;
+}
