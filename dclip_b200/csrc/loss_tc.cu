@@ -19,8 +19,10 @@
 //   softmax_row + softmax_col = p_ij (1/rowsum_i + 1/colsum_j).
 // Valid while 2*log2e/tau stays inside the fp32 exponent range: tau >= 0.025 (reference: 0.05).
 //
-// Warps: 0 = TMA producer, 1 = MMA issuer (+ TMEM alloc), 2..5 = epilogue (one TMEM lane quadrant
-// each).  Pipelines: 3-slot ring of 32 KB (two 128x64 boxes) between TMA and MMA; S double-buffered
+// Warps: 0-2 = TMA producers, one per ring slot (a single thread needs ~650 cycles per
+// wait/expect_tx/issue round trip — measured with tools/tc_bench — so one producer cannot feed the
+// MMAs), 3 = MMA issuer (+ TMEM alloc), 4..7 = epilogue (one TMEM lane quadrant each).
+// Pipelines: 3-slot ring of 32 KB (two 128x64 boxes) between TMA and MMA; S double-buffered
 // MMA<->epilogue; G double-buffered epilogue<->MMA.  Phase 1 of tile t+1 is issued before phase 2 of
 // tile t so the tensor pipe works while the epilogue of tile t runs.
 #include "common.cuh"
@@ -37,7 +39,7 @@ constexpr int kBoxBytes = TJ * 128;    // 128 rows x 64 fp16 = 16 KB
 constexpr int kSlotBytes = 2 * kBoxBytes;
 constexpr int kXBoxBytes = NI * 128;   // 64 rows x 64 fp16 = 8 KB
 constexpr int kGBytes = TJ * 128;      // G tile: 128 j rows x 64 i fp16 = 16 KB
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 256;        // warps 0-2: TMA producers (one ring slot each), 3: MMA issuer, 4-7: epilogue
 constexpr int kAccCols = 384;          // S buffers live at columns 384 and 448
 constexpr float kGScaleLog2 = 13.0f;   // G stored as fp16 * 2^13 (softmax sums <= 2 -> <= 16384)
 constexpr uint32_t kSpin = 1u << 24;   // bounded waits: a protocol bug times out instead of hanging
@@ -101,7 +103,7 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
         mbar_init(x_full, 1); mbar_init(acc_full, 1);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_ptr, 512);
+    if (warp == 3) tmem_alloc(tmem_ptr, 512);
     fence_before_thread_sync();
     __syncthreads();
     if (kC > 1) cluster_sync_all();      // peers' barriers are initialised before anyone multicasts
@@ -110,40 +112,45 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
     bool ok = true;
 
     if (T > 0) {
-        if (warp == 0) {
-            // ===================== TMA producer =====================
+        if (warp < kSlots) {
+            // ===================== TMA producers: warp w owns ring slot w =====================
             if (elect_one()) {
-                tma_prefetch_desc(tmx);
                 tma_prefetch_desc(tmy);
-                mbar_arrive_expect_tx(x_full, (uint32_t)(nkb * kXBoxBytes));
-                for (int kb = 0; kb < nkb; ++kb) tma_load_2d(xs + (size_t)kb * kXBoxBytes, tmx, x_full, kb * 64, (int32_t)row0);
-                Pipe p;
-                auto load_tile = [&](int t) {
-                    const int32_t j0 = (int32_t)((t_begin + t) * TJ);
-                    for (int s = 0; s < NS && ok; ++s) {
-                        ok = mbar_wait(&empty[p.stage], p.phase ^ 1, kSpin);
-                        uint8_t* dst = ring + (size_t)p.stage * kSlotBytes;
-                        mbar_arrive_expect_tx(&full[p.stage], kSlotBytes);
-                        if (kC == 1) {
-                            tma_load_2d(dst, tmy, &full[p.stage], (2 * s) * 64, j0);
-                            tma_load_2d(dst + kBoxBytes, tmy, &full[p.stage], (2 * s + 1) * 64, j0);
-                        } else if (kC == 2) {        // CTA r loads box r of the slot for both CTAs
-                            tma_load_2d_mcast(dst + crank * kBoxBytes, tmy, &full[p.stage], (2 * s + (int)crank) * 64, j0, kMask);
-                        } else {                     // kC == 4: CTA r loads rows [64 (r&1), +64) of box r>>1
-                            const int box = (int)(crank >> 1), half = (int)(crank & 1);
-                            tma_load_2d_mcast(dst + box * kBoxBytes + half * (kBoxBytes / 2), tmh, &full[p.stage], (2 * s + box) * 64,
-                                              j0 + half * 64, kMask);
-                        }
-                        p.advance();
+                if (warp == 0) {
+                    tma_prefetch_desc(tmx);
+                    mbar_arrive_expect_tx(x_full, (uint32_t)(nkb * kXBoxBytes));
+                    for (int kb = 0; kb < nkb; ++kb) tma_load_2d(xs + (size_t)kb * kXBoxBytes, tmx, x_full, kb * 64, (int32_t)row0);
+                }
+                // Job q (in MMA consumption order) uses slot q % kSlots.  Order: P1(0), then per tile t:
+                // P1(t+1) [if any], P2(t) [bwd].  Both phases of (tile, s) load the same two boxes.
+                const int njobs = kBwd ? 2 * NS * T : NS * T;
+                uint8_t* dst = ring + (size_t)warp * kSlotBytes;
+                uint32_t phase = 0;
+                for (int q = warp; q < njobs && ok; q += kSlots, phase ^= 1) {
+                    int tile, sidx;
+                    if (!kBwd) { tile = q / NS; sidx = q - tile * NS; }
+                    else if (q < NS) { tile = 0; sidx = q; }
+                    else {
+                        const int qq = q - NS, blk = min(qq / (2 * NS), T - 1), r = qq - blk * 2 * NS;
+                        if (blk < T - 1 && r < NS) { tile = blk + 1; sidx = r; }
+                        else { tile = blk; sidx = blk < T - 1 ? r - NS : r; }
                     }
-                };
-                load_tile(0);
-                for (int t = 0; t < T && ok; ++t) {
-                    if (t + 1 < T) load_tile(t + 1);
-                    if (kBwd && ok) load_tile(t);
+                    const int32_t j0 = (int32_t)((t_begin + tile) * TJ);
+                    ok = mbar_wait(&empty[warp], phase ^ 1, kSpin);
+                    mbar_arrive_expect_tx(&full[warp], kSlotBytes);
+                    if (kC == 1) {
+                        tma_load_2d(dst, tmy, &full[warp], (2 * sidx) * 64, j0);
+                        tma_load_2d(dst + kBoxBytes, tmy, &full[warp], (2 * sidx + 1) * 64, j0);
+                    } else if (kC == 2) {        // CTA r loads box r of the slot for both CTAs
+                        tma_load_2d_mcast(dst + crank * kBoxBytes, tmy, &full[warp], (2 * sidx + (int)crank) * 64, j0, kMask);
+                    } else {                     // kC == 4: CTA r loads rows [64 (r&1), +64) of box r>>1
+                        const int box = (int)(crank >> 1), half = (int)(crank & 1);
+                        tma_load_2d_mcast(dst + box * kBoxBytes + half * (kBoxBytes / 2), tmh, &full[warp], (2 * sidx + box) * 64,
+                                          j0 + half * 64, kMask);
+                    }
                 }
             }
-        } else if (warp == 1) {
+        } else if (warp == 3) {
             // ===================== MMA issuer =====================
             if (elect_one()) {
                 const uint32_t idesc1 = make_idesc_f16(128, NI, kFmtF16, 0, 0);
@@ -307,7 +314,7 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
                 }
             }
         }
-    } else if (warp >= 2) {
+    } else if (warp >= 4) {
         // empty column range (only possible with an over-split grid): contribute zeros
         const int et = (warp & 3) * 32 + lane;
         if (!kBwd) {
@@ -323,7 +330,7 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
     fence_before_thread_sync();
     __syncthreads();
     if (kC > 1) cluster_sync_all();      // nobody leaves while a peer may still multicast into / signal this CTA
-    if (warp == 1) tmem_dealloc(tmem, 512);
+    if (warp == 3) tmem_dealloc(tmem, 512);
 }
 
 // lse[i] = 1/tau + ln(sum over splits of the partial row sums)
@@ -375,12 +382,12 @@ bool tc_loss_shape_ok(int64_t d, float temperature) {
     return d % 128 == 0 && d >= 128 && d <= 768 && temperature >= 0.025f;
 }
 
-static int tc_cluster_size() {   // DCLIP_TC_CLUSTER = 1 | 2 | 4 (default 2)
+static int tc_cluster_size() {   // DCLIP_TC_CLUSTER = 1 | 2 | 4 (default 1: multicast measured no gain, the kernel is not L2-bound)
     static int c = 0;
     if (!c) {
         const char* e = getenv("DCLIP_TC_CLUSTER");
-        c = e ? atoi(e) : 2;
-        if (c != 1 && c != 2 && c != 4) c = 2;
+        c = e ? atoi(e) : 1;
+        if (c != 1 && c != 2 && c != 4) c = 1;
     }
     return c;
 }

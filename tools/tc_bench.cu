@@ -92,7 +92,7 @@ static void run_mma() {
 
 // ---- (2) TMA streaming rate ---------------------------------------------------------------------
 __global__ void __launch_bounds__(64) k_tma_rate(const __grid_constant__ CUtensorMap tm, int slots, int boxes_per_slot, int jobs, int rows_total,
-                                                 int distinct, long long* cycles) {
+                                                 int distinct, int mode, long long* cycles) {
     extern __shared__ uint8_t raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
     __shared__ uint64_t full[16], empty[16];
@@ -107,10 +107,13 @@ __global__ void __launch_bounds__(64) k_tma_rate(const __grid_constant__ CUtenso
         uint32_t stage = 0, phase = 0;
         for (int j = 0; j < jobs; ++j) {
             if (!mbar_wait(&empty[stage], phase ^ 1, 1u << 22)) break;
-            mbar_arrive_expect_tx(&full[stage], slot_bytes);
-            const int tile = distinct ? (int)((blockIdx.x * 7 + j / 6) % ntiles) : (j / 6) % ntiles;
-            for (int b = 0; b < boxes_per_slot; ++b)
-                tma_load_2d(smem + stage * slot_bytes + b * 16384, &tm, &full[stage], ((j % 6) * boxes_per_slot + b) * 64 % 768, tile * 128);
+            if (mode == 1) { mbar_arrive(&full[stage]); }     // handshake only, no TMA
+            else {
+                mbar_arrive_expect_tx(&full[stage], slot_bytes);
+                const int tile = distinct ? (int)((blockIdx.x * 7 + j / 6) % ntiles) : (j / 6) % ntiles;
+                for (int b = 0; b < boxes_per_slot; ++b)
+                    tma_load_2d(smem + stage * slot_bytes + b * 16384, &tm, &full[stage], ((j % 6) * boxes_per_slot + b) * 64 % 768, tile * 128);
+            }
             if (++stage == (uint32_t)slots) { stage = 0; phase ^= 1; }
         }
     } else if (uniform_warp_idx() == 1 && elect_one()) {   // consumer: wait + release
@@ -139,27 +142,29 @@ static void run_tma() {
     printf("%-6s %-6s %-9s %-9s | bytes/clk/SM   aggregate TB/s (at measured SM clock)\n", "grid", "slots", "slotKB", "distinct");
     int clk_khz = 0;
     cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, 0);
-    for (int grid : {1, 32, 64, 128, 148})
-        for (int cfg = 0; cfg < 4; ++cfg)
-            for (int distinct = 0; distinct < 2; ++distinct) {
-                const int slots = cfg == 0 ? 3 : cfg == 1 ? 6 : cfg == 2 ? 6 : 12;
-                const int bps = cfg == 0 ? 2 : cfg == 1 ? 2 : 1;
-                if (slots * bps * 16384 > 200 * 1024) continue;
-                const int jobs = 600;
-                CK(cudaMemset(cyc, 0, 148 * 8));
-                k_tma_rate<<<grid, 64, 220 * 1024>>>(tm, slots, bps, jobs, rows, distinct, cyc);
-                cudaError_t e = cudaDeviceSynchronize();
-                if (e != cudaSuccess) { printf("CUDA ERROR %s\n", cudaGetErrorString(e)); exit(3); }
-                long long h[148];
-                CK(cudaMemcpy(h, cyc, grid * 8, cudaMemcpyDeviceToHost));
-                double avg = 0; bool to = false;
-                for (int i = 0; i < grid; ++i) { avg += (double)h[i]; to |= h[i] < 0; }
-                avg /= grid;
-                const double bpc = (double)jobs * bps * 16384 / avg;
-                printf("%-6d %-6d %-9d %-9d | %8.1f        %6.2f%s\n", grid, slots, bps * 16, distinct, bpc, bpc * grid * clk_khz * 1e3 / 1e12,
-                       to ? "  TIMEOUT" : "");
-                fflush(stdout);
-            }
+    for (int grid : {1, 148})
+        for (int cfg = 0; cfg < 7; ++cfg) {
+            // cfg: slots, boxes per slot, mode
+            const int slots_[7] = {3, 6, 12, 3, 2, 6, 3};
+            const int bps_[7] = {2, 1, 1, 4, 6, 2, 2};
+            const int mode_[7] = {0, 0, 0, 0, 0, 0, 1};
+            const int slots = slots_[cfg], bps = bps_[cfg], mode = mode_[cfg], distinct = 0;
+            if (slots * bps * 16384 > 200 * 1024) continue;
+            const int jobs = 600;
+            CK(cudaMemset(cyc, 0, 148 * 8));
+            k_tma_rate<<<grid, 64, 220 * 1024>>>(tm, slots, bps, jobs, rows, distinct, mode, cyc);
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) { printf("CUDA ERROR %s\n", cudaGetErrorString(e)); exit(3); }
+            long long h[148];
+            CK(cudaMemcpy(h, cyc, grid * 8, cudaMemcpyDeviceToHost));
+            double avg = 0; bool to = false;
+            for (int i = 0; i < grid; ++i) { avg += (double)h[i]; to |= h[i] < 0; }
+            avg /= grid;
+            const double bpc = (double)jobs * bps * 16384 / avg;
+            printf("grid %-4d slots %-3d slotKB %-4d mode %d | %7.1f cycles/job  %7.1f B/clk/SM  %6.2f TB/s%s\n", grid, slots, bps * 16, mode,
+                   avg / jobs, bpc, bpc * grid * clk_khz * 1e3 / 1e12, to ? "  TIMEOUT" : "");
+            fflush(stdout);
+        }
 }
 
 int main(int argc, char** argv) {
