@@ -19,11 +19,10 @@
 //   softmax_row + softmax_col = p_ij (1/rowsum_i + 1/colsum_j).
 // Valid while 2*log2e/tau stays inside the fp32 exponent range: tau >= 0.025 (reference: 0.05).
 //
-// Warps: 0-5 = TMA producers, one per ring box (a single thread needs ~650 cycles per
+// Warps: 0-2 = TMA producers, one per ring slot (a single thread needs ~650 cycles per
 // wait/expect_tx/issue round trip — measured with tools/tc_bench — so one producer cannot feed the
-// MMAs), 6 = MMA issuer (+ TMEM alloc), 7..10 = epilogue (one TMEM lane quadrant each).
-// Pipelines: ring of six 16 KB boxes (128 rows x 64 columns) between TMA and MMA — phase 1 consumes
-// and releases single boxes, phase 2 aligned pairs (one 128-column slice); S double-buffered
+// MMAs), 3 = MMA issuer (+ TMEM alloc), 4..7 = epilogue (one TMEM lane quadrant each).
+// Pipelines: 3-slot ring of 32 KB (two 128x64 boxes) between TMA and MMA; S double-buffered
 // MMA<->epilogue; G double-buffered epilogue<->MMA.  Phase 1 of tile t+1 is issued before phase 2 of
 // tile t so the tensor pipe works while the epilogue of tile t runs.
 #include "common.cuh"
@@ -35,13 +34,12 @@ using namespace tc;
 
 constexpr int NI = 64;                 // X rows per CTA  (MMA N)
 constexpr int TJ = 128;                // Y rows per tile (MMA M in phase 1, K in phase 2)
-constexpr int kBoxes = 6;              // ring of 16 KB boxes; pairs (2p, 2p+1) form one 128-column slice
+constexpr int kSlots = 3;
 constexpr int kBoxBytes = TJ * 128;    // 128 rows x 64 fp16 = 16 KB
+constexpr int kSlotBytes = 2 * kBoxBytes;
 constexpr int kXBoxBytes = NI * 128;   // 64 rows x 64 fp16 = 8 KB
 constexpr int kGBytes = TJ * 128;      // G tile: 128 j rows x 64 i fp16 = 16 KB
-constexpr int kProducerWarps = kBoxes; // one TMA producer warp per ring box
-constexpr int kMmaWarp = kProducerWarps;
-constexpr int kTcThreads = (kProducerWarps + 1 + 4) * 32;   // 6 producers, 1 MMA issuer, 4 epilogue warps
+constexpr int kTcThreads = 256;        // warps 0-2: TMA producers (one ring slot each), 3: MMA issuer, 4-7: epilogue
 constexpr int kAccCols = 384;          // S buffers live at columns 384 and 448
 constexpr float kGScaleLog2 = 13.0f;   // G stored as fp16 * 2^13 (softmax sums <= 2 -> <= 16384)
 constexpr uint32_t kSpin = 1u << 24;   // bounded waits: a protocol bug times out instead of hanging
@@ -49,34 +47,38 @@ constexpr uint32_t kSpin = 1u << 24;   // bounded waits: a protocol bug times ou
 struct Pipe {
     uint32_t stage = 0, phase = 0;
     __device__ __forceinline__ void advance() {
-        if (++stage == kBoxes) { stage = 0; phase ^= 1; }
+        if (++stage == kSlots) { stage = 0; phase ^= 1; }
     }
 };
 
-// (A thread-block-cluster variant that TMA-multicasts the Y boxes to 2 or 4 CTAs was built and
-// measured: no gain — the kernel is bound by TMA round-trip latency and MMA operand fetch, not by
-// L2 -> SM bandwidth (tools/tc_bench: 31 TB/s aggregate on L2 hits) — so it was dropped.)
-template <bool kBwd>
+// kC = thread-block cluster size along the row-block axis.  The kC CTAs of a cluster own different
+// row blocks but walk the same Y tiles, so each loads 1/kC of every ring slot and multicasts it to
+// all of them: L2 -> SM traffic per CTA drops by kC (the kernel is otherwise bound by it).
+template <bool kBwd, int kC>
 __global__ void __launch_bounds__(kTcThreads, 1)
 k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CUtensorMap tmy0,
-             const __grid_constant__ CUtensorMap tmx1, const __grid_constant__ CUtensorMap tmy1, const TcArgs a) {
+             const __grid_constant__ CUtensorMap tmx1, const __grid_constant__ CUtensorMap tmy1,
+             const __grid_constant__ CUtensorMap tmh0, const __grid_constant__ CUtensorMap tmh1, const TcArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int side = blockIdx.z;
     const CUtensorMap* tmx = side ? &tmx1 : &tmx0;
     const CUtensorMap* tmy = side ? &tmy1 : &tmy0;
+    const CUtensorMap* tmh = side ? &tmh1 : &tmh0;      // same matrix as tmy, 64-row boxes (kC == 4)
     const TcSide S = a.s[side];
+    const uint32_t crank = kC > 1 ? cluster_ctarank() : 0;
+    constexpr uint16_t kMask = (uint16_t)((1u << kC) - 1);
     const int d = (int)a.d;
     const int nkb = d / 64;            // 64-column boxes along K
     const int NS = d / 128;            // ring slots per phase (= accumulator d-blocks)
 
     uint8_t* xs = smem;                                   // resident X_I: nkb boxes of 8 KB
-    uint8_t* ring = xs + (size_t)nkb * kXBoxBytes;        // kBoxes x 16 KB
-    uint8_t* gs = ring + kBoxes * kBoxBytes;              // 2 x 16 KB (bwd)
+    uint8_t* ring = xs + (size_t)nkb * kXBoxBytes;        // kSlots x 32 KB
+    uint8_t* gs = ring + kSlots * kSlotBytes;             // 2 x 16 KB (bwd)
     uint8_t* tail = gs + (kBwd ? 2 * kGBytes : 0);
-    uint64_t* full = reinterpret_cast<uint64_t*>(tail);   // [kBoxes]
-    uint64_t* empty = full + kBoxes;                      // [kBoxes]
-    uint64_t* s_full = empty + kBoxes;                    // [2]
+    uint64_t* full = reinterpret_cast<uint64_t*>(tail);   // [kSlots]
+    uint64_t* empty = full + kSlots;                      // [kSlots]
+    uint64_t* s_full = empty + kSlots;                    // [2]
     uint64_t* s_empty = s_full + 2;                       // [2]
     uint64_t* g_full = s_empty + 2;                       // [2]
     uint64_t* g_empty = g_full + 2;                       // [2]
@@ -93,7 +95,7 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
     const int T = (int)(t_end - t_begin);
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kBoxes; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < kSlots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kC); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 128);
             mbar_init(&g_full[i], 128); mbar_init(&g_empty[i], 1);
@@ -101,16 +103,17 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
         mbar_init(x_full, 1); mbar_init(acc_full, 1);
         fence_barrier_init();
     }
-    if (warp == kMmaWarp) tmem_alloc(tmem_ptr, 512);
+    if (warp == 3) tmem_alloc(tmem_ptr, 512);
     fence_before_thread_sync();
     __syncthreads();
+    if (kC > 1) cluster_sync_all();      // peers' barriers are initialised before anyone multicasts
     fence_after_thread_sync();
     const uint32_t tmem = *tmem_ptr;
     bool ok = true;
 
     if (T > 0) {
-        if (warp < kProducerWarps) {
-            // ===================== TMA producers: warp w owns ring box w =====================
+        if (warp < kSlots) {
+            // ===================== TMA producers: warp w owns ring slot w =====================
             if (elect_one()) {
                 tma_prefetch_desc(tmy);
                 if (warp == 0) {
@@ -118,29 +121,36 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
                     mbar_arrive_expect_tx(x_full, (uint32_t)(nkb * kXBoxBytes));
                     for (int kb = 0; kb < nkb; ++kb) tma_load_2d(xs + (size_t)kb * kXBoxBytes, tmx, x_full, kb * 64, (int32_t)row0);
                 }
-                // Box job q (in MMA consumption order) uses ring box q % kBoxes; jobs (2p, 2p+1) are the two
-                // 64-column boxes of slice p.  Slice order: P1(0), then per tile t: P1(t+1) [if any], P2(t)
-                // [bwd].  Both phases of (tile, slice) load the same boxes.
-                const int njobs = (kBwd ? 2 * NS * T : NS * T) * 2;
-                uint8_t* dst = ring + (size_t)warp * kBoxBytes;
+                // Job q (in MMA consumption order) uses slot q % kSlots.  Order: P1(0), then per tile t:
+                // P1(t+1) [if any], P2(t) [bwd].  Both phases of (tile, s) load the same two boxes.
+                const int njobs = kBwd ? 2 * NS * T : NS * T;
+                uint8_t* dst = ring + (size_t)warp * kSlotBytes;
                 uint32_t phase = 0;
-                for (int q = warp; q < njobs && ok; q += kBoxes, phase ^= 1) {
-                    const int pq = q >> 1, h = q & 1;
+                for (int q = warp; q < njobs && ok; q += kSlots, phase ^= 1) {
                     int tile, sidx;
-                    if (!kBwd) { tile = pq / NS; sidx = pq - tile * NS; }
-                    else if (pq < NS) { tile = 0; sidx = pq; }
+                    if (!kBwd) { tile = q / NS; sidx = q - tile * NS; }
+                    else if (q < NS) { tile = 0; sidx = q; }
                     else {
-                        const int qq = pq - NS, blk = min(qq / (2 * NS), T - 1), r = qq - blk * 2 * NS;
+                        const int qq = q - NS, blk = min(qq / (2 * NS), T - 1), r = qq - blk * 2 * NS;
                         if (blk < T - 1 && r < NS) { tile = blk + 1; sidx = r; }
                         else { tile = blk; sidx = blk < T - 1 ? r - NS : r; }
                     }
                     const int32_t j0 = (int32_t)((t_begin + tile) * TJ);
                     ok = mbar_wait(&empty[warp], phase ^ 1, kSpin);
-                    mbar_arrive_expect_tx(&full[warp], kBoxBytes);
-                    tma_load_2d(dst, tmy, &full[warp], (2 * sidx + h) * 64, j0);
+                    mbar_arrive_expect_tx(&full[warp], kSlotBytes);
+                    if (kC == 1) {
+                        tma_load_2d(dst, tmy, &full[warp], (2 * sidx) * 64, j0);
+                        tma_load_2d(dst + kBoxBytes, tmy, &full[warp], (2 * sidx + 1) * 64, j0);
+                    } else if (kC == 2) {        // CTA r loads box r of the slot for both CTAs
+                        tma_load_2d_mcast(dst + crank * kBoxBytes, tmy, &full[warp], (2 * sidx + (int)crank) * 64, j0, kMask);
+                    } else {                     // kC == 4: CTA r loads rows [64 (r&1), +64) of box r>>1
+                        const int box = (int)(crank >> 1), half = (int)(crank & 1);
+                        tma_load_2d_mcast(dst + box * kBoxBytes + half * (kBoxBytes / 2), tmh, &full[warp], (2 * sidx + box) * 64,
+                                          j0 + half * 64, kMask);
+                    }
                 }
             }
-        } else if (warp == kMmaWarp) {
+        } else if (warp == 3) {
             // ===================== MMA issuer =====================
             if (elect_one()) {
                 const uint32_t idesc1 = make_idesc_f16(128, NI, kFmtF16, 0, 0);
@@ -156,15 +166,18 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
                     ok = ok && mbar_wait(&s_empty[b], ((t >> 1) & 1) ^ 1, kSpin);
                     fence_after_thread_sync();
                     const uint32_t dcol = tmem + kAccCols + b * NI;
-                    for (int kb = 0; kb < 2 * NS && ok; ++kb) {          // one 64-column box per job
+                    for (int s = 0; s < NS && ok; ++s) {
                         ok = mbar_wait(&full[p.stage], p.phase, kSpin);
                         fence_after_thread_sync();
-                        const uint64_t da0 = smem_desc(hiK, ring_addr + p.stage * kBoxBytes);
-                        const uint64_t db0 = smem_desc(hiK, xs_addr + kb * kXBoxBytes);
+                        const uint64_t da0 = smem_desc(hiK, ring_addr + p.stage * kSlotBytes);
+                        const uint64_t db0 = smem_desc(hiK, xs_addr + (2 * s) * kXBoxBytes);
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)                  // +32 B per K step (>>4 encoded)
-                            umma_f16(dcol, da0 + (uint64_t)(ks * 2), db0 + (uint64_t)(ks * 2), idesc1, (kb | ks) != 0);
-                        umma_commit(&empty[p.stage]);
+                        for (int h = 0; h < 2; ++h)
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks)      // +32 B per K step, next box at +16 KB (A) / +8 KB (B); >>4 encoded
+                                umma_f16(dcol, da0 + (uint64_t)(h * (kBoxBytes >> 4) + ks * 2), db0 + (uint64_t)(h * (kXBoxBytes >> 4) + ks * 2), idesc1,
+                                         (s | h | ks) != 0);
+                        if (kC == 1) umma_commit(&empty[p.stage]); else umma_commit_mcast(&empty[p.stage], kMask);
                         p.advance();
                     }
                     umma_commit(&s_full[b]);
@@ -174,18 +187,15 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
                     ok = ok && mbar_wait(&g_full[b], (t >> 1) & 1, kSpin);
                     fence_after_thread_sync();
                     const uint32_t gaddr = gs_addr + b * kGBytes;
-                    for (int s = 0; s < NS && ok; ++s) {                 // one aligned box pair (128 d columns) per job
-                        const uint32_t st0 = p.stage;
-                        ok = mbar_wait(&full[st0], p.phase, kSpin) && mbar_wait(&full[st0 + 1], p.phase, kSpin);
+                    for (int s = 0; s < NS && ok; ++s) {
+                        ok = mbar_wait(&full[p.stage], p.phase, kSpin);
                         fence_after_thread_sync();
-                        const uint64_t da0 = smem_desc(hiA2, ring_addr + st0 * kBoxBytes);
+                        const uint64_t da0 = smem_desc(hiA2, ring_addr + p.stage * kSlotBytes);
                         const uint64_t db0 = smem_desc(hiB2, gaddr);
 #pragma unroll
                         for (int ks = 0; ks < 8; ++ks)          // 16 j per step = two 8-row groups = +2048 B
                             umma_f16(tmem + s * NI, da0 + (uint64_t)(ks * 128), db0 + (uint64_t)(ks * 128), idesc2, (t | ks) != 0);
-                        umma_commit(&empty[st0]);
-                        umma_commit(&empty[st0 + 1]);
-                        p.advance();
+                        if (kC == 1) umma_commit(&empty[p.stage]); else umma_commit_mcast(&empty[p.stage], kMask);
                         p.advance();
                     }
                     umma_commit(&g_empty[b]);
@@ -304,7 +314,7 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
                 }
             }
         }
-    } else if (warp > kMmaWarp) {
+    } else if (warp >= 4) {
         // empty column range (only possible with an over-split grid): contribute zeros
         const int et = (warp & 3) * 32 + lane;
         if (!kBwd) {
@@ -319,7 +329,8 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
     if (!ok && lane == 0 && a.error_flag) atomicExch(a.error_flag, 1);
     fence_before_thread_sync();
     __syncthreads();
-    if (warp == kMmaWarp) tmem_dealloc(tmem, 512);
+    if (kC > 1) cluster_sync_all();      // nobody leaves while a peer may still multicast into / signal this CTA
+    if (warp == 3) tmem_dealloc(tmem, 512);
 }
 
 // lse[i] = 1/tau + ln(sum over splits of the partial row sums)
@@ -371,8 +382,19 @@ bool tc_loss_shape_ok(int64_t d, float temperature) {
     return d % 128 == 0 && d >= 128 && d <= 768 && temperature >= 0.025f;
 }
 
+static int tc_cluster_size() {   // DCLIP_TC_CLUSTER = 1 | 2 | 4 (default 1: multicast measured no gain, the kernel is not L2-bound)
+    static int c = 0;
+    if (!c) {
+        const char* e = getenv("DCLIP_TC_CLUSTER");
+        c = e ? atoi(e) : 1;
+        if (c != 1 && c != 2 && c != 4) c = 1;
+    }
+    return c;
+}
+
 int tc_nsplit(int64_t m, int64_t n, int nsides) {
-    const int64_t row_ctas = ceil_div(m, NI) * nsides;
+    const int C = tc_cluster_size();
+    const int64_t row_ctas = ceil_div(ceil_div(m, NI), C) * C * nsides;
     const int64_t ntiles = ceil_div(n, TJ);
     int64_t want = sm_count() / (row_ctas > 0 ? row_ctas : 1);
     if (want < 1) want = 1;
@@ -381,7 +403,7 @@ int tc_nsplit(int64_t m, int64_t n, int nsides) {
 }
 
 static size_t tc_smem_bytes(int64_t d, bool bwd) {
-    return 1024 + (size_t)(d / 64) * kXBoxBytes + (size_t)kBoxes * kBoxBytes + (bwd ? 2 * kGBytes : 0) + 512;
+    return 1024 + (size_t)(d / 64) * kXBoxBytes + (size_t)kSlots * kSlotBytes + (bwd ? 2 * kGBytes : 0) + 512;
 }
 
 static int* tc_error_flag() {   // one device int per device, lazily allocated, never freed
@@ -401,25 +423,39 @@ int launch_infonce_tc(bool bwd, int nsides, const void* const x[2], const void* 
                       cudaStream_t st) {
     if (!device_is_sm100()) return fail(DCLIP_ERR_ARCH, "tensor path needs an sm_100 device");
     TcArgs a = args_in;
-    CUtensorMap tmx[2], tmy[2];
+    CUtensorMap tmx[2], tmy[2], tmh[2];
     for (int s = 0; s < 2; ++s) {
         const int src = s < nsides ? s : 0;
         if (!make_tmap_2d_sw128(&tmx[s], x[src], (uint64_t)a.m, (uint64_t)a.d, NI, 0) ||
-            !make_tmap_2d_sw128(&tmy[s], y[src], (uint64_t)a.n, (uint64_t)a.d, TJ, 0))
+            !make_tmap_2d_sw128(&tmy[s], y[src], (uint64_t)a.n, (uint64_t)a.d, TJ, 0) ||
+            !make_tmap_2d_sw128(&tmh[s], y[src], (uint64_t)a.n, (uint64_t)a.d, TJ / 2, 0))
             return fail(DCLIP_ERR_CUDA, "cuTensorMapEncodeTiled failed (m=%lld n=%lld d=%lld)", (long long)a.m, (long long)a.n, (long long)a.d);
     }
     const int64_t ntiles = ceil_div(a.n, TJ);
     a.tiles_per_split = (int)ceil_div(ntiles, nsplit);
     a.error_flag = tc_error_flag();
     const size_t smem = tc_smem_bytes(a.d, bwd);
-    dim3 grid((unsigned)ceil_div(a.m, NI), (unsigned)nsplit, (unsigned)nsides);
+    const int C = tc_cluster_size();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(ceil_div(ceil_div(a.m, NI), C) * C), (unsigned)nsplit, (unsigned)nsides);
+    cfg.blockDim = dim3(kTcThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+#define DCLIP_TC_LAUNCH(BWD, CL)                                                                                              \
+    do {                                                                                                                      \
+        DCLIP_CUDA_OK(cudaFuncSetAttribute(k_infonce_tc<BWD, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+        DCLIP_CUDA_OK(cudaLaunchKernelEx(&cfg, k_infonce_tc<BWD, CL>, tmx[0], tmy[0], tmx[1], tmy[1], tmh[0], tmh[1], a));    \
+    } while (0)
     if (bwd) {
-        DCLIP_CUDA_OK(cudaFuncSetAttribute(k_infonce_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_infonce_tc<true><<<grid, kTcThreads, smem, st>>>(tmx[0], tmy[0], tmx[1], tmy[1], a);
+        if (C == 1) DCLIP_TC_LAUNCH(true, 1); else if (C == 2) DCLIP_TC_LAUNCH(true, 2); else DCLIP_TC_LAUNCH(true, 4);
     } else {
-        DCLIP_CUDA_OK(cudaFuncSetAttribute(k_infonce_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_infonce_tc<false><<<grid, kTcThreads, smem, st>>>(tmx[0], tmy[0], tmx[1], tmy[1], a);
+        if (C == 1) DCLIP_TC_LAUNCH(false, 1); else if (C == 2) DCLIP_TC_LAUNCH(false, 2); else DCLIP_TC_LAUNCH(false, 4);
     }
+#undef DCLIP_TC_LAUNCH
     DCLIP_LAUNCH_OK("k_infonce_tc");
     return DCLIP_OK;
 }
