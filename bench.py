@@ -43,6 +43,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=B_GLOBAL)
     ap.add_argument("--dim", type=int, default=DIM)
     ap.add_argument("--no-retrieval", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel/collective from Python instead of one CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -177,22 +178,32 @@ def main():
 
     host = [t.to(tdtype)[rank * m:(rank + 1) * m].contiguous().pin_memory() for t in synthetic.loss_inputs(B, d, seed=42)]
     resident = [t.to(dev) for t in host]
-    staging = [torch.empty_like(t) for t in resident]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
     launches_per_step = lib.dclip_distill_loss_launch_count(m, B, d, _lib.path_code(path), 1 if world > 1 else 0)
 
-    def step_resident():
+    def step_fn(s_img, s_txt, t_img, t_txt):
         if world == 1:
-            return L.distill_loss_fwd_bwd(*resident, temperature=TEMPERATURE, path=path)
-        return L.sharded_distill_loss_fwd_bwd(*resident, temperature=TEMPERATURE, path=path)
+            return L.distill_loss_fwd_bwd(s_img, s_txt, t_img, t_txt, temperature=TEMPERATURE, path=path)
+        return L.sharded_distill_loss_fwd_bwd(s_img, s_txt, t_img, t_txt, temperature=TEMPERATURE, path=path)
+
+    graphed = None
+    if not args.no_graph:
+        # the public API's CUDA-graph wrapper: one graph launch per step (kernels + NCCL collectives)
+        graphed = L.GraphedStep(step_fn, resident)
+        step_inputs = graphed.static_in           # the resident inputs ARE the graph's static inputs
+    else:
+        step_inputs = resident
+
+    def step_resident():
+        if graphed is not None:
+            graphed.graph.replay()
+            return graphed.static_out
+        return step_fn(*step_inputs)
 
     def step_e2e():
-        for dst, src in zip(staging, host):
-            dst.copy_(src, non_blocking=True)
-        if world == 1:
-            losses, _, _ = L.distill_loss_fwd_bwd(*staging, temperature=TEMPERATURE, path=path)
-        else:
-            losses, _, _ = L.sharded_distill_loss_fwd_bwd(*staging, temperature=TEMPERATURE, path=path)
+        for dst, src in zip(step_inputs, host):
+            dst.copy_(src, non_blocking=True)       # pinned host -> device, inside the timed region
+        losses = step_resident()[0]
         return losses.cpu()          # device->host read of the step's result
 
     def barrier():
@@ -248,6 +259,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": f"distill-loss fwd+bwd, global batch {B}, d={d}, tau={TEMPERATURE} (BASELINE configs[3])",
                        "global_batch": B, "dim": d, "rows_per_gpu": m, "path": path, "l2_flush": "256 MiB write between timed steps",
+                       "launch": "python" if args.no_graph else "cuda-graph (dclip_b200.losses.GraphedStep)",
                        "parallelism": f"dp{world} (batch-sharded, operand all-gather)" if world > 1 else "single GPU"},
             "clocks": clocks,
             "e2e": {"value": B / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,

@@ -19,7 +19,7 @@ from ._lib import check, dtype_code, path_code, ptr, require_cuda, stream_ptr, w
 
 __all__ = [
     "compute_contrastive_loss", "cosine_distillation_loss", "DistillationLoss", "distill_loss_fwd_bwd",
-    "sharded_distill_loss_fwd_bwd", "ShardedDistillationLoss", "CudaLossOps",
+    "sharded_distill_loss_fwd_bwd", "ShardedDistillationLoss", "CudaLossOps", "GraphedStep",
 ]
 
 
@@ -183,11 +183,11 @@ class CudaLossOps:
                                            ptr(inv), ptr(cos), stream_ptr(dev)), "loss_prep")
         return inv, cos
 
-    def rowlse(self, x_hat, y_all, temperature, row_offset, want_diag):
+    def rowlse(self, x_hat, y_all, temperature, row_offset, want_diag, out=None):
         dev = require_cuda(x_hat, y_all)
         m, d = x_hat.shape
         n = y_all.shape[0]
-        lse = torch.empty(m, dtype=torch.float32, device=dev)
+        lse = out if out is not None else torch.empty(m, dtype=torch.float32, device=dev)
         diag = torch.empty(m, dtype=torch.float32, device=dev) if want_diag else None
         ws = workspace(self.lib.dclip_infonce_rowlse_workspace_bytes(m, n, d, self.path), dev)
         with torch.cuda.device(dev):
@@ -218,9 +218,9 @@ class CudaLossOps:
                   "loss_grad_tail")
         return out
 
-    def partial_sums(self, lse_u, lse_v, diag, cos_img, cos_txt):
+    def partial_sums(self, lse_u, lse_v, diag, cos_img, cos_txt, out=None):
         dev = require_cuda(lse_u, lse_v, diag, cos_img, cos_txt)
-        out = torch.empty(3, dtype=torch.float32, device=dev)
+        out = out if out is not None else torch.empty(3, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             check(self.lib.dclip_loss_partial_sums(ptr(lse_u), ptr(lse_v), ptr(diag), ptr(cos_img), ptr(cos_txt),
                                                    lse_u.shape[0], ptr(out), stream_ptr(dev)), "loss_partial_sums")
@@ -249,28 +249,32 @@ def sharded_distill_loss_fwd_bwd(s_img, s_txt, t_img=None, t_txt=None, temperatu
     dev = s_img.device
 
     # (1) normalise local rows straight into this rank's slot of the gathered operand buffers
-    u_all = torch.empty((B, d), dtype=ops.op_torch_dtype, device=dev)
-    v_all = torch.empty((B, d), dtype=ops.op_torch_dtype, device=dev)
+    ops_all = torch.empty((2, B, d), dtype=ops.op_torch_dtype, device=dev)
+    u_all, v_all = ops_all[0], ops_all[1]
     u_loc = u_all[row_offset:row_offset + m]
     v_loc = v_all[row_offset:row_offset + m]
     inv_u, cos_img = ops.prep(s_img, t_img, u_loc)
     inv_v, cos_txt = ops.prep(s_txt, t_txt, v_loc)
     if world > 1:
-        dist.all_gather_into_tensor(u_all, u_loc.clone(), group=group)
-        dist.all_gather_into_tensor(v_all, v_loc.clone(), group=group)
+        # in-place all-gathers: every rank's input is its own slice of the output buffer
+        dist.all_gather_into_tensor(u_all, u_loc, group=group)
+        dist.all_gather_into_tensor(v_all, v_loc, group=group)
 
-    # (2) forward: log-sum-exp of the local row block of S (image side) and of S^T (text side)
-    lse_u, diag = ops.rowlse(u_loc, v_all, temperature, row_offset, True)
-    lse_v, _ = ops.rowlse(v_loc, u_all, temperature, row_offset, False)
-    sums = ops.partial_sums(lse_u, lse_v, diag, cos_img if t_img is not None else None,
-                            cos_txt if t_txt is not None else None)
-    lse_u_all, lse_v_all = lse_u, lse_v
+    # (2) forward: log-sum-exp of the local row block of S (image side) and of S^T (text side); the two
+    #     lse vectors and the three partial loss sums travel in ONE small all-gather
+    stat = torch.zeros((world, 2 * m + 4), dtype=torch.float32, device=dev)
+    mine = stat[rank]
+    lse_u, diag = ops.rowlse(u_loc, v_all, temperature, row_offset, True, out=mine[0:m])
+    lse_v, _ = ops.rowlse(v_loc, u_all, temperature, row_offset, False, out=mine[m:2 * m])
+    ops.partial_sums(lse_u, lse_v, diag, cos_img if t_img is not None else None, cos_txt if t_txt is not None else None,
+                     out=mine[2 * m:2 * m + 3])
     if world > 1:
-        lse_u_all = torch.empty(B, dtype=torch.float32, device=dev)
-        lse_v_all = torch.empty(B, dtype=torch.float32, device=dev)
-        dist.all_gather_into_tensor(lse_u_all, lse_u, group=group)
-        dist.all_gather_into_tensor(lse_v_all, lse_v, group=group)
-        dist.all_reduce(sums, group=group)
+        dist.all_gather_into_tensor(stat.view(-1), mine.clone(), group=group)
+        lse_u_all = stat[:, 0:m].reshape(B)
+        lse_v_all = stat[:, m:2 * m].reshape(B)
+    else:
+        lse_u_all, lse_v_all = lse_u, lse_v
+    sums = stat[:, 2 * m:2 * m + 3].sum(dim=0)          # fixed rank order -> same value on every rank
     l_con = sums[0] / (2.0 * B)
     l_img = sums[1] / B if t_img is not None else torch.zeros((), device=dev)
     l_txt = sums[2] / B if t_txt is not None else torch.zeros((), device=dev)
@@ -280,11 +284,43 @@ def sharded_distill_loss_fwd_bwd(s_img, s_txt, t_img=None, t_txt=None, temperatu
 
     # (3) backward: score tiles recomputed; gradients of the local rows only
     coef = w_con / (2.0 * B)
-    du_hat = ops.grad(u_loc, v_all, temperature, row_offset, lse_u, lse_v_all, coef) if w_con != 0 else None
-    dv_hat = ops.grad(v_loc, u_all, temperature, row_offset, lse_v, lse_u_all, coef) if w_con != 0 else None
+    du_hat = ops.grad(u_loc, v_all, temperature, row_offset, lse_u.contiguous(), lse_v_all, coef) if w_con != 0 else None
+    dv_hat = ops.grad(v_loc, u_all, temperature, row_offset, lse_v.contiguous(), lse_u_all, coef) if w_con != 0 else None
     d_img = ops.tail(s_img, t_img, inv_u, du_hat, w_img / B, grad_scale)
     d_txt = ops.tail(s_txt, t_txt, inv_v, dv_hat, w_txt / B, grad_scale)
     return losses, d_img, d_txt
+
+
+class GraphedStep:
+    """Capture a fixed-shape step (the sharded objective including its NCCL collectives, or the
+    single-GPU composite) into one CUDA graph and replay it: the data-parallel step at B = 4096 is
+    launch-latency bound (a few us of work per kernel), so the ~25 host-side launches and
+    collective enqueues are replaced by a single graph launch.  Inputs are copied into static
+    buffers; outputs are the graph's static outputs (valid until the next call)."""
+
+    def __init__(self, fn, example_inputs, warmup=3):
+        self.fn = fn
+        self.static_in = [None if t is None else torch.empty_like(t) for t in example_inputs]
+        for dst, src in zip(self.static_in, example_inputs):
+            if dst is not None:
+                dst.copy_(src)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                fn(*self.static_in)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_out = fn(*self.static_in)
+
+    def __call__(self, *inputs):
+        for dst, src in zip(self.static_in, inputs):
+            if dst is not None:
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.static_out
 
 
 class _ShardedFn(torch.autograd.Function):

@@ -1,0 +1,53 @@
+"""torchrun worker: sharded loss / retrieval across real GPUs (NCCL) vs the single-GPU result."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from dclip_b200 import losses as L  # noqa: E402
+from dclip_b200 import retrieval as R  # noqa: E402
+from oracle import synthetic  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+    dist.init_process_group("nccl", device_id=dev)
+    for path, dtype, B, d, tol in (("fp32", torch.float32, 64 * world, 256, 2e-5), ("tensor", torch.bfloat16, 512 * world, 768, 2e-3)):
+        m = B // world
+        full = [t.to(dtype).to(dev) for t in synthetic.loss_inputs(B, d, seed=7)]
+        ref_losses, ref_di, ref_dt = L.distill_loss_fwd_bwd(*full, path=path)
+        loc = [t[rank * m:(rank + 1) * m].contiguous() for t in full]
+        losses, di, dt = L.sharded_distill_loss_fwd_bwd(*loc, path=path)
+        torch.cuda.synchronize()
+        assert torch.allclose(losses, ref_losses, rtol=tol, atol=1e-5), (path, losses, ref_losses)
+        for a, b in ((di, ref_di[rank * m:(rank + 1) * m]), (dt, ref_dt[rank * m:(rank + 1) * m])):
+            rel = float((a.float() - b.float()).norm() / b.float().norm())
+            assert rel < tol + (2 ** -8 if dtype == torch.bfloat16 else 0), (path, rel)
+    # gallery-sharded top-k and Recall@K ranks
+    gal, q, planted = synthetic.gallery_inputs(4000, 33, 128, seed=5)
+    ws, wi = R.topk_ip(torch.from_numpy(q).to(dev), torch.from_numpy(gal).to(dev), 10)
+    n = gal.shape[0] // world
+    a, b = rank * n, (rank + 1) * n if rank < world - 1 else gal.shape[0]
+    s, i = R.sharded_topk_ip(torch.from_numpy(q).to(dev), torch.from_numpy(gal[a:b]).to(dev), 10, a)
+    assert torch.equal(i, wi) and torch.equal(s, ws)
+    qd, gd = torch.from_numpy(q).to(dev), torch.from_numpy(gal).to(dev)
+    tgt = torch.from_numpy(planted.astype(np.int64)).to(dev)
+    ts = R.pair_scores(qd, gd, tgt)
+    want = R.rank_counts(qd, gd, ts, tgt)
+    got = R.sharded_retrieval_ranks(qd, gd[a:b].contiguous(), ts, tgt, a)
+    assert torch.equal(got, want)
+    dist.barrier()
+    if rank == 0:
+        print(f"SHARDED_OK world={world}")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -27,10 +27,14 @@ class OracleLossOps:
             cos = (out_hat * om.normalize(teacher.double())).sum(1).float()
         return (1.0 / nx).squeeze(1).float(), cos
 
-    def rowlse(self, x_hat, y_all, temperature, row_offset, want_diag):
+    def rowlse(self, x_hat, y_all, temperature, row_offset, want_diag, out=None):
         s = x_hat @ y_all.T / temperature
         diag = s[torch.arange(s.shape[0]), row_offset + torch.arange(s.shape[0])].float() if want_diag else None
-        return torch.logsumexp(s, dim=1).float(), diag
+        lse = torch.logsumexp(s, dim=1).float()
+        if out is not None:
+            out.copy_(lse)
+            lse = out
+        return lse, diag
 
     def grad(self, x_hat, y_all, temperature, row_offset, lse_x, lse_y_all, coef):
         s = x_hat @ y_all.T / temperature
@@ -45,8 +49,9 @@ class OracleLossOps:
         xh = x.double() * inv.double()[:, None]
         return ((g - xh * (xh * g).sum(1, keepdim=True)) * inv.double()[:, None] * grad_scale).to(x.dtype)
 
-    def partial_sums(self, lse_u, lse_v, diag, cos_img, cos_txt):
-        out = torch.zeros(3)
+    def partial_sums(self, lse_u, lse_v, diag, cos_img, cos_txt, out=None):
+        out = out if out is not None else torch.zeros(3)
+        out.zero_()
         out[0] = (lse_u + lse_v - 2 * diag).sum()
         if cos_img is not None:
             out[1] = (1 - cos_img).sum()
