@@ -271,7 +271,14 @@ def main():
         line.update(extra)
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # tearing NCCL down while captured graphs still reference its streams can block: drop the graph,
+        # drain the device, leave through a barrier and exit without the (optional) communicator destroy.
+        graphed = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def kernel_roofline(L, _lib, resident, B, m, d, path, rank, peaks):
