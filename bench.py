@@ -337,23 +337,25 @@ def retrieval_bench(dev):
     dt = (time.perf_counter() - t0) / reps
     out["flickr_eval"] = {"queries_per_s": 6000 / dt, "ms_per_eval": dt * 1e3, "t2i_R@1": m["t2i"]["R@1"],
                           "i2t_R@1": m["i2t"]["R@1"], "workload": "1k images x 5k captions, d=512, R@1/5/10 both directions"}
-    ng, nq, dd = 1_000_000, 1024, 768
+    ng, nq, dd = 1_000_000, 4096, 768
     g = torch.randn(ng, dd, device=dev, generator=torch.Generator(device=dev).manual_seed(42))
     g = (g / g.norm(dim=1, keepdim=True)).half()
     idx = torch.randperm(ng, device=dev)[:nq]
     q = g[idx].float() + 0.1 / np.sqrt(dd) * torch.randn(nq, dd, device=dev)
     q = (q / q.norm(dim=1, keepdim=True)).half()
-    s, i = R.topk_ip(q, g, 10)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    s, i = R.topk_ip(q, g, 10)
-    e1.record()
-    torch.cuda.synchronize()
-    sec = e0.elapsed_time(e1) * 1e-3
-    out["top10"] = {"queries_per_s": nq / sec, "ms": sec * 1e3, "planted_R@1": float((i[:, 0] == idx).float().mean()),
-                    "tflops": 2.0 * nq * ng * dd / sec / 1e12,
-                    "workload": f"exact IP top-10, {ng} x {dd} fp16 gallery, {nq} queries, 1 GPU"}
+    gallery = R.TensorGallery(g)
+    for name, path in (("top10", "auto"), ("top10_fp32_path", "fp32")):
+        s, i = R.topk_ip(q, g, 10, path=path, gallery=gallery)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        s, i = R.topk_ip(q, g, 10, path=path, gallery=gallery)
+        e1.record()
+        torch.cuda.synchronize()
+        sec = e0.elapsed_time(e1) * 1e-3
+        out[name] = {"queries_per_s": nq / sec, "ms": sec * 1e3, "planted_R@1": float((i[:, 0] == idx).float().mean()),
+                     "tflops": 2.0 * nq * ng * dd / sec / 1e12, "path": path,
+                     "workload": f"exact IP top-10, {ng} x {dd} fp16 gallery, {nq} queries, 1 GPU"}
     return out
 
 

@@ -54,6 +54,10 @@ SIGNATURES = {
     "dclip_recall_metrics": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _sz, _vp]),
     "dclip_topk_ip_workspace_bytes": (_sz, [_i64, _i64, _i64, _i64, _i32, _i32, _i32]),
     "dclip_topk_ip": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _i32, _i64, _vp, _vp, _vp, _sz, _i32, _vp]),
+    "dclip_max_row_norm": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp]),
+    "dclip_topk_ip_tc_workspace_bytes": (_sz, [_i64, _i64, _i64, _i32]),
+    "dclip_topk_ip_tc": (_i32, [_vp, _i32, _vp, _i32, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
+                                _vp]),
     "dclip_topk_merge": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
 }
 

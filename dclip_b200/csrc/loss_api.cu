@@ -77,7 +77,7 @@ int dclip_infonce_rowlse(const void* x_hat, int64_t m, const void* y_hat, int64_
         a.m = m; a.n = n; a.d = d; a.inv_tau = 1.0f / temperature; a.row_offset = row_offset;
         const void* xs[2] = {x_hat, x_hat};
         const void* ys[2] = {y_hat, y_hat};
-        if (int e = launch_infonce_tc(false, 1, xs, ys, a, ns, st)) return e;
+        if (int e = launch_infonce_tc(0, 1, xs, ys, a, ns, st)) return e;
         if (int e = launch_tc_lse_combine(part, ns, m, a.inv_tau, lse, st)) return e;
         if (diag) return launch_tc_diag(x_hat, y_hat, m, n, d, a.inv_tau, row_offset, diag, st);
         return DCLIP_OK;
@@ -127,7 +127,7 @@ int dclip_infonce_grad(const void* x_hat, int64_t m, const void* y_hat, int64_t 
         a.out_scale = coef / temperature * (1.0f / 8192.0f);
         const void* xs[2] = {x_hat, x_hat};
         const void* ys[2] = {y_hat, y_hat};
-        if (int e = launch_infonce_tc(true, 1, xs, ys, a, ns, st)) return e;
+        if (int e = launch_infonce_tc(1, 1, xs, ys, a, ns, st)) return e;
         if (ns > 1) return launch_tc_grad_combine(out, ns, m, d, dx_hat, st);
         return DCLIP_OK;
     }
@@ -247,7 +247,7 @@ int dclip_distill_loss_fwd_bwd(const void* s_img, const void* s_txt, const void*
         fa.s[0] = TcSide{nullptr, nullptr, part[0]};
         fa.s[1] = TcSide{nullptr, nullptr, part[2]};
         fa.m = B; fa.n = B; fa.d = d; fa.inv_tau = 1.0f / temperature; fa.row_offset = 0;
-        if (int e = launch_infonce_tc(false, 2, xs2, ys2, fa, ns, st)) return e;
+        if (int e = launch_infonce_tc(0, 2, xs2, ys2, fa, ns, st)) return e;
         FinalizeArgs fz{part[0], part[2], ns, B, fa.inv_tau, lse_u, lse_v,
                         SumsArgs{lse_u, lse_v, diag, t_img ? cos_img : nullptr, t_txt ? cos_txt : nullptr, B, nullptr, losses, w_img, w_txt, w_con}};
         if (int e = launch_tc_finalize(fz, st)) return e;
@@ -272,7 +272,7 @@ int dclip_distill_loss_fwd_bwd(const void* s_img, const void* s_txt, const void*
             ga.s[1] = TcSide{lse_v, lse_u, dv_part};
             ga.m = B; ga.n = B; ga.d = d; ga.inv_tau = 1.0f / temperature; ga.row_offset = 0;
             ga.out_scale = w_con / (2.0f * (float)B) / temperature * (1.0f / 8192.0f);
-            if (int e = launch_infonce_tc(true, 2, xs2, ys2, ga, ns, st)) return e;
+            if (int e = launch_infonce_tc(1, 2, xs2, ys2, ga, ns, st)) return e;
             if (ns > 1) {
                 if (int e = launch_tc_grad_combine(du_part, ns, B, d, du_hat, st)) return e;
                 if (int e = launch_tc_grad_combine(dv_part, ns, B, d, dv_hat, st)) return e;

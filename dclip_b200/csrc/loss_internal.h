@@ -58,12 +58,14 @@ struct TcArgs {
     int tiles_per_split;
     float out_scale;      // bwd: coef / tau * 2^-13
     int* error_flag;      // set to 1 on a pipeline timeout
+    float* cand_s;        // retrieval mode: [nsplit][m][32] approximate scores (descending)
+    int32_t* cand_i;      //                 [nsplit][m][32] gallery rows (-1 = empty)
 };
 
 
 bool tc_loss_shape_ok(int64_t d, float temperature);
 int tc_nsplit(int64_t m, int64_t n, int nsides);
-int launch_infonce_tc(bool bwd, int nsides, const void* const x[2], const void* const y[2], const TcArgs& args, int nsplit,
+int launch_infonce_tc(int mode, int nsides, const void* const x[2], const void* const y[2], const TcArgs& args, int nsplit,
                       cudaStream_t st);
 int launch_tc_lse_combine(const float* part, int nsplit, int64_t m, float inv_tau, float* lse, cudaStream_t st);
 int launch_tc_grad_combine(const float* part, int nsplit, int64_t m, int64_t d, float* dx, cudaStream_t st);

@@ -54,7 +54,10 @@ struct Pipe {
 // kC = thread-block cluster size along the row-block axis.  The kC CTAs of a cluster own different
 // row blocks but walk the same Y tiles, so each loads 1/kC of every ring slot and multicasts it to
 // all of them: L2 -> SM traffic per CTA drops by kC (the kernel is otherwise bound by it).
-template <bool kBwd, int kC>
+// kMode: 0 = loss forward (row sums), 1 = loss backward, 2 = retrieval (approximate top-32 candidate
+// lists per X row: the same TMA -> tcgen05 pipeline with queries as the resident X block and the
+// gallery streaming as Y; see retrieval_tc.cu for the exact re-scoring that follows).
+template <int kMode, int kC>
 __global__ void __launch_bounds__(kTcThreads, 1)
 k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CUtensorMap tmy0,
              const __grid_constant__ CUtensorMap tmx1, const __grid_constant__ CUtensorMap tmy1,
@@ -65,6 +68,8 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
     const CUtensorMap* tmx = side ? &tmx1 : &tmx0;
     const CUtensorMap* tmy = side ? &tmy1 : &tmy0;
     const CUtensorMap* tmh = side ? &tmh1 : &tmh0;      // same matrix as tmy, 64-row boxes (kC == 4)
+    constexpr bool kBwd = kMode == 1;
+    constexpr bool kTopk = kMode == 2;
     const TcSide S = a.s[side];
     const uint32_t crank = kC > 1 ? cluster_ctarank() : 0;
     constexpr uint16_t kMask = (uint16_t)((1u << kC) - 1);
@@ -75,7 +80,7 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
     uint8_t* xs = smem;                                   // resident X_I: nkb boxes of 8 KB
     uint8_t* ring = xs + (size_t)nkb * kXBoxBytes;        // kSlots x 32 KB
     uint8_t* gs = ring + kSlots * kSlotBytes;             // 2 x 16 KB (bwd)
-    uint8_t* tail = gs + (kBwd ? 2 * kGBytes : 0);
+    uint8_t* tail = gs + ((kBwd || kTopk) ? 2 * kGBytes : 0);
     uint64_t* full = reinterpret_cast<uint64_t*>(tail);   // [kSlots]
     uint64_t* empty = full + kSlots;                      // [kSlots]
     uint64_t* s_full = empty + kSlots;                    // [2]
@@ -213,10 +218,23 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
             const int et = q * 32 + lane;                 // j row inside the tile == TMEM lane
             const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
             const float c = a.inv_tau * 1.4426950408889634f;    // log2(e) / tau
-            float sums[kBwd ? 1 : NI];
-            if (!kBwd) {
+            float sums[kMode == 0 ? NI : 1];
+            if (kMode == 0) {
 #pragma unroll
                 for (int i = 0; i < NI; ++i) sums[i] = 0.f;
+            }
+            // retrieval mode: per-query sorted candidate lists (32 best approximate scores) in shared memory
+            float* lst_s = reinterpret_cast<float*>(gs);                  // [NI][32]
+            int32_t* lst_i = reinterpret_cast<int32_t*>(gs + 8192);       // [NI][32]
+            float* que_s = reinterpret_cast<float*>(gs + 16384);          // [2048] pending candidates of one chunk
+            uint32_t* que_k = reinterpret_cast<uint32_t*>(gs + 24576);    // [2048] (query << 26) | gallery row
+            float* thr = a_s;                                             // [NI] current 32nd-best score
+            int* qcount = reinterpret_cast<int*>(a_s + NI);
+            if (kTopk) {
+                for (int idx = et; idx < NI * 32; idx += 128) { lst_s[idx] = -INFINITY; lst_i[idx] = INT32_MAX; }
+                if (et < NI) thr[et] = -INFINITY;
+                if (et == 0) *qcount = 0;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
             }
             if (kBwd) {
                 if (et < NI) {
@@ -241,10 +259,63 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
                 fence_before_thread_sync();
                 mbar_arrive(&s_empty[b]);                 // S buffer may be overwritten by phase 1 of tile t+2
                 const bool jvalid = gj < a.n;
-                if (!kBwd) {
+                if (kMode == 0) {
                     if (jvalid) {
 #pragma unroll
                         for (int i = 0; i < NI; ++i) sums[i] += exp2f(fmaf(__uint_as_float(r[i]), c, -c));
+                    }
+                } else if (kTopk) {
+                    // threshold filter: a score enters the queue only if it beats the query's current 32nd
+                    // best; 16 queries per chunk bound the queue at 128 x 16 = 2048 entries.
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            const int i = ch * 16 + e;
+                            const float sv = __uint_as_float(r[i]);
+                            if (jvalid && sv > thr[i]) {
+                                const int slot = atomicAdd(qcount, 1);
+                                que_s[slot] = sv;
+                                que_k[slot] = (static_cast<uint32_t>(i) << 26) | static_cast<uint32_t>(gj);
+                            }
+                        }
+                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                        const int nq_pending = *qcount;
+                        if (nq_pending > 0) {
+                            // warp w drains the candidates of queries q with (q & 3) == w: one owner per list
+                            for (int base = 0; base < nq_pending; base += 32) {
+                                const int e = base + lane;
+                                const bool valid = e < nq_pending;
+                                const uint32_t key = valid ? que_k[e] : 0u;
+                                const float sc = valid ? que_s[e] : 0.f;
+                                unsigned mask = __ballot_sync(0xffffffffu, valid && (((key >> 26) & 3u) == (uint32_t)q));
+                                while (mask) {
+                                    const int src = __ffs(mask) - 1;
+                                    mask &= mask - 1;
+                                    const float cs = __shfl_sync(0xffffffffu, sc, src);
+                                    const uint32_t ck = __shfl_sync(0xffffffffu, key, src);
+                                    const int cq = (int)(ck >> 26);
+                                    const int32_t ci = (int32_t)(ck & 0x3FFFFFFu);
+                                    float ls = lst_s[cq * 32 + lane];
+                                    int32_t li = lst_i[cq * 32 + lane];
+                                    const unsigned after = __ballot_sync(0xffffffffu, cs > ls || (cs == ls && ci < li));
+                                    if (after) {
+                                        const int pos = __ffs(after) - 1;
+                                        const float ps = __shfl_up_sync(0xffffffffu, ls, 1);
+                                        const int32_t pi = __shfl_up_sync(0xffffffffu, li, 1);
+                                        if (lane == pos) { ls = cs; li = ci; }
+                                        else if (lane > pos) { ls = ps; li = pi; }
+                                        lst_s[cq * 32 + lane] = ls;
+                                        lst_i[cq * 32 + lane] = li;
+                                        if (lane == 31) thr[cq] = ls;
+                                    }
+                                    __syncwarp();
+                                }
+                            }
+                            asm volatile("bar.sync 1, 128;" ::: "memory");
+                            if (et == 0) *qcount = 0;
+                            asm volatile("bar.sync 1, 128;" ::: "memory");
+                        }
                     }
                 } else {
                     ok = ok && mbar_wait(&g_empty[b], ((t >> 1) & 1) ^ 1, kSpin);
@@ -279,7 +350,17 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
                     mbar_arrive(&g_full[b]);
                 }
             }
-            if (!kBwd) {
+            if (kTopk) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int idx = et; idx < NI * 32; idx += 128) {
+                    const int64_t gq = row0 + (idx >> 5);
+                    if (gq < a.m) {
+                        const int64_t o = ((int64_t)blockIdx.y * a.m + gq) * 32 + (idx & 31);
+                        a.cand_s[o] = lst_s[idx];
+                        a.cand_i[o] = lst_i[idx] == INT32_MAX ? -1 : lst_i[idx];
+                    }
+                }
+            } else if (kMode == 0) {
                 // cross-thread reduction of the per-column sums: stage through the (now idle) ring
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 float* red = reinterpret_cast<float*>(ring);          // [128][NI + 1]
@@ -317,7 +398,16 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
     } else if (warp >= 4) {
         // empty column range (only possible with an over-split grid): contribute zeros
         const int et = (warp & 3) * 32 + lane;
-        if (!kBwd) {
+        if (kTopk) {
+            for (int idx = et; idx < NI * 32; idx += 128) {
+                const int64_t gq = row0 + (idx >> 5);
+                if (gq < a.m) {
+                    const int64_t o = ((int64_t)blockIdx.y * a.m + gq) * 32 + (idx & 31);
+                    a.cand_s[o] = -INFINITY;
+                    a.cand_i[o] = -1;
+                }
+            }
+        } else if (kMode == 0) {
             if (et < NI && row0 + et < a.m) S.out[(int64_t)blockIdx.y * a.m + row0 + et] = 0.f;
         } else {
             float* outp = S.out + (int64_t)blockIdx.y * a.m * a.d;
@@ -402,8 +492,8 @@ int tc_nsplit(int64_t m, int64_t n, int nsides) {
     return (int)want;
 }
 
-static size_t tc_smem_bytes(int64_t d, bool bwd) {
-    return 1024 + (size_t)(d / 64) * kXBoxBytes + (size_t)kSlots * kSlotBytes + (bwd ? 2 * kGBytes : 0) + 512;
+static size_t tc_smem_bytes(int64_t d, int mode) {
+    return 1024 + (size_t)((d + 63) / 64) * kXBoxBytes + (size_t)kSlots * kSlotBytes + (mode != 0 ? 2 * kGBytes : 0) + 512;
 }
 
 static int* tc_error_flag() {   // one device int per device, lazily allocated, never freed
@@ -419,7 +509,7 @@ static int* tc_error_flag() {   // one device int per device, lazily allocated, 
 }
 
 // x[side]: local rows [m, d] fp16; y[side]: all rows [n, d] fp16.
-int launch_infonce_tc(bool bwd, int nsides, const void* const x[2], const void* const y[2], const TcArgs& args_in, int nsplit,
+int launch_infonce_tc(int mode, int nsides, const void* const x[2], const void* const y[2], const TcArgs& args_in, int nsplit,
                       cudaStream_t st) {
     if (!device_is_sm100()) return fail(DCLIP_ERR_ARCH, "tensor path needs an sm_100 device");
     TcArgs a = args_in;
@@ -434,7 +524,7 @@ int launch_infonce_tc(bool bwd, int nsides, const void* const x[2], const void* 
     const int64_t ntiles = ceil_div(a.n, TJ);
     a.tiles_per_split = (int)ceil_div(ntiles, nsplit);
     a.error_flag = tc_error_flag();
-    const size_t smem = tc_smem_bytes(a.d, bwd);
+    const size_t smem = tc_smem_bytes(a.d, mode);
     const int C = tc_cluster_size();
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(ceil_div(ceil_div(a.m, NI), C) * C), (unsigned)nsplit, (unsigned)nsides);
@@ -450,10 +540,12 @@ int launch_infonce_tc(bool bwd, int nsides, const void* const x[2], const void* 
         DCLIP_CUDA_OK(cudaFuncSetAttribute(k_infonce_tc<BWD, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
         DCLIP_CUDA_OK(cudaLaunchKernelEx(&cfg, k_infonce_tc<BWD, CL>, tmx[0], tmy[0], tmx[1], tmy[1], tmh[0], tmh[1], a));    \
     } while (0)
-    if (bwd) {
-        if (C == 1) DCLIP_TC_LAUNCH(true, 1); else if (C == 2) DCLIP_TC_LAUNCH(true, 2); else DCLIP_TC_LAUNCH(true, 4);
+    if (mode == 1) {
+        if (C == 1) DCLIP_TC_LAUNCH(1, 1); else if (C == 2) DCLIP_TC_LAUNCH(1, 2); else DCLIP_TC_LAUNCH(1, 4);
+    } else if (mode == 0) {
+        if (C == 1) DCLIP_TC_LAUNCH(0, 1); else if (C == 2) DCLIP_TC_LAUNCH(0, 2); else DCLIP_TC_LAUNCH(0, 4);
     } else {
-        if (C == 1) DCLIP_TC_LAUNCH(false, 1); else if (C == 2) DCLIP_TC_LAUNCH(false, 2); else DCLIP_TC_LAUNCH(false, 4);
+        if (C == 1) DCLIP_TC_LAUNCH(2, 1); else if (C == 2) DCLIP_TC_LAUNCH(2, 2); else DCLIP_TC_LAUNCH(2, 4);
     }
 #undef DCLIP_TC_LAUNCH
     DCLIP_LAUNCH_OK("k_infonce_tc");

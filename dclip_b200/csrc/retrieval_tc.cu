@@ -1,0 +1,232 @@
+// Retrieval — tensor path: tcgen05 candidate generation + exact FP32 re-scoring with a certificate.
+//
+// Replaces the brute-force search of faiss IndexFlatIP (training/compute_faiss.py:27,79;
+// training/image_tokenizer.py:262) at BASELINE configs[4] scale (10 M x 768 fp16 gallery sharded over
+// 8 GPUs, 100 k queries, top-10).
+//
+//   1. k_infonce_tc<2>: queries are the resident X block (64 per CTA), the gallery streams through the
+//      TMA ring as Y; fp16 operands, fp32 accumulation in TMEM.  The epilogue keeps, per query, the 32
+//      best APPROXIMATE scores (threshold filter + warp insertion); the score matrix never exists.
+//   2. candidate lists of the gallery splits are merged (32 per query).
+//   3. k_topk_rescore: every candidate is re-scored with the bit-exact contract of the FP32 path
+//      (fp32 fmaf chain over k ascending on the stored values), sorted by (-score, +index), top-k kept.
+//   4. certificate: any row outside the 32 candidates has approximate score <= a32 (the weakest kept),
+//      hence exact score <= a32 + eps, eps = eps_rel * |q| * max_g |g|.  If exact_k > a32 + eps the exact
+//      top-k is provably inside the candidates; otherwise the query is flagged and the caller re-runs
+//      it on the exact FP32 path.  Results are therefore always bit-exact against the oracle.
+#include "common.cuh"
+#include "loss_internal.h"
+
+namespace dclip {
+
+constexpr int kCand = 32;
+
+template <typename T>
+__global__ void k_to_f16(const T* __restrict__ in, __half* __restrict__ out, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __float2half_rn(to_f32<T>(in[i]));
+}
+
+// max_i |x_i|_2 over the rows of x (fp32 math), atomicMax on the float bits (norms are >= 0)
+template <typename T>
+__global__ void __launch_bounds__(256) k_max_row_norm(const T* __restrict__ x, int64_t n, int64_t d, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    float best = 0.f;
+    for (int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < n; row += (int64_t)gridDim.x * 8) {
+        float ss = 0.f;
+        for (int64_t k = lane; k < d; k += 32) { const float v = to_f32<T>(x[row * d + k]); ss = fmaf(v, v, ss); }
+        ss = warp_sum(ss);
+        best = fmaxf(best, sqrtf(ss));
+    }
+    if (lane == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(best));
+}
+
+// merge the sorted candidate lists of the gallery splits: one warp per query
+__global__ void k_cand_merge(const float* __restrict__ in_s, const int32_t* __restrict__ in_i, int nsplit, int64_t nq,
+                             float* __restrict__ out_s, int32_t* __restrict__ out_i) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    float ls = -INFINITY;
+    int32_t li = INT32_MAX;
+    for (int p = 0; p < nsplit; ++p) {
+        const int64_t base = ((int64_t)p * nq + q) * kCand;
+        const float s = in_s[base + lane];
+        const int32_t gi = in_i[base + lane];
+        unsigned m = __ballot_sync(0xffffffffu, gi >= 0);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const float cs = __shfl_sync(0xffffffffu, s, src);
+            const int32_t ci = __shfl_sync(0xffffffffu, gi, src);
+            const unsigned after = __ballot_sync(0xffffffffu, cs > ls || (cs == ls && ci < li));
+            if (!after) break;      // lists are sorted: the rest of this list cannot enter either
+            const int pos = __ffs(after) - 1;
+            const float ps = __shfl_up_sync(0xffffffffu, ls, 1);
+            const int32_t pi = __shfl_up_sync(0xffffffffu, li, 1);
+            if (lane == pos) { ls = cs; li = ci; }
+            else if (lane > pos) { ls = ps; li = pi; }
+        }
+    }
+    out_s[q * kCand + lane] = ls;
+    out_i[q * kCand + lane] = li == INT32_MAX ? -1 : li;
+}
+
+// exact re-scoring + certificate: one warp per query, lane l owns candidate l
+template <typename TQ, typename TG>
+__global__ void __launch_bounds__(256) k_topk_rescore(const TQ* __restrict__ q, const TG* __restrict__ g, int64_t nq, int64_t d, int k,
+                                                      const float* __restrict__ cand_s, const int32_t* __restrict__ cand_i,
+                                                      const float* __restrict__ gmax, float eps_rel, int64_t g_index_offset,
+                                                      float* __restrict__ out_s, int64_t* __restrict__ out_i, int32_t* __restrict__ flags,
+                                                      int32_t* __restrict__ n_flagged) {
+    extern __shared__ float qs_all[];                      // [8 warps][d]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t qi = (int64_t)blockIdx.x * 8 + warp;
+    if (qi >= nq) return;
+    float* qs = qs_all + (size_t)warp * d;
+    float qn = 0.f;
+    for (int64_t c = lane; c < d; c += 32) { const float v = to_f32<TQ>(q[qi * d + c]); qs[c] = v; qn = fmaf(v, v, qn); }
+    qn = sqrtf(warp_sum(qn));
+    __syncwarp();
+    const int32_t ci = cand_i[qi * kCand + lane];
+    const float approx = cand_s[qi * kCand + lane];
+    float s = -INFINITY;
+    if (ci >= 0) {
+        const TG* gr = g + (int64_t)ci * d;
+        float acc = 0.f;
+        for (int64_t c = 0; c < d; ++c) acc = fmaf(qs[c], to_f32<TG>(gr[c]), acc);      // the contract's chain, k ascending
+        s = acc;
+    }
+    const int64_t gi = ci >= 0 ? g_index_offset + ci : INT64_MAX;
+    // rank among the 32 by (-score, +index)
+    int rank = 0;
+#pragma unroll
+    for (int o = 0; o < 32; ++o) {
+        const float so = __shfl_sync(0xffffffffu, s, o);
+        const int64_t io = __shfl_sync(0xffffffffu, gi, o);
+        rank += (so > s || (so == s && io < gi)) ? 1 : 0;
+    }
+    if (ci < 0) rank = 32 + lane;     // empty slots never rank inside k
+    if (rank < k) {
+        out_s[qi * k + rank] = s;
+        out_i[qi * k + rank] = gi;
+    }
+    const int nvalid = __popc(__ballot_sync(0xffffffffu, ci >= 0));
+    if (lane >= nvalid && lane < k) {                      // fewer than k candidates: faiss-style padding
+        out_s[qi * k + lane] = -INFINITY;
+        out_i[qi * k + lane] = -1;
+    }
+    // certificate
+    const float a32 = __shfl_sync(0xffffffffu, approx, 31);
+    const bool full = __shfl_sync(0xffffffffu, ci, 31) >= 0;
+    const unsigned kth = __ballot_sync(0xffffffffu, rank == k - 1);
+    float exact_k = -INFINITY;
+    if (kth) exact_k = __shfl_sync(0xffffffffu, s, __ffs(kth) - 1);
+    const bool certified = !full || (exact_k > a32 + eps_rel * qn * gmax[0]);
+    if (lane == 0) {
+        flags[qi] = certified ? 0 : 1;
+        if (!certified) atomicAdd(n_flagged, 1);
+    }
+}
+
+int tc_topk_nsplit(int64_t nq, int64_t ng) {
+    const int64_t row_ctas = ceil_div(nq, 64);
+    const int64_t ntiles = ceil_div(ng, 128);
+    int64_t want = sm_count() / (row_ctas > 0 ? row_ctas : 1);
+    if (want < 1) want = 1;
+    if (want > ntiles) want = ntiles;
+    return (int)want;
+}
+
+}  // namespace dclip
+
+using namespace dclip;
+
+extern "C" {
+
+int dclip_max_row_norm(const void* x, int64_t n, int64_t d, int dtype, float* out, void* stream) {
+    DCLIP_REQUIRE(x && out && n >= 0 && d > 0, "max_row_norm: bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    DCLIP_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float), st));
+    if (n == 0) return DCLIP_OK;
+    const unsigned grid = (unsigned)min((int64_t)sm_count() * 8, ceil_div(n, 8));
+    DCLIP_DISPATCH_DTYPE(dtype, (k_max_row_norm<T><<<grid, 256, 0, st>>>(static_cast<const T*>(x), n, d, out)));
+    DCLIP_LAUNCH_OK("k_max_row_norm");
+    return DCLIP_OK;
+}
+
+size_t dclip_topk_ip_tc_workspace_bytes(int64_t nq, int64_t ng, int64_t d, int q_dtype) {
+    const int ns = tc_topk_nsplit(nq, ng);
+    size_t total = 0;
+    total += align_up((size_t)nq * d * 2, 256);                       // fp16 queries
+    total += 2 * align_up((size_t)ns * nq * kCand * 4, 256);          // per-split candidates
+    total += 2 * align_up((size_t)nq * kCand * 4, 256);               // merged candidates
+    (void)q_dtype;
+    return total + 1024;
+}
+
+/* Tensor-path exact top-k.  q: [nq, d] (any dtype), g_exact: [ng, d] in g_dtype = the stored gallery the
+ * scores are defined on, g_fp16: the same gallery in fp16 for the tensor pass (== g_exact when g_dtype is
+ * DCLIP_F16).  gmax: device float = max gallery row norm (dclip_max_row_norm).  flags: int32[nq] (1 = the
+ * certificate failed: re-run that query with dclip_topk_ip on the FP32 path), n_flagged: device int32. */
+int dclip_topk_ip_tc(const void* q, int q_dtype, const void* g_exact, int g_dtype, const void* g_fp16, int64_t nq, int64_t ng,
+                     int64_t d, int64_t k, int64_t g_index_offset, const float* gmax, float* out_scores, int64_t* out_index,
+                     int32_t* flags, int32_t* n_flagged, void* workspace, size_t workspace_bytes, void* stream) {
+    DCLIP_REQUIRE(q && g_exact && g_fp16 && gmax && out_scores && out_index && flags && n_flagged, "topk_ip_tc: null pointer");
+    DCLIP_REQUIRE(k >= 1 && k <= 16, "topk_ip_tc: k must be in [1, 16] (32 candidates are re-scored)");
+    DCLIP_REQUIRE(d % 128 == 0 && d >= 128 && d <= 768, "topk_ip_tc: tensor path needs d %% 128 == 0 and 128 <= d <= 768 (got %lld)", (long long)d);
+    DCLIP_REQUIRE(ng > 0 && ng < (1ll << 26), "topk_ip_tc: gallery shard must have 1 .. 2^26-1 rows (got %lld)", (long long)ng);
+    DCLIP_REQUIRE(aligned16(g_fp16) && aligned16(workspace), "topk_ip_tc: pointers must be 16-byte aligned");
+    if (!device_is_sm100()) return fail(DCLIP_ERR_ARCH, "tensor path needs an sm_100 device");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (nq == 0) return DCLIP_OK;
+    const int ns = tc_topk_nsplit(nq, ng);
+    Workspace ws(workspace, workspace_bytes);
+    __half* q16 = static_cast<__half*>(ws.take((size_t)nq * d * 2));
+    float* ps = static_cast<float*>(ws.take((size_t)ns * nq * kCand * 4));
+    int32_t* pi = static_cast<int32_t*>(ws.take((size_t)ns * nq * kCand * 4));
+    float* ms = static_cast<float*>(ws.take((size_t)nq * kCand * 4));
+    int32_t* mi = static_cast<int32_t*>(ws.take((size_t)nq * kCand * 4));
+    if (!ws.ok()) return fail(DCLIP_ERR_WORKSPACE, "topk_ip_tc: workspace too small (%zu < %zu)", workspace_bytes, ws.used);
+    const void* qh = q;
+    if (q_dtype != DCLIP_F16) {
+        DCLIP_DISPATCH_DTYPE(q_dtype, (k_to_f16<T><<<(unsigned)ceil_div(nq * d, 256), 256, 0, st>>>(static_cast<const T*>(q), q16, nq * d)));
+        DCLIP_LAUNCH_OK("k_to_f16");
+        qh = q16;
+    }
+    TcArgs a{};
+    a.m = nq; a.n = ng; a.d = d; a.inv_tau = 1.f; a.row_offset = 0;
+    a.cand_s = ps; a.cand_i = pi;
+    const void* xs[2] = {qh, qh};
+    const void* ys[2] = {g_fp16, g_fp16};
+    if (int e = launch_infonce_tc(2, 1, xs, ys, a, ns, st)) return e;
+    const float* cs = ps;
+    const int32_t* ci = pi;
+    if (ns > 1) {
+        k_cand_merge<<<(unsigned)ceil_div(nq, 8), 256, 0, st>>>(ps, pi, ns, nq, ms, mi);
+        DCLIP_LAUNCH_OK("k_cand_merge");
+        cs = ms; ci = mi;
+    }
+    DCLIP_CUDA_OK(cudaMemsetAsync(n_flagged, 0, sizeof(int32_t), st));
+    // eps_rel: accumulation-order difference of exact fp16 products (d * 2^-22, worst case) plus the fp16
+    // rounding of operands that were not fp16 to begin with (2^-11 each)
+    float eps_rel = (float)d * 2.384185791015625e-07f;
+    if (q_dtype != DCLIP_F16) eps_rel += 4.8828125e-4f;
+    if (g_dtype != DCLIP_F16) eps_rel += 4.8828125e-4f;
+    const size_t smem = (size_t)8 * d * sizeof(float);
+    const unsigned grid = (unsigned)ceil_div(nq, 8);
+#define DCLIP_RESCORE(TQ, TG)                                                                                                    \
+    k_topk_rescore<TQ, TG><<<grid, 256, smem, st>>>(static_cast<const TQ*>(q), static_cast<const TG*>(g_exact), nq, d, (int)k, cs, ci, \
+                                                    gmax, eps_rel, g_index_offset, out_scores, out_index, flags, n_flagged)
+    if (q_dtype == DCLIP_F32 && g_dtype == DCLIP_F32) DCLIP_RESCORE(float, float);
+    else if (q_dtype == DCLIP_F32 && g_dtype == DCLIP_F16) DCLIP_RESCORE(float, __half);
+    else if (q_dtype == DCLIP_F16 && g_dtype == DCLIP_F16) DCLIP_RESCORE(__half, __half);
+    else if (q_dtype == DCLIP_F16 && g_dtype == DCLIP_F32) DCLIP_RESCORE(__half, float);
+    else if (q_dtype == DCLIP_BF16 && g_dtype == DCLIP_BF16) DCLIP_RESCORE(__nv_bfloat16, __nv_bfloat16);
+    else return fail(DCLIP_ERR_UNSUPPORTED, "topk_ip_tc: dtype combination q=%d g=%d not supported", q_dtype, g_dtype);
+#undef DCLIP_RESCORE
+    DCLIP_LAUNCH_OK("k_topk_rescore");
+    return DCLIP_OK;
+}
+
+}  // extern "C"

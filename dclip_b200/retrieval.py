@@ -23,6 +23,7 @@ from ._lib import check, dtype_code, path_code, ptr, require_cuda, stream_ptr, w
 
 __all__ = ["calculate_retrieval_metrics", "retrieval_metrics_from_embeddings", "retrieval_ranks", "normalize_rows",
            "pair_scores", "rank_counts", "matrix_ranks", "recall_metrics", "topk_ip", "topk_merge", "IndexFlatIP",
+           "TensorGallery", "tensor_path_ok",
            "build_eval_index", "sharded_topk_ip", "sharded_retrieval_ranks"]
 
 
@@ -96,22 +97,89 @@ def recall_metrics(rank, group=None, n_groups=0):
     return out
 
 
-def topk_ip(q, g, k, g_index_offset=0, path="fp32"):
-    """Exact inner-product top-k: (scores float32[nq,k] descending, index int64[nq,k])."""
+class TensorGallery:
+    """What the tensor path needs besides the stored gallery: its float16 image for the tcgen05 pass
+    (the gallery itself when it is stored in float16) and the largest row norm for the exactness
+    certificate.  Built once per index / shard and reused by every search."""
+
+    def __init__(self, g):
+        dev = require_cuda(g)
+        self.g = g
+        self.g16 = g if g.dtype == torch.float16 else g.to(torch.float16)
+        self.gmax = torch.empty(1, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(_lib.load_library().dclip_max_row_norm(ptr(g), g.shape[0], g.shape[1], dtype_code(g), ptr(self.gmax),
+                                                         stream_ptr(dev)), "max_row_norm")
+
+
+def tensor_path_ok(q, g, k):
+    """Shapes the tcgen05 retrieval kernel supports (otherwise the exact FP32 path is used)."""
+    d = g.shape[1]
+    return (d % 128 == 0 and 128 <= d <= 768 and 1 <= k <= 16 and 0 < g.shape[0] < (1 << 26)
+            and q.dtype in (torch.float32, torch.float16) and g.dtype in (torch.float32, torch.float16)
+            and _lib.load_library().dclip_device_supports_tensor_path(g.device.index or 0) == 1)
+
+
+def _topk_fp32(q, g, k, g_index_offset):
     dev = require_cuda(q, g)
     lib = _lib.load_library()
     nq, d = q.shape
     ng = g.shape[0]
-    if g.shape[1] != d:
-        raise ValueError(f"topk_ip: dim mismatch {q.shape} vs {g.shape}")
     out_s = torch.empty((nq, k), dtype=torch.float32, device=dev)
     out_i = torch.empty((nq, k), dtype=torch.int64, device=dev)
-    pc = path_code(path)
-    ws = workspace(lib.dclip_topk_ip_workspace_bytes(nq, ng, d, k, dtype_code(q), dtype_code(g), pc), dev)
+    ws = workspace(lib.dclip_topk_ip_workspace_bytes(nq, ng, d, k, dtype_code(q), dtype_code(g), _lib.PATH_FP32), dev)
     with torch.cuda.device(dev):
         check(lib.dclip_topk_ip(ptr(q), ptr(g), nq, ng, d, k, dtype_code(q), dtype_code(g), int(g_index_offset),
-                                ptr(out_s), ptr(out_i), ptr(ws), ws.numel(), pc, stream_ptr(dev)), "topk_ip")
+                                ptr(out_s), ptr(out_i), ptr(ws), ws.numel(), _lib.PATH_FP32, stream_ptr(dev)), "topk_ip")
     return out_s, out_i
+
+
+def _topk_tensor(q, gallery, k, g_index_offset):
+    g = gallery.g
+    dev = require_cuda(q, g)
+    lib = _lib.load_library()
+    nq, d = q.shape
+    ng = g.shape[0]
+    out_s = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    out_i = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    flags = torch.empty(nq, dtype=torch.int32, device=dev)
+    n_flagged = torch.empty(1, dtype=torch.int32, device=dev)
+    ws = workspace(lib.dclip_topk_ip_tc_workspace_bytes(nq, ng, d, dtype_code(q)), dev)
+    with torch.cuda.device(dev):
+        check(lib.dclip_topk_ip_tc(ptr(q), dtype_code(q), ptr(g), dtype_code(g), ptr(gallery.g16), nq, ng, d, k,
+                                   int(g_index_offset), ptr(gallery.gmax), ptr(out_s), ptr(out_i), ptr(flags),
+                                   ptr(n_flagged), ptr(ws), ws.numel(), stream_ptr(dev)), "topk_ip_tc")
+    # the one host read of a search: queries whose exactness certificate failed (more than 32 near-ties)
+    # are re-run on the exact FP32 path, so the result is bit-exact in every case
+    if int(n_flagged.item()) > 0:
+        idx = torch.nonzero(flags, as_tuple=False).flatten()
+        s2, i2 = _topk_fp32(q.index_select(0, idx).contiguous(), g, k, g_index_offset)
+        out_s.index_copy_(0, idx, s2)
+        out_i.index_copy_(0, idx, i2)
+    return out_s, out_i
+
+
+def topk_ip(q, g, k, g_index_offset=0, path="auto", gallery=None):
+    """Exact inner-product top-k: (scores float32[nq,k] descending, index int64[nq,k]), ties by ascending
+    index, bit-exact against the oracle contract on every path.
+      path "fp32"   CUDA-core kernel, every score is the contract's fmaf chain
+      path "tensor" tcgen05 candidate generation + exact re-scoring + certificate (large galleries)
+      path "auto"   tensor when the shape is supported and the gallery has >= 16384 rows
+    `gallery`: an optional TensorGallery(g) to reuse across calls (IndexFlatIP keeps one)."""
+    if isinstance(g, TensorGallery):
+        gallery, g = g, g.g
+    require_cuda(q, g)
+    if g.shape[1] != q.shape[1]:
+        raise ValueError(f"topk_ip: dim mismatch {tuple(q.shape)} vs {tuple(g.shape)}")
+    if path not in ("auto", "fp32", "tensor"):
+        raise ValueError(f"topk_ip: unknown path {path!r}")
+    use_tensor = path == "tensor" or (path == "auto" and g.shape[0] >= 16384 and tensor_path_ok(q, g, k))
+    if use_tensor:
+        if not tensor_path_ok(q, g, k):
+            raise RuntimeError("topk_ip: tensor path needs d % 128 == 0, 128 <= d <= 768, k <= 16, float16/float32 "
+                               f"inputs and an sm_100 device (got q {tuple(q.shape)} {q.dtype}, g {tuple(g.shape)} {g.dtype}, k={k})")
+        return _topk_tensor(q, gallery or TensorGallery(g), k, g_index_offset)
+    return _topk_fp32(q, g, k, g_index_offset)
 
 
 def topk_merge(scores, index):
@@ -235,13 +303,14 @@ class IndexFlatIP:
     `search` returns numpy arrays for numpy queries (faiss convention) and CUDA tensors for CUDA
     queries.  Results are ordered by (-score, +index); missing slots are (-inf, -1)."""
 
-    def __init__(self, d, device=None, storage="float32", path="fp32"):
+    def __init__(self, d, device=None, storage="float32", path="auto"):
         self.d = int(d)
         self.device = torch.device(device) if device is not None else None
         self.storage = torch.float32 if storage == "float32" else torch.float16
         self.path = path
         self._chunks = []
         self._data = None
+        self._tensor_gallery = None
         self.index_offset = 0     # global index of row 0 (gallery sharding)
 
     @property
@@ -261,6 +330,7 @@ class IndexFlatIP:
             parts = ([self._data] if self._data is not None else []) + self._chunks
             self._data = parts[0] if len(parts) == 1 else torch.cat(parts, dim=0)
             self._chunks = []
+            self._tensor_gallery = None
         if self._data is None:
             dev = self.device or torch.device("cuda", torch.cuda.current_device())
             self._data = torch.empty((0, self.d), dtype=self.storage, device=dev)
@@ -274,19 +344,24 @@ class IndexFlatIP:
             qd = qd.float()
         if g.dtype == torch.float32 and qd.dtype != torch.float32:
             qd = qd.float()
-        scores, index = topk_ip(qd, g, int(k), self.index_offset, self.path)
+        gallery = None
+        if self.path != "fp32" and g.shape[0] >= 16384 and tensor_path_ok(qd, g, int(k)):
+            if self._tensor_gallery is None:
+                self._tensor_gallery = TensorGallery(g)
+            gallery = self._tensor_gallery
+        scores, index = topk_ip(qd, g, int(k), self.index_offset, self.path, gallery)
         if as_numpy:
             return scores.cpu().numpy(), index.cpu().numpy()
         return scores, index
 
     def reset(self):
-        self._chunks, self._data = [], None
+        self._chunks, self._data, self._tensor_gallery = [], None, None
 
 
 # ------------------------------------------------------------------------------------------------
 # gallery sharding across ranks — SURVEY.md §8(e)
 # ------------------------------------------------------------------------------------------------
-def sharded_topk_ip(q, g_shard, k, g_index_offset, group=None, path="fp32", topk_fn=None, merge_fn=None):
+def sharded_topk_ip(q, g_shard, k, g_index_offset, group=None, path="auto", topk_fn=None, merge_fn=None):
     """Every rank holds all queries and one contiguous gallery shard (global row index =
     g_index_offset + local row).  Per-rank top-k, all-gather of the [nq, k] (score, index)
     lists, merge by (-score, +index).  Returns the same global result on every rank."""

@@ -175,6 +175,22 @@ size_t dclip_topk_ip_workspace_bytes(int64_t nq, int64_t ng, int64_t d, int64_t 
 int dclip_topk_ip(const void* q, const void* g, int64_t nq, int64_t ng, int64_t d, int64_t k, int q_dtype,
                   int g_dtype, int64_t g_index_offset, float* out_scores, int64_t* out_index, void* workspace,
                   size_t workspace_bytes, int path, void* stream);
+/* Tensor path of the exact top-k (tcgen05 candidate generation + exact re-scoring + certificate):
+ *   q        [nq, d] queries in q_dtype
+ *   g_exact  [ng, d] the stored gallery (g_dtype) that scores are DEFINED on (same contract as above)
+ *   g_fp16   the same gallery in float16 for the tensor pass (== g_exact when g_dtype is DCLIP_F16)
+ *   gmax     device float: max gallery row norm, from dclip_max_row_norm (cache it per index)
+ *   flags    int32[nq]: 1 = the exactness certificate failed for that query (more than 32 near-ties):
+ *            re-run it with dclip_topk_ip on the FP32 path; n_flagged: device int32 count.
+ * Unflagged rows of out_scores / out_index are bit-identical to dclip_topk_ip(FP32).
+ * Needs d % 128 == 0, 128 <= d <= 768, k <= 16, ng < 2^26 per shard. */
+int dclip_max_row_norm(const void* x, int64_t n, int64_t d, int dtype, float* out, void* stream);
+size_t dclip_topk_ip_tc_workspace_bytes(int64_t nq, int64_t ng, int64_t d, int q_dtype);
+int dclip_topk_ip_tc(const void* q, int q_dtype, const void* g_exact, int g_dtype, const void* g_fp16, int64_t nq,
+                     int64_t ng, int64_t d, int64_t k, int64_t g_index_offset, const float* gmax, float* out_scores,
+                     int64_t* out_index, int32_t* flags, int32_t* n_flagged, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
 /* Merge `nlists` per-shard results ([nlists, nq, k] each) into one [nq, k] by (-score, +index). */
 int dclip_topk_merge(const float* in_scores, const int64_t* in_index, int64_t nlists, int64_t nq, int64_t k,
                      float* out_scores, int64_t* out_index, void* stream);
