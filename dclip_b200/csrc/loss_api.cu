@@ -37,7 +37,7 @@ int dclip_loss_prep(const void* x, const void* teacher, int64_t m, int64_t d, in
 
 size_t dclip_infonce_rowlse_workspace_bytes(int64_t m, int64_t n, int64_t d, int path) {
     int ns = simt_rowlse_nsplit(m, n, d);
-    if (path == DCLIP_PATH_TENSOR) ns = tc_nsplit(m, n, 1);
+    if (path == DCLIP_PATH_TENSOR) ns = stream_nsplit(m, n, 1);
     if (ns < 1) ns = 1;
     return 2 * align_up((size_t)ns * m * sizeof(float), 256) + 256;
 }
@@ -68,7 +68,7 @@ int dclip_infonce_rowlse(const void* x_hat, int64_t m, const void* y_hat, int64_
             return fail(DCLIP_ERR_UNSUPPORTED, "rowlse: tensor path needs d %% 128 == 0, 128 <= d <= 768 and temperature >= 0.025 (d=%lld tau=%g)", (long long)d, temperature);
         DCLIP_REQUIRE(aligned16(x_hat) && aligned16(y_hat), "rowlse: operands must be 16-byte aligned");
         cudaStream_t st = static_cast<cudaStream_t>(stream);
-        const int ns = tc_nsplit(m, n, 1);
+        const int ns = stream_nsplit(m, n, 1);
         Workspace ws(workspace, workspace_bytes);
         float* part = static_cast<float*>(ws.take((size_t)ns * m * sizeof(float)));
         if (!ws.ok()) return fail(DCLIP_ERR_WORKSPACE, "rowlse: workspace too small (%zu < %zu)", workspace_bytes, ws.used);
@@ -77,7 +77,7 @@ int dclip_infonce_rowlse(const void* x_hat, int64_t m, const void* y_hat, int64_
         a.m = m; a.n = n; a.d = d; a.inv_tau = 1.0f / temperature; a.row_offset = row_offset;
         const void* xs[2] = {x_hat, x_hat};
         const void* ys[2] = {y_hat, y_hat};
-        if (int e = launch_infonce_tc(0, 1, xs, ys, a, ns, st)) return e;
+        if (int e = launch_stream_tc(0, 1, xs, ys, a, ns, st)) return e;
         if (int e = launch_tc_lse_combine(part, ns, m, a.inv_tau, lse, st)) return e;
         if (diag) return launch_tc_diag(x_hat, y_hat, m, n, d, a.inv_tau, row_offset, diag, st);
         return DCLIP_OK;
@@ -181,8 +181,8 @@ size_t dclip_distill_loss_workspace_bytes(int64_t B, int64_t d, int path) {
     total += 4 * align_up((size_t)ns * B * 4, 256);         // partials
     total += 2 * align_up((size_t)B * d * 4, 256);          // dx_hat
     if (path == DCLIP_PATH_TENSOR) {
-        const int tns = tc_nsplit(B, B, 2);
-        total += 4 * align_up((size_t)tns * B * 4, 256);
+        const int tns = tc_nsplit(B, B, 2), fns = stream_nsplit(B, B, 2);
+        total += 4 * align_up((size_t)fns * B * 4, 256);
         if (tns > 1) total += align_up((size_t)2 * tns * B * d * 4, 256);
     }
     return total + 1024;
@@ -214,7 +214,8 @@ int dclip_distill_loss_fwd_bwd(const void* s_img, const void* s_txt, const void*
     float* vec[8];
     for (auto& v : vec) v = static_cast<float*>(ws.take((size_t)B * 4));
     float *inv_u = vec[0], *inv_v = vec[1], *cos_img = vec[2], *cos_txt = vec[3], *lse_u = vec[4], *lse_v = vec[5], *diag = vec[6];
-    const int ns = tensor ? tc_nsplit(B, B, 2) : simt_rowlse_nsplit(B, B, d);
+    const int ns = tensor ? stream_nsplit(B, B, 2) : simt_rowlse_nsplit(B, B, d);   // forward column splits
+    const int nsb = tensor ? tc_nsplit(B, B, 2) : 1;                                 // backward column splits
     if (ns == 0) return fail(DCLIP_ERR_UNSUPPORTED, "FP32 loss path supports d <= 1024 (got %lld)", (long long)d);
     float* part[4];
     for (auto& p : part) p = static_cast<float*>(ws.take((size_t)ns * B * 4));
@@ -222,9 +223,9 @@ int dclip_distill_loss_fwd_bwd(const void* s_img, const void* s_txt, const void*
     float* dv_hat = static_cast<float*>(ws.take((size_t)B * d * 4));
     float* du_part = du_hat;
     float* dv_part = dv_hat;
-    if (tensor && ns > 1 && d_s_img) {
-        du_part = static_cast<float*>(ws.take((size_t)2 * ns * B * d * 4));   // [side][split][B][d], sides contiguous
-        dv_part = du_part + (size_t)ns * B * d;
+    if (tensor && nsb > 1 && d_s_img) {
+        du_part = static_cast<float*>(ws.take((size_t)2 * nsb * B * d * 4));   // [side][split][B][d], sides contiguous
+        dv_part = du_part + (size_t)nsb * B * d;
     }
     if (!ws.ok()) return fail(DCLIP_ERR_WORKSPACE, "distill_loss: workspace too small (%zu < %zu)", workspace_bytes, ws.used);
     if (stats) { lse_u = stats; lse_v = stats + B; }
@@ -247,7 +248,7 @@ int dclip_distill_loss_fwd_bwd(const void* s_img, const void* s_txt, const void*
         fa.s[0] = TcSide{nullptr, nullptr, part[0]};
         fa.s[1] = TcSide{nullptr, nullptr, part[2]};
         fa.m = B; fa.n = B; fa.d = d; fa.inv_tau = 1.0f / temperature; fa.row_offset = 0;
-        if (int e = launch_infonce_tc(0, 2, xs2, ys2, fa, ns, st)) return e;
+        if (int e = launch_stream_tc(0, 2, xs2, ys2, fa, ns, st)) return e;
         FinalizeArgs fz{part[0], part[2], ns, B, fa.inv_tau, lse_u, lse_v,
                         SumsArgs{lse_u, lse_v, diag, t_img ? cos_img : nullptr, t_txt ? cos_txt : nullptr, B, nullptr, losses, w_img, w_txt, w_con}};
         if (int e = launch_tc_finalize(fz, st)) return e;
@@ -272,10 +273,10 @@ int dclip_distill_loss_fwd_bwd(const void* s_img, const void* s_txt, const void*
             ga.s[1] = TcSide{lse_v, lse_u, dv_part};
             ga.m = B; ga.n = B; ga.d = d; ga.inv_tau = 1.0f / temperature; ga.row_offset = 0;
             ga.out_scale = w_con / (2.0f * (float)B) / temperature * (1.0f / 8192.0f);
-            if (int e = launch_infonce_tc(1, 2, xs2, ys2, ga, ns, st)) return e;
-            if (ns > 1) {
-                if (int e = launch_tc_grad_combine(du_part, ns, B, d, du_hat, st)) return e;
-                if (int e = launch_tc_grad_combine(dv_part, ns, B, d, dv_hat, st)) return e;
+            if (int e = launch_infonce_tc(1, 2, xs2, ys2, ga, nsb, st)) return e;
+            if (nsb > 1) {
+                if (int e = launch_tc_grad_combine(du_part, nsb, B, d, du_hat, st)) return e;
+                if (int e = launch_tc_grad_combine(dv_part, nsb, B, d, dv_hat, st)) return e;
             }
         } else if (need_con) {
             GradArgs ga{};

@@ -72,6 +72,10 @@ int launch_tc_grad_combine(const float* part, int nsplit, int64_t m, int64_t d, 
 int launch_tc_diag(const void* x, const void* y, int64_t m, int64_t n, int64_t d, float inv_tau, int64_t row_offset, float* diag,
                    cudaStream_t st);
 int tc_check_error_flag(cudaStream_t st);
+// streaming 128 x 256 score-tile kernel (stream_tc.cu): mode 0 = row sums, mode 2 = top-32 candidates
+int stream_nsplit(int64_t m, int64_t n, int nsides);
+int launch_stream_tc(int mode, int nsides, const void* const x[2], const void* const y[2], const TcArgs& args, int nsplit,
+                     cudaStream_t st);
 
 int launch_loss_prep(const PrepArgs& a, int nsides, int dtype, int op_dtype, cudaStream_t st);
 // both sides of row i in one warp + diag[i] = u_hat_i . v_hat_i / tau from the rounded operands

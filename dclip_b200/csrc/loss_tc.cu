@@ -496,7 +496,7 @@ static size_t tc_smem_bytes(int64_t d, int mode) {
     return 1024 + (size_t)((d + 63) / 64) * kXBoxBytes + (size_t)kSlots * kSlotBytes + (mode != 0 ? 2 * kGBytes : 0) + 512;
 }
 
-static int* tc_error_flag() {   // one device int per device, lazily allocated, never freed
+int* tc_error_flag() {   // one device int per device, lazily allocated, never freed
     static thread_local int* flag[16] = {nullptr};
     int dev = 0;
     cudaGetDevice(&dev);

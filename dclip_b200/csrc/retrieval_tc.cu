@@ -4,9 +4,9 @@
 // training/image_tokenizer.py:262) at BASELINE configs[4] scale (10 M x 768 fp16 gallery sharded over
 // 8 GPUs, 100 k queries, top-10).
 //
-//   1. k_infonce_tc<2>: queries are the resident X block (64 per CTA), the gallery streams through the
-//      TMA ring as Y; fp16 operands, fp32 accumulation in TMEM.  The epilogue keeps, per query, the 32
-//      best APPROXIMATE scores (threshold filter + warp insertion); the score matrix never exists.
+//   1. k_stream_tc<2> (stream_tc.cu): 128 queries per CTA against 256-row gallery tiles streamed by TMA;
+//      fp16 operands, fp32 accumulation in TMEM.  Each epilogue thread owns one query and keeps its 32
+//      best APPROXIMATE scores (threshold filter); the score matrix never exists.
 //   2. candidate lists of the gallery splits are merged (32 per query).
 //   3. k_topk_rescore: every candidate is re-scored with the bit-exact contract of the FP32 path
 //      (fp32 fmaf chain over k ascending on the stored values), sorted by (-score, +index), top-k kept.
@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(256) k_max_row_norm(const T* __restrict__ x, i
     if (lane == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(best));
 }
 
-// merge the sorted candidate lists of the gallery splits: one warp per query
+// merge the (unsorted) candidate lists of the gallery splits into one sorted list: one warp per query
 __global__ void k_cand_merge(const float* __restrict__ in_s, const int32_t* __restrict__ in_i, int nsplit, int64_t nq,
                              float* __restrict__ out_s, int32_t* __restrict__ out_i) {
     const int lane = threadIdx.x & 31;
@@ -60,7 +60,7 @@ __global__ void k_cand_merge(const float* __restrict__ in_s, const int32_t* __re
             const float cs = __shfl_sync(0xffffffffu, s, src);
             const int32_t ci = __shfl_sync(0xffffffffu, gi, src);
             const unsigned after = __ballot_sync(0xffffffffu, cs > ls || (cs == ls && ci < li));
-            if (!after) break;      // lists are sorted: the rest of this list cannot enter either
+            if (!after) continue;   // (per-split lists are unsorted: every entry is tried)
             const int pos = __ffs(after) - 1;
             const float ps = __shfl_up_sync(0xffffffffu, ls, 1);
             const int32_t pi = __shfl_up_sync(0xffffffffu, li, 1);
@@ -117,8 +117,10 @@ __global__ void __launch_bounds__(256) k_topk_rescore(const TQ* __restrict__ q, 
         out_i[qi * k + lane] = -1;
     }
     // certificate
-    const float a32 = __shfl_sync(0xffffffffu, approx, 31);
-    const bool full = __shfl_sync(0xffffffffu, ci, 31) >= 0;
+    const bool full = nvalid == kCand;
+    float a32 = ci >= 0 ? approx : INFINITY;              // weakest kept approximate score (lists may be unsorted)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a32 = fminf(a32, __shfl_xor_sync(0xffffffffu, a32, o));
     const unsigned kth = __ballot_sync(0xffffffffu, rank == k - 1);
     float exact_k = -INFINITY;
     if (kth) exact_k = __shfl_sync(0xffffffffu, s, __ffs(kth) - 1);
@@ -129,14 +131,7 @@ __global__ void __launch_bounds__(256) k_topk_rescore(const TQ* __restrict__ q, 
     }
 }
 
-int tc_topk_nsplit(int64_t nq, int64_t ng) {
-    const int64_t row_ctas = ceil_div(nq, 64);
-    const int64_t ntiles = ceil_div(ng, 128);
-    int64_t want = sm_count() / (row_ctas > 0 ? row_ctas : 1);
-    if (want < 1) want = 1;
-    if (want > ntiles) want = ntiles;
-    return (int)want;
-}
+int tc_topk_nsplit(int64_t nq, int64_t ng) { return stream_nsplit(nq, ng, 1); }
 
 }  // namespace dclip
 
@@ -174,7 +169,7 @@ int dclip_topk_ip_tc(const void* q, int q_dtype, const void* g_exact, int g_dtyp
                      int32_t* flags, int32_t* n_flagged, void* workspace, size_t workspace_bytes, void* stream) {
     DCLIP_REQUIRE(q && g_exact && g_fp16 && gmax && out_scores && out_index && flags && n_flagged, "topk_ip_tc: null pointer");
     DCLIP_REQUIRE(k >= 1 && k <= 16, "topk_ip_tc: k must be in [1, 16] (32 candidates are re-scored)");
-    DCLIP_REQUIRE(d % 128 == 0 && d >= 128 && d <= 768, "topk_ip_tc: tensor path needs d %% 128 == 0 and 128 <= d <= 768 (got %lld)", (long long)d);
+    DCLIP_REQUIRE(d % 8 == 0 && d >= 64 && d <= 1024, "topk_ip_tc: tensor path needs d %% 8 == 0 and 64 <= d <= 1024 (got %lld)", (long long)d);
     DCLIP_REQUIRE(ng > 0 && ng < (1ll << 26), "topk_ip_tc: gallery shard must have 1 .. 2^26-1 rows (got %lld)", (long long)ng);
     DCLIP_REQUIRE(aligned16(g_fp16) && aligned16(workspace), "topk_ip_tc: pointers must be 16-byte aligned");
     if (!device_is_sm100()) return fail(DCLIP_ERR_ARCH, "tensor path needs an sm_100 device");
@@ -199,7 +194,7 @@ int dclip_topk_ip_tc(const void* q, int q_dtype, const void* g_exact, int g_dtyp
     a.cand_s = ps; a.cand_i = pi;
     const void* xs[2] = {qh, qh};
     const void* ys[2] = {g_fp16, g_fp16};
-    if (int e = launch_infonce_tc(2, 1, xs, ys, a, ns, st)) return e;
+    if (int e = launch_stream_tc(2, 1, xs, ys, a, ns, st)) return e;
     const float* cs = ps;
     const int32_t* ci = pi;
     if (ns > 1) {

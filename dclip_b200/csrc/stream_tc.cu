@@ -1,0 +1,242 @@
+// Streaming score-tile kernel (tcgen05 / TMEM / TMA): row log-sum-exp of the InfoNCE forward and the
+// approximate top-32 candidate lists of the retrieval path.
+//
+// Both consume S = X . Y^T tile by tile without keeping it: a CTA owns 128 rows of X (one TMEM lane /
+// epilogue thread each) and walks over 256-row tiles of Y:
+//     S[128 i x 256 j] = X_I . Y_J^T        (M = 128, N = 256, K = d in 64-column stages, fp16 in, fp32 acc)
+// The 128 x 256 tile shape is chosen for shared-memory bandwidth: tcgen05.mma re-reads both operands
+// from shared memory for every K = 16 step ((128 + N) * 32 B), and TMA writes share the same 128 B/clk,
+// so N = 256 moves 1.7x fewer shared-memory bytes per MAC than the 128 x 64 tiles of the backward
+// kernel (which is pinned to N = 64 by its TMEM-resident gradient accumulator; measured with
+// tools/tc_bench: N = 64 -> 53 cycles/MMA, N = 256 -> 132).  Neither operand is resident: a stage
+// of the 4-deep ring holds one X box (128 x 64, 16 KB) and one Y box (256 x 64, 32 KB); X_I is only
+// 128 x d and stays hot in L2.
+//
+// Warps: 0-3 TMA producers (one ring stage each), 4 MMA issuer (+ TMEM alloc), 5-8 epilogue.
+// TMEM: two 256-column S buffers, so the epilogue of tile t overlaps the MMAs of tile t+1.
+//   mode 0 (loss forward):  thread i adds exp2((s - 1) * log2e / tau) over the valid columns -> out[i]
+//   mode 2 (retrieval):     thread i keeps its query's 32 best approximate scores (threshold filter,
+//                           replace-the-minimum list in shared memory) -> cand_s / cand_i[i][32]
+#include "common.cuh"
+#include "loss_internal.h"
+#include "tcgen05.cuh"
+
+namespace dclip {
+using namespace tc;
+
+constexpr int SM_ROWS = 128;             // X rows per CTA (MMA M)
+constexpr int SN_COLS = 256;             // Y rows per tile (MMA N)
+constexpr int kStages = 4;
+constexpr int kXStageBytes = SM_ROWS * 128;   // 16 KB
+constexpr int kYStageBytes = SN_COLS * 128;   // 32 KB
+constexpr int kStageBytes = kXStageBytes + kYStageBytes;
+constexpr int kStreamThreads = (kStages + 1 + 4) * 32;
+constexpr int kListLen = 32;
+constexpr uint32_t kSpinS = 1u << 24;
+
+template <int kMode>
+__global__ void __launch_bounds__(kStreamThreads, 1)
+k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CUtensorMap tmy0,
+            const __grid_constant__ CUtensorMap tmx1, const __grid_constant__ CUtensorMap tmy1, const TcArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int side = blockIdx.z;
+    const CUtensorMap* tmx = side ? &tmx1 : &tmx0;
+    const CUtensorMap* tmy = side ? &tmy1 : &tmy0;
+    const TcSide S = a.s[side];
+    const int nkb = (int)((a.d + 63) / 64);
+
+    uint8_t* ring = smem;                                             // kStages x 48 KB
+    uint8_t* lists = ring + kStages * kStageBytes;                    // mode 2: [32][128] float + [32][128] int32 = 32 KB
+    uint8_t* tail = lists + (kMode == 2 ? 2 * kListLen * SM_ROWS * 4 : 0);
+    uint64_t* full = reinterpret_cast<uint64_t*>(tail);               // [kStages]
+    uint64_t* empty = full + kStages;                                 // [kStages]
+    uint64_t* s_full = empty + kStages;                               // [2]
+    uint64_t* s_empty = s_full + 2;                                   // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(s_empty + 2);
+
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+    const int64_t row0 = (int64_t)blockIdx.x * SM_ROWS;
+    const int64_t ntiles = (a.n + SN_COLS - 1) / SN_COLS;
+    const int64_t t_begin = (int64_t)blockIdx.y * a.tiles_per_split;
+    const int64_t t_end = min(ntiles, t_begin + a.tiles_per_split);
+    const int T = (int)max((int64_t)0, t_end - t_begin);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 128); }
+        fence_barrier_init();
+    }
+    if (warp == kStages) tmem_alloc(tmem_ptr, 512);
+    fence_before_thread_sync();
+    __syncthreads();
+    fence_after_thread_sync();
+    const uint32_t tmem = *tmem_ptr;
+    bool ok = true;
+
+    if (warp < kStages) {
+        // ===================== TMA producers: warp w owns ring stage w =====================
+        if (T > 0 && elect_one()) {
+            tma_prefetch_desc(tmx);
+            tma_prefetch_desc(tmy);
+            const int njobs = T * nkb;
+            uint8_t* dst = ring + (size_t)warp * kStageBytes;
+            uint32_t phase = 0;
+            for (int q = warp; q < njobs && ok; q += kStages, phase ^= 1) {
+                const int tile = q / nkb, kb = q - tile * nkb;
+                const int32_t j0 = (int32_t)((t_begin + tile) * SN_COLS);
+                ok = mbar_wait(&empty[warp], phase ^ 1, kSpinS);
+                mbar_arrive_expect_tx(&full[warp], kStageBytes);
+                tma_load_2d(dst, tmx, &full[warp], kb * 64, (int32_t)row0);
+                tma_load_2d(dst + kXStageBytes, tmy, &full[warp], kb * 64, j0);
+            }
+        }
+    } else if (warp == kStages) {
+        // ===================== MMA issuer =====================
+        if (T > 0 && elect_one()) {
+            const uint32_t idesc = make_idesc_f16(SM_ROWS, SN_COLS, kFmtF16, 0, 0);
+            const uint64_t hiK = make_smem_desc_hi(0, 1024, kSwizzle128B);
+            const uint32_t ring_addr = smem_u32(ring);
+            uint32_t stage = 0, phase = 0;
+            for (int t = 0; t < T && ok; ++t) {
+                const int b = t & 1;
+                ok = mbar_wait(&s_empty[b], ((t >> 1) & 1) ^ 1, kSpinS);
+                fence_after_thread_sync();
+                const uint32_t dcol = tmem + b * SN_COLS;
+                for (int kb = 0; kb < nkb && ok; ++kb) {
+                    ok = mbar_wait(&full[stage], phase, kSpinS);
+                    fence_after_thread_sync();
+                    const uint64_t da0 = smem_desc(hiK, ring_addr + stage * kStageBytes);
+                    const uint64_t db0 = smem_desc(hiK, ring_addr + stage * kStageBytes + kXStageBytes);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) umma_f16(dcol, da0 + (uint64_t)(ks * 2), db0 + (uint64_t)(ks * 2), idesc, (kb | ks) != 0);
+                    umma_commit(&empty[stage]);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&s_full[b]);
+            }
+        }
+    } else {
+        // ===================== epilogue: thread = one X row =====================
+        const int qd = warp & 3;                          // TMEM lane quadrant
+        const int et = qd * 32 + lane;                    // row inside the CTA block
+        const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
+        const int64_t grow = row0 + et;
+        const float c = a.inv_tau * 1.4426950408889634f;
+        float sum = 0.f;
+        // retrieval state: unsorted list of the 32 best in smem ([entry][row]: bank-conflict free),
+        // current minimum cached in registers
+        float* ls = reinterpret_cast<float*>(lists);
+        int32_t* li = reinterpret_cast<int32_t*>(lists + kListLen * SM_ROWS * 4);
+        int cnt = 0, mn_pos = 0;
+        float mn = -INFINITY;                             // threshold: -inf until the list is full
+        for (int t = 0; t < T && ok; ++t) {
+            const int b = t & 1;
+            const int64_t j0 = (t_begin + t) * SN_COLS;
+            const int ncols = (int)min((int64_t)SN_COLS, a.n - j0);
+            ok = mbar_wait(&s_full[b], (t >> 1) & 1, kSpinS);
+            ok = __all_sync(0xffffffffu, ok);
+            if (!ok) break;
+            fence_after_thread_sync();
+#pragma unroll 1
+            for (int c0 = 0; c0 < SN_COLS; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(tmem + lane_addr + b * SN_COLS + c0, r);
+                tmem_ld_wait();
+                if (c0 >= ncols) continue;                // warp-uniform: whole chunk beyond the last Y row
+                if (kMode == 0) {
+                    if (c0 + 32 <= ncols) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) sum += exp2f(fmaf(__uint_as_float(r[i]), c, -c));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (c0 + i < ncols) sum += exp2f(fmaf(__uint_as_float(r[i]), c, -c));
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float sv = __uint_as_float(r[i]);
+                        if (sv > mn && c0 + i < ncols) {
+                            const int32_t gi = (int32_t)(j0 + c0 + i);
+                            if (cnt < kListLen) {
+                                ls[cnt * SM_ROWS + et] = sv;
+                                li[cnt * SM_ROWS + et] = gi;
+                                ++cnt;
+                                if (cnt < kListLen) continue;
+                            } else {
+                                ls[mn_pos * SM_ROWS + et] = sv;
+                                li[mn_pos * SM_ROWS + et] = gi;
+                            }
+                            // list is full: find the new minimum (the threshold for everything that follows)
+                            float m2 = ls[et];
+                            int p2 = 0;
+                            for (int e = 1; e < kListLen; ++e) {
+                                const float v = ls[e * SM_ROWS + et];
+                                if (v < m2) { m2 = v; p2 = e; }
+                            }
+                            mn = m2;
+                            mn_pos = p2;
+                        }
+                    }
+                }
+            }
+            fence_before_thread_sync();
+            mbar_arrive(&s_empty[b]);                     // all of this thread's TMEM reads of buffer b are done
+        }
+        if (kMode == 0) {
+            if (grow < a.m) S.out[(int64_t)blockIdx.y * a.m + grow] = sum;
+        } else if (grow < a.m) {
+            const int64_t o = ((int64_t)blockIdx.y * a.m + grow) * kListLen;
+            for (int e = 0; e < kListLen; ++e) {
+                a.cand_s[o + e] = e < cnt ? ls[e * SM_ROWS + et] : -INFINITY;
+                a.cand_i[o + e] = e < cnt ? li[e * SM_ROWS + et] : -1;
+            }
+        }
+    }
+    if (!ok && lane == 0 && a.error_flag) atomicExch(a.error_flag, 1);
+    fence_before_thread_sync();
+    __syncthreads();
+    if (warp == kStages) tmem_dealloc(tmem, 512);
+}
+
+int stream_nsplit(int64_t m, int64_t n, int nsides) {
+    const int64_t row_ctas = ceil_div(m, SM_ROWS) * nsides;
+    const int64_t ntiles = ceil_div(n, SN_COLS);
+    int64_t want = sm_count() / (row_ctas > 0 ? row_ctas : 1);
+    if (want < 1) want = 1;
+    if (want > ntiles) want = ntiles;
+    return (int)want;
+}
+
+int* tc_error_flag();   // loss_tc.cu
+
+// mode 0: x/y per side are the fp16 operands, a.s[side].out = partial row sums [nsplit][m]
+// mode 2: a.cand_s / a.cand_i = candidate lists [nsplit][m][32]
+int launch_stream_tc(int mode, int nsides, const void* const x[2], const void* const y[2], const TcArgs& args_in, int nsplit, cudaStream_t st) {
+    if (!device_is_sm100()) return fail(DCLIP_ERR_ARCH, "tensor path needs an sm_100 device");
+    TcArgs a = args_in;
+    CUtensorMap tmx[2], tmy[2];
+    for (int s = 0; s < 2; ++s) {
+        const int src = s < nsides ? s : 0;
+        if (!make_tmap_2d_sw128(&tmx[s], x[src], (uint64_t)a.m, (uint64_t)a.d, SM_ROWS, 0) ||
+            !make_tmap_2d_sw128(&tmy[s], y[src], (uint64_t)a.n, (uint64_t)a.d, SN_COLS, 0))
+            return fail(DCLIP_ERR_CUDA, "cuTensorMapEncodeTiled failed (m=%lld n=%lld d=%lld)", (long long)a.m, (long long)a.n, (long long)a.d);
+    }
+    const int64_t ntiles = ceil_div(a.n, SN_COLS);
+    a.tiles_per_split = (int)ceil_div(ntiles, nsplit);
+    a.error_flag = tc_error_flag();
+    const size_t smem = 1024 + (size_t)kStages * kStageBytes + (mode == 2 ? 2 * kListLen * SM_ROWS * 4 : 0) + 256;
+    dim3 grid((unsigned)ceil_div(a.m, SM_ROWS), (unsigned)nsplit, (unsigned)nsides);
+    if (mode == 0) {
+        DCLIP_CUDA_OK(cudaFuncSetAttribute(k_stream_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_stream_tc<0><<<grid, kStreamThreads, smem, st>>>(tmx[0], tmy[0], tmx[1], tmy[1], a);
+    } else {
+        DCLIP_CUDA_OK(cudaFuncSetAttribute(k_stream_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_stream_tc<2><<<grid, kStreamThreads, smem, st>>>(tmx[0], tmy[0], tmx[1], tmy[1], a);
+    }
+    DCLIP_LAUNCH_OK("k_stream_tc");
+    return DCLIP_OK;
+}
+
+}  // namespace dclip

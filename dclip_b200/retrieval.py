@@ -115,7 +115,7 @@ class TensorGallery:
 def tensor_path_ok(q, g, k):
     """Shapes the tcgen05 retrieval kernel supports (otherwise the exact FP32 path is used)."""
     d = g.shape[1]
-    return (d % 128 == 0 and 128 <= d <= 768 and 1 <= k <= 16 and 0 < g.shape[0] < (1 << 26)
+    return (d % 8 == 0 and 64 <= d <= 1024 and 1 <= k <= 16 and 0 < g.shape[0] < (1 << 26)
             and q.dtype in (torch.float32, torch.float16) and g.dtype in (torch.float32, torch.float16)
             and _lib.load_library().dclip_device_supports_tensor_path(g.device.index or 0) == 1)
 
@@ -176,7 +176,7 @@ def topk_ip(q, g, k, g_index_offset=0, path="auto", gallery=None):
     use_tensor = path == "tensor" or (path == "auto" and g.shape[0] >= 16384 and tensor_path_ok(q, g, k))
     if use_tensor:
         if not tensor_path_ok(q, g, k):
-            raise RuntimeError("topk_ip: tensor path needs d % 128 == 0, 128 <= d <= 768, k <= 16, float16/float32 "
+            raise RuntimeError("topk_ip: tensor path needs d % 8 == 0, 64 <= d <= 1024, k <= 16, float16/float32 "
                                f"inputs and an sm_100 device (got q {tuple(q.shape)} {q.dtype}, g {tuple(g.shape)} {g.dtype}, k={k})")
         return _topk_tensor(q, gallery or TensorGallery(g), k, g_index_offset)
     return _topk_fp32(q, g, k, g_index_offset)

@@ -183,7 +183,7 @@ int dclip_topk_ip(const void* q, const void* g, int64_t nq, int64_t ng, int64_t 
  *   flags    int32[nq]: 1 = the exactness certificate failed for that query (more than 32 near-ties):
  *            re-run it with dclip_topk_ip on the FP32 path; n_flagged: device int32 count.
  * Unflagged rows of out_scores / out_index are bit-identical to dclip_topk_ip(FP32).
- * Needs d % 128 == 0, 128 <= d <= 768, k <= 16, ng < 2^26 per shard. */
+ * Needs d % 8 == 0, 64 <= d <= 1024, k <= 16, ng < 2^26 per shard. */
 int dclip_max_row_norm(const void* x, int64_t n, int64_t d, int dtype, float* out, void* stream);
 size_t dclip_topk_ip_tc_workspace_bytes(int64_t nq, int64_t ng, int64_t d, int q_dtype);
 int dclip_topk_ip_tc(const void* q, int q_dtype, const void* g_exact, int g_dtype, const void* g_fp16, int64_t nq,

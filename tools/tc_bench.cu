@@ -129,6 +129,87 @@ __global__ void __launch_bounds__(64) k_tma_rate(const __grid_constant__ CUtenso
     }
 }
 
+// multi-producer variant: warp w < nprod owns slot w (as the product kernels do); warp nprod consumes.
+__global__ void __launch_bounds__(256) k_tma_rate_mp(const __grid_constant__ CUtensorMap tm, int nprod, int boxes_per_slot, int jobs, int rows_total,
+                                                     long long* cycles, long long* latency) {
+    extern __shared__ uint8_t raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t full[16], empty[16];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < nprod; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        fence_barrier_init();
+    }
+    __syncthreads();
+    const int slot_bytes = boxes_per_slot * 16384;
+    const int ntiles = rows_total / 128;
+    const int w = uniform_warp_idx();
+    if (w < nprod && elect_one()) {
+        uint32_t phase = 0;
+        for (int j = w; j < jobs; j += nprod, phase ^= 1) {
+            if (!mbar_wait(&empty[w], phase ^ 1, 1u << 22)) break;
+            mbar_arrive_expect_tx(&full[w], slot_bytes);
+            const long long t0 = clock64();
+            for (int b = 0; b < boxes_per_slot; ++b)
+                tma_load_2d(smem + w * slot_bytes + b * 16384, &tm, &full[w], ((j % 6) * boxes_per_slot + b) * 64 % 768, ((j / 6) % ntiles) * 128);
+            if (j == w && latency) {           // first job of this producer: measure issue -> data-landed latency
+                mbar_wait(&full[w], 0, 1u << 22);
+                latency[blockIdx.x * 8 + w] = clock64() - t0;
+            }
+        }
+    } else if (w == nprod && elect_one()) {
+        uint32_t stage = 0, phase = 0;
+        const long long t0 = clock64();
+        bool ok = true;
+        for (int j = 0; j < jobs && ok; ++j) {
+            ok = mbar_wait(&full[stage], phase, 1u << 22);
+            mbar_arrive(&empty[stage]);
+            if (++stage == (uint32_t)nprod) { stage = 0; phase ^= 1; }
+        }
+        cycles[blockIdx.x] = ok ? clock64() - t0 : -1;
+    }
+}
+
+static void run_tma_mp() {
+    const int rows = 4096, cols = 768;
+    __half* d;
+    CK(cudaMalloc(&d, (size_t)rows * cols * 2));
+    CK(cudaMemset(d, 0, (size_t)rows * cols * 2));
+    CUtensorMap tm;
+    if (!make_tmap_2d_sw128(&tm, d, rows, cols, 128, 0)) { printf("tmap failed\n"); exit(2); }
+    long long *cyc, *lat;
+    CK(cudaMalloc(&cyc, 148 * 8));
+    CK(cudaMalloc(&lat, 148 * 8 * 8));
+    CK(cudaFuncSetAttribute(k_tma_rate_mp, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    int clk_khz = 0;
+    cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, 0);
+    for (int grid : {1, 148})
+        for (int cfg = 0; cfg < 5; ++cfg) {
+            const int nprod_[5] = {3, 6, 3, 6, 4};
+            const int bps_[5] = {2, 1, 4, 2, 3};
+            const int nprod = nprod_[cfg], bps = bps_[cfg];
+            if (nprod * bps * 16384 > 200 * 1024) continue;
+            const int jobs = 600;
+            CK(cudaMemset(cyc, 0, 148 * 8));
+            CK(cudaMemset(lat, 0, 148 * 64));
+            k_tma_rate_mp<<<grid, 256, 220 * 1024>>>(tm, nprod, bps, jobs, rows, cyc, lat);
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) { printf("CUDA ERROR %s\n", cudaGetErrorString(e)); exit(3); }
+            long long h[148], hl[148 * 8];
+            CK(cudaMemcpy(h, cyc, grid * 8, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(hl, lat, grid * 64, cudaMemcpyDeviceToHost));
+            double avg = 0; bool to = false;
+            for (int i = 0; i < grid; ++i) { avg += (double)h[i]; to |= h[i] < 0; }
+            avg /= grid;
+            double l = 0;
+            for (int i = 0; i < grid; ++i) l += (double)hl[i * 8];
+            l /= grid;
+            const double bpc = (double)jobs * bps * 16384 / avg;
+            printf("MP grid %-4d producers %-2d slotKB %-4d | %7.1f cycles/job  %7.1f B/clk/SM  %6.2f TB/s | first-load latency %6.0f cyc%s\n", grid, nprod,
+                   bps * 16, avg / jobs, bpc, bpc * grid * clk_khz * 1e3 / 1e12, l, to ? "  TIMEOUT" : "");
+            fflush(stdout);
+        }
+}
+
 static void run_tma() {
     const int rows = 4096, cols = 768;
     __half* d;
@@ -170,6 +251,7 @@ static void run_tma() {
 int main(int argc, char** argv) {
     if (argc >= 2 && !strcmp(argv[1], "mma")) { run_mma(); return 0; }
     if (argc >= 2 && !strcmp(argv[1], "tma")) { run_tma(); return 0; }
+    if (argc >= 2 && !strcmp(argv[1], "tmamp")) { run_tma_mp(); return 0; }
     printf("usage: tc_bench mma | tma\n");
     return 64;
 }
