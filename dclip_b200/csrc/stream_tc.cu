@@ -82,9 +82,21 @@ k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CU
             const int njobs = T * nkb;
             uint8_t* dst = ring + (size_t)warp * kStageBytes;
             uint32_t phase = 0;
+            // When Y does not fit in L2 (retrieval galleries) the row-block CTAs of a split all want the same
+            // boxes, so only kStages distinct boxes per split are in flight and the stream runs at DRAM
+            // LATENCY.  Each Y tile is therefore prefetched into L2 kPrefetchAhead tiles early by exactly one
+            // of the gridDim.x CTAs that walk this split (the others then hit L2).
+            constexpr int kPrefetchAhead = 16;
+            const bool prefetch = a.n * a.d * 2 > (int64_t)32 * 1024 * 1024;
             for (int q = warp; q < njobs && ok; q += kStages, phase ^= 1) {
                 const int tile = q / nkb, kb = q - tile * nkb;
                 const int32_t j0 = (int32_t)((t_begin + tile) * SN_COLS);
+                if (prefetch && kb == 0) {
+                    const int first = tile == 0 ? 0 : kPrefetchAhead;        // the first tile also covers 0 .. ahead-1
+                    for (int pt = tile + first; pt <= tile + kPrefetchAhead && pt < T; ++pt)
+                        if (pt % (int)gridDim.x == (int)blockIdx.x)
+                            for (int k2 = 0; k2 < nkb; ++k2) tma_prefetch_l2_2d(tmy, k2 * 64, (int32_t)((t_begin + pt) * SN_COLS));
+                }
                 ok = mbar_wait(&empty[warp], phase ^ 1, kSpinS);
                 mbar_arrive_expect_tx(&full[warp], kStageBytes);
                 tma_load_2d(dst, tmx, &full[warp], kb * 64, (int32_t)row0);
