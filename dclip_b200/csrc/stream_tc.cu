@@ -15,8 +15,9 @@
 // Warps: 0-3 TMA producers (one ring stage each), 4 MMA issuer (+ TMEM alloc), 5-8 epilogue.
 // TMEM: two 256-column S buffers, so the epilogue of tile t overlaps the MMAs of tile t+1.
 //   mode 0 (loss forward):  thread i adds exp2((s - 1) * log2e / tau) over the valid columns -> out[i]
-//   mode 2 (retrieval):     thread i keeps its query's 32 best approximate scores (threshold filter,
-//                           replace-the-minimum list in shared memory) -> cand_s / cand_i[i][32]
+//   mode 2 (retrieval):     thread i caches the admission threshold of its query; a warp-wide max test
+//                           rejects whole 32-score chunks, the rare hits are inserted warp-cooperatively
+//                           into that query's 32-entry list in shared memory -> cand_s / cand_i[i][32]
 #include "common.cuh"
 #include "loss_internal.h"
 #include "tcgen05.cuh"
@@ -136,12 +137,16 @@ k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CU
         const int64_t grow = row0 + et;
         const float c = a.inv_tau * 1.4426950408889634f;
         float sum = 0.f;
-        // retrieval state: unsorted list of the 32 best in smem ([entry][row]: bank-conflict free),
-        // current minimum cached in registers
+        // retrieval state: per X row an unsorted list of its 32 best approximate scores in shared memory,
+        // laid out [row][32] so that a whole warp can work on one row's list without bank conflicts; the
+        // owning thread caches the list minimum (= admission threshold) in a register.
         float* ls = reinterpret_cast<float*>(lists);
         int32_t* li = reinterpret_cast<int32_t*>(lists + kListLen * SM_ROWS * 4);
-        int cnt = 0, mn_pos = 0;
-        float mn = -INFINITY;                             // threshold: -inf until the list is full
+        float mn = -INFINITY;
+        if (kMode == 2) {
+            for (int e = 0; e < kListLen; ++e) { ls[et * kListLen + e] = -INFINITY; li[et * kListLen + e] = -1; }
+            __syncwarp();
+        }
         for (int t = 0; t < T && ok; ++t) {
             const int b = t & 1;
             const int64_t j0 = (t_begin + t) * SN_COLS;
@@ -166,29 +171,39 @@ k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CU
                             if (c0 + i < ncols) sum += exp2f(fmaf(__uint_as_float(r[i]), c, -c));
                     }
                 } else {
+                    // fast reject: does any of this thread's 32 scores beat its threshold?  (one max per
+                    // score, no divergence; almost always "no" for the whole warp once the lists are warm)
+                    float best = -INFINITY;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float sv = __uint_as_float(r[i]);
-                        if (sv > mn && c0 + i < ncols) {
-                            const int32_t gi = (int32_t)(j0 + c0 + i);
-                            if (cnt < kListLen) {
-                                ls[cnt * SM_ROWS + et] = sv;
-                                li[cnt * SM_ROWS + et] = gi;
-                                ++cnt;
-                                if (cnt < kListLen) continue;
-                            } else {
-                                ls[mn_pos * SM_ROWS + et] = sv;
-                                li[mn_pos * SM_ROWS + et] = gi;
+                    for (int i = 0; i < 32; ++i) best = fmaxf(best, (c0 + i < ncols) ? __uint_as_float(r[i]) : -INFINITY);
+                    if (__any_sync(0xffffffffu, best > mn)) {
+                        // slow path: the warp inserts the hits of one thread after the other, cooperatively
+                        // (lane e looks at entry e of that row's list: replace the minimum, find the new one)
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {        // (unrolled: r[] must stay in registers)
+                            const float sv = __uint_as_float(r[i]);
+                            unsigned hits = __ballot_sync(0xffffffffu, sv > mn && c0 + i < ncols);
+                            while (hits) {
+                                const int src = __ffs(hits) - 1;
+                                hits &= hits - 1;
+                                const float cs = __shfl_sync(0xffffffffu, sv, src);
+                                const int row = qd * 32 + src;
+                                float v = ls[row * kListLen + lane];
+                                float m = v;
+#pragma unroll
+                                for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                                const int pos = __ffs(__ballot_sync(0xffffffffu, v == m)) - 1;
+                                if (lane == pos) {
+                                    v = cs;
+                                    ls[row * kListLen + lane] = cs;
+                                    li[row * kListLen + lane] = (int32_t)(j0 + c0 + i);
+                                }
+                                float m2 = v;
+#pragma unroll
+                                for (int o = 16; o > 0; o >>= 1) m2 = fminf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+                                if (lane == src) mn = m2;
+                                __syncwarp();
                             }
-                            // list is full: find the new minimum (the threshold for everything that follows)
-                            float m2 = ls[et];
-                            int p2 = 0;
-                            for (int e = 1; e < kListLen; ++e) {
-                                const float v = ls[e * SM_ROWS + et];
-                                if (v < m2) { m2 = v; p2 = e; }
-                            }
-                            mn = m2;
-                            mn_pos = p2;
                         }
                     }
                 }
@@ -198,11 +213,14 @@ k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CU
         }
         if (kMode == 0) {
             if (grow < a.m) S.out[(int64_t)blockIdx.y * a.m + grow] = sum;
-        } else if (grow < a.m) {
-            const int64_t o = ((int64_t)blockIdx.y * a.m + grow) * kListLen;
-            for (int e = 0; e < kListLen; ++e) {
-                a.cand_s[o + e] = e < cnt ? ls[e * SM_ROWS + et] : -INFINITY;
-                a.cand_i[o + e] = e < cnt ? li[e * SM_ROWS + et] : -1;
+        } else {
+            __syncwarp();
+            if (grow < a.m) {
+                const int64_t o = ((int64_t)blockIdx.y * a.m + grow) * kListLen;
+                for (int e = 0; e < kListLen; ++e) {
+                    a.cand_s[o + e] = ls[et * kListLen + e];
+                    a.cand_i[o + e] = li[et * kListLen + e];
+                }
             }
         }
     }
