@@ -72,6 +72,24 @@ __global__ void k_cand_merge(const float* __restrict__ in_s, const int32_t* __re
     out_i[q * kCand + lane] = li == INT32_MAX ? -1 : li;
 }
 
+template <typename T> __device__ __forceinline__ void ld8(const T* p, float (&v)[8]);
+template <> __device__ __forceinline__ void ld8<float>(const float* p, float (&v)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <> __device__ __forceinline__ void ld8<__half>(const __half* p, float (&v)[8]) {
+    const uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+    const __half2* h = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+template <> __device__ __forceinline__ void ld8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+
 // exact re-scoring + certificate: one warp per query, lane l owns candidate l
 template <typename TQ, typename TG>
 __global__ void __launch_bounds__(256) k_topk_rescore(const TQ* __restrict__ q, const TG* __restrict__ g, int64_t nq, int64_t d, int k,
@@ -94,7 +112,12 @@ __global__ void __launch_bounds__(256) k_topk_rescore(const TQ* __restrict__ q, 
     if (ci >= 0) {
         const TG* gr = g + (int64_t)ci * d;
         float acc = 0.f;
-        for (int64_t c = 0; c < d; ++c) acc = fmaf(qs[c], to_f32<TG>(gr[c]), acc);      // the contract's chain, k ascending
+        for (int64_t c = 0; c < d; c += 8) {          // 16/32-byte loads; the fma chain itself stays k-ascending (the contract)
+            float gv[8];
+            ld8<TG>(gr + c, gv);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc = fmaf(qs[c + e], gv[e], acc);
+        }
         s = acc;
     }
     const int64_t gi = ci >= 0 ? g_index_offset + ci : INT64_MAX;

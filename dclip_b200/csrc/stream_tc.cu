@@ -230,13 +230,28 @@ k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CU
     if (warp == kStages) tmem_dealloc(tmem, 512);
 }
 
+// Column splits: enough CTAs to fill the SMs when there are few row blocks; with many row blocks the
+// smallest split count (<= 4) whose grid fills >= 95 % of its last wave (782 row blocks x 1 split
+// would leave the 6th wave 28 % full; x 2 fills 96 %).
 int stream_nsplit(int64_t m, int64_t n, int nsides) {
     const int64_t row_ctas = ceil_div(m, SM_ROWS) * nsides;
     const int64_t ntiles = ceil_div(n, SN_COLS);
-    int64_t want = sm_count() / (row_ctas > 0 ? row_ctas : 1);
-    if (want < 1) want = 1;
-    if (want > ntiles) want = ntiles;
-    return (int)want;
+    const int64_t sms = sm_count();
+    if (row_ctas <= 0) return 1;
+    if (row_ctas < sms) {
+        int64_t want = sms / row_ctas;
+        if (want > ntiles) want = ntiles;
+        return (int)(want < 1 ? 1 : want);
+    }
+    int best = 1;
+    double best_eff = 0.0;
+    for (int ns = 1; ns <= 4 && ns <= ntiles; ++ns) {
+        const double ctas = (double)(row_ctas * ns);
+        const double eff = ctas / (double)(ceil_div(row_ctas * ns, sms) * sms);
+        if (eff > best_eff + 1e-9) { best_eff = eff; best = ns; }
+        if (eff >= 0.95) { best = ns; break; }
+    }
+    return best;
 }
 
 int* tc_error_flag();   // loss_tc.cu
