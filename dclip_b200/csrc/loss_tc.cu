@@ -54,9 +54,8 @@ struct Pipe {
 // kC = thread-block cluster size along the row-block axis.  The kC CTAs of a cluster own different
 // row blocks but walk the same Y tiles, so each loads 1/kC of every ring slot and multicasts it to
 // all of them: L2 -> SM traffic per CTA drops by kC (the kernel is otherwise bound by it).
-// kMode: 0 = loss forward (row sums), 1 = loss backward, 2 = retrieval (approximate top-32 candidate
-// lists per X row: the same TMA -> tcgen05 pipeline with queries as the resident X block and the
-// gallery streaming as Y; see retrieval_tc.cu for the exact re-scoring that follows).
+// kMode: 1 = loss backward (the product path).  0 = row sums with the same 128 x 64 tiles: superseded by
+// the 128 x 256 streaming kernel of stream_tc.cu for the forward and kept only as a cross-check.
 template <int kMode, int kC>
 __global__ void __launch_bounds__(kTcThreads, 1)
 k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CUtensorMap tmy0,
@@ -69,7 +68,6 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
     const CUtensorMap* tmy = side ? &tmy1 : &tmy0;
     const CUtensorMap* tmh = side ? &tmh1 : &tmh0;      // same matrix as tmy, 64-row boxes (kC == 4)
     constexpr bool kBwd = kMode == 1;
-    constexpr bool kTopk = kMode == 2;
     const TcSide S = a.s[side];
     const uint32_t crank = kC > 1 ? cluster_ctarank() : 0;
     constexpr uint16_t kMask = (uint16_t)((1u << kC) - 1);
@@ -80,7 +78,7 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
     uint8_t* xs = smem;                                   // resident X_I: nkb boxes of 8 KB
     uint8_t* ring = xs + (size_t)nkb * kXBoxBytes;        // kSlots x 32 KB
     uint8_t* gs = ring + kSlots * kSlotBytes;             // 2 x 16 KB (bwd)
-    uint8_t* tail = gs + ((kBwd || kTopk) ? 2 * kGBytes : 0);
+    uint8_t* tail = gs + (kBwd ? 2 * kGBytes : 0);
     uint64_t* full = reinterpret_cast<uint64_t*>(tail);   // [kSlots]
     uint64_t* empty = full + kSlots;                      // [kSlots]
     uint64_t* s_full = empty + kSlots;                    // [2]
@@ -223,19 +221,6 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
 #pragma unroll
                 for (int i = 0; i < NI; ++i) sums[i] = 0.f;
             }
-            // retrieval mode: per-query sorted candidate lists (32 best approximate scores) in shared memory
-            float* lst_s = reinterpret_cast<float*>(gs);                  // [NI][32]
-            int32_t* lst_i = reinterpret_cast<int32_t*>(gs + 8192);       // [NI][32]
-            float* que_s = reinterpret_cast<float*>(gs + 16384);          // [2048] pending candidates of one chunk
-            uint32_t* que_k = reinterpret_cast<uint32_t*>(gs + 24576);    // [2048] (query << 26) | gallery row
-            float* thr = a_s;                                             // [NI] current 32nd-best score
-            int* qcount = reinterpret_cast<int*>(a_s + NI);
-            if (kTopk) {
-                for (int idx = et; idx < NI * 32; idx += 128) { lst_s[idx] = -INFINITY; lst_i[idx] = INT32_MAX; }
-                if (et < NI) thr[et] = -INFINITY;
-                if (et == 0) *qcount = 0;
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-            }
             if (kBwd) {
                 if (et < NI) {
                     const int64_t gi = row0 + et;
@@ -263,59 +248,6 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
                     if (jvalid) {
 #pragma unroll
                         for (int i = 0; i < NI; ++i) sums[i] += exp2f(fmaf(__uint_as_float(r[i]), c, -c));
-                    }
-                } else if (kTopk) {
-                    // threshold filter: a score enters the queue only if it beats the query's current 32nd
-                    // best; 16 queries per chunk bound the queue at 128 x 16 = 2048 entries.
-#pragma unroll
-                    for (int ch = 0; ch < 4; ++ch) {
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) {
-                            const int i = ch * 16 + e;
-                            const float sv = __uint_as_float(r[i]);
-                            if (jvalid && sv > thr[i]) {
-                                const int slot = atomicAdd(qcount, 1);
-                                que_s[slot] = sv;
-                                que_k[slot] = (static_cast<uint32_t>(i) << 26) | static_cast<uint32_t>(gj);
-                            }
-                        }
-                        asm volatile("bar.sync 1, 128;" ::: "memory");
-                        const int nq_pending = *qcount;
-                        if (nq_pending > 0) {
-                            // warp w drains the candidates of queries q with (q & 3) == w: one owner per list
-                            for (int base = 0; base < nq_pending; base += 32) {
-                                const int e = base + lane;
-                                const bool valid = e < nq_pending;
-                                const uint32_t key = valid ? que_k[e] : 0u;
-                                const float sc = valid ? que_s[e] : 0.f;
-                                unsigned mask = __ballot_sync(0xffffffffu, valid && (((key >> 26) & 3u) == (uint32_t)q));
-                                while (mask) {
-                                    const int src = __ffs(mask) - 1;
-                                    mask &= mask - 1;
-                                    const float cs = __shfl_sync(0xffffffffu, sc, src);
-                                    const uint32_t ck = __shfl_sync(0xffffffffu, key, src);
-                                    const int cq = (int)(ck >> 26);
-                                    const int32_t ci = (int32_t)(ck & 0x3FFFFFFu);
-                                    float ls = lst_s[cq * 32 + lane];
-                                    int32_t li = lst_i[cq * 32 + lane];
-                                    const unsigned after = __ballot_sync(0xffffffffu, cs > ls || (cs == ls && ci < li));
-                                    if (after) {
-                                        const int pos = __ffs(after) - 1;
-                                        const float ps = __shfl_up_sync(0xffffffffu, ls, 1);
-                                        const int32_t pi = __shfl_up_sync(0xffffffffu, li, 1);
-                                        if (lane == pos) { ls = cs; li = ci; }
-                                        else if (lane > pos) { ls = ps; li = pi; }
-                                        lst_s[cq * 32 + lane] = ls;
-                                        lst_i[cq * 32 + lane] = li;
-                                        if (lane == 31) thr[cq] = ls;
-                                    }
-                                    __syncwarp();
-                                }
-                            }
-                            asm volatile("bar.sync 1, 128;" ::: "memory");
-                            if (et == 0) *qcount = 0;
-                            asm volatile("bar.sync 1, 128;" ::: "memory");
-                        }
                     }
                 } else {
                     ok = ok && mbar_wait(&g_empty[b], ((t >> 1) & 1) ^ 1, kSpin);
@@ -350,17 +282,7 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
                     mbar_arrive(&g_full[b]);
                 }
             }
-            if (kTopk) {
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                for (int idx = et; idx < NI * 32; idx += 128) {
-                    const int64_t gq = row0 + (idx >> 5);
-                    if (gq < a.m) {
-                        const int64_t o = ((int64_t)blockIdx.y * a.m + gq) * 32 + (idx & 31);
-                        a.cand_s[o] = lst_s[idx];
-                        a.cand_i[o] = lst_i[idx] == INT32_MAX ? -1 : lst_i[idx];
-                    }
-                }
-            } else if (kMode == 0) {
+            if (kMode == 0) {
                 // cross-thread reduction of the per-column sums: stage through the (now idle) ring
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 float* red = reinterpret_cast<float*>(ring);          // [128][NI + 1]
@@ -398,16 +320,7 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
     } else if (warp >= 4) {
         // empty column range (only possible with an over-split grid): contribute zeros
         const int et = (warp & 3) * 32 + lane;
-        if (kTopk) {
-            for (int idx = et; idx < NI * 32; idx += 128) {
-                const int64_t gq = row0 + (idx >> 5);
-                if (gq < a.m) {
-                    const int64_t o = ((int64_t)blockIdx.y * a.m + gq) * 32 + (idx & 31);
-                    a.cand_s[o] = -INFINITY;
-                    a.cand_i[o] = -1;
-                }
-            }
-        } else if (kMode == 0) {
+        if (kMode == 0) {
             if (et < NI && row0 + et < a.m) S.out[(int64_t)blockIdx.y * a.m + row0 + et] = 0.f;
         } else {
             float* outp = S.out + (int64_t)blockIdx.y * a.m * a.d;
@@ -542,10 +455,8 @@ int launch_infonce_tc(int mode, int nsides, const void* const x[2], const void* 
     } while (0)
     if (mode == 1) {
         if (C == 1) DCLIP_TC_LAUNCH(1, 1); else if (C == 2) DCLIP_TC_LAUNCH(1, 2); else DCLIP_TC_LAUNCH(1, 4);
-    } else if (mode == 0) {
-        if (C == 1) DCLIP_TC_LAUNCH(0, 1); else if (C == 2) DCLIP_TC_LAUNCH(0, 2); else DCLIP_TC_LAUNCH(0, 4);
     } else {
-        if (C == 1) DCLIP_TC_LAUNCH(2, 1); else if (C == 2) DCLIP_TC_LAUNCH(2, 2); else DCLIP_TC_LAUNCH(2, 4);
+        if (C == 1) DCLIP_TC_LAUNCH(0, 1); else if (C == 2) DCLIP_TC_LAUNCH(0, 2); else DCLIP_TC_LAUNCH(0, 4);
     }
 #undef DCLIP_TC_LAUNCH
     DCLIP_LAUNCH_OK("k_infonce_tc");
