@@ -45,7 +45,7 @@ fi
 
 if has ncu; then
   P=fp32; [ "$TENSOR_OK" = "0" ] && P=tensor
-  CMD="python bench.py --steps 2 --warmup 3 --path $P --no-retrieval --no-cpu-baseline"
+  CMD="python bench.py --steps 2 --warmup 3 --path $P --no-retrieval --no-cpu-baseline --no-graph"
   timeout 600 $CMD > $OUT/ncu_plain.log 2>&1 && \
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$P.csv $CMD > $OUT/ncu_run.log 2>&1
   echo "ncu exit=$?"; tail -3 $OUT/ncu_run.log
@@ -67,10 +67,15 @@ PY
 fi
 
 if has ncufull; then
-  # one full capture of the dominant kernel (backward contraction), after the plain run passed
-  CMD="python bench.py --steps 1 --warmup 3 --path tensor --no-retrieval --no-cpu-baseline"
+  # one full capture of the tensor-path kernels of the loss step (after the plain run passed) ...
+  CMD="python bench.py --steps 1 --warmup 3 --path tensor --no-retrieval --no-cpu-baseline --no-graph"
   timeout 600 $CMD > $OUT/ncufull_plain.log 2>&1 && \
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_infonce_tc -s 4 -c 2 -f -o $OUT/prof_infonce_tc $CMD > $OUT/ncufull_run.log 2>&1
-  echo "ncufull exit=$?"; tail -3 $OUT/ncufull_run.log
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_infonce_tc|k_stream_tc" -s 6 -c 2 -f -o $OUT/prof_loss_tc $CMD > $OUT/ncufull_run.log 2>&1
+  echo "ncufull loss exit=$?"; tail -2 $OUT/ncufull_run.log
+  # ... and of the retrieval streaming kernel
+  CMD2="python tools/prof_retrieval.py 1000000 16384"
+  timeout 600 $CMD2 > $OUT/ncufull2_plain.log 2>&1 && \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_stream_tc -s 2 -c 1 -f -o $OUT/prof_retrieval_tc $CMD2 > $OUT/ncufull2_run.log 2>&1
+  echo "ncufull retrieval exit=$?"; tail -2 $OUT/ncufull2_run.log
 fi
 echo "gpu_round done"
