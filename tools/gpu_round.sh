@@ -44,7 +44,7 @@ if has bench; then
 fi
 
 if has ncu; then
-  P=fp32; [ "$TENSOR_OK" = "0" ] && P=tensor
+  P=${NCU_PATH:-tensor}
   CMD="python bench.py --steps 2 --warmup 3 --path $P --no-retrieval --no-cpu-baseline --no-graph"
   timeout 600 $CMD > $OUT/ncu_plain.log 2>&1 && \
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$P.csv $CMD > $OUT/ncu_run.log 2>&1
