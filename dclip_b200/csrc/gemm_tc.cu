@@ -1,0 +1,211 @@
+// Grouped tcgen05 GEMM for the cross-attention projections and their gradients (16-bit operands,
+// fp32 accumulation in TMEM, fp32 output):
+//     C[M, N] = A'(M, K) . B'(K, N) (+ bias[n]) (+ residual[m, n])        for up to 8 problems per launch
+// replacing the cuBLAS calls under nn.MultiheadAttention's in-/out-projections
+// (training/patch_text_aggregation.py:33,42) and the autograd GEMMs of their backward.
+//
+// Operand storage (row-major matrices, loaded by TMA with SWIZZLE_128B):
+//   A K-major  : A stored [M, K]  (activations X, dY)          box [128 m  x 64 k]
+//   A MN-major : A stored [K, M]  (dY^T for weight gradients)  2 boxes [64 k x 64 m], LBO = 8 KB
+//   B K-major  : B stored [N, K]  (nn.Linear weights)          box [256 n  x 64 k]
+//   B MN-major : B stored [K, N]  (X for dW, W for dX)         4 boxes [64 k x 64 n], LBO = 8 KB
+// (the MN-major canonical layout is the same bytes TMA writes for a [k rows x 64 columns] box; both
+// were validated against a CPU GEMM with tools/tc_probe).  Tile 128 x 256, K in 64-wide stages, 4-stage
+// ring, 4 producer warps, 1 MMA-issuer warp, 4 epilogue warps (thread = output row).  One CTA per tile.
+#include "common.cuh"
+#include "gemm_tc.h"
+#include "tcgen05.cuh"
+
+namespace dclip {
+using namespace tc;
+
+constexpr int GM = 128, GN = 256, GKS = 64;
+constexpr int kGStages = 4;
+constexpr int kGAStage = GM * 128;          // 16 KB
+constexpr int kGBStage = GN * 128;          // 32 KB
+constexpr int kGStageBytes = kGAStage + kGBStage;
+constexpr int kGThreads = (kGStages + 1 + 4) * 32;
+constexpr uint32_t kSpinG = 1u << 24;
+
+struct TcGemmDev {
+    float* C; const float* bias; const float* residual;
+    int M, N, K, ldc, ldr;
+    int a_mn, b_mn;
+    int tiles_n, tile_begin;      // tiles of this problem occupy [tile_begin, tile_begin + tiles_m * tiles_n)
+    int accumulate;
+    void* C16; int c16_kind;      // optional 16-bit copy of C (0 none, 1 bf16, 2 fp16), same ldc
+};
+struct TcGemmArgs {
+    CUtensorMap ta[kTcGemmMax], tb[kTcGemmMax];
+    TcGemmDev p[kTcGemmMax];
+    int count;
+    int ab_fmt;                   // kFmtBF16 / kFmtF16
+    int* error_flag;
+};
+
+__global__ void __launch_bounds__(kGThreads, 1) k_gemm_tc(const __grid_constant__ TcGemmArgs g) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(ring + kGStages * kGStageBytes);
+    uint64_t* empty = full + kGStages;
+    uint64_t* acc_full = empty + kGStages;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+    // which problem / tile
+    int pi = 0;
+    for (int i = 1; i < g.count; ++i)
+        if ((int)blockIdx.x >= g.p[i].tile_begin) pi = i;
+    const TcGemmDev& P = g.p[pi];
+    const int local = (int)blockIdx.x - P.tile_begin;
+    const int tm = local / P.tiles_n, tn = local - tm * P.tiles_n;
+    const int m0 = tm * GM, n0 = tn * GN;
+    const int nkb = (P.K + GKS - 1) / GKS;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kGStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == kGStages) tmem_alloc(tmem_ptr, 256);
+    fence_before_thread_sync();
+    __syncthreads();
+    fence_after_thread_sync();
+    const uint32_t tmem = *tmem_ptr;
+    bool ok = true;
+
+    if (warp < kGStages) {
+        if (elect_one()) {
+            const CUtensorMap* ta = &g.ta[pi];
+            const CUtensorMap* tb = &g.tb[pi];
+            tma_prefetch_desc(ta);
+            tma_prefetch_desc(tb);
+            uint8_t* dst = ring + (size_t)warp * kGStageBytes;
+            uint32_t phase = 0;
+            for (int kb = warp; kb < nkb && ok; kb += kGStages, phase ^= 1) {
+                const int k0 = kb * GKS;
+                ok = mbar_wait(&empty[warp], phase ^ 1, kSpinG);
+                mbar_arrive_expect_tx(&full[warp], kGStageBytes);
+                if (!P.a_mn) tma_load_2d(dst, ta, &full[warp], k0, m0);                     // [128 m x 64 k]
+                else
+                    for (int h = 0; h < 2; ++h) tma_load_2d(dst + h * 8192, ta, &full[warp], m0 + h * 64, k0);   // [64 k x 64 m]
+                if (!P.b_mn) tma_load_2d(dst + kGAStage, tb, &full[warp], k0, n0);           // [256 n x 64 k]
+                else
+                    for (int h = 0; h < 4; ++h) tma_load_2d(dst + kGAStage + h * 8192, tb, &full[warp], n0 + h * 64, k0);
+            }
+        }
+    } else if (warp == kGStages) {
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc_f16(GM, GN, (uint32_t)g.ab_fmt, (uint32_t)P.a_mn, (uint32_t)P.b_mn);
+            const uint64_t hiA = make_smem_desc_hi(P.a_mn ? 8192 : 0, 1024, kSwizzle128B);
+            const uint64_t hiB = make_smem_desc_hi(P.b_mn ? 8192 : 0, 1024, kSwizzle128B);
+            const uint32_t stepA = P.a_mn ? 128u : 2u, stepB = P.b_mn ? 128u : 2u;   // per K=16 step, >>4 encoded
+            const uint32_t ring_addr = smem_u32(ring);
+            uint32_t stage = 0, phase = 0;
+            for (int kb = 0; kb < nkb && ok; ++kb) {
+                ok = mbar_wait(&full[stage], phase, kSpinG);
+                fence_after_thread_sync();
+                const uint64_t da0 = smem_desc(hiA, ring_addr + stage * kGStageBytes);
+                const uint64_t db0 = smem_desc(hiB, ring_addr + stage * kGStageBytes + kGAStage);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) umma_f16(tmem, da0 + (uint64_t)(ks * stepA), db0 + (uint64_t)(ks * stepB), idesc, (kb | ks) != 0);
+                umma_commit(&empty[stage]);
+                if (++stage == kGStages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(acc_full);
+        }
+    } else {
+        const int qd = warp & 3;
+        const int row = m0 + qd * 32 + lane;
+        const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
+        ok = mbar_wait(acc_full, 0, kSpinG);
+        ok = __all_sync(0xffffffffu, ok);
+        if (ok) {
+            fence_after_thread_sync();
+#pragma unroll 1
+            for (int c0 = 0; c0 < GN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(tmem + lane_addr + c0, r);
+                tmem_ld_wait();
+                if (row < P.M && n0 + c0 < P.N) {
+                    float* crow = P.C + (size_t)row * P.ldc + n0 + c0;
+                    const float* rrow = P.residual ? P.residual + (size_t)row * P.ldr + n0 + c0 : nullptr;
+                    float v[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        v[i] = __uint_as_float(r[i]);
+                        if (n0 + c0 + i < P.N) {
+                            if (P.bias) v[i] += P.bias[n0 + c0 + i];
+                            if (rrow) v[i] += rrow[i];
+                            if (P.accumulate) v[i] += crow[i];
+                        }
+                    }
+                    if (n0 + c0 + 32 <= P.N) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(crow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        if (P.c16_kind == 1) {
+                            __nv_bfloat16* o = static_cast<__nv_bfloat16*>(P.C16) + (size_t)row * P.ldc + n0 + c0;
+#pragma unroll
+                            for (int i = 0; i < 32; i += 2) *reinterpret_cast<__nv_bfloat162*>(o + i) = __floats2bfloat162_rn(v[i], v[i + 1]);
+                        } else if (P.c16_kind == 2) {
+                            __half* o = static_cast<__half*>(P.C16) + (size_t)row * P.ldc + n0 + c0;
+#pragma unroll
+                            for (int i = 0; i < 32; i += 2) *reinterpret_cast<__half2*>(o + i) = __floats2half2_rn(v[i], v[i + 1]);
+                        }
+                    } else {
+                        for (int i = 0; i < 32 && n0 + c0 + i < P.N; ++i) {
+                            crow[i] = v[i];
+                            if (P.c16_kind == 1) static_cast<__nv_bfloat16*>(P.C16)[(size_t)row * P.ldc + n0 + c0 + i] = __float2bfloat16_rn(v[i]);
+                            else if (P.c16_kind == 2) static_cast<__half*>(P.C16)[(size_t)row * P.ldc + n0 + c0 + i] = __float2half_rn(v[i]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (!ok && lane == 0 && g.error_flag) atomicExch(g.error_flag, 1);
+    fence_before_thread_sync();
+    __syncthreads();
+    if (warp == kGStages) tmem_dealloc(tmem, 256);
+}
+
+int* tc_error_flag();   // loss_tc.cu
+
+// dtype16: 1 = bf16, 2 = fp16 (dclip_dtype values)
+int launch_gemm_tc(const TcGemmProblem* probs, int count, int dtype16, cudaStream_t st) {
+    if (count < 1 || count > kTcGemmMax) return fail(DCLIP_ERR_INVALID, "gemm_tc: 1..%d problems per launch", kTcGemmMax);
+    if (!device_is_sm100()) return fail(DCLIP_ERR_ARCH, "tensor path needs an sm_100 device");
+    TcGemmArgs g{};
+    g.count = count;
+    g.ab_fmt = dtype16 == DCLIP_BF16 ? (int)kFmtBF16 : (int)kFmtF16;
+    g.error_flag = tc_error_flag();
+    const int dt = dtype16 == DCLIP_BF16 ? 1 : 0;
+    int tiles = 0;
+    for (int i = 0; i < count; ++i) {
+        const TcGemmProblem& q = probs[i];
+        if (q.M <= 0 || q.N <= 0 || q.K <= 0) return fail(DCLIP_ERR_INVALID, "gemm_tc: empty problem %d", i);
+        if (q.lda % 8 || q.ldb % 8 || q.ldc % 4) return fail(DCLIP_ERR_INVALID, "gemm_tc: leading dimensions must keep 16-byte row alignment");
+        bool okm;
+        // A: K-major stored [M, K] (rows = M, cols = K); MN-major stored [K, M]
+        if (!q.a_mn) okm = make_tmap_2d_sw128_ld(&g.ta[i], q.A, (uint64_t)q.M, (uint64_t)q.K, (uint64_t)q.lda, GM, dt);
+        else okm = make_tmap_2d_sw128_ld(&g.ta[i], q.A, (uint64_t)q.K, (uint64_t)q.M, (uint64_t)q.lda, GKS, dt);
+        if (!q.b_mn) okm = okm && make_tmap_2d_sw128_ld(&g.tb[i], q.B, (uint64_t)q.N, (uint64_t)q.K, (uint64_t)q.ldb, GN, dt);
+        else okm = okm && make_tmap_2d_sw128_ld(&g.tb[i], q.B, (uint64_t)q.K, (uint64_t)q.N, (uint64_t)q.ldb, GKS, dt);
+        if (!okm) return fail(DCLIP_ERR_CUDA, "gemm_tc: cuTensorMapEncodeTiled failed for problem %d", i);
+        TcGemmDev& d = g.p[i];
+        d.C = q.C; d.bias = q.bias; d.residual = q.residual;
+        d.M = q.M; d.N = q.N; d.K = q.K; d.ldc = q.ldc; d.ldr = q.ldr;
+        d.a_mn = q.a_mn; d.b_mn = q.b_mn; d.accumulate = q.accumulate;
+        d.C16 = q.C16; d.c16_kind = q.C16 ? (dtype16 == DCLIP_BF16 ? 1 : 2) : 0;
+        d.tiles_n = (q.N + GN - 1) / GN;
+        d.tile_begin = tiles;
+        tiles += ((q.M + GM - 1) / GM) * d.tiles_n;
+    }
+    const size_t smem = 1024 + (size_t)kGStages * kGStageBytes + 256;
+    DCLIP_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_gemm_tc<<<tiles, kGThreads, smem, st>>>(g);
+    DCLIP_LAUNCH_OK("k_gemm_tc");
+    return DCLIP_OK;
+}
+
+}  // namespace dclip

@@ -199,19 +199,23 @@ inline PFN_encodeTiled get_encode_tiled() {
     return fn;
 }
 
-// dtype16: 0 = fp16, 1 = bf16.  Returns false on failure.
-inline bool make_tmap_2d_sw128(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, int dtype16,
-                               uint32_t box_cols = 64) {
+// dtype16: 0 = fp16, 1 = bf16.  ld = row stride in elements.  Returns false on failure.
+inline bool make_tmap_2d_sw128_ld(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                                  int dtype16, uint32_t box_cols = 64) {
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return false;
     cuuint64_t gdim[2] = {cols, rows};
-    cuuint64_t gstride[1] = {cols * 2};
+    cuuint64_t gstride[1] = {ld * 2};
     cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(out, dtype16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim,
                      gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
+}
+inline bool make_tmap_2d_sw128(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, int dtype16,
+                               uint32_t box_cols = 64) {
+    return make_tmap_2d_sw128_ld(out, base, rows, cols, cols, box_rows, dtype16, box_cols);
 }
 
 }  // namespace tc

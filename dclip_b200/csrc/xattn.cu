@@ -8,7 +8,11 @@
 //   and the autograd backward the teacher step runs through them
 //   (training/train_contrastive_teacher.py:347-362).
 //
-// This file is the fp32 CUDA-core implementation (exact tier).  All intermediates are fp32 in a
+// Two tiers.  fp32 inputs: everything below runs in fp32 on CUDA cores (exact tier).  16-bit inputs
+// (bf16 / fp16 parameters and activations, BASELINE configs[2]): the ten projection GEMMs of the forward
+// and backward (97 % of the FLOPs) run on tcgen05 through gemm_tc.cu with the 16-bit tensors as operands
+// and fp32 accumulation; attention cores, LayerNorm, aggregation and all statistics stay fp32.
+// This file is the fp32 CUDA-core implementation plus the orchestration of both tiers.  All intermediates are fp32 in a
 // caller-provided `saved` buffer that the backward re-reads (Q, K|V, attention output, pre-LN sums,
 // LN statistics); attention probabilities are never stored — the backward recomputes them per
 // (batch, head) in shared memory.  16-bit inputs/parameters are widened once on entry.
@@ -16,6 +20,9 @@
 // Row layout: text rows = b*T + t, image rows = b*R + r (batch-first, as the callers hold them; the
 // reference's transpose to [L, B, d] only permutes rows of the same per-(b, head) problems).
 #include "common.cuh"
+#include "gemm_tc.h"
+
+#include <cstdlib>
 
 namespace dclip {
 
@@ -474,7 +481,7 @@ __global__ void k_combine_bwd(const T* __restrict__ dout, int64_t n, const int* 
 // saved-buffer layout (floats)
 // ---------------------------------------------------------------------------------------------
 struct XLayout {
-    size_t Xt, Xi, Qt, KVi, Qi, KVt, Ot, Oi, Zt, Zi, St, Si, W, total;
+    size_t Xt, Xi, Qt, KVi, Qi, KVt, Ot, Oi, Zt, Zi, St, Si, O16t, O16i, W, total;
     // W: fp32 copies of the 12 parameter tensors (only when dtype != f32)
 };
 static const int kParamCount = 12;
@@ -500,6 +507,7 @@ static XLayout xlayout(int64_t B, int64_t T, int64_t R, int64_t d, bool widen) {
     L.Qt = take(nt * d); L.KVi = take(ni * 2 * d); L.Qi = take(ni * d); L.KVt = take(nt * 2 * d);
     L.Ot = take(nt * d); L.Oi = take(ni * d); L.Zt = take(nt * d); L.Zi = take(ni * d);
     L.St = take(nt * 2); L.Si = take(ni * 2);
+    L.O16t = take(widen ? (nt * d + 1) / 2 : 0); L.O16i = take(widen ? (ni * d + 1) / 2 : 0);   // 16-bit copies of O (tensor tier)
     L.W = o;
     if (widen) for (int i = 0; i < kParamCount; ++i) take(param_numel(i, d));
     L.total = o;
@@ -521,6 +529,22 @@ static int narrow(const float* src, void* dst, size_t n, cudaStream_t st) {
     return DCLIP_OK;
 }
 
+// tensor tier available?  (16-bit dtype on an sm_100 device; DCLIP_XATTN_TENSOR=0 forces the fp32 tier)
+static bool xattn_use_tc(int dtype, int64_t d) {
+    if (dtype == DCLIP_F32 || d % 8 != 0 || !device_is_sm100()) return false;
+    const char* e = getenv("DCLIP_XATTN_TENSOR");
+    return !(e && e[0] == '0');
+}
+
+static TcGemmProblem tcp(const void* A, int lda, bool a_mn, const void* B, int ldb, bool b_mn, float* C, int ldc, int M, int N, int K,
+                         const float* bias = nullptr, const float* residual = nullptr, int ldr = 0, bool accumulate = false) {
+    TcGemmProblem p{};
+    p.A = A; p.B = B; p.C = C; p.bias = bias; p.residual = residual; p.C16 = nullptr;
+    p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldb = ldb; p.ldc = ldc; p.ldr = ldr;
+    p.a_mn = a_mn; p.b_mn = b_mn; p.accumulate = accumulate;
+    return p;
+}
+
 static size_t attn_fwd_smem(int Lk, int hd) { return ((size_t)2 * Lk * (hd + 1) + 4 * hd + 4 * Lk) * 4; }
 static size_t attn_bwd_smem(int Lq, int Lk, int hd) { return ((size_t)(2 * Lq + 2 * Lk) * (hd + 1) + (size_t)2 * Lq * (Lk + 1)) * 4; }
 
@@ -537,7 +561,7 @@ size_t dclip_xattn_saved_bytes(int64_t B, int64_t T, int64_t R, int64_t d, int d
 size_t dclip_xattn_bwd_scratch_bytes(int64_t B, int64_t T, int64_t R, int64_t d, int dtype) {
     const size_t nt = (size_t)B * T, ni = (size_t)B * R;
     size_t f = (nt + ni) * d * 6 + (nt + ni) * 2 * d + 1024;       // dY, dZ, zhat, dO, dQ, dX + dKV
-    if (dtype != DCLIP_F32) { f += (nt + ni) * d; for (int i = 0; i < kParamCount; ++i) f += param_numel(i, d) + 64; }
+    if (dtype != DCLIP_F32) { f += (nt + ni) * d; for (int i = 0; i < kParamCount; ++i) f += param_numel(i, d) + 64; f += (nt + ni) * d * 2 + 1024; }
     return f * sizeof(float) + 4096;
 }
 
@@ -573,13 +597,26 @@ int dclip_xattn_fwd(const void* text, const void* image, int64_t B, int64_t T, i
         for (int i = 0; i < kParamCount; ++i) Wp[i] = static_cast<const float*>(params[i]);
     }
     // (1) in-projections: Q_t, K|V_i (text_to_image) and Q_i, K|V_t (image_to_text)
-    GemmGroup g{};
-    g.p[0] = gemm(Xt, D, false, Wp[0], D, true, S + L.Qt, D, nt, D, D, Wp[1]);
-    g.p[1] = gemm(Xi, D, false, Wp[0] + (size_t)d * d, D, true, S + L.KVi, 2 * D, ni, 2 * D, D, Wp[1] + d);
-    g.p[2] = gemm(Xi, D, false, Wp[4], D, true, S + L.Qi, D, ni, D, D, Wp[5]);
-    g.p[3] = gemm(Xt, D, false, Wp[4] + (size_t)d * d, D, true, S + L.KVt, 2 * D, nt, 2 * D, D, Wp[5] + d);
-    g.count = 4;
-    if (int e = launch_gemm_group(g, st)) return e;
+    const bool tc = xattn_use_tc(dtype, d);
+    const size_t esz = 2;   // 16-bit element size (tensor tier only)
+    const char* w_t2i = static_cast<const char*>(params[0]);
+    const char* w_i2t = static_cast<const char*>(params[4]);
+    if (tc) {
+        TcGemmProblem pr[4];
+        pr[0] = tcp(text, D, false, w_t2i, D, false, S + L.Qt, D, nt, D, D, Wp[1]);
+        pr[1] = tcp(image, D, false, w_t2i + (size_t)d * d * esz, D, false, S + L.KVi, 2 * D, ni, 2 * D, D, Wp[1] + d);
+        pr[2] = tcp(image, D, false, w_i2t, D, false, S + L.Qi, D, ni, D, D, Wp[5]);
+        pr[3] = tcp(text, D, false, w_i2t + (size_t)d * d * esz, D, false, S + L.KVt, 2 * D, nt, 2 * D, D, Wp[5] + d);
+        if (int e = launch_gemm_tc(pr, 4, dtype, st)) return e;
+    } else {
+        GemmGroup g{};
+        g.p[0] = gemm(Xt, D, false, Wp[0], D, true, S + L.Qt, D, nt, D, D, Wp[1]);
+        g.p[1] = gemm(Xi, D, false, Wp[0] + (size_t)d * d, D, true, S + L.KVi, 2 * D, ni, 2 * D, D, Wp[1] + d);
+        g.p[2] = gemm(Xi, D, false, Wp[4], D, true, S + L.Qi, D, ni, D, D, Wp[5]);
+        g.p[3] = gemm(Xt, D, false, Wp[4] + (size_t)d * d, D, true, S + L.KVt, 2 * D, nt, 2 * D, D, Wp[5] + d);
+        g.count = 4;
+        if (int e = launch_gemm_group(g, st)) return e;
+    }
     // (2) attention cores
     AttnArgs a{};
     a.B = (int)B; a.heads = heads; a.hd = hd; a.d = D; a.scale = 1.0f / sqrtf((float)hd);
@@ -590,11 +627,22 @@ int dclip_xattn_fwd(const void* text, const void* image, int64_t B, int64_t T, i
     k_attn_fwd<<<dim3((unsigned)(B * heads), 2), 128, smf, st>>>(a);
     DCLIP_LAUNCH_OK("k_attn_fwd");
     // (3) out-projection + bias + residual -> Z
-    GemmGroup g2{};
-    g2.p[0] = gemm(S + L.Ot, D, false, Wp[2], D, true, S + L.Zt, D, nt, D, D, Wp[3], Xt, D);
-    g2.p[1] = gemm(S + L.Oi, D, false, Wp[6], D, true, S + L.Zi, D, ni, D, D, Wp[7], Xi, D);
-    g2.count = 2;
-    if (int e = launch_gemm_group(g2, st)) return e;
+    if (tc) {
+        void* O16t = const_cast<float*>(S + L.O16t);
+        void* O16i = const_cast<float*>(S + L.O16i);
+        DCLIP_DISPATCH_DTYPE(dtype, { if (int e = narrow<T>(S + L.Ot, O16t, (size_t)nt * d, st)) return e; });
+        DCLIP_DISPATCH_DTYPE(dtype, { if (int e = narrow<T>(S + L.Oi, O16i, (size_t)ni * d, st)) return e; });
+        TcGemmProblem pr[2];
+        pr[0] = tcp(O16t, D, false, params[2], D, false, S + L.Zt, D, nt, D, D, Wp[3], Xt, D);
+        pr[1] = tcp(O16i, D, false, params[6], D, false, S + L.Zi, D, ni, D, D, Wp[7], Xi, D);
+        if (int e = launch_gemm_tc(pr, 2, dtype, st)) return e;
+    } else {
+        GemmGroup g2{};
+        g2.p[0] = gemm(S + L.Ot, D, false, Wp[2], D, true, S + L.Zt, D, nt, D, D, Wp[3], Xt, D);
+        g2.p[1] = gemm(S + L.Oi, D, false, Wp[6], D, true, S + L.Zi, D, ni, D, D, Wp[7], Xi, D);
+        g2.count = 2;
+        if (int e = launch_gemm_group(g2, st)) return e;
+    }
     // (4) LayerNorm
     if (!wide) {
         k_ln_fwd<<<(unsigned)ceil_div(nt, 8), 256, 0, st>>>(S + L.Zt, Wp[8], Wp[9], nt, D, static_cast<float*>(text_out), S + L.St);
@@ -636,6 +684,11 @@ int dclip_xattn_bwd(const void* text, const void* image, int64_t B, int64_t T, i
     float* dQt = take((size_t)nt * d); float* dQi = take((size_t)ni * d);
     float* dKVi = take((size_t)ni * 2 * d); float* dKVt = take((size_t)nt * 2 * d);
     float* dXt = take((size_t)nt * d); float* dXi = take((size_t)ni * d);
+    const bool tc = xattn_use_tc(dtype, d);
+    // 16-bit GEMM operands of the tensor tier (element counts halved: two per float slot)
+    void* dZ16t = tc ? take(((size_t)nt * d + 1) / 2) : nullptr; void* dZ16i = tc ? take(((size_t)ni * d + 1) / 2) : nullptr;
+    void* dQ16t = tc ? take(((size_t)nt * d + 1) / 2) : nullptr; void* dQ16i = tc ? take(((size_t)ni * d + 1) / 2) : nullptr;
+    void* dKV16i = tc ? take((size_t)ni * d) : nullptr;           void* dKV16t = tc ? take((size_t)nt * d) : nullptr;
     float* Xt_w = nullptr; float* Xi_w = nullptr;
     float* G[kParamCount];
     const float* Wp[kParamCount];
@@ -671,13 +724,24 @@ int dclip_xattn_bwd(const void* text, const void* image, int64_t B, int64_t T, i
     k_colsum<<<(unsigned)ceil_div(D, 32), 256, 0, st>>>(dZt, nullptr, nt, D, D, 0, G[3], nullptr);
     k_colsum<<<(unsigned)ceil_div(D, 32), 256, 0, st>>>(dZi, nullptr, ni, D, D, 0, G[7], nullptr);
     DCLIP_LAUNCH_OK("k_colsum");
-    GemmGroup g{};
-    g.p[0] = gemm(dZt, D, true, S + L.Ot, D, false, G[2], D, D, D, nt);
-    g.p[1] = gemm(dZi, D, true, S + L.Oi, D, false, G[6], D, D, D, ni);
-    g.p[2] = gemm(dZt, D, false, Wp[2], D, false, dOt, D, nt, D, D);
-    g.p[3] = gemm(dZi, D, false, Wp[6], D, false, dOi, D, ni, D, D);
-    g.count = 4;
-    if (int e = launch_gemm_group(g, st)) return e;
+    if (tc) {
+        DCLIP_DISPATCH_DTYPE(dtype, { if (int e = narrow<T>(dZt, dZ16t, (size_t)nt * d, st)) return e; });
+        DCLIP_DISPATCH_DTYPE(dtype, { if (int e = narrow<T>(dZi, dZ16i, (size_t)ni * d, st)) return e; });
+        TcGemmProblem pr[4];
+        pr[0] = tcp(dZ16t, D, true, S + L.O16t, D, true, G[2], D, D, D, nt);             // dWo = dZ^T O
+        pr[1] = tcp(dZ16i, D, true, S + L.O16i, D, true, G[6], D, D, D, ni);
+        pr[2] = tcp(dZ16t, D, false, params[2], D, true, dOt, D, nt, D, D);              // dO = dZ Wo
+        pr[3] = tcp(dZ16i, D, false, params[6], D, true, dOi, D, ni, D, D);
+        if (int e = launch_gemm_tc(pr, 4, dtype, st)) return e;
+    } else {
+        GemmGroup g{};
+        g.p[0] = gemm(dZt, D, true, S + L.Ot, D, false, G[2], D, D, D, nt);
+        g.p[1] = gemm(dZi, D, true, S + L.Oi, D, false, G[6], D, D, D, ni);
+        g.p[2] = gemm(dZt, D, false, Wp[2], D, false, dOt, D, nt, D, D);
+        g.p[3] = gemm(dZi, D, false, Wp[6], D, false, dOi, D, ni, D, D);
+        g.count = 4;
+        if (int e = launch_gemm_group(g, st)) return e;
+    }
     // (2') attention cores backward
     AttnArgs a{};
     a.B = (int)B; a.heads = heads; a.hd = hd; a.d = D; a.scale = 1.0f / sqrtf((float)hd);
@@ -692,25 +756,52 @@ int dclip_xattn_bwd(const void* text, const void* image, int64_t B, int64_t T, i
     k_colsum<<<(unsigned)ceil_div(D, 32), 256, 0, st>>>(dQi, nullptr, ni, D, D, 0, G[5], nullptr);
     k_colsum<<<(unsigned)ceil_div(2 * D, 32), 256, 0, st>>>(dKVt, nullptr, nt, 2 * D, 2 * D, 0, G[5] + d, nullptr);
     DCLIP_LAUNCH_OK("k_colsum");
-    GemmGroup g2{};
-    g2.p[0] = gemm(dQt, D, true, Xt, D, false, G[0], D, D, D, nt);
-    g2.p[1] = gemm(dKVi, 2 * D, true, Xi, D, false, G[0] + (size_t)d * d, D, 2 * D, D, ni);
-    g2.p[2] = gemm(dQi, D, true, Xi, D, false, G[4], D, D, D, ni);
-    g2.p[3] = gemm(dKVt, 2 * D, true, Xt, D, false, G[4] + (size_t)d * d, D, 2 * D, D, nt);
-    g2.count = 4;
-    if (int e = launch_gemm_group(g2, st)) return e;
+    const char* w_t2i = static_cast<const char*>(params[0]);
+    const char* w_i2t = static_cast<const char*>(params[4]);
+    if (tc) {
+        DCLIP_DISPATCH_DTYPE(dtype, { if (int e = narrow<T>(dQt, dQ16t, (size_t)nt * d, st)) return e; });
+        DCLIP_DISPATCH_DTYPE(dtype, { if (int e = narrow<T>(dQi, dQ16i, (size_t)ni * d, st)) return e; });
+        DCLIP_DISPATCH_DTYPE(dtype, { if (int e = narrow<T>(dKVi, dKV16i, (size_t)ni * 2 * d, st)) return e; });
+        DCLIP_DISPATCH_DTYPE(dtype, { if (int e = narrow<T>(dKVt, dKV16t, (size_t)nt * 2 * d, st)) return e; });
+        TcGemmProblem pr[4];
+        pr[0] = tcp(dQ16t, D, true, text, D, true, G[0], D, D, D, nt);                              // dWq = dQ^T X
+        pr[1] = tcp(dKV16i, 2 * D, true, image, D, true, G[0] + (size_t)d * d, D, 2 * D, D, ni);     // dWkv = dKV^T X
+        pr[2] = tcp(dQ16i, D, true, image, D, true, G[4], D, D, D, ni);
+        pr[3] = tcp(dKV16t, 2 * D, true, text, D, true, G[4] + (size_t)d * d, D, 2 * D, D, nt);
+        if (int e = launch_gemm_tc(pr, 4, dtype, st)) return e;
+        if (d_text) {
+            TcGemmProblem px[2];
+            px[0] = tcp(dQ16t, D, false, w_t2i, D, true, dXt, D, nt, D, D, nullptr, dZt, D);       // residual path + dQ Wq
+            px[1] = tcp(dQ16i, D, false, w_i2t, D, true, dXi, D, ni, D, D, nullptr, dZi, D);
+            if (int e = launch_gemm_tc(px, 2, dtype, st)) return e;
+            TcGemmProblem py[2];
+            py[0] = tcp(dKV16t, 2 * D, false, w_i2t + (size_t)d * d * 2, D, true, dXt, D, nt, D, 2 * D, nullptr, nullptr, 0, true);
+            py[1] = tcp(dKV16i, 2 * D, false, w_t2i + (size_t)d * d * 2, D, true, dXi, D, ni, D, 2 * D, nullptr, nullptr, 0, true);
+            if (int e = launch_gemm_tc(py, 2, dtype, st)) return e;
+        }
+    } else {
+        GemmGroup g2{};
+        g2.p[0] = gemm(dQt, D, true, Xt, D, false, G[0], D, D, D, nt);
+        g2.p[1] = gemm(dKVi, 2 * D, true, Xi, D, false, G[0] + (size_t)d * d, D, 2 * D, D, ni);
+        g2.p[2] = gemm(dQi, D, true, Xi, D, false, G[4], D, D, D, ni);
+        g2.p[3] = gemm(dKVt, 2 * D, true, Xt, D, false, G[4] + (size_t)d * d, D, 2 * D, D, nt);
+        g2.count = 4;
+        if (int e = launch_gemm_group(g2, st)) return e;
+        if (d_text) {
+            // input gradients: residual path + query projection + key/value projection of the other direction
+            GemmGroup g3{};
+            g3.p[0] = gemm(dQt, D, false, Wp[0], D, false, dXt, D, nt, D, D, nullptr, dZt, D);
+            g3.p[1] = gemm(dQi, D, false, Wp[4], D, false, dXi, D, ni, D, D, nullptr, dZi, D);
+            g3.count = 2;
+            if (int e = launch_gemm_group(g3, st)) return e;
+            GemmGroup g4{};
+            g4.p[0] = gemm(dKVt, 2 * D, false, Wp[4] + (size_t)d * d, D, false, dXt, D, nt, D, 2 * D, nullptr, nullptr, 0, true);
+            g4.p[1] = gemm(dKVi, 2 * D, false, Wp[0] + (size_t)d * d, D, false, dXi, D, ni, D, 2 * D, nullptr, nullptr, 0, true);
+            g4.count = 2;
+            if (int e = launch_gemm_group(g4, st)) return e;
+        }
+    }
     if (d_text) {
-        // input gradients: residual path + query projection + key/value projection of the other direction
-        GemmGroup g3{};
-        g3.p[0] = gemm(dQt, D, false, Wp[0], D, false, dXt, D, nt, D, D, nullptr, dZt, D);
-        g3.p[1] = gemm(dQi, D, false, Wp[4], D, false, dXi, D, ni, D, D, nullptr, dZi, D);
-        g3.count = 2;
-        if (int e = launch_gemm_group(g3, st)) return e;
-        GemmGroup g4{};
-        g4.p[0] = gemm(dKVt, 2 * D, false, Wp[4] + (size_t)d * d, D, false, dXt, D, nt, D, 2 * D, nullptr, nullptr, 0, true);
-        g4.p[1] = gemm(dKVi, 2 * D, false, Wp[0] + (size_t)d * d, D, false, dXi, D, ni, D, 2 * D, nullptr, nullptr, 0, true);
-        g4.count = 2;
-        if (int e = launch_gemm_group(g4, st)) return e;
         if (wide) {
             DCLIP_DISPATCH_DTYPE(dtype, { if (int e = narrow<T>(dXt, d_text, (size_t)nt * d, st)) return e; });
             DCLIP_DISPATCH_DTYPE(dtype, { if (int e = narrow<T>(dXi, d_image, (size_t)ni * d, st)) return e; });

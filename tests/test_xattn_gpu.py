@@ -105,6 +105,35 @@ def test_bf16_cfg3_shape(built_library):
     assert _rel(t_out, rt) < 4e-3 and _rel(i_out, ri) < 4e-3
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_16bit_tensor_tier_forward_backward(built_library, dtype):
+    """16-bit parameters/activations: the projection GEMMs run on tcgen05 (gemm_tc.cu).  Compared with the
+    fp64 oracle on the same rounded inputs; tolerance = a few 16-bit roundings of GEMM operands."""
+    from dclip_b200 import _lib
+    B, T, R, d, heads = 8, 77, 36, 768, 8
+    params = {k: v.to(dtype).float() for k, v in om.perturbed_cross_attention_params(d, heads, 11).items()}
+    m = _module(d, heads, params, dtype)
+    text, image = synthetic.xattn_inputs(B, T, R, d, 11, ragged=True)
+    text, image = text.to(dtype), image.to(dtype)
+    a = text.to(DEV).requires_grad_(True)
+    b = image.to(DEV).requires_grad_(True)
+    glob = m.global_embedding(a, b)
+    w = torch.randn(B, d, generator=torch.Generator().manual_seed(2))
+    (glob.float() * w.to(DEV)).sum().backward()
+    torch.cuda.synchronize()
+    assert built_library.dclip_debug_pipeline_error(_lib.stream_ptr(torch.device(DEV))) == 0
+    p64 = {k: v.double().requires_grad_(True) for k, v in params.items()}
+    a64 = text.double().requires_grad_(True)
+    b64 = image.double().requires_grad_(True)
+    ref = om.global_embedding(p64, a64, b64, heads)
+    (ref * w.double()).sum().backward()
+    tol = 2e-2 if dtype == torch.bfloat16 else 4e-3
+    assert _rel(glob, ref) < tol
+    assert _rel(a.grad, a64.grad) < tol and _rel(b.grad, b64.grad) < tol
+    for k, p in m.cross_modal_attention.named_parameters():
+        assert _rel(p.grad, p64[k].grad) < tol, (k, _rel(p.grad, p64[k].grad))
+
+
 def test_nan_guard_zeroes_whole_tensor(built_library):
     from dclip_b200.patch_text_aggregation import combine_global
     a = torch.randn(4, 16, device=DEV, requires_grad=True)
