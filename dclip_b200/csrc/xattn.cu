@@ -134,26 +134,56 @@ __global__ void k_from_f32(const float* __restrict__ in, T* __restrict__ out, in
     if (i < n) out[i] = from_f32<T>(in[i]);
 }
 
-// out[c] = sum_rows M[row, c]   (and optionally out2[c] = sum_rows M[row,c] * W[row,c]); fixed order
-__global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ Mx, const float* __restrict__ W, int rows, int cols, int ld,
-                                                int ldw, float* __restrict__ out, float* __restrict__ out2) {
-    __shared__ float r1[8][33], r2[8][33];
-    const int c = blockIdx.x * 32 + (threadIdx.x & 31), g = threadIdx.x >> 5;
+// grouped casts: up to 12 tensors per launch (blockIdx.y = tensor)
+struct CastGroup { const void* src[12]; void* dst[12]; long long n[12]; int count; };
+template <typename T>
+__global__ void k_widen_group(const __grid_constant__ CastGroup g) {
+    const T* in = static_cast<const T*>(g.src[blockIdx.y]);
+    float* out = static_cast<float*>(g.dst[blockIdx.y]);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < g.n[blockIdx.y]; i += (long long)gridDim.x * blockDim.x)
+        out[i] = to_f32<T>(in[i]);
+}
+template <typename T>
+__global__ void k_narrow_group(const __grid_constant__ CastGroup g) {
+    const float* in = static_cast<const float*>(g.src[blockIdx.y]);
+    T* out = static_cast<T*>(g.dst[blockIdx.y]);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < g.n[blockIdx.y]; i += (long long)gridDim.x * blockDim.x)
+        out[i] = from_f32<T>(in[i]);
+}
+
+// out[c] = sum_rows M[row, c]   (and optionally out2[c] = sum_rows M[row,c] * W[row,c]); fixed order.
+// Up to 8 problems per launch (blockIdx.y); a block owns 32 columns, 32 row lanes.
+struct ColsumProblem { const float* Mx; const float* W; int rows, cols, ld, ldw; float* out; float* out2; };
+struct ColsumGroup { ColsumProblem p[8]; int count; };
+__global__ void __launch_bounds__(1024) k_colsum(const __grid_constant__ ColsumGroup g) {
+    const ColsumProblem& P = g.p[blockIdx.y];
+    if ((int)blockIdx.x * 32 >= P.cols) return;
+    __shared__ float r1[32][33], r2[32][33];
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane;
     float s1 = 0.f, s2 = 0.f;
-    if (c < cols)
-        for (int r = g; r < rows; r += 8) {
-            const float v = Mx[(size_t)r * ld + c];
+    if (c < P.cols)
+        for (int r = grp; r < P.rows; r += 32) {
+            const float v = P.Mx[(size_t)r * P.ld + c];
             s1 += v;
-            if (W) s2 += v * W[(size_t)r * ldw + c];
+            if (P.W) s2 = fmaf(v, P.W[(size_t)r * P.ldw + c], s2);
         }
-    r1[g][threadIdx.x & 31] = s1; r2[g][threadIdx.x & 31] = s2;
+    r1[grp][lane] = s1; r2[grp][lane] = s2;
     __syncthreads();
-    if (g == 0 && c < cols) {
+    if (grp == 0 && c < P.cols) {
         float a = 0.f, b = 0.f;
-        for (int i = 0; i < 8; ++i) { a += r1[i][threadIdx.x]; b += r2[i][threadIdx.x]; }
-        if (out) out[c] = a;
-        if (out2) out2[c] = b;
+        for (int i = 0; i < 32; ++i) { a += r1[i][lane]; b += r2[i][lane]; }
+        if (P.out) P.out[c] = a;
+        if (P.out2) P.out2[c] = b;
     }
+}
+static int launch_colsum(const ColsumGroup& g, cudaStream_t st) {
+    int maxc = 0;
+    for (int i = 0; i < g.count; ++i) maxc = max(maxc, g.p[i].cols);
+    if (maxc == 0) return DCLIP_OK;
+    k_colsum<<<dim3((maxc + 31) / 32, g.count), 1024, 0, st>>>(g);
+    DCLIP_LAUNCH_OK("k_colsum");
+    return DCLIP_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -170,54 +200,103 @@ struct AttnDir {
 };
 struct AttnArgs { AttnDir dir[2]; int B, heads, hd, d; float scale; };
 
-__global__ void __launch_bounds__(128) k_attn_fwd(const __grid_constant__ AttnArgs a) {
-    extern __shared__ float sm[];
-    const AttnDir& D = a.dir[blockIdx.y];
-    const int b = blockIdx.x / a.heads, h = blockIdx.x % a.heads, hd = a.hd, ld = hd + 1;
-    float* Ks = sm;                         // [Lk][ld]
-    float* Vs = Ks + D.Lk * ld;             // [Lk][ld]
-    float* qs = Vs + D.Lk * ld;             // [4][hd]
-    float* ps = qs + 4 * hd;                // [4][Lk]
-    for (int idx = threadIdx.x; idx < D.Lk * hd; idx += 128) {
-        const int j = idx / hd, e = idx - j * hd;
-        const float* row = D.KV + (size_t)(b * D.Lk + j) * D.ldkv + h * hd + e;
-        Ks[j * ld + e] = row[0];
-        Vs[j * ld + e] = row[a.d];
-    }
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* q = qs + warp * hd;
-    float* p = ps + warp * D.Lk;
-    for (int qi = warp; qi < D.Lq; qi += 4) {
-        const float* qrow = D.Q + (size_t)(b * D.Lq + qi) * D.ldq + h * hd;
-        for (int e = lane; e < hd; e += 32) q[e] = qrow[e];
-        __syncwarp();
-        float mx = -INFINITY;
-        for (int j = lane; j < D.Lk; j += 32) {
-            float s = 0.f;
-            for (int e = 0; e < hd; ++e) s = fmaf(q[e], Ks[j * ld + e], s);
-            s *= a.scale;
-            p[j] = s;
-            mx = fmaxf(mx, s);
+// C[m][n] = sum_k a(m,k) b(k,n) for small operands living in shared memory, all kAttnThreads threads,
+// 4 x 4 outputs per thread, a warp covers a 16 x 32 block of C (4 x 8 micro-tiles: operand reads are
+// broadcasts or conflict-free).  a(m,k) = TA ? A[k*lda+m] : A[m*lda+k];  b(k,n) = TB ? B[n*ldb+k] : B[k*ldb+n].
+constexpr int kAttnThreads = 256;
+template <bool TA, bool TB, typename F>
+__device__ __forceinline__ void smem_gemm(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, int M, int N, int K,
+                                          F&& store) {
+    const int tiles_m = (M + 3) >> 2, tiles_n = (N + 3) >> 2;
+    const int blocks_n = (tiles_n + 7) >> 3, blocks_m = (tiles_m + 3) >> 2;
+    for (int t = threadIdx.x; t < blocks_m * blocks_n * 32; t += kAttnThreads) {
+        const int blk = t >> 5, inb = t & 31;
+        const int tm = (blk / blocks_n) * 4 + (inb >> 3), tn = (blk % blocks_n) * 8 + (inb & 7);
+        if (tm >= tiles_m || tn >= tiles_n) continue;
+        const int m0 = tm * 4, n0 = tn * 4;
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+        for (int k = 0; k < K; ++k) {
+            float av[4], bv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int m = min(m0 + i, M - 1), n = min(n0 + i, N - 1);     // clamped reads, masked stores
+                av[i] = TA ? A[k * lda + m] : A[m * lda + k];
+                bv[i] = TB ? B[n * ldb + k] : B[k * ldb + n];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
         }
-        mx = warp_max(mx);
-        float sum = 0.f;
-        for (int j = lane; j < D.Lk; j += 32) { const float ev = expf(p[j] - mx); p[j] = ev; sum += ev; }
-        sum = warp_sum(sum);
-        const float inv = 1.0f / sum;
-        __syncwarp();
-        float* orow = D.O + (size_t)(b * D.Lq + qi) * a.d + h * hd;
-        for (int e = lane; e < hd; e += 32) {
-            float o = 0.f;
-            for (int j = 0; j < D.Lk; ++j) o = fmaf(p[j], Vs[j * ld + e], o);
-            orow[e] = o * inv;
-        }
-        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (m0 + i < M && n0 + j < N) store(m0 + i, n0 + j, acc[i][j]);
     }
 }
 
-// backward: recompute P, then dV = P^T dO, dS = P o (dP - rowsum(dP o P)), dQ = scale dS K, dK = scale dS^T Q
-__global__ void __launch_bounds__(128) k_attn_bwd(const __grid_constant__ AttnArgs a) {
+// row softmax of P[Lq][lp] in place (one warp per row); optionally dS = P o (dP - rowsum(dP o P)) * scale
+__device__ __forceinline__ void smem_softmax_rows(float* P, int lp, int Lq, int Lk, float* dS, float scale) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int q = warp; q < Lq; q += kAttnThreads / 32) {
+        float mx = -INFINITY;
+        for (int j = lane; j < Lk; j += 32) mx = fmaxf(mx, P[q * lp + j]);
+        mx = warp_max(mx);
+        float sum = 0.f;
+        for (int j = lane; j < Lk; j += 32) { const float e = expf(P[q * lp + j] - mx); P[q * lp + j] = e; sum += e; }
+        sum = warp_sum(sum);
+        const float inv = 1.0f / sum;
+        float dot = 0.f;
+        for (int j = lane; j < Lk; j += 32) {
+            const float pv = P[q * lp + j] * inv;
+            P[q * lp + j] = pv;
+            if (dS) dot = fmaf(pv, dS[q * lp + j], dot);
+        }
+        if (dS) {
+            dot = warp_sum(dot);
+            for (int j = lane; j < Lk; j += 32) dS[q * lp + j] = P[q * lp + j] * (dS[q * lp + j] - dot) * scale;
+        }
+    }
+}
+
+__device__ __forceinline__ void load_head(float* dst, int ld, const float* src, int64_t row0, int rows, int64_t ldsrc, int col0, int hd) {
+    for (int idx = threadIdx.x; idx < rows * hd; idx += kAttnThreads) {
+        const int r = idx / hd, e = idx - r * hd;
+        dst[r * ld + e] = src[(row0 + r) * ldsrc + col0 + e];
+    }
+}
+
+__global__ void __launch_bounds__(kAttnThreads) k_attn_fwd(const __grid_constant__ AttnArgs a) {
+    extern __shared__ float sm[];
+    const AttnDir& D = a.dir[blockIdx.y];
+    const int b = blockIdx.x / a.heads, h = blockIdx.x % a.heads, hd = a.hd, ld = hd + 1;
+    const int Lq = D.Lq, Lk = D.Lk, lp = Lk + 1;
+    float* Qs = sm;                   // [Lq][ld]
+    float* Ks = Qs + Lq * ld;         // [Lk][ld]
+    float* Vs = Ks + Lk * ld;         // [Lk][ld]
+    float* Ps = Vs + Lk * ld;         // [Lq][lp]
+    load_head(Qs, ld, D.Q, (int64_t)b * Lq, Lq, D.ldq, h * hd, hd);
+    load_head(Ks, ld, D.KV, (int64_t)b * Lk, Lk, D.ldkv, h * hd, hd);
+    load_head(Vs, ld, D.KV, (int64_t)b * Lk, Lk, D.ldkv, a.d + h * hd, hd);
+    __syncthreads();
+    const float scale = a.scale;
+    smem_gemm<false, true>(Qs, ld, Ks, ld, Lq, Lk, hd, [&](int q, int j, float v) { Ps[q * lp + j] = v * scale; });
+    __syncthreads();
+    smem_softmax_rows(Ps, lp, Lq, Lk, nullptr, 0.f);
+    __syncthreads();
+    float* O = D.O + (size_t)b * Lq * a.d + h * hd;
+    const int dd = a.d;
+    smem_gemm<false, false>(Ps, lp, Vs, ld, Lq, hd, Lk, [&](int q, int e, float v) { O[(size_t)q * dd + e] = v; });
+}
+
+// backward: recompute P, then dV = P^T dO, dS = P o (dP - rowsum(dP o P)) scale, dQ = dS K, dK = dS^T Q
+__global__ void __launch_bounds__(kAttnThreads) k_attn_bwd(const __grid_constant__ AttnArgs a) {
     extern __shared__ float sm[];
     const AttnDir& D = a.dir[blockIdx.y];
     const int b = blockIdx.x / a.heads, h = blockIdx.x % a.heads, hd = a.hd, ld = hd + 1;
@@ -228,60 +307,23 @@ __global__ void __launch_bounds__(128) k_attn_bwd(const __grid_constant__ AttnAr
     float* Vs = Ks + Lk * ld;           // [Lk][ld]
     float* Ps = Vs + Lk * ld;           // [Lq][lp]
     float* dSs = Ps + Lq * lp;          // [Lq][lp]
-    for (int idx = threadIdx.x; idx < Lq * hd; idx += 128) {
-        const int qi = idx / hd, e = idx - qi * hd;
-        Qs[qi * ld + e] = D.Q[(size_t)(b * Lq + qi) * D.ldq + h * hd + e];
-        dOs[qi * ld + e] = D.dO[(size_t)(b * Lq + qi) * a.d + h * hd + e];
-    }
-    for (int idx = threadIdx.x; idx < Lk * hd; idx += 128) {
-        const int j = idx / hd, e = idx - j * hd;
-        const float* row = D.KV + (size_t)(b * Lk + j) * D.ldkv + h * hd + e;
-        Ks[j * ld + e] = row[0];
-        Vs[j * ld + e] = row[a.d];
-    }
+    load_head(Qs, ld, D.Q, (int64_t)b * Lq, Lq, D.ldq, h * hd, hd);
+    load_head(dOs, ld, D.dO, (int64_t)b * Lq, Lq, a.d, h * hd, hd);
+    load_head(Ks, ld, D.KV, (int64_t)b * Lk, Lk, D.ldkv, h * hd, hd);
+    load_head(Vs, ld, D.KV, (int64_t)b * Lk, Lk, D.ldkv, a.d + h * hd, hd);
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int qi = warp; qi < Lq; qi += 4) {
-        float mx = -INFINITY;
-        for (int j = lane; j < Lk; j += 32) {
-            float s = 0.f, dp = 0.f;
-            for (int e = 0; e < hd; ++e) {
-                s = fmaf(Qs[qi * ld + e], Ks[j * ld + e], s);
-                dp = fmaf(dOs[qi * ld + e], Vs[j * ld + e], dp);
-            }
-            s *= a.scale;
-            Ps[qi * lp + j] = s;
-            dSs[qi * lp + j] = dp;
-            mx = fmaxf(mx, s);
-        }
-        mx = warp_max(mx);
-        float sum = 0.f;
-        for (int j = lane; j < Lk; j += 32) { const float ev = expf(Ps[qi * lp + j] - mx); Ps[qi * lp + j] = ev; sum += ev; }
-        sum = warp_sum(sum);
-        const float inv = 1.0f / sum;
-        float dot = 0.f;
-        for (int j = lane; j < Lk; j += 32) { const float pv = Ps[qi * lp + j] * inv; Ps[qi * lp + j] = pv; dot = fmaf(pv, dSs[qi * lp + j], dot); }
-        dot = warp_sum(dot);
-        for (int j = lane; j < Lk; j += 32) dSs[qi * lp + j] = Ps[qi * lp + j] * (dSs[qi * lp + j] - dot) * a.scale;
-    }
+    const float scale = a.scale;
+    smem_gemm<false, true>(Qs, ld, Ks, ld, Lq, Lk, hd, [&](int q, int j, float v) { Ps[q * lp + j] = v * scale; });
+    smem_gemm<false, true>(dOs, ld, Vs, ld, Lq, Lk, hd, [&](int q, int j, float v) { dSs[q * lp + j] = v; });      // dP
     __syncthreads();
-    for (int idx = threadIdx.x; idx < Lq * hd; idx += 128) {          // dQ
-        const int qi = idx / hd, e = idx - qi * hd;
-        float v = 0.f;
-        for (int j = 0; j < Lk; ++j) v = fmaf(dSs[qi * lp + j], Ks[j * ld + e], v);
-        D.dQ[(size_t)(b * Lq + qi) * a.d + h * hd + e] = v;
-    }
-    for (int idx = threadIdx.x; idx < Lk * hd; idx += 128) {          // dK, dV
-        const int j = idx / hd, e = idx - j * hd;
-        float dk = 0.f, dv = 0.f;
-        for (int qi = 0; qi < Lq; ++qi) {
-            dk = fmaf(dSs[qi * lp + j], Qs[qi * ld + e], dk);
-            dv = fmaf(Ps[qi * lp + j], dOs[qi * ld + e], dv);
-        }
-        float* row = D.dKV + (size_t)(b * Lk + j) * (2 * a.d) + h * hd + e;
-        row[0] = dk;
-        row[a.d] = dv;
-    }
+    smem_softmax_rows(Ps, lp, Lq, Lk, dSs, scale);
+    __syncthreads();
+    const int dd = a.d;
+    float* dQ = D.dQ + (size_t)b * Lq * dd + h * hd;
+    float* dKV = D.dKV + (size_t)b * Lk * 2 * dd + h * hd;
+    smem_gemm<false, false>(dSs, lp, Ks, ld, Lq, hd, Lk, [&](int q, int e, float v) { dQ[(size_t)q * dd + e] = v; });
+    smem_gemm<true, false>(dSs, lp, Qs, ld, Lk, hd, Lq, [&](int j, int e, float v) { dKV[(size_t)j * 2 * dd + e] = v; });         // dK
+    smem_gemm<true, false>(Ps, lp, dOs, ld, Lk, hd, Lq, [&](int j, int e, float v) { dKV[(size_t)j * 2 * dd + dd + e] = v; });   // dV
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -332,27 +374,28 @@ __global__ void __launch_bounds__(256) k_ln_bwd(const float* __restrict__ dy, co
 // aggregation (patch_text_aggregation.py:243-265): one CTA per batch element
 // ---------------------------------------------------------------------------------------------
 constexpr float kCosEps = 1e-8f;
-__device__ __forceinline__ float block_sum(float v, float* red) {   // 256 threads
+constexpr int kAggThreads = 1024;
+__device__ __forceinline__ float block_sum(float v, float* red) {   // kAggThreads threads
     v = warp_sum(v);
     __syncthreads();
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
     __syncthreads();
     float t = 0.f;
-    for (int i = 0; i < 8; ++i) t += red[i];
+    for (int i = 0; i < kAggThreads / 32; ++i) t += red[i];
     return t;
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) k_aggregate_fwd(const T* __restrict__ x, int L, int d, float temperature, T* __restrict__ out,
+__global__ void __launch_bounds__(kAggThreads) k_aggregate_fwd(const T* __restrict__ x, int L, int d, float temperature, T* __restrict__ out,
                                                        float* __restrict__ w_saved) {
     extern __shared__ float sm[];
     float* mean = sm;            // [d]
     float* cs = mean + d;        // [L]
-    float* red = cs + L;         // [8]
+    float* red = cs + L;         // [32]
     const int b = blockIdx.x;
     const T* xb = x + (size_t)b * L * d;
     float part = 0.f;
-    for (int c = threadIdx.x; c < d; c += 256) {
+    for (int c = threadIdx.x; c < d; c += kAggThreads) {
         float s = 0.f;
         for (int l = 0; l < L; ++l) s += to_f32<T>(xb[(size_t)l * d + c]);
         s /= L;
@@ -361,7 +404,7 @@ __global__ void __launch_bounds__(256) k_aggregate_fwd(const T* __restrict__ x, 
     }
     const float nm = fmaxf(sqrtf(block_sum(part, red)), kCosEps);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int l = warp; l < L; l += 8) {
+    for (int l = warp; l < L; l += kAggThreads / 32) {
         float dot = 0.f, nx = 0.f;
         for (int c = lane; c < d; c += 32) { const float v = to_f32<T>(xb[(size_t)l * d + c]); dot = fmaf(v, mean[c], dot); nx = fmaf(v, v, nx); }
         dot = warp_sum(dot); nx = warp_sum(nx);
@@ -373,13 +416,13 @@ __global__ void __launch_bounds__(256) k_aggregate_fwd(const T* __restrict__ x, 
     float den = 0.f;
     for (int l = 0; l < L; ++l) den += expf(cs[l] - mx);
     __syncthreads();
-    for (int l = threadIdx.x; l < L; l += 256) {
+    for (int l = threadIdx.x; l < L; l += kAggThreads) {
         const float w = expf(cs[l] - mx) / den;
         cs[l] = w;
         if (w_saved) w_saved[(size_t)b * L + l] = w;
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < d; c += 256) {
+    for (int c = threadIdx.x; c < d; c += kAggThreads) {
         float s = 0.f;
         for (int l = 0; l < L; ++l) s = fmaf(cs[l], to_f32<T>(xb[(size_t)l * d + c]), s);
         out[(size_t)b * d + c] = from_f32<T>(s);
@@ -387,7 +430,7 @@ __global__ void __launch_bounds__(256) k_aggregate_fwd(const T* __restrict__ x, 
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) k_aggregate_bwd(const T* __restrict__ x, const float* __restrict__ w_saved, const T* __restrict__ dout,
+__global__ void __launch_bounds__(kAggThreads) k_aggregate_bwd(const T* __restrict__ x, const float* __restrict__ w_saved, const T* __restrict__ dout,
                                                        int L, int d, float temperature, T* __restrict__ dx) {
     extern __shared__ float sm[];
     float* mean = sm;            // [d]
@@ -401,7 +444,7 @@ __global__ void __launch_bounds__(256) k_aggregate_bwd(const T* __restrict__ x, 
     const T* dg = dout + (size_t)b * d;
     const float* w = w_saved + (size_t)b * L;
     float part = 0.f;
-    for (int c = threadIdx.x; c < d; c += 256) {
+    for (int c = threadIdx.x; c < d; c += kAggThreads) {
         float s = 0.f;
         for (int l = 0; l < L; ++l) s += to_f32<T>(xb[(size_t)l * d + c]);
         s /= L;
@@ -412,7 +455,7 @@ __global__ void __launch_bounds__(256) k_aggregate_bwd(const T* __restrict__ x, 
     const float nm = fmaxf(nm_raw, kCosEps);
     const bool m_clamped = nm_raw < kCosEps;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int l = warp; l < L; l += 8) {
+    for (int l = warp; l < L; l += kAggThreads / 32) {
         float dot = 0.f, nx = 0.f, dw = 0.f;
         for (int c = lane; c < d; c += 32) {
             const float v = to_f32<T>(xb[(size_t)l * d + c]);
@@ -430,10 +473,10 @@ __global__ void __launch_bounds__(256) k_aggregate_bwd(const T* __restrict__ x, 
     float sdot = 0.f;
     for (int l = 0; l < L; ++l) sdot = fmaf(w[l], dcs[l], sdot);
     __syncthreads();
-    for (int l = threadIdx.x; l < L; l += 256) dcs[l] = w[l] / temperature * (dcs[l] - sdot);
+    for (int l = threadIdx.x; l < L; l += kAggThreads) dcs[l] = w[l] / temperature * (dcs[l] - sdot);
     __syncthreads();
     // dmean[c] = sum_l dc_l (x_l[c] / (nx_l nm) - cos_l mean[c] / nm^2)
-    for (int c = threadIdx.x; c < d; c += 256) {
+    for (int c = threadIdx.x; c < d; c += kAggThreads) {
         float s = 0.f;
         for (int l = 0; l < L; ++l) {
             const float nx = fabsf(nxs[l]);
@@ -444,7 +487,7 @@ __global__ void __launch_bounds__(256) k_aggregate_bwd(const T* __restrict__ x, 
         dmean[c] = s / L;
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < L * d; idx += 256) {
+    for (int idx = threadIdx.x; idx < L * d; idx += kAggThreads) {
         const int l = idx / d, c = idx - l * d;
         const float xv = to_f32<T>(xb[idx]);
         const float nx = fabsf(nxs[l]);
@@ -529,6 +572,21 @@ static int narrow(const float* src, void* dst, size_t n, cudaStream_t st) {
     return DCLIP_OK;
 }
 
+static int launch_cast_group(const CastGroup& g, bool widen_dir, int dtype, cudaStream_t st) {
+    if (g.count == 0) return DCLIP_OK;
+    long long mx = 0;
+    for (int i = 0; i < g.count; ++i) mx = g.n[i] > mx ? g.n[i] : mx;
+    if (mx == 0) return DCLIP_OK;
+    const dim3 grid((unsigned)min((long long)1184, (mx + 255) / 256), g.count);
+    if (widen_dir) { DCLIP_DISPATCH_DTYPE(dtype, (k_widen_group<T><<<grid, 256, 0, st>>>(g))); }
+    else { DCLIP_DISPATCH_DTYPE(dtype, (k_narrow_group<T><<<grid, 256, 0, st>>>(g))); }
+    DCLIP_LAUNCH_OK("k_cast_group");
+    return DCLIP_OK;
+}
+static void cast_add(CastGroup& g, const void* src, void* dst, size_t n) {
+    g.src[g.count] = src; g.dst[g.count] = dst; g.n[g.count] = (long long)n; ++g.count;
+}
+
 // tensor tier available?  (16-bit dtype on an sm_100 device; DCLIP_XATTN_TENSOR=0 forces the fp32 tier)
 static bool xattn_use_tc(int dtype, int64_t d) {
     if (dtype == DCLIP_F32 || d % 8 != 0 || !device_is_sm100()) return false;
@@ -545,7 +603,7 @@ static TcGemmProblem tcp(const void* A, int lda, bool a_mn, const void* B, int l
     return p;
 }
 
-static size_t attn_fwd_smem(int Lk, int hd) { return ((size_t)2 * Lk * (hd + 1) + 4 * hd + 4 * Lk) * 4; }
+static size_t attn_fwd_smem(int Lq, int Lk, int hd) { return ((size_t)(Lq + 2 * Lk) * (hd + 1) + (size_t)Lq * (Lk + 1)) * 4; }
 static size_t attn_bwd_smem(int Lq, int Lk, int hd) { return ((size_t)(2 * Lq + 2 * Lk) * (hd + 1) + (size_t)2 * Lq * (Lk + 1)) * 4; }
 
 }  // namespace dclip
@@ -574,7 +632,7 @@ int dclip_xattn_fwd(const void* text, const void* image, int64_t B, int64_t T, i
     const XLayout L = xlayout(B, T, R, d, wide);
     if (saved_bytes < L.total * sizeof(float)) return fail(DCLIP_ERR_WORKSPACE, "xattn_fwd: saved buffer too small (%zu < %zu)", saved_bytes, L.total * sizeof(float));
     const int hd = (int)(d / heads);
-    const size_t sm_t2i = attn_fwd_smem((int)R, hd), sm_i2t = attn_fwd_smem((int)T, hd);
+    const size_t sm_t2i = attn_fwd_smem((int)T, (int)R, hd), sm_i2t = attn_fwd_smem((int)R, (int)T, hd);
     if (max(sm_t2i, sm_i2t) > 220 * 1024) return fail(DCLIP_ERR_UNSUPPORTED, "xattn_fwd: sequence x head_dim too large for shared memory");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     float* S = static_cast<float*>(saved);
@@ -582,22 +640,29 @@ int dclip_xattn_fwd(const void* text, const void* image, int64_t B, int64_t T, i
     const float* Xt = static_cast<const float*>(text);
     const float* Xi = static_cast<const float*>(image);
     const float* Wp[kParamCount];
+    const bool tc = xattn_use_tc(dtype, d);
     if (wide) {
+        // fp32 copies: parameters (the tensor tier consumes the four weight matrices in 16 bit directly and
+        // only needs the small bias / LayerNorm vectors widened) and the two inputs (residual path)
+        CastGroup cg{};
         size_t o = L.W;
         for (int i = 0; i < kParamCount; ++i) {
             const size_t n = param_numel(i, d);
-            DCLIP_DISPATCH_DTYPE(dtype, { if (int e = widen<T>(params[i], S + o, n, st)) return e; });
+            const bool is_matrix = (i % 4 == 0 || i % 4 == 2) && i < 8;
+            if (!(tc && is_matrix)) cast_add(cg, params[i], S + o, n);
             Wp[i] = S + o;
             o += (n + 63) / 64 * 64;
         }
-        DCLIP_DISPATCH_DTYPE(dtype, { if (int e = widen<T>(text, S + L.Xt, (size_t)nt * d, st)) return e; });
-        DCLIP_DISPATCH_DTYPE(dtype, { if (int e = widen<T>(image, S + L.Xi, (size_t)ni * d, st)) return e; });
+        if (int e = launch_cast_group(cg, true, dtype, st)) return e;
+        CastGroup cx{};
+        cast_add(cx, text, S + L.Xt, (size_t)nt * d);
+        cast_add(cx, image, S + L.Xi, (size_t)ni * d);
+        if (int e = launch_cast_group(cx, true, dtype, st)) return e;
         Xt = S + L.Xt; Xi = S + L.Xi;
     } else {
         for (int i = 0; i < kParamCount; ++i) Wp[i] = static_cast<const float*>(params[i]);
     }
     // (1) in-projections: Q_t, K|V_i (text_to_image) and Q_i, K|V_t (image_to_text)
-    const bool tc = xattn_use_tc(dtype, d);
     const size_t esz = 2;   // 16-bit element size (tensor tier only)
     const char* w_t2i = static_cast<const char*>(params[0]);
     const char* w_i2t = static_cast<const char*>(params[4]);
@@ -624,14 +689,16 @@ int dclip_xattn_fwd(const void* text, const void* image, int64_t B, int64_t T, i
     a.dir[1] = AttnDir{S + L.Qi, D, S + L.KVt, 2 * D, S + L.Oi, (int)R, (int)T, nullptr, nullptr, nullptr};
     const size_t smf = max(sm_t2i, sm_i2t);
     DCLIP_CUDA_OK(cudaFuncSetAttribute(k_attn_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf));
-    k_attn_fwd<<<dim3((unsigned)(B * heads), 2), 128, smf, st>>>(a);
+    k_attn_fwd<<<dim3((unsigned)(B * heads), 2), kAttnThreads, smf, st>>>(a);
     DCLIP_LAUNCH_OK("k_attn_fwd");
     // (3) out-projection + bias + residual -> Z
     if (tc) {
         void* O16t = const_cast<float*>(S + L.O16t);
         void* O16i = const_cast<float*>(S + L.O16i);
-        DCLIP_DISPATCH_DTYPE(dtype, { if (int e = narrow<T>(S + L.Ot, O16t, (size_t)nt * d, st)) return e; });
-        DCLIP_DISPATCH_DTYPE(dtype, { if (int e = narrow<T>(S + L.Oi, O16i, (size_t)ni * d, st)) return e; });
+        CastGroup co{};
+        cast_add(co, S + L.Ot, O16t, (size_t)nt * d);
+        cast_add(co, S + L.Oi, O16i, (size_t)ni * d);
+        if (int e = launch_cast_group(co, false, dtype, st)) return e;
         TcGemmProblem pr[2];
         pr[0] = tcp(O16t, D, false, params[2], D, false, S + L.Zt, D, nt, D, D, Wp[3], Xt, D);
         pr[1] = tcp(O16i, D, false, params[6], D, false, S + L.Zi, D, ni, D, D, Wp[7], Xi, D);
@@ -653,8 +720,10 @@ int dclip_xattn_fwd(const void* text, const void* image, int64_t B, int64_t T, i
         k_ln_fwd<<<(unsigned)ceil_div(nt, 8), 256, 0, st>>>(S + L.Zt, Wp[8], Wp[9], nt, D, S + L.Xt, S + L.St);
         k_ln_fwd<<<(unsigned)ceil_div(ni, 8), 256, 0, st>>>(S + L.Zi, Wp[10], Wp[11], ni, D, S + L.Xi, S + L.Si);
         DCLIP_LAUNCH_OK("k_ln_fwd");
-        DCLIP_DISPATCH_DTYPE(dtype, { if (int e = narrow<T>(S + L.Xt, text_out, (size_t)nt * d, st)) return e; });
-        DCLIP_DISPATCH_DTYPE(dtype, { if (int e = narrow<T>(S + L.Xi, image_out, (size_t)ni * d, st)) return e; });
+        CastGroup cy{};
+        cast_add(cy, S + L.Xt, text_out, (size_t)nt * d);
+        cast_add(cy, S + L.Xi, image_out, (size_t)ni * d);
+        if (int e = launch_cast_group(cy, false, dtype, st)) return e;
     }
     return DCLIP_OK;
 }
@@ -704,10 +773,14 @@ int dclip_xattn_bwd(const void* text, const void* image, int64_t B, int64_t T, i
             Wp[i] = S + wo;
             wo += (param_numel(i, d) + 63) / 64 * 64;
         }
-        DCLIP_DISPATCH_DTYPE(dtype, { if (int e = widen<T>(text, Xt_w, (size_t)nt * d, st)) return e; });
-        DCLIP_DISPATCH_DTYPE(dtype, { if (int e = widen<T>(image, Xi_w, (size_t)ni * d, st)) return e; });
-        DCLIP_DISPATCH_DTYPE(dtype, { if (int e = widen<T>(d_text_out, dYt, (size_t)nt * d, st)) return e; });
-        DCLIP_DISPATCH_DTYPE(dtype, { if (int e = widen<T>(d_image_out, dYi, (size_t)ni * d, st)) return e; });
+        CastGroup cw{};
+        if (!tc) {   // the tensor tier feeds the 16-bit inputs to the GEMMs directly
+            cast_add(cw, text, Xt_w, (size_t)nt * d);
+            cast_add(cw, image, Xi_w, (size_t)ni * d);
+        }
+        cast_add(cw, d_text_out, dYt, (size_t)nt * d);
+        cast_add(cw, d_image_out, dYi, (size_t)ni * d);
+        if (int e = launch_cast_group(cw, true, dtype, st)) return e;
         Xt = Xt_w; Xi = Xi_w; dyt = dYt; dyi = dYi;
     } else {
         for (int i = 0; i < kParamCount; ++i) { G[i] = static_cast<float*>(grads[i]); Wp[i] = static_cast<const float*>(params[i]); }
@@ -718,15 +791,19 @@ int dclip_xattn_bwd(const void* text, const void* image, int64_t B, int64_t T, i
     k_ln_bwd<<<(unsigned)ceil_div(nt, 8), 256, 0, st>>>(dyt, S + L.Zt, Wp[8], S + L.St, nt, D, dZt, zht);
     k_ln_bwd<<<(unsigned)ceil_div(ni, 8), 256, 0, st>>>(dyi, S + L.Zi, Wp[10], S + L.Si, ni, D, dZi, zhi);
     DCLIP_LAUNCH_OK("k_ln_bwd");
-    k_colsum<<<(unsigned)ceil_div(D, 32), 256, 0, st>>>(dyt, zht, nt, D, D, D, G[9], G[8]);
-    k_colsum<<<(unsigned)ceil_div(D, 32), 256, 0, st>>>(dyi, zhi, ni, D, D, D, G[11], G[10]);
+    ColsumGroup cg{};
+    cg.p[0] = ColsumProblem{dyt, zht, nt, D, D, D, G[9], G[8]};       // dbeta = colsum(dY), dgamma = colsum(dY * zhat)
+    cg.p[1] = ColsumProblem{dyi, zhi, ni, D, D, D, G[11], G[10]};
+    cg.p[2] = ColsumProblem{dZt, nullptr, nt, D, D, 0, G[3], nullptr};   // out-proj bias
+    cg.p[3] = ColsumProblem{dZi, nullptr, ni, D, D, 0, G[7], nullptr};
+    cg.count = 4;
+    if (int e = launch_colsum(cg, st)) return e;
     // (3') out-projection backward: dWo = dZ^T O, dbo = colsum(dZ), dO = dZ Wo
-    k_colsum<<<(unsigned)ceil_div(D, 32), 256, 0, st>>>(dZt, nullptr, nt, D, D, 0, G[3], nullptr);
-    k_colsum<<<(unsigned)ceil_div(D, 32), 256, 0, st>>>(dZi, nullptr, ni, D, D, 0, G[7], nullptr);
-    DCLIP_LAUNCH_OK("k_colsum");
     if (tc) {
-        DCLIP_DISPATCH_DTYPE(dtype, { if (int e = narrow<T>(dZt, dZ16t, (size_t)nt * d, st)) return e; });
-        DCLIP_DISPATCH_DTYPE(dtype, { if (int e = narrow<T>(dZi, dZ16i, (size_t)ni * d, st)) return e; });
+        CastGroup cz{};
+        cast_add(cz, dZt, dZ16t, (size_t)nt * d);
+        cast_add(cz, dZi, dZ16i, (size_t)ni * d);
+        if (int e = launch_cast_group(cz, false, dtype, st)) return e;
         TcGemmProblem pr[4];
         pr[0] = tcp(dZ16t, D, true, S + L.O16t, D, true, G[2], D, D, D, nt);             // dWo = dZ^T O
         pr[1] = tcp(dZ16i, D, true, S + L.O16i, D, true, G[6], D, D, D, ni);
@@ -748,21 +825,25 @@ int dclip_xattn_bwd(const void* text, const void* image, int64_t B, int64_t T, i
     a.dir[0] = AttnDir{S + L.Qt, D, S + L.KVi, 2 * D, nullptr, (int)T, (int)R, dOt, dQt, dKVi};
     a.dir[1] = AttnDir{S + L.Qi, D, S + L.KVt, 2 * D, nullptr, (int)R, (int)T, dOi, dQi, dKVt};
     DCLIP_CUDA_OK(cudaFuncSetAttribute(k_attn_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb));
-    k_attn_bwd<<<dim3((unsigned)(B * heads), 2), 128, smb, st>>>(a);
+    k_attn_bwd<<<dim3((unsigned)(B * heads), 2), kAttnThreads, smb, st>>>(a);
     DCLIP_LAUNCH_OK("k_attn_bwd");
     // (1') in-projection backward: weight grads (rows 0..d = q, d..3d = k|v) and bias grads
-    k_colsum<<<(unsigned)ceil_div(D, 32), 256, 0, st>>>(dQt, nullptr, nt, D, D, 0, G[1], nullptr);
-    k_colsum<<<(unsigned)ceil_div(2 * D, 32), 256, 0, st>>>(dKVi, nullptr, ni, 2 * D, 2 * D, 0, G[1] + d, nullptr);
-    k_colsum<<<(unsigned)ceil_div(D, 32), 256, 0, st>>>(dQi, nullptr, ni, D, D, 0, G[5], nullptr);
-    k_colsum<<<(unsigned)ceil_div(2 * D, 32), 256, 0, st>>>(dKVt, nullptr, nt, 2 * D, 2 * D, 0, G[5] + d, nullptr);
-    DCLIP_LAUNCH_OK("k_colsum");
+    ColsumGroup cg2{};
+    cg2.p[0] = ColsumProblem{dQt, nullptr, nt, D, D, 0, G[1], nullptr};
+    cg2.p[1] = ColsumProblem{dKVi, nullptr, ni, 2 * D, 2 * D, 0, G[1] + d, nullptr};
+    cg2.p[2] = ColsumProblem{dQi, nullptr, ni, D, D, 0, G[5], nullptr};
+    cg2.p[3] = ColsumProblem{dKVt, nullptr, nt, 2 * D, 2 * D, 0, G[5] + d, nullptr};
+    cg2.count = 4;
+    if (int e = launch_colsum(cg2, st)) return e;
     const char* w_t2i = static_cast<const char*>(params[0]);
     const char* w_i2t = static_cast<const char*>(params[4]);
     if (tc) {
-        DCLIP_DISPATCH_DTYPE(dtype, { if (int e = narrow<T>(dQt, dQ16t, (size_t)nt * d, st)) return e; });
-        DCLIP_DISPATCH_DTYPE(dtype, { if (int e = narrow<T>(dQi, dQ16i, (size_t)ni * d, st)) return e; });
-        DCLIP_DISPATCH_DTYPE(dtype, { if (int e = narrow<T>(dKVi, dKV16i, (size_t)ni * 2 * d, st)) return e; });
-        DCLIP_DISPATCH_DTYPE(dtype, { if (int e = narrow<T>(dKVt, dKV16t, (size_t)nt * 2 * d, st)) return e; });
+        CastGroup cq{};
+        cast_add(cq, dQt, dQ16t, (size_t)nt * d);
+        cast_add(cq, dQi, dQ16i, (size_t)ni * d);
+        cast_add(cq, dKVi, dKV16i, (size_t)ni * 2 * d);
+        cast_add(cq, dKVt, dKV16t, (size_t)nt * 2 * d);
+        if (int e = launch_cast_group(cq, false, dtype, st)) return e;
         TcGemmProblem pr[4];
         pr[0] = tcp(dQ16t, D, true, text, D, true, G[0], D, D, D, nt);                              // dWq = dQ^T X
         pr[1] = tcp(dKV16i, 2 * D, true, image, D, true, G[0] + (size_t)d * d, D, 2 * D, D, ni);     // dWkv = dKV^T X
@@ -803,28 +884,32 @@ int dclip_xattn_bwd(const void* text, const void* image, int64_t B, int64_t T, i
     }
     if (d_text) {
         if (wide) {
-            DCLIP_DISPATCH_DTYPE(dtype, { if (int e = narrow<T>(dXt, d_text, (size_t)nt * d, st)) return e; });
-            DCLIP_DISPATCH_DTYPE(dtype, { if (int e = narrow<T>(dXi, d_image, (size_t)ni * d, st)) return e; });
+            CastGroup cdx{};
+            cast_add(cdx, dXt, d_text, (size_t)nt * d);
+            cast_add(cdx, dXi, d_image, (size_t)ni * d);
+            if (int e = launch_cast_group(cdx, false, dtype, st)) return e;
         } else {
             DCLIP_CUDA_OK(cudaMemcpyAsync(d_text, dXt, (size_t)nt * d * 4, cudaMemcpyDeviceToDevice, st));
             DCLIP_CUDA_OK(cudaMemcpyAsync(d_image, dXi, (size_t)ni * d * 4, cudaMemcpyDeviceToDevice, st));
         }
     }
-    if (wide)
-        for (int i = 0; i < kParamCount; ++i)
-            DCLIP_DISPATCH_DTYPE(dtype, { if (int e = narrow<T>(G[i], grads[i], param_numel(i, d), st)) return e; });
+    if (wide) {
+        CastGroup cgr{};
+        for (int i = 0; i < kParamCount; ++i) cast_add(cgr, G[i], grads[i], param_numel(i, d));
+        if (int e = launch_cast_group(cgr, false, dtype, st)) return e;
+    }
     return DCLIP_OK;
 }
 
 int dclip_aggregate_fwd(const void* x, int64_t B, int64_t L, int64_t d, int dtype, float temperature, void* out, float* weights,
                         void* stream) {
     DCLIP_REQUIRE(x && out && B > 0 && L > 0 && d > 0 && temperature > 0.f, "aggregate_fwd: bad arguments");
-    const size_t sm = (size_t)(d + L + 8) * 4;
+    const size_t sm = (size_t)(d + L + 32) * 4;
     if (sm > 200 * 1024) return fail(DCLIP_ERR_UNSUPPORTED, "aggregate_fwd: d + L too large");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     DCLIP_DISPATCH_DTYPE(dtype, {
         DCLIP_CUDA_OK(cudaFuncSetAttribute(k_aggregate_fwd<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        k_aggregate_fwd<T><<<(unsigned)B, 256, sm, st>>>(static_cast<const T*>(x), (int)L, (int)d, temperature, static_cast<T*>(out), weights);
+        k_aggregate_fwd<T><<<(unsigned)B, kAggThreads, sm, st>>>(static_cast<const T*>(x), (int)L, (int)d, temperature, static_cast<T*>(out), weights);
     });
     DCLIP_LAUNCH_OK("k_aggregate_fwd");
     return DCLIP_OK;
@@ -833,12 +918,12 @@ int dclip_aggregate_fwd(const void* x, int64_t B, int64_t L, int64_t d, int dtyp
 int dclip_aggregate_bwd(const void* x, const float* weights, const void* d_out, int64_t B, int64_t L, int64_t d, int dtype,
                         float temperature, void* d_x, void* stream) {
     DCLIP_REQUIRE(x && weights && d_out && d_x && B > 0 && L > 0 && d > 0 && temperature > 0.f, "aggregate_bwd: bad arguments");
-    const size_t sm = (size_t)(2 * d + 3 * L + 8) * 4;
+    const size_t sm = (size_t)(2 * d + 3 * L + 32) * 4;
     if (sm > 200 * 1024) return fail(DCLIP_ERR_UNSUPPORTED, "aggregate_bwd: d + L too large");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     DCLIP_DISPATCH_DTYPE(dtype, {
         DCLIP_CUDA_OK(cudaFuncSetAttribute(k_aggregate_bwd<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        k_aggregate_bwd<T><<<(unsigned)B, 256, sm, st>>>(static_cast<const T*>(x), weights, static_cast<const T*>(d_out), (int)L, (int)d,
+        k_aggregate_bwd<T><<<(unsigned)B, kAggThreads, sm, st>>>(static_cast<const T*>(x), weights, static_cast<const T*>(d_out), (int)L, (int)d,
                                                          temperature, static_cast<T*>(d_x));
     });
     DCLIP_LAUNCH_OK("k_aggregate_bwd");

@@ -41,6 +41,9 @@ def run(B, T, R, d, dtype, cpu=False):
         line += f" | CPU oracle port ({os.cpu_count()} threads): {c:.1f} ms/step"
     print(line, flush=True)
 
-run(32, 77, 8, 512, torch.float32, cpu=True)
-run(32, 77, 36, 768, torch.bfloat16, cpu=True)
-run(32, 77, 36, 768, torch.float32)
+if len(sys.argv) > 1 and sys.argv[1] == "bf16":
+    run(32, 77, 36, 768, torch.bfloat16)
+else:
+    run(32, 77, 8, 512, torch.float32, cpu=True)
+    run(32, 77, 36, 768, torch.bfloat16, cpu=True)
+    run(32, 77, 36, 768, torch.float32)
