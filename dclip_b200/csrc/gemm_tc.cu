@@ -116,50 +116,42 @@ __global__ void __launch_bounds__(kGThreads, 1) k_gemm_tc(const __grid_constant_
         }
     } else {
         const int qd = warp & 3;
-        const int row = m0 + qd * 32 + lane;
-        const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
+            const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
         ok = mbar_wait(acc_full, 0, kSpinG);
         ok = __all_sync(0xffffffffu, ok);
         if (ok) {
             fence_after_thread_sync();
+            // TMEM hands each thread one output ROW; global memory wants a warp on one row.  Each warp
+            // transposes its 32 x 32 chunk through a private padded smem tile so that bias / residual reads
+            // and the C stores are 128-byte coalesced.
+            float* tile = reinterpret_cast<float*>(ring + kGStages * kGStageBytes + 256) + (size_t)qd * 32 * 33;
+            const int rbase = m0 + qd * 32;
 #pragma unroll 1
             for (int c0 = 0; c0 < GN; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(tmem + lane_addr + c0, r);
                 tmem_ld_wait();
-                if (row < P.M && n0 + c0 < P.N) {
-                    float* crow = P.C + (size_t)row * P.ldc + n0 + c0;
-                    const float* rrow = P.residual ? P.residual + (size_t)row * P.ldr + n0 + c0 : nullptr;
-                    float v[32];
+                if (n0 + c0 >= P.N) continue;              // warp-uniform
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        v[i] = __uint_as_float(r[i]);
-                        if (n0 + c0 + i < P.N) {
-                            if (P.bias) v[i] += P.bias[n0 + c0 + i];
-                            if (rrow) v[i] += rrow[i];
-                            if (P.accumulate) v[i] += crow[i];
-                        }
-                    }
-                    if (n0 + c0 + 32 <= P.N) {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(crow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                        if (P.c16_kind == 1) {
-                            __nv_bfloat16* o = static_cast<__nv_bfloat16*>(P.C16) + (size_t)row * P.ldc + n0 + c0;
-#pragma unroll
-                            for (int i = 0; i < 32; i += 2) *reinterpret_cast<__nv_bfloat162*>(o + i) = __floats2bfloat162_rn(v[i], v[i + 1]);
-                        } else if (P.c16_kind == 2) {
-                            __half* o = static_cast<__half*>(P.C16) + (size_t)row * P.ldc + n0 + c0;
-#pragma unroll
-                            for (int i = 0; i < 32; i += 2) *reinterpret_cast<__half2*>(o + i) = __floats2half2_rn(v[i], v[i + 1]);
-                        }
-                    } else {
-                        for (int i = 0; i < 32 && n0 + c0 + i < P.N; ++i) {
-                            crow[i] = v[i];
-                            if (P.c16_kind == 1) static_cast<__nv_bfloat16*>(P.C16)[(size_t)row * P.ldc + n0 + c0 + i] = __float2bfloat16_rn(v[i]);
-                            else if (P.c16_kind == 2) static_cast<__half*>(P.C16)[(size_t)row * P.ldc + n0 + c0 + i] = __float2half_rn(v[i]);
-                        }
+                for (int i = 0; i < 32; ++i) tile[lane * 33 + i] = __uint_as_float(r[i]);
+                __syncwarp();
+                const int col = n0 + c0 + lane;
+                const bool cvalid = col < P.N;
+                const float bv = (P.bias && cvalid) ? P.bias[col] : 0.f;
+                for (int rr = 0; rr < 32; ++rr) {
+                    const int grow = rbase + rr;
+                    if (grow >= P.M) break;                 // warp-uniform
+                    if (cvalid) {
+                        float v = tile[rr * 33 + lane] + bv;
+                        if (P.residual) v += P.residual[(size_t)grow * P.ldr + col];
+                        float* cp = P.C + (size_t)grow * P.ldc + col;
+                        if (P.accumulate) v += *cp;
+                        *cp = v;
+                        if (P.c16_kind == 1) static_cast<__nv_bfloat16*>(P.C16)[(size_t)grow * P.ldc + col] = __float2bfloat16_rn(v);
+                        else if (P.c16_kind == 2) static_cast<__half*>(P.C16)[(size_t)grow * P.ldc + col] = __float2half_rn(v);
                     }
                 }
+                __syncwarp();
             }
         }
     }
@@ -201,7 +193,7 @@ int launch_gemm_tc(const TcGemmProblem* probs, int count, int dtype16, cudaStrea
         d.tile_begin = tiles;
         tiles += ((q.M + GM - 1) / GM) * d.tiles_n;
     }
-    const size_t smem = 1024 + (size_t)kGStages * kGStageBytes + 256;
+    const size_t smem = 1024 + (size_t)kGStages * kGStageBytes + 256 + 4 * 32 * 33 * sizeof(float);
     DCLIP_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_gemm_tc<<<tiles, kGThreads, smem, st>>>(g);
     DCLIP_LAUNCH_OK("k_gemm_tc");
