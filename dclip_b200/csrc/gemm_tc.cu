@@ -135,20 +135,46 @@ __global__ void __launch_bounds__(kGThreads, 1) k_gemm_tc(const __grid_constant_
 #pragma unroll
                 for (int i = 0; i < 32; ++i) tile[lane * 33 + i] = __uint_as_float(r[i]);
                 __syncwarp();
-                const int col = n0 + c0 + lane;
-                const bool cvalid = col < P.N;
-                const float bv = (P.bias && cvalid) ? P.bias[col] : 0.f;
-                for (int rr = 0; rr < 32; ++rr) {
+                // lane -> (row within a group of 4, 4 consecutive columns): 8 unrolled iterations cover the 32 rows,
+                // every access is a float4 on a 128-byte contiguous row segment
+                const int rsub = lane >> 3, cg = (lane & 7) * 4;
+                const int col = n0 + c0 + cg;
+                const bool full4 = col + 4 <= P.N && (P.ldc & 3) == 0;
+                float bv[4] = {0.f, 0.f, 0.f, 0.f};
+                if (P.bias)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) bv[j] = col + j < P.N ? P.bias[col + j] : 0.f;
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int rr = it * 4 + rsub;
                     const int grow = rbase + rr;
-                    if (grow >= P.M) break;                 // warp-uniform
-                    if (cvalid) {
-                        float v = tile[rr * 33 + lane] + bv;
-                        if (P.residual) v += P.residual[(size_t)grow * P.ldr + col];
+                    if (grow < P.M && col < P.N) {
+                        float v[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) v[j] = tile[rr * 33 + cg + j] + bv[j];
                         float* cp = P.C + (size_t)grow * P.ldc + col;
-                        if (P.accumulate) v += *cp;
-                        *cp = v;
-                        if (P.c16_kind == 1) static_cast<__nv_bfloat16*>(P.C16)[(size_t)grow * P.ldc + col] = __float2bfloat16_rn(v);
-                        else if (P.c16_kind == 2) static_cast<__half*>(P.C16)[(size_t)grow * P.ldc + col] = __float2half_rn(v);
+                        if (full4) {
+                            if (P.residual) {
+                                const float4 rv = *reinterpret_cast<const float4*>(P.residual + (size_t)grow * P.ldr + col);
+                                v[0] += rv.x; v[1] += rv.y; v[2] += rv.z; v[3] += rv.w;
+                            }
+                            if (P.accumulate) {
+                                const float4 cv = *reinterpret_cast<const float4*>(cp);
+                                v[0] += cv.x; v[1] += cv.y; v[2] += cv.z; v[3] += cv.w;
+                            }
+                            *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
+                        } else {
+                            for (int j = 0; j < 4 && col + j < P.N; ++j) {
+                                if (P.residual) v[j] += P.residual[(size_t)grow * P.ldr + col + j];
+                                if (P.accumulate) v[j] += cp[j];
+                                cp[j] = v[j];
+                            }
+                        }
+                        if (P.c16_kind)
+                            for (int j = 0; j < 4 && col + j < P.N; ++j) {
+                                if (P.c16_kind == 1) static_cast<__nv_bfloat16*>(P.C16)[(size_t)grow * P.ldc + col + j] = __float2bfloat16_rn(v[j]);
+                                else static_cast<__half*>(P.C16)[(size_t)grow * P.ldc + col + j] = __float2half_rn(v[j]);
+                            }
                     }
                 }
                 __syncwarp();
