@@ -127,7 +127,7 @@ int dclip_infonce_grad(const void* x_hat, int64_t m, const void* y_hat, int64_t 
         a.out_scale = coef / temperature * (1.0f / 8192.0f);
         const void* xs[2] = {x_hat, x_hat};
         const void* ys[2] = {y_hat, y_hat};
-        if (int e = launch_infonce_tc(1, 1, xs, ys, a, ns, st)) return e;
+        if (int e = launch_infonce_bwd_tc(1, xs, ys, a, ns, st)) return e;
         if (ns > 1) return launch_tc_grad_combine(out, ns, m, d, dx_hat, st);
         return DCLIP_OK;
     }
@@ -273,7 +273,7 @@ int dclip_distill_loss_fwd_bwd(const void* s_img, const void* s_txt, const void*
             ga.s[1] = TcSide{lse_v, lse_u, dv_part};
             ga.m = B; ga.n = B; ga.d = d; ga.inv_tau = 1.0f / temperature; ga.row_offset = 0;
             ga.out_scale = w_con / (2.0f * (float)B) / temperature * (1.0f / 8192.0f);
-            if (int e = launch_infonce_tc(1, 2, xs2, ys2, ga, nsb, st)) return e;
+            if (int e = launch_infonce_bwd_tc(2, xs2, ys2, ga, nsb, st)) return e;
             if (nsb > 1) {
                 if (int e = launch_tc_grad_combine(du_part, nsb, B, d, du_hat, st)) return e;
                 if (int e = launch_tc_grad_combine(dv_part, nsb, B, d, dv_hat, st)) return e;

@@ -65,8 +65,8 @@ struct TcArgs {
 
 bool tc_loss_shape_ok(int64_t d, float temperature);
 int tc_nsplit(int64_t m, int64_t n, int nsides);
-int launch_infonce_tc(int mode, int nsides, const void* const x[2], const void* const y[2], const TcArgs& args, int nsplit,
-                      cudaStream_t st);
+int launch_infonce_bwd_tc(int nsides, const void* const x[2], const void* const y[2], const TcArgs& args, int nsplit,
+                          cudaStream_t st);
 int launch_tc_lse_combine(const float* part, int nsplit, int64_t m, float inv_tau, float* lse, cudaStream_t st);
 int launch_tc_grad_combine(const float* part, int nsplit, int64_t m, int64_t d, float* dx, cudaStream_t st);
 int launch_tc_diag(const void* x, const void* y, int64_t m, int64_t n, int64_t d, float inv_tau, int64_t row_offset, float* diag,

@@ -1,21 +1,19 @@
-// Distillation objective — tcgen05 / TMEM / TMA tensor path (sm_100a).
-//
-// One warp-specialised kernel template serves the forward (row log-sum-exp) and the backward
-// (dX_hat = coef/tau * G . Y_hat with G recomputed) of the symmetric InfoNCE term
-// (training/CLIP_image_distillation.py:545-560 and its autograd backward).  The B x B logits only
-// ever exist as 128 x 64 fp32 tiles in tensor memory.
+// Distillation objective — tcgen05 / TMEM / TMA tensor path (sm_100a): the InfoNCE BACKWARD
+// (dX_hat = coef/tau * G . Y_hat with G recomputed; autograd backward of
+// training/CLIP_image_distillation.py:545-560).  The forward row log-sum-exp runs on the 128 x 256
+// streaming kernel in stream_tc.cu.  The B x B logits only ever exist as 128 x 64 fp32 tiles in TMEM.
 //
 // Work decomposition.  A CTA owns NI = 64 rows of X_hat (kept resident in shared memory for the
 // whole kernel) and walks over 128-row tiles J of Y_hat:
 //   phase 1   S^T[128 j x 64 i] = Y_J . X_I^T          (M=128, N=64, K=d;  K-major operands)
-//   epilogue  thread = one j (TMEM lane), 64 i columns: p = exp2((s - 1) * log2e / tau)
-//             fwd: per-column running sums;  bwd: g = p (a_i + b_j) - 2 [i == j], scaled by 2^13,
-//             rounded to fp16 and stored as a 128B-swizzled [j][i] tile (an MN-major B operand)
+//   epilogue  thread = one j (TMEM lane), 64 i columns: p = exp2((s - 1) * log2e / tau),
+//             g = p (a_i + b_j) - 2 [i == j], scaled by 2^13, rounded to fp16 and stored as a
+//             128B-swizzled [j][i] tile (an MN-major B operand)
 //   phase 2   dX^T[d x 64 i] += Y_J^T[d x 128 j] . G^T   (M=128 per d-block, N=64, K=128 j;
 //             A = the very same TMA boxes as phase 1 read MN-major, B = the G tile)
-// Accumulators: d/128 blocks x 64 columns (<= 384) + two 64-column S buffers = 512 TMEM columns.
-// The fixed offset (s <= 1 for unit rows) replaces the running max of an online softmax, so row
-// sums are plain sums and the backward needs a single exp per logit:
+// Accumulators: d/128 blocks x 64 columns (<= 384) + two 64-column S buffers = 512 TMEM columns: the
+// gradient accumulator pins N to 64.  The fixed offset (s <= 1 for unit rows) replaces the running max
+// of an online softmax, so the backward needs a single exp per logit:
 //   softmax_row + softmax_col = p_ij (1/rowsum_i + 1/colsum_j).
 // Valid while 2*log2e/tau stays inside the fp32 exponent range: tau >= 0.025 (reference: 0.05).
 //
@@ -25,6 +23,9 @@
 // Pipelines: 3-slot ring of 32 KB (two 128x64 boxes) between TMA and MMA; S double-buffered
 // MMA<->epilogue; G double-buffered epilogue<->MMA.  Phase 1 of tile t+1 is issued before phase 2 of
 // tile t so the tensor pipe works while the epilogue of tile t runs.
+// Bound: shared-memory bandwidth — every 128x64x16 MMA re-reads 6 KB of operands and the TMA ring
+// writes another 4 KB per MMA, ~80 cycles at 128 B/clk against 32 cycles of math (ncu: tensor pipe
+// active 38 %, profiles/r1_ncu_full_loss_kernels.txt).
 #include "common.cuh"
 #include "loss_internal.h"
 #include "tcgen05.cuh"
@@ -51,26 +52,18 @@ struct Pipe {
     }
 };
 
-// kC = thread-block cluster size along the row-block axis.  The kC CTAs of a cluster own different
-// row blocks but walk the same Y tiles, so each loads 1/kC of every ring slot and multicasts it to
-// all of them: L2 -> SM traffic per CTA drops by kC (the kernel is otherwise bound by it).
-// kMode: 1 = loss backward (the product path).  0 = row sums with the same 128 x 64 tiles: superseded by
-// the 128 x 256 streaming kernel of stream_tc.cu for the forward and kept only as a cross-check.
-template <int kMode, int kC>
+// (A thread-block-cluster variant that TMA-multicast the Y boxes to 2 or 4 CTAs was built and measured:
+// no gain — the kernel is bound by shared-memory operand bandwidth, not by L2 -> SM traffic — and dropped.
+// The forward used to run on this 128 x 64 tiling too; it moved to the 128 x 256 kernel in stream_tc.cu.)
 __global__ void __launch_bounds__(kTcThreads, 1)
-k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CUtensorMap tmy0,
-             const __grid_constant__ CUtensorMap tmx1, const __grid_constant__ CUtensorMap tmy1,
-             const __grid_constant__ CUtensorMap tmh0, const __grid_constant__ CUtensorMap tmh1, const TcArgs a) {
+k_infonce_bwd_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CUtensorMap tmy0,
+             const __grid_constant__ CUtensorMap tmx1, const __grid_constant__ CUtensorMap tmy1, const TcArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int side = blockIdx.z;
     const CUtensorMap* tmx = side ? &tmx1 : &tmx0;
     const CUtensorMap* tmy = side ? &tmy1 : &tmy0;
-    const CUtensorMap* tmh = side ? &tmh1 : &tmh0;      // same matrix as tmy, 64-row boxes (kC == 4)
-    constexpr bool kBwd = kMode == 1;
     const TcSide S = a.s[side];
-    const uint32_t crank = kC > 1 ? cluster_ctarank() : 0;
-    constexpr uint16_t kMask = (uint16_t)((1u << kC) - 1);
     const int d = (int)a.d;
     const int nkb = d / 64;            // 64-column boxes along K
     const int NS = d / 128;            // ring slots per phase (= accumulator d-blocks)
@@ -78,7 +71,7 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
     uint8_t* xs = smem;                                   // resident X_I: nkb boxes of 8 KB
     uint8_t* ring = xs + (size_t)nkb * kXBoxBytes;        // kSlots x 32 KB
     uint8_t* gs = ring + kSlots * kSlotBytes;             // 2 x 16 KB (bwd)
-    uint8_t* tail = gs + (kBwd ? 2 * kGBytes : 0);
+    uint8_t* tail = gs + 2 * kGBytes;
     uint64_t* full = reinterpret_cast<uint64_t*>(tail);   // [kSlots]
     uint64_t* empty = full + kSlots;                      // [kSlots]
     uint64_t* s_full = empty + kSlots;                    // [2]
@@ -98,7 +91,7 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
     const int T = (int)(t_end - t_begin);
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kSlots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kC); }
+        for (int i = 0; i < kSlots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 128);
             mbar_init(&g_full[i], 128); mbar_init(&g_empty[i], 1);
@@ -109,7 +102,6 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
     if (warp == 3) tmem_alloc(tmem_ptr, 512);
     fence_before_thread_sync();
     __syncthreads();
-    if (kC > 1) cluster_sync_all();      // peers' barriers are initialised before anyone multicasts
     fence_after_thread_sync();
     const uint32_t tmem = *tmem_ptr;
     bool ok = true;
@@ -126,13 +118,12 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
                 }
                 // Job q (in MMA consumption order) uses slot q % kSlots.  Order: P1(0), then per tile t:
                 // P1(t+1) [if any], P2(t) [bwd].  Both phases of (tile, s) load the same two boxes.
-                const int njobs = kBwd ? 2 * NS * T : NS * T;
+                const int njobs = 2 * NS * T;
                 uint8_t* dst = ring + (size_t)warp * kSlotBytes;
                 uint32_t phase = 0;
                 for (int q = warp; q < njobs && ok; q += kSlots, phase ^= 1) {
                     int tile, sidx;
-                    if (!kBwd) { tile = q / NS; sidx = q - tile * NS; }
-                    else if (q < NS) { tile = 0; sidx = q; }
+                    if (q < NS) { tile = 0; sidx = q; }
                     else {
                         const int qq = q - NS, blk = min(qq / (2 * NS), T - 1), r = qq - blk * 2 * NS;
                         if (blk < T - 1 && r < NS) { tile = blk + 1; sidx = r; }
@@ -141,16 +132,8 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
                     const int32_t j0 = (int32_t)((t_begin + tile) * TJ);
                     ok = mbar_wait(&empty[warp], phase ^ 1, kSpin);
                     mbar_arrive_expect_tx(&full[warp], kSlotBytes);
-                    if (kC == 1) {
-                        tma_load_2d(dst, tmy, &full[warp], (2 * sidx) * 64, j0);
-                        tma_load_2d(dst + kBoxBytes, tmy, &full[warp], (2 * sidx + 1) * 64, j0);
-                    } else if (kC == 2) {        // CTA r loads box r of the slot for both CTAs
-                        tma_load_2d_mcast(dst + crank * kBoxBytes, tmy, &full[warp], (2 * sidx + (int)crank) * 64, j0, kMask);
-                    } else {                     // kC == 4: CTA r loads rows [64 (r&1), +64) of box r>>1
-                        const int box = (int)(crank >> 1), half = (int)(crank & 1);
-                        tma_load_2d_mcast(dst + box * kBoxBytes + half * (kBoxBytes / 2), tmh, &full[warp], (2 * sidx + box) * 64,
-                                          j0 + half * 64, kMask);
-                    }
+                    tma_load_2d(dst, tmy, &full[warp], (2 * sidx) * 64, j0);
+                    tma_load_2d(dst + kBoxBytes, tmy, &full[warp], (2 * sidx + 1) * 64, j0);
                 }
             }
         } else if (warp == 3) {
@@ -180,7 +163,7 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
                             for (int ks = 0; ks < 4; ++ks)      // +32 B per K step, next box at +16 KB (A) / +8 KB (B); >>4 encoded
                                 umma_f16(dcol, da0 + (uint64_t)(h * (kBoxBytes >> 4) + ks * 2), db0 + (uint64_t)(h * (kXBoxBytes >> 4) + ks * 2), idesc1,
                                          (s | h | ks) != 0);
-                        if (kC == 1) umma_commit(&empty[p.stage]); else umma_commit_mcast(&empty[p.stage], kMask);
+                        umma_commit(&empty[p.stage]);
                         p.advance();
                     }
                     umma_commit(&s_full[b]);
@@ -198,7 +181,7 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
 #pragma unroll
                         for (int ks = 0; ks < 8; ++ks)          // 16 j per step = two 8-row groups = +2048 B
                             umma_f16(tmem + s * NI, da0 + (uint64_t)(ks * 128), db0 + (uint64_t)(ks * 128), idesc2, (t | ks) != 0);
-                        if (kC == 1) umma_commit(&empty[p.stage]); else umma_commit_mcast(&empty[p.stage], kMask);
+                        umma_commit(&empty[p.stage]);
                         p.advance();
                     }
                     umma_commit(&g_empty[b]);
@@ -206,9 +189,9 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
                 if (ok) phase1(0);
                 for (int t = 0; t < T && ok; ++t) {
                     if (t + 1 < T) phase1(t + 1);
-                    if (kBwd && ok) phase2(t);
+                    if (ok) phase2(t);
                 }
-                if (kBwd) umma_commit(acc_full);
+                umma_commit(acc_full);
             }
         } else {
             // ===================== epilogue warps (128 threads) =====================
@@ -216,19 +199,12 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
             const int et = q * 32 + lane;                 // j row inside the tile == TMEM lane
             const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
             const float c = a.inv_tau * 1.4426950408889634f;    // log2(e) / tau
-            float sums[kMode == 0 ? NI : 1];
-            if (kMode == 0) {
-#pragma unroll
-                for (int i = 0; i < NI; ++i) sums[i] = 0.f;
+            if (et < NI) {
+                const int64_t gi = row0 + et;
+                // a'_i = 2^13 / rowsum_i = exp2((1/tau - lse_x) * log2e + 13)
+                a_s[et] = gi < a.m ? exp2f((a.inv_tau - S.lse_x[gi]) * 1.4426950408889634f + kGScaleLog2) : 0.f;
             }
-            if (kBwd) {
-                if (et < NI) {
-                    const int64_t gi = row0 + et;
-                    // a'_i = 2^13 / rowsum_i = exp2((1/tau - lse_x) * log2e + 13)
-                    a_s[et] = gi < a.m ? exp2f((a.inv_tau - S.lse_x[gi]) * 1.4426950408889634f + kGScaleLog2) : 0.f;
-                }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
             for (int t = 0; t < T && ok; ++t) {
                 const int b = t & 1;
                 const int64_t j0 = (t_begin + t) * TJ;
@@ -244,12 +220,7 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
                 fence_before_thread_sync();
                 mbar_arrive(&s_empty[b]);                 // S buffer may be overwritten by phase 1 of tile t+2
                 const bool jvalid = gj < a.n;
-                if (kMode == 0) {
-                    if (jvalid) {
-#pragma unroll
-                        for (int i = 0; i < NI; ++i) sums[i] += exp2f(fmaf(__uint_as_float(r[i]), c, -c));
-                    }
-                } else {
+                {
                     ok = ok && mbar_wait(&g_empty[b], ((t >> 1) & 1) ^ 1, kSpin);
                     const float bj = jvalid ? exp2f((a.inv_tau - S.lse_y[gj]) * 1.4426950408889634f + kGScaleLog2) : 0.f;
                     // diagonal element of this row, if it falls inside the CTA's 64 columns
@@ -282,20 +253,7 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
                     mbar_arrive(&g_full[b]);
                 }
             }
-            if (kMode == 0) {
-                // cross-thread reduction of the per-column sums: stage through the (now idle) ring
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                float* red = reinterpret_cast<float*>(ring);          // [128][NI + 1]
-#pragma unroll
-                for (int i = 0; i < NI; ++i) red[et * (NI + 1) + i] = sums[i];
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (et < NI) {
-                    float tot = 0.f;
-                    for (int r2 = 0; r2 < 128; ++r2) tot += red[r2 * (NI + 1) + et];
-                    const int64_t gi = row0 + et;
-                    if (gi < a.m) S.out[(int64_t)blockIdx.y * a.m + gi] = tot;
-                }
-            } else if (__all_sync(0xffffffffu, ok) && (ok = __all_sync(0xffffffffu, mbar_wait(acc_full, 0, kSpin)))) {
+            if (__all_sync(0xffffffffu, ok) && (ok = __all_sync(0xffffffffu, mbar_wait(acc_full, 0, kSpin)))) {
                 fence_after_thread_sync();
                 float* outp = S.out + (int64_t)blockIdx.y * a.m * a.d;
                 for (int s = 0; s < NS; ++s) {
@@ -320,19 +278,14 @@ k_infonce_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ C
     } else if (warp >= 4) {
         // empty column range (only possible with an over-split grid): contribute zeros
         const int et = (warp & 3) * 32 + lane;
-        if (kMode == 0) {
-            if (et < NI && row0 + et < a.m) S.out[(int64_t)blockIdx.y * a.m + row0 + et] = 0.f;
-        } else {
-            float* outp = S.out + (int64_t)blockIdx.y * a.m * a.d;
-            for (int i = 0; i < NI; ++i)
-                if (row0 + i < a.m)
-                    for (int c2 = et; c2 < d; c2 += 128) outp[(row0 + i) * a.d + c2] = 0.f;
-        }
+        float* outp = S.out + (int64_t)blockIdx.y * a.m * a.d;
+        for (int i = 0; i < NI; ++i)
+            if (row0 + i < a.m)
+                for (int c2 = et; c2 < d; c2 += 128) outp[(row0 + i) * a.d + c2] = 0.f;
     }
     if (!ok && lane == 0 && a.error_flag) atomicExch(a.error_flag, 1);
     fence_before_thread_sync();
     __syncthreads();
-    if (kC > 1) cluster_sync_all();      // nobody leaves while a peer may still multicast into / signal this CTA
     if (warp == 3) tmem_dealloc(tmem, 512);
 }
 
@@ -385,19 +338,8 @@ bool tc_loss_shape_ok(int64_t d, float temperature) {
     return d % 128 == 0 && d >= 128 && d <= 768 && temperature >= 0.025f;
 }
 
-static int tc_cluster_size() {   // DCLIP_TC_CLUSTER = 1 | 2 | 4 (default 1: multicast measured no gain, the kernel is not L2-bound)
-    static int c = 0;
-    if (!c) {
-        const char* e = getenv("DCLIP_TC_CLUSTER");
-        c = e ? atoi(e) : 1;
-        if (c != 1 && c != 2 && c != 4) c = 1;
-    }
-    return c;
-}
-
 int tc_nsplit(int64_t m, int64_t n, int nsides) {
-    const int C = tc_cluster_size();
-    const int64_t row_ctas = ceil_div(ceil_div(m, NI), C) * C * nsides;
+    const int64_t row_ctas = ceil_div(m, NI) * nsides;
     const int64_t ntiles = ceil_div(n, TJ);
     int64_t want = sm_count() / (row_ctas > 0 ? row_ctas : 1);
     if (want < 1) want = 1;
@@ -405,8 +347,8 @@ int tc_nsplit(int64_t m, int64_t n, int nsides) {
     return (int)want;
 }
 
-static size_t tc_smem_bytes(int64_t d, int mode) {
-    return 1024 + (size_t)((d + 63) / 64) * kXBoxBytes + (size_t)kSlots * kSlotBytes + (mode != 0 ? 2 * kGBytes : 0) + 512;
+static size_t tc_smem_bytes(int64_t d) {
+    return 1024 + (size_t)((d + 63) / 64) * kXBoxBytes + (size_t)kSlots * kSlotBytes + 2 * kGBytes + 512;
 }
 
 int* tc_error_flag() {   // one device int per device, lazily allocated, never freed
@@ -421,45 +363,25 @@ int* tc_error_flag() {   // one device int per device, lazily allocated, never f
     return flag[dev];
 }
 
-// x[side]: local rows [m, d] fp16; y[side]: all rows [n, d] fp16.
-int launch_infonce_tc(int mode, int nsides, const void* const x[2], const void* const y[2], const TcArgs& args_in, int nsplit,
-                      cudaStream_t st) {
+// x[side]: local rows [m, d] fp16; y[side]: all rows [n, d] fp16.  a.s[side].out = partial dx [nsplit][m][d].
+int launch_infonce_bwd_tc(int nsides, const void* const x[2], const void* const y[2], const TcArgs& args_in, int nsplit, cudaStream_t st) {
     if (!device_is_sm100()) return fail(DCLIP_ERR_ARCH, "tensor path needs an sm_100 device");
     TcArgs a = args_in;
-    CUtensorMap tmx[2], tmy[2], tmh[2];
+    CUtensorMap tmx[2], tmy[2];
     for (int s = 0; s < 2; ++s) {
         const int src = s < nsides ? s : 0;
         if (!make_tmap_2d_sw128(&tmx[s], x[src], (uint64_t)a.m, (uint64_t)a.d, NI, 0) ||
-            !make_tmap_2d_sw128(&tmy[s], y[src], (uint64_t)a.n, (uint64_t)a.d, TJ, 0) ||
-            !make_tmap_2d_sw128(&tmh[s], y[src], (uint64_t)a.n, (uint64_t)a.d, TJ / 2, 0))
+            !make_tmap_2d_sw128(&tmy[s], y[src], (uint64_t)a.n, (uint64_t)a.d, TJ, 0))
             return fail(DCLIP_ERR_CUDA, "cuTensorMapEncodeTiled failed (m=%lld n=%lld d=%lld)", (long long)a.m, (long long)a.n, (long long)a.d);
     }
     const int64_t ntiles = ceil_div(a.n, TJ);
     a.tiles_per_split = (int)ceil_div(ntiles, nsplit);
     a.error_flag = tc_error_flag();
-    const size_t smem = tc_smem_bytes(a.d, mode);
-    const int C = tc_cluster_size();
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)(ceil_div(ceil_div(a.m, NI), C) * C), (unsigned)nsplit, (unsigned)nsides);
-    cfg.blockDim = dim3(kTcThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-#define DCLIP_TC_LAUNCH(BWD, CL)                                                                                              \
-    do {                                                                                                                      \
-        DCLIP_CUDA_OK(cudaFuncSetAttribute(k_infonce_tc<BWD, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-        DCLIP_CUDA_OK(cudaLaunchKernelEx(&cfg, k_infonce_tc<BWD, CL>, tmx[0], tmy[0], tmx[1], tmy[1], tmh[0], tmh[1], a));    \
-    } while (0)
-    if (mode == 1) {
-        if (C == 1) DCLIP_TC_LAUNCH(1, 1); else if (C == 2) DCLIP_TC_LAUNCH(1, 2); else DCLIP_TC_LAUNCH(1, 4);
-    } else {
-        if (C == 1) DCLIP_TC_LAUNCH(0, 1); else if (C == 2) DCLIP_TC_LAUNCH(0, 2); else DCLIP_TC_LAUNCH(0, 4);
-    }
-#undef DCLIP_TC_LAUNCH
-    DCLIP_LAUNCH_OK("k_infonce_tc");
+    const size_t smem = tc_smem_bytes(a.d);
+    dim3 grid((unsigned)ceil_div(a.m, NI), (unsigned)nsplit, (unsigned)nsides);
+    DCLIP_CUDA_OK(cudaFuncSetAttribute(k_infonce_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_infonce_bwd_tc<<<grid, kTcThreads, smem, st>>>(tmx[0], tmy[0], tmx[1], tmy[1], a);
+    DCLIP_LAUNCH_OK("k_infonce_bwd_tc");
     return DCLIP_OK;
 }
 

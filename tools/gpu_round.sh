@@ -5,7 +5,7 @@ set -u
 cd "$(dirname "$0")/.."
 OUT=gpurun_out
 mkdir -p $OUT
-STAGES="${*:-probe simt tensor bench ncu}"
+STAGES="${*:-probe simt tensor bench ncu}"   # stages: probe simt tensor bench ncu ncufull
 nvidia-smi --query-gpu=name,driver_version,clocks.max.sm,power.limit --format=csv > $OUT/gpu.txt 2>&1
 
 has() { [[ " $STAGES " == *" $1 "* ]]; }
@@ -50,27 +50,11 @@ if has ncu; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$P.csv $CMD > $OUT/ncu_run.log 2>&1
   echo "ncu exit=$?"; tail -3 $OUT/ncu_run.log
 fi
-if has cluster; then
-  for C in 1 2 4; do
-    DCLIP_TC_CLUSTER=$C timeout 600 python -m pytest tests/test_loss_tensor_gpu.py -q -m gpu > $OUT/pytest_tensor_c$C.log 2>&1
-    echo "cluster=$C pytest exit=$?"; tail -4 $OUT/pytest_tensor_c$C.log
-    DCLIP_TC_CLUSTER=$C timeout 600 python bench.py --steps 20 --warmup 5 --path tensor --no-retrieval --no-cpu-baseline > $OUT/bench_tensor_c$C.json 2> $OUT/bench_tensor_c$C.err
-    echo "cluster=$C bench exit=$?"; tail -2 $OUT/bench_tensor_c$C.err
-    python - <<PY
-import json
-try:
-    d=json.loads(open("$OUT/bench_tensor_c$C.json").read().strip().splitlines()[-1])
-    print("cluster=$C ms_per_step", d["ms_per_step"], "value", d["value"], "e2e", d["e2e"]["value"], "roof", d["roofline"]["frac"], d["roofline"]["avg_launch_us"])
-except Exception as e: print("no bench json", e)
-PY
-  done
-fi
-
 if has ncufull; then
   # one full capture of the tensor-path kernels of the loss step (after the plain run passed) ...
   CMD="python bench.py --steps 1 --warmup 3 --path tensor --no-retrieval --no-cpu-baseline --no-graph"
   timeout 600 $CMD > $OUT/ncufull_plain.log 2>&1 && \
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_infonce_tc|k_stream_tc" -s 6 -c 2 -f -o $OUT/prof_loss_tc $CMD > $OUT/ncufull_run.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_infonce_bwd_tc|k_stream_tc" -s 6 -c 2 -f -o $OUT/prof_loss_tc $CMD > $OUT/ncufull_run.log 2>&1
   echo "ncufull loss exit=$?"; tail -2 $OUT/ncufull_run.log
   # ... and of the retrieval streaming kernel
   CMD2="python tools/prof_retrieval.py 1000000 16384"

@@ -27,16 +27,18 @@ def launches(path, out):
             d = dict(zip(hdr, r))
             if d.get("Metric Name") == "gpu__time_duration.sum":
                 k = d["Kernel Name"]
-                a = agg.setdefault(k, [0, 0.0, d["Grid Size"], d["Block Size"]])
+                a = agg.setdefault(k, [0, 0.0, d["Grid Size"], d["Block Size"], []])
                 a[0] += 1
                 a[1] += float(d["Metric Value"])
+                a[4].append(float(d["Metric Value"]))
     tot = sum(v[1] for v in agg.values())
     with open(out, "w") as f:
         f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none  ({path})\n")
-        f.write("# cold-cache, serialised launches: compare SHARES, not absolutes\n")
-        f.write("share%  total_us  launches  avg_us  grid  block  kernel\n")
+        f.write("# cold-cache, serialised launches: compare SHARES, not absolutes (the first launch of a kernel pays module load)\n")
+        f.write("share%  total_us  launches  avg_us  median_us  grid  block  kernel\n")
         for k, v in sorted(agg.items(), key=lambda x: -x[1][1]):
-            f.write(f"{100*v[1]/tot:6.1f}  {v[1]/1e3:9.1f}  {v[0]:5d}  {v[1]/v[0]/1e3:8.1f}  {v[2]}  {v[3]}  {k[:110]}\n")
+            med = sorted(v[4])[len(v[4]) // 2]
+            f.write(f"{100*v[1]/tot:6.1f}  {v[1]/1e3:9.1f}  {v[0]:5d}  {v[1]/v[0]/1e3:8.1f}  {med/1e3:8.1f}  {v[2]}  {v[3]}  {k[:110]}\n")
 
 
 def full(rep, out):
