@@ -134,6 +134,58 @@ int dclip_infonce_grad(const void* x_hat, int64_t m, const void* y_hat, int64_t 
     return fail(DCLIP_ERR_UNSUPPORTED, "infonce_grad: path %d not available", path);
 }
 
+size_t dclip_infonce_grad_pair_workspace_bytes(int64_t B, int64_t d, int path) {
+    if (path == DCLIP_PATH_TENSOR) {
+        const int ns = tc_nsplit(B, B, 2);
+        return ns > 1 ? align_up((size_t)2 * ns * B * d * sizeof(float), 256) + 256 : 256;
+    }
+    return 256;
+}
+
+int dclip_infonce_grad_pair(const void* u_hat, const void* v_hat, int64_t B, int64_t d, int op_dtype, float temperature,
+                            const float* lse_u, const float* lse_v, float coef, float* du_hat, float* dv_hat, void* workspace,
+                            size_t workspace_bytes, int path, void* stream) {
+    if (int e = check_common(B, d)) return e;
+    DCLIP_REQUIRE(u_hat && v_hat && lse_u && lse_v && du_hat && dv_hat && B > 0, "infonce_grad_pair: null pointer or empty batch");
+    DCLIP_REQUIRE(temperature > 0.f, "infonce_grad_pair: temperature must be > 0");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    path = resolve_loss_path(path, op_dtype);
+    if (path == DCLIP_PATH_FP32) {
+        DCLIP_REQUIRE(op_dtype == DCLIP_F32, "infonce_grad_pair: FP32 path needs float32 operands");
+        GradArgs ga{};
+        ga.s[0] = GradSide{(const float*)u_hat, (const float*)v_hat, lse_u, lse_v, du_hat};
+        ga.s[1] = GradSide{(const float*)v_hat, (const float*)u_hat, lse_v, lse_u, dv_hat};
+        ga.m = B; ga.n = B; ga.d = d; ga.temperature = temperature; ga.row_offset = 0;
+        ga.coef_over_tau = coef / temperature;
+        return launch_grad_simt(ga, 2, st);
+    }
+    DCLIP_REQUIRE(op_dtype == DCLIP_F16, "infonce_grad_pair: tensor path needs float16 operands");
+    if (!tc_loss_shape_ok(d, temperature))
+        return fail(DCLIP_ERR_UNSUPPORTED, "infonce_grad_pair: tensor path needs d %% 128 == 0, 128 <= d <= 768 and temperature >= 0.025 (d=%lld tau=%g)", (long long)d, temperature);
+    const int ns = tc_nsplit(B, B, 2);
+    float* du = du_hat;
+    float* dv = dv_hat;
+    if (ns > 1) {
+        Workspace ws(workspace, workspace_bytes);
+        du = static_cast<float*>(ws.take((size_t)2 * ns * B * d * sizeof(float)));
+        if (!ws.ok()) return fail(DCLIP_ERR_WORKSPACE, "infonce_grad_pair: workspace too small (%zu < %zu)", workspace_bytes, ws.used);
+        dv = du + (size_t)ns * B * d;
+    }
+    TcArgs ga{};
+    ga.s[0] = TcSide{lse_u, lse_v, du};
+    ga.s[1] = TcSide{lse_v, lse_u, dv};
+    ga.m = B; ga.n = B; ga.d = d; ga.inv_tau = 1.0f / temperature; ga.row_offset = 0;
+    ga.out_scale = coef / temperature * (1.0f / 8192.0f);
+    const void* xs[2] = {u_hat, v_hat};
+    const void* ys[2] = {v_hat, u_hat};
+    if (int e = launch_infonce_bwd_tc(2, xs, ys, ga, ns, st)) return e;
+    if (ns > 1) {
+        if (int e = launch_tc_grad_combine(du, ns, B, d, du_hat, st)) return e;
+        if (int e = launch_tc_grad_combine(dv, ns, B, d, dv_hat, st)) return e;
+    }
+    return DCLIP_OK;
+}
+
 int dclip_loss_grad_tail(const void* x, const void* teacher, const float* inv_norm, const float* dx_hat, int64_t m,
                          int64_t d, int dtype, float w_cos_over_B, float grad_scale, void* d_x, void* stream) {
     if (int e = check_common(m, d)) return e;

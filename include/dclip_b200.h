@@ -113,6 +113,12 @@ size_t dclip_infonce_grad_workspace_bytes(int64_t m, int64_t n, int64_t d, int p
 int dclip_infonce_grad(const void* x_hat, int64_t m, const void* y_hat, int64_t n, int64_t d, int op_dtype,
                        float temperature, int64_t row_offset, const float* lse_x, const float* lse_y, float coef,
                        float* dx_hat, void* workspace, size_t workspace_bytes, int path, void* stream);
+/* (3b) both directions of (3) in ONE launch for the single-GPU case (m == n == B, row_offset 0):
+ *      du_hat from (u_hat, v_hat, lse_u, lse_v) and dv_hat from (v_hat, u_hat, lse_v, lse_u). */
+size_t dclip_infonce_grad_pair_workspace_bytes(int64_t B, int64_t d, int path);
+int dclip_infonce_grad_pair(const void* u_hat, const void* v_hat, int64_t B, int64_t d, int op_dtype, float temperature,
+                            const float* lse_u, const float* lse_v, float coef, float* du_hat, float* dv_hat,
+                            void* workspace, size_t workspace_bytes, int path, void* stream);
 /* (4) row-local tail: adds the cosine-distillation gradient (-w_cos/B_global * t_hat), applies the
  *     normalise backward  dx = (g - x_hat (x_hat . g)) * inv_norm  and writes d_x in `dtype`.
  *     dx_hat may be NULL (cosine term only).  teacher may be NULL. */
