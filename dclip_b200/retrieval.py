@@ -173,6 +173,9 @@ def topk_ip(q, g, k, g_index_offset=0, path="auto", gallery=None):
         raise ValueError(f"topk_ip: dim mismatch {tuple(q.shape)} vs {tuple(g.shape)}")
     if path not in ("auto", "fp32", "tensor"):
         raise ValueError(f"topk_ip: unknown path {path!r}")
+    if q.shape[0] == 0 or g.shape[0] == 0:      # nothing to score: faiss-style (-inf, -1) padding
+        return (torch.full((q.shape[0], k), float("-inf"), dtype=torch.float32, device=q.device),
+                torch.full((q.shape[0], k), -1, dtype=torch.int64, device=q.device))
     use_tensor = path == "tensor" or (path == "auto" and g.shape[0] >= 16384 and tensor_path_ok(q, g, k))
     if use_tensor:
         if not tensor_path_ok(q, g, k):
