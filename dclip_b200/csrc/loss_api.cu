@@ -220,6 +220,98 @@ int dclip_distill_loss_launch_count(int64_t m, int64_t n, int64_t d, int path, i
     return 2 + 2 * 3 + 1 + 2 * (1 + (tc_nsplit(m, n, 1) > 1 ? 1 : 0)) + 2;
 }
 
+// ---- fused per-rank phases of the sharded objective (tensor path) -----------------------------
+size_t dclip_sharded_loss_workspace_bytes(int64_t m, int64_t n, int64_t d) {
+    const int nf = stream_nsplit(m, n, 2), nb = tc_nsplit(m, n, 2);
+    size_t total = 2 * align_up((size_t)nf * m * 4, 256);                 // forward partial row sums (two sides)
+    total += 2 * align_up((size_t)m * d * 4, 256);                        // du_hat, dv_hat
+    if (nb > 1) total += align_up((size_t)2 * nb * m * d * 4, 256);       // backward partials
+    return total + 1024;
+}
+
+int dclip_sharded_loss_prep(const void* s_img, const void* s_txt, const void* t_img, const void* t_txt, int64_t m, int64_t d, int dtype,
+                            float temperature, void* u_all, void* v_all, int64_t row_offset, float* inv_u, float* inv_v, float* cos_img,
+                            float* cos_txt, float* diag, void* stream) {
+    if (int e = check_common(m, d)) return e;
+    DCLIP_REQUIRE(s_img && s_txt && u_all && v_all && inv_u && inv_v && cos_img && cos_txt && diag, "sharded_loss_prep: null pointer");
+    DCLIP_REQUIRE((t_img == nullptr) == (t_txt == nullptr), "sharded_loss_prep: give both teachers or neither");
+    PrepArgs pa{};
+    pa.s[0] = PrepSide{s_img, t_img, static_cast<char*>(u_all) + (size_t)row_offset * d * 2, inv_u, cos_img};
+    pa.s[1] = PrepSide{s_txt, t_txt, static_cast<char*>(v_all) + (size_t)row_offset * d * 2, inv_v, cos_txt};
+    pa.m = m; pa.d = d; pa.diag = diag; pa.inv_tau = 1.0f / temperature;
+    return launch_loss_prep_pair(pa, dtype, DCLIP_F16, static_cast<cudaStream_t>(stream));
+}
+
+int dclip_sharded_loss_fwd(const void* u_all, const void* v_all, int64_t m, int64_t n, int64_t d, float temperature, int64_t row_offset,
+                           const float* cos_img, const float* cos_txt, const float* diag, float* stat_row, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+    if (int e = check_common(m, d)) return e;
+    DCLIP_REQUIRE(u_all && v_all && diag && stat_row && n >= m && m > 0, "sharded_loss_fwd: bad arguments");
+    if (!tc_loss_shape_ok(d, temperature))
+        return fail(DCLIP_ERR_UNSUPPORTED, "sharded_loss_fwd: tensor path needs d %% 128 == 0, 128 <= d <= 768 and temperature >= 0.025");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int nf = stream_nsplit(m, n, 2);
+    Workspace ws(workspace, workspace_bytes);
+    float* pu = static_cast<float*>(ws.take((size_t)nf * m * 4));
+    float* pv = static_cast<float*>(ws.take((size_t)nf * m * 4));
+    if (!ws.ok()) return fail(DCLIP_ERR_WORKSPACE, "sharded_loss_fwd: workspace too small (%zu < %zu)", workspace_bytes, ws.used);
+    const char* ul = static_cast<const char*>(u_all) + (size_t)row_offset * d * 2;
+    const char* vl = static_cast<const char*>(v_all) + (size_t)row_offset * d * 2;
+    TcArgs fa{};
+    fa.s[0] = TcSide{nullptr, nullptr, pu};
+    fa.s[1] = TcSide{nullptr, nullptr, pv};
+    fa.m = m; fa.n = n; fa.d = d; fa.inv_tau = 1.0f / temperature; fa.row_offset = row_offset;
+    const void* xs[2] = {ul, vl};
+    const void* ys[2] = {v_all, u_all};
+    if (int e = launch_stream_tc(0, 2, xs, ys, fa, nf, st)) return e;
+    FinalizeArgs fz{pu, pv, nf, m, fa.inv_tau, stat_row, stat_row + m,
+                    SumsArgs{stat_row, stat_row + m, diag, cos_img, cos_txt, m, stat_row + 2 * m, nullptr, 0.f, 0.f, 0.f}};
+    return launch_tc_finalize(fz, st);
+}
+
+int dclip_sharded_loss_bwd(const void* s_img, const void* s_txt, const void* t_img, const void* t_txt, const void* u_all, const void* v_all,
+                           int64_t m, int64_t n, int64_t d, int dtype, float temperature, int64_t row_offset, int rank, int world,
+                           const float* stat_all, const float* inv_u, const float* inv_v, float w_img, float w_txt, float w_con,
+                           float grad_scale, float* losses, void* d_s_img, void* d_s_txt, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+    if (int e = check_common(m, d)) return e;
+    DCLIP_REQUIRE(s_img && s_txt && u_all && v_all && stat_all && inv_u && inv_v && losses, "sharded_loss_bwd: null pointer");
+    DCLIP_REQUIRE(world >= 1 && rank >= 0 && rank < world && n == m * world, "sharded_loss_bwd: n must equal m * world");
+    DCLIP_REQUIRE((d_s_img == nullptr) == (d_s_txt == nullptr), "sharded_loss_bwd: give both gradients or neither");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t stride = 2 * m + 4;
+    if (int e = launch_sharded_losses(stat_all, world, stride, 2 * m, n, t_img != nullptr, t_txt != nullptr, w_img, w_txt, w_con, losses, st)) return e;
+    if (!d_s_img) return DCLIP_OK;
+    const int nb = tc_nsplit(m, n, 2);
+    Workspace ws(workspace, workspace_bytes);
+    ws.take((size_t)stream_nsplit(m, n, 2) * m * 4); ws.take((size_t)stream_nsplit(m, n, 2) * m * 4);   // (forward partials: same carve)
+    float* du_hat = static_cast<float*>(ws.take((size_t)m * d * 4));
+    float* dv_hat = static_cast<float*>(ws.take((size_t)m * d * 4));
+    float* part = nb > 1 ? static_cast<float*>(ws.take((size_t)2 * nb * m * d * 4)) : nullptr;
+    if (!ws.ok()) return fail(DCLIP_ERR_WORKSPACE, "sharded_loss_bwd: workspace too small (%zu < %zu)", workspace_bytes, ws.used);
+    const bool need_con = w_con != 0.f;
+    if (need_con) {
+        const float* mine = stat_all + (int64_t)rank * stride;
+        TcArgs ga{};
+        ga.s[0] = TcSide{mine, stat_all + m, nb > 1 ? part : du_hat, m, stride};                       // lse_y = lse_v of every rank
+        ga.s[1] = TcSide{mine + m, stat_all, nb > 1 ? part + (size_t)nb * m * d : dv_hat, m, stride};  // lse_y = lse_u of every rank
+        ga.m = m; ga.n = n; ga.d = d; ga.inv_tau = 1.0f / temperature; ga.row_offset = row_offset;
+        ga.out_scale = w_con / (2.0f * (float)n) / temperature * (1.0f / 8192.0f);
+        const void* xs[2] = {static_cast<const char*>(u_all) + (size_t)row_offset * d * 2, static_cast<const char*>(v_all) + (size_t)row_offset * d * 2};
+        const void* ys[2] = {v_all, u_all};
+        if (int e = launch_infonce_bwd_tc(2, xs, ys, ga, nb, st)) return e;
+        if (nb > 1)
+            if (int e = launch_tc_grad_combine2(part, nb, m, d, du_hat, dv_hat, st)) return e;
+    }
+    TailArgs ta{};
+    ta.m = m; ta.d = d; ta.grad_scale = grad_scale;
+    ta.s[0] = TailSide{s_img, t_img, inv_u, need_con ? du_hat : nullptr, d_s_img};
+    ta.s[1] = TailSide{s_txt, t_txt, inv_v, need_con ? dv_hat : nullptr, d_s_txt};
+    ta.w_cos_over_B[0] = w_img / (float)n;
+    ta.w_cos_over_B[1] = w_txt / (float)n;
+    return launch_grad_tail(ta, 2, dtype, st);
+}
+
 // ---- single-GPU composite -------------------------------------------------------------------
 // workspace: u_hat, v_hat [B,d] operands | inv_u, inv_v, cos_img, cos_txt, lse_u, lse_v, diag [B]
 //            | partials 2 x 2 x [nsplit, B] | du_hat, dv_hat [B,d] fp32

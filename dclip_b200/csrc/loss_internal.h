@@ -47,8 +47,9 @@ struct SumsArgs {
 // ---- tensor path (loss_tc.cu) ----
 struct TcSide {
     const float* lse_x;   // [m]   (bwd)
-    const float* lse_y;   // [n]   (bwd)
+    const float* lse_y;   // [n]   (bwd); with lse_y_block > 0 element j lives at (j / block) * stride + j % block
     float* out;           // fwd: partial row sums [nsplit][m];  bwd: partial dx [nsplit][m][d]
+    int64_t lse_y_block, lse_y_stride;   // blocked layout of the all-gathered per-rank statistics (sharded path)
 };
 struct TcArgs {
     TcSide s[2];
@@ -69,6 +70,8 @@ int launch_infonce_bwd_tc(int nsides, const void* const x[2], const void* const 
                           cudaStream_t st);
 int launch_tc_lse_combine(const float* part, int nsplit, int64_t m, float inv_tau, float* lse, cudaStream_t st);
 int launch_tc_grad_combine(const float* part, int nsplit, int64_t m, int64_t d, float* dx, cudaStream_t st);
+// both sides in one launch: part = [2][nsplit][m][d], dx0 / dx1 the two outputs
+int launch_tc_grad_combine2(const float* part, int nsplit, int64_t m, int64_t d, float* dx0, float* dx1, cudaStream_t st);
 int launch_tc_diag(const void* x, const void* y, int64_t m, int64_t n, int64_t d, float inv_tau, int64_t row_offset, float* diag,
                    cudaStream_t st);
 int tc_check_error_flag(cudaStream_t st);
@@ -86,6 +89,9 @@ struct FinalizeArgs {
     float* lse_u; float* lse_v; SumsArgs sums;
 };
 int launch_tc_finalize(const FinalizeArgs& a, cudaStream_t st);
+// global losses {total, img, txt, con} from the all-gathered per-rank raw sums stat[r * stride + off + 0..2]
+int launch_sharded_losses(const float* stat, int world, int64_t stride, int64_t off, int64_t B, int has_img, int has_txt,
+                          float w_img, float w_txt, float w_con, float* losses, cudaStream_t st);
 int simt_rowlse_nsplit(int64_t m, int64_t n, int64_t d);
 int launch_rowlse_simt(LseArgs a, int nsides, cudaStream_t st);
 int launch_grad_simt(const GradArgs& a, int nsides, cudaStream_t st);

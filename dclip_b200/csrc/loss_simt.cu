@@ -189,12 +189,26 @@ __global__ void __launch_bounds__(1024) k_tc_finalize(FinalizeArgs f) {
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        const float l_con = red[0][0] / (2.0f * (float)f.m);
-        const float l_img = a.cos_img ? red[1][0] / (float)f.m : 0.f;
-        const float l_txt = a.cos_txt ? red[2][0] / (float)f.m : 0.f;
-        a.losses[0] = a.w_img * l_img + a.w_txt * l_txt + a.w_con * l_con;
-        a.losses[1] = l_img; a.losses[2] = l_txt; a.losses[3] = l_con;
+        if (a.out3) { a.out3[0] = red[0][0]; a.out3[1] = red[1][0]; a.out3[2] = red[2][0]; }   // sharded: raw local sums
+        if (a.losses) {
+            const float l_con = red[0][0] / (2.0f * (float)f.m);
+            const float l_img = a.cos_img ? red[1][0] / (float)f.m : 0.f;
+            const float l_txt = a.cos_txt ? red[2][0] / (float)f.m : 0.f;
+            a.losses[0] = a.w_img * l_img + a.w_txt * l_txt + a.w_con * l_con;
+            a.losses[1] = l_img; a.losses[2] = l_txt; a.losses[3] = l_con;
+        }
     }
+}
+
+// global losses from the per-rank raw sums (fixed rank order: every rank gets the same bits)
+__global__ void k_sharded_losses(const float* __restrict__ stat, int world, int64_t stride, int64_t off, float B, int has_img, int has_txt,
+                                 float w_img, float w_txt, float w_con, float* __restrict__ losses) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int r = 0; r < world; ++r) { s0 += stat[r * stride + off]; s1 += stat[r * stride + off + 1]; s2 += stat[r * stride + off + 2]; }
+    const float l_con = s0 / (2.0f * B), l_img = has_img ? s1 / B : 0.f, l_txt = has_txt ? s2 / B : 0.f;
+    losses[0] = w_img * l_img + w_txt * l_txt + w_con * l_con;
+    losses[1] = l_img; losses[2] = l_txt; losses[3] = l_con;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -537,6 +551,13 @@ int launch_loss_prep_pair(const PrepArgs& a, int dtype, int op_dtype, cudaStream
         return fail(DCLIP_ERR_INVALID, "loss_prep_pair: bad op_dtype %d", op_dtype);
     }
     DCLIP_LAUNCH_OK("k_loss_prep_pair");
+    return DCLIP_OK;
+}
+
+int launch_sharded_losses(const float* stat, int world, int64_t stride, int64_t off, int64_t B, int has_img, int has_txt, float w_img,
+                          float w_txt, float w_con, float* losses, cudaStream_t st) {
+    k_sharded_losses<<<1, 32, 0, st>>>(stat, world, stride, off, (float)B, has_img, has_txt, w_img, w_txt, w_con, losses);
+    DCLIP_LAUNCH_OK("k_sharded_losses");
     return DCLIP_OK;
 }
 

@@ -222,7 +222,8 @@ k_infonce_bwd_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant
                 const bool jvalid = gj < a.n;
                 {
                     ok = ok && mbar_wait(&g_empty[b], ((t >> 1) & 1) ^ 1, kSpin);
-                    const float bj = jvalid ? exp2f((a.inv_tau - S.lse_y[gj]) * 1.4426950408889634f + kGScaleLog2) : 0.f;
+                    const int64_t ly = S.lse_y_block > 0 ? (gj / S.lse_y_block) * S.lse_y_stride + gj % S.lse_y_block : gj;
+                    const float bj = jvalid ? exp2f((a.inv_tau - S.lse_y[ly]) * 1.4426950408889634f + kGScaleLog2) : 0.f;
                     // diagonal element of this row, if it falls inside the CTA's 64 columns
                     const int64_t di = gj - a.row_offset - row0;      // column index i with global i == j
                     uint8_t* grow = gs + (size_t)b * kGBytes + (size_t)et * 128;
@@ -310,6 +311,18 @@ __global__ void k_tc_grad_combine(const float* __restrict__ part, int nsplit, in
     reinterpret_cast<float4*>(dx)[i] = acc;
 }
 
+__global__ void k_tc_grad_combine2(const float* __restrict__ part, int nsplit, int64_t count4, float* __restrict__ dx0, float* __restrict__ dx1) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count4) return;
+    const float4* src = reinterpret_cast<const float4*>(part) + (int64_t)blockIdx.y * nsplit * count4;
+    float4 acc = src[i];
+    for (int p = 1; p < nsplit; ++p) {
+        const float4 v = src[(int64_t)p * count4 + i];
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    reinterpret_cast<float4*>(blockIdx.y ? dx1 : dx0)[i] = acc;
+}
+
 // diag[i] = x_hat_i . y_hat_{off+i} / tau from the fp16 operands (one warp per row)
 __global__ void k_tc_diag(const __half* __restrict__ x, const __half* __restrict__ y, int64_t m, int64_t n, int64_t d, float inv_tau,
                           int64_t row_offset, float* __restrict__ diag) {
@@ -394,6 +407,12 @@ int launch_tc_grad_combine(const float* part, int nsplit, int64_t m, int64_t d, 
     const int64_t count4 = m * d / 4;
     k_tc_grad_combine<<<(unsigned)ceil_div(count4, 256), 256, 0, st>>>(part, nsplit, count4, dx);
     DCLIP_LAUNCH_OK("k_tc_grad_combine");
+    return DCLIP_OK;
+}
+int launch_tc_grad_combine2(const float* part, int nsplit, int64_t m, int64_t d, float* dx0, float* dx1, cudaStream_t st) {
+    const int64_t count4 = m * d / 4;
+    k_tc_grad_combine2<<<dim3((unsigned)ceil_div(count4, 256), 2), 256, 0, st>>>(part, nsplit, count4, dx0, dx1);
+    DCLIP_LAUNCH_OK("k_tc_grad_combine2");
     return DCLIP_OK;
 }
 int launch_tc_diag(const void* x, const void* y, int64_t m, int64_t n, int64_t d, float inv_tau, int64_t row_offset, float* diag,

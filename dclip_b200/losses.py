@@ -240,6 +240,8 @@ def sharded_distill_loss_fwd_bwd(s_img, s_txt, t_img=None, t_txt=None, temperatu
     """
     import torch.distributed as dist
 
+    if ops is None and _fused_sharded_ok(s_img, temperature, path):
+        return _sharded_fused(s_img, s_txt, t_img, t_txt, temperature, w_img, w_txt, w_con, grad_scale, need_grad, group)
     ops = ops or CudaLossOps(path)
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -288,6 +290,61 @@ def sharded_distill_loss_fwd_bwd(s_img, s_txt, t_img=None, t_txt=None, temperatu
     dv_hat = ops.grad(v_loc, u_all, temperature, row_offset, lse_v.contiguous(), lse_u_all, coef) if w_con != 0 else None
     d_img = ops.tail(s_img, t_img, inv_u, du_hat, w_img / B, grad_scale)
     d_txt = ops.tail(s_txt, t_txt, inv_v, dv_hat, w_txt / B, grad_scale)
+    return losses, d_img, d_txt
+
+
+def _fused_sharded_ok(x, temperature, path):
+    """The fused 7-launch per-rank path needs the tensor kernels: 16-bit inputs (or path="tensor"),
+    d % 128 == 0, d <= 768, temperature >= 0.025, an sm_100 device."""
+    if path == "fp32" or not x.is_cuda:
+        return False
+    if path == "auto" and x.dtype == torch.float32:
+        return False
+    d = x.shape[1]
+    lib = _lib.load_library()
+    return (d % 128 == 0 and 128 <= d <= 768 and temperature >= 0.025
+            and lib.dclip_device_supports_tensor_path(x.device.index or 0) == 1)
+
+
+def _sharded_fused(s_img, s_txt, t_img, t_txt, temperature, w_img, w_txt, w_con, grad_scale, need_grad, group):
+    """Per-rank step on the fused C-ABI phases: prep -> [all-gather u, v] -> forward + local statistics ->
+    [all-gather stats] -> global losses + backward + gradient tail."""
+    import torch.distributed as dist
+
+    lib = _lib.load_library()
+    dev = require_cuda(s_img, s_txt, t_img, t_txt)
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    m, d = s_img.shape
+    n = m * world
+    row_offset = rank * m
+    f32 = dict(dtype=torch.float32, device=dev)
+    ops_all = torch.empty((2, n, d), dtype=torch.float16, device=dev)
+    u_all, v_all = ops_all[0], ops_all[1]
+    vecs = torch.empty((5, m), **f32)                       # inv_u, inv_v, cos_img, cos_txt, diag
+    stat = torch.empty((world, 2 * m + 4), **f32)
+    losses = torch.empty(4, **f32)
+    d_img = torch.empty_like(s_img) if need_grad else None
+    d_txt = torch.empty_like(s_txt) if need_grad else None
+    ws = workspace(lib.dclip_sharded_loss_workspace_bytes(m, n, d), dev)
+    has_t = t_img is not None
+    with torch.cuda.device(dev):
+        st = stream_ptr(dev)
+        check(lib.dclip_sharded_loss_prep(ptr(s_img), ptr(s_txt), ptr(t_img), ptr(t_txt), m, d, dtype_code(s_img),
+                                          float(temperature), ptr(u_all), ptr(v_all), row_offset, ptr(vecs[0]), ptr(vecs[1]),
+                                          ptr(vecs[2]), ptr(vecs[3]), ptr(vecs[4]), st), "sharded_loss_prep")
+        if world > 1:
+            dist.all_gather_into_tensor(u_all, u_all[row_offset:row_offset + m], group=group)
+            dist.all_gather_into_tensor(v_all, v_all[row_offset:row_offset + m], group=group)
+        check(lib.dclip_sharded_loss_fwd(ptr(u_all), ptr(v_all), m, n, d, float(temperature), row_offset,
+                                         ptr(vecs[2]) if has_t else None, ptr(vecs[3]) if has_t else None, ptr(vecs[4]),
+                                         ptr(stat[rank]), ptr(ws), ws.numel(), st), "sharded_loss_fwd")
+        if world > 1:
+            dist.all_gather_into_tensor(stat.view(-1), stat[rank], group=group)
+        check(lib.dclip_sharded_loss_bwd(ptr(s_img), ptr(s_txt), ptr(t_img), ptr(t_txt), ptr(u_all), ptr(v_all), m, n, d,
+                                         dtype_code(s_img), float(temperature), row_offset, rank, world, ptr(stat), ptr(vecs[0]),
+                                         ptr(vecs[1]), float(w_img), float(w_txt), float(w_con), float(grad_scale), ptr(losses),
+                                         ptr(d_img), ptr(d_txt), ptr(ws), ws.numel(), st), "sharded_loss_bwd")
     return losses, d_img, d_txt
 
 

@@ -130,6 +130,24 @@ int dclip_loss_grad_tail(const void* x, const void* teacher, const float* inv_no
 int dclip_loss_partial_sums(const float* lse_u, const float* lse_v, const float* diag, const float* cos_img,
                             const float* cos_txt, int64_t m, float* out3, void* stream);
 
+/* Fused form of (1)-(5) for the tensor path: three calls per rank and step, 7 kernel launches, with the
+ * host's all-gathers in between.  u_all / v_all: float16 [n, d] gather buffers (this rank writes rows
+ * [row_offset, row_offset + m) in _prep, the host all-gathers them in place).  stat: float [world][2m + 4]
+ * gather buffer; _fwd fills this rank's row {lse_u[m], lse_v[m], 3 raw loss sums}, the host all-gathers it,
+ * _bwd reads every rank's row (blocked lse lookup inside the kernel, global losses from the raw sums). */
+size_t dclip_sharded_loss_workspace_bytes(int64_t m, int64_t n, int64_t d);
+int dclip_sharded_loss_prep(const void* s_img, const void* s_txt, const void* t_img, const void* t_txt, int64_t m, int64_t d,
+                            int dtype, float temperature, void* u_all, void* v_all, int64_t row_offset, float* inv_u,
+                            float* inv_v, float* cos_img, float* cos_txt, float* diag, void* stream);
+int dclip_sharded_loss_fwd(const void* u_all, const void* v_all, int64_t m, int64_t n, int64_t d, float temperature,
+                           int64_t row_offset, const float* cos_img, const float* cos_txt, const float* diag, float* stat_row,
+                           void* workspace, size_t workspace_bytes, void* stream);
+int dclip_sharded_loss_bwd(const void* s_img, const void* s_txt, const void* t_img, const void* t_txt, const void* u_all,
+                           const void* v_all, int64_t m, int64_t n, int64_t d, int dtype, float temperature, int64_t row_offset,
+                           int rank, int world, const float* stat_all, const float* inv_u, const float* inv_v, float w_img,
+                           float w_txt, float w_con, float grad_scale, float* losses, void* d_s_img, void* d_s_txt,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Retrieval   (replaces the similarity build + calculate_retrieval_metrics,
  *   eval_scripts/flickr30k_eval.py:243-266 and :16-88, and the faiss IndexFlatIP add/search

@@ -24,8 +24,13 @@ def main():
         full = [t.to(dtype).to(dev) for t in synthetic.loss_inputs(B, d, seed=7)]
         ref_losses, ref_di, ref_dt = L.distill_loss_fwd_bwd(*full, path=path)
         loc = [t[rank * m:(rank + 1) * m].contiguous() for t in full]
-        losses, di, dt = L.sharded_distill_loss_fwd_bwd(*loc, path=path)
+        losses, di, dt = L.sharded_distill_loss_fwd_bwd(*loc, path=path)       # fused phases on the tensor path
         torch.cuda.synchronize()
+        if path == "tensor":                                                     # generic building-block choreography
+            l2, di2, dt2 = L.sharded_distill_loss_fwd_bwd(*loc, path=path, ops=L.CudaLossOps("tensor"))
+            torch.cuda.synchronize()
+            assert torch.allclose(l2, losses, rtol=1e-5, atol=1e-6), (l2, losses)
+            assert torch.allclose(di2.float(), di.float(), rtol=2e-2, atol=1e-6)
         assert torch.allclose(losses, ref_losses, rtol=tol, atol=1e-5), (path, losses, ref_losses)
         for a, b in ((di, ref_di[rank * m:(rank + 1) * m]), (dt, ref_dt[rank * m:(rank + 1) * m])):
             rel = float((a.float() - b.float()).norm() / b.float().norm())
