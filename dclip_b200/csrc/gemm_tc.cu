@@ -11,7 +11,7 @@
 //   B MN-major : B stored [K, N]  (X for dW, W for dX)         4 boxes [64 k x 64 n], LBO = 8 KB
 // (the MN-major canonical layout is the same bytes TMA writes for a [k rows x 64 columns] box; both
 // were validated against a CPU GEMM with tools/tc_probe).  Tile 128 x 256, K in 64-wide stages, 4-stage
-// ring, 4 producer warps, 1 MMA-issuer warp, 4 epilogue warps (thread = output row).  One CTA per tile.
+// ring, 4 producer warps, 1 MMA-issuer warp, 4 epilogue warps (thread = output row).  Persistent CTAs.
 #include "common.cuh"
 #include "gemm_tc.h"
 #include "tcgen05.cuh"
@@ -33,41 +33,47 @@ struct TcGemmDev {
     int a_mn, b_mn;
     int tiles_n, tile_begin;      // tiles of this problem occupy [tile_begin, tile_begin + tiles_m * tiles_n)
     int accumulate;
-    void* C16; int c16_kind;      // optional 16-bit copy of C (0 none, 1 bf16, 2 fp16), same ldc
+    void* C16; int c16_kind, ldc16;   // optional 16-bit copy of C (0 none, 1 bf16, 2 fp16); C itself may then be null
 };
 struct TcGemmArgs {
     CUtensorMap ta[kTcGemmMax], tb[kTcGemmMax];
     TcGemmDev p[kTcGemmMax];
-    int count;
+    int count, total_tiles;
     int ab_fmt;                   // kFmtBF16 / kFmtF16
     int* error_flag;
 };
 
+struct TileCoord { int pi, m0, n0, nkb; };
+__device__ __forceinline__ TileCoord tile_coord(const TcGemmArgs& g, int tile) {
+    int pi = 0;
+    for (int i = 1; i < g.count; ++i)
+        if (tile >= g.p[i].tile_begin) pi = i;
+    const TcGemmDev& P = g.p[pi];
+    const int local = tile - P.tile_begin;
+    const int tm = local / P.tiles_n, tn = local - tm * P.tiles_n;
+    return TileCoord{pi, tm * GM, tn * GN, (P.K + GKS - 1) / GKS};
+}
+
+// Persistent: gridDim.x CTAs walk the tile list with stride gridDim.x.  The TMA ring keeps flowing across
+// tile boundaries and the two 256-column TMEM accumulators let the epilogue of tile t overlap the main loop
+// of tile t+1, so the per-tile prologue / epilogue latency is paid once per CTA, not once per tile.
 __global__ void __launch_bounds__(kGThreads, 1) k_gemm_tc(const __grid_constant__ TcGemmArgs g) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full = reinterpret_cast<uint64_t*>(ring + kGStages * kGStageBytes);
     uint64_t* empty = full + kGStages;
-    uint64_t* acc_full = empty + kGStages;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 1);
-
-    // which problem / tile
-    int pi = 0;
-    for (int i = 1; i < g.count; ++i)
-        if ((int)blockIdx.x >= g.p[i].tile_begin) pi = i;
-    const TcGemmDev& P = g.p[pi];
-    const int local = (int)blockIdx.x - P.tile_begin;
-    const int tm = local / P.tiles_n, tn = local - tm * P.tiles_n;
-    const int m0 = tm * GM, n0 = tn * GN;
-    const int nkb = (P.K + GKS - 1) / GKS;
+    uint64_t* acc_full = empty + kGStages;       // [2]
+    uint64_t* acc_empty = acc_full + 2;          // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
     const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+    const int total_tiles = g.total_tiles;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kGStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        mbar_init(acc_full, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
         fence_barrier_init();
     }
-    if (warp == kGStages) tmem_alloc(tmem_ptr, 256);
+    if (warp == kGStages) tmem_alloc(tmem_ptr, 512);
     fence_before_thread_sync();
     __syncthreads();
     fence_after_thread_sync();
@@ -75,84 +81,105 @@ __global__ void __launch_bounds__(kGThreads, 1) k_gemm_tc(const __grid_constant_
     bool ok = true;
 
     if (warp < kGStages) {
+        // ---- TMA producers: warp w owns ring stage w; stage job q = running k-block index over all my tiles
         if (elect_one()) {
-            const CUtensorMap* ta = &g.ta[pi];
-            const CUtensorMap* tb = &g.tb[pi];
-            tma_prefetch_desc(ta);
-            tma_prefetch_desc(tb);
+            for (int i = 0; i < g.count; ++i) { tma_prefetch_desc(&g.ta[i]); tma_prefetch_desc(&g.tb[i]); }
             uint8_t* dst = ring + (size_t)warp * kGStageBytes;
             uint32_t phase = 0;
-            for (int kb = warp; kb < nkb && ok; kb += kGStages, phase ^= 1) {
-                const int k0 = kb * GKS;
-                ok = mbar_wait(&empty[warp], phase ^ 1, kSpinG);
-                mbar_arrive_expect_tx(&full[warp], kGStageBytes);
-                if (!P.a_mn) tma_load_2d(dst, ta, &full[warp], k0, m0);                     // [128 m x 64 k]
-                else
-                    for (int h = 0; h < 2; ++h) tma_load_2d(dst + h * 8192, ta, &full[warp], m0 + h * 64, k0);   // [64 k x 64 m]
-                if (!P.b_mn) tma_load_2d(dst + kGAStage, tb, &full[warp], k0, n0);           // [256 n x 64 k]
-                else
-                    for (int h = 0; h < 4; ++h) tma_load_2d(dst + kGAStage + h * 8192, tb, &full[warp], n0 + h * 64, k0);
+            int q0 = 0;                                    // job index of the first k-block of the current tile
+            for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+                const TileCoord tc = tile_coord(g, tile);
+                const TcGemmDev& P = g.p[tc.pi];
+                const CUtensorMap* ta = &g.ta[tc.pi];
+                const CUtensorMap* tb = &g.tb[tc.pi];
+                // my k-blocks of this tile: those with (q0 + kb) % kGStages == warp
+                int kb = (warp - q0 % kGStages + kGStages) % kGStages;
+                for (; kb < tc.nkb && ok; kb += kGStages, phase ^= 1) {
+                    const int k0 = kb * GKS;
+                    ok = mbar_wait(&empty[warp], phase ^ 1, kSpinG);
+                    mbar_arrive_expect_tx(&full[warp], kGStageBytes);
+                    if (!P.a_mn) tma_load_2d(dst, ta, &full[warp], k0, tc.m0);                     // [128 m x 64 k]
+                    else
+                        for (int h = 0; h < 2; ++h) tma_load_2d(dst + h * 8192, ta, &full[warp], tc.m0 + h * 64, k0);   // [64 k x 64 m]
+                    if (!P.b_mn) tma_load_2d(dst + kGAStage, tb, &full[warp], k0, tc.n0);           // [256 n x 64 k]
+                    else
+                        for (int h = 0; h < 4; ++h) tma_load_2d(dst + kGAStage + h * 8192, tb, &full[warp], tc.n0 + h * 64, k0);
+                }
+                q0 += tc.nkb;
             }
         }
     } else if (warp == kGStages) {
+        // ---- MMA issuer
         if (elect_one()) {
-            const uint32_t idesc = make_idesc_f16(GM, GN, (uint32_t)g.ab_fmt, (uint32_t)P.a_mn, (uint32_t)P.b_mn);
-            const uint64_t hiA = make_smem_desc_hi(P.a_mn ? 8192 : 0, 1024, kSwizzle128B);
-            const uint64_t hiB = make_smem_desc_hi(P.b_mn ? 8192 : 0, 1024, kSwizzle128B);
-            const uint32_t stepA = P.a_mn ? 128u : 2u, stepB = P.b_mn ? 128u : 2u;   // per K=16 step, >>4 encoded
             const uint32_t ring_addr = smem_u32(ring);
             uint32_t stage = 0, phase = 0;
-            for (int kb = 0; kb < nkb && ok; ++kb) {
-                ok = mbar_wait(&full[stage], phase, kSpinG);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x, ++it) {
+                const TileCoord tc = tile_coord(g, tile);
+                const TcGemmDev& P = g.p[tc.pi];
+                const int b = it & 1;
+                const uint32_t idesc = make_idesc_f16(GM, GN, (uint32_t)g.ab_fmt, (uint32_t)P.a_mn, (uint32_t)P.b_mn);
+                const uint64_t hiA = make_smem_desc_hi(P.a_mn ? 8192 : 0, 1024, kSwizzle128B);
+                const uint64_t hiB = make_smem_desc_hi(P.b_mn ? 8192 : 0, 1024, kSwizzle128B);
+                const uint32_t stepA = P.a_mn ? 128u : 2u, stepB = P.b_mn ? 128u : 2u;   // per K=16 step, >>4 encoded
+                ok = mbar_wait(&acc_empty[b], ((it >> 1) & 1) ^ 1, kSpinG);
                 fence_after_thread_sync();
-                const uint64_t da0 = smem_desc(hiA, ring_addr + stage * kGStageBytes);
-                const uint64_t db0 = smem_desc(hiB, ring_addr + stage * kGStageBytes + kGAStage);
+                for (int kb = 0; kb < tc.nkb && ok; ++kb) {
+                    ok = mbar_wait(&full[stage], phase, kSpinG);
+                    fence_after_thread_sync();
+                    const uint64_t da0 = smem_desc(hiA, ring_addr + stage * kGStageBytes);
+                    const uint64_t db0 = smem_desc(hiB, ring_addr + stage * kGStageBytes + kGAStage);
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) umma_f16(tmem, da0 + (uint64_t)(ks * stepA), db0 + (uint64_t)(ks * stepB), idesc, (kb | ks) != 0);
-                umma_commit(&empty[stage]);
-                if (++stage == kGStages) { stage = 0; phase ^= 1; }
+                    for (int ks = 0; ks < 4; ++ks)
+                        umma_f16(tmem + b * GN, da0 + (uint64_t)(ks * stepA), db0 + (uint64_t)(ks * stepB), idesc, (kb | ks) != 0);
+                    umma_commit(&empty[stage]);
+                    if (++stage == kGStages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&acc_full[b]);
             }
-            umma_commit(acc_full);
         }
     } else {
+        // ---- epilogue: TMEM hands each thread one output ROW; global memory wants a warp on one row.  Each
+        // warp transposes its 32 x 32 chunk through a private padded smem tile so that bias / residual reads
+        // and the C stores are 128-byte coalesced float4 accesses.
         const int qd = warp & 3;
-            const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
-        ok = mbar_wait(acc_full, 0, kSpinG);
-        ok = __all_sync(0xffffffffu, ok);
-        if (ok) {
+        const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
+        float* tile_s = reinterpret_cast<float*>(ring + kGStages * kGStageBytes + 256) + (size_t)qd * 32 * 33;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const TileCoord tc = tile_coord(g, tile);
+            const TcGemmDev& P = g.p[tc.pi];
+            const int b = it & 1;
+            ok = mbar_wait(&acc_full[b], (it >> 1) & 1, kSpinG);
+            ok = __all_sync(0xffffffffu, ok);
+            if (!ok) break;
             fence_after_thread_sync();
-            // TMEM hands each thread one output ROW; global memory wants a warp on one row.  Each warp
-            // transposes its 32 x 32 chunk through a private padded smem tile so that bias / residual reads
-            // and the C stores are 128-byte coalesced.
-            float* tile = reinterpret_cast<float*>(ring + kGStages * kGStageBytes + 256) + (size_t)qd * 32 * 33;
-            const int rbase = m0 + qd * 32;
+            const int rbase = tc.m0 + qd * 32;
 #pragma unroll 1
             for (int c0 = 0; c0 < GN; c0 += 32) {
                 uint32_t r[32];
-                tmem_ld_32x32b_x32(tmem + lane_addr + c0, r);
+                tmem_ld_32x32b_x32(tmem + lane_addr + b * GN + c0, r);
                 tmem_ld_wait();
-                if (n0 + c0 >= P.N) continue;              // warp-uniform
+                if (tc.n0 + c0 >= P.N) continue;              // warp-uniform
 #pragma unroll
-                for (int i = 0; i < 32; ++i) tile[lane * 33 + i] = __uint_as_float(r[i]);
+                for (int i = 0; i < 32; ++i) tile_s[lane * 33 + i] = __uint_as_float(r[i]);
                 __syncwarp();
-                // lane -> (row within a group of 4, 4 consecutive columns): 8 unrolled iterations cover the 32 rows,
-                // every access is a float4 on a 128-byte contiguous row segment
                 const int rsub = lane >> 3, cg = (lane & 7) * 4;
-                const int col = n0 + c0 + cg;
+                const int col = tc.n0 + c0 + cg;
                 const bool full4 = col + 4 <= P.N && (P.ldc & 3) == 0;
                 float bv[4] = {0.f, 0.f, 0.f, 0.f};
                 if (P.bias)
 #pragma unroll
                     for (int j = 0; j < 4; ++j) bv[j] = col + j < P.N ? P.bias[col + j] : 0.f;
 #pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    const int rr = it * 4 + rsub;
+                for (int rit = 0; rit < 8; ++rit) {
+                    const int rr = rit * 4 + rsub;
                     const int grow = rbase + rr;
                     if (grow < P.M && col < P.N) {
                         float v[4];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) v[j] = tile[rr * 33 + cg + j] + bv[j];
-                        float* cp = P.C + (size_t)grow * P.ldc + col;
+                        for (int j = 0; j < 4; ++j) v[j] = tile_s[rr * 33 + cg + j] + bv[j];
+                        float* cp = P.C ? P.C + (size_t)grow * P.ldc + col : nullptr;
                         if (full4) {
                             if (P.residual) {
                                 const float4 rv = *reinterpret_cast<const float4*>(P.residual + (size_t)grow * P.ldr + col);
@@ -162,29 +189,31 @@ __global__ void __launch_bounds__(kGThreads, 1) k_gemm_tc(const __grid_constant_
                                 const float4 cv = *reinterpret_cast<const float4*>(cp);
                                 v[0] += cv.x; v[1] += cv.y; v[2] += cv.z; v[3] += cv.w;
                             }
-                            *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
+                            if (cp) *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
                         } else {
                             for (int j = 0; j < 4 && col + j < P.N; ++j) {
                                 if (P.residual) v[j] += P.residual[(size_t)grow * P.ldr + col + j];
                                 if (P.accumulate) v[j] += cp[j];
-                                cp[j] = v[j];
+                                if (cp) cp[j] = v[j];
                             }
                         }
                         if (P.c16_kind)
                             for (int j = 0; j < 4 && col + j < P.N; ++j) {
-                                if (P.c16_kind == 1) static_cast<__nv_bfloat16*>(P.C16)[(size_t)grow * P.ldc + col + j] = __float2bfloat16_rn(v[j]);
-                                else static_cast<__half*>(P.C16)[(size_t)grow * P.ldc + col + j] = __float2half_rn(v[j]);
+                                if (P.c16_kind == 1) static_cast<__nv_bfloat16*>(P.C16)[(size_t)grow * P.ldc16 + col + j] = __float2bfloat16_rn(v[j]);
+                                else static_cast<__half*>(P.C16)[(size_t)grow * P.ldc16 + col + j] = __float2half_rn(v[j]);
                             }
                     }
                 }
                 __syncwarp();
             }
+            fence_before_thread_sync();
+            mbar_arrive(&acc_empty[b]);
         }
     }
     if (!ok && lane == 0 && g.error_flag) atomicExch(g.error_flag, 1);
     fence_before_thread_sync();
     __syncthreads();
-    if (warp == kGStages) tmem_dealloc(tmem, 256);
+    if (warp == kGStages) tmem_dealloc(tmem, 512);
 }
 
 int* tc_error_flag();   // loss_tc.cu
@@ -202,6 +231,8 @@ int launch_gemm_tc(const TcGemmProblem* probs, int count, int dtype16, cudaStrea
     for (int i = 0; i < count; ++i) {
         const TcGemmProblem& q = probs[i];
         if (q.M <= 0 || q.N <= 0 || q.K <= 0) return fail(DCLIP_ERR_INVALID, "gemm_tc: empty problem %d", i);
+        if (!q.C && !q.C16) return fail(DCLIP_ERR_INVALID, "gemm_tc: problem %d has no output", i);
+        if (q.accumulate && !q.C) return fail(DCLIP_ERR_INVALID, "gemm_tc: accumulate needs the fp32 output");
         if (q.lda % 8 || q.ldb % 8 || q.ldc % 4) return fail(DCLIP_ERR_INVALID, "gemm_tc: leading dimensions must keep 16-byte row alignment");
         bool okm;
         // A: K-major stored [M, K] (rows = M, cols = K); MN-major stored [K, M]
@@ -214,14 +245,15 @@ int launch_gemm_tc(const TcGemmProblem* probs, int count, int dtype16, cudaStrea
         d.C = q.C; d.bias = q.bias; d.residual = q.residual;
         d.M = q.M; d.N = q.N; d.K = q.K; d.ldc = q.ldc; d.ldr = q.ldr;
         d.a_mn = q.a_mn; d.b_mn = q.b_mn; d.accumulate = q.accumulate;
-        d.C16 = q.C16; d.c16_kind = q.C16 ? (dtype16 == DCLIP_BF16 ? 1 : 2) : 0;
+        d.C16 = q.C16; d.c16_kind = q.C16 ? (dtype16 == DCLIP_BF16 ? 1 : 2) : 0; d.ldc16 = q.ldc16 > 0 ? q.ldc16 : q.ldc;
         d.tiles_n = (q.N + GN - 1) / GN;
         d.tile_begin = tiles;
         tiles += ((q.M + GM - 1) / GM) * d.tiles_n;
     }
+    g.total_tiles = tiles;
     const size_t smem = 1024 + (size_t)kGStages * kGStageBytes + 256 + 4 * 32 * 33 * sizeof(float);
     DCLIP_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_gemm_tc<<<tiles, kGThreads, smem, st>>>(g);
+    k_gemm_tc<<<min(tiles, sm_count()), kGThreads, smem, st>>>(g);
     DCLIP_LAUNCH_OK("k_gemm_tc");
     return DCLIP_OK;
 }

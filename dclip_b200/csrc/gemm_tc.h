@@ -13,6 +13,7 @@ struct TcGemmProblem {
     const void* A; const void* B; float* C; const float* bias; const float* residual; void* C16;
     int M, N, K, lda, ldb, ldc, ldr;
     int a_mn, b_mn, accumulate;
+    int ldc16;      // row stride of C16 (0 = ldc); C may be null when only the 16-bit output is wanted
 };
 
 int launch_gemm_tc(const TcGemmProblem* probs, int count, int dtype16, cudaStream_t st);
