@@ -87,7 +87,7 @@ int dclip_infonce_rowlse(const void* x_hat, int64_t m, const void* y_hat, int64_
 
 size_t dclip_infonce_grad_workspace_bytes(int64_t m, int64_t n, int64_t d, int path) {
     if (path == DCLIP_PATH_TENSOR) {
-        const int ns = tc_nsplit(m, n, 1);
+        const int ns = tc_nsplit(m, n, d, 1);
         return ns > 1 ? align_up((size_t)ns * m * d * sizeof(float), 256) + 256 : 256;
     }
     return 256;
@@ -114,7 +114,7 @@ int dclip_infonce_grad(const void* x_hat, int64_t m, const void* y_hat, int64_t 
         if (!tc_loss_shape_ok(d, temperature))
             return fail(DCLIP_ERR_UNSUPPORTED, "infonce_grad: tensor path needs d %% 128 == 0, 128 <= d <= 768 and temperature >= 0.025 (d=%lld tau=%g)", (long long)d, temperature);
         cudaStream_t st = static_cast<cudaStream_t>(stream);
-        const int ns = tc_nsplit(m, n, 1);
+        const int ns = tc_nsplit(m, n, d, 1);
         float* out = dx_hat;
         if (ns > 1) {
             Workspace ws(workspace, workspace_bytes);
@@ -136,7 +136,7 @@ int dclip_infonce_grad(const void* x_hat, int64_t m, const void* y_hat, int64_t 
 
 size_t dclip_infonce_grad_pair_workspace_bytes(int64_t B, int64_t d, int path) {
     if (path == DCLIP_PATH_TENSOR) {
-        const int ns = tc_nsplit(B, B, 2);
+        const int ns = tc_nsplit(B, B, d, 2);
         return ns > 1 ? align_up((size_t)2 * ns * B * d * sizeof(float), 256) + 256 : 256;
     }
     return 256;
@@ -162,7 +162,7 @@ int dclip_infonce_grad_pair(const void* u_hat, const void* v_hat, int64_t B, int
     DCLIP_REQUIRE(op_dtype == DCLIP_F16, "infonce_grad_pair: tensor path needs float16 operands");
     if (!tc_loss_shape_ok(d, temperature))
         return fail(DCLIP_ERR_UNSUPPORTED, "infonce_grad_pair: tensor path needs d %% 128 == 0, 128 <= d <= 768 and temperature >= 0.025 (d=%lld tau=%g)", (long long)d, temperature);
-    const int ns = tc_nsplit(B, B, 2);
+    const int ns = tc_nsplit(B, B, d, 2);
     float* du = du_hat;
     float* dv = dv_hat;
     if (ns > 1) {
@@ -216,13 +216,13 @@ int dclip_distill_loss_launch_count(int64_t m, int64_t n, int64_t d, int path, i
     path = resolve_loss_path(path, DCLIP_F32);
     if (path == DCLIP_PATH_FP32) return sharded ? 11 : 6;   // prep, rowlse+combine, sums, grad, tail (x2 sides when sharded)
     // tensor path: prep, fwd tiles, 2 lse combines, diag, sums, bwd tiles, (grad combine), 2 tails
-    if (!sharded) return 5 + (tc_nsplit(m, n, 2) > 1 ? 2 : 0);   // prep_pair, fwd tiles, finalize, bwd tiles, tail
-    return 2 + 2 * 3 + 1 + 2 * (1 + (tc_nsplit(m, n, 1) > 1 ? 1 : 0)) + 2;
+    if (!sharded) return 5 + (tc_nsplit(m, n, d, 2) > 1 ? 2 : 0);   // prep_pair, fwd tiles, finalize, bwd tiles, tail
+    return 2 + 2 * 3 + 1 + 2 * (1 + (tc_nsplit(m, n, d, 1) > 1 ? 1 : 0)) + 2;
 }
 
 // ---- fused per-rank phases of the sharded objective (tensor path) -----------------------------
 size_t dclip_sharded_loss_workspace_bytes(int64_t m, int64_t n, int64_t d) {
-    const int nf = stream_nsplit(m, n, 2), nb = tc_nsplit(m, n, 2);
+    const int nf = stream_nsplit(m, n, 2), nb = tc_nsplit(m, n, d, 2);
     size_t total = 2 * align_up((size_t)nf * m * 4, 256);                 // forward partial row sums (two sides)
     total += 2 * align_up((size_t)m * d * 4, 256);                        // du_hat, dv_hat
     if (nb > 1) total += align_up((size_t)2 * nb * m * d * 4, 256);       // backward partials
@@ -282,7 +282,7 @@ int dclip_sharded_loss_bwd(const void* s_img, const void* s_txt, const void* t_i
     const int64_t stride = 2 * m + 4;
     if (int e = launch_sharded_losses(stat_all, world, stride, 2 * m, n, t_img != nullptr, t_txt != nullptr, w_img, w_txt, w_con, losses, st)) return e;
     if (!d_s_img) return DCLIP_OK;
-    const int nb = tc_nsplit(m, n, 2);
+    const int nb = tc_nsplit(m, n, d, 2);
     Workspace ws(workspace, workspace_bytes);
     ws.take((size_t)stream_nsplit(m, n, 2) * m * 4); ws.take((size_t)stream_nsplit(m, n, 2) * m * 4);   // (forward partials: same carve)
     float* du_hat = static_cast<float*>(ws.take((size_t)m * d * 4));
@@ -325,7 +325,7 @@ size_t dclip_distill_loss_workspace_bytes(int64_t B, int64_t d, int path) {
     total += 4 * align_up((size_t)ns * B * 4, 256);         // partials
     total += 2 * align_up((size_t)B * d * 4, 256);          // dx_hat
     if (path == DCLIP_PATH_TENSOR) {
-        const int tns = tc_nsplit(B, B, 2), fns = stream_nsplit(B, B, 2);
+        const int tns = tc_nsplit(B, B, d, 2), fns = stream_nsplit(B, B, 2);
         total += 4 * align_up((size_t)fns * B * 4, 256);
         if (tns > 1) total += align_up((size_t)2 * tns * B * d * 4, 256);
     }
@@ -359,7 +359,7 @@ int dclip_distill_loss_fwd_bwd(const void* s_img, const void* s_txt, const void*
     for (auto& v : vec) v = static_cast<float*>(ws.take((size_t)B * 4));
     float *inv_u = vec[0], *inv_v = vec[1], *cos_img = vec[2], *cos_txt = vec[3], *lse_u = vec[4], *lse_v = vec[5], *diag = vec[6];
     const int ns = tensor ? stream_nsplit(B, B, 2) : simt_rowlse_nsplit(B, B, d);   // forward column splits
-    const int nsb = tensor ? tc_nsplit(B, B, 2) : 1;                                 // backward column splits
+    const int nsb = tensor ? tc_nsplit(B, B, d, 2) : 1;                                 // backward column splits
     if (ns == 0) return fail(DCLIP_ERR_UNSUPPORTED, "FP32 loss path supports d <= 1024 (got %lld)", (long long)d);
     float* part[4];
     for (auto& p : part) p = static_cast<float*>(ws.take((size_t)ns * B * 4));

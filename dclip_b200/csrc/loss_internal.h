@@ -65,7 +65,7 @@ struct TcArgs {
 
 
 bool tc_loss_shape_ok(int64_t d, float temperature);
-int tc_nsplit(int64_t m, int64_t n, int nsides);
+int tc_nsplit(int64_t m, int64_t n, int64_t d, int nsides);
 int launch_infonce_bwd_tc(int nsides, const void* const x[2], const void* const y[2], const TcArgs& args, int nsplit,
                           cudaStream_t st);
 int launch_tc_lse_combine(const float* part, int nsplit, int64_t m, float inv_tau, float* lse, cudaStream_t st);

@@ -26,6 +26,8 @@
 // Bound: shared-memory bandwidth — every 128x64x16 MMA re-reads 6 KB of operands and the TMA ring
 // writes another 4 KB per MMA, ~80 cycles at 128 B/clk against 32 cycles of math (ncu: tensor pipe
 // active 38 %, profiles/r1_ncu_full_loss_kernels.txt).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "loss_internal.h"
 #include "tcgen05.cuh"
@@ -351,7 +353,18 @@ bool tc_loss_shape_ok(int64_t d, float temperature) {
     return d % 128 == 0 && d >= 128 && d <= 768 && temperature >= 0.025f;
 }
 
-int tc_nsplit(int64_t m, int64_t n, int nsides) {
+// The CTA-pair kernel (loss_tc_pair.cu) serves every d that splits into 256-wide blocks; DCLIP_BWD_SINGLE=1
+// forces the single-CTA kernel above (A/B measurements, tests).
+bool tc_pair_shape_ok(int64_t d);
+int tc_pair_nsplit(int64_t m, int64_t n, int nsides);
+int launch_infonce_bwd_pair(int nsides, const void* const x[2], const void* const y[2], const TcArgs& args, int nsplit, cudaStream_t st);
+static bool use_pair_kernel(int64_t d) {
+    static const bool forced_single = [] { const char* e = getenv("DCLIP_BWD_SINGLE"); return e && e[0] == '1'; }();
+    return !forced_single && tc_pair_shape_ok(d);
+}
+
+int tc_nsplit(int64_t m, int64_t n, int64_t d, int nsides) {
+    if (use_pair_kernel(d)) return tc_pair_nsplit(m, n, nsides);
     const int64_t row_ctas = ceil_div(m, NI) * nsides;
     const int64_t ntiles = ceil_div(n, TJ);
     int64_t want = sm_count() / (row_ctas > 0 ? row_ctas : 1);
@@ -379,6 +392,7 @@ int* tc_error_flag() {   // one device int per device, lazily allocated, never f
 // x[side]: local rows [m, d] fp16; y[side]: all rows [n, d] fp16.  a.s[side].out = partial dx [nsplit][m][d].
 int launch_infonce_bwd_tc(int nsides, const void* const x[2], const void* const y[2], const TcArgs& args_in, int nsplit, cudaStream_t st) {
     if (!device_is_sm100()) return fail(DCLIP_ERR_ARCH, "tensor path needs an sm_100 device");
+    if (use_pair_kernel(args_in.d)) return launch_infonce_bwd_pair(nsides, x, y, args_in, nsplit, st);
     TcArgs a = args_in;
     CUtensorMap tmx[2], tmy[2];
     for (int s = 0; s < 2; ++s) {

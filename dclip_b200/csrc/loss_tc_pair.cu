@@ -1,0 +1,341 @@
+// Distillation objective — InfoNCE BACKWARD on CTA PAIRS (tcgen05 cta_group::2, sm_100a):
+//   dX_hat = coef/tau * G . Y_hat,  G = softmax_row + softmax_col - 2 I  recomputed tile by tile
+// (autograd backward of training/CLIP_image_distillation.py:545-560; SURVEY.md 8(a) "exact backward math").
+//
+// Why pairs.  The gradient accumulator dX^T[d x i] has to stay in TMEM for the whole walk over Y; with one
+// CTA (loss_tc.cu) its 512 columns hold d/128 blocks of only 64 i-columns, so every MMA is 128 x 64 x 16 and
+// re-reads 6 KB of shared-memory operands for 32 cycles of math (shared-memory bound, tensor pipe 38 %).
+// A pair has two TMEMs: each CTA keeps HALF of d (d/256 blocks of 128 lanes) for 128 i-columns, and every
+// MMA is a 256 x 128 x 16 cta_group::2 instruction: the same 6 KB of operand reads per CTA now feed 64
+// cycles of math, and the 128 X rows are split between the two shared memories (64 rows = 96 KB each).
+//
+// Per pair: 128 rows of X_hat (I block), walking 256-row tiles J of Y_hat:
+//   phase 1   S^T[256 j x 128 i] = Y_J . X_I^T     M = 256 (CTA c: its 128 j rows), N = 128 (CTA c: 64 i rows
+//             of X, resident), K = d.  CTA c receives S^T rows [128c, 128c + 128) in TMEM columns 384-511.
+//   epilogue  thread = one j (TMEM lane); g = p (a_i + b_j) - 2 [i == j], scaled by 2^13, fp16.  Columns
+//             i < 64 go to the LEADER's G tile, i >= 64 to the PEER's (st.shared::cluster): each CTA ends up
+//             with G^T[256 j x 64 i] = its half of the phase-2 B operand.
+//   phase 2   dX^T[256 d x 128 i] += Y_J^T[256 d x 256 j] . G^T   per 256-wide d block: M = 256 (CTA c: d
+//             columns [256 blk + 128c, +128) read MN-major from the TMA boxes), N = 128, K = 256 j.
+// TMEM per CTA: d/256 accumulators of 128 columns (<= 384) + one 128-column S buffer.
+// Warps: 0-2 TMA producers (one 32 KB ring slot each, both CTAs), 3 MMA issuer (leader only; both allocate
+// TMEM), 4-11 epilogue (lane quadrant = warp & 3, column half = (warp - 4) >> 2).
+// Barriers at identical offsets in both CTAs; `full`, `x_full`, `s_empty`, `g_full` are used in the leader's
+// copy only (TMA bytes of both CTAs and remote arrivals are credited there), `empty`, `s_full`, `g_empty`,
+// `acc_full` are signalled in both CTAs by multicast tcgen05.commit.
+#include "common.cuh"
+#include "loss_internal.h"
+#include "tcgen05.cuh"
+
+namespace dclip {
+using namespace tc;
+
+namespace pk {
+constexpr int NI = 128;                // X rows per pair (MMA N)
+constexpr int NH = 64;                 // X rows resident per CTA
+constexpr int TJ = 256;                // Y rows per tile
+constexpr int kSlots = 3;
+constexpr int kBoxBytes = 128 * 128;   // [128 rows x 64 fp16] = 16 KB
+constexpr int kSlotBytes = 2 * kBoxBytes;
+constexpr int kXBoxBytes = NH * 128;   // [64 rows x 64 fp16] = 8 KB
+constexpr int kGBytes = TJ * 128;      // G^T half: [256 j x 64 i] fp16 = 32 KB
+constexpr int kThreads = 384;
+constexpr int kEpiWarps = 8;
+constexpr int kSCol = 384;
+constexpr float kGScaleLog2 = 13.0f;   // G stored as fp16 * 2^13 (softmax sums <= 2 -> <= 16384)
+constexpr uint32_t kSpin = 1u << 24;
+}  // namespace pk
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(pk::kThreads, 1)
+k_infonce_bwd_pair(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CUtensorMap tmy0,
+                   const __grid_constant__ CUtensorMap tmx1, const __grid_constant__ CUtensorMap tmy1, const TcArgs a) {
+    using namespace pk;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int side = blockIdx.z;
+    const CUtensorMap* tmx = side ? &tmx1 : &tmx0;
+    const CUtensorMap* tmy = side ? &tmy1 : &tmy0;
+    const TcSide S = a.s[side];
+    const int d = (int)a.d;
+    const int nkb = d / 64;            // 64-column boxes along d
+    const int NS = d / 128;            // ring-slot jobs per phase (phase 1: 2 k-boxes each; phase 2: (d block, j half))
+
+    uint8_t* xs = smem;                                   // resident X half: nkb boxes of 8 KB
+    uint8_t* ring = xs + (size_t)nkb * kXBoxBytes;        // kSlots x 32 KB
+    uint8_t* gs = ring + kSlots * kSlotBytes;             // 32 KB
+    uint8_t* tail = gs + kGBytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(tail);   // [kSlots]  (leader)
+    uint64_t* empty = full + kSlots;                      // [kSlots]
+    uint64_t* x_full = empty + kSlots;                    // (leader)
+    uint64_t* s_full = x_full + 1;
+    uint64_t* s_empty = s_full + 1;                       // (leader) 16 warp arrivals
+    uint64_t* g_full = s_empty + 1;                       // (leader) 16 warp arrivals
+    uint64_t* g_empty = g_full + 1;
+    uint64_t* acc_full = g_empty + 1;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 1);
+    float* a_s = reinterpret_cast<float*>(tmem_ptr + 2);  // [NI] column factors 2^13 / rowsum_i
+
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+    const uint32_t cr = cluster_ctarank();
+    const int64_t row0 = (int64_t)(blockIdx.x >> 1) * NI;           // first X row of the pair
+    const int64_t ntiles = (a.n + TJ - 1) / TJ;
+    const int64_t t_begin = (int64_t)blockIdx.y * a.tiles_per_split;
+    const int64_t t_end = min(ntiles, t_begin + a.tiles_per_split);
+    const int T = (int)max((int64_t)0, t_end - t_begin);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kSlots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(x_full, 1);
+        mbar_init(s_full, 1); mbar_init(s_empty, 2 * kEpiWarps);
+        mbar_init(g_full, 2 * kEpiWarps); mbar_init(g_empty, 1);
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 3) tmem_alloc_pair(tmem_ptr, 512);
+    fence_before_thread_sync();
+    __syncthreads();
+    cluster_sync_all();                // peer barriers initialised, both TMEMs allocated
+    fence_after_thread_sync();
+    const uint32_t tmem = *tmem_ptr;
+    bool ok = true;
+
+    if (T > 0) {
+        if (warp < kSlots) {
+            // ===================== TMA producers (both CTAs): warp w owns ring slot w =====================
+            if (elect_one()) {
+                tma_prefetch_desc(tmy);
+                if (warp == 0) {
+                    tma_prefetch_desc(tmx);
+                    const uint32_t xbar = mapa_u32(smem_u32(x_full), 0);
+                    if (cr == 0) mbar_arrive_expect_tx(x_full, (uint32_t)(2 * nkb * kXBoxBytes));
+                    for (int kb = 0; kb < nkb; ++kb)
+                        tma_load_2d_pair(xs + (size_t)kb * kXBoxBytes, tmx, xbar, kb * 64, (int32_t)(row0 + cr * NH));
+                }
+                // Job q (MMA consumption order) uses slot q % kSlots.  Order: P1(0), then per tile t: P1(t+1) [if any], P2(t).
+                const int njobs = 2 * NS * T;
+                uint8_t* dst = ring + (size_t)warp * kSlotBytes;
+                const uint32_t fbar = mapa_u32(smem_u32(&full[warp]), 0);
+                uint32_t phase = 0;
+                for (int q = warp; q < njobs && ok; q += kSlots, phase ^= 1) {
+                    int tile, sidx, ph;
+                    if (q < NS) { tile = 0; sidx = q; ph = 1; }
+                    else {
+                        const int qq = q - NS, blk = min(qq / (2 * NS), T - 1), r = qq - blk * 2 * NS;
+                        if (blk < T - 1 && r < NS) { tile = blk + 1; sidx = r; ph = 1; }
+                        else { tile = blk; sidx = blk < T - 1 ? r - NS : r; ph = 2; }
+                    }
+                    const int32_t j0 = (int32_t)((t_begin + tile) * TJ);
+                    ok = mbar_wait_cluster(&empty[warp], phase ^ 1, kSpin);
+                    if (cr == 0) mbar_arrive_expect_tx(&full[warp], 2 * kSlotBytes);     // bytes of both CTAs
+                    if (ph == 1) {
+                        // K-major A: my 128 j rows, k boxes 2 sidx and 2 sidx + 1
+                        tma_load_2d_pair(dst, tmy, fbar, (2 * sidx) * 64, j0 + (int32_t)cr * 128);
+                        tma_load_2d_pair(dst + kBoxBytes, tmy, fbar, (2 * sidx + 1) * 64, j0 + (int32_t)cr * 128);
+                    } else {
+                        // MN-major A: d block sidx >> 1 (my 128 columns = two 64-wide boxes), j half sidx & 1
+                        const int32_t c0 = (sidx >> 1) * 256 + (int32_t)cr * 128, r0 = j0 + (sidx & 1) * 128;
+                        tma_load_2d_pair(dst, tmy, fbar, c0, r0);
+                        tma_load_2d_pair(dst + kBoxBytes, tmy, fbar, c0 + 64, r0);
+                    }
+                }
+            }
+        } else if (warp == 3) {
+            // ===================== MMA issuer (leader only) =====================
+            if (cr == 0 && elect_one()) {
+                const uint32_t idesc1 = make_idesc_f16(256, NI, kFmtF16, 0, 0);
+                const uint32_t idesc2 = make_idesc_f16(256, NI, kFmtF16, 1, 1);
+                const uint64_t hiK = make_smem_desc_hi(0, 1024, kSwizzle128B);
+                const uint64_t hiA2 = make_smem_desc_hi(kBoxBytes, 1024, kSwizzle128B);   // MN-major A: LBO = next 64-d group
+                const uint64_t hiB2 = make_smem_desc_hi(0, 1024, kSwizzle128B);           // MN-major B (G half), 64 i = one group
+                const uint32_t xs_addr = smem_u32(xs), ring_addr = smem_u32(ring), gs_addr = smem_u32(gs);
+                uint32_t stage = 0, sphase = 0;
+                ok = mbar_wait_cluster(x_full, 0, kSpin);
+                auto phase1 = [&](int t) {
+                    ok = ok && mbar_wait_cluster(s_empty, (t & 1) ^ 1, kSpin);
+                    fence_after_thread_sync();
+                    for (int s = 0; s < NS && ok; ++s) {
+                        ok = mbar_wait_cluster(&full[stage], sphase, kSpin);
+                        fence_after_thread_sync();
+                        const uint64_t da0 = smem_desc(hiK, ring_addr + stage * kSlotBytes);
+                        const uint64_t db0 = smem_desc(hiK, xs_addr + (2 * s) * kXBoxBytes);
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks)
+                                umma_f16_pair(tmem + kSCol, da0 + (uint64_t)(h * (kBoxBytes >> 4) + ks * 2),
+                                              db0 + (uint64_t)(h * (kXBoxBytes >> 4) + ks * 2), idesc1, (s | h | ks) != 0);
+                        umma_commit_pair(&empty[stage]);
+                        if (++stage == kSlots) { stage = 0; sphase ^= 1; }
+                    }
+                    umma_commit_pair(s_full);
+                };
+                auto phase2 = [&](int t) {
+                    ok = ok && mbar_wait_cluster(g_full, t & 1, kSpin);
+                    fence_proxy_async_all();
+                    fence_after_thread_sync();
+                    for (int s = 0; s < NS && ok; ++s) {
+                        ok = mbar_wait_cluster(&full[stage], sphase, kSpin);
+                        fence_after_thread_sync();
+                        const int jh = s & 1;
+                        const uint64_t da0 = smem_desc(hiA2, ring_addr + stage * kSlotBytes);
+                        const uint64_t db0 = smem_desc(hiB2, gs_addr + jh * (kGBytes / 2));
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks)          // 16 j per step = two 8-row groups = +2048 B
+                            umma_f16_pair(tmem + (s >> 1) * NI, da0 + (uint64_t)(ks * 128), db0 + (uint64_t)(ks * 128), idesc2, (t | jh | ks) != 0);
+                        umma_commit_pair(&empty[stage]);
+                        if (++stage == kSlots) { stage = 0; sphase ^= 1; }
+                    }
+                    umma_commit_pair(g_empty);
+                };
+                if (ok) phase1(0);
+                for (int t = 0; t < T && ok; ++t) {
+                    if (t + 1 < T) phase1(t + 1);
+                    if (ok) phase2(t);
+                }
+                umma_commit_pair(acc_full);
+            }
+        } else {
+            // ===================== epilogue warps (256 threads per CTA) =====================
+            const int q = warp & 3;                       // TMEM lane quadrant this warp may access
+            const int hh = (warp - 4) >> 2;               // column half: i in [64 hh, 64 hh + 64) -> G tile of CTA hh
+            const int et = q * 32 + lane;                 // j row inside my 128-row half == TMEM lane
+            const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+            const float c = a.inv_tau * 1.4426950408889634f;    // log2(e) / tau
+            {
+                const int idx = (warp - 4) * 32 + lane;
+                if (idx < NI) {
+                    const int64_t gi = row0 + idx;
+                    a_s[idx] = gi < a.m ? exp2f((a.inv_tau - S.lse_x[gi]) * 1.4426950408889634f + kGScaleLog2) : 0.f;
+                }
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const uint32_t s_empty_l = mapa_u32(smem_u32(s_empty), 0), g_full_l = mapa_u32(smem_u32(g_full), 0);
+            const uint32_t grow_local = smem_u32(gs) + (uint32_t)(cr * 128 + et) * 128;
+            const uint32_t grow_dst = mapa_u32(grow_local, (uint32_t)hh);
+            const bool local_dst = (uint32_t)hh == cr;
+            for (int t = 0; t < T; ++t) {
+                const int64_t j0 = (t_begin + t) * TJ;
+                const int64_t gj = j0 + cr * 128 + et;
+                ok = mbar_wait_cluster(s_full, t & 1, kSpin);
+                ok = __all_sync(0xffffffffu, ok);         // keep the .aligned TMEM loads warp-uniform
+                if (!ok) break;
+                fence_after_thread_sync();
+                uint32_t r[64];
+                tmem_ld_32x32b_x32(tmem + lane_addr + kSCol + hh * 64, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+                tmem_ld_32x32b_x32(tmem + lane_addr + kSCol + hh * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+                tmem_ld_wait();
+                fence_before_thread_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(s_empty_l);      // S may be overwritten by phase 1 of tile t+1
+                const bool jvalid = gj < a.n;
+                const int64_t ly = S.lse_y_block > 0 ? (gj / S.lse_y_block) * S.lse_y_stride + gj % S.lse_y_block : gj;
+                const float bj = jvalid ? exp2f((a.inv_tau - S.lse_y[ly]) * 1.4426950408889634f + kGScaleLog2) : 0.f;
+                const int64_t di = gj - a.row_offset - row0 - hh * 64;   // my column with global i == j, if in [0, 64)
+                uint32_t packed[32];
+#pragma unroll
+                for (int e2 = 0; e2 < 32; ++e2) {
+                    float g2[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int i = e2 * 2 + e;
+                        float g = 0.f;
+                        if (jvalid) {
+                            const float p = exp2f(fmaf(__uint_as_float(r[i]), c, -c));
+                            g = p * (a_s[hh * 64 + i] + bj);
+                            if (di == i) g -= 16384.0f;      // 2 * 2^13
+                        }
+                        g2[e] = g;
+                    }
+                    const __half2 hv = __floats2half2_rn(g2[0], g2[1]);
+                    packed[e2] = *reinterpret_cast<const uint32_t*>(&hv);
+                }
+                ok = mbar_wait_cluster(g_empty, (t & 1) ^ 1, kSpin);      // phase 2 of tile t-1 has read G
+                // 128B swizzle: 16-byte chunk ch of row r lands at chunk (ch ^ (r & 7)); (128 cr + et) & 7 == et & 7
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) {
+                    const uint4 v = make_uint4(packed[4 * ch], packed[4 * ch + 1], packed[4 * ch + 2], packed[4 * ch + 3]);
+                    const uint32_t off = (uint32_t)((ch ^ (et & 7)) << 4);
+                    if (local_dst) *reinterpret_cast<uint4*>(gs + (size_t)(cr * 128 + et) * 128 + off) = v;
+                    else st_shared_cluster_v4(grow_dst + off, v);
+                }
+                fence_proxy_async_all();                  // generic-proxy stores -> visible to the MMAs (async proxy) of both CTAs
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(g_full_l);
+            }
+            if (__all_sync(0xffffffffu, ok) && (ok = __all_sync(0xffffffffu, mbar_wait_cluster(acc_full, 0, kSpin)))) {
+                fence_after_thread_sync();
+                float* outp = S.out + (int64_t)blockIdx.y * a.m * a.d;
+                for (int s = 0; s < NS / 2; ++s) {
+                    uint32_t r0[32], r1[32];
+                    tmem_ld_32x32b_x32(tmem + lane_addr + s * NI + hh * 64, r0);
+                    tmem_ld_32x32b_x32(tmem + lane_addr + s * NI + hh * 64 + 32, r1);
+                    tmem_ld_wait();
+                    const int dcol = s * 256 + (int)cr * 128 + et;    // TMEM lane = d index inside my half of the block
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int64_t gi = row0 + hh * 64 + i;
+                        if (gi < a.m) outp[gi * a.d + dcol] = __uint_as_float(r0[i]) * a.out_scale;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int64_t gi = row0 + hh * 64 + 32 + i;
+                        if (gi < a.m) outp[gi * a.d + dcol] = __uint_as_float(r1[i]) * a.out_scale;
+                    }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // empty column range (only possible with an over-split grid): contribute zeros
+        const int et = (warp - 4) * 32 + lane;
+        float* outp = S.out + (int64_t)blockIdx.y * a.m * a.d;
+        for (int i = 0; i < NH; ++i) {
+            const int64_t gi = row0 + cr * NH + i;
+            if (gi < a.m)
+                for (int c2 = et; c2 < d; c2 += 256) outp[gi * a.d + c2] = 0.f;
+        }
+    }
+    if (!ok && lane == 0 && a.error_flag) atomicExch(a.error_flag, 1);
+    fence_before_thread_sync();
+    __syncthreads();
+    cluster_sync_all();                // no CTA leaves while its peer can still touch its shared memory / TMEM
+    if (warp == 3) tmem_dealloc_pair(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+bool tc_pair_shape_ok(int64_t d) { return d % 256 == 0 && d >= 256 && d <= 768; }
+
+int tc_pair_nsplit(int64_t m, int64_t n, int nsides) {
+    const int64_t pairs = ceil_div(m, pk::NI) * nsides;
+    const int64_t ntiles = ceil_div(n, pk::TJ);
+    int64_t want = (sm_count() / 2) / (pairs > 0 ? pairs : 1);
+    if (want < 1) want = 1;
+    if (want > ntiles) want = ntiles;
+    return (int)want;
+}
+
+int* tc_error_flag();   // loss_tc.cu
+
+int launch_infonce_bwd_pair(int nsides, const void* const x[2], const void* const y[2], const TcArgs& args_in, int nsplit, cudaStream_t st) {
+    using namespace pk;
+    TcArgs a = args_in;
+    CUtensorMap tmx[2], tmy[2];
+    for (int s = 0; s < 2; ++s) {
+        const int src = s < nsides ? s : 0;
+        if (!make_tmap_2d_sw128(&tmx[s], x[src], (uint64_t)a.m, (uint64_t)a.d, NH, 0) ||
+            !make_tmap_2d_sw128(&tmy[s], y[src], (uint64_t)a.n, (uint64_t)a.d, 128, 0))
+            return fail(DCLIP_ERR_CUDA, "cuTensorMapEncodeTiled failed (m=%lld n=%lld d=%lld)", (long long)a.m, (long long)a.n, (long long)a.d);
+    }
+    const int64_t ntiles = ceil_div(a.n, TJ);
+    a.tiles_per_split = (int)ceil_div(ntiles, nsplit);
+    a.error_flag = tc_error_flag();
+    const size_t smem = 1024 + (size_t)(a.d / 64) * kXBoxBytes + (size_t)kSlots * kSlotBytes + kGBytes + 1024;
+    dim3 grid((unsigned)(2 * ceil_div(a.m, NI)), (unsigned)nsplit, (unsigned)nsides);
+    DCLIP_CUDA_OK(cudaFuncSetAttribute(k_infonce_bwd_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_infonce_bwd_pair<<<grid, kThreads, smem, st>>>(tmx[0], tmy[0], tmx[1], tmy[1], a);
+    DCLIP_LAUNCH_OK("k_infonce_bwd_pair");
+    return DCLIP_OK;
+}
+
+}  // namespace dclip
