@@ -12,17 +12,20 @@
 // Per pair: 128 rows of X_hat (I block), walking 256-row tiles J of Y_hat:
 //   phase 1   S^T[256 j x 128 i] = Y_J . X_I^T     M = 256 (CTA c: its 128 j rows), N = 128 (CTA c: 64 i rows
 //             of X, resident), K = d.  CTA c receives S^T rows [128c, 128c + 128) in TMEM columns 384-511.
-//   epilogue  thread = one j (TMEM lane); g = p (a_i + b_j) - 2 [i == j], scaled by 2^13, fp16.  Columns
+//   epilogue  thread = one j (TMEM lane); g = p (a_i + b_j), scaled by 2^13, fp16.  (The -2 [i == j] term of G
+//             is one extra phase-2 step at the end: K = the 128 Y rows facing X_I, B = -2 * 2^13 I, exact.)  Columns
 //             i < 64 go to the LEADER's G tile, i >= 64 to the PEER's (st.shared::cluster): each CTA ends up
 //             with G^T[256 j x 64 i] = its half of the phase-2 B operand.
 //   phase 2   dX^T[256 d x 128 i] += Y_J^T[256 d x 256 j] . G^T   per 256-wide d block: M = 256 (CTA c: d
 //             columns [256 blk + 128c, +128) read MN-major from the TMA boxes), N = 128, K = 256 j.
 // TMEM per CTA: d/256 accumulators of 128 columns (<= 384) + one 128-column S buffer.
 // Warps: 0-2 TMA producers (one 32 KB ring slot each, both CTAs), 3 MMA issuer (leader only; both allocate
-// TMEM), 4-11 epilogue (lane quadrant = warp & 3, column half = (warp - 4) >> 2).
+// TMEM), 4-11 epilogue (lane quadrant = warp & 3, column half = (warp - (kSlots + 1)) >> 2).
 // Barriers at identical offsets in both CTAs; `full`, `x_full`, `s_empty`, `g_full` are used in the leader's
 // copy only (TMA bytes of both CTAs and remote arrivals are credited there), `empty`, `s_full`, `g_empty`,
 // `acc_full` are signalled in both CTAs by multicast tcgen05.commit.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "loss_internal.h"
 #include "tcgen05.cuh"
@@ -30,23 +33,45 @@
 namespace dclip {
 using namespace tc;
 
+// Optional stall accounting (build with -DDCLIP_PAIR_PROF): cycles the roles of cluster 0 spend in each wait.
+#ifdef DCLIP_PAIR_PROF
+__device__ unsigned long long g_pair_prof[32];
+#define PROF_ON (blockIdx.x < 2 && blockIdx.y == 0 && blockIdx.z == 0)
+#define PROF_BEGIN(v) const long long v = clock64()
+#define PROF_END(v, slot) do { if (PROF_ON) atomicAdd(&g_pair_prof[slot], (unsigned long long)(clock64() - v)); } while (0)
+#else
+#define PROF_BEGIN(v) do { } while (0)
+#define PROF_END(v, slot) do { } while (0)
+#endif
+
 namespace pk {
 constexpr int NI = 128;                // X rows per pair (MMA N)
 constexpr int NH = 64;                 // X rows resident per CTA
 constexpr int TJ = 256;                // Y rows per tile
-constexpr int kSlots = 3;
 constexpr int kBoxBytes = 128 * 128;   // [128 rows x 64 fp16] = 16 KB
 constexpr int kSlotBytes = 2 * kBoxBytes;
 constexpr int kXBoxBytes = NH * 128;   // [64 rows x 64 fp16] = 8 KB
 constexpr int kGBytes = TJ * 128;      // G^T half: [256 j x 64 i] fp16 = 32 KB
-constexpr int kThreads = 384;
 constexpr int kEpiWarps = 8;
 constexpr int kSCol = 384;
 constexpr float kGScaleLog2 = 13.0f;   // G stored as fp16 * 2^13 (softmax sums <= 2 -> <= 16384)
 constexpr uint32_t kSpin = 1u << 24;
 }  // namespace pk
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(pk::kThreads, 1)
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+// exponent arguments stay inside [-2 log2e / tau, 0] (tau >= 0.025): no denormal handling needed
+__device__ __forceinline__ float ex2_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <int kSlots>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((kSlots + 9) * 32, 1)
 k_infonce_bwd_pair(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CUtensorMap tmy0,
                    const __grid_constant__ CUtensorMap tmx1, const __grid_constant__ CUtensorMap tmy1, const TcArgs a) {
     using namespace pk;
@@ -73,7 +98,7 @@ k_infonce_bwd_pair(const __grid_constant__ CUtensorMap tmx0, const __grid_consta
     uint64_t* g_empty = g_full + 1;
     uint64_t* acc_full = g_empty + 1;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 1);
-    float* a_s = reinterpret_cast<float*>(tmem_ptr + 2);  // [NI] column factors 2^13 / rowsum_i
+    float* a_s = reinterpret_cast<float*>(tail + 256);    // [NI] column factors 2^13 / rowsum_i (16-byte aligned: read as float4)
 
     const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const uint32_t cr = cluster_ctarank();
@@ -82,7 +107,9 @@ k_infonce_bwd_pair(const __grid_constant__ CUtensorMap tmx0, const __grid_consta
     const int64_t t_begin = (int64_t)blockIdx.y * a.tiles_per_split;
     const int64_t t_end = min(ntiles, t_begin + a.tiles_per_split);
     const int T = (int)max((int64_t)0, t_end - t_begin);
+    const bool diag = blockIdx.y == 0;                    // the -2 I term of G is applied once, by column split 0
 
+    PROF_BEGIN(p_kernel);
     if (threadIdx.x == 0) {
         for (int i = 0; i < kSlots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         mbar_init(x_full, 1);
@@ -91,13 +118,14 @@ k_infonce_bwd_pair(const __grid_constant__ CUtensorMap tmx0, const __grid_consta
         mbar_init(acc_full, 1);
         fence_barrier_init();
     }
-    if (warp == 3) tmem_alloc_pair(tmem_ptr, 512);
+    if (warp == kSlots) tmem_alloc_pair(tmem_ptr, 512);
     fence_before_thread_sync();
     __syncthreads();
     cluster_sync_all();                // peer barriers initialised, both TMEMs allocated
     fence_after_thread_sync();
     const uint32_t tmem = *tmem_ptr;
     bool ok = true;
+    if (threadIdx.x == 0) PROF_END(p_kernel, 28);
 
     if (T > 0) {
         if (warp < kSlots) {
@@ -113,33 +141,40 @@ k_infonce_bwd_pair(const __grid_constant__ CUtensorMap tmx0, const __grid_consta
                 }
                 // Job q (MMA consumption order) uses slot q % kSlots.  Order: P1(0), then per tile t: P1(t+1) [if any], P2(t).
                 const int njobs = 2 * NS * T;
+                const int ndiag = diag ? NS / 2 : 0;          // extra P2-style jobs of the diagonal step (one per d block)
                 uint8_t* dst = ring + (size_t)warp * kSlotBytes;
                 const uint32_t fbar = mapa_u32(smem_u32(&full[warp]), 0);
                 uint32_t phase = 0;
-                for (int q = warp; q < njobs && ok; q += kSlots, phase ^= 1) {
-                    int tile, sidx, ph;
-                    if (q < NS) { tile = 0; sidx = q; ph = 1; }
+                for (int q = warp; q < njobs + ndiag && ok; q += kSlots, phase ^= 1) {
+                    int tile = 0, sidx = 0, ph;
+                    if (q >= njobs) { sidx = q - njobs; ph = 3; }
+                    else if (q < NS) { tile = 0; sidx = q; ph = 1; }
                     else {
                         const int qq = q - NS, blk = min(qq / (2 * NS), T - 1), r = qq - blk * 2 * NS;
                         if (blk < T - 1 && r < NS) { tile = blk + 1; sidx = r; ph = 1; }
                         else { tile = blk; sidx = blk < T - 1 ? r - NS : r; ph = 2; }
                     }
                     const int32_t j0 = (int32_t)((t_begin + tile) * TJ);
+                    PROF_BEGIN(p_em);
                     ok = mbar_wait_cluster(&empty[warp], phase ^ 1, kSpin);
+                    PROF_END(p_em, 6 + (int)cr);
                     if (cr == 0) mbar_arrive_expect_tx(&full[warp], 2 * kSlotBytes);     // bytes of both CTAs
                     if (ph == 1) {
                         // K-major A: my 128 j rows, k boxes 2 sidx and 2 sidx + 1
                         tma_load_2d_pair(dst, tmy, fbar, (2 * sidx) * 64, j0 + (int32_t)cr * 128);
                         tma_load_2d_pair(dst + kBoxBytes, tmy, fbar, (2 * sidx + 1) * 64, j0 + (int32_t)cr * 128);
                     } else {
-                        // MN-major A: d block sidx >> 1 (my 128 columns = two 64-wide boxes), j half sidx & 1
-                        const int32_t c0 = (sidx >> 1) * 256 + (int32_t)cr * 128, r0 = j0 + (sidx & 1) * 128;
+                        // MN-major A: my 128 columns of a d block (two 64-wide boxes); phase 2: block sidx >> 1, j half
+                        // sidx & 1; diagonal step: block sidx, the 128 Y rows facing the pair's X rows
+                        const int blk = ph == 2 ? sidx >> 1 : sidx;
+                        const int32_t c0 = blk * 256 + (int32_t)cr * 128;
+                        const int32_t r0 = ph == 2 ? j0 + (sidx & 1) * 128 : (int32_t)(a.row_offset + row0);
                         tma_load_2d_pair(dst, tmy, fbar, c0, r0);
                         tma_load_2d_pair(dst + kBoxBytes, tmy, fbar, c0 + 64, r0);
                     }
                 }
             }
-        } else if (warp == 3) {
+        } else if (warp == kSlots) {
             // ===================== MMA issuer (leader only) =====================
             if (cr == 0 && elect_one()) {
                 const uint32_t idesc1 = make_idesc_f16(256, NI, kFmtF16, 0, 0);
@@ -149,12 +184,18 @@ k_infonce_bwd_pair(const __grid_constant__ CUtensorMap tmx0, const __grid_consta
                 const uint64_t hiB2 = make_smem_desc_hi(0, 1024, kSwizzle128B);           // MN-major B (G half), 64 i = one group
                 const uint32_t xs_addr = smem_u32(xs), ring_addr = smem_u32(ring), gs_addr = smem_u32(gs);
                 uint32_t stage = 0, sphase = 0;
+                PROF_BEGIN(p_all);
                 ok = mbar_wait_cluster(x_full, 0, kSpin);
+                PROF_END(p_all, 1);
                 auto phase1 = [&](int t) {
+                    PROF_BEGIN(p_se);
                     ok = ok && mbar_wait_cluster(s_empty, (t & 1) ^ 1, kSpin);
+                    PROF_END(p_se, 2);
                     fence_after_thread_sync();
                     for (int s = 0; s < NS && ok; ++s) {
+                        PROF_BEGIN(p_f1);
                         ok = mbar_wait_cluster(&full[stage], sphase, kSpin);
+                        PROF_END(p_f1, 3);
                         fence_after_thread_sync();
                         const uint64_t da0 = smem_desc(hiK, ring_addr + stage * kSlotBytes);
                         const uint64_t db0 = smem_desc(hiK, xs_addr + (2 * s) * kXBoxBytes);
@@ -170,11 +211,15 @@ k_infonce_bwd_pair(const __grid_constant__ CUtensorMap tmx0, const __grid_consta
                     umma_commit_pair(s_full);
                 };
                 auto phase2 = [&](int t) {
+                    PROF_BEGIN(p_gf);
                     ok = ok && mbar_wait_cluster(g_full, t & 1, kSpin);
+                    PROF_END(p_gf, 4);
                     fence_proxy_async_all();
                     fence_after_thread_sync();
                     for (int s = 0; s < NS && ok; ++s) {
+                        PROF_BEGIN(p_f2);
                         ok = mbar_wait_cluster(&full[stage], sphase, kSpin);
+                        PROF_END(p_f2, 5);
                         fence_after_thread_sync();
                         const int jh = s & 1;
                         const uint64_t da0 = smem_desc(hiA2, ring_addr + stage * kSlotBytes);
@@ -192,17 +237,35 @@ k_infonce_bwd_pair(const __grid_constant__ CUtensorMap tmx0, const __grid_consta
                     if (t + 1 < T) phase1(t + 1);
                     if (ok) phase2(t);
                 }
+                if (diag && ok) {
+                    // diagonal step: dX^T[256 d x 128 i] += Y_D^T[256 d x 128 j'] . (-2 * 2^13 I), Y_D = the Y rows facing X_I
+                    ok = mbar_wait_cluster(g_full, T & 1, kSpin);
+                    fence_proxy_async_all();
+                    fence_after_thread_sync();
+                    for (int s = 0; s < NS / 2 && ok; ++s) {
+                        ok = mbar_wait_cluster(&full[stage], sphase, kSpin);
+                        fence_after_thread_sync();
+                        const uint64_t da0 = smem_desc(hiA2, ring_addr + stage * kSlotBytes);
+                        const uint64_t db0 = smem_desc(hiB2, gs_addr);
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks)
+                            umma_f16_pair(tmem + s * NI, da0 + (uint64_t)(ks * 128), db0 + (uint64_t)(ks * 128), idesc2, 1);
+                        umma_commit_pair(&empty[stage]);
+                        if (++stage == kSlots) { stage = 0; sphase ^= 1; }
+                    }
+                }
                 umma_commit_pair(acc_full);
+                PROF_END(p_all, 0);
             }
         } else {
             // ===================== epilogue warps (256 threads per CTA) =====================
             const int q = warp & 3;                       // TMEM lane quadrant this warp may access
-            const int hh = (warp - 4) >> 2;               // column half: i in [64 hh, 64 hh + 64) -> G tile of CTA hh
+            const int hh = (warp - (kSlots + 1)) >> 2;               // column half: i in [64 hh, 64 hh + 64) -> G tile of CTA hh
             const int et = q * 32 + lane;                 // j row inside my 128-row half == TMEM lane
             const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
             const float c = a.inv_tau * 1.4426950408889634f;    // log2(e) / tau
             {
-                const int idx = (warp - 4) * 32 + lane;
+                const int idx = (warp - (kSlots + 1)) * 32 + lane;
                 if (idx < NI) {
                     const int64_t gi = row0 + idx;
                     a_s[idx] = gi < a.m ? exp2f((a.inv_tau - S.lse_x[gi]) * 1.4426950408889634f + kGScaleLog2) : 0.f;
@@ -213,13 +276,17 @@ k_infonce_bwd_pair(const __grid_constant__ CUtensorMap tmx0, const __grid_consta
             const uint32_t grow_local = smem_u32(gs) + (uint32_t)(cr * 128 + et) * 128;
             const uint32_t grow_dst = mapa_u32(grow_local, (uint32_t)hh);
             const bool local_dst = (uint32_t)hh == cr;
+            const uint32_t a_addr = smem_u32(a_s) + (uint32_t)hh * 256;
             for (int t = 0; t < T; ++t) {
                 const int64_t j0 = (t_begin + t) * TJ;
                 const int64_t gj = j0 + cr * 128 + et;
+                PROF_BEGIN(p_sf);
                 ok = mbar_wait_cluster(s_full, t & 1, kSpin);
+                if (q == 0 && lane == 0) PROF_END(p_sf, 8 + 5 * ((int)cr * 2 + hh));
                 ok = __all_sync(0xffffffffu, ok);         // keep the .aligned TMEM loads warp-uniform
                 if (!ok) break;
                 fence_after_thread_sync();
+                PROF_BEGIN(p_ld);
                 uint32_t r[64];
                 tmem_ld_32x32b_x32(tmem + lane_addr + kSCol + hh * 64, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
                 tmem_ld_32x32b_x32(tmem + lane_addr + kSCol + hh * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
@@ -227,29 +294,31 @@ k_infonce_bwd_pair(const __grid_constant__ CUtensorMap tmx0, const __grid_consta
                 fence_before_thread_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(s_empty_l);      // S may be overwritten by phase 1 of tile t+1
+                if (q == 0 && lane == 0) PROF_END(p_ld, 9 + 5 * ((int)cr * 2 + hh));
+                PROF_BEGIN(p_cp);
                 const bool jvalid = gj < a.n;
                 const int64_t ly = S.lse_y_block > 0 ? (gj / S.lse_y_block) * S.lse_y_stride + gj % S.lse_y_block : gj;
                 const float bj = jvalid ? exp2f((a.inv_tau - S.lse_y[ly]) * 1.4426950408889634f + kGScaleLog2) : 0.f;
-                const int64_t di = gj - a.row_offset - row0 - hh * 64;   // my column with global i == j, if in [0, 64)
+                const float vm = jvalid ? 1.f : 0.f;      // rows past n: TMA zero-filled S, coefficient forced to 0
+                // g = p (a_i + b_j); the -2 [i == j] term of G is applied to the accumulator in the final drain
                 uint32_t packed[32];
 #pragma unroll
-                for (int e2 = 0; e2 < 32; ++e2) {
-                    float g2[2];
+                for (int ch = 0; ch < 8; ++ch) {
+                    const float4 a0 = lds_f4(a_addr + ch * 32), a1 = lds_f4(a_addr + ch * 32 + 16);
+                    const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int i = e2 * 2 + e;
-                        float g = 0.f;
-                        if (jvalid) {
-                            const float p = exp2f(fmaf(__uint_as_float(r[i]), c, -c));
-                            g = p * (a_s[hh * 64 + i] + bj);
-                            if (di == i) g -= 16384.0f;      // 2 * 2^13
-                        }
-                        g2[e] = g;
+                    for (int h = 0; h < 4; ++h) {
+                        const float p0 = ex2_ftz(fmaf(__uint_as_float(r[ch * 8 + 2 * h]), c, -c));
+                        const float p1 = ex2_ftz(fmaf(__uint_as_float(r[ch * 8 + 2 * h + 1]), c, -c));
+                        const __half2 hv = __floats2half2_rn(p0 * fmaf(av[2 * h], vm, bj), p1 * fmaf(av[2 * h + 1], vm, bj));
+                        packed[ch * 4 + h] = *reinterpret_cast<const uint32_t*>(&hv);
                     }
-                    const __half2 hv = __floats2half2_rn(g2[0], g2[1]);
-                    packed[e2] = *reinterpret_cast<const uint32_t*>(&hv);
                 }
+                if (q == 0 && lane == 0) PROF_END(p_cp, 10 + 5 * ((int)cr * 2 + hh));
+                PROF_BEGIN(p_ge);
                 ok = mbar_wait_cluster(g_empty, (t & 1) ^ 1, kSpin);      // phase 2 of tile t-1 has read G
+                if (q == 0 && lane == 0) PROF_END(p_ge, 11 + 5 * ((int)cr * 2 + hh));
+                PROF_BEGIN(p_st);
                 // 128B swizzle: 16-byte chunk ch of row r lands at chunk (ch ^ (r & 7)); (128 cr + et) & 7 == et & 7
 #pragma unroll
                 for (int ch = 0; ch < 8; ++ch) {
@@ -258,35 +327,53 @@ k_infonce_bwd_pair(const __grid_constant__ CUtensorMap tmx0, const __grid_consta
                     if (local_dst) *reinterpret_cast<uint4*>(gs + (size_t)(cr * 128 + et) * 128 + off) = v;
                     else st_shared_cluster_v4(grow_dst + off, v);
                 }
-                fence_proxy_async_all();                  // generic-proxy stores -> visible to the MMAs (async proxy) of both CTAs
+                if (q == 0 && lane == 0) PROF_END(p_st, 12 + 5 * ((int)cr * 2 + hh));
+                PROF_BEGIN(p_fe);
+                fence_proxy_async_smem_cluster();         // generic-proxy stores -> visible to the MMAs (async proxy) of both CTAs
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(g_full_l);
+                if (q == 0 && lane == 0 && cr == 0) PROF_END(p_fe, 30 + hh);
+            }
+            if (diag && __all_sync(0xffffffffu, ok)) {
+                // my own B half of the diagonal step: G^T[128 j' x 64 i] = -2 * 2^13 [j' == 64 cr + i]  (fp16 0xF400 = -16384)
+                ok = mbar_wait_cluster(g_empty, (T & 1) ^ 1, kSpin);
+                const int e = (warp - (kSlots + 1)) * 32 + lane;      // 0..255: row e >> 1, chunks 4 (e & 1) .. +3
+                const int jr = e >> 1, il = jr - (int)cr * NH;          // the one non-zero column of row jr, if in [0, 64)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int ch = (e & 1) * 4 + k, pos = il - ch * 8;   // element position inside the 8-wide chunk
+                    uint32_t w[4] = {0u, 0u, 0u, 0u};
+                    if (pos >= 0 && pos < 8) w[pos >> 1] = (pos & 1) ? 0xF4000000u : 0x0000F400u;
+                    *reinterpret_cast<uint4*>(gs + (size_t)jr * 128 + ((ch ^ (jr & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+                fence_proxy_async_all();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(g_full_l);
             }
             if (__all_sync(0xffffffffu, ok) && (ok = __all_sync(0xffffffffu, mbar_wait_cluster(acc_full, 0, kSpin)))) {
                 fence_after_thread_sync();
+                PROF_BEGIN(p_dr);
                 float* outp = S.out + (int64_t)blockIdx.y * a.m * a.d;
                 for (int s = 0; s < NS / 2; ++s) {
-                    uint32_t r0[32], r1[32];
-                    tmem_ld_32x32b_x32(tmem + lane_addr + s * NI + hh * 64, r0);
-                    tmem_ld_32x32b_x32(tmem + lane_addr + s * NI + hh * 64 + 32, r1);
-                    tmem_ld_wait();
                     const int dcol = s * 256 + (int)cr * 128 + et;    // TMEM lane = d index inside my half of the block
+                    float* op = outp + (row0 + hh * 64) * a.d + dcol;
+                    const int rows_left = (int)min((int64_t)64, a.m - row0 - hh * 64);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int64_t gi = row0 + hh * 64 + i;
-                        if (gi < a.m) outp[gi * a.d + dcol] = __uint_as_float(r0[i]) * a.out_scale;
-                    }
+                    for (int h = 0; h < 2; ++h) {
+                        uint32_t rr[32];
+                        tmem_ld_32x32b_x32(tmem + lane_addr + s * NI + hh * 64 + h * 32, rr);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int64_t gi = row0 + hh * 64 + 32 + i;
-                        if (gi < a.m) outp[gi * a.d + dcol] = __uint_as_float(r1[i]) * a.out_scale;
+                        for (int i = 0; i < 32; ++i)
+                            if (h * 32 + i < rows_left) op[(size_t)(h * 32 + i) * d] = __uint_as_float(rr[i]) * a.out_scale;
                     }
                 }
+                if (q == 0 && lane == 0 && hh == 0) PROF_END(p_dr, 29);
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp >= kSlots + 1) {
         // empty column range (only possible with an over-split grid): contribute zeros
-        const int et = (warp - 4) * 32 + lane;
+        const int et = (warp - (kSlots + 1)) * 32 + lane;
         float* outp = S.out + (int64_t)blockIdx.y * a.m * a.d;
         for (int i = 0; i < NH; ++i) {
             const int64_t gi = row0 + cr * NH + i;
@@ -298,7 +385,8 @@ k_infonce_bwd_pair(const __grid_constant__ CUtensorMap tmx0, const __grid_consta
     fence_before_thread_sync();
     __syncthreads();
     cluster_sync_all();                // no CTA leaves while its peer can still touch its shared memory / TMEM
-    if (warp == 3) tmem_dealloc_pair(tmem, 512);
+    if (threadIdx.x == 0 && cr == 1) PROF_END(p_kernel, 27);
+    if (warp == kSlots) tmem_dealloc_pair(tmem, 512);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -330,12 +418,31 @@ int launch_infonce_bwd_pair(int nsides, const void* const x[2], const void* cons
     const int64_t ntiles = ceil_div(a.n, TJ);
     a.tiles_per_split = (int)ceil_div(ntiles, nsplit);
     a.error_flag = tc_error_flag();
-    const size_t smem = 1024 + (size_t)(a.d / 64) * kXBoxBytes + (size_t)kSlots * kSlotBytes + kGBytes + 1024;
+    // ring depth: as many 32 KB slots as fit next to the resident X half and the G tile (3 at d = 768, 4 at d = 512)
+    static const int forced_slots = [] { const char* e = getenv("DCLIP_PAIR_SLOTS"); return e ? atoi(e) : 0; }();
+    const size_t fixed = 1024 + (size_t)(a.d / 64) * kXBoxBytes + kGBytes + 1024;
+    int slots = (int)((232448 - fixed) / kSlotBytes);
+    if (slots > 4) slots = 4;
+    if (forced_slots >= 2 && forced_slots <= slots) slots = forced_slots;
+    const size_t smem = fixed + (size_t)slots * kSlotBytes;
     dim3 grid((unsigned)(2 * ceil_div(a.m, NI)), (unsigned)nsplit, (unsigned)nsides);
-    DCLIP_CUDA_OK(cudaFuncSetAttribute(k_infonce_bwd_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_infonce_bwd_pair<<<grid, kThreads, smem, st>>>(tmx[0], tmy[0], tmx[1], tmy[1], a);
+    auto kern = slots == 4 ? k_infonce_bwd_pair<4> : slots == 3 ? k_infonce_bwd_pair<3> : k_infonce_bwd_pair<2>;
+    DCLIP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, (slots + 9) * 32, smem, st>>>(tmx[0], tmy[0], tmx[1], tmy[1], a);
     DCLIP_LAUNCH_OK("k_infonce_bwd_pair");
     return DCLIP_OK;
 }
 
 }  // namespace dclip
+
+#ifdef DCLIP_PAIR_PROF
+extern "C" int dclip_debug_pair_prof(unsigned long long* out32, int reset) {
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(out32, dclip::g_pair_prof, 32 * sizeof(unsigned long long)) != cudaSuccess) return -1;
+    if (reset) {
+        unsigned long long z[32] = {0};
+        cudaMemcpyToSymbol(dclip::g_pair_prof, z, sizeof(z));
+    }
+    return 0;
+}
+#endif

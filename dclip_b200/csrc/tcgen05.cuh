@@ -175,6 +175,8 @@ __device__ __forceinline__ bool mbar_wait_cluster(uint64_t* bar, uint32_t parity
     return false;
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// generic-proxy writes to shared memory of ANY CTA of the cluster -> visible to the async proxy (UMMA / TMA)
+__device__ __forceinline__ void fence_proxy_async_smem_cluster() { asm volatile("fence.proxy.async.shared::cluster;" ::: "memory"); }
 __device__ __forceinline__ void st_shared_cluster_v4(uint32_t cluster_addr, uint4 v) {
     asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
