@@ -328,6 +328,8 @@ size_t dclip_distill_loss_workspace_bytes(int64_t B, int64_t d, int path) {
         const int tns = tc_nsplit(B, B, d, 2), fns = stream_nsplit(B, B, 2);
         total += 4 * align_up((size_t)fns * B * 4, 256);
         if (tns > 1) total += align_up((size_t)2 * tns * B * d * 4, 256);
+        // one-pass forward: row partials [stream_nsplit(1 side)][B] + column partials [ceil(B / 128)][B]
+        total += align_up((size_t)stream_nsplit(B, B, 1) * B * 4, 256) + align_up((size_t)ceil_div(B, 128) * B * 4, 256);
     }
     return total + 1024;
 }
@@ -371,6 +373,11 @@ int dclip_distill_loss_fwd_bwd(const void* s_img, const void* s_txt, const void*
         du_part = static_cast<float*>(ws.take((size_t)2 * nsb * B * d * 4));   // [side][split][B][d], sides contiguous
         dv_part = du_part + (size_t)nsb * B * d;
     }
+    // tensor path forward: ONE pass over S gives the row sums (lse_u) and the column sums (lse_v)
+    const int ns1 = tensor ? stream_nsplit(B, B, 1) : 0;
+    const int nib = (int)ceil_div(B, 128);
+    float* rowpart = tensor ? static_cast<float*>(ws.take((size_t)ns1 * B * 4)) : nullptr;
+    float* colpart = tensor ? static_cast<float*>(ws.take((size_t)nib * B * 4)) : nullptr;
     if (!ws.ok()) return fail(DCLIP_ERR_WORKSPACE, "distill_loss: workspace too small (%zu < %zu)", workspace_bytes, ws.used);
     if (stats) { lse_u = stats; lse_v = stats + B; }
 
@@ -389,12 +396,13 @@ int dclip_distill_loss_fwd_bwd(const void* s_img, const void* s_txt, const void*
     const void* ys2[2] = {v_hat, u_hat};
     if (tensor) {
         TcArgs fa{};
-        fa.s[0] = TcSide{nullptr, nullptr, part[0]};
-        fa.s[1] = TcSide{nullptr, nullptr, part[2]};
+        fa.s[0] = TcSide{nullptr, nullptr, rowpart};
+        fa.col_out = colpart;
         fa.m = B; fa.n = B; fa.d = d; fa.inv_tau = 1.0f / temperature; fa.row_offset = 0;
-        if (int e = launch_stream_tc(0, 2, xs2, ys2, fa, ns, st)) return e;
-        FinalizeArgs fz{part[0], part[2], ns, B, fa.inv_tau, lse_u, lse_v,
-                        SumsArgs{lse_u, lse_v, diag, t_img ? cos_img : nullptr, t_txt ? cos_txt : nullptr, B, nullptr, losses, w_img, w_txt, w_con}};
+        if (int e = launch_stream_tc(1, 1, xs2, ys2, fa, ns1, st)) return e;
+        FinalizeArgs fz{rowpart, colpart, ns1, B, fa.inv_tau, lse_u, lse_v,
+                        SumsArgs{lse_u, lse_v, diag, t_img ? cos_img : nullptr, t_txt ? cos_txt : nullptr, B, nullptr, losses, w_img, w_txt, w_con},
+                        nib};
         if (int e = launch_tc_finalize(fz, st)) return e;
     } else {
         LseArgs la{};

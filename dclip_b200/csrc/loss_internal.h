@@ -61,6 +61,7 @@ struct TcArgs {
     int* error_flag;      // set to 1 on a pipeline timeout
     float* cand_s;        // retrieval mode: [nsplit][m][32] approximate scores (descending)
     int32_t* cand_i;      //                 [nsplit][m][32] gallery rows (-1 = empty)
+    float* col_out;       // stream mode 1: partial column sums [ceil(m / 128)][n]
 };
 
 
@@ -87,6 +88,7 @@ int launch_loss_prep_pair(const PrepArgs& a, int dtype, int op_dtype, cudaStream
 struct FinalizeArgs {
     const float* part_u; const float* part_v; int nsplit; int64_t m; float inv_tau;
     float* lse_u; float* lse_v; SumsArgs sums;
+    int nsplit_v;         // partial count of part_v when it differs from part_u's (0 = nsplit): column-sum partials
 };
 int launch_tc_finalize(const FinalizeArgs& a, cudaStream_t st);
 // global losses {total, img, txt, con} from the all-gathered per-rank raw sums stat[r * stride + off + 0..2]

@@ -12,6 +12,7 @@
 // shared loads conflict-free.  Grid: (row tiles, column splits, sides).
 #include "common.cuh"
 #include "loss_internal.h"
+#include "tcgen05.cuh"
 
 namespace dclip {
 
@@ -164,14 +165,24 @@ __global__ void __launch_bounds__(kThreads) k_loss_prep_pair(PrepArgs a) {
     if (lane == 0 && a.diag) a.diag[row] = dot * a.inv_tau;
 }
 
-// tensor path finalize: both lse vectors from the partial row sums + the loss sums (single CTA)
-__global__ void __launch_bounds__(1024) k_tc_finalize(FinalizeArgs f) {
-    __shared__ float red[3][1024];
+// tensor path finalize: both lse vectors from the partial sums + the loss sums.  One cluster of 8 CTAs (a
+// single CTA spends its time on load latency); every reduction runs in a fixed order, so the result is
+// bit-reproducible: thread -> rows i = g, g + 4096, ...; CTA tree; then cluster rank 0 adds the 8 CTA sums
+// it received through distributed shared memory in rank order.
+constexpr int kFinCtas = 8, kFinThreads = 512;
+__global__ void __cluster_dims__(kFinCtas, 1, 1) __launch_bounds__(kFinThreads) k_tc_finalize(FinalizeArgs f) {
+    __shared__ float red[3][kFinThreads];
+    __shared__ float gather[kFinCtas][4];
     const SumsArgs& a = f.sums;
+    const uint32_t rank = tc::cluster_ctarank();
+    const int nsv = f.nsplit_v > 0 ? f.nsplit_v : f.nsplit;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-    for (int64_t i = threadIdx.x; i < f.m; i += 1024) {
+    for (int64_t i = (int64_t)rank * kFinThreads + threadIdx.x; i < f.m; i += kFinCtas * kFinThreads) {
         float su = 0.f, sv = 0.f;
-        for (int p = 0; p < f.nsplit; ++p) { su += f.part_u[(int64_t)p * f.m + i]; sv += f.part_v[(int64_t)p * f.m + i]; }
+#pragma unroll 4
+        for (int p = 0; p < f.nsplit; ++p) su += f.part_u[(int64_t)p * f.m + i];
+#pragma unroll 8
+        for (int p = 0; p < nsv; ++p) sv += f.part_v[(int64_t)p * f.m + i];
         const float lu = f.inv_tau + logf(su), lv = f.inv_tau + logf(sv);
         f.lse_u[i] = lu; f.lse_v[i] = lv;
         s0 += lu + lv - 2.0f * a.diag[i];
@@ -180,7 +191,7 @@ __global__ void __launch_bounds__(1024) k_tc_finalize(FinalizeArgs f) {
     }
     red[0][threadIdx.x] = s0; red[1][threadIdx.x] = s1; red[2][threadIdx.x] = s2;
     __syncthreads();
-    for (int o = 512; o > 0; o >>= 1) {
+    for (int o = kFinThreads / 2; o > 0; o >>= 1) {
         if ((int)threadIdx.x < o) {
             red[0][threadIdx.x] += red[0][threadIdx.x + o];
             red[1][threadIdx.x] += red[1][threadIdx.x + o];
@@ -188,12 +199,16 @@ __global__ void __launch_bounds__(1024) k_tc_finalize(FinalizeArgs f) {
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) {
-        if (a.out3) { a.out3[0] = red[0][0]; a.out3[1] = red[1][0]; a.out3[2] = red[2][0]; }   // sharded: raw local sums
+    if (threadIdx.x < 3) tc::st_shared_cluster_f32(tc::mapa_u32(tc::smem_u32(&gather[rank][threadIdx.x]), 0), red[threadIdx.x][0]);
+    tc::cluster_sync_all();
+    if (rank == 0 && threadIdx.x == 0) {
+        float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+        for (int r = 0; r < kFinCtas; ++r) { t0 += gather[r][0]; t1 += gather[r][1]; t2 += gather[r][2]; }
+        if (a.out3) { a.out3[0] = t0; a.out3[1] = t1; a.out3[2] = t2; }   // sharded: raw local sums
         if (a.losses) {
-            const float l_con = red[0][0] / (2.0f * (float)f.m);
-            const float l_img = a.cos_img ? red[1][0] / (float)f.m : 0.f;
-            const float l_txt = a.cos_txt ? red[2][0] / (float)f.m : 0.f;
+            const float l_con = t0 / (2.0f * (float)f.m);
+            const float l_img = a.cos_img ? t1 / (float)f.m : 0.f;
+            const float l_txt = a.cos_txt ? t2 / (float)f.m : 0.f;
             a.losses[0] = a.w_img * l_img + a.w_txt * l_txt + a.w_con * l_con;
             a.losses[1] = l_img; a.losses[2] = l_txt; a.losses[3] = l_con;
         }
@@ -562,7 +577,7 @@ int launch_sharded_losses(const float* stat, int world, int64_t stride, int64_t 
 }
 
 int launch_tc_finalize(const FinalizeArgs& a, cudaStream_t st) {
-    k_tc_finalize<<<1, 1024, 0, st>>>(a);
+    k_tc_finalize<<<kFinCtas, kFinThreads, 0, st>>>(a);
     DCLIP_LAUNCH_OK("k_tc_finalize");
     return DCLIP_OK;
 }

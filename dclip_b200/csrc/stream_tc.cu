@@ -12,9 +12,16 @@
 // of the 4-deep ring holds one X box (128 x 64, 16 KB) and one Y box (256 x 64, 32 KB); X_I is only
 // 128 x d and stays hot in L2.
 //
-// Warps: 0-3 TMA producers (one ring stage each), 4 MMA issuer (+ TMEM alloc), 5-8 epilogue.
+// Warps: 0-3 TMA producers (one ring stage each), 4 MMA issuer (+ TMEM alloc), 5-8 epilogue (mode 1: 5-12,
+// two warps per lane quadrant with 128 of the tile's 256 columns each).
 // TMEM: two 256-column S buffers, so the epilogue of tile t overlaps the MMAs of tile t+1.
 //   mode 0 (loss forward):  thread i adds exp2((s - 1) * log2e / tau) over the valid columns -> out[i]
+//   mode 1 (loss forward, both directions from ONE pass over S; single-GPU objective where the column
+//                           direction is the other side's row direction): row sums as mode 0, plus the column
+//                           sums of the same p tile: a 32 x 32 butterfly (31 shuffles) leaves lane l with the
+//                           sum of column l over the warp's 32 rows, the four warps meet in shared memory and
+//                           the tile's 256 column sums go to col_out[row block][j] (summed over row blocks,
+//                           in fixed order, by the finalize kernel)
 //   mode 2 (retrieval):     thread i caches the admission threshold of its query; a warp-wide max test
 //                           rejects whole 32-score chunks, the rare hits are inserted warp-cooperatively
 //                           into that query's 32-entry list in shared memory -> cand_s / cand_i[i][32]
@@ -31,12 +38,20 @@ constexpr int kStages = 4;
 constexpr int kXStageBytes = SM_ROWS * 128;   // 16 KB
 constexpr int kYStageBytes = SN_COLS * 128;   // 32 KB
 constexpr int kStageBytes = kXStageBytes + kYStageBytes;
-constexpr int kStreamThreads = (kStages + 1 + 4) * 32;
+constexpr int stream_epi_warps(int mode) { return mode == 1 ? 8 : 4; }   // mode 1: two warps per TMEM lane quadrant, 128 columns each
+constexpr int stream_threads(int mode) { return (kStages + 1 + stream_epi_warps(mode)) * 32; }
 constexpr int kListLen = 32;
 constexpr uint32_t kSpinS = 1u << 24;
 
+// exponent arguments stay inside [-2 log2e / tau, 0] (tau >= 0.025): no denormal handling needed
+__device__ __forceinline__ float ex2_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 template <int kMode>
-__global__ void __launch_bounds__(kStreamThreads, 1)
+__global__ void __launch_bounds__(stream_threads(kMode), 1)
 k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CUtensorMap tmy0,
             const __grid_constant__ CUtensorMap tmx1, const __grid_constant__ CUtensorMap tmy1, const TcArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -49,7 +64,7 @@ k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CU
 
     uint8_t* ring = smem;                                             // kStages x 48 KB
     uint8_t* lists = ring + kStages * kStageBytes;                    // mode 2: [32][128] float + [32][128] int32 = 32 KB
-    uint8_t* tail = lists + (kMode == 2 ? 2 * kListLen * SM_ROWS * 4 : 0);
+    uint8_t* tail = lists + (kMode == 2 ? 2 * kListLen * SM_ROWS * 4 : kMode == 1 ? 2 * 4 * SN_COLS * 4 : 0);   // mode 1: colsum[2][4][256]
     uint64_t* full = reinterpret_cast<uint64_t*>(tail);               // [kStages]
     uint64_t* empty = full + kStages;                                 // [kStages]
     uint64_t* s_full = empty + kStages;                               // [2]
@@ -65,7 +80,7 @@ k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CU
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], stream_epi_warps(kMode) * 32); }
         fence_barrier_init();
     }
     if (warp == kStages) tmem_alloc(tmem_ptr, 512);
@@ -137,6 +152,10 @@ k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CU
         const int64_t grow = row0 + et;
         const float c = a.inv_tau * 1.4426950408889634f;
         float sum = 0.f;
+        float* colsum = reinterpret_cast<float*>(lists);  // mode 1
+        const float rowvalid = grow < a.m ? 1.f : 0.f;    // rows past m are TMA zero-filled: keep them out of the column sums
+        const int chalf = kMode == 1 ? (warp - (kStages + 1)) >> 2 : 0;     // mode 1: my 128-column half of the tile
+        (void)colsum; (void)rowvalid;
         // retrieval state: per X row an unsorted list of its 32 best approximate scores in shared memory,
         // laid out [row][32] so that a whole warp can work on one row's list without bank conflicts; the
         // owning thread caches the list minimum (= admission threshold) in a register.
@@ -156,12 +175,41 @@ k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CU
             if (!ok) break;
             fence_after_thread_sync();
 #pragma unroll 1
-            for (int c0 = 0; c0 < SN_COLS; c0 += 32) {
+            for (int c0 = chalf * 128; c0 < (kMode == 1 ? chalf * 128 + 128 : SN_COLS); c0 += 32) {
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(tmem + lane_addr + b * SN_COLS + c0, r);
                 tmem_ld_wait();
                 if (c0 >= ncols) continue;                // warp-uniform: whole chunk beyond the last Y row
-                if (kMode == 0) {
+                if (kMode == 1) {
+                    // p for the row sum and, through a 32 x 32 transpose-reduce, for the column sums
+                    float v[32];
+                    if (c0 + 32 <= ncols) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float p = ex2_ftz(fmaf(__uint_as_float(r[i]), c, -c));
+                            sum += p;
+                            v[i] = p * rowvalid;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float p = (c0 + i < ncols) ? ex2_ftz(fmaf(__uint_as_float(r[i]), c, -c)) : 0.f;
+                            sum += p;
+                            v[i] = p * rowvalid;
+                        }
+                    }
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) {
+                        const bool upper = (lane & off) != 0;
+#pragma unroll
+                        for (int i = 0; i < off; ++i) {
+                            const float send = upper ? v[i] : v[i + off];
+                            const float keep = upper ? v[i + off] : v[i];
+                            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                        }
+                    }
+                    colsum[(b * 4 + qd) * SN_COLS + c0 + lane] = v[0];     // column c0 + lane over my warp's 32 rows
+                } else if (kMode == 0) {
                     if (c0 + 32 <= ncols) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) sum += exp2f(fmaf(__uint_as_float(r[i]), c, -c));
@@ -210,8 +258,24 @@ k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CU
             }
             fence_before_thread_sync();
             mbar_arrive(&s_empty[b]);                     // all of this thread's TMEM reads of buffer b are done
+            if (kMode == 1) {
+                // the four warps' partial column sums meet here (buffer b is rewritten two tiles later, after
+                // every thread has passed the next tile's barrier)
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                const int col = chalf * 128 + et;
+                if (col < ncols) {
+                    const float* cs = colsum + b * 4 * SN_COLS + col;
+                    a.col_out[(int64_t)blockIdx.x * a.n + j0 + col] = (cs[0] + cs[SN_COLS]) + (cs[2 * SN_COLS] + cs[3 * SN_COLS]);
+                }
+            }
         }
-        if (kMode == 0) {
+        if (kMode == 1) {
+            // the two column halves of a row meet in shared memory (colsum is free after the last tile's barrier)
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            if (chalf == 1) colsum[et] = sum;
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            if (chalf == 0 && grow < a.m) S.out[(int64_t)blockIdx.y * a.m + grow] = sum + colsum[et];
+        } else if (kMode == 0) {
             if (grow < a.m) S.out[(int64_t)blockIdx.y * a.m + grow] = sum;
         } else {
             __syncwarp();
@@ -257,6 +321,7 @@ int stream_nsplit(int64_t m, int64_t n, int nsides) {
 int* tc_error_flag();   // loss_tc.cu
 
 // mode 0: x/y per side are the fp16 operands, a.s[side].out = partial row sums [nsplit][m]
+// mode 1: one side; additionally a.col_out = partial column sums [ceil(m / 128)][n]
 // mode 2: a.cand_s / a.cand_i = candidate lists [nsplit][m][32]
 int launch_stream_tc(int mode, int nsides, const void* const x[2], const void* const y[2], const TcArgs& args_in, int nsplit, cudaStream_t st) {
     if (!device_is_sm100()) return fail(DCLIP_ERR_ARCH, "tensor path needs an sm_100 device");
@@ -271,14 +336,18 @@ int launch_stream_tc(int mode, int nsides, const void* const x[2], const void* c
     const int64_t ntiles = ceil_div(a.n, SN_COLS);
     a.tiles_per_split = (int)ceil_div(ntiles, nsplit);
     a.error_flag = tc_error_flag();
-    const size_t smem = 1024 + (size_t)kStages * kStageBytes + (mode == 2 ? 2 * kListLen * SM_ROWS * 4 : 0) + 256;
+    if (mode == 1 && (!a.col_out || nsides != 1)) return fail(DCLIP_ERR_INVALID, "stream_tc: mode 1 is single-sided and needs col_out");
+    const size_t smem = 1024 + (size_t)kStages * kStageBytes + (mode == 2 ? 2 * kListLen * SM_ROWS * 4 : mode == 1 ? 2 * 4 * SN_COLS * 4 : 0) + 256;
     dim3 grid((unsigned)ceil_div(a.m, SM_ROWS), (unsigned)nsplit, (unsigned)nsides);
     if (mode == 0) {
         DCLIP_CUDA_OK(cudaFuncSetAttribute(k_stream_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_stream_tc<0><<<grid, kStreamThreads, smem, st>>>(tmx[0], tmy[0], tmx[1], tmy[1], a);
+        k_stream_tc<0><<<grid, stream_threads(0), smem, st>>>(tmx[0], tmy[0], tmx[1], tmy[1], a);
+    } else if (mode == 1) {
+        DCLIP_CUDA_OK(cudaFuncSetAttribute(k_stream_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_stream_tc<1><<<grid, stream_threads(1), smem, st>>>(tmx[0], tmy[0], tmx[1], tmy[1], a);
     } else {
         DCLIP_CUDA_OK(cudaFuncSetAttribute(k_stream_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_stream_tc<2><<<grid, kStreamThreads, smem, st>>>(tmx[0], tmy[0], tmx[1], tmy[1], a);
+        k_stream_tc<2><<<grid, stream_threads(2), smem, st>>>(tmx[0], tmy[0], tmx[1], tmy[1], a);
     }
     DCLIP_LAUNCH_OK("k_stream_tc");
     return DCLIP_OK;

@@ -180,6 +180,9 @@ __device__ __forceinline__ void fence_proxy_async_smem_cluster() { asm volatile(
 __device__ __forceinline__ void st_shared_cluster_v4(uint32_t cluster_addr, uint4 v) {
     asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+__device__ __forceinline__ void st_shared_cluster_f32(uint32_t cluster_addr, float v) {
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
+}
 // 2-D tile load into THIS CTA's shared memory whose completion bytes are credited to an mbarrier that may
 // live in the peer CTA (bar_cluster_addr = mapa_u32(barrier, leader)).
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int32_t c0, int32_t c1) {
