@@ -334,7 +334,7 @@ def kernel_roofline(L, _lib, resident, B, m, d, path, rank, peaks):
     flops = 4.0 * B * B * d
     achieved = flops / sec / 1e12
     peak = peaks["bf16_tflops"]
-    return {"bound": "tensor", "kernel": "k_infonce_bwd_tc (both directions, one launch: dU = G V, dV = G^T U; score tiles recomputed)",
+    return {"bound": "tensor", "kernel": "k_infonce_bwd_pair (CTA pairs, cta_group::2; both directions in one launch: dU = G V, dV = G^T U; score tiles recomputed)",
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "peak_source": peaks["source"] + " bf16 burst (kernel timed alone, back to back, L2-warm)",
             "algorithmic_flops_per_launch": flops, "executed_flops_per_launch": 2.0 * flops,

@@ -49,7 +49,6 @@ constexpr int NI = 128;                // X rows per pair (MMA N)
 constexpr int NH = 64;                 // X rows resident per CTA
 constexpr int TJ = 256;                // Y rows per tile
 constexpr int kBoxBytes = 128 * 128;   // [128 rows x 64 fp16] = 16 KB
-constexpr int kSlotBytes = 2 * kBoxBytes;
 constexpr int kXBoxBytes = NH * 128;   // [64 rows x 64 fp16] = 8 KB
 constexpr int kGBytes = TJ * 128;      // G^T half: [256 j x 64 i] fp16 = 32 KB
 constexpr int kEpiWarps = 8;
@@ -86,8 +85,8 @@ k_infonce_bwd_pair(const __grid_constant__ CUtensorMap tmx0, const __grid_consta
     const int NS = d / 128;            // ring-slot jobs per phase (phase 1: 2 k-boxes each; phase 2: (d block, j half))
 
     uint8_t* xs = smem;                                   // resident X half: nkb boxes of 8 KB
-    uint8_t* ring = xs + (size_t)nkb * kXBoxBytes;        // kSlots x 32 KB
-    uint8_t* gs = ring + kSlots * kSlotBytes;             // 32 KB
+    uint8_t* ring = xs + (size_t)nkb * kXBoxBytes;        // kSlots x 16 KB boxes
+    uint8_t* gs = ring + kSlots * kBoxBytes;              // 32 KB
     uint8_t* tail = gs + kGBytes;
     uint64_t* full = reinterpret_cast<uint64_t*>(tail);   // [kSlots]  (leader)
     uint64_t* empty = full + kSlots;                      // [kSlots]
@@ -139,39 +138,37 @@ k_infonce_bwd_pair(const __grid_constant__ CUtensorMap tmx0, const __grid_consta
                     for (int kb = 0; kb < nkb; ++kb)
                         tma_load_2d_pair(xs + (size_t)kb * kXBoxBytes, tmx, xbar, kb * 64, (int32_t)(row0 + cr * NH));
                 }
-                // Job q (MMA consumption order) uses slot q % kSlots.  Order: P1(0), then per tile t: P1(t+1) [if any], P2(t).
-                const int njobs = 2 * NS * T;
-                const int ndiag = diag ? NS / 2 : 0;          // extra P2-style jobs of the diagonal step (one per d block)
-                uint8_t* dst = ring + (size_t)warp * kSlotBytes;
+                // Box job q (MMA consumption order) uses slot q % kSlots.  Order: P1(0), then per tile t: P1(t+1) [if any],
+                // P2(t); every phase consumes nkb boxes (phase 2 / diagonal step: in aligned pairs).
+                const int NB = nkb;
+                const int njobs = 2 * NB * T;
+                const int ndiag = diag ? NB / 2 : 0;
+                uint8_t* dst = ring + (size_t)warp * kBoxBytes;
                 const uint32_t fbar = mapa_u32(smem_u32(&full[warp]), 0);
                 uint32_t phase = 0;
                 for (int q = warp; q < njobs + ndiag && ok; q += kSlots, phase ^= 1) {
-                    int tile = 0, sidx = 0, ph;
-                    if (q >= njobs) { sidx = q - njobs; ph = 3; }
-                    else if (q < NS) { tile = 0; sidx = q; ph = 1; }
+                    int tile = 0, idx = 0, ph;
+                    if (q >= njobs) { idx = q - njobs; ph = 3; }
+                    else if (q < NB) { tile = 0; idx = q; ph = 1; }
                     else {
-                        const int qq = q - NS, blk = min(qq / (2 * NS), T - 1), r = qq - blk * 2 * NS;
-                        if (blk < T - 1 && r < NS) { tile = blk + 1; sidx = r; ph = 1; }
-                        else { tile = blk; sidx = blk < T - 1 ? r - NS : r; ph = 2; }
+                        const int qq = q - NB, blk = min(qq / (2 * NB), T - 1), r = qq - blk * 2 * NB;
+                        if (blk < T - 1 && r < NB) { tile = blk + 1; idx = r; ph = 1; }
+                        else { tile = blk; idx = blk < T - 1 ? r - NB : r; ph = 2; }
                     }
                     const int32_t j0 = (int32_t)((t_begin + tile) * TJ);
+                    int32_t c0, r0;
+                    if (ph == 1) {              // K-major A: my 128 j rows, k box idx
+                        c0 = idx * 64; r0 = j0 + (int32_t)cr * 128;
+                    } else if (ph == 2) {       // MN-major A: box idx & 1 of my 128 columns of d block idx >> 2, j half (idx >> 1) & 1
+                        c0 = (idx >> 2) * 256 + (int32_t)cr * 128 + (idx & 1) * 64; r0 = j0 + ((idx >> 1) & 1) * 128;
+                    } else {                    // diagonal step: d block idx >> 1, the 128 Y rows facing the pair's X rows
+                        c0 = (idx >> 1) * 256 + (int32_t)cr * 128 + (idx & 1) * 64; r0 = (int32_t)(a.row_offset + row0);
+                    }
                     PROF_BEGIN(p_em);
                     ok = mbar_wait_cluster(&empty[warp], phase ^ 1, kSpin);
                     PROF_END(p_em, 6 + (int)cr);
-                    if (cr == 0) mbar_arrive_expect_tx(&full[warp], 2 * kSlotBytes);     // bytes of both CTAs
-                    if (ph == 1) {
-                        // K-major A: my 128 j rows, k boxes 2 sidx and 2 sidx + 1
-                        tma_load_2d_pair(dst, tmy, fbar, (2 * sidx) * 64, j0 + (int32_t)cr * 128);
-                        tma_load_2d_pair(dst + kBoxBytes, tmy, fbar, (2 * sidx + 1) * 64, j0 + (int32_t)cr * 128);
-                    } else {
-                        // MN-major A: my 128 columns of a d block (two 64-wide boxes); phase 2: block sidx >> 1, j half
-                        // sidx & 1; diagonal step: block sidx, the 128 Y rows facing the pair's X rows
-                        const int blk = ph == 2 ? sidx >> 1 : sidx;
-                        const int32_t c0 = blk * 256 + (int32_t)cr * 128;
-                        const int32_t r0 = ph == 2 ? j0 + (sidx & 1) * 128 : (int32_t)(a.row_offset + row0);
-                        tma_load_2d_pair(dst, tmy, fbar, c0, r0);
-                        tma_load_2d_pair(dst + kBoxBytes, tmy, fbar, c0 + 64, r0);
-                    }
+                    if (cr == 0) mbar_arrive_expect_tx(&full[warp], 2 * kBoxBytes);     // bytes of both CTAs
+                    tma_load_2d_pair(dst, tmy, fbar, c0, r0);
                 }
             }
         } else if (warp == kSlots) {
@@ -192,19 +189,16 @@ k_infonce_bwd_pair(const __grid_constant__ CUtensorMap tmx0, const __grid_consta
                     ok = ok && mbar_wait_cluster(s_empty, (t & 1) ^ 1, kSpin);
                     PROF_END(p_se, 2);
                     fence_after_thread_sync();
-                    for (int s = 0; s < NS && ok; ++s) {
+                    for (int kb = 0; kb < nkb && ok; ++kb) {
                         PROF_BEGIN(p_f1);
                         ok = mbar_wait_cluster(&full[stage], sphase, kSpin);
                         PROF_END(p_f1, 3);
                         fence_after_thread_sync();
-                        const uint64_t da0 = smem_desc(hiK, ring_addr + stage * kSlotBytes);
-                        const uint64_t db0 = smem_desc(hiK, xs_addr + (2 * s) * kXBoxBytes);
+                        const uint64_t da0 = smem_desc(hiK, ring_addr + stage * kBoxBytes);
+                        const uint64_t db0 = smem_desc(hiK, xs_addr + kb * kXBoxBytes);
 #pragma unroll
-                        for (int h = 0; h < 2; ++h)
-#pragma unroll
-                            for (int ks = 0; ks < 4; ++ks)
-                                umma_f16_pair(tmem + kSCol, da0 + (uint64_t)(h * (kBoxBytes >> 4) + ks * 2),
-                                              db0 + (uint64_t)(h * (kXBoxBytes >> 4) + ks * 2), idesc1, (s | h | ks) != 0);
+                        for (int ks = 0; ks < 4; ++ks)
+                            umma_f16_pair(tmem + kSCol, da0 + (uint64_t)(ks * 2), db0 + (uint64_t)(ks * 2), idesc1, (kb | ks) != 0);
                         umma_commit_pair(&empty[stage]);
                         if (++stage == kSlots) { stage = 0; sphase ^= 1; }
                     }
@@ -216,19 +210,21 @@ k_infonce_bwd_pair(const __grid_constant__ CUtensorMap tmx0, const __grid_consta
                     PROF_END(p_gf, 4);
                     fence_proxy_async_all();
                     fence_after_thread_sync();
-                    for (int s = 0; s < NS && ok; ++s) {
+                    for (int s = 0; s < NS && ok; ++s) {         // (d block s >> 1, j half s & 1): two adjacent ring boxes
                         PROF_BEGIN(p_f2);
-                        ok = mbar_wait_cluster(&full[stage], sphase, kSpin);
+                        ok = mbar_wait_cluster(&full[stage], sphase, kSpin) && mbar_wait_cluster(&full[stage + 1], sphase, kSpin);
                         PROF_END(p_f2, 5);
                         fence_after_thread_sync();
                         const int jh = s & 1;
-                        const uint64_t da0 = smem_desc(hiA2, ring_addr + stage * kSlotBytes);
+                        const uint64_t da0 = smem_desc(hiA2, ring_addr + stage * kBoxBytes);
                         const uint64_t db0 = smem_desc(hiB2, gs_addr + jh * (kGBytes / 2));
 #pragma unroll
                         for (int ks = 0; ks < 8; ++ks)          // 16 j per step = two 8-row groups = +2048 B
                             umma_f16_pair(tmem + (s >> 1) * NI, da0 + (uint64_t)(ks * 128), db0 + (uint64_t)(ks * 128), idesc2, (t | jh | ks) != 0);
                         umma_commit_pair(&empty[stage]);
-                        if (++stage == kSlots) { stage = 0; sphase ^= 1; }
+                        umma_commit_pair(&empty[stage + 1]);
+                        stage += 2;
+                        if (stage == kSlots) { stage = 0; sphase ^= 1; }
                     }
                     umma_commit_pair(g_empty);
                 };
@@ -243,15 +239,17 @@ k_infonce_bwd_pair(const __grid_constant__ CUtensorMap tmx0, const __grid_consta
                     fence_proxy_async_all();
                     fence_after_thread_sync();
                     for (int s = 0; s < NS / 2 && ok; ++s) {
-                        ok = mbar_wait_cluster(&full[stage], sphase, kSpin);
+                        ok = mbar_wait_cluster(&full[stage], sphase, kSpin) && mbar_wait_cluster(&full[stage + 1], sphase, kSpin);
                         fence_after_thread_sync();
-                        const uint64_t da0 = smem_desc(hiA2, ring_addr + stage * kSlotBytes);
+                        const uint64_t da0 = smem_desc(hiA2, ring_addr + stage * kBoxBytes);
                         const uint64_t db0 = smem_desc(hiB2, gs_addr);
 #pragma unroll
                         for (int ks = 0; ks < 8; ++ks)
                             umma_f16_pair(tmem + s * NI, da0 + (uint64_t)(ks * 128), db0 + (uint64_t)(ks * 128), idesc2, 1);
                         umma_commit_pair(&empty[stage]);
-                        if (++stage == kSlots) { stage = 0; sphase ^= 1; }
+                        umma_commit_pair(&empty[stage + 1]);
+                        stage += 2;
+                        if (stage == kSlots) { stage = 0; sphase ^= 1; }
                     }
                 }
                 umma_commit_pair(acc_full);
@@ -418,15 +416,16 @@ int launch_infonce_bwd_pair(int nsides, const void* const x[2], const void* cons
     const int64_t ntiles = ceil_div(a.n, TJ);
     a.tiles_per_split = (int)ceil_div(ntiles, nsplit);
     a.error_flag = tc_error_flag();
-    // ring depth: as many 32 KB slots as fit next to the resident X half and the G tile (3 at d = 768, 4 at d = 512)
+    // ring: 16 KB boxes, one producer warp each (finer slots keep more of the ring in flight: a slot is refilled
+    // ~900-1000 cycles after its release, tools/tc_bench tmamp); 6 boxes fit next to X (96 KB) and G at d = 768
     static const int forced_slots = [] { const char* e = getenv("DCLIP_PAIR_SLOTS"); return e ? atoi(e) : 0; }();
     const size_t fixed = 1024 + (size_t)(a.d / 64) * kXBoxBytes + kGBytes + 1024;
-    int slots = (int)((232448 - fixed) / kSlotBytes);
-    if (slots > 4) slots = 4;
-    if (forced_slots >= 2 && forced_slots <= slots) slots = forced_slots;
-    const size_t smem = fixed + (size_t)slots * kSlotBytes;
+    int slots = (int)((232448 - fixed) / kBoxBytes) & ~1;
+    if (slots > 6) slots = 6;
+    if (forced_slots >= 2 && forced_slots <= slots && forced_slots % 2 == 0) slots = forced_slots;
+    const size_t smem = fixed + (size_t)slots * kBoxBytes;
     dim3 grid((unsigned)(2 * ceil_div(a.m, NI)), (unsigned)nsplit, (unsigned)nsides);
-    auto kern = slots == 4 ? k_infonce_bwd_pair<4> : slots == 3 ? k_infonce_bwd_pair<3> : k_infonce_bwd_pair<2>;
+    auto kern = slots == 6 ? k_infonce_bwd_pair<6> : slots == 4 ? k_infonce_bwd_pair<4> : k_infonce_bwd_pair<2>;
     DCLIP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, (slots + 9) * 32, smem, st>>>(tmx[0], tmy[0], tmx[1], tmy[1], a);
     DCLIP_LAUNCH_OK("k_infonce_bwd_pair");
