@@ -62,6 +62,7 @@ struct TcArgs {
     float* cand_s;        // retrieval mode: [nsplit][m][32] approximate scores (descending)
     int32_t* cand_i;      //                 [nsplit][m][32] gallery rows (-1 = empty)
     float* col_out;       // stream mode 1: partial column sums [ceil(m / 128)][n]
+    int debug_skip;       // timing experiments only (results are garbage): 1 = no phase-1 MMAs, 2 = no phase-2 MMAs, 4 = no G stores
 };
 
 

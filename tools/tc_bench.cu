@@ -23,15 +23,16 @@ using namespace dclip::tc;
     } while (0)
 
 // ---- (1) MMA rate: one thread issues `iters` x `per` MMAs on resident (zeroed) operands ---------
+template <int commit_every>
 __global__ void __launch_bounds__(128) k_mma_rate(int N, int a_mn, int b_mn, int iters, int per, int spread, long long* cycles) {
     extern __shared__ uint8_t raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bar, bar2;
     __shared__ uint32_t tmem_base;
     for (int i = threadIdx.x; i < 160 * 1024 / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async_smem();
     if (threadIdx.x < 32) tmem_alloc(&tmem_base, 512);
-    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_init(&bar2, 1); fence_barrier_init(); }
     fence_before_thread_sync();
     __syncthreads();
     fence_after_thread_sync();
@@ -49,7 +50,10 @@ __global__ void __launch_bounds__(128) k_mma_rate(int N, int a_mn, int b_mn, int
             for (int k8 = 0; k8 < per; k8 += 8) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k)
+                {
                     umma_f16(tmem + (k & 1) * 256, dA + (uint64_t)(k * stepA), dB + (uint64_t)((k & 3) * stepB), idesc, 1);
+                    if (commit_every && (k + 1) % commit_every == 0) umma_commit(&bar2);
+                }
             }
             umma_commit(&bar);
             if (!mbar_wait(&bar, parity, 1u << 22)) { cycles[blockIdx.x] = -1; break; }
@@ -66,7 +70,7 @@ __global__ void __launch_bounds__(128) k_mma_rate(int N, int a_mn, int b_mn, int
 static void run_mma() {
     long long* cyc;
     CK(cudaMalloc(&cyc, 148 * 8));
-    CK(cudaFuncSetAttribute(k_mma_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(k_mma_rate<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     printf("%-6s %-4s %-4s %-7s %-6s | cycles/MMA (ideal M*N/256... 128*N*16/4096)\n", "N", "Amn", "Bmn", "spread", "grid");
     const int Ns[3] = {64, 128, 256};
     for (int grid : {1, 148})
@@ -77,7 +81,7 @@ static void run_mma() {
                     if (b_mn && N > 64 && 0) continue;
                     CK(cudaMemset(cyc, 0, 148 * 8));
                     const int iters = 20, per = 64;
-                    k_mma_rate<<<grid, 128, 200 * 1024>>>(N, a_mn, b_mn, iters, per, spread, cyc);
+                    k_mma_rate<0><<<grid, 128, 200 * 1024>>>(N, a_mn, b_mn, iters, per, spread, cyc);
                     cudaError_t e = cudaDeviceSynchronize();
                     if (e != cudaSuccess) { printf("N=%d maj=%d: CUDA ERROR %s\n", N, maj, cudaGetErrorString(e)); exit(3); }
                     long long h[148];
@@ -88,6 +92,92 @@ static void run_mma() {
                     printf("%-6d %-4d %-4d %-7d %-6d | %8.1f   (ideal %d)%s\n", N, a_mn, b_mn, spread, grid, avg / (iters * per), N / 2,
                            h[0] < 0 ? "  TIMEOUT" : "");
                 }
+}
+
+// ---- (1b) CTA-pair MMA rate: the leader issues `iters` x `per` cta_group::2 MMAs (M = 256) on resident operands ------
+template <int commit_every, int commit_mode>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) k_mma2_rate(int N, int a_mn, int b_mn, int iters, int per,
+                                                                             long long* cycles) {
+    extern __shared__ uint8_t raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t bar, bar2;
+    __shared__ uint32_t tmem_base;
+    for (int i = threadIdx.x; i < 160 * 1024 / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+    if (threadIdx.x < 32) tmem_alloc_pair(&tmem_base, 512);
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_init(&bar2, 1); fence_barrier_init(); }
+    fence_before_thread_sync();
+    __syncthreads();
+    cluster_sync_all();
+    fence_after_thread_sync();
+    const uint32_t tmem = tmem_base;
+    if (cluster_ctarank() == 0 && uniform_warp_idx() == 0 && elect_one()) {
+        const uint32_t idesc = make_idesc_f16(256, N, kFmtF16, a_mn, b_mn);
+        const uint64_t hiA = make_smem_desc_hi(a_mn ? 16384 : 0, 1024, kSwizzle128B);
+        const uint64_t hiB = make_smem_desc_hi(b_mn ? 16384 : 0, 1024, kSwizzle128B);
+        const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem) + 64 * 1024;
+        uint32_t parity = 0;
+        const long long t0 = clock64();
+        for (int it = 0; it < iters; ++it) {
+            const uint64_t dA = smem_desc(hiA, a0), dB = smem_desc(hiB, b0);
+            const uint32_t stepA = a_mn ? 128u : 2u, stepB = b_mn ? 128u : 2u;
+            for (int k8 = 0; k8 < per; k8 += 8) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    umma_f16_pair(tmem + (k & 1) * 256, dA + (uint64_t)(k * stepA), dB + (uint64_t)((k & 3) * stepB), idesc, 1);
+                    if (commit_every && (k + 1) % commit_every == 0) {
+                        if (commit_mode == 1) umma_commit_pair(&bar2);             // multicast to both CTAs
+                        else if (commit_mode == 2) umma_commit_pair(&bar2, 1);     // multicast form, leader only
+                        else asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar2)) : "memory");
+                    }
+                }
+            }
+            umma_commit_pair(&bar);
+            if (!mbar_wait(&bar, parity, 1u << 22)) { cycles[blockIdx.x >> 1] = -1; break; }
+            parity ^= 1;
+        }
+        const long long t1 = clock64();
+        if (cycles[blockIdx.x >> 1] != -1) cycles[blockIdx.x >> 1] = t1 - t0;
+    }
+    fence_before_thread_sync();
+    __syncthreads();
+    cluster_sync_all();
+    if (threadIdx.x < 32) tmem_dealloc_pair(tmem, 512);
+}
+
+template <int CE>
+static double one_mma1(int N, long long* cyc) {
+    CK(cudaFuncSetAttribute(k_mma_rate<CE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaMemset(cyc, 0, 148 * 8));
+    k_mma_rate<CE><<<1, 128, 200 * 1024>>>(N, 0, 0, 20, 64, 1, cyc);
+    CK(cudaDeviceSynchronize());
+    long long h;
+    CK(cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost));
+    return (double)h / (20 * 64);
+}
+template <int CE, int MODE>
+static double one_mma2(int N, long long* cyc) {
+    CK(cudaFuncSetAttribute((k_mma2_rate<CE, MODE>), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaMemset(cyc, 0, 148 * 8));
+    k_mma2_rate<CE, MODE><<<2, 128, 200 * 1024>>>(N, 0, 0, 20, 64, cyc);
+    CK(cudaDeviceSynchronize());
+    long long h;
+    CK(cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost));
+    return (double)h / (20 * 64);
+}
+
+static void run_mma2() {
+    long long* cyc;
+    CK(cudaMalloc(&cyc, 148 * 8));
+    printf("cycles per MMA with a tcgen05.commit every CE MMAs (CE = 0: only at the end of 64)\n");
+    for (int N : {64, 128, 256})
+        printf("single CTA  M=128 N=%-3d | CE=0 %6.1f  CE=8 %6.1f  CE=4 %6.1f  CE=2 %6.1f\n", N, one_mma1<0>(N, cyc), one_mma1<8>(N, cyc), one_mma1<4>(N, cyc), one_mma1<2>(N, cyc));
+    for (int N : {128, 256}) {
+        printf("CTA pair    M=256 N=%-3d | CE=0 %6.1f | multicast both: CE=8 %6.1f CE=4 %6.1f | leader only: CE=8 %6.1f CE=4 %6.1f | plain: CE=8 %6.1f CE=4 %6.1f\n", N,
+               one_mma2<0, 1>(N, cyc), one_mma2<8, 1>(N, cyc), one_mma2<4, 1>(N, cyc), one_mma2<8, 2>(N, cyc), one_mma2<4, 2>(N, cyc),
+               one_mma2<8, 3>(N, cyc), one_mma2<4, 3>(N, cyc));
+        fflush(stdout);
+    }
 }
 
 // ---- (2) TMA streaming rate ---------------------------------------------------------------------
@@ -250,6 +340,7 @@ static void run_tma() {
 
 int main(int argc, char** argv) {
     if (argc >= 2 && !strcmp(argv[1], "mma")) { run_mma(); return 0; }
+    if (argc >= 2 && !strcmp(argv[1], "mma2")) { run_mma2(); return 0; }
     if (argc >= 2 && !strcmp(argv[1], "tma")) { run_tma(); return 0; }
     if (argc >= 2 && !strcmp(argv[1], "tmamp")) { run_tma_mp(); return 0; }
     printf("usage: tc_bench mma | tma\n");
