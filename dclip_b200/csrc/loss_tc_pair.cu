@@ -457,7 +457,7 @@ int launch_infonce_bwd_pair(int nsides, const void* const x[2], const void* cons
     static const int forced_slots = [] { const char* e = getenv("DCLIP_PAIR_SLOTS"); return e ? atoi(e) : 0; }();
     const size_t fixed = 1024 + (size_t)(a.d / 64) * kXBoxBytes + kGBytes + 1024;
     int slots = (int)((232448 - fixed) / kBoxBytes) & ~1;
-    if (slots > 6) slots = 6;
+    if (slots > 6) slots = 6;      // 8 boxes = 17 warps: the register cap (96) spills the epilogue, measured slower at d = 512
     if (forced_slots >= 2 && forced_slots <= slots && forced_slots % 2 == 0) slots = forced_slots;
     const size_t smem = fixed + (size_t)slots * kBoxBytes;
     dim3 grid((unsigned)(2 * ceil_div(a.m, NI)), (unsigned)nsplit, (unsigned)nsides);

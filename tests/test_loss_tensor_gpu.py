@@ -83,3 +83,24 @@ def test_tensor_path_rejects_unsupported(built_library):
     y = torch.randn(64, 256, device=dev)
     with pytest.raises(RuntimeError, match="temperature"):
         L.distill_loss_fwd_bwd(y, y.clone(), temperature=0.01, path="tensor")
+
+
+def test_pair_backward_is_bit_reproducible(built_library):
+    """The CTA-pair backward publishes its G tiles across the pair without GPU-scope membars (ordering by
+    construction, csrc/loss_tc_pair.cu).  A lost ordering would show up as run-to-run differences: every run
+    must be bit-identical (fixed reduction order everywhere)."""
+    from dclip_b200 import losses as L
+    dev = torch.device("cuda:0")
+    for B, d in ((1024, 768), (4096, 256), (640, 512)):
+        s_img, s_txt, t_img, t_txt = (t.to(torch.bfloat16).to(dev) for t in synthetic.loss_inputs(B, d, seed=7))
+        ref = None
+        for _ in range(25):
+            losses, d_img, d_txt = L.distill_loss_fwd_bwd(s_img, s_txt, t_img, t_txt, path="tensor")
+            cur = (losses.clone(), d_img.clone(), d_txt.clone())
+            if ref is None:
+                ref = cur
+            else:
+                for a, b in zip(ref, cur):
+                    assert torch.equal(a, b)
+    torch.cuda.synchronize()
+    assert _pipeline_ok(built_library)
