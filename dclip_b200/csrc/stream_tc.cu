@@ -25,6 +25,8 @@
 //   mode 2 (retrieval):     thread i caches the admission threshold of its query; a warp-wide max test
 //                           rejects whole 32-score chunks, the rare hits are inserted warp-cooperatively
 //                           into that query's 32-entry list in shared memory -> cand_s / cand_i[i][32]
+#include <cstdlib>
+
 #include "common.cuh"
 #include "loss_internal.h"
 #include "tcgen05.cuh"
@@ -32,14 +34,26 @@
 namespace dclip {
 using namespace tc;
 
+// Optional stall accounting (build with -DDCLIP_PAIR_PROF): cycles CTA (0,0,0) spends in each wait.
+#ifdef DCLIP_PAIR_PROF
+__device__ unsigned long long g_stream_prof[16];
+#define SPROF_BEGIN(v) const long long v = clock64()
+#define SPROF_END(v, slot) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) atomicAdd(&g_stream_prof[slot], (unsigned long long)(clock64() - v)); } while (0)
+#else
+#define SPROF_BEGIN(v) do { } while (0)
+#define SPROF_END(v, slot) do { } while (0)
+#endif
+
 constexpr int SM_ROWS = 128;             // X rows per CTA (MMA M)
 constexpr int SN_COLS = 256;             // Y rows per tile (MMA N)
-constexpr int kStages = 4;
+constexpr int kStagesSingle = 4;          // single-CTA ring: X box + 256-row Y box = 48 KB per stage
+constexpr int kStagesPair = 6;            // CTA-pair ring: X box + MY 128 rows of the Y tile = 32 KB per stage
 constexpr int kXStageBytes = SM_ROWS * 128;   // 16 KB
 constexpr int kYStageBytes = SN_COLS * 128;   // 32 KB
-constexpr int kStageBytes = kXStageBytes + kYStageBytes;
+constexpr int stream_stages(bool pair) { return pair ? kStagesPair : kStagesSingle; }
+constexpr int stream_stage_bytes(bool pair) { return kXStageBytes + (pair ? kYStageBytes / 2 : kYStageBytes); }
 constexpr int stream_epi_warps(int mode) { return mode == 1 ? 8 : 4; }   // mode 1: two warps per TMEM lane quadrant, 128 columns each
-constexpr int stream_threads(int mode) { return (kStages + 1 + stream_epi_warps(mode)) * 32; }
+constexpr int stream_threads(int mode, bool pair) { return (stream_stages(pair) + 1 + stream_epi_warps(mode)) * 32; }
 constexpr int kListLen = 32;
 constexpr uint32_t kSpinS = 1u << 24;
 
@@ -50,8 +64,11 @@ __device__ __forceinline__ float ex2_ftz(float x) {
     return y;
 }
 
-template <int kMode>
-__global__ void __launch_bounds__(stream_threads(kMode), 1)
+// kPair: the two CTAs of a (2,1,1) cluster share every 256-row Y tile (cta_group::2, M = 256 = both CTAs' 128 X rows,
+// N = 256 = 128 Y rows from each CTA's shared memory): each CTA streams only HALF of Y, a stage shrinks from 48 to
+// 32 KB and the ring deepens from 4 to 6 stages.  Row mapping is unchanged (CTA x owns X rows [128 x, 128 x + 128)).
+template <int kMode, bool kPair>
+__global__ void __launch_bounds__(stream_threads(kMode, kPair), 1)
 k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CUtensorMap tmy0,
             const __grid_constant__ CUtensorMap tmx1, const __grid_constant__ CUtensorMap tmy1, const TcArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -61,8 +78,11 @@ k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CU
     const CUtensorMap* tmy = side ? &tmy1 : &tmy0;
     const TcSide S = a.s[side];
     const int nkb = (int)((a.d + 63) / 64);
+    constexpr int kStages = stream_stages(kPair);
+    constexpr int kStageBytes = stream_stage_bytes(kPair);
+    const uint32_t cr = kPair ? cluster_ctarank() : 0u;
 
-    uint8_t* ring = smem;                                             // kStages x 48 KB
+    uint8_t* ring = smem;                                             // kStages x (48 | 32) KB
     uint8_t* lists = ring + kStages * kStageBytes;                    // mode 2: [32][128] float + [32][128] int32 = 32 KB
     uint8_t* tail = lists + (kMode == 2 ? 2 * kListLen * SM_ROWS * 4 : kMode == 1 ? 2 * 4 * SN_COLS * 4 : 0);   // mode 1: colsum[2][4][256]
     uint64_t* full = reinterpret_cast<uint64_t*>(tail);               // [kStages]
@@ -80,12 +100,14 @@ k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CU
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], stream_epi_warps(kMode) * 32); }
+        // s_empty: every epilogue thread (single CTA) / one lane per epilogue warp of BOTH CTAs (pair; leader's copy)
+        for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], kPair ? 2 * stream_epi_warps(kMode) : stream_epi_warps(kMode) * 32); }
         fence_barrier_init();
     }
-    if (warp == kStages) tmem_alloc(tmem_ptr, 512);
+    if (warp == kStages) { if (kPair) tmem_alloc_pair(tmem_ptr, 512); else tmem_alloc(tmem_ptr, 512); }
     fence_before_thread_sync();
     __syncthreads();
+    if (kPair) cluster_sync_all();          // peer barriers initialised, both TMEMs allocated
     fence_after_thread_sync();
     const uint32_t tmem = *tmem_ptr;
     bool ok = true;
@@ -113,36 +135,55 @@ k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CU
                         if (pt % (int)gridDim.x == (int)blockIdx.x)
                             for (int k2 = 0; k2 < nkb; ++k2) tma_prefetch_l2_2d(tmy, k2 * 64, (int32_t)((t_begin + pt) * SN_COLS));
                 }
+                SPROF_BEGIN(p_em);
                 ok = mbar_wait(&empty[warp], phase ^ 1, kSpinS);
-                mbar_arrive_expect_tx(&full[warp], kStageBytes);
-                tma_load_2d(dst, tmx, &full[warp], kb * 64, (int32_t)row0);
-                tma_load_2d(dst + kXStageBytes, tmy, &full[warp], kb * 64, j0);
+                if (warp == 0) SPROF_END(p_em, 5);
+                if (kPair) {
+                    // both CTAs' bytes are credited to the leader's barrier; my B half = Y rows [j0 + 128 cr, + 128)
+                    const uint32_t fbar = mapa_u32(smem_u32(&full[warp]), 0);
+                    if (cr == 0) mbar_arrive_expect_tx(&full[warp], 2 * kStageBytes);
+                    tma_load_2d_pair(dst, tmx, fbar, kb * 64, (int32_t)row0);
+                    tma_load_2d_pair(dst + kXStageBytes, tmy, fbar, kb * 64, j0 + (int32_t)cr * 128);
+                } else {
+                    mbar_arrive_expect_tx(&full[warp], kStageBytes);
+                    tma_load_2d(dst, tmx, &full[warp], kb * 64, (int32_t)row0);
+                    tma_load_2d(dst + kXStageBytes, tmy, &full[warp], kb * 64, j0);
+                }
             }
         }
     } else if (warp == kStages) {
         // ===================== MMA issuer =====================
-        if (T > 0 && elect_one()) {
-            const uint32_t idesc = make_idesc_f16(SM_ROWS, SN_COLS, kFmtF16, 0, 0);
+        if (T > 0 && cr == 0 && elect_one()) {
+            const uint32_t idesc = make_idesc_f16(kPair ? 2 * SM_ROWS : SM_ROWS, SN_COLS, kFmtF16, 0, 0);
             const uint64_t hiK = make_smem_desc_hi(0, 1024, kSwizzle128B);
             const uint32_t ring_addr = smem_u32(ring);
             uint32_t stage = 0, phase = 0;
+            SPROF_BEGIN(p_all);
             for (int t = 0; t < T && ok; ++t) {
                 const int b = t & 1;
+                SPROF_BEGIN(p_se);
                 ok = mbar_wait(&s_empty[b], ((t >> 1) & 1) ^ 1, kSpinS);
+                SPROF_END(p_se, 1);
                 fence_after_thread_sync();
                 const uint32_t dcol = tmem + b * SN_COLS;
                 for (int kb = 0; kb < nkb && ok; ++kb) {
+                    SPROF_BEGIN(p_fu);
                     ok = mbar_wait(&full[stage], phase, kSpinS);
+                    SPROF_END(p_fu, 2);
                     fence_after_thread_sync();
                     const uint64_t da0 = smem_desc(hiK, ring_addr + stage * kStageBytes);
                     const uint64_t db0 = smem_desc(hiK, ring_addr + stage * kStageBytes + kXStageBytes);
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) umma_f16(dcol, da0 + (uint64_t)(ks * 2), db0 + (uint64_t)(ks * 2), idesc, (kb | ks) != 0);
-                    umma_commit(&empty[stage]);
+                    for (int ks = 0; ks < 4; ++ks) {
+                        if (kPair) umma_f16_pair(dcol, da0 + (uint64_t)(ks * 2), db0 + (uint64_t)(ks * 2), idesc, (kb | ks) != 0);
+                        else umma_f16(dcol, da0 + (uint64_t)(ks * 2), db0 + (uint64_t)(ks * 2), idesc, (kb | ks) != 0);
+                    }
+                    if (kPair) umma_commit_pair(&empty[stage]); else umma_commit(&empty[stage]);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&s_full[b]);
+                if (kPair) umma_commit_pair(&s_full[b]); else umma_commit(&s_full[b]);
             }
+            SPROF_END(p_all, 0);
         }
     } else {
         // ===================== epilogue: thread = one X row =====================
@@ -170,10 +211,13 @@ k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CU
             const int b = t & 1;
             const int64_t j0 = (t_begin + t) * SN_COLS;
             const int ncols = (int)min((int64_t)SN_COLS, a.n - j0);
+            SPROF_BEGIN(p_sf);
             ok = mbar_wait(&s_full[b], (t >> 1) & 1, kSpinS);
+            if (threadIdx.x == (kStages + 1) * 32) SPROF_END(p_sf, 3);
             ok = __all_sync(0xffffffffu, ok);
             if (!ok) break;
             fence_after_thread_sync();
+            SPROF_BEGIN(p_ep);
 #pragma unroll 1
             for (int c0 = chalf * 128; c0 < (kMode == 1 ? chalf * 128 + 128 : SN_COLS); c0 += 32) {
                 uint32_t r[32];
@@ -257,13 +301,19 @@ k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CU
                 }
             }
             fence_before_thread_sync();
-            mbar_arrive(&s_empty[b]);                     // all of this thread's TMEM reads of buffer b are done
+            if (kPair) {                                  // one (relaxed: no data published) arrival per warp on the leader's barrier
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&s_empty[b]), 0));
+            } else {
+                mbar_arrive(&s_empty[b]);                 // all of this thread's TMEM reads of buffer b are done
+            }
+            if (threadIdx.x == (kStages + 1) * 32) SPROF_END(p_ep, 4);
             if (kMode == 1) {
                 // the four warps' partial column sums meet here (buffer b is rewritten two tiles later, after
                 // every thread has passed the next tile's barrier)
                 asm volatile("bar.sync 2, 256;" ::: "memory");
                 const int col = chalf * 128 + et;
-                if (col < ncols) {
+                if (col < ncols && row0 < a.m) {          // (a padded pair CTA past the last row block writes nothing)
                     const float* cs = colsum + b * 4 * SN_COLS + col;
                     a.col_out[(int64_t)blockIdx.x * a.n + j0 + col] = (cs[0] + cs[SN_COLS]) + (cs[2 * SN_COLS] + cs[3 * SN_COLS]);
                 }
@@ -291,7 +341,8 @@ k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CU
     if (!ok && lane == 0 && a.error_flag) atomicExch(a.error_flag, 1);
     fence_before_thread_sync();
     __syncthreads();
-    if (warp == kStages) tmem_dealloc(tmem, 512);
+    if (kPair) cluster_sync_all();          // no CTA leaves while its peer can still signal its barriers / read its operands
+    if (warp == kStages) { if (kPair) tmem_dealloc_pair(tmem, 512); else tmem_dealloc(tmem, 512); }
 }
 
 // Column splits: enough CTAs to fill the SMs when there are few row blocks; with many row blocks the
@@ -326,31 +377,57 @@ int* tc_error_flag();   // loss_tc.cu
 int launch_stream_tc(int mode, int nsides, const void* const x[2], const void* const y[2], const TcArgs& args_in, int nsplit, cudaStream_t st) {
     if (!device_is_sm100()) return fail(DCLIP_ERR_ARCH, "tensor path needs an sm_100 device");
     TcArgs a = args_in;
+    // CTA pairs whenever there is more than one 128-row block of X (DCLIP_STREAM_SINGLE=1 forces the single-CTA kernel)
+    static const bool forced_single = [] { const char* e = getenv("DCLIP_STREAM_SINGLE"); return e && e[0] == '1'; }();
+    const bool pair = !forced_single && a.m > SM_ROWS;
     CUtensorMap tmx[2], tmy[2];
     for (int s = 0; s < 2; ++s) {
         const int src = s < nsides ? s : 0;
         if (!make_tmap_2d_sw128(&tmx[s], x[src], (uint64_t)a.m, (uint64_t)a.d, SM_ROWS, 0) ||
-            !make_tmap_2d_sw128(&tmy[s], y[src], (uint64_t)a.n, (uint64_t)a.d, SN_COLS, 0))
+            !make_tmap_2d_sw128(&tmy[s], y[src], (uint64_t)a.n, (uint64_t)a.d, pair ? SN_COLS / 2 : SN_COLS, 0))
             return fail(DCLIP_ERR_CUDA, "cuTensorMapEncodeTiled failed (m=%lld n=%lld d=%lld)", (long long)a.m, (long long)a.n, (long long)a.d);
     }
     const int64_t ntiles = ceil_div(a.n, SN_COLS);
     a.tiles_per_split = (int)ceil_div(ntiles, nsplit);
     a.error_flag = tc_error_flag();
     if (mode == 1 && (!a.col_out || nsides != 1)) return fail(DCLIP_ERR_INVALID, "stream_tc: mode 1 is single-sided and needs col_out");
-    const size_t smem = 1024 + (size_t)kStages * kStageBytes + (mode == 2 ? 2 * kListLen * SM_ROWS * 4 : mode == 1 ? 2 * 4 * SN_COLS * 4 : 0) + 256;
-    dim3 grid((unsigned)ceil_div(a.m, SM_ROWS), (unsigned)nsplit, (unsigned)nsides);
-    if (mode == 0) {
-        DCLIP_CUDA_OK(cudaFuncSetAttribute(k_stream_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_stream_tc<0><<<grid, stream_threads(0), smem, st>>>(tmx[0], tmy[0], tmx[1], tmy[1], a);
-    } else if (mode == 1) {
-        DCLIP_CUDA_OK(cudaFuncSetAttribute(k_stream_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_stream_tc<1><<<grid, stream_threads(1), smem, st>>>(tmx[0], tmy[0], tmx[1], tmy[1], a);
-    } else {
-        DCLIP_CUDA_OK(cudaFuncSetAttribute(k_stream_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_stream_tc<2><<<grid, stream_threads(2), smem, st>>>(tmx[0], tmy[0], tmx[1], tmy[1], a);
-    }
+    const size_t smem = 1024 + (size_t)stream_stages(pair) * stream_stage_bytes(pair) +
+                        (mode == 2 ? 2 * kListLen * SM_ROWS * 4 : mode == 1 ? 2 * 4 * SN_COLS * 4 : 0) + 256;
+    const int64_t row_blocks = ceil_div(a.m, SM_ROWS);
+    dim3 grid((unsigned)(pair ? (row_blocks + 1) / 2 * 2 : row_blocks), (unsigned)nsplit, (unsigned)nsides);
+#define DCLIP_STREAM_LAUNCH(MODE, PAIR)                                                                                   \
+    do {                                                                                                                  \
+        DCLIP_CUDA_OK(cudaFuncSetAttribute((k_stream_tc<MODE, PAIR>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        if (PAIR) {                                                                                                       \
+            cudaLaunchConfig_t cfg = {};                                                                                  \
+            cfg.gridDim = grid; cfg.blockDim = dim3(stream_threads(MODE, PAIR)); cfg.dynamicSmemBytes = smem; cfg.stream = st; \
+            cudaLaunchAttribute at[1];                                                                                    \
+            at[0].id = cudaLaunchAttributeClusterDimension;                                                               \
+            at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;                          \
+            cfg.attrs = at; cfg.numAttrs = 1;                                                                             \
+            DCLIP_CUDA_OK(cudaLaunchKernelEx(&cfg, k_stream_tc<MODE, PAIR>, tmx[0], tmy[0], tmx[1], tmy[1], a));          \
+        } else {                                                                                                          \
+            k_stream_tc<MODE, PAIR><<<grid, stream_threads(MODE, PAIR), smem, st>>>(tmx[0], tmy[0], tmx[1], tmy[1], a);   \
+        }                                                                                                                 \
+    } while (0)
+    if (mode == 0) { if (pair) DCLIP_STREAM_LAUNCH(0, true); else DCLIP_STREAM_LAUNCH(0, false); }
+    else if (mode == 1) { if (pair) DCLIP_STREAM_LAUNCH(1, true); else DCLIP_STREAM_LAUNCH(1, false); }
+    else { if (pair) DCLIP_STREAM_LAUNCH(2, true); else DCLIP_STREAM_LAUNCH(2, false); }
+#undef DCLIP_STREAM_LAUNCH
     DCLIP_LAUNCH_OK("k_stream_tc");
     return DCLIP_OK;
 }
 
 }  // namespace dclip
+
+#ifdef DCLIP_PAIR_PROF
+extern "C" int dclip_debug_stream_prof(unsigned long long* out16, int reset) {
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(out16, dclip::g_stream_prof, 16 * sizeof(unsigned long long)) != cudaSuccess) return -1;
+    if (reset) {
+        unsigned long long z[16] = {0};
+        cudaMemcpyToSymbol(dclip::g_stream_prof, z, sizeof(z));
+    }
+    return 0;
+}
+#endif
