@@ -53,6 +53,15 @@ SIGNATURES = {
     "dclip_sharded_loss_fwd": (_i32, [_vp, _vp, _i64, _i64, _i64, _f32, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dclip_sharded_loss_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _f32, _i64, _i32, _i32, _vp, _vp, _vp,
                                       _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "dclip_p2p_flags_bytes": (_sz, []),
+    "dclip_p2p_alloc": (_i32, [_sz, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p]),
+    "dclip_p2p_init_flags": (_i32, [_vp, _sz, _i32]),
+    "dclip_p2p_open": (_i32, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]),
+    "dclip_p2p_close": (_i32, [_vp]),
+    "dclip_p2p_free": (_i32, [_vp]),
+    "dclip_p2p_push": (_i32, [ctypes.POINTER(ctypes.c_void_p), _i32, _i32, ctypes.POINTER(_sz), ctypes.POINTER(_sz), _i32, _sz, _i32,
+                              _i32, _vp]),
+    "dclip_p2p_wait": (_i32, [_vp, _sz, _i32, _i32, _i32, _vp]),
     "dclip_normalize_rows": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp]),
     "dclip_pair_scores": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp]),
     "dclip_rank_counts_workspace_bytes": (_sz, [_i64, _i64, _i64, _i32]),

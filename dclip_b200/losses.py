@@ -228,7 +228,7 @@ class CudaLossOps:
 
 
 def sharded_distill_loss_fwd_bwd(s_img, s_txt, t_img=None, t_txt=None, temperature=0.05, w_img=1.0, w_txt=1.0,
-                                 w_con=1.0, grad_scale=1.0, need_grad=True, group=None, ops=None, path="auto"):
+                                 w_con=1.0, grad_scale=1.0, need_grad=True, group=None, ops=None, path="auto", comm="auto"):
     """Global-batch objective with the batch sharded over the ranks of `group`.
 
     Every rank passes its own [m, d] rows (equal m on all ranks; rank r owns global rows
@@ -237,11 +237,15 @@ def sharded_distill_loss_fwd_bwd(s_img, s_txt, t_img=None, t_txt=None, temperatu
     batch.  Collectives: all-gather of the normalised operands (2 x [m, d]), all-gather of
     the two log-sum-exp vectors (2 x [m] floats), all-reduce of 3 floats.  Each rank
     recomputes the column block it owns, so no [B, d] gradient reduce-scatter is needed.
+
+    comm: "p2p" = the fused phases exchange through symmetric NVLink peer memory (dclip_b200.peer: push kernels +
+    flag waits, no NCCL call in the step); "nccl" = torch.distributed all-gathers; "auto" = p2p on the fused
+    tensor path when the peer mapping can be set up (env DCLIP_SHARDED_COMM overrides), else nccl.
     """
     import torch.distributed as dist
 
     if ops is None and _fused_sharded_ok(s_img, temperature, path):
-        return _sharded_fused(s_img, s_txt, t_img, t_txt, temperature, w_img, w_txt, w_con, grad_scale, need_grad, group)
+        return _sharded_fused(s_img, s_txt, t_img, t_txt, temperature, w_img, w_txt, w_con, grad_scale, need_grad, group, comm)
     ops = ops or CudaLossOps(path)
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -306,9 +310,42 @@ def _fused_sharded_ok(x, temperature, path):
             and lib.dclip_device_supports_tensor_path(x.device.index or 0) == 1)
 
 
-def _sharded_fused(s_img, s_txt, t_img, t_txt, temperature, w_img, w_txt, w_con, grad_scale, need_grad, group):
+_PEER_BUFFERS = {}
+
+
+def _peer_buffer(group, m, n, d, world, dev):
+    """Symmetric buffer of one (group, shape): u_all | v_all [n, d] fp16, stat [world, 2m + 4] fp32, flags.
+    Returns None (and remembers it) when the peer mapping cannot be established on this system."""
+    import os
+    import warnings
+
+    import torch.distributed as dist
+    key = (id(group), m, n, d, dev.index)
+    if key not in _PEER_BUFFERS:
+        from .peer import PeerBuffer
+        ops_bytes = (n * d * 2 + 255) // 256 * 256
+        stat_bytes = world * (2 * m + 4) * 4
+        buf, ok = None, 1
+        try:
+            buf = PeerBuffer(2 * ops_bytes + stat_bytes, dev, group)
+        except RuntimeError as e:                                   # e.g. cudaIpc not permitted in this container
+            warnings.warn(f"dclip_b200: peer-memory exchange unavailable ({e}); using NCCL all-gathers")
+            ok = 0
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)    # all ranks or none
+        if int(flag) == 0:
+            buf = None
+        _PEER_BUFFERS[key] = (buf, ops_bytes)
+    return _PEER_BUFFERS[key]
+
+
+def _sharded_fused(s_img, s_txt, t_img, t_txt, temperature, w_img, w_txt, w_con, grad_scale, need_grad, group, comm="auto"):
     """Per-rank step on the fused C-ABI phases: prep -> [all-gather u, v] -> forward + local statistics ->
-    [all-gather stats] -> global losses + backward + gradient tail."""
+    [all-gather stats] -> global losses + backward + gradient tail.  The two exchanges are either pushes through
+    NVLink peer memory (comm = "p2p": dclip_p2p_push / dclip_p2p_wait, 5 extra small kernels, no collective) or
+    NCCL all-gathers."""
+    import os
+
     import torch.distributed as dist
 
     lib = _lib.load_library()
@@ -319,10 +356,23 @@ def _sharded_fused(s_img, s_txt, t_img, t_txt, temperature, w_img, w_txt, w_con,
     n = m * world
     row_offset = rank * m
     f32 = dict(dtype=torch.float32, device=dev)
-    ops_all = torch.empty((2, n, d), dtype=torch.float16, device=dev)
-    u_all, v_all = ops_all[0], ops_all[1]
+    if comm == "auto":
+        comm = os.environ.get("DCLIP_SHARDED_COMM", "p2p")
+    pb = None
+    if world > 1 and comm == "p2p" and m % 2 == 0:
+        pb, ops_bytes = _peer_buffer(group, m, n, d, world, dev)
+    stride = 2 * m + 4
+    if pb is not None:
+        import ctypes
+        from .peer import KIND_DONE, KIND_OPERANDS, KIND_STATS
+        p_u, p_v, p_stat = pb.ptr(0), pb.ptr(ops_bytes), pb.ptr(2 * ops_bytes)
+        p_stat_row = pb.ptr(2 * ops_bytes + rank * stride * 4)
+    else:
+        ops_all = torch.empty((2, n, d), dtype=torch.float16, device=dev)
+        u_all, v_all = ops_all[0], ops_all[1]
+        stat = torch.empty((world, stride), **f32)
+        p_u, p_v, p_stat, p_stat_row = ptr(u_all), ptr(v_all), ptr(stat), ptr(stat[rank])
     vecs = torch.empty((5, m), **f32)                       # inv_u, inv_v, cos_img, cos_txt, diag
-    stat = torch.empty((world, 2 * m + 4), **f32)
     losses = torch.empty(4, **f32)
     d_img = torch.empty_like(s_img) if need_grad else None
     d_txt = torch.empty_like(s_txt) if need_grad else None
@@ -331,20 +381,30 @@ def _sharded_fused(s_img, s_txt, t_img, t_txt, temperature, w_img, w_txt, w_con,
     with torch.cuda.device(dev):
         st = stream_ptr(dev)
         check(lib.dclip_sharded_loss_prep(ptr(s_img), ptr(s_txt), ptr(t_img), ptr(t_txt), m, d, dtype_code(s_img),
-                                          float(temperature), ptr(u_all), ptr(v_all), row_offset, ptr(vecs[0]), ptr(vecs[1]),
+                                          float(temperature), p_u, p_v, row_offset, ptr(vecs[0]), ptr(vecs[1]),
                                           ptr(vecs[2]), ptr(vecs[3]), ptr(vecs[4]), st), "sharded_loss_prep")
-        if world > 1:
+        if pb is not None:
+            rows = (row_offset * d * 2, m * d * 2)
+            # my rows -> every peer (after the peers have finished reading the previous step's operands)
+            pb.push([rows, (ops_bytes + rows[0], rows[1])], KIND_DONE, KIND_OPERANDS)
+            pb.wait(KIND_OPERANDS)
+        elif world > 1:
             dist.all_gather_into_tensor(u_all, u_all[row_offset:row_offset + m], group=group)
             dist.all_gather_into_tensor(v_all, v_all[row_offset:row_offset + m], group=group)
-        check(lib.dclip_sharded_loss_fwd(ptr(u_all), ptr(v_all), m, n, d, float(temperature), row_offset,
+        check(lib.dclip_sharded_loss_fwd(p_u, p_v, m, n, d, float(temperature), row_offset,
                                          ptr(vecs[2]) if has_t else None, ptr(vecs[3]) if has_t else None, ptr(vecs[4]),
-                                         ptr(stat[rank]), ptr(ws), ws.numel(), st), "sharded_loss_fwd")
-        if world > 1:
+                                         p_stat_row, ptr(ws), ws.numel(), st), "sharded_loss_fwd")
+        if pb is not None:
+            pb.push([(2 * ops_bytes + rank * stride * 4, stride * 4)], -1, KIND_STATS)
+            pb.wait(KIND_STATS)
+        elif world > 1:
             dist.all_gather_into_tensor(stat.view(-1), stat[rank], group=group)
-        check(lib.dclip_sharded_loss_bwd(ptr(s_img), ptr(s_txt), ptr(t_img), ptr(t_txt), ptr(u_all), ptr(v_all), m, n, d,
-                                         dtype_code(s_img), float(temperature), row_offset, rank, world, ptr(stat), ptr(vecs[0]),
+        check(lib.dclip_sharded_loss_bwd(ptr(s_img), ptr(s_txt), ptr(t_img), ptr(t_txt), p_u, p_v, m, n, d,
+                                         dtype_code(s_img), float(temperature), row_offset, rank, world, p_stat, ptr(vecs[0]),
                                          ptr(vecs[1]), float(w_img), float(w_txt), float(w_con), float(grad_scale), ptr(losses),
                                          ptr(d_img), ptr(d_txt), ptr(ws), ws.numel(), st), "sharded_loss_bwd")
+        if pb is not None:
+            pb.push([], -1, KIND_DONE)           # my reads of this step's operands / statistics are stream-ordered before this
     return losses, d_img, d_txt
 
 

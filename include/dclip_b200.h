@@ -149,6 +149,29 @@ int dclip_sharded_loss_bwd(const void* s_img, const void* s_txt, const void* t_i
                            void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Push-based exchange over NVLink peer memory (replaces NCCL's all-gathers in the data-parallel objective;
+ * "all-gather of the normalised operands", "all-gather of the LSE vectors").
+ * Every rank allocates ONE symmetric buffer (same layout everywhere) that also holds a flag block of
+ * dclip_p2p_flags_bytes() at `flags_offset`; the 64-byte handles are exchanged by the host (torch.distributed)
+ * and opened in every peer process.  peer_bases[r] = address of rank r's buffer in THIS process
+ * (peer_bases[rank] = the local allocation).
+ *   push:  optional wait on `wait_kind` (all peers), copy `nranges` byte ranges of the local buffer to the same
+ *          offsets of every peer, then bump arrive[signal_kind][rank] on every peer (nranges = 0: signal only)
+ *   wait:  block the stream until every peer has pushed `kind` once more than this rank has consumed so far
+ * Kinds are small integers (0..3) chosen by the caller.  Everything is asynchronous on `stream` and can be
+ * captured in a CUDA graph.  Waits time out after 10 s (dclip_debug_pipeline_error reports it).
+ */
+size_t dclip_p2p_flags_bytes(void);
+int dclip_p2p_alloc(size_t bytes, void** dev_ptr, unsigned char* handle64);
+int dclip_p2p_init_flags(void* base, size_t flags_offset, int credit_kind);
+int dclip_p2p_open(const unsigned char* handle64, void** dev_ptr);
+int dclip_p2p_close(void* dev_ptr);
+int dclip_p2p_free(void* dev_ptr);
+int dclip_p2p_push(void* const* peer_bases, int world, int rank, const size_t* offsets, const size_t* bytes, int nranges,
+                   size_t flags_offset, int wait_kind, int signal_kind, void* stream);
+int dclip_p2p_wait(void* local_base, size_t flags_offset, int world, int rank, int kind, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Retrieval   (replaces the similarity build + calculate_retrieval_metrics,
  *   eval_scripts/flickr30k_eval.py:243-266 and :16-88, and the faiss IndexFlatIP add/search
  *   used by training/compute_faiss.py:27,79 and training/image_tokenizer.py:262)

@@ -26,6 +26,22 @@ def main():
         loc = [t[rank * m:(rank + 1) * m].contiguous() for t in full]
         losses, di, dt = L.sharded_distill_loss_fwd_bwd(*loc, path=path)       # fused phases on the tensor path
         torch.cuda.synchronize()
+        if path == "tensor":
+            # the same fused phases with NCCL all-gathers instead of the peer-memory pushes: bit-identical
+            l3, di3, dt3 = L.sharded_distill_loss_fwd_bwd(*loc, path=path, comm="nccl")
+            torch.cuda.synchronize()
+            assert torch.equal(l3, losses) and torch.equal(di3, di) and torch.equal(dt3, dt), "p2p vs nccl exchange differ"
+            for _ in range(20):                                                  # flag counters over many steps
+                l4, di4, dt4 = L.sharded_distill_loss_fwd_bwd(*loc, path=path)
+            torch.cuda.synchronize()
+            assert torch.equal(l4, losses) and torch.equal(di4, di)
+            graphed = L.GraphedStep(lambda *a: L.sharded_distill_loss_fwd_bwd(*a, path=path), loc)
+            for _ in range(5):
+                l5, di5, dt5 = graphed(*loc)
+            torch.cuda.synchronize()
+            assert torch.equal(l5, losses) and torch.equal(di5, di) and torch.equal(dt5, dt)
+            from dclip_b200 import _lib
+            assert _lib.load_library().dclip_debug_pipeline_error(_lib.stream_ptr(dev)) == 0, "pipeline / peer wait timed out"
         if path == "tensor":                                                     # generic building-block choreography
             l2, di2, dt2 = L.sharded_distill_loss_fwd_bwd(*loc, path=path, ops=L.CudaLossOps("tensor"))
             torch.cuda.synchronize()
