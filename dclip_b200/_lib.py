@@ -60,7 +60,7 @@ SIGNATURES = {
     "dclip_p2p_close": (_i32, [_vp]),
     "dclip_p2p_free": (_i32, [_vp]),
     "dclip_p2p_push": (_i32, [ctypes.POINTER(ctypes.c_void_p), _i32, _i32, ctypes.POINTER(_sz), ctypes.POINTER(_sz), _i32, _sz, _i32,
-                              _i32, _vp]),
+                              _i32, _i32, _vp]),
     "dclip_p2p_wait": (_i32, [_vp, _sz, _i32, _i32, _i32, _vp]),
     "dclip_normalize_rows": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp]),
     "dclip_pair_scores": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp]),

@@ -212,12 +212,13 @@ int dclip_tensor_path_ready(void) { return DCLIP_TENSOR_PATH_READY; }
 int dclip_debug_pipeline_error(void* stream) { return tc_check_error_flag(static_cast<cudaStream_t>(stream)); }
 
 int dclip_distill_loss_launch_count(int64_t m, int64_t n, int64_t d, int path, int sharded) {
-    (void)m; (void)n; (void)d;
     path = resolve_loss_path(path, DCLIP_F32);
     if (path == DCLIP_PATH_FP32) return sharded ? 11 : 6;   // prep, rowlse+combine, sums, grad, tail (x2 sides when sharded)
-    // tensor path: prep, fwd tiles, 2 lse combines, diag, sums, bwd tiles, (grad combine), 2 tails
-    if (!sharded) return 5 + (tc_nsplit(m, n, d, 2) > 1 ? 2 : 0);   // prep_pair, fwd tiles, finalize, bwd tiles, tail
-    return 2 + 2 * 3 + 1 + 2 * (1 + (tc_nsplit(m, n, d, 1) > 1 ? 1 : 0)) + 2;
+    // tensor path, single GPU: prep_pair, one-pass forward tiles, finalize, backward tiles (+ partial combines), tail
+    if (!sharded) return 5 + (tc_nsplit(m, n, d, 2) > 1 ? 2 : 0);
+    // fused sharded phases: prep, forward tiles, finalize, global losses, backward tiles (+ combine), tail
+    // + the three peer-memory pushes (operands, statistics, step-done) that replace the NCCL all-gathers
+    return 6 + (tc_nsplit(m, n, d, 2) > 1 ? 1 : 0) + 3;
 }
 
 // ---- fused per-rank phases of the sharded objective (tensor path) -----------------------------

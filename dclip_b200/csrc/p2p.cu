@@ -34,6 +34,7 @@ struct PushArgs {
     int nranges, world, rank;
     size_t flags_offset;
     int wait_kind, signal_kind;
+    int wait_after;       // 1: the kernel also waits until every peer's push of `signal_kind` has landed HERE (push + wait in one launch)
     int* error_flag;
 };
 
@@ -96,6 +97,19 @@ __global__ void __launch_bounds__(256) k_p2p_push(const PushArgs a) {
             if (a.wait_kind >= 0) mine->expected[a.wait_kind] += 1;
             mine->done_ctr = 0;
             __threadfence_system();
+            s_ok = 2;                  // this block is the last one
+        }
+    }
+    __syncthreads();
+    if (a.wait_after && a.signal_kind >= 0 && s_ok == 2) {
+        // the kernel (hence the stream) does not proceed before the peers' pushes of the same kind are here
+        if (threadIdx.x < 32) {
+            const unsigned int target = ld_volatile_sys(&mine->expected[a.signal_kind]) + 1;
+            const bool ok = wait_arrivals(mine, a.signal_kind, target, a.world, a.rank, threadIdx.x);
+            if (!__all_sync(0xffffffffu, ok) && threadIdx.x == 0 && a.error_flag) atomicExch(a.error_flag, 1);
+            __threadfence_system();
+            __syncwarp();
+            if (threadIdx.x == 0) mine->expected[a.signal_kind] += 1;
         }
     }
 }
@@ -165,7 +179,7 @@ int dclip_p2p_free(void* dev_ptr) {
 }
 
 int dclip_p2p_push(void* const* peer_bases, int world, int rank, const size_t* offsets, const size_t* bytes, int nranges,
-                   size_t flags_offset, int wait_kind, int signal_kind, void* stream) {
+                   size_t flags_offset, int wait_kind, int signal_kind, int wait_after, void* stream) {
     using namespace dclip;
     DCLIP_REQUIRE(peer_bases && world >= 1 && world <= kP2PMaxWorld && rank >= 0 && rank < world, "p2p_push: bad world / rank");
     DCLIP_REQUIRE(nranges >= 0 && nranges <= kP2PMaxRanges && wait_kind < kP2PKinds && signal_kind < kP2PKinds, "p2p_push: bad ranges / kinds");
@@ -181,7 +195,7 @@ int dclip_p2p_push(void* const* peer_bases, int world, int rank, const size_t* o
         total += bytes[r];
     }
     a.nranges = nranges; a.world = world; a.rank = rank; a.flags_offset = flags_offset;
-    a.wait_kind = wait_kind; a.signal_kind = signal_kind; a.error_flag = tc_error_flag();
+    a.wait_kind = wait_kind; a.signal_kind = signal_kind; a.wait_after = wait_after; a.error_flag = tc_error_flag();
     int blocks = (int)ceil_div((int64_t)(total / 16), 256 * 4);
     if (blocks < 1) blocks = 1;
     if (blocks > 2 * sm_count()) blocks = 2 * sm_count();

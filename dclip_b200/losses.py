@@ -342,7 +342,7 @@ def _peer_buffer(group, m, n, d, world, dev):
 def _sharded_fused(s_img, s_txt, t_img, t_txt, temperature, w_img, w_txt, w_con, grad_scale, need_grad, group, comm="auto"):
     """Per-rank step on the fused C-ABI phases: prep -> [all-gather u, v] -> forward + local statistics ->
     [all-gather stats] -> global losses + backward + gradient tail.  The two exchanges are either pushes through
-    NVLink peer memory (comm = "p2p": dclip_p2p_push / dclip_p2p_wait, 5 extra small kernels, no collective) or
+    NVLink peer memory (comm = "p2p": dclip_p2p_push, 3 extra small kernels, no collective) or
     NCCL all-gathers."""
     import os
 
@@ -386,8 +386,7 @@ def _sharded_fused(s_img, s_txt, t_img, t_txt, temperature, w_img, w_txt, w_con,
         if pb is not None:
             rows = (row_offset * d * 2, m * d * 2)
             # my rows -> every peer (after the peers have finished reading the previous step's operands)
-            pb.push([rows, (ops_bytes + rows[0], rows[1])], KIND_DONE, KIND_OPERANDS)
-            pb.wait(KIND_OPERANDS)
+            pb.push([rows, (ops_bytes + rows[0], rows[1])], KIND_DONE, KIND_OPERANDS, wait_after=True)
         elif world > 1:
             dist.all_gather_into_tensor(u_all, u_all[row_offset:row_offset + m], group=group)
             dist.all_gather_into_tensor(v_all, v_all[row_offset:row_offset + m], group=group)
@@ -395,8 +394,7 @@ def _sharded_fused(s_img, s_txt, t_img, t_txt, temperature, w_img, w_txt, w_con,
                                          ptr(vecs[2]) if has_t else None, ptr(vecs[3]) if has_t else None, ptr(vecs[4]),
                                          p_stat_row, ptr(ws), ws.numel(), st), "sharded_loss_fwd")
         if pb is not None:
-            pb.push([(2 * ops_bytes + rank * stride * 4, stride * 4)], -1, KIND_STATS)
-            pb.wait(KIND_STATS)
+            pb.push([(2 * ops_bytes + rank * stride * 4, stride * 4)], -1, KIND_STATS, wait_after=True)
         elif world > 1:
             dist.all_gather_into_tensor(stat.view(-1), stat[rank], group=group)
         check(lib.dclip_sharded_loss_bwd(ptr(s_img), ptr(s_txt), ptr(t_img), ptr(t_txt), p_u, p_v, m, n, d,

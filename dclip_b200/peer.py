@@ -50,13 +50,14 @@ class PeerBuffer:
     def ptr(self, offset=0):
         return ctypes.c_void_p(self.base + offset)
 
-    def push(self, ranges, wait_kind, signal_kind):
-        """ranges: [(offset, nbytes), ...] of the local buffer, written to the same offsets of every peer."""
+    def push(self, ranges, wait_kind, signal_kind, wait_after=False):
+        """ranges: [(offset, nbytes), ...] of the local buffer, written to the same offsets of every peer.
+        wait_after: the same launch also waits for every peer's push of `signal_kind` (= an all-gather)."""
         n = len(ranges)
         offs = (ctypes.c_size_t * max(n, 1))(*[o for o, _ in ranges])
         lens = (ctypes.c_size_t * max(n, 1))(*[b for _, b in ranges])
         check(self.lib.dclip_p2p_push(self._peer_arr, self.world, self.rank, offs, lens, n, self.flags_offset, wait_kind, signal_kind,
-                                      stream_ptr(self.device)), "p2p_push")
+                                      1 if wait_after else 0, stream_ptr(self.device)), "p2p_push")
 
     def wait(self, kind):
         check(self.lib.dclip_p2p_wait(ctypes.c_void_p(self.base), self.flags_offset, self.world, self.rank, kind, stream_ptr(self.device)),

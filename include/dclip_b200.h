@@ -156,7 +156,8 @@ int dclip_sharded_loss_bwd(const void* s_img, const void* s_txt, const void* t_i
  * and opened in every peer process.  peer_bases[r] = address of rank r's buffer in THIS process
  * (peer_bases[rank] = the local allocation).
  *   push:  optional wait on `wait_kind` (all peers), copy `nranges` byte ranges of the local buffer to the same
- *          offsets of every peer, then bump arrive[signal_kind][rank] on every peer (nranges = 0: signal only)
+ *          offsets of every peer, then bump arrive[signal_kind][rank] on every peer (nranges = 0: signal only);
+ *          wait_after = 1 also performs the wait below for `signal_kind` inside the same launch (all-gather)
  *   wait:  block the stream until every peer has pushed `kind` once more than this rank has consumed so far
  * Kinds are small integers (0..3) chosen by the caller.  Everything is asynchronous on `stream` and can be
  * captured in a CUDA graph.  Waits time out after 10 s (dclip_debug_pipeline_error reports it).
@@ -168,7 +169,7 @@ int dclip_p2p_open(const unsigned char* handle64, void** dev_ptr);
 int dclip_p2p_close(void* dev_ptr);
 int dclip_p2p_free(void* dev_ptr);
 int dclip_p2p_push(void* const* peer_bases, int world, int rank, const size_t* offsets, const size_t* bytes, int nranges,
-                   size_t flags_offset, int wait_kind, int signal_kind, void* stream);
+                   size_t flags_offset, int wait_kind, int signal_kind, int wait_after, void* stream);
 int dclip_p2p_wait(void* local_base, size_t flags_offset, int world, int rank, int kind, void* stream);
 
 /* ------------------------------------------------------------------------------------------
