@@ -62,6 +62,9 @@ struct TcArgs {
     float* cand_s;        // retrieval mode: [nsplit][m][32] approximate scores (descending)
     int32_t* cand_i;      //                 [nsplit][m][32] gallery rows (-1 = empty)
     float* col_out;       // stream mode 1: partial column sums [ceil(m / 128)][n]
+    // stream kernel: soft lockstep of concurrently running CTAs (keeps the Y tiles they share inside L2); null = off
+    unsigned int* sync_ctr;   // [groups][sync_epochs], zeroed before the launch
+    int sync_every, sync_group, sync_epochs;
     int debug_skip;       // timing experiments only (results are garbage): 1 = no phase-1 MMAs, 2 = no phase-2 MMAs, 4 = no G stores
 };
 
@@ -81,6 +84,8 @@ int tc_check_error_flag(cudaStream_t st);
 int stream_nsplit(int64_t m, int64_t n, int nsides);
 int launch_stream_tc(int mode, int nsides, const void* const x[2], const void* const y[2], const TcArgs& args, int nsplit,
                      cudaStream_t st);
+// lockstep counters the streaming kernel wants for this problem (0 = lockstep not used); see stream_tc.cu
+size_t stream_sync_bytes(int64_t m, int64_t n, int64_t d, int nsplit);
 
 int launch_loss_prep(const PrepArgs& a, int nsides, int dtype, int op_dtype, cudaStream_t st);
 // both sides of row i in one warp + diag[i] = u_hat_i . v_hat_i / tau from the rounded operands

@@ -179,6 +179,7 @@ size_t dclip_topk_ip_tc_workspace_bytes(int64_t nq, int64_t ng, int64_t d, int q
     total += align_up((size_t)nq * d * 2, 256);                       // fp16 queries
     total += 2 * align_up((size_t)ns * nq * kCand * 4, 256);          // per-split candidates
     total += 2 * align_up((size_t)nq * kCand * 4, 256);               // merged candidates
+    total += align_up(stream_sync_bytes(nq, ng, d, ns), 256);         // lockstep counters of the streaming kernel
     (void)q_dtype;
     return total + 1024;
 }
@@ -205,6 +206,8 @@ int dclip_topk_ip_tc(const void* q, int q_dtype, const void* g_exact, int g_dtyp
     int32_t* pi = static_cast<int32_t*>(ws.take((size_t)ns * nq * kCand * 4));
     float* ms = static_cast<float*>(ws.take((size_t)nq * kCand * 4));
     int32_t* mi = static_cast<int32_t*>(ws.take((size_t)nq * kCand * 4));
+    const size_t sync_bytes = stream_sync_bytes(nq, ng, d, ns);
+    unsigned int* sync_ctr = sync_bytes ? static_cast<unsigned int*>(ws.take(sync_bytes)) : nullptr;
     if (!ws.ok()) return fail(DCLIP_ERR_WORKSPACE, "topk_ip_tc: workspace too small (%zu < %zu)", workspace_bytes, ws.used);
     const void* qh = q;
     if (q_dtype != DCLIP_F16) {
@@ -215,6 +218,7 @@ int dclip_topk_ip_tc(const void* q, int q_dtype, const void* g_exact, int g_dtyp
     TcArgs a{};
     a.m = nq; a.n = ng; a.d = d; a.inv_tau = 1.f; a.row_offset = 0;
     a.cand_s = ps; a.cand_i = pi;
+    a.sync_ctr = sync_ctr;
     const void* xs[2] = {qh, qh};
     const void* ys[2] = {g_fp16, g_fp16};
     if (int e = launch_stream_tc(2, 1, xs, ys, a, ns, st)) return e;

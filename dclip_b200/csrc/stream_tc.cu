@@ -135,6 +135,19 @@ k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CU
                         if (pt % (int)gridDim.x == (int)blockIdx.x)
                             for (int k2 = 0; k2 < nkb; ++k2) tma_prefetch_l2_2d(tmy, k2 * 64, (int32_t)((t_begin + pt) * SN_COLS));
                 }
+                if (a.sync_ctr && kb == 0 && tile % a.sync_every == 0) {
+                    // soft lockstep: CTAs that run concurrently (same group of consecutive block ids) walk the gallery at
+                    // the same pace, so a Y tile fetched from HBM once serves all of them out of L2.  Purely a
+                    // performance device: the wait is bounded (~100 us) and the result never depends on it.
+                    const unsigned lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+                    const unsigned grp = lin / (unsigned)a.sync_group;
+                    const unsigned total = gridDim.x * gridDim.y * gridDim.z;
+                    const unsigned members = min((unsigned)a.sync_group, total - grp * (unsigned)a.sync_group);
+                    unsigned int* c = a.sync_ctr + (size_t)grp * a.sync_epochs + tile / a.sync_every;
+                    atomicAdd(c, 1u);
+                    const long long t0 = clock64();
+                    while (*reinterpret_cast<volatile unsigned int*>(c) < members && clock64() - t0 < 200000) __nanosleep(200);
+                }
                 SPROF_BEGIN(p_em);
                 ok = mbar_wait(&empty[warp], phase ^ 1, kSpinS);
                 if (warp == 0) SPROF_END(p_em, 5);
@@ -339,6 +352,11 @@ k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CU
         }
     }
     if (!ok && lane == 0 && a.error_flag) atomicExch(a.error_flag, 1);
+    if (a.sync_ctr && threadIdx.x == 0) {   // epochs this CTA never reaches (shorter column range): count it as arrived
+        const unsigned lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+        unsigned int* c = a.sync_ctr + (size_t)(lin / (unsigned)a.sync_group) * a.sync_epochs;
+        for (int e = (T + a.sync_every - 1) / a.sync_every; e < a.sync_epochs; ++e) atomicAdd(c + e, 1u);
+    }
     fence_before_thread_sync();
     __syncthreads();
     if (kPair) cluster_sync_all();          // no CTA leaves while its peer can still signal its barriers / read its operands
@@ -371,6 +389,18 @@ int stream_nsplit(int64_t m, int64_t n, int nsides) {
 
 int* tc_error_flag();   // loss_tc.cu
 
+// Lockstep is worth it when the Y operand does not fit in L2 and several waves of CTAs stream it: one group =
+// one wave of SM-count consecutive CTAs, one epoch = 64 tiles (25 MB of Y at d = 768).
+constexpr int kSyncEvery = 64;
+size_t stream_sync_bytes(int64_t m, int64_t n, int64_t d, int nsplit) {
+    if (n * d * 2 <= (int64_t)96 * 1024 * 1024) return 0;
+    const int64_t ctas = (ceil_div(m, SM_ROWS) + 1) / 2 * 2 * nsplit;
+    if (ctas < 2 * sm_count()) return 0;
+    const int64_t groups = ceil_div(ctas, sm_count());
+    const int64_t epochs = ceil_div(ceil_div(ceil_div(n, SN_COLS), nsplit), kSyncEvery);
+    return (size_t)(groups * epochs) * sizeof(unsigned int);
+}
+
 // mode 0: x/y per side are the fp16 operands, a.s[side].out = partial row sums [nsplit][m]
 // mode 1: one side; additionally a.col_out = partial column sums [ceil(m / 128)][n]
 // mode 2: a.cand_s / a.cand_i = candidate lists [nsplit][m][32]
@@ -390,6 +420,16 @@ int launch_stream_tc(int mode, int nsides, const void* const x[2], const void* c
     const int64_t ntiles = ceil_div(a.n, SN_COLS);
     a.tiles_per_split = (int)ceil_div(ntiles, nsplit);
     a.error_flag = tc_error_flag();
+    if (a.sync_ctr) {                       // caller provided stream_sync_bytes() of counters: zero them, fill in the geometry
+        const size_t sb = stream_sync_bytes(a.m, a.n, a.d, nsplit);
+        static const bool no_sync = [] { const char* e = getenv("DCLIP_STREAM_NOSYNC"); return e && e[0] == '1'; }();
+        if (sb == 0 || !pair || nsides != 1 || no_sync) a.sync_ctr = nullptr;
+        else {
+            DCLIP_CUDA_OK(cudaMemsetAsync(a.sync_ctr, 0, sb, st));
+            a.sync_every = kSyncEvery; a.sync_group = sm_count();
+            a.sync_epochs = (int)ceil_div(a.tiles_per_split, kSyncEvery);
+        }
+    }
     if (mode == 1 && (!a.col_out || nsides != 1)) return fail(DCLIP_ERR_INVALID, "stream_tc: mode 1 is single-sided and needs col_out");
     const size_t smem = 1024 + (size_t)stream_stages(pair) * stream_stage_bytes(pair) +
                         (mode == 2 ? 2 * kListLen * SM_ROWS * 4 : mode == 1 ? 2 * 4 * SN_COLS * 4 : 0) + 256;
