@@ -390,14 +390,17 @@ int stream_nsplit(int64_t m, int64_t n, int nsides) {
 int* tc_error_flag();   // loss_tc.cu
 
 // Lockstep is worth it when the Y operand does not fit in L2 and several waves of CTAs stream it: one group =
-// one wave of SM-count consecutive CTAs, one epoch = 64 tiles (25 MB of Y at d = 768).
-constexpr int kSyncEvery = 64;
+// one wave of SM-count consecutive CTAs, one epoch = sync_every() tiles.
+static int sync_every() {      // tiles per lockstep epoch (DCLIP_STREAM_SYNC_EVERY overrides; 64 tiles = 25 MB of Y at d = 768)
+    static const int v = [] { const char* e = getenv("DCLIP_STREAM_SYNC_EVERY"); const int x = e ? atoi(e) : 0; return x > 0 ? x : 64; }();
+    return v;
+}
 size_t stream_sync_bytes(int64_t m, int64_t n, int64_t d, int nsplit) {
     if (n * d * 2 <= (int64_t)96 * 1024 * 1024) return 0;
     const int64_t ctas = (ceil_div(m, SM_ROWS) + 1) / 2 * 2 * nsplit;
     if (ctas < 2 * sm_count()) return 0;
     const int64_t groups = ceil_div(ctas, sm_count());
-    const int64_t epochs = ceil_div(ceil_div(ceil_div(n, SN_COLS), nsplit), kSyncEvery);
+    const int64_t epochs = ceil_div(ceil_div(ceil_div(n, SN_COLS), nsplit), sync_every());
     return (size_t)(groups * epochs) * sizeof(unsigned int);
 }
 
@@ -426,8 +429,8 @@ int launch_stream_tc(int mode, int nsides, const void* const x[2], const void* c
         if (sb == 0 || !pair || nsides != 1 || no_sync) a.sync_ctr = nullptr;
         else {
             DCLIP_CUDA_OK(cudaMemsetAsync(a.sync_ctr, 0, sb, st));
-            a.sync_every = kSyncEvery; a.sync_group = sm_count();
-            a.sync_epochs = (int)ceil_div(a.tiles_per_split, kSyncEvery);
+            a.sync_every = sync_every(); a.sync_group = sm_count();
+            a.sync_epochs = (int)ceil_div(a.tiles_per_split, sync_every());
         }
     }
     if (mode == 1 && (!a.col_out || nsides != 1)) return fail(DCLIP_ERR_INVALID, "stream_tc: mode 1 is single-sided and needs col_out");
