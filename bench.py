@@ -62,7 +62,7 @@ def load_peaks():
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons through NVML while the timed region runs."""
 
-    def __init__(self, index=0, period=0.05):
+    def __init__(self, index=0, period=0.002):      # the timed loop lasts only tens of ms: sample every 2 ms
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
