@@ -32,6 +32,19 @@ def run(B, T, R, d, dtype, cpu=False):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
     line = f"teacher step B={B} T={T} R={R} d={d} {dtype}: {ms:.3f} ms/step = {B/ms*1e3:.0f} pairs/s"
+    # the same step replayed as one CUDA graph
+    from dclip_b200.patch_text_aggregation import GraphedTeacherStep
+    ref_grads = [p.grad.clone() for p in m.parameters()]
+    ref_loss = float(step())
+    gs = GraphedTeacherStep(m, lambda mod, t, i, x: L.compute_contrastive_loss(mod.global_embedding(t, i), x, path="fp32"), [tg, ig, xg])
+    for _ in range(3): gs(tg, ig, xg)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(n): gl = gs(tg, ig, xg)
+    e1.record(); torch.cuda.synchronize()
+    gms = e0.elapsed_time(e1) / n
+    same = all(torch.equal(a, p.grad) for a, p in zip(ref_grads, m.parameters())) and float(gl) == ref_loss
+    line += f" | CUDA graph: {gms:.3f} ms/step (bit-identical to eager: {same})"
     if cpu:
         torch.set_num_threads(os.cpu_count())
         om.teacher_step(params, text, image, txt)
