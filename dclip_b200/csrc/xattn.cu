@@ -385,15 +385,28 @@ __device__ __forceinline__ float block_sum(float v, float* red) {   // kAggThrea
     return t;
 }
 
+// The kernels make several passes over x[b] (L x d); staged once into shared memory when it fits (16-byte
+// coalesced loads), every later pass reads shared memory instead of L dependent global loads per column.
+template <typename T>
+__device__ __forceinline__ const T* agg_stage(const T* xb, int L, int d, void* stage_raw, bool staged) {
+    if (!staged) return xb;
+    const size_t n16 = (size_t)L * d * sizeof(T) / 16;
+    const uint4* src = reinterpret_cast<const uint4*>(xb);
+    uint4* dst = reinterpret_cast<uint4*>(stage_raw);
+    for (size_t i = threadIdx.x; i < n16; i += kAggThreads) dst[i] = __ldg(src + i);
+    __syncthreads();
+    return reinterpret_cast<const T*>(stage_raw);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kAggThreads) k_aggregate_fwd(const T* __restrict__ x, int L, int d, float temperature, T* __restrict__ out,
-                                                       float* __restrict__ w_saved) {
-    extern __shared__ float sm[];
+                                                       float* __restrict__ w_saved, int staged) {
+    extern __shared__ __align__(16) float sm[];
     float* mean = sm;            // [d]
     float* cs = mean + d;        // [L]
     float* red = cs + L;         // [32]
     const int b = blockIdx.x;
-    const T* xb = x + (size_t)b * L * d;
+    const T* xb = agg_stage<T>(x + (size_t)b * L * d, L, d, sm + (((size_t)d + L + 32 + 3) & ~(size_t)3), staged != 0);
     float part = 0.f;
     for (int c = threadIdx.x; c < d; c += kAggThreads) {
         float s = 0.f;
@@ -431,16 +444,16 @@ __global__ void __launch_bounds__(kAggThreads) k_aggregate_fwd(const T* __restri
 
 template <typename T>
 __global__ void __launch_bounds__(kAggThreads) k_aggregate_bwd(const T* __restrict__ x, const float* __restrict__ w_saved, const T* __restrict__ dout,
-                                                       int L, int d, float temperature, T* __restrict__ dx) {
-    extern __shared__ float sm[];
+                                                       int L, int d, float temperature, T* __restrict__ dx, int staged) {
+    extern __shared__ __align__(16) float sm[];
     float* mean = sm;            // [d]
     float* dmean = mean + d;     // [d]
     float* cosv = dmean + d;     // [L]  cosine similarities
     float* nxs = cosv + L;       // [L]  clamped row norms
     float* dcs = nxs + L;        // [L]  d loss / d cos
-    float* red = dcs + L;        // [8]
+    float* red = dcs + L;        // [32]
     const int b = blockIdx.x;
-    const T* xb = x + (size_t)b * L * d;
+    const T* xb = agg_stage<T>(x + (size_t)b * L * d, L, d, sm + (((size_t)2 * d + 3 * L + 32 + 3) & ~(size_t)3), staged != 0);
     const T* dg = dout + (size_t)b * d;
     const float* w = w_saved + (size_t)b * L;
     float part = 0.f;
@@ -473,27 +486,38 @@ __global__ void __launch_bounds__(kAggThreads) k_aggregate_bwd(const T* __restri
     float sdot = 0.f;
     for (int l = 0; l < L; ++l) sdot = fmaf(w[l], dcs[l], sdot);
     __syncthreads();
-    for (int l = threadIdx.x; l < L; l += kAggThreads) dcs[l] = w[l] / temperature * (dcs[l] - sdot);
+    // per-row coefficients (no division left in the two L x d passes below):
+    //   dc_l = w_l / T (dw_l - sum w dw);  e_l = dc_l / (nx_l nm);  f_l = dc_l cos_l / nx_l^2 (0 if the row norm is clamped)
+    //   dmean_c = (sum_l e_l x_lc - mean_c S2) / L,  S2 = sum_l dc_l cos_l / nm^2 (0 if the mean norm is clamped)
+    //   dx_lc   = w_l dg_c + e_l mean_c - f_l x_lc + dmean_c
+    float* el = nxs;             // reuse: e_l   (after reading nxs below)
+    float* fl = cosv;            // reuse: f_l
+    float s2part = 0.f;
+    for (int l = threadIdx.x; l < L; l += kAggThreads) {
+        const float dc = w[l] / temperature * (dcs[l] - sdot);
+        const float nx = fabsf(nxs[l]);
+        const bool row_ok = nxs[l] > 0.f;
+        const float cosl = cosv[l];
+        s2part += m_clamped ? 0.f : dc * cosl / (nm * nm);
+        dcs[l] = dc;
+        el[l] = dc / (nx * nm);
+        fl[l] = row_ok ? dc * cosl / (nx * nx) : 0.f;
+    }
+    const float S2 = block_sum(s2part, red);
     __syncthreads();
-    // dmean[c] = sum_l dc_l (x_l[c] / (nx_l nm) - cos_l mean[c] / nm^2)
     for (int c = threadIdx.x; c < d; c += kAggThreads) {
         float s = 0.f;
-        for (int l = 0; l < L; ++l) {
-            const float nx = fabsf(nxs[l]);
-            float t = to_f32<T>(xb[(size_t)l * d + c]) / (nx * nm);
-            if (!m_clamped) t -= cosv[l] * mean[c] / (nm * nm);
-            s = fmaf(dcs[l], t, s);
-        }
-        dmean[c] = s / L;
+        for (int l = 0; l < L; ++l) s = fmaf(el[l], to_f32<T>(xb[(size_t)l * d + c]), s);
+        dmean[c] = (s - mean[c] * S2) / L;
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < L * d; idx += kAggThreads) {
-        const int l = idx / d, c = idx - l * d;
-        const float xv = to_f32<T>(xb[idx]);
-        const float nx = fabsf(nxs[l]);
-        float t = mean[c] / (nx * nm);
-        if (nxs[l] > 0.f) t -= cosv[l] * xv / (nx * nx);
-        dx[(size_t)b * L * d + idx] = from_f32<T>(w[l] * to_f32<T>(dg[c]) + dcs[l] * t + dmean[c]);
+    const int warp2 = threadIdx.x >> 5, lane2 = threadIdx.x & 31;
+    for (int l = warp2; l < L; l += kAggThreads / 32) {
+        const float wl = w[l], e = el[l], f = fl[l];
+        const T* xr = xb + (size_t)l * d;
+        T* dr = dx + ((size_t)b * L + l) * d;
+        for (int c = lane2; c < d; c += 32)
+            dr[c] = from_f32<T>(fmaf(wl, to_f32<T>(dg[c]), fmaf(e, mean[c], fmaf(-f, to_f32<T>(xr[c]), dmean[c]))));
     }
 }
 
@@ -904,12 +928,16 @@ int dclip_xattn_bwd(const void* text, const void* image, int64_t B, int64_t T, i
 int dclip_aggregate_fwd(const void* x, int64_t B, int64_t L, int64_t d, int dtype, float temperature, void* out, float* weights,
                         void* stream) {
     DCLIP_REQUIRE(x && out && B > 0 && L > 0 && d > 0 && temperature > 0.f, "aggregate_fwd: bad arguments");
-    const size_t sm = (size_t)(d + L + 32) * 4;
+    size_t sm = (((size_t)d + L + 32 + 3) & ~(size_t)3) * 4;
     if (sm > 200 * 1024) return fail(DCLIP_ERR_UNSUPPORTED, "aggregate_fwd: d + L too large");
+    const size_t rows = (size_t)L * d * dtype_size(dtype);
+    const int staged = rows % 16 == 0 && aligned16(x) && sm + rows <= 220 * 1024 ? 1 : 0;
+    if (staged) sm += rows;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     DCLIP_DISPATCH_DTYPE(dtype, {
         DCLIP_CUDA_OK(cudaFuncSetAttribute(k_aggregate_fwd<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        k_aggregate_fwd<T><<<(unsigned)B, kAggThreads, sm, st>>>(static_cast<const T*>(x), (int)L, (int)d, temperature, static_cast<T*>(out), weights);
+        k_aggregate_fwd<T><<<(unsigned)B, kAggThreads, sm, st>>>(static_cast<const T*>(x), (int)L, (int)d, temperature, static_cast<T*>(out), weights,
+                                                         staged);
     });
     DCLIP_LAUNCH_OK("k_aggregate_fwd");
     return DCLIP_OK;
@@ -918,13 +946,16 @@ int dclip_aggregate_fwd(const void* x, int64_t B, int64_t L, int64_t d, int dtyp
 int dclip_aggregate_bwd(const void* x, const float* weights, const void* d_out, int64_t B, int64_t L, int64_t d, int dtype,
                         float temperature, void* d_x, void* stream) {
     DCLIP_REQUIRE(x && weights && d_out && d_x && B > 0 && L > 0 && d > 0 && temperature > 0.f, "aggregate_bwd: bad arguments");
-    const size_t sm = (size_t)(2 * d + 3 * L + 32) * 4;
+    size_t sm = (((size_t)2 * d + 3 * L + 32 + 3) & ~(size_t)3) * 4;
     if (sm > 200 * 1024) return fail(DCLIP_ERR_UNSUPPORTED, "aggregate_bwd: d + L too large");
+    const size_t rows = (size_t)L * d * dtype_size(dtype);
+    const int staged = rows % 16 == 0 && aligned16(x) && sm + rows <= 220 * 1024 ? 1 : 0;
+    if (staged) sm += rows;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     DCLIP_DISPATCH_DTYPE(dtype, {
         DCLIP_CUDA_OK(cudaFuncSetAttribute(k_aggregate_bwd<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         k_aggregate_bwd<T><<<(unsigned)B, kAggThreads, sm, st>>>(static_cast<const T*>(x), weights, static_cast<const T*>(d_out), (int)L, (int)d,
-                                                         temperature, static_cast<T*>(d_x));
+                                                         temperature, static_cast<T*>(d_x), staged);
     });
     DCLIP_LAUNCH_OK("k_aggregate_bwd");
     return DCLIP_OK;
