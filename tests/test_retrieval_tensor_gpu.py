@@ -75,3 +75,35 @@ def test_index_flat_ip_auto_uses_tensor_and_stays_exact(built_library):
     assert index._tensor_gallery is not None          # the tensor path really ran
     ws, wi = orc.c_topk(q, gal, 3)
     assert np.array_equal(I, wi) and np.array_equal(D, ws)
+
+
+def test_pair_kernel_odd_row_blocks_matches_oracle(built_library):
+    """More than 128 queries run on CTA pairs (cta_group::2); 300 queries = 3 row blocks = a padded second pair,
+    and a gallery size that is not a multiple of the 256-row tile."""
+    from dclip_b200 import retrieval as R
+    gal, q, planted = synthetic.gallery_inputs(20001, 300, 128, seed=11)
+    gal, q = gal.astype(np.float16), q.astype(np.float16)
+    s, i = R.topk_ip(_d(q), _d(gal), 10, path="tensor")
+    torch.cuda.synchronize()
+    assert _pipeline_ok(built_library)
+    ws, wi = orc.c_topk(q.astype(np.float32), gal.astype(np.float32), 10)
+    assert np.array_equal(i.cpu().numpy(), wi)
+    assert np.array_equal(s.cpu().numpy(), ws)
+
+
+def test_lockstep_streaming_matches_fp32_path(built_library):
+    """Gallery larger than L2 (107 MB) and more than two waves of CTAs: the streaming kernel runs with its soft
+    lockstep barrier.  The barrier is a performance device only - results stay bit-identical to the FP32 path."""
+    from dclip_b200 import retrieval as R
+    ng, nq, d = 70000, 19000, 768
+    g = torch.randn(ng, d, device=DEV, generator=torch.Generator(device=DEV).manual_seed(5))
+    g = (g / g.norm(dim=1, keepdim=True)).half()
+    idx = torch.randint(0, ng, (nq,), device=DEV, generator=torch.Generator(device=DEV).manual_seed(6))
+    q = (g[idx].float() + 0.02 * torch.randn(nq, d, device=DEV)).half()
+    lib = built_library
+    assert lib.dclip_topk_ip_tc_workspace_bytes(nq, ng, d, 2) > 0
+    s1, i1 = R.topk_ip(q, g, 10, path="tensor")
+    s2, i2 = R.topk_ip(q, g, 10, path="fp32")
+    torch.cuda.synchronize()
+    assert _pipeline_ok(built_library)
+    assert torch.equal(i1, i2) and torch.equal(s1, s2)
