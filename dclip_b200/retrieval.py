@@ -185,6 +185,28 @@ def topk_ip(q, g, k, g_index_offset=0, path="auto", gallery=None):
     return _topk_fp32(q, g, k, g_index_offset)
 
 
+def zero_shot_topk_accuracy(image_features, text_features, labels, k=5, logit_scale=100.0):
+    """Zero-shot classification scoring (reference eval_scripts/test_zero_shot_ImageNet.py:79-108 and
+    CIFAR_zeroshot.py:93-122): `F.normalize(image_features)`, `100 * (img @ text.T)`,
+    `topk(5)`, top-1 / top-k hit counts - one top-k kernel call and a device-side comparison instead of the
+    matmul + topk + per-sample Python `label in indices[i]` loop.
+
+    image_features [n, d] un-normalised, text_features [classes, d] as the caller holds them (already
+    normalised in the reference), labels int64 [n].  Returns {"top1", "top5" (= top-k), "correct_top1",
+    "correct_topk", "values" [n,k] = logit_scale * score, "indices" [n,k]}; ties go to the lower class index."""
+    dev = require_cuda(image_features, text_features, labels)
+    n = image_features.shape[0]
+    k = min(int(k), text_features.shape[0])
+    img = torch.nn.functional.normalize(image_features.float(), dim=1)        # eps 1e-12, as the reference
+    scores, indices = topk_ip(img.contiguous(), text_features.float().contiguous(), k, path="fp32")
+    lab = labels.to(dev).view(-1, 1)
+    hit = indices == lab
+    c1 = int(hit[:, 0].sum())
+    ck = int(hit.any(dim=1).sum())
+    return {"top1": c1 / n if n else 0, "top5": ck / n if n else 0, "correct_top1": c1, "correct_topk": ck,
+            "values": scores * float(logit_scale), "indices": indices}
+
+
 def topk_merge(scores, index):
     """[nlists, nq, k] per-shard results -> [nq, k] by (-score, +index)."""
     dev = require_cuda(scores, index)

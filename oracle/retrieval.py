@@ -195,3 +195,21 @@ def min_rank_gap(similarity_matrix):
     s = np.sort(np.asarray(similarity_matrix, dtype=np.float64), axis=0)
     g0 = np.diff(s, axis=0).min()
     return float(min(g0, g1))
+
+
+def zero_shot_counts(image_features, text_features, labels, k=5):
+    """Restated eval_scripts/test_zero_shot_ImageNet.py:79-108 (torch on CPU, line for line): normalise the image
+    features, 100 * (img @ text.T), topk(k), top-1 hits and the per-sample `label in indices[i]` loop."""
+    import torch
+    import torch.nn.functional as F
+    img = F.normalize(torch.as_tensor(np.asarray(image_features, dtype=np.float32)), dim=1)
+    txt = torch.as_tensor(np.asarray(text_features, dtype=np.float32))
+    lab = torch.as_tensor(np.asarray(labels, dtype=np.int64))
+    similarity = 100.0 * (img @ txt.T)
+    values, indices = similarity.topk(min(k, txt.shape[0]), dim=1)
+    top1 = int((indices[:, 0] == lab).sum().item())
+    topk = 0
+    for i, label in enumerate(lab):
+        if label in indices[i]:
+            topk += 1
+    return top1, topk, values.numpy(), indices.numpy()

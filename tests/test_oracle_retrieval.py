@@ -57,3 +57,20 @@ def test_identity_embeddings_give_perfect_recall():
     cap = np.repeat(img, 2, axis=0)
     m = orc.metrics_from_ranks(*orc.ranks_from_embeddings_c(cap, img, list(range(16)), [i // 2 for i in range(32)]))
     assert m["t2i"]["R@1"] == 1.0 and m["i2t"]["R@1"] == 1.0 and m["t2i"]["MAP"] == 1.0
+
+
+def test_zero_shot_counts_restatement():
+    """oracle.retrieval.zero_shot_counts (test_zero_shot_ImageNet.py:79-108 restated) against plain numpy."""
+    from oracle import retrieval as orc
+    rng = np.random.default_rng(0)
+    txt = rng.standard_normal((50, 64)).astype(np.float32)
+    txt /= np.linalg.norm(txt, axis=1, keepdims=True)
+    labels = rng.integers(0, 50, size=40)
+    img = (txt[labels] + 0.35 * rng.standard_normal((40, 64))).astype(np.float32) * 3.0
+    top1, top5, values, indices = orc.zero_shot_counts(img, txt, labels, 5)
+    s = (img / np.linalg.norm(img, axis=1, keepdims=True)) @ txt.T
+    order = np.argsort(-s, axis=1, kind="stable")[:, :5]
+    assert np.array_equal(indices, order)
+    assert top1 == int((order[:, 0] == labels).sum())
+    assert top5 == int((order == labels[:, None]).any(axis=1).sum())
+    assert np.allclose(values, 100.0 * np.take_along_axis(s, order, axis=1), rtol=1e-5)

@@ -122,3 +122,22 @@ def test_index_flat_ip_surface(built_library):
     ws, wi = orc.c_topk(q[:1], gal, 3)
     assert np.array_equal(I, wi) and np.array_equal(D, ws)
     assert I[0, 0] == planted[0] and D[0, 0] >= 0.85
+
+
+@pytest.mark.parametrize("n,classes,d", [(257, 1000, 512), (64, 10, 512), (100, 100, 768)])
+def test_zero_shot_topk_accuracy_matches_reference_loop(built_library, n, classes, d):
+    """zero-shot top-1 / top-5 (test_zero_shot_ImageNet.py:79-108) on tie-free synthetic features."""
+    from dclip_b200 import retrieval as R
+    rng = np.random.default_rng(n + classes)
+    txt = rng.standard_normal((classes, d)).astype(np.float32)
+    txt /= np.linalg.norm(txt, axis=1, keepdims=True)
+    labels = rng.integers(0, classes, size=n)
+    other = rng.integers(0, classes, size=n)                      # a distractor class of varying strength: some top-1 misses
+    a = rng.uniform(0.4, 1.6, size=(n, 1)).astype(np.float32)
+    img = ((txt[labels] + a * txt[other] + 0.5 * rng.standard_normal((n, d)).astype(np.float32) / np.sqrt(d)) * 7.5).astype(np.float32)
+    got = R.zero_shot_topk_accuracy(torch.from_numpy(img).cuda(), torch.from_numpy(txt).cuda(), torch.from_numpy(labels).cuda(), k=5)
+    top1, top5, values, indices = orc.zero_shot_counts(img, txt, labels, 5)
+    assert got["correct_top1"] == top1 and got["correct_topk"] == top5
+    assert np.array_equal(got["indices"].cpu().numpy(), indices)
+    assert np.allclose(got["values"].cpu().numpy(), values, rtol=1e-5, atol=1e-4)
+    assert 0 < top1 < n          # the fixture is neither trivial nor hopeless
