@@ -213,6 +213,17 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # N > 1: after the host barrier the ranks still enqueue their step tens of microseconds apart (host jitter),
+    # and max-over-ranks timing of an isolated 0.15 ms step would mostly measure that.  A device-side gate (one
+    # peer-memory signal + wait, dclip_p2p_push) right before the start event releases all GPUs together.
+    gate = None
+    if world > 1:
+        try:
+            from dclip_b200.peer import PeerBuffer
+            gate = PeerBuffer(256, dev)
+        except RuntimeError:
+            gate = None
+
     def timed(fn, steps, warmup):
         for _ in range(warmup):
             fn()
@@ -221,6 +232,8 @@ def main():
         for _ in range(steps):
             flush.zero_()                                    # L2 flush between timed iterations (untimed)
             barrier()
+            if gate is not None:
+                gate.push([], -1, 3, wait_after=True)        # device-side start gate (untimed)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             fn()
@@ -266,7 +279,8 @@ def main():
             "config": {"workload": f"distill-loss fwd+bwd, global batch {B}, d={d}, tau={TEMPERATURE} (BASELINE configs[3])",
                        "global_batch": B, "dim": d, "rows_per_gpu": m, "path": path, "l2_flush": "256 MiB write between timed steps",
                        "launch": "python" if args.no_graph else "cuda-graph (dclip_b200.losses.GraphedStep)",
-                       "parallelism": f"dp{world} (batch-sharded, operand all-gather)" if world > 1 else "single GPU"},
+                       "parallelism": f"dp{world} (batch-sharded, operand all-gather over NVLink peer memory)" if world > 1 else "single GPU",
+                       "start": "host barrier + device-side peer-memory gate before the start event" if gate is not None else "host barrier"},
             "clocks": clocks,
             "e2e": {"value": B / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in host) * world,
