@@ -389,8 +389,9 @@ int stream_nsplit(int64_t m, int64_t n, int nsides) {
 
 int* tc_error_flag();   // loss_tc.cu
 
-// Lockstep is worth it when the Y operand does not fit in L2 and several waves of CTAs stream it: one group =
-// one wave of SM-count consecutive CTAs, one epoch = sync_every() tiles.
+// Lockstep is worth it when the Y operand does not fit in L2 and many CTAs stream it (measured: +21 % with a
+// single wave of 128 CTAs over a 6 GB gallery, +37 % at cfg5): one group = one wave of SM-count consecutive CTAs,
+// one epoch = sync_every() tiles.
 static int sync_every() {      // tiles per lockstep epoch (DCLIP_STREAM_SYNC_EVERY overrides; 64 tiles = 25 MB of Y at d = 768)
     static const int v = [] { const char* e = getenv("DCLIP_STREAM_SYNC_EVERY"); const int x = e ? atoi(e) : 0; return x > 0 ? x : 64; }();
     return v;
@@ -398,7 +399,8 @@ static int sync_every() {      // tiles per lockstep epoch (DCLIP_STREAM_SYNC_EV
 size_t stream_sync_bytes(int64_t m, int64_t n, int64_t d, int nsplit) {
     if (n * d * 2 <= (int64_t)96 * 1024 * 1024) return 0;
     const int64_t ctas = (ceil_div(m, SM_ROWS) + 1) / 2 * 2 * nsplit;
-    if (ctas < 2 * sm_count()) return 0;
+    static const int min_ctas = [] { const char* e = getenv("DCLIP_STREAM_SYNC_MIN_CTAS"); return e ? atoi(e) : 64; }();
+    if (ctas < min_ctas) return 0;
     const int64_t groups = ceil_div(ctas, sm_count());
     const int64_t epochs = ceil_div(ceil_div(ceil_div(n, SN_COLS), nsplit), sync_every());
     return (size_t)(groups * epochs) * sizeof(unsigned int);
