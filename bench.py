@@ -202,7 +202,13 @@ def main():
             return graphed.static_out
         return step_fn(*step_inputs)
 
+    host_step = L.HostDistillStep(B, d, tdtype, dev, temperature=TEMPERATURE, path=path) if world == 1 else None
+
     def step_e2e():
+        if host_step is not None:
+            # public host-buffer API: pinned host -> device copies (students first), the contrastive part overlapped
+            # with the teachers' copy, device -> host read of the four losses; all inside the timed region
+            return host_step(*host)[0]
         for dst, src in zip(step_inputs, host):
             dst.copy_(src, non_blocking=True)       # pinned host -> device, inside the timed region
         losses = step_resident()[0]

@@ -26,6 +26,9 @@ SIGNATURES = {
     "dclip_distill_loss_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "dclip_distill_loss_fwd_bwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _f32, _f32, _f32, _f32, _f32, _vp, _vp,
                                           _vp, _vp, _vp, _sz, _i32, _vp]),
+    "dclip_distill_loss_students": (_i32, [_vp, _vp, _i64, _i64, _i32, _f32, _f32, _vp, _sz, _i32, _vp]),
+    "dclip_distill_loss_teachers": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _sz,
+                                           _i32, _vp]),
     "dclip_distill_loss_launch_count": (_i32, [_i64, _i64, _i64, _i32, _i32]),
     "dclip_tensor_path_ready": (_i32, []),
     "dclip_debug_pipeline_error": (_i32, [_vp]),

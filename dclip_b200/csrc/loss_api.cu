@@ -335,13 +335,18 @@ size_t dclip_distill_loss_workspace_bytes(int64_t B, int64_t d, int path) {
     return total + 1024;
 }
 
-int dclip_distill_loss_fwd_bwd(const void* s_img, const void* s_txt, const void* t_img, const void* t_txt, int64_t B,
-                               int64_t d, int dtype, float temperature, float w_img, float w_txt, float w_con,
-                               float grad_scale, float* losses, void* d_s_img, void* d_s_txt, float* stats,
-                               void* workspace, size_t workspace_bytes, int path, void* stream) {
+// phase 0: the whole objective.  Phases 1 / 2 split it at the point where the TEACHER embeddings are first
+// needed, so that a caller whose inputs arrive over PCIe can overlap the teachers' copy with the contrastive
+// part (dclip_distill_loss_students / _teachers; both phases carve the same workspace):
+//   phase 1 (students only): normalise, forward tiles, log-sum-exp, backward tiles -> du_hat, dv_hat, lse, diag
+//   phase 2 (teachers):      cosine terms, the four losses, gradient tail (normalise backward + cosine gradient)
+static int distill_loss_impl(int phase, const void* s_img, const void* s_txt, const void* t_img, const void* t_txt, int64_t B,
+                             int64_t d, int dtype, float temperature, float w_img, float w_txt, float w_con,
+                             float grad_scale, float* losses, void* d_s_img, void* d_s_txt, float* stats,
+                             void* workspace, size_t workspace_bytes, int path, void* stream) {
     if (int e = check_common(B, d)) return e;
     DCLIP_REQUIRE(B > 0, "distill_loss: empty batch");
-    DCLIP_REQUIRE(s_img && s_txt && losses, "distill_loss: null pointer");
+    DCLIP_REQUIRE(s_img && s_txt && (losses || phase == 1), "distill_loss: null pointer");
     DCLIP_REQUIRE((t_img == nullptr) == (t_txt == nullptr), "distill_loss: give both teachers or neither");
     DCLIP_REQUIRE((d_s_img == nullptr) == (d_s_txt == nullptr), "distill_loss: give both gradients or neither");
     DCLIP_REQUIRE(temperature > 0.f, "distill_loss: temperature must be > 0");
@@ -370,7 +375,7 @@ int dclip_distill_loss_fwd_bwd(const void* s_img, const void* s_txt, const void*
     float* dv_hat = static_cast<float*>(ws.take((size_t)B * d * 4));
     float* du_part = du_hat;
     float* dv_part = dv_hat;
-    if (tensor && nsb > 1 && d_s_img) {
+    if (tensor && nsb > 1 && (d_s_img || phase != 0)) {
         du_part = static_cast<float*>(ws.take((size_t)2 * nsb * B * d * 4));   // [side][split][B][d], sides contiguous
         dv_part = du_part + (size_t)nsb * B * d;
     }
@@ -382,11 +387,25 @@ int dclip_distill_loss_fwd_bwd(const void* s_img, const void* s_txt, const void*
     if (!ws.ok()) return fail(DCLIP_ERR_WORKSPACE, "distill_loss: workspace too small (%zu < %zu)", workspace_bytes, ws.used);
     if (stats) { lse_u = stats; lse_v = stats + B; }
 
+    const bool do_students = phase != 2, do_teachers = phase != 1;
+    if (phase == 2) {
+        // cosine terms of the rows (the norms of the students are phase 1's), then the four losses
+        if (t_img) {
+            CosArgs ca{};
+            ca.s[0] = CosSide{s_img, t_img, inv_u, cos_img};
+            ca.s[1] = CosSide{s_txt, t_txt, inv_v, cos_txt};
+            ca.m = B; ca.d = d;
+            if (int e = launch_cos_rows(ca, dtype, st)) return e;
+        }
+        SumsArgs sa{lse_u, lse_v, diag, t_img ? cos_img : nullptr, t_txt ? cos_txt : nullptr, B, nullptr, losses, w_img, w_txt, w_con};
+        if (int e = launch_loss_sums(sa, st)) return e;
+    }
     PrepArgs pa{};
-    pa.s[0] = PrepSide{s_img, t_img, u_hat, inv_u, cos_img};
-    pa.s[1] = PrepSide{s_txt, t_txt, v_hat, inv_v, cos_txt};
+    pa.s[0] = PrepSide{s_img, phase == 1 ? nullptr : t_img, u_hat, inv_u, cos_img};
+    pa.s[1] = PrepSide{s_txt, phase == 1 ? nullptr : t_txt, v_hat, inv_v, cos_txt};
     pa.m = B; pa.d = d;
-    if (tensor) {
+    if (!do_students) {
+    } else if (tensor) {
         pa.diag = diag; pa.inv_tau = 1.0f / temperature;
         if (int e = launch_loss_prep_pair(pa, dtype, op_dtype, st)) return e;
     } else {
@@ -395,14 +414,16 @@ int dclip_distill_loss_fwd_bwd(const void* s_img, const void* s_txt, const void*
 
     const void* xs2[2] = {u_hat, v_hat};
     const void* ys2[2] = {v_hat, u_hat};
-    if (tensor) {
+    if (!do_students) {
+    } else if (tensor) {
         TcArgs fa{};
         fa.s[0] = TcSide{nullptr, nullptr, rowpart};
         fa.col_out = colpart;
         fa.m = B; fa.n = B; fa.d = d; fa.inv_tau = 1.0f / temperature; fa.row_offset = 0;
         if (int e = launch_stream_tc(1, 1, xs2, ys2, fa, ns1, st)) return e;
         FinalizeArgs fz{rowpart, colpart, ns1, B, fa.inv_tau, lse_u, lse_v,
-                        SumsArgs{lse_u, lse_v, diag, t_img ? cos_img : nullptr, t_txt ? cos_txt : nullptr, B, nullptr, losses, w_img, w_txt, w_con},
+                        SumsArgs{lse_u, lse_v, diag, t_img ? cos_img : nullptr, t_txt ? cos_txt : nullptr, B, nullptr, phase == 0 ? losses : nullptr,
+                                 w_img, w_txt, w_con},
                         nib};
         if (int e = launch_tc_finalize(fz, st)) return e;
     } else {
@@ -413,14 +434,15 @@ int dclip_distill_loss_fwd_bwd(const void* s_img, const void* s_txt, const void*
         if (int e = launch_rowlse_simt(la, 2, st)) return e;
     }
 
-    if (!tensor) {
+    if (!tensor && phase == 0) {
         SumsArgs sa{lse_u, lse_v, diag, t_img ? cos_img : nullptr, t_txt ? cos_txt : nullptr, B, nullptr, losses, w_img, w_txt, w_con};
         if (int e = launch_loss_sums(sa, st)) return e;
     }
 
-    if (d_s_img) {
+    if (d_s_img || phase == 1) {
         const bool need_con = w_con != 0.f;
-        if (need_con && tensor) {
+        if (!do_students) {
+        } else if (need_con && tensor) {
             TcArgs ga{};
             ga.s[0] = TcSide{lse_u, lse_v, du_part};
             ga.s[1] = TcSide{lse_v, lse_u, dv_part};
@@ -439,6 +461,7 @@ int dclip_distill_loss_fwd_bwd(const void* s_img, const void* s_txt, const void*
             ga.coef_over_tau = w_con / (2.0f * (float)B) / temperature;
             if (int e = launch_grad_simt(ga, 2, st)) return e;
         }
+        if (!do_teachers || !d_s_img) return DCLIP_OK;
         TailArgs ta{};
         ta.m = B; ta.d = d; ta.grad_scale = grad_scale;
         ta.s[0] = TailSide{s_img, t_img, inv_u, need_con ? du_hat : nullptr, d_s_img};
@@ -448,6 +471,27 @@ int dclip_distill_loss_fwd_bwd(const void* s_img, const void* s_txt, const void*
         if (int e = launch_grad_tail(ta, 2, dtype, st)) return e;
     }
     return DCLIP_OK;
+}
+
+int dclip_distill_loss_fwd_bwd(const void* s_img, const void* s_txt, const void* t_img, const void* t_txt, int64_t B,
+                               int64_t d, int dtype, float temperature, float w_img, float w_txt, float w_con,
+                               float grad_scale, float* losses, void* d_s_img, void* d_s_txt, float* stats,
+                               void* workspace, size_t workspace_bytes, int path, void* stream) {
+    return distill_loss_impl(0, s_img, s_txt, t_img, t_txt, B, d, dtype, temperature, w_img, w_txt, w_con, grad_scale, losses, d_s_img,
+                             d_s_txt, stats, workspace, workspace_bytes, path, stream);
+}
+
+int dclip_distill_loss_students(const void* s_img, const void* s_txt, int64_t B, int64_t d, int dtype, float temperature, float w_con,
+                                void* workspace, size_t workspace_bytes, int path, void* stream) {
+    return distill_loss_impl(1, s_img, s_txt, nullptr, nullptr, B, d, dtype, temperature, 0.f, 0.f, w_con, 1.f, nullptr, nullptr, nullptr,
+                             nullptr, workspace, workspace_bytes, path, stream);
+}
+
+int dclip_distill_loss_teachers(const void* s_img, const void* s_txt, const void* t_img, const void* t_txt, int64_t B, int64_t d,
+                                int dtype, float temperature, float w_img, float w_txt, float w_con, float grad_scale, float* losses,
+                                void* d_s_img, void* d_s_txt, void* workspace, size_t workspace_bytes, int path, void* stream) {
+    return distill_loss_impl(2, s_img, s_txt, t_img, t_txt, B, d, dtype, temperature, w_img, w_txt, w_con, grad_scale, losses, d_s_img,
+                             d_s_txt, nullptr, workspace, workspace_bytes, path, stream);
 }
 
 }  // extern "C"

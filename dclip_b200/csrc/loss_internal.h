@@ -11,6 +11,10 @@ namespace dclip {
 struct PrepSide { const void* x; const void* t; void* xhat; float* inv_norm; float* cos; };
 struct PrepArgs { PrepSide s[2]; int64_t m, d; float* diag; float inv_tau; };   // diag: pair kernel only
 
+// cosine terms of the rows against the teacher, students' inverse norms given (phase 2 of the split objective)
+struct CosSide { const void* x; const void* t; const float* inv_norm; float* cos; };
+struct CosArgs { CosSide s[2]; int64_t m, d; };
+
 struct LseSide {
     const float* x; const float* y;   // FP32 path operands (normalised rows)
     float* part_m; float* part_l;     // [nsplit, m] online-softmax partials
@@ -88,6 +92,7 @@ int launch_stream_tc(int mode, int nsides, const void* const x[2], const void* c
 size_t stream_sync_bytes(int64_t m, int64_t n, int64_t d, int nsplit);
 
 int launch_loss_prep(const PrepArgs& a, int nsides, int dtype, int op_dtype, cudaStream_t st);
+int launch_cos_rows(const CosArgs& a, int dtype, cudaStream_t st);
 // both sides of row i in one warp + diag[i] = u_hat_i . v_hat_i / tau from the rounded operands
 int launch_loss_prep_pair(const PrepArgs& a, int dtype, int op_dtype, cudaStream_t st);
 // tensor path: lse = 1/tau + ln(sum of partial row sums) for both sides + the loss sums, one launch

@@ -165,6 +165,28 @@ __global__ void __launch_bounds__(kThreads) k_loss_prep_pair(PrepArgs a) {
     if (lane == 0 && a.diag) a.diag[row] = dot * a.inv_tau;
 }
 
+// cos(x_i, t_i) for both sides with the students' clamped inverse norms from the prep kernel (one warp per row)
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_cos_rows(CosArgs a) {
+    const CosSide s = a.s[blockIdx.y];
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    if (row >= a.m) return;
+    const int64_t d = a.d;
+    const T* x = static_cast<const T*>(s.x) + row * d;
+    const T* t = static_cast<const T*>(s.t) + row * d;
+    float tt = 0.f, xt = 0.f;
+    for (int64_t k = lane * 8; k < d; k += 256) {
+        float xv[8], tv[8];
+        load8<T>(x + k, xv);
+        load8<T>(t + k, tv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { tt = fmaf(tv[i], tv[i], tt); xt = fmaf(xv[i], tv[i], xt); }
+    }
+    tt = warp_sum(tt); xt = warp_sum(xt);
+    if (lane == 0) s.cos[row] = xt * s.inv_norm[row] / fmaxf(sqrtf(tt), kNormEps);
+}
+
 // tensor path finalize: both lse vectors from the partial sums + the loss sums.  One cluster of 8 CTAs (a
 // single CTA spends its time on load latency); every reduction runs in a fixed order, so the result is
 // bit-reproducible: thread -> rows i = g, g + 4096, ...; CTA tree; then cluster rank 0 adds the 8 CTA sums
@@ -566,6 +588,14 @@ int launch_loss_prep_pair(const PrepArgs& a, int dtype, int op_dtype, cudaStream
         return fail(DCLIP_ERR_INVALID, "loss_prep_pair: bad op_dtype %d", op_dtype);
     }
     DCLIP_LAUNCH_OK("k_loss_prep_pair");
+    return DCLIP_OK;
+}
+
+int launch_cos_rows(const CosArgs& a, int dtype, cudaStream_t st) {
+    if (a.m == 0) return DCLIP_OK;
+    dim3 grid((unsigned)ceil_div(a.m, kThreads / 32), 2);
+    DCLIP_DISPATCH_DTYPE(dtype, (k_cos_rows<T><<<grid, kThreads, 0, st>>>(a)));
+    DCLIP_LAUNCH_OK("k_cos_rows");
     return DCLIP_OK;
 }
 

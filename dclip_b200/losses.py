@@ -61,6 +61,64 @@ def distill_loss_fwd_bwd(s_img, s_txt, t_img=None, t_txt=None, temperature=0.05,
     return losses, d_img, d_txt
 
 
+class HostDistillStep:
+    """Distillation objective for inputs that live in (pinned) HOST memory: the four [B, d] tensors are copied
+    to the device on a copy stream, students first, and the objective is split where the teachers are first
+    needed (``dclip_distill_loss_students`` / ``_teachers``): the contrastive part - normalise, forward tiles,
+    log-sum-exp, backward tiles, 85 % of the step - runs while the teachers are still crossing PCIe.
+
+        step = HostDistillStep(B, d, torch.bfloat16, device)
+        losses_host, d_img, d_txt = step(s_img_h, s_txt_h, t_img_h, t_txt_h)     # losses: CPU tensor [4]
+
+    The gradients stay on the device (valid until the next call).  One host synchronisation per call (the read of
+    the losses), as in the reference's ``loss.item()``."""
+
+    def __init__(self, B, d, dtype, device, temperature=0.05, w_img=1.0, w_txt=1.0, w_con=1.0, grad_scale=1.0, path="auto"):
+        self.lib = _lib.load_library()
+        self.dev = torch.device(device)
+        self.B, self.d, self.dtype = int(B), int(d), dtype
+        self.hyper = (float(temperature), float(w_img), float(w_txt), float(w_con), float(grad_scale))
+        self.pc = path_code(path)
+        self.bufs = [torch.empty((B, d), dtype=dtype, device=self.dev) for _ in range(4)]
+        self.losses = torch.empty(4, dtype=torch.float32, device=self.dev)
+        self.losses_host = torch.empty(4, dtype=torch.float32).pin_memory()
+        self.d_img = torch.empty((B, d), dtype=dtype, device=self.dev)
+        self.d_txt = torch.empty((B, d), dtype=dtype, device=self.dev)
+        self.ws = workspace(self.lib.dclip_distill_loss_workspace_bytes(B, d, self.pc), self.dev)
+        self.copy_stream = torch.cuda.Stream(self.dev)
+        self.ev_students = torch.cuda.Event()
+        self.ev_teachers = torch.cuda.Event()
+
+    def __call__(self, s_img, s_txt, t_img, t_txt):
+        for t in (s_img, s_txt, t_img, t_txt):
+            if t.is_cuda or tuple(t.shape) != (self.B, self.d) or t.dtype != self.dtype:
+                raise ValueError(f"HostDistillStep: expected four host [{self.B}, {self.d}] {self.dtype} tensors")
+        temperature, w_img, w_txt, w_con, grad_scale = self.hyper
+        cur = torch.cuda.current_stream(self.dev)
+        b = self.bufs
+        self.copy_stream.wait_stream(cur)                  # the previous step has finished with the device buffers
+        with torch.cuda.stream(self.copy_stream):
+            b[0].copy_(s_img, non_blocking=True)
+            b[1].copy_(s_txt, non_blocking=True)
+            self.ev_students.record()
+            b[2].copy_(t_img, non_blocking=True)
+            b[3].copy_(t_txt, non_blocking=True)
+            self.ev_teachers.record()
+        dt = dtype_code(b[0])
+        with torch.cuda.device(self.dev):
+            cur.wait_event(self.ev_students)
+            check(self.lib.dclip_distill_loss_students(ptr(b[0]), ptr(b[1]), self.B, self.d, dt, temperature, w_con, ptr(self.ws),
+                                                       self.ws.numel(), self.pc, stream_ptr(self.dev)), "distill_loss_students")
+            cur.wait_event(self.ev_teachers)
+            check(self.lib.dclip_distill_loss_teachers(ptr(b[0]), ptr(b[1]), ptr(b[2]), ptr(b[3]), self.B, self.d, dt, temperature, w_img,
+                                                       w_txt, w_con, grad_scale, ptr(self.losses), ptr(self.d_img), ptr(self.d_txt),
+                                                       ptr(self.ws), self.ws.numel(), self.pc, stream_ptr(self.dev)),
+                  "distill_loss_teachers")
+            self.losses_host.copy_(self.losses, non_blocking=True)
+            cur.synchronize()
+        return self.losses_host, self.d_img, self.d_txt
+
+
 class _DistillLossFn(torch.autograd.Function):
     """Autograd shell: the library computes loss and gradients in one call; backward only
     scales the saved gradients by the upstream scalar."""

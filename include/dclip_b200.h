@@ -83,6 +83,16 @@ int dclip_distill_loss_fwd_bwd(const void* s_img, const void* s_txt, const void*
 
 /* Number of kernels of this library one step launches (single-GPU composite when sharded == 0, the
  * per-rank building blocks (1)-(5) when sharded != 0); used by bench.py for "gpu_launches". */
+/* The same objective split where the TEACHER embeddings are first needed, for callers whose inputs arrive over
+ * PCIe: _students (normalise, forward tiles, log-sum-exp, backward tiles) needs only the student rows and can run
+ * while the teachers are still being copied; _teachers (cosine terms, the four losses, gradient tail) finishes
+ * the step.  Both calls must get the SAME workspace (dclip_distill_loss_workspace_bytes), B, d, dtype, temperature,
+ * w_con and path; results equal dclip_distill_loss_fwd_bwd up to the rounding of one reciprocal. */
+int dclip_distill_loss_students(const void* s_img, const void* s_txt, int64_t B, int64_t d, int dtype, float temperature, float w_con,
+                                void* workspace, size_t workspace_bytes, int path, void* stream);
+int dclip_distill_loss_teachers(const void* s_img, const void* s_txt, const void* t_img, const void* t_txt, int64_t B, int64_t d,
+                                int dtype, float temperature, float w_img, float w_txt, float w_con, float grad_scale, float* losses,
+                                void* d_s_img, void* d_s_txt, void* workspace, size_t workspace_bytes, int path, void* stream);
 int dclip_distill_loss_launch_count(int64_t m, int64_t n, int64_t d, int path, int sharded);
 /* 1 when the tcgen05 tensor path of the loss is compiled in and validated for use. */
 int dclip_tensor_path_ready(void);

@@ -104,3 +104,20 @@ def test_pair_backward_is_bit_reproducible(built_library):
                     assert torch.equal(a, b)
     torch.cuda.synchronize()
     assert _pipeline_ok(built_library)
+
+
+@pytest.mark.parametrize("B,d,dtype,path", [(512, 768, torch.bfloat16, "tensor"), (96, 256, torch.float32, "fp32")])
+def test_host_step_split_matches_composite(built_library, B, d, dtype, path):
+    """HostDistillStep (students / teachers phases, copies overlapped) against the one-call composite."""
+    from dclip_b200 import losses as L
+    dev = torch.device("cuda:0")
+    host = [t.to(dtype).contiguous().pin_memory() for t in synthetic.loss_inputs(B, d, seed=3)]
+    step = L.HostDistillStep(B, d, dtype, dev, path=path)
+    for _ in range(3):
+        lh, di, dt = step(*host)
+    ref_l, ref_di, ref_dt = L.distill_loss_fwd_bwd(*(t.to(dev) for t in host), path=path)
+    torch.cuda.synchronize()
+    assert _pipeline_ok(built_library)
+    assert torch.allclose(lh, ref_l.cpu(), rtol=1e-5, atol=1e-6), (lh, ref_l)
+    assert _rel(di, ref_di) < 1e-5 + (2 ** -8 if dtype == torch.bfloat16 else 0)
+    assert _rel(dt, ref_dt) < 1e-5 + (2 ** -8 if dtype == torch.bfloat16 else 0)
