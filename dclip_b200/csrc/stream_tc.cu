@@ -67,6 +67,13 @@ __device__ __forceinline__ float ex2_ftz(float x) {
 // kPair: the two CTAs of a (2,1,1) cluster share every 256-row Y tile (cta_group::2, M = 256 = both CTAs' 128 X rows,
 // N = 256 = 128 Y rows from each CTA's shared memory): each CTA streams only HALF of Y, a stage shrinks from 48 to
 // 32 KB and the ring deepens from 4 to 6 stages.  Row mapping is unchanged (CTA x owns X rows [128 x, 128 x + 128)).
+// order-preserving float <-> uint32 map (for redux.sync.min on scores; -inf sorts below every finite value)
+__device__ __forceinline__ unsigned float_to_ord(float f) {
+    const unsigned b = __float_as_uint(f);
+    return b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ float ord_to_float(unsigned u) { return __uint_as_float(u ^ ((u >> 31) ? 0x80000000u : 0xFFFFFFFFu)); }
+
 template <int kMode, bool kPair>
 __global__ void __launch_bounds__(stream_threads(kMode, kPair), 1)
 k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CUtensorMap tmy0,
@@ -294,18 +301,14 @@ k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CU
                                 const float cs = __shfl_sync(0xffffffffu, sv, src);
                                 const int row = qd * 32 + src;
                                 float v = ls[row * kListLen + lane];
-                                float m = v;
-#pragma unroll
-                                for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                                const float m = __shfl_sync(0xffffffffu, mn, src);     // the row's minimum = its owner's cached threshold
                                 const int pos = __ffs(__ballot_sync(0xffffffffu, v == m)) - 1;
                                 if (lane == pos) {
                                     v = cs;
                                     ls[row * kListLen + lane] = cs;
                                     li[row * kListLen + lane] = (int32_t)(j0 + c0 + i);
                                 }
-                                float m2 = v;
-#pragma unroll
-                                for (int o = 16; o > 0; o >>= 1) m2 = fminf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+                                const float m2 = ord_to_float(__reduce_min_sync(0xffffffffu, float_to_ord(v)));     // one REDUX instead of 5 shuffles
                                 if (lane == src) mn = m2;
                                 __syncwarp();
                             }
