@@ -285,14 +285,23 @@ k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CU
                 } else {
                     // fast reject: does any of this thread's 32 scores beat its threshold?  (one max per
                     // score, no divergence; almost always "no" for the whole warp once the lists are warm)
-                    float best = -INFINITY;
+                    float bg[4];                              // maxima of the four 8-score groups (the slow path skips clean groups)
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) best = fmaxf(best, (c0 + i < ncols) ? __uint_as_float(r[i]) : -INFINITY);
+                    for (int g = 0; g < 4; ++g) {
+                        bg[g] = -INFINITY;
+#pragma unroll
+                        for (int ii = 0; ii < 8; ++ii) bg[g] = fmaxf(bg[g], (c0 + 8 * g + ii < ncols) ? __uint_as_float(r[8 * g + ii]) : -INFINITY);
+                    }
+                    const float best = fmaxf(fmaxf(bg[0], bg[1]), fmaxf(bg[2], bg[3]));
                     if (__any_sync(0xffffffffu, best > mn)) {
                         // slow path: the warp inserts the hits of one thread after the other, cooperatively
                         // (lane e looks at entry e of that row's list: replace the minimum, find the new one)
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {        // (unrolled: r[] must stay in registers)
+                        for (int g = 0; g < 4; ++g) {
+                          if (!__any_sync(0xffffffffu, bg[g] > mn)) continue;          // whole 8-score group below every threshold
+#pragma unroll
+                          for (int ii = 0; ii < 8; ++ii) {    // (fully unrolled: r[] must stay in registers)
+                            const int i = 8 * g + ii;
                             const float sv = __uint_as_float(r[i]);
                             unsigned hits = __ballot_sync(0xffffffffu, sv > mn && c0 + i < ncols);
                             while (hits) {
@@ -312,6 +321,7 @@ k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CU
                                 if (lane == src) mn = m2;
                                 __syncwarp();
                             }
+                          }
                         }
                     }
                 }
