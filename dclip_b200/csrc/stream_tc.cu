@@ -286,11 +286,20 @@ k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CU
                     // fast reject: does any of this thread's 32 scores beat its threshold?  (one max per
                     // score, no divergence; almost always "no" for the whole warp once the lists are warm)
                     float bg[4];                              // maxima of the four 8-score groups (the slow path skips clean groups)
+                    if (c0 + 32 <= ncols) {                   // full chunk (all but the last tile): no column predicate
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        bg[g] = -INFINITY;
+                        for (int g = 0; g < 4; ++g) {
+                            bg[g] = __uint_as_float(r[8 * g]);
 #pragma unroll
-                        for (int ii = 0; ii < 8; ++ii) bg[g] = fmaxf(bg[g], (c0 + 8 * g + ii < ncols) ? __uint_as_float(r[8 * g + ii]) : -INFINITY);
+                            for (int ii = 1; ii < 8; ++ii) bg[g] = fmaxf(bg[g], __uint_as_float(r[8 * g + ii]));
+                        }
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            bg[g] = -INFINITY;
+#pragma unroll
+                            for (int ii = 0; ii < 8; ++ii) bg[g] = fmaxf(bg[g], (c0 + 8 * g + ii < ncols) ? __uint_as_float(r[8 * g + ii]) : -INFINITY);
+                        }
                     }
                     const float best = fmaxf(fmaxf(bg[0], bg[1]), fmaxf(bg[2], bg[3]));
                     if (__any_sync(0xffffffffu, best > mn)) {
