@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(128) k_mma_rate(int N, int a_mn, int b_mn, int
                 for (int k = 0; k < 8; ++k)
                 {
                     umma_f16(tmem + (k & 1) * 256, dA + (uint64_t)(k * stepA), dB + (uint64_t)((k & 3) * stepB), idesc, 1);
-                    if (commit_every && (k + 1) % commit_every == 0) umma_commit(&bar2);
+                    if constexpr (commit_every > 0) { if ((k + 1) % commit_every == 0) umma_commit(&bar2); }
                 }
             }
             umma_commit(&bar);
@@ -125,7 +125,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) k_mma2_rate(int
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     umma_f16_pair(tmem + (k & 1) * 256, dA + (uint64_t)(k * stepA), dB + (uint64_t)((k & 3) * stepB), idesc, 1);
-                    if (commit_every && (k + 1) % commit_every == 0) {
+                    if constexpr (commit_every > 0) if ((k + 1) % commit_every == 0) {
                         if (commit_mode == 1) umma_commit_pair(&bar2);             // multicast to both CTAs
                         else if (commit_mode == 2) umma_commit_pair(&bar2, 1);     // multicast form, leader only
                         else asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar2)) : "memory");
