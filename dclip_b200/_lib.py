@@ -31,6 +31,7 @@ SIGNATURES = {
                                            _i32, _vp]),
     "dclip_distill_loss_launch_count": (_i32, [_i64, _i64, _i64, _i32, _i32]),
     "dclip_tensor_path_ready": (_i32, []),
+    "dclip_resolve_loss_path": (_i32, [_i32, _i32, _i64, _i64, _f32]),
     "dclip_debug_pipeline_error": (_i32, [_vp]),
     "dclip_loss_prep": (_i32, [_vp, _vp, _i64, _i64, _i32, _vp, _i32, _vp, _vp, _vp]),
     "dclip_infonce_rowlse_workspace_bytes": (_sz, [_i64, _i64, _i64, _i32]),
@@ -136,6 +137,14 @@ def path_code(path) -> int:
         return _PATHS[path]
     except KeyError:
         raise ValueError(f"dclip_b200: unknown path {path!r} (auto / fp32 / tensor)") from None
+
+
+def resolve_loss_path(path, x, temperature, global_batch=None) -> int:
+    """DCLIP_PATH_AUTO -> tensor / fp32 for the objective on `x` ([m, d], any supported dtype): decided by the
+    library (dclip_resolve_loss_path) so that the single-GPU and the sharded entry points agree."""
+    B = int(x.shape[0] if global_batch is None else global_batch)
+    with torch.cuda.device(x.device):
+        return load_library().dclip_resolve_loss_path(path_code(path), dtype_code(x), B, int(x.shape[1]), float(temperature))
 
 
 def require_cuda(*tensors):

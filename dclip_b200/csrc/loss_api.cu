@@ -6,12 +6,23 @@ using namespace dclip;
 
 namespace {
 
-// AUTO: the exact FP32 path unless the caller asked for the tensor path.  The Python layer picks
-// TENSOR for 16-bit inputs with supported shapes (dclip_b200/losses.py::resolve_path).
-int resolve_loss_path(int path, int op_dtype_hint) {
-    (void)op_dtype_hint;
-    if (path == DCLIP_PATH_AUTO) return DCLIP_PATH_FP32;
-    return path;
+#ifndef DCLIP_TENSOR_PATH_READY
+#define DCLIP_TENSOR_PATH_READY 1   // validated on B200 (tests/test_loss_tensor_gpu.py)
+#endif
+
+// The ONE place DCLIP_PATH_AUTO is resolved (dclip_resolve_loss_path exports it to the host layer, which uses it for
+// the single-GPU and the sharded entry points alike): the tcgen05 path for 16-bit inputs / fp16 operands when the
+// shape is supported on an sm_100 device and the batch fills at least one 128-row tile, the exact FP32 path
+// otherwise (fp32 inputs always: the 1e-5 tier; tiny batches: launch-bound either way, FP32 is exact).
+int resolve_loss_path(int path, int dtype, int64_t B, int64_t d, float temperature) {
+    if (path != DCLIP_PATH_AUTO) return path;
+    if (dtype != DCLIP_F32 && B >= 128 && DCLIP_TENSOR_PATH_READY && tc_loss_shape_ok(d, temperature) && device_is_sm100()) return DCLIP_PATH_TENSOR;
+    return DCLIP_PATH_FP32;
+}
+// building blocks: the operand dtype already says which tier produced the operands
+int resolve_block_path(int path, int op_dtype) {
+    if (path != DCLIP_PATH_AUTO) return path;
+    return op_dtype == DCLIP_F16 ? DCLIP_PATH_TENSOR : DCLIP_PATH_FP32;
 }
 
 int check_common(int64_t m, int64_t d) {
@@ -48,7 +59,7 @@ int dclip_infonce_rowlse(const void* x_hat, int64_t m, const void* y_hat, int64_
     if (int e = check_common(m, d)) return e;
     DCLIP_REQUIRE(x_hat && y_hat && lse && n > 0, "rowlse: null pointer or empty n");
     DCLIP_REQUIRE(temperature > 0.f, "rowlse: temperature must be > 0");
-    path = resolve_loss_path(path, op_dtype);
+    path = resolve_block_path(path, op_dtype);
     if (path == DCLIP_PATH_FP32) {
         DCLIP_REQUIRE(op_dtype == DCLIP_F32, "rowlse: FP32 path needs float32 operands");
         LseArgs a{};
@@ -100,7 +111,7 @@ int dclip_infonce_grad(const void* x_hat, int64_t m, const void* y_hat, int64_t 
     if (int e = check_common(m, d)) return e;
     DCLIP_REQUIRE(x_hat && y_hat && lse_x && lse_y && dx_hat && n > 0, "infonce_grad: null pointer or empty n");
     DCLIP_REQUIRE(temperature > 0.f, "infonce_grad: temperature must be > 0");
-    path = resolve_loss_path(path, op_dtype);
+    path = resolve_block_path(path, op_dtype);
     if (path == DCLIP_PATH_FP32) {
         DCLIP_REQUIRE(op_dtype == DCLIP_F32, "infonce_grad: FP32 path needs float32 operands");
         GradArgs a{};
@@ -149,7 +160,7 @@ int dclip_infonce_grad_pair(const void* u_hat, const void* v_hat, int64_t B, int
     DCLIP_REQUIRE(u_hat && v_hat && lse_u && lse_v && du_hat && dv_hat && B > 0, "infonce_grad_pair: null pointer or empty batch");
     DCLIP_REQUIRE(temperature > 0.f, "infonce_grad_pair: temperature must be > 0");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    path = resolve_loss_path(path, op_dtype);
+    path = resolve_block_path(path, op_dtype);
     if (path == DCLIP_PATH_FP32) {
         DCLIP_REQUIRE(op_dtype == DCLIP_F32, "infonce_grad_pair: FP32 path needs float32 operands");
         GradArgs ga{};
@@ -204,15 +215,14 @@ int dclip_loss_partial_sums(const float* lse_u, const float* lse_v, const float*
     return launch_loss_sums(a, static_cast<cudaStream_t>(stream));
 }
 
-#ifndef DCLIP_TENSOR_PATH_READY
-#define DCLIP_TENSOR_PATH_READY 1   // validated on B200 (tests/test_loss_tensor_gpu.py)
-#endif
 int dclip_tensor_path_ready(void) { return DCLIP_TENSOR_PATH_READY; }
+
+int dclip_resolve_loss_path(int path, int dtype, int64_t B, int64_t d, float temperature) { return resolve_loss_path(path, dtype, B, d, temperature); }
 
 int dclip_debug_pipeline_error(void* stream) { return tc_check_error_flag(static_cast<cudaStream_t>(stream)); }
 
 int dclip_distill_loss_launch_count(int64_t m, int64_t n, int64_t d, int path, int sharded) {
-    path = resolve_loss_path(path, DCLIP_F32);
+    if (path == DCLIP_PATH_AUTO) path = DCLIP_PATH_FP32;   // callers pass the resolved path (dclip_resolve_loss_path)
     if (path == DCLIP_PATH_FP32) return sharded ? 11 : 6;   // prep, rowlse+combine, sums, grad, tail (x2 sides when sharded)
     // tensor path, single GPU: prep_pair, one-pass forward tiles, finalize, backward tiles (+ partial combines), tail
     if (!sharded) return 5 + (tc_nsplit(m, n, d, 2) > 1 ? 2 : 0);
@@ -317,7 +327,7 @@ int dclip_sharded_loss_bwd(const void* s_img, const void* s_txt, const void* t_i
 // workspace: u_hat, v_hat [B,d] operands | inv_u, inv_v, cos_img, cos_txt, lse_u, lse_v, diag [B]
 //            | partials 2 x 2 x [nsplit, B] | du_hat, dv_hat [B,d] fp32
 size_t dclip_distill_loss_workspace_bytes(int64_t B, int64_t d, int path) {
-    (void)path;
+    if (path == DCLIP_PATH_AUTO && tc_loss_shape_ok(d, 0.05f)) path = DCLIP_PATH_TENSOR;   // AUTO may resolve to either: size for both
     int ns = simt_rowlse_nsplit(B, B, d);
     if (ns < 1) ns = 1;
     size_t total = 0;
@@ -352,7 +362,7 @@ static int distill_loss_impl(int phase, const void* s_img, const void* s_txt, co
     DCLIP_REQUIRE(temperature > 0.f, "distill_loss: temperature must be > 0");
     DCLIP_REQUIRE(aligned16(s_img) && aligned16(s_txt) && aligned16(workspace), "distill_loss: pointers must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    path = resolve_loss_path(path, dtype);
+    path = resolve_loss_path(path, dtype, B, d, temperature);
     const bool tensor = path == DCLIP_PATH_TENSOR;
     if (tensor && !tc_loss_shape_ok(d, temperature))
         return fail(DCLIP_ERR_UNSUPPORTED, "distill_loss: tensor path needs d %% 128 == 0, 128 <= d <= 768 and temperature >= 0.025 (d=%lld tau=%g)", (long long)d, temperature);

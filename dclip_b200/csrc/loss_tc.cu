@@ -29,6 +29,8 @@
 #include <cstdlib>
 
 #include "common.cuh"
+
+#include <mutex>
 #include "loss_internal.h"
 #include "tcgen05.cuh"
 
@@ -377,14 +379,29 @@ static size_t tc_smem_bytes(int64_t d) {
     return 1024 + (size_t)((d + 63) / 64) * kXBoxBytes + (size_t)kSlots * kSlotBytes + 2 * kGBytes + 512;
 }
 
-int* tc_error_flag() {   // one device int per device, lazily allocated, never freed
-    static thread_local int* flag[16] = {nullptr};
+// One pipeline-error int per device for the whole process (kernels launched from PyTorch's autograd thread report
+// into the same flag the main thread reads).  Allocated on first use with cudaMalloc (legal while another stream is
+// being captured in relaxed / thread-local mode; a global-mode capture must call dclip_debug_pipeline_error once
+// before capturing) and cleared on a private non-blocking stream, never on the legacy stream.
+int* tc_error_flag() {
+    static std::mutex mu;
+    static int* flag[16] = {nullptr};
     int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 16) return nullptr;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
     if (!flag[dev]) {
-        if (cudaMalloc(&flag[dev], sizeof(int)) != cudaSuccess) return nullptr;
-        cudaMemset(flag[dev], 0, sizeof(int));
+        int* p = nullptr;
+        if (cudaMalloc(&p, sizeof(int)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        cudaStream_t s = nullptr;
+        if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) == cudaSuccess) {
+            cudaMemsetAsync(p, 0, sizeof(int), s);
+            cudaStreamSynchronize(s);
+            cudaStreamDestroy(s);
+        } else {
+            cudaGetLastError();
+            cudaMemset(p, 0, sizeof(int));
+        }
+        flag[dev] = p;
     }
     return flag[dev];
 }

@@ -43,6 +43,7 @@ using namespace tc;
 
 // Optional stall accounting (build with -DDCLIP_PAIR_PROF): cycles the roles of cluster 0 spend in each wait.
 #ifdef DCLIP_PAIR_PROF
+#define DCLIP_DBG_SKIP(bit) (a.debug_skip & (bit))
 __device__ unsigned long long g_pair_prof[32];
 __device__ unsigned int g_pair_trace[8][2048];   // leader CTA of cluster 0: per-role clock stamps (low 32 bits)
 #define PROF_ON (blockIdx.x < 2 && blockIdx.y == 0 && blockIdx.z == 0)
@@ -50,6 +51,7 @@ __device__ unsigned int g_pair_trace[8][2048];   // leader CTA of cluster 0: per
 #define PROF_BEGIN(v) const long long v = clock64()
 #define PROF_END(v, slot) do { if (PROF_ON) atomicAdd(&g_pair_prof[slot], (unsigned long long)(clock64() - v)); } while (0)
 #else
+#define DCLIP_DBG_SKIP(bit) false
 #define PROF_BEGIN(v) do { } while (0)
 #define PROF_END(v, slot) do { } while (0)
 #define TRACE(role, idx) do { } while (0)
@@ -214,7 +216,7 @@ k_infonce_bwd_pair(const __grid_constant__ CUtensorMap tmx0, const __grid_consta
                         for (int h = 0; h < 2; ++h) {
                             const uint64_t da0 = smem_desc(hiK, ring_addr + (stage + h) * kBoxBytes);
                             const uint64_t db0 = smem_desc(hiK, xs_addr + (kb + h) * kXBoxBytes);
-                            if (!(a.debug_skip & 1))
+                            if (!DCLIP_DBG_SKIP(1))
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks)
                                 umma_f16_pair(tmem + kSCol, da0 + (uint64_t)(ks * 2), db0 + (uint64_t)(ks * 2), idesc1, (kb | h | ks) != 0);
@@ -241,7 +243,7 @@ k_infonce_bwd_pair(const __grid_constant__ CUtensorMap tmx0, const __grid_consta
                         const int jh = s & 1;
                         const uint64_t da0 = smem_desc(hiA2, ring_addr + stage * kBoxBytes);
                         const uint64_t db0 = smem_desc(hiB2, gs_addr + jh * (kGBytes / 2));
-                        if (!(a.debug_skip & 2))
+                        if (!DCLIP_DBG_SKIP(2))
 #pragma unroll
                         for (int ks = 0; ks < 8; ++ks)          // 16 j per step = two 8-row groups = +2048 B
                             umma_f16_pair(tmem + (s >> 1) * NI, da0 + (uint64_t)(ks * 128), db0 + (uint64_t)(ks * 128), idesc2, (t | jh | ks) != 0);
@@ -352,7 +354,7 @@ k_infonce_bwd_pair(const __grid_constant__ CUtensorMap tmx0, const __grid_consta
                 if (q == 0 && lane == 0) PROF_END(p_ge, 11 + 5 * ((int)cr * 2 + hh));
                 PROF_BEGIN(p_st);
                 // 128B swizzle: 16-byte chunk ch of row r lands at chunk (ch ^ (r & 7)); (128 cr + et) & 7 == et & 7
-                if (!(a.debug_skip & 4))
+                if (!DCLIP_DBG_SKIP(4))
 #pragma unroll
                 for (int ch = 0; ch < 8; ++ch) {
                     const uint4 v = make_uint4(packed[4 * ch], packed[4 * ch + 1], packed[4 * ch + 2], packed[4 * ch + 3]);
@@ -451,7 +453,11 @@ int launch_infonce_bwd_pair(int nsides, const void* const x[2], const void* cons
     const int64_t ntiles = ceil_div(a.n, TJ);
     a.tiles_per_split = (int)ceil_div(ntiles, nsplit);
     a.error_flag = tc_error_flag();
+#ifdef DCLIP_PAIR_PROF   // timing ablation (results are garbage): only in the stall-accounting build, never in the release library
     { static const int dbg = [] { const char* e = getenv("DCLIP_PAIR_DEBUG_SKIP"); return e ? atoi(e) : 0; }(); a.debug_skip = dbg; }
+#else
+    a.debug_skip = 0;
+#endif
     // ring: 16 KB boxes, one producer warp each (finer slots keep more of the ring in flight: a slot is refilled
     // ~900-1000 cycles after its release, tools/tc_bench tmamp); 6 boxes fit next to X (96 KB) and G at d = 768
     static const int forced_slots = [] { const char* e = getenv("DCLIP_PAIR_SLOTS"); return e ? atoi(e) : 0; }();

@@ -13,7 +13,9 @@
 // and bumps the peers' arrive counters (system-scope atomics).  The waiter spins with volatile system-scope
 // loads and fences before it lets the stream continue.  Reuse of the buffers across steps is protected by a
 // third kind ("step done"): a rank does not push step k+1 into a peer that has not finished reading step k.
-// All spins are time-bounded (10 s of %globaltimer); a timeout sets the library's pipeline error flag.
+// A peer that never arrives is FATAL, as with NCCL's watchdog: after 120 s of %globaltimer the waiting kernel sets
+// the library's pipeline error flag and executes `trap`, so the stream never continues on stale operands and the
+// next CUDA call on this context raises (expected[] is not advanced, nothing of the next step is published).
 #include "common.cuh"
 
 namespace dclip {
@@ -21,6 +23,7 @@ namespace dclip {
 constexpr int kP2PMaxWorld = 16;
 constexpr int kP2PKinds = 4;
 constexpr int kP2PMaxRanges = 4;
+constexpr unsigned long long kP2PTimeoutNs = 120000000000ull;
 
 struct P2PFlags {
     unsigned int arrive[kP2PKinds][kP2PMaxWorld];
@@ -54,11 +57,17 @@ __device__ bool wait_arrivals(const P2PFlags* f, int kind, unsigned int target, 
     if (lane < world && lane != rank) {
         const unsigned long long t0 = globaltimer_ns();
         while ((int)(ld_volatile_sys(&f->arrive[kind][lane]) - target) < 0) {
-            if (globaltimer_ns() - t0 > 10000000000ull) { ok = false; break; }
+            if (globaltimer_ns() - t0 > kP2PTimeoutNs) { ok = false; break; }
             __nanosleep(64);
         }
     }
     return ok;
+}
+// a wait that timed out: record it and kill the context (no silent continuation on the previous step's data)
+__device__ __forceinline__ void p2p_fatal(int* error_flag) {
+    if (error_flag) atomicExch(error_flag, 1);
+    __threadfence_system();
+    __trap();
 }
 
 __global__ void __launch_bounds__(256) k_p2p_push(const PushArgs a) {
@@ -70,7 +79,7 @@ __global__ void __launch_bounds__(256) k_p2p_push(const PushArgs a) {
         // every block waits (the grid may not be co-resident with a block that would do it for all)
         if (threadIdx.x < 32) {
             const unsigned int target = ld_volatile_sys(&mine->expected[a.wait_kind]) + 1;
-            if (!wait_arrivals(mine, a.wait_kind, target, a.world, a.rank, threadIdx.x)) s_ok = 0;
+            if (!wait_arrivals(mine, a.wait_kind, target, a.world, a.rank, threadIdx.x)) p2p_fatal(a.error_flag);
         }
         __syncthreads();
         __threadfence_system();
@@ -87,7 +96,6 @@ __global__ void __launch_bounds__(256) k_p2p_push(const PushArgs a) {
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
-        if (!s_ok && a.error_flag) atomicExch(a.error_flag, 1);
         if (atomicAdd(&mine->done_ctr, 1u) == gridDim.x - 1) {        // last block: everything of this rank has landed
             __threadfence_system();
             if (a.signal_kind >= 0)
@@ -105,8 +113,7 @@ __global__ void __launch_bounds__(256) k_p2p_push(const PushArgs a) {
         // the kernel (hence the stream) does not proceed before the peers' pushes of the same kind are here
         if (threadIdx.x < 32) {
             const unsigned int target = ld_volatile_sys(&mine->expected[a.signal_kind]) + 1;
-            const bool ok = wait_arrivals(mine, a.signal_kind, target, a.world, a.rank, threadIdx.x);
-            if (!__all_sync(0xffffffffu, ok) && threadIdx.x == 0 && a.error_flag) atomicExch(a.error_flag, 1);
+            if (!wait_arrivals(mine, a.signal_kind, target, a.world, a.rank, threadIdx.x)) p2p_fatal(a.error_flag);
             __threadfence_system();
             __syncwarp();
             if (threadIdx.x == 0) mine->expected[a.signal_kind] += 1;
@@ -116,8 +123,7 @@ __global__ void __launch_bounds__(256) k_p2p_push(const PushArgs a) {
 
 __global__ void k_p2p_wait(P2PFlags* mine, int kind, int world, int rank, int* error_flag) {
     const unsigned int target = ld_volatile_sys(&mine->expected[kind]) + 1;
-    const bool ok = wait_arrivals(mine, kind, target, world, rank, threadIdx.x);
-    if (!__all_sync(0xffffffffu, ok) && threadIdx.x == 0 && error_flag) atomicExch(error_flag, 1);
+    if (!wait_arrivals(mine, kind, target, world, rank, threadIdx.x)) p2p_fatal(error_flag);
     __threadfence_system();
     __syncwarp();
     if (threadIdx.x == 0) mine->expected[kind] += 1;

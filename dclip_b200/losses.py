@@ -19,7 +19,7 @@ from ._lib import check, dtype_code, path_code, ptr, require_cuda, stream_ptr, w
 
 __all__ = [
     "compute_contrastive_loss", "cosine_distillation_loss", "DistillationLoss", "distill_loss_fwd_bwd",
-    "sharded_distill_loss_fwd_bwd", "ShardedDistillationLoss", "CudaLossOps", "GraphedStep",
+    "sharded_distill_loss_fwd_bwd", "ShardedDistillationLoss", "CudaLossOps", "GraphedStep", "close_peer_buffers",
 ]
 
 
@@ -45,7 +45,7 @@ def distill_loss_fwd_bwd(s_img, s_txt, t_img=None, t_txt=None, temperature=0.05,
     dev = require_cuda(s_img, s_txt, t_img, t_txt)
     lib = _lib.load_library()
     B, d = s_img.shape
-    pc = path_code(path)
+    pc = _lib.resolve_loss_path(path, s_img, temperature)      # auto: tcgen05 path for 16-bit inputs, FP32 otherwise
     losses = torch.empty(4, dtype=torch.float32, device=dev)
     d_img = torch.empty_like(s_img) if need_grad else None
     d_txt = torch.empty_like(s_txt) if need_grad else None
@@ -78,8 +78,8 @@ class HostDistillStep:
         self.dev = torch.device(device)
         self.B, self.d, self.dtype = int(B), int(d), dtype
         self.hyper = (float(temperature), float(w_img), float(w_txt), float(w_con), float(grad_scale))
-        self.pc = path_code(path)
         self.bufs = [torch.empty((B, d), dtype=dtype, device=self.dev) for _ in range(4)]
+        self.pc = _lib.resolve_loss_path(path, self.bufs[0], temperature)
         self.losses = torch.empty(4, dtype=torch.float32, device=self.dev)
         self.losses_host = torch.empty(4, dtype=torch.float32).pin_memory()
         self.d_img = torch.empty((B, d), dtype=dtype, device=self.dev)
@@ -302,7 +302,7 @@ def sharded_distill_loss_fwd_bwd(s_img, s_txt, t_img=None, t_txt=None, temperatu
     """
     import torch.distributed as dist
 
-    if ops is None and _fused_sharded_ok(s_img, temperature, path):
+    if ops is None and _fused_sharded_ok(s_img, temperature, path, group):
         return _sharded_fused(s_img, s_txt, t_img, t_txt, temperature, w_img, w_txt, w_con, grad_scale, need_grad, group, comm)
     ops = ops or CudaLossOps(path)
     world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -355,46 +355,52 @@ def sharded_distill_loss_fwd_bwd(s_img, s_txt, t_img=None, t_txt=None, temperatu
     return losses, d_img, d_txt
 
 
-def _fused_sharded_ok(x, temperature, path):
+def _fused_sharded_ok(x, temperature, path, group=None):
     """The fused 7-launch per-rank path needs the tensor kernels: 16-bit inputs (or path="tensor"),
     d % 128 == 0, d <= 768, temperature >= 0.025, an sm_100 device."""
-    if path == "fp32" or not x.is_cuda:
+    if not x.is_cuda:
         return False
-    if path == "auto" and x.dtype == torch.float32:
-        return False
-    d = x.shape[1]
-    lib = _lib.load_library()
-    return (d % 128 == 0 and 128 <= d <= 768 and temperature >= 0.025
-            and lib.dclip_device_supports_tensor_path(x.device.index or 0) == 1)
+    if path == "tensor":      # explicit request: any dtype, the shape rules are enforced by the library
+        d = x.shape[1]
+        return (d % 128 == 0 and 128 <= d <= 768 and temperature >= 0.025
+                and _lib.load_library().dclip_device_supports_tensor_path(x.device.index or 0) == 1)
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    return _lib.resolve_loss_path(path, x, temperature, global_batch=x.shape[0] * world) == _lib.PATH_TENSOR
 
 
-_PEER_BUFFERS = {}
+_PEER_BUFFERS = {}        # (process group object, m, n, d, device index) -> (PeerBuffer | None, ops_bytes)
 
 
 def _peer_buffer(group, m, n, d, world, dev):
     """Symmetric buffer of one (group, shape): u_all | v_all [n, d] fp16, stat [world, 2m + 4] fp32, flags.
-    Returns None (and remembers it) when the peer mapping cannot be established on this system."""
-    import os
+    Returns (None, ops_bytes) - on EVERY rank, and remembers it - when the peer mapping cannot be established
+    anywhere: PeerBuffer's constructor agrees on success collectively after each phase, so a failure on some
+    ranks never leaves the others inside a mismatched collective."""
     import warnings
 
     import torch.distributed as dist
-    key = (id(group), m, n, d, dev.index)
+    pg = group if group is not None else dist.group.WORLD
+    key = (pg, m, n, d, dev.index)          # the group OBJECT (kept alive by the cache), not its id()
     if key not in _PEER_BUFFERS:
-        from .peer import PeerBuffer
+        from .peer import PeerBuffer, PeerSetupError
         ops_bytes = (n * d * 2 + 255) // 256 * 256
         stat_bytes = world * (2 * m + 4) * 4
-        buf, ok = None, 1
         try:
             buf = PeerBuffer(2 * ops_bytes + stat_bytes, dev, group)
-        except RuntimeError as e:                                   # e.g. cudaIpc not permitted in this container
+        except PeerSetupError as e:          # raised on all ranks together (e.g. cudaIpc not permitted in this container)
             warnings.warn(f"dclip_b200: peer-memory exchange unavailable ({e}); using NCCL all-gathers")
-            ok = 0
-        flag = torch.tensor([ok], device=dev)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)    # all ranks or none
-        if int(flag) == 0:
             buf = None
         _PEER_BUFFERS[key] = (buf, ops_bytes)
     return _PEER_BUFFERS[key]
+
+
+def close_peer_buffers():
+    """Unmap and free every cached symmetric buffer (collective: call on all ranks, before destroy_process_group)."""
+    for key in sorted(_PEER_BUFFERS, key=lambda k: k[1:]):
+        buf, _ = _PEER_BUFFERS.pop(key)
+        if buf is not None:
+            buf.close()
 
 
 def _sharded_fused(s_img, s_txt, t_img, t_txt, temperature, w_img, w_txt, w_con, grad_scale, need_grad, group, comm="auto"):

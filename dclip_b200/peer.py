@@ -15,8 +15,16 @@ from ._lib import check, stream_ptr
 KIND_OPERANDS, KIND_STATS, KIND_DONE = 0, 1, 2
 
 
+class PeerSetupError(RuntimeError):
+    """The symmetric buffer could not be set up; raised on EVERY rank of the group together."""
+
+
 class PeerBuffer:
-    """``nbytes`` of symmetric device memory (+ the flag block) shared by the ranks of ``group``."""
+    """``nbytes`` of symmetric device memory (+ the flag block) shared by the ranks of ``group``.
+
+    Construction is collective and fails collectively: after each phase (allocate + export, map the peers) the
+    ranks all-reduce a status, so either every rank returns a usable buffer or every rank raises PeerSetupError
+    after releasing what it had allocated / mapped - no rank is left waiting in a collective the others skipped."""
 
     def __init__(self, nbytes, device, group=None):
         import torch.distributed as dist
@@ -27,25 +35,54 @@ class PeerBuffer:
         self.rank = dist.get_rank(group)
         self.flags_offset = (int(nbytes) + 255) // 256 * 256
         self.nbytes = self.flags_offset + self.lib.dclip_p2p_flags_bytes()
+        self.base = None
+        self.peers = [None] * self.world
+        self._closed = True
+
+        def agree(ok, err):
+            flag = torch.tensor([1 if ok else 0], device=device, dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if int(flag) == 0:
+                self._release()
+                raise PeerSetupError(err or "a peer rank could not set up its symmetric buffer")
+
         with torch.cuda.device(device):
-            base = ctypes.c_void_p()
-            handle = ctypes.create_string_buffer(64)
-            check(self.lib.dclip_p2p_alloc(self.nbytes, ctypes.byref(base), handle), "p2p_alloc")
-            self.base = base.value
-            check(self.lib.dclip_p2p_init_flags(ctypes.c_void_p(self.base), self.flags_offset, KIND_DONE), "p2p_init_flags")
+            # phase 1: allocate, initialise the flags, export the handle
+            err, handle = None, ctypes.create_string_buffer(64)
+            try:
+                base = ctypes.c_void_p()
+                check(self.lib.dclip_p2p_alloc(self.nbytes, ctypes.byref(base), handle), "p2p_alloc")
+                self.base = base.value
+                check(self.lib.dclip_p2p_init_flags(ctypes.c_void_p(self.base), self.flags_offset, KIND_DONE), "p2p_init_flags")
+            except RuntimeError as e:
+                err = str(e)
+            agree(err is None, err)
+            # phase 2: exchange the handles (every rank takes part: phase 1 succeeded everywhere), map the peers
             handles = [None] * self.world
             dist.all_gather_object(handles, (self.rank, handle.raw), group=group)
-            self.peers = [None] * self.world
-            for r, raw in handles:
-                if r == self.rank:
-                    self.peers[r] = self.base
-                else:
-                    p = ctypes.c_void_p()
-                    check(self.lib.dclip_p2p_open(raw, ctypes.byref(p)), "p2p_open")
-                    self.peers[r] = p.value
-            dist.barrier(group=group)            # every rank has initialised its flags and mapped its peers
+            try:
+                for r, raw in handles:
+                    if r == self.rank:
+                        self.peers[r] = self.base
+                    else:
+                        p = ctypes.c_void_p()
+                        check(self.lib.dclip_p2p_open(raw, ctypes.byref(p)), "p2p_open")
+                        self.peers[r] = p.value
+            except RuntimeError as e:
+                err = str(e)
+            agree(err is None, err)          # doubles as the barrier: every rank has initialised its flags and mapped its peers
         self._peer_arr = (ctypes.c_void_p * self.world)(*self.peers)
         self._closed = False
+
+    def _release(self):
+        """Local clean-up of a partially constructed buffer (no collective)."""
+        for r, p in enumerate(self.peers):
+            if r != self.rank and p:
+                self.lib.dclip_p2p_close(ctypes.c_void_p(p))
+        self.peers = [None] * self.world
+        if self.base:
+            self.lib.dclip_p2p_free(ctypes.c_void_p(self.base))
+            self.base = None
 
     def ptr(self, offset=0):
         return ctypes.c_void_p(self.base + offset)

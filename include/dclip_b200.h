@@ -96,6 +96,11 @@ int dclip_distill_loss_teachers(const void* s_img, const void* s_txt, const void
 int dclip_distill_loss_launch_count(int64_t m, int64_t n, int64_t d, int path, int sharded);
 /* 1 when the tcgen05 tensor path of the loss is compiled in and validated for use. */
 int dclip_tensor_path_ready(void);
+/* Resolves DCLIP_PATH_AUTO for the objective (the single place it is decided): DCLIP_PATH_TENSOR for 16-bit
+ * inputs (`dtype` != DCLIP_F32) when B >= 128 (global batch), d % 128 == 0, 128 <= d <= 768, temperature >= 0.025
+ * and the current device is sm_100; DCLIP_PATH_FP32 otherwise.  An explicit path is returned unchanged.  The host layer resolves once
+ * and hands the result to the workspace query and to the single-GPU / sharded entry points alike. */
+int dclip_resolve_loss_path(int path, int dtype, int64_t B, int64_t d, float temperature);
 
 /* Test / debug hook: 1 if a tensor-path kernel hit a bounded-wait timeout since the last call
  * (clears the flag).  Synchronises `stream`; never called on the product path. */

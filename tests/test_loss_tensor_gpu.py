@@ -21,8 +21,15 @@ def _pipeline_ok(lib):
 
 
 @pytest.mark.parametrize("B,d,dtype", [(128, 128, torch.float32), (64, 768, torch.bfloat16), (256, 768, torch.bfloat16),
-                                        (1024, 512, torch.float16), (200, 256, torch.bfloat16), (4096, 768, torch.bfloat16)])
+                                        (1024, 512, torch.float16), (200, 256, torch.bfloat16), (4096, 768, torch.bfloat16),
+                                        (4096, 768, torch.float32), (4096, 768, torch.float16)])
 def test_tensor_path_matches_oracle(built_library, B, d, dtype):
+    """Losses and gradients of the tcgen05 path within 1e-3 of the fp64 oracle (north_star's bf16/tf32 tier).
+
+    fp32 I/O (operands still fp16, fp32 accumulate) is held to 1e-3 outright - including the headline shape
+    B=4096, d=768.  With 16-bit OUTPUTS the final rounding alone costs e_r = |round(oracle) - oracle| / |oracle|
+    (~1.7e-3 for bf16), which no implementation can avoid: the error of the tensor MATH is what is left after
+    removing it in quadrature (independent errors), and that is what is held to 1e-3; both are printed."""
     from dclip_b200 import losses as L
     dev = torch.device("cuda:0")
     s_img, s_txt, t_img, t_txt = (t.to(dtype) for t in synthetic.loss_inputs(B, d, seed=B + d))
@@ -37,9 +44,14 @@ def test_tensor_path_matches_oracle(built_library, B, d, dtype):
     want = torch.stack([tot, li, lt, lc])
     got = losses.cpu().double()
     assert torch.allclose(got, want, rtol=TOL, atol=1e-5), (got, want)
-    out_tol = TOL + (2 ** -8 if dtype == torch.bfloat16 else 2 ** -10 if dtype == torch.float16 else 0)
-    assert _rel(d_img, gs * g_img) < out_tol, _rel(d_img, gs * g_img)
-    assert _rel(d_txt, gs * g_txt) < out_tol, _rel(d_txt, gs * g_txt)
+    for name, ours, ref in (("d_img", d_img, gs * g_img), ("d_txt", d_txt, gs * g_txt)):
+        total = _rel(ours, ref)
+        rounding = _rel(ref.to(dtype), ref)                       # the oracle's own gradient rounded to the output dtype
+        math_err = max(0.0, total * total - rounding * rounding) ** 0.5
+        print(f"[tensor-path parity] B={B} d={d} {dtype} {name}: total {total:.3e}  output-rounding {rounding:.3e}  "
+              f"tensor-math {math_err:.3e}  (bound {TOL:.0e})")
+        assert math_err < TOL, (name, total, rounding, math_err)
+        assert total < TOL + rounding, (name, total, rounding)
 
 
 def test_tensor_building_blocks_and_splits(built_library):

@@ -10,6 +10,7 @@ from oracle import synthetic
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
+RANK_PATHS = ("fp32",)
 
 
 def _d(a):
@@ -33,6 +34,24 @@ def test_golden_metrics(built_library, name):
     got2 = np.array([m2[dn][k] for dn in ("t2i", "i2t") for k in ("R@1", "R@5", "R@10", "MAP")])
     assert np.array_equal(got2[[0, 1, 2, 4, 5, 6]], want[[0, 1, 2, 4, 5, 6]])
     assert np.allclose(got2[[3, 7]], want[[3, 7]], rtol=0, atol=1e-12)
+
+
+def test_golden_metrics_cfg2_shape(built_library):
+    """BASELINE configs[1] shape against the REFERENCE's metrics (tests/golden/retrieval_cfg2.npz, t2i R@1 = 0.489):
+    Recall@K bit-exact on both the fused form and the materialised-matrix form, on the FP32 and the tcgen05 path."""
+    from dclip_b200 import retrieval as R
+    from test_oracle_golden import _cfg2_inputs
+    g = load_golden("retrieval_cfg2")
+    cap, img, image_ids, cap_ids = _cfg2_inputs(g)
+    want = g["metrics"]
+    for path in RANK_PATHS:
+        m = R.retrieval_metrics_from_embeddings(cap, img, image_ids, cap_ids, path=path)
+        got = np.array([m[dn][k] for dn in ("t2i", "i2t") for k in ("R@1", "R@5", "R@10", "MAP")])
+        assert np.array_equal(got[[0, 1, 2, 4, 5, 6]], want[[0, 1, 2, 4, 5, 6]]), (path, got, want)
+        assert np.allclose(got[[3, 7]], want[[3, 7]], rtol=0, atol=1e-6), path
+    m2 = R.calculate_retrieval_metrics(orc.numpy_similarity(cap, img), image_ids, cap_ids)
+    got2 = np.array([m2[dn][k] for dn in ("t2i", "i2t") for k in ("R@1", "R@5", "R@10", "MAP")])
+    assert np.array_equal(got2[[0, 1, 2, 4, 5, 6]], want[[0, 1, 2, 4, 5, 6]])
 
 
 def test_normalize_and_scores_bit_exact(built_library):
