@@ -12,8 +12,8 @@
 // Per pair: 128 rows of X_hat (I block), walking 256-row tiles J of Y_hat:
 //   phase 1   S^T[256 j x 128 i] = Y_J . X_I^T     M = 256 (CTA c: its 128 j rows), N = 128 (CTA c: 64 i rows
 //             of X, resident), K = d.  CTA c receives S^T rows [128c, 128c + 128) in TMEM columns 384-511.
-//   epilogue  thread = one j (TMEM lane); g = p (a_i + b_j), scaled by 2^13, fp16.  (The -2 [i == j] term of G
-//             is one extra phase-2 step at the end: K = the 128 Y rows facing X_I, B = -2 * 2^13 I, exact.)  Columns
+//   epilogue  thread = one j (TMEM lane); g = p (a_i + b_j) - 2 [i == j], scaled by 2^13, fp16 (the diagonal term is
+//             subtracted in fp32 before the rounding, in the one tile of the walk that faces the pair's rows).  Columns
 //             i < 64 go to the LEADER's G tile, i >= 64 to the PEER's (st.shared::cluster): each CTA ends up
 //             with G^T[256 j x 64 i] = its half of the phase-2 B operand.
 //   phase 2   dX^T[256 d x 128 i] += Y_J^T[256 d x 256 j] . G^T   per 256-wide d block: M = 256 (CTA c: d
@@ -120,7 +120,7 @@ k_infonce_bwd_pair(const __grid_constant__ CUtensorMap tmx0, const __grid_consta
     const int64_t t_begin = (int64_t)blockIdx.y * a.tiles_per_split;
     const int64_t t_end = min(ntiles, t_begin + a.tiles_per_split);
     const int T = (int)max((int64_t)0, t_end - t_begin);
-    const bool diag = blockIdx.y == 0;                    // the -2 I term of G is applied once, by column split 0
+    constexpr bool diag = false;       // the -2 I term of G is folded into the G tiles (epilogue, before the fp16 rounding): no extra MMA step
 
     PROF_BEGIN(p_kernel);
     if (threadIdx.x == 0) {
@@ -334,18 +334,44 @@ k_infonce_bwd_pair(const __grid_constant__ CUtensorMap tmx0, const __grid_consta
                 const int64_t ly = S.lse_y_block > 0 ? (gj / S.lse_y_block) * S.lse_y_stride + gj % S.lse_y_block : gj;
                 const float bj = jvalid ? exp2f((a.inv_tau - S.lse_y[ly]) * 1.4426950408889634f + kGScaleLog2) : 0.f;
                 const float vm = jvalid ? 1.f : 0.f;      // rows past n: TMA zero-filled S, coefficient forced to 0
-                // g = p (a_i + b_j); the -2 [i == j] term of G is applied to the accumulator in the final drain
+                // g = p (a_i + b_j) - 2 [i == j], all scaled by 2^13.  The diagonal term is subtracted in fp32 BEFORE the
+                // fp16 rounding: p_ii (a_i + b_i) approaches 2 as training converges and G_ii is the small difference -
+                // rounding the large value first (and subtracting an exact -2 afterwards, as a separate MMA step once
+                // did) leaves an absolute error of 2^-11 * 2 on a quantity that can be 100x smaller.  Only the one tile
+                // of the walk that faces the pair's own rows has a diagonal: a CTA-uniform branch keeps the common loop
+                // free of the compare.
+                const int64_t di = gj - (a.row_offset + row0 + hh * 64);      // my diagonal column inside this warp's 64, if in range
+                const bool tile_has_diag = j0 + (int64_t)cr * 128 < a.row_offset + row0 + hh * 64 + 64 &&
+                                           j0 + (int64_t)cr * 128 + 128 > a.row_offset + row0 + hh * 64;
                 uint32_t packed[32];
+                if (!tile_has_diag) {
 #pragma unroll
-                for (int ch = 0; ch < 8; ++ch) {
-                    const float4 a0 = lds_f4(a_addr + ch * 32), a1 = lds_f4(a_addr + ch * 32 + 16);
-                    const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                    for (int ch = 0; ch < 8; ++ch) {
+                        const float4 a0 = lds_f4(a_addr + ch * 32), a1 = lds_f4(a_addr + ch * 32 + 16);
+                        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
-                    for (int h = 0; h < 4; ++h) {
-                        const float p0 = ex2_ftz(fmaf(__uint_as_float(r[ch * 8 + 2 * h]), c, -c));
-                        const float p1 = ex2_ftz(fmaf(__uint_as_float(r[ch * 8 + 2 * h + 1]), c, -c));
-                        const __half2 hv = __floats2half2_rn(p0 * fmaf(av[2 * h], vm, bj), p1 * fmaf(av[2 * h + 1], vm, bj));
-                        packed[ch * 4 + h] = *reinterpret_cast<const uint32_t*>(&hv);
+                        for (int h = 0; h < 4; ++h) {
+                            const float p0 = ex2_ftz(fmaf(__uint_as_float(r[ch * 8 + 2 * h]), c, -c));
+                            const float p1 = ex2_ftz(fmaf(__uint_as_float(r[ch * 8 + 2 * h + 1]), c, -c));
+                            const __half2 hv = __floats2half2_rn(p0 * fmaf(av[2 * h], vm, bj), p1 * fmaf(av[2 * h + 1], vm, bj));
+                            packed[ch * 4 + h] = *reinterpret_cast<const uint32_t*>(&hv);
+                        }
+                    }
+                } else {
+                    const int dcol = (di >= 0 && di < 64 && jvalid) ? (int)di : -1;
+#pragma unroll
+                    for (int ch = 0; ch < 8; ++ch) {
+                        const float4 a0 = lds_f4(a_addr + ch * 32), a1 = lds_f4(a_addr + ch * 32 + 16);
+                        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) {
+                            const float p0 = ex2_ftz(fmaf(__uint_as_float(r[ch * 8 + 2 * h]), c, -c));
+                            const float p1 = ex2_ftz(fmaf(__uint_as_float(r[ch * 8 + 2 * h + 1]), c, -c));
+                            const float g0 = fmaf(p0, fmaf(av[2 * h], vm, bj), dcol == ch * 8 + 2 * h ? -16384.0f : 0.f);
+                            const float g1 = fmaf(p1, fmaf(av[2 * h + 1], vm, bj), dcol == ch * 8 + 2 * h + 1 ? -16384.0f : 0.f);
+                            const __half2 hv = __floats2half2_rn(g0, g1);
+                            packed[ch * 4 + h] = *reinterpret_cast<const uint32_t*>(&hv);
+                        }
                     }
                 }
                 if (q == 0 && lane == 0) PROF_END(p_cp, 10 + 5 * ((int)cr * 2 + hh));

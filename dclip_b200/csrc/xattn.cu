@@ -925,6 +925,27 @@ int dclip_xattn_bwd(const void* text, const void* image, int64_t B, int64_t T, i
     return DCLIP_OK;
 }
 
+// out[n, m] = x[n, k] W[m, k]^T (+ bias[m]) - the per-token `text_projection` loop of training/text_tokenizer.py:202-207
+// as ONE GEMM over all rows (nn.Linear layout: W is [out_features, in_features]).  16-bit inputs: tcgen05 (gemm_tc.cu,
+// fp32 accumulation, output rounded once); fp32 inputs: the exact fp32 GEMM.
+int dclip_linear_rows(const void* x, const void* W, const float* bias, int64_t n, int64_t k, int64_t m, int dtype, void* out, void* stream) {
+    DCLIP_REQUIRE(x && W && out && n > 0 && k > 0 && m > 0, "linear_rows: bad arguments");
+    DCLIP_REQUIRE(n < (1ll << 31) && k < (1ll << 31) && m < (1ll << 31), "linear_rows: dimension too large");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == DCLIP_F32) {
+        GemmGroup g{};
+        g.p[0] = gemm(static_cast<const float*>(x), (int)k, false, static_cast<const float*>(W), (int)k, true, static_cast<float*>(out), (int)m,
+                      (int)n, (int)m, (int)k, bias);
+        g.count = 1;
+        return launch_gemm_group(g, st);
+    }
+    DCLIP_REQUIRE(k % 8 == 0 && m % 8 == 0, "linear_rows: the 16-bit path needs in / out features in multiples of 8 (got %lld, %lld)", (long long)k, (long long)m);
+    if (!device_is_sm100()) return fail(DCLIP_ERR_ARCH, "linear_rows: the 16-bit path needs an sm_100 device");
+    TcGemmProblem p = tcp(x, (int)k, false, W, (int)k, false, nullptr, (int)m, (int)n, (int)m, (int)k, bias);
+    p.C16 = out; p.ldc16 = (int)m;
+    return launch_gemm_tc(&p, 1, dtype, st);
+}
+
 int dclip_aggregate_fwd(const void* x, int64_t B, int64_t L, int64_t d, int dtype, float temperature, void* out, float* weights,
                         void* stream) {
     DCLIP_REQUIRE(x && out && B > 0 && L > 0 && d > 0 && temperature > 0.f, "aggregate_fwd: bad arguments");

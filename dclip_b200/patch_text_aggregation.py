@@ -209,10 +209,15 @@ class GraphedTeacherStep:
     ``zero_grad(set_to_none=True)`` afterwards (every replay overwrites the gradients anyway).
 
     loss_fn(module, *inputs) -> scalar loss tensor; shapes and dtypes are fixed at construction.
+    optimizer: an optional dclip_b200.optim.FusedAdam over the same parameters; its step (two launches for all 12
+    tensors, step counter and clip coefficient in device memory) is captured at the end of the graph, so one replay
+    is the reference's whole ``backward(); optimizer.step()`` (train_contrastive_teacher.py:361-362).  The warm-up
+    iterations do not step the optimizer.
     """
 
-    def __init__(self, module, loss_fn, example_inputs, warmup=3):
+    def __init__(self, module, loss_fn, example_inputs, warmup=3, optimizer=None):
         self.module = module
+        self.optimizer = optimizer
         self.params = [p for p in module.parameters() if p.requires_grad]
         self.static_in = [t.detach().clone() for t in example_inputs]
         cur = torch.cuda.current_stream()
@@ -231,6 +236,8 @@ class GraphedTeacherStep:
         with torch.cuda.graph(self.graph):
             self.static_loss = loss_fn(module, *self.static_in)
             self.static_loss.backward()
+            if optimizer is not None:
+                optimizer.step()
 
     def __call__(self, *inputs):
         for dst, src in zip(self.static_in, inputs):

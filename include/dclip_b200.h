@@ -294,6 +294,54 @@ int dclip_aggregate_bwd(const void* x, const float* weights, const void* d_out, 
 int dclip_combine_guard_fwd(const void* a, const void* b, int64_t n, int dtype, void* out, int* flag, void* stream);
 int dclip_combine_guard_bwd(const void* d_out, int64_t n, int dtype, const int* flag, void* d_a, void* d_b, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Ragged batch assembly - the step immediately upstream of the cross-attention:
+ *   the zero-pad / truncate / stack loops of training/patch_text_aggregation.py:555-620 and the token filter +
+ *   per-token text_projection loop of training/text_tokenizer.py:196-213, as a varlen layout.
+ * ------------------------------------------------------------------------------------------ */
+/* Token filter of text_tokenizer.py:199-201: token i of sample b is kept iff input_ids[b,i] > 0, 0 < i < L - 1 and
+ * attention_mask[b,i] == 1.  lengths[b] = kept tokens, positions[b, 0..lengths[b]) = their positions, in order. */
+int dclip_token_select(const int64_t* input_ids, const int64_t* attention_mask, int64_t B, int64_t L, int* lengths,
+                       int* positions, void* stream);
+/* cu_seqlens[B + 1] = exclusive scan of max(lengths, min_len); *max_len (optional, device) = the batch maximum. */
+int dclip_cu_seqlens(const int* lengths, int64_t B, int min_len, int* cu_seqlens, int* max_len, void* stream);
+/* out[B, max_len, d]: row t of sample b = its t-th source row for t < len_b (truncated at max_len), EXACT zeros
+ * beyond (the padding stays attended downstream: no mask exists in the reference).
+ *   flat source  : src [total, d], cu_seqlens [B + 1]               (positions NULL; lengths optional)
+ *   strided source: src [B, L_src, d], lengths [B], positions [B, L_src]   (the projected hidden states)
+ *   fallback [B, d] (optional): used as row 0 of a sample with no rows (text_tokenizer.py:209-211)
+ *   nan_guard: a sample holding a NaN / Inf is written as all zeros (patch_text_aggregation.py:542-544);
+ *              sample_flags int[B] receives the flags. */
+int dclip_pad_gather(const void* src, int dtype, const int* cu_seqlens, const int* lengths, const int* positions,
+                     int64_t L_src, const void* fallback, int nan_guard, int* sample_flags, int64_t B, int64_t max_len,
+                     int64_t d, void* out, void* stream);
+/* out[n, m] = x[n, k] W[m, k]^T (+ bias[m], fp32): all token projections as one GEMM (text_tokenizer.py:202-207).
+ * 16-bit dtype: tcgen05, fp32 accumulation; DCLIP_F32: exact fp32 GEMM. */
+int dclip_linear_rows(const void* x, const void* W, const float* bias, int64_t n, int64_t k, int64_t m, int dtype,
+                      void* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused multi-tensor Adam / AdamW + global-norm clip: torch.optim.Adam at
+ *   training/train_contrastive_teacher.py:245-248, :360-362; AdamW + gradient_clip_val = 0.5 at
+ *   training/CLIP_image_distillation.py:679-682, training/CLIP_image_distill_training.py:41-42.
+ * `state` = dclip_optim_state_bytes() of device memory holding the step counter and the clip coefficient, so the
+ * two launches are graph-capturable.  Moments are fp32; parameters / gradients share `dtype`.  Up to 64 tensors.
+ * ------------------------------------------------------------------------------------------ */
+size_t dclip_optim_state_bytes(void);
+size_t dclip_optim_workspace_bytes(const int64_t* numel, int count);
+int dclip_optim_init_state(void* state, void* stream);
+/* clip_coef = min(1, max_norm / (||all grads||_2 + 1e-6)) into `state` (torch.nn.utils.clip_grad_norm_); the
+ * gradients themselves are left untouched, dclip_adam_step applies the coefficient.  max_norm <= 0: only the norm. */
+int dclip_grad_clip_coef(const void* const* grads, const int64_t* numel, int count, int dtype, float max_norm, void* state,
+                         void* workspace, size_t workspace_bytes, void* stream);
+/* One optimizer step over all tensors.  lr_dev (optional, device float) overrides lr (schedulers inside a graph).
+ * decoupled_weight_decay: 1 = AdamW, 0 = Adam's L2 form. */
+int dclip_adam_step(void* const* params, const void* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                    const int64_t* numel, int count, int dtype, float lr, const float* lr_dev, float beta1, float beta2,
+                    float eps, float weight_decay, int decoupled_weight_decay, void* state, void* stream);
+/* Host read of {grad_norm, clip_coef, step} (synchronises `stream`; logging / tests). */
+int dclip_optim_read_state(const void* state, float* grad_norm, float* clip_coef, int* step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
