@@ -79,6 +79,9 @@ SIGNATURES = {
     "dclip_topk_ip_tc": (_i32, [_vp, _i32, _vp, _i32, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
                                 _vp]),
     "dclip_topk_merge": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "dclip_global_embedding_flags_bytes": (_sz, [_i64]),
+    "dclip_global_embedding_fwd": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _f32, _vp, _vp, _vp, _vp, _vp]),
+    "dclip_global_embedding_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i32, _f32, _vp, _vp, _vp]),
     "dclip_token_select": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     "dclip_cu_seqlens": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp]),
     "dclip_pad_gather": (_i32, [_vp, _i32, _vp, _vp, _vp, _i64, _vp, _i32, _vp, _i64, _i64, _i64, _vp, _vp]),
@@ -88,7 +91,7 @@ SIGNATURES = {
     "dclip_optim_init_state": (_i32, [_vp, _vp]),
     "dclip_grad_clip_coef": (_i32, [ctypes.POINTER(_vp), ctypes.POINTER(_i64), _i32, _i32, _f32, _vp, _vp, _sz, _vp]),
     "dclip_adam_step": (_i32, [ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_i64),
-                               _i32, _i32, _f32, _vp, _f32, _f32, _f32, _f32, _i32, _vp, _vp]),
+                               _i32, _i32, ctypes.c_double, _vp, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, _i32, _vp, _vp]),
     "dclip_optim_read_state": (_i32, [_vp, ctypes.POINTER(_f32), ctypes.POINTER(_f32), ctypes.POINTER(_i32), _vp]),
 }
 

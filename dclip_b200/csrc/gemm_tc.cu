@@ -11,7 +11,10 @@
 //   B MN-major : B stored [K, N]  (X for dW, W for dX)         4 boxes [64 k x 64 n], LBO = 8 KB
 // (the MN-major canonical layout is the same bytes TMA writes for a [k rows x 64 columns] box; both
 // were validated against a CPU GEMM with tools/tc_probe).  Tile 128 x 256, K in 64-wide stages, 4-stage
-// ring, 4 producer warps, 1 MMA-issuer warp, 4 epilogue warps (thread = output row).  Persistent CTAs.
+// ring, 4 producer warps, 1 MMA-issuer warp, 8 epilogue warps (thread = output row; two warps per TMEM lane
+// quadrant split the columns; bias / residual / conversion in registers, 16-byte stores straight from the row the
+// thread owns - the epilogue of a K = 768 tile must not cost more than its 12-stage main loop).  Persistent CTAs.
+// bias / residual: fp32 or the operands' 16-bit type; outputs: fp32 C and / or 16-bit C16.
 #include "common.cuh"
 #include "gemm_tc.h"
 #include "tcgen05.cuh"
@@ -24,11 +27,12 @@ constexpr int kGStages = 4;
 constexpr int kGAStage = GM * 128;          // 16 KB
 constexpr int kGBStage = GN * 128;          // 32 KB
 constexpr int kGStageBytes = kGAStage + kGBStage;
-constexpr int kGThreads = (kGStages + 1 + 4) * 32;
+constexpr int kGEpiWarps = 8;           // two per TMEM lane quadrant: each takes half of the tile's 256 columns
+constexpr int kGThreads = (kGStages + 1 + kGEpiWarps) * 32;
 constexpr uint32_t kSpinG = 1u << 24;
 
 struct TcGemmDev {
-    float* C; const float* bias; const float* residual;
+    float* C; const void* bias; const void* residual; int bias_kind, res_kind;
     int M, N, K, ldc, ldr;
     int a_mn, b_mn;
     int tiles_n, tile_begin;      // tiles of this problem occupy [tile_begin, tile_begin + tiles_m * tiles_n)
@@ -70,7 +74,7 @@ __global__ void __launch_bounds__(kGThreads, 1) k_gemm_tc(const __grid_constant_
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kGStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kGEpiWarps * 32); }
         fence_barrier_init();
     }
     if (warp == kGStages) tmem_alloc(tmem_ptr, 512);
@@ -139,72 +143,89 @@ __global__ void __launch_bounds__(kGThreads, 1) k_gemm_tc(const __grid_constant_
             }
         }
     } else {
-        // ---- epilogue: TMEM hands each thread one output ROW; global memory wants a warp on one row.  Each
-        // warp transposes its 32 x 32 chunk through a private padded smem tile so that bias / residual reads
-        // and the C stores are 128-byte coalesced float4 accesses.
+        // ---- epilogue: TMEM hands each thread one output ROW (lane) and 32 consecutive columns per load; the thread
+        // adds bias / residual in registers and stores its 64 (16-bit) or 128 (fp32) contiguous bytes with 16-byte
+        // stores - no shared-memory transposition, ~70 instructions per 32 x 32 chunk.  Eight warps: warp % 4 is the
+        // TMEM lane quadrant it may read, the two warps of a quadrant split the tile's columns.  N % 8 == 0 (checked on
+        // the host), so every 8-column group is entirely inside or outside C.
         const int qd = warp & 3;
+        const int half = (warp - (kGStages + 1)) >> 2;
         const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
-        float* tile_s = reinterpret_cast<float*>(ring + kGStages * kGStageBytes + 256) + (size_t)qd * 32 * 33;
+        const bool bf = g.ab_fmt == (int)kFmtBF16;
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const TileCoord tc = tile_coord(g, tile);
-            const TcGemmDev& P = g.p[tc.pi];
+            const TcGemmDev P = g.p[tc.pi];
             const int b = it & 1;
             ok = mbar_wait(&acc_full[b], (it >> 1) & 1, kSpinG);
             ok = __all_sync(0xffffffffu, ok);
             if (!ok) break;
             fence_after_thread_sync();
-            const int rbase = tc.m0 + qd * 32;
+            const int grow = tc.m0 + qd * 32 + lane;
+            const bool row_ok = grow < P.M;
 #pragma unroll 1
-            for (int c0 = 0; c0 < GN; c0 += 32) {
+            for (int c0 = half * (GN / 2); c0 < (half + 1) * (GN / 2); c0 += 32) {
+                const int col = tc.n0 + c0;
+                if (col >= P.N) break;                        // warp-uniform
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(tmem + lane_addr + b * GN + c0, r);
                 tmem_ld_wait();
-                if (tc.n0 + c0 >= P.N) continue;              // warp-uniform
+                float v[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) tile_s[lane * 33 + i] = __uint_as_float(r[i]);
-                __syncwarp();
-                const int rsub = lane >> 3, cg = (lane & 7) * 4;
-                const int col = tc.n0 + c0 + cg;
-                const bool full4 = col + 4 <= P.N && (P.ldc & 3) == 0;
-                float bv[4] = {0.f, 0.f, 0.f, 0.f};
-                if (P.bias)
+                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+                const int ngrp = min(4, (P.N - col) >> 3);      // 8-column groups of this chunk inside C (warp-uniform)
+                if (P.bias) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) bv[j] = col + j < P.N ? P.bias[col + j] : 0.f;
+                    for (int q = 0; q < 4; ++q)
+                        if (q < ngrp) {
+                            float bv[8];
+                            if (P.bias_kind == 0) load8<float>(static_cast<const float*>(P.bias) + col + q * 8, bv);
+                            else if (bf) load8<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(P.bias) + col + q * 8, bv);
+                            else load8<__half>(static_cast<const __half*>(P.bias) + col + q * 8, bv);
 #pragma unroll
-                for (int rit = 0; rit < 8; ++rit) {
-                    const int rr = rit * 4 + rsub;
-                    const int grow = rbase + rr;
-                    if (grow < P.M && col < P.N) {
-                        float v[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) v[j] = tile_s[rr * 33 + cg + j] + bv[j];
-                        float* cp = P.C ? P.C + (size_t)grow * P.ldc + col : nullptr;
-                        if (full4) {
-                            if (P.residual) {
-                                const float4 rv = *reinterpret_cast<const float4*>(P.residual + (size_t)grow * P.ldr + col);
-                                v[0] += rv.x; v[1] += rv.y; v[2] += rv.z; v[3] += rv.w;
-                            }
-                            if (P.accumulate) {
-                                const float4 cv = *reinterpret_cast<const float4*>(cp);
-                                v[0] += cv.x; v[1] += cv.y; v[2] += cv.z; v[3] += cv.w;
-                            }
-                            if (cp) *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
-                        } else {
-                            for (int j = 0; j < 4 && col + j < P.N; ++j) {
-                                if (P.residual) v[j] += P.residual[(size_t)grow * P.ldr + col + j];
-                                if (P.accumulate) v[j] += cp[j];
-                                if (cp) cp[j] = v[j];
-                            }
+                            for (int i = 0; i < 8; ++i) v[q * 8 + i] += bv[i];
                         }
-                        if (P.c16_kind)
-                            for (int j = 0; j < 4 && col + j < P.N; ++j) {
-                                if (P.c16_kind == 1) static_cast<__nv_bfloat16*>(P.C16)[(size_t)grow * P.ldc16 + col + j] = __float2bfloat16_rn(v[j]);
-                                else static_cast<__half*>(P.C16)[(size_t)grow * P.ldc16 + col + j] = __float2half_rn(v[j]);
+                }
+                if (row_ok) {
+                    if (P.residual) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (q < ngrp) {
+                                float rv[8];
+                                const size_t off = (size_t)grow * P.ldr + col + q * 8;
+                                if (P.res_kind == 0) load8<float>(static_cast<const float*>(P.residual) + off, rv);
+                                else if (bf) load8<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(P.residual) + off, rv);
+                                else load8<__half>(static_cast<const __half*>(P.residual) + off, rv);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) v[q * 8 + i] += rv[i];
+                            }
+                    }
+                    if (P.C) {
+                        float* cp = P.C + (size_t)grow * P.ldc + col;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (q < ngrp) {
+                                if (P.accumulate) {
+                                    float cv[8];
+                                    load8<float>(cp + q * 8, cv);
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) v[q * 8 + i] += cv[i];
+                                }
+                                const float o[8] = {v[q * 8], v[q * 8 + 1], v[q * 8 + 2], v[q * 8 + 3], v[q * 8 + 4], v[q * 8 + 5], v[q * 8 + 6], v[q * 8 + 7]};
+                                store8<float>(cp + q * 8, o);
+                            }
+                    }
+                    if (P.c16_kind) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (q < ngrp) {
+                                const float o[8] = {v[q * 8], v[q * 8 + 1], v[q * 8 + 2], v[q * 8 + 3], v[q * 8 + 4], v[q * 8 + 5], v[q * 8 + 6], v[q * 8 + 7]};
+                                const size_t off = (size_t)grow * P.ldc16 + col + q * 8;
+                                if (bf) store8<__nv_bfloat16>(static_cast<__nv_bfloat16*>(P.C16) + off, o);
+                                else store8<__half>(static_cast<__half*>(P.C16) + off, o);
                             }
                     }
                 }
-                __syncwarp();
             }
             fence_before_thread_sync();
             mbar_arrive(&acc_empty[b]);
@@ -234,6 +255,11 @@ int launch_gemm_tc(const TcGemmProblem* probs, int count, int dtype16, cudaStrea
         if (!q.C && !q.C16) return fail(DCLIP_ERR_INVALID, "gemm_tc: problem %d has no output", i);
         if (q.accumulate && !q.C) return fail(DCLIP_ERR_INVALID, "gemm_tc: accumulate needs the fp32 output");
         if (q.lda % 8 || q.ldb % 8 || q.ldc % 4) return fail(DCLIP_ERR_INVALID, "gemm_tc: leading dimensions must keep 16-byte row alignment");
+        if (q.N % 8) return fail(DCLIP_ERR_INVALID, "gemm_tc: N must be a multiple of 8 (got %d)", q.N);
+        if ((q.C && ((reinterpret_cast<uintptr_t>(q.C) & 15) || q.ldc % 4)) || (q.C16 && ((reinterpret_cast<uintptr_t>(q.C16) & 15) || (q.ldc16 > 0 ? q.ldc16 : q.ldc) % 8)))
+            return fail(DCLIP_ERR_INVALID, "gemm_tc: outputs must be 16-byte aligned with 16-byte aligned rows");
+        if ((q.bias && (reinterpret_cast<uintptr_t>(q.bias) & 15)) || (q.residual && ((reinterpret_cast<uintptr_t>(q.residual) & 15) || q.ldr % (q.res_kind ? 8 : 4))))
+            return fail(DCLIP_ERR_INVALID, "gemm_tc: bias / residual must be 16-byte aligned");
         bool okm;
         // A: K-major stored [M, K] (rows = M, cols = K); MN-major stored [K, M]
         if (!q.a_mn) okm = make_tmap_2d_sw128_ld(&g.ta[i], q.A, (uint64_t)q.M, (uint64_t)q.K, (uint64_t)q.lda, GM, dt);
@@ -242,7 +268,8 @@ int launch_gemm_tc(const TcGemmProblem* probs, int count, int dtype16, cudaStrea
         else okm = okm && make_tmap_2d_sw128_ld(&g.tb[i], q.B, (uint64_t)q.K, (uint64_t)q.N, (uint64_t)q.ldb, GKS, dt);
         if (!okm) return fail(DCLIP_ERR_CUDA, "gemm_tc: cuTensorMapEncodeTiled failed for problem %d", i);
         TcGemmDev& d = g.p[i];
-        d.C = q.C; d.bias = q.bias; d.residual = q.residual;
+        d.C = q.C; d.bias = q.bias; d.residual = q.residual; d.bias_kind = q.bias_kind; d.res_kind = q.res_kind;
+
         d.M = q.M; d.N = q.N; d.K = q.K; d.ldc = q.ldc; d.ldr = q.ldr;
         d.a_mn = q.a_mn; d.b_mn = q.b_mn; d.accumulate = q.accumulate;
         d.C16 = q.C16; d.c16_kind = q.C16 ? (dtype16 == DCLIP_BF16 ? 1 : 2) : 0; d.ldc16 = q.ldc16 > 0 ? q.ldc16 : q.ldc;
@@ -251,7 +278,7 @@ int launch_gemm_tc(const TcGemmProblem* probs, int count, int dtype16, cudaStrea
         tiles += ((q.M + GM - 1) / GM) * d.tiles_n;
     }
     g.total_tiles = tiles;
-    const size_t smem = 1024 + (size_t)kGStages * kGStageBytes + 256 + 4 * 32 * 33 * sizeof(float);
+    const size_t smem = 1024 + (size_t)kGStages * kGStageBytes + 256;
     DCLIP_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_gemm_tc<<<min(tiles, sm_count()), kGThreads, smem, st>>>(g);
     DCLIP_LAUNCH_OK("k_gemm_tc");

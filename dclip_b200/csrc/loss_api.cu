@@ -1,4 +1,6 @@
 // C-ABI of the distillation objective: argument checking, workspace carving, path choice.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "loss_internal.h"
 
@@ -223,6 +225,7 @@ int dclip_debug_pipeline_error(void* stream) { return tc_check_error_flag(static
 
 int dclip_distill_loss_launch_count(int64_t m, int64_t n, int64_t d, int path, int sharded) {
     if (path == DCLIP_PATH_AUTO) path = DCLIP_PATH_FP32;   // callers pass the resolved path (dclip_resolve_loss_path)
+    if (path == DCLIP_PATH_FP32 && !sharded && small_loss_shape_ok(m, d) && m == n) return 1;      // k_distill_small
     if (path == DCLIP_PATH_FP32) return sharded ? 11 : 6;   // prep, rowlse+combine, sums, grad, tail (x2 sides when sharded)
     // tensor path, single GPU: prep_pair, one-pass forward tiles, finalize, backward tiles (+ partial combines), tail
     if (!sharded) return 5 + (tc_nsplit(m, n, d, 2) > 1 ? 2 : 0);
@@ -368,6 +371,14 @@ static int distill_loss_impl(int phase, const void* s_img, const void* s_txt, co
         return fail(DCLIP_ERR_UNSUPPORTED, "distill_loss: tensor path needs d %% 128 == 0, 128 <= d <= 768 and temperature >= 0.025 (d=%lld tau=%g)", (long long)d, temperature);
     if (!tensor && path != DCLIP_PATH_FP32) return fail(DCLIP_ERR_INVALID, "distill_loss: unknown path %d", path);
 
+    // small batches (the teacher step's B = 32, the reference's own distillation batch): the whole objective in ONE
+    // launch of one 8-CTA cluster instead of six launch-latency-bound kernels (DCLIP_LOSS_SMALL=0: generic path)
+    if (phase == 0 && !tensor && small_loss_shape_ok(B, d) && (B * (ceil_div(ceil_div(d, 8), 8) * 8 + 1) * 16 + B * B * 12) < 200 * 1024) {
+        static const bool off = [] { const char* e = getenv("DCLIP_LOSS_SMALL"); return e && e[0] == '0'; }();
+        if (!off)
+            return launch_distill_small(s_img, s_txt, t_img, t_txt, B, d, dtype, temperature, w_img, w_txt, w_con, grad_scale, losses, d_s_img,
+                                        d_s_txt, stats, st);
+    }
     const int op_dtype = tensor ? DCLIP_F16 : DCLIP_F32;
     const size_t op_size = tensor ? 2 : 4;
     Workspace ws(workspace, workspace_bytes);

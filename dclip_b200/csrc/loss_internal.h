@@ -110,5 +110,10 @@ int launch_rowlse_simt(LseArgs a, int nsides, cudaStream_t st);
 int launch_grad_simt(const GradArgs& a, int nsides, cudaStream_t st);
 int launch_grad_tail(const TailArgs& a, int nsides, int dtype, cudaStream_t st);
 int launch_loss_sums(const SumsArgs& a, cudaStream_t st);
+// whole objective for B <= 64 in one launch (loss_small.cu): one cluster of 8 CTAs, fp32 arithmetic
+bool small_loss_shape_ok(int64_t B, int64_t d);
+int launch_distill_small(const void* s_img, const void* s_txt, const void* t_img, const void* t_txt, int64_t B, int64_t d, int dtype,
+                         float temperature, float w_img, float w_txt, float w_con, float grad_scale, float* losses, void* d_img, void* d_txt,
+                         float* stats, cudaStream_t st);
 
 }  // namespace dclip

@@ -23,50 +23,6 @@ constexpr float kNormEps = 1e-12f;  // F.normalize eps
 // ---------------------------------------------------------------------------------------------
 // prep: one warp per row.  x_hat = x / max(|x|, eps); cos = x_hat . t_hat
 // ---------------------------------------------------------------------------------------------
-template <typename T>
-__device__ __forceinline__ void load8(const T* p, float (&v)[8]);
-template <>
-__device__ __forceinline__ void load8<float>(const float* p, float (&v)[8]) {
-    float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-}
-template <>
-__device__ __forceinline__ void load8<__half>(const __half* p, float (&v)[8]) {
-    uint4 r = *reinterpret_cast<const uint4*>(p);
-    const __half2* h = reinterpret_cast<const __half2*>(&r);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
-}
-template <>
-__device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
-    uint4 r = *reinterpret_cast<const uint4*>(p);
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
-}
-template <typename T>
-__device__ __forceinline__ void store8(T* p, const float (&v)[8]);
-template <>
-__device__ __forceinline__ void store8<float>(float* p, const float (&v)[8]) {
-    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
-}
-template <>
-__device__ __forceinline__ void store8<__half>(__half* p, const float (&v)[8]) {
-    uint4 r;
-    __half2* h = reinterpret_cast<__half2*>(&r);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-    *reinterpret_cast<uint4*>(p) = r;
-}
-template <>
-__device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[8]) {
-    uint4 r;
-    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-    *reinterpret_cast<uint4*>(p) = r;
-}
 
 template <typename T, typename OT>
 __global__ void __launch_bounds__(kThreads) k_loss_prep(PrepArgs a) {

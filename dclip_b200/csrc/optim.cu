@@ -142,7 +142,8 @@ __global__ void __launch_bounds__(kOptThreads) k_grad_sumsq(const __grid_constan
     }
 }
 
-struct AdamHyper { float lr, beta1, beta2, eps, weight_decay; int decoupled; const float* lr_dev; };
+// hyper-parameters stay in double until the point where torch casts its Python scalars to the tensor dtype
+struct AdamHyper { double lr, beta1, beta2, eps, weight_decay; int decoupled; const float* lr_dev; };
 
 template <typename T>
 __global__ void __launch_bounds__(kOptThreads) k_adam_step(const __grid_constant__ OptTensors t, const AdamHyper h, OptState* st, int nchunks) {
@@ -158,14 +159,15 @@ __global__ void __launch_bounds__(kOptThreads) k_adam_step(const __grid_constant
     const bool vecF = ((reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0;
     // scalars: the step this launch performs is st->step + 1 (every block reads the same, the last block advances it)
     const int step = st->step + 1;
-    const float lr = h.lr_dev ? *h.lr_dev : h.lr;
-    const double bc1 = 1.0 - pow((double)h.beta1, (double)step);
-    const double bc2 = 1.0 - pow((double)h.beta2, (double)step);
-    const float step_size = (float)((double)lr / bc1);
+    const double lr = h.lr_dev ? (double)*h.lr_dev : h.lr;
+    const double bc1 = 1.0 - pow(h.beta1, (double)step);
+    const double bc2 = 1.0 - pow(h.beta2, (double)step);
+    const float step_size = (float)(lr / bc1);
     const float bc2_sqrt = (float)sqrt(bc2);
     const float coef = st->clip_coef;
-    const float decay = h.decoupled ? 1.0f - lr * h.weight_decay : 1.0f;
-    const float l2 = h.decoupled ? 0.f : h.weight_decay;
+    const float decay = h.decoupled ? (float)(1.0 - lr * h.weight_decay) : 1.0f;
+    const float l2 = h.decoupled ? 0.f : (float)h.weight_decay;
+    const float b2 = (float)h.beta2, omb1 = (float)(1.0 - h.beta1), omb2 = (float)(1.0 - h.beta2), eps = (float)h.eps;
     for (int it = 0; it < kOptChunk / (kOptThreads * 4); ++it) {
         const long long i = base + ((long long)it * kOptThreads + threadIdx.x) * 4;
         if (i >= n) break;
@@ -180,9 +182,9 @@ __global__ void __launch_bounds__(kOptThreads) k_adam_step(const __grid_constant
             float gj = gv[j] * coef;
             float pj = pv[j] * decay;
             gj = fmaf(l2, pv[j], gj);
-            mv[j] = fmaf(h.beta1, mv[j], (1.0f - h.beta1) * gj);          // lerp(m, g, 1 - b1)
-            vv[j] = fmaf(h.beta2, vv[j], (1.0f - h.beta2) * gj * gj);
-            const float denom = sqrtf(vv[j]) / bc2_sqrt + h.eps;
+            mv[j] = fmaf(omb1, gj - mv[j], mv[j]);                        // exp_avg.lerp_(grad, 1 - beta1)
+            vv[j] = fmaf(omb2 * gj, gj, b2 * vv[j]);                      // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value = 1 - beta2)
+            const float denom = sqrtf(vv[j]) / bc2_sqrt + eps;
             pv[j] = pj - step_size * (mv[j] / denom);
         }
         store4<T>(p, i, n, pv, vecT && full);
@@ -255,11 +257,11 @@ int dclip_grad_clip_coef(const void* const* grads, const int64_t* numel, int cou
 }
 
 int dclip_adam_step(void* const* params, const void* const* grads, float* const* exp_avg, float* const* exp_avg_sq, const int64_t* numel,
-                    int count, int dtype, float lr, const float* lr_dev, float beta1, float beta2, float eps, float weight_decay,
+                    int count, int dtype, double lr, const float* lr_dev, double beta1, double beta2, double eps, double weight_decay,
                     int decoupled_weight_decay, void* state, void* stream) {
     DCLIP_REQUIRE(params && grads && exp_avg && exp_avg_sq && numel && state && count > 0 && count <= kOptMaxTensors,
                   "adam_step: 1..%d tensors", kOptMaxTensors);
-    DCLIP_REQUIRE(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f && weight_decay >= 0.f, "adam_step: bad hyper-parameters");
+    DCLIP_REQUIRE(beta1 >= 0.0 && beta1 < 1.0 && beta2 >= 0.0 && beta2 < 1.0 && eps >= 0.0 && weight_decay >= 0.0, "adam_step: bad hyper-parameters");
     for (int i = 0; i < count; ++i)
         DCLIP_REQUIRE(params[i] && grads[i] && exp_avg[i] && exp_avg_sq[i] && numel[i] > 0, "adam_step: tensor %d is null or empty", i);
     OptTensors t{};

@@ -627,6 +627,22 @@ static TcGemmProblem tcp(const void* A, int lda, bool a_mn, const void* B, int l
     return p;
 }
 
+// 16-bit tier with every contraction on tcgen05 (xattn_tc.cu)
+bool xattn_tc_shape_ok(int64_t T, int64_t R, int64_t d, int heads);
+size_t xattn_tc_saved_bytes(int64_t B, int64_t T, int64_t R, int64_t d);
+size_t xattn_tc_scratch_bytes(int64_t B, int64_t T, int64_t R, int64_t d);
+int xattn_fwd_tc(const void* text, const void* image, int64_t B, int64_t T, int64_t R, int64_t d, int heads, int dtype, const void* const* params,
+                 void* text_out, void* image_out, void* saved, size_t saved_bytes, cudaStream_t st);
+int xattn_bwd_tc(const void* text, const void* image, int64_t B, int64_t T, int64_t R, int64_t d, int heads, int dtype, const void* const* params,
+                 const void* saved, const void* d_text_out, const void* d_image_out, void* const* grads, void* d_text, void* d_image,
+                 void* scratch, size_t scratch_bytes, cudaStream_t st);
+// DCLIP_XATTN_ATTN=simt keeps the round-1 hybrid (tcgen05 projections, fp32 CUDA-core attention) for A/B timing
+static bool xattn_full_tc(int dtype, int64_t T, int64_t R, int64_t d, int heads) {
+    if (!xattn_use_tc(dtype, d) || !xattn_tc_shape_ok(T, R, d, heads)) return false;
+    const char* e = getenv("DCLIP_XATTN_ATTN");
+    return !(e && e[0] == 's');
+}
+
 static size_t attn_fwd_smem(int Lq, int Lk, int hd) { return ((size_t)(Lq + 2 * Lk) * (hd + 1) + (size_t)Lq * (Lk + 1)) * 4; }
 static size_t attn_bwd_smem(int Lq, int Lk, int hd) { return ((size_t)(2 * Lq + 2 * Lk) * (hd + 1) + (size_t)2 * Lq * (Lk + 1)) * 4; }
 
@@ -637,14 +653,16 @@ using namespace dclip;
 extern "C" {
 
 size_t dclip_xattn_saved_bytes(int64_t B, int64_t T, int64_t R, int64_t d, int dtype) {
-    return xlayout(B, T, R, d, dtype != DCLIP_F32).total * sizeof(float) + 256;
+    const size_t base = xlayout(B, T, R, d, dtype != DCLIP_F32).total * sizeof(float) + 256;
+    return dtype != DCLIP_F32 ? max(base, xattn_tc_saved_bytes(B, T, R, d)) : base;     // either 16-bit tier may be chosen at call time
 }
 // scratch for the backward: dZ, zhat, dO (text+image), dQ, dKV (both) + widened output grads
 size_t dclip_xattn_bwd_scratch_bytes(int64_t B, int64_t T, int64_t R, int64_t d, int dtype) {
     const size_t nt = (size_t)B * T, ni = (size_t)B * R;
     size_t f = (nt + ni) * d * 6 + (nt + ni) * 2 * d + 1024;       // dY, dZ, zhat, dO, dQ, dX + dKV
     if (dtype != DCLIP_F32) { f += (nt + ni) * d; for (int i = 0; i < kParamCount; ++i) f += param_numel(i, d) + 64; f += (nt + ni) * d * 2 + 1024; }
-    return f * sizeof(float) + 4096;
+    const size_t base = f * sizeof(float) + 4096;
+    return dtype != DCLIP_F32 ? max(base, xattn_tc_scratch_bytes(B, T, R, d)) : base;
 }
 
 int dclip_xattn_fwd(const void* text, const void* image, int64_t B, int64_t T, int64_t R, int64_t d, int heads, int dtype,
@@ -652,6 +670,8 @@ int dclip_xattn_fwd(const void* text, const void* image, int64_t B, int64_t T, i
     DCLIP_REQUIRE(text && image && params && text_out && image_out && saved, "xattn_fwd: null pointer");
     DCLIP_REQUIRE(B > 0 && T > 0 && R > 0 && d > 0 && heads > 0 && d % heads == 0, "xattn_fwd: bad shape B=%lld T=%lld R=%lld d=%lld heads=%d",
                   (long long)B, (long long)T, (long long)R, (long long)d, heads);
+    if (xattn_full_tc(dtype, T, R, d, heads))
+        return xattn_fwd_tc(text, image, B, T, R, d, heads, dtype, params, text_out, image_out, saved, saved_bytes, static_cast<cudaStream_t>(stream));
     const bool wide = dtype != DCLIP_F32;
     const XLayout L = xlayout(B, T, R, d, wide);
     if (saved_bytes < L.total * sizeof(float)) return fail(DCLIP_ERR_WORKSPACE, "xattn_fwd: saved buffer too small (%zu < %zu)", saved_bytes, L.total * sizeof(float));
@@ -758,6 +778,9 @@ int dclip_xattn_bwd(const void* text, const void* image, int64_t B, int64_t T, i
     DCLIP_REQUIRE(text && image && params && saved && d_text_out && d_image_out && grads && scratch, "xattn_bwd: null pointer");
     DCLIP_REQUIRE((d_text == nullptr) == (d_image == nullptr), "xattn_bwd: give both input gradients or neither");
     if (scratch_bytes < dclip_xattn_bwd_scratch_bytes(B, T, R, d, dtype)) return fail(DCLIP_ERR_WORKSPACE, "xattn_bwd: scratch too small");
+    if (xattn_full_tc(dtype, T, R, d, heads))
+        return xattn_bwd_tc(text, image, B, T, R, d, heads, dtype, params, saved, d_text_out, d_image_out, grads, d_text, d_image, scratch,
+                            scratch_bytes, static_cast<cudaStream_t>(stream));
     const bool wide = dtype != DCLIP_F32;
     const XLayout L = xlayout(B, T, R, d, wide);
     const int hd = (int)(d / heads);

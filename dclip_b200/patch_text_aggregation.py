@@ -21,7 +21,8 @@ import torch.nn as nn
 from . import _lib
 from ._lib import check, dtype_code, ptr, require_cuda, stream_ptr, workspace
 
-__all__ = ["CrossModalAttention", "PatchTextAggregation", "aggregation", "combine_global", "PARAM_ORDER", "GraphedTeacherStep"]
+__all__ = ["CrossModalAttention", "PatchTextAggregation", "aggregation", "combine_global", "fused_global_embedding", "PARAM_ORDER",
+           "GraphedTeacherStep"]
 
 PARAM_ORDER = (
     "text_to_image.in_proj_weight", "text_to_image.in_proj_bias", "text_to_image.out_proj.weight",
@@ -129,6 +130,49 @@ class _CombineGuardFn(torch.autograd.Function):
         return da, db
 
 
+class _GlobalEmbeddingFn(torch.autograd.Function):
+    """aggregation(text) + aggregation(image) + 0.5 / 0.5 combine + whole-tensor NaN / Inf guard: one launch each way."""
+
+    @staticmethod
+    def forward(ctx, attended_text, attended_image, temperature):
+        dev = require_cuda(attended_text, attended_image)
+        lib = _lib.load_library()
+        B, T, d = attended_text.shape
+        R = attended_image.shape[1]
+        out = torch.empty((B, d), dtype=attended_text.dtype, device=dev)
+        w_t = torch.empty((B, T), dtype=torch.float32, device=dev)
+        w_i = torch.empty((B, R), dtype=torch.float32, device=dev)
+        flags = torch.empty(B + 1, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.dclip_global_embedding_fwd(ptr(attended_text), ptr(attended_image), B, T, R, d, dtype_code(attended_text),
+                                                 float(temperature), ptr(out), ptr(w_t), ptr(w_i), ptr(flags), stream_ptr(dev)),
+                  "global_embedding_fwd")
+        ctx.save_for_backward(attended_text, attended_image, w_t, w_i, flags)
+        ctx.temperature = float(temperature)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        attended_text, attended_image, w_t, w_i, flags = ctx.saved_tensors
+        dev = attended_text.device
+        B, T, d = attended_text.shape
+        R = attended_image.shape[1]
+        d_out = d_out.contiguous()
+        d_t = torch.empty_like(attended_text)
+        d_i = torch.empty_like(attended_image)
+        with torch.cuda.device(dev):
+            check(_lib.load_library().dclip_global_embedding_bwd(ptr(attended_text), ptr(attended_image), ptr(w_t), ptr(w_i), ptr(d_out),
+                                                                 ptr(flags), B, T, R, d, dtype_code(attended_text), ctx.temperature,
+                                                                 ptr(d_t), ptr(d_i), stream_ptr(dev)), "global_embedding_bwd")
+        return d_t, d_i, None
+
+
+def fused_global_embedding(attended_text, attended_image, temperature=2.0):
+    """0.5 * aggregation(attended_text) + 0.5 * aggregation(attended_image) with the reference's whole-tensor NaN / Inf
+    guard (patch_text_aggregation.py:640-656) as one fused op (embed_dim % 8 == 0, <= 1024)."""
+    return _GlobalEmbeddingFn.apply(attended_text.contiguous(), attended_image.contiguous(), temperature)
+
+
 def aggregation(attended_text, temperature=2.0):
     """Temperature-scaled aggregation (reference :243-265): softmax over cos(x_l, mean) / temperature."""
     if attended_text.dim() != 3:
@@ -195,6 +239,8 @@ class PatchTextAggregation(nn.Module):
     def global_embedding(self, batch_text, batch_patches, temperature=2.0):
         """Tail of compute_global_embedding_batch (:632-656) on already assembled padded batches."""
         attended_text, attended_image = self.cross_attention(batch_text, batch_patches)
+        if self.embed_dim % 8 == 0 and self.embed_dim <= 1024:
+            return fused_global_embedding(attended_text, attended_image, temperature)
         return combine_global(self.aggregation(attended_text, temperature), self.aggregation(attended_image, temperature))
 
 

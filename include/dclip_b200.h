@@ -294,6 +294,21 @@ int dclip_aggregate_bwd(const void* x, const float* weights, const void* d_out, 
 int dclip_combine_guard_fwd(const void* a, const void* b, int64_t n, int dtype, void* out, int* flag, void* stream);
 int dclip_combine_guard_bwd(const void* d_out, int64_t n, int dtype, const int* flag, void* d_a, void* d_b, void* stream);
 
+/* Fused tail of compute_global_embedding_batch (training/patch_text_aggregation.py:640-656): both aggregations
+ * (:243-265), the 0.5 / 0.5 combine (:647) and the whole-tensor NaN / Inf guard (:649-651) in ONE launch, and the
+ * backward of the same in one launch.  attended_text [B, T, d], attended_image [B, R, d], out [B, d]; d % 8 == 0,
+ * d <= 1024.  w_text [B, T] / w_image [B, R]: the softmax weights (saved for the backward).  flags: int[B + 1]
+ * (dclip_global_embedding_flags_bytes): per-element non-finite flags + a completion counter; device-side decision,
+ * no host synchronisation. */
+size_t dclip_global_embedding_flags_bytes(int64_t B);
+int dclip_global_embedding_fwd(const void* attended_text, const void* attended_image, int64_t B, int64_t T, int64_t R,
+                               int64_t d, int dtype, float temperature, void* out, float* w_text, float* w_image,
+                               int* flags, void* stream);
+int dclip_global_embedding_bwd(const void* attended_text, const void* attended_image, const float* w_text,
+                               const float* w_image, const void* d_out, const int* flags, int64_t B, int64_t T,
+                               int64_t R, int64_t d, int dtype, float temperature, void* d_attended_text,
+                               void* d_attended_image, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Ragged batch assembly - the step immediately upstream of the cross-attention:
  *   the zero-pad / truncate / stack loops of training/patch_text_aggregation.py:555-620 and the token filter +
@@ -335,10 +350,11 @@ int dclip_optim_init_state(void* state, void* stream);
 int dclip_grad_clip_coef(const void* const* grads, const int64_t* numel, int count, int dtype, float max_norm, void* state,
                          void* workspace, size_t workspace_bytes, void* stream);
 /* One optimizer step over all tensors.  lr_dev (optional, device float) overrides lr (schedulers inside a graph).
- * decoupled_weight_decay: 1 = AdamW, 0 = Adam's L2 form. */
+ * decoupled_weight_decay: 1 = AdamW, 0 = Adam's L2 form.  Hyper-parameters are doubles: like torch's Python scalars
+ * they are rounded to fp32 only where they meet the tensors (1 - beta in double first). */
 int dclip_adam_step(void* const* params, const void* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
-                    const int64_t* numel, int count, int dtype, float lr, const float* lr_dev, float beta1, float beta2,
-                    float eps, float weight_decay, int decoupled_weight_decay, void* state, void* stream);
+                    const int64_t* numel, int count, int dtype, double lr, const float* lr_dev, double beta1, double beta2,
+                    double eps, double weight_decay, int decoupled_weight_decay, void* state, void* stream);
 /* Host read of {grad_norm, clip_coef, step} (synchronises `stream`; logging / tests). */
 int dclip_optim_read_state(const void* state, float* grad_norm, float* clip_coef, int* step, void* stream);
 

@@ -40,3 +40,11 @@ print(f"# warm per-kernel device time, teacher step B={B} T={T} R={R} d={d} {dty
 print("share%  us/step  launches/step  avg_us  kernel")
 for k, c, t in rows:
     print(f"{100 * t / tot:6.1f} {t / n:8.1f} {c / n:8.1f} {t / c:8.2f}  {k[:110]}")
+
+# one step in launch order (the last of the profiled steps): which of the same-named launches is the slow one
+evs = sorted((e for e in prof.events() if e.device_time_total > 0 and getattr(e, "device_type", None) is not None and "CUDA" in str(e.device_type)),
+             key=lambda e: e.time_range.start)
+per = len(evs) // n
+print(f"# launch order, last step ({per} launches)")
+for e in evs[-per:]:
+    print(f"{e.device_time_total:8.2f} us  {e.name[:100]}")
