@@ -1,14 +1,21 @@
 #!/usr/bin/env python
 """bench.py — DCLIP hot-path benchmark on B200 (contract in the task brief).
 
-Headline workload (BASELINE.json configs[3], "ViT-L/14 distillation contrastive+KL loss, global
-batch 4096, d=768"): one step = distill-loss forward+backward (symmetric InfoNCE + cosine feature
-matching) over the global batch; metric = pairs/s.  N > 1 shards the global
-batch over the ranks (strong scaling: the global batch is fixed at 4096) with the operand
-all-gather + lse all-gather choreography of dclip_b200.losses.sharded_distill_loss_fwd_bwd.
+Headline workload (BASELINE.json configs[3], "ViT-L/14 distillation contrastive+KL loss, global batch 4096,
+d=768"): one step = distill-loss forward+backward (symmetric InfoNCE + cosine feature matching, SURVEY.md §8a
+a9-a11) over the global batch; metric = pairs/s.  N > 1 shards the global batch over the ranks (strong scaling:
+the global batch stays 4096) with the peer-memory operand / statistics exchange of
+dclip_b200.losses.sharded_distill_loss_fwd_bwd; every rank re-computes the objective on ONE GPU and the line
+carries `parity_check` (sharded == single-GPU losses and gradients).
 
-The second BASELINE metric (retrieval queries/s, top-10) is reported in the same JSON line under
-"retrieval" (Flickr-shaped eval, configs[1], and an exact top-10 search over a gallery slice).
+Extra keys of the same JSON line (they explain the headline, the driver reads the top-level fields):
+  roofline / cpu_baseline      dominant kernel vs the measured bf16 peak; the reference's own code on the host cores
+  retrieval.sharded_top10      BASELINE configs[4]: 10 M x 768 fp16 gallery sharded over the ranks, 100 k queries,
+                               + 256 sampled queries re-run on the exact FP32 path (bit-identical or the run fails)
+  retrieval.flickr_eval ...    configs[1] (N = 1) with the reference's calculate_retrieval_metrics timed beside it
+  teacher_step.cfg0 / .cfg2    BASELINE configs[0] / [2]: meta-teacher cross-attention + aggregation + InfoNCE fwd+bwd
+                               (one CUDA graph), us/step, roofline fraction, reference module on the host cores
+  weak_scaling                 N > 1: 4096 rows PER GPU (the shape on which the NVLink exchange can reach 85 %)
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 """
@@ -43,11 +50,19 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=B_GLOBAL)
     ap.add_argument("--dim", type=int, default=DIM)
     ap.add_argument("--no-retrieval", action="store_true")
+    ap.add_argument("--no-teacher", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel/collective from Python instead of one CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gallery", type=int, default=10_000_000, help="total gallery rows of the sharded top-10 workload (configs[4])")
     ap.add_argument("--queries", type=int, default=100_000)
     return ap.parse_args()
+
+
+def shared_config(B, d, world):
+    """The `config` object: identical in the GPU arm and in the reference arm of the same invocation."""
+    return {"workload": f"distill-loss fwd+bwd, global batch {B}, d={d}, tau={TEMPERATURE} (BASELINE configs[3])",
+            "global_batch": B, "dim": d, "temperature": TEMPERATURE, "rows_per_gpu": B // max(world, 1),
+            "l2_flush": "256 MiB write between timed steps (GPU arm); none needed on the host arm"}
 
 
 def load_peaks():
@@ -104,49 +119,52 @@ class ClockSampler(threading.Thread):
         self._stop_evt.set()
         self.join(timeout=2)
         s = sorted(self.samples)
-        # median of the upper half = clock under load (idle samples between steps pull the plain median down)
-        med = s[len(s) // 2] if s else None
-        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+        # the steps are short bursts between untimed L2 flushes and barriers: the clock UNDER LOAD is the median of
+        # the upper half of the samples; the plain median is reported beside it
+        upper = s[len(s) // 2:]
+        return {"sm_mhz": upper[len(upper) // 2] if upper else None, "sm_mhz_median_all": s[len(s) // 2] if s else None,
+                "sm_mhz_min": s[0] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
 
 
-def cpu_reference_step(s_img, s_txt, t_img, t_txt):
-    from oracle import reference_math as om
-    return om.distill_total_with_grads(s_img, s_txt, t_img, t_txt, TEMPERATURE)
-
-
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm (host cores): the reference's own code where it is staged (oracle/_ref), else the oracle port
+# ------------------------------------------------------------------------------------------------------------------
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path (oracle port: the reference is
-    pure Python/PyTorch and cannot travel to the GPU box; the port is pinned to it by tests/golden)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import synthetic
+    from oracle import reference_arm, synthetic
+    arm = reference_arm.load()
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     B, d = args.batch, args.dim
-    s_img, s_txt, t_img, t_txt = synthetic.loss_inputs(B, d, seed=42)
+    inputs = synthetic.loss_inputs(B, d, seed=42)
     for _ in range(max(1, min(args.warmup, 2))):
-        cpu_reference_step(s_img, s_txt, t_img, t_txt)
+        arm.loss_step(*inputs, TEMPERATURE)
     steps = max(1, min(args.steps, 20))
     t0 = time.perf_counter()
     for _ in range(steps):
-        cpu_reference_step(s_img, s_txt, t_img, t_txt)
+        arm.loss_step(*inputs, TEMPERATURE)
     dt = (time.perf_counter() - t0) / steps
     val = B / dt
+    what = ("the reference's cosine_distillation_loss x2 + compute_contrastive_loss + backward (training/CLIP_image_distillation.py:532-576, "
+            "staged unmodified in oracle/_ref)") if arm.kind == "reference" else "the oracle port (oracle/reference_math.py; no staged reference found)"
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"distill-loss fwd+bwd, global batch {B}, d={d}, tau={TEMPERATURE} (BASELINE configs[3])",
-                   "global_batch": B, "dim": d},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{steps} full steps of the B={B} d={d} workload, torch fp32 on {cores} threads"},
+        "config": shared_config(B, d, args.gpus),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": arm.kind,
+                         "sample": f"{steps} full steps of the B={B} d={d} workload: {what}; torch fp32 on {cores} threads"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------------------
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -172,13 +190,13 @@ def main():
     B, d = args.batch, args.dim
     assert B % world == 0
     m = B // world
+    full_cpu = [t.to(tdtype) for t in synthetic.loss_inputs(B, d, seed=42)]
     path = args.path
-    if path == "auto":
-        path = "tensor" if (lib.dclip_device_supports_tensor_path(local_rank) and tdtype != torch.float32
-                            and os.environ.get("DCLIP_DISABLE_TENSOR", "0") != "1"
-                            and lib.dclip_tensor_path_ready()) else "fp32"
+    if path == "auto":       # the library's own rule (dclip_resolve_loss_path): tcgen05 path for 16-bit inputs
+        probe = torch.empty((1, d), dtype=tdtype, device=dev)
+        path = "tensor" if _lib.resolve_loss_path("auto", probe, TEMPERATURE, global_batch=B) == _lib.PATH_TENSOR else "fp32"
 
-    host = [t.to(tdtype)[rank * m:(rank + 1) * m].contiguous().pin_memory() for t in synthetic.loss_inputs(B, d, seed=42)]
+    host = [t[rank * m:(rank + 1) * m].contiguous().pin_memory() for t in full_cpu]
     resident = [t.to(dev) for t in host]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
     launches_per_step = lib.dclip_distill_loss_launch_count(m, B, d, _lib.path_code(path), 1 if world > 1 else 0)
@@ -188,9 +206,30 @@ def main():
             return L.distill_loss_fwd_bwd(s_img, s_txt, t_img, t_txt, temperature=TEMPERATURE, path=path)
         return L.sharded_distill_loss_fwd_bwd(s_img, s_txt, t_img, t_txt, temperature=TEMPERATURE, path=path)
 
+    # ---- parity of the sharded step against the single-GPU step (N > 1): same seed -> the N = 1 values are constants ----
+    parity = None
+    if world > 1:
+        full_dev = [t.to(dev) for t in full_cpu]
+        ref_losses, ref_di, ref_dt = L.distill_loss_fwd_bwd(*full_dev, temperature=TEMPERATURE, path=path)
+        got_losses, got_di, got_dt = step_fn(*resident)
+        torch.cuda.synchronize()
+        sl = slice(rank * m, (rank + 1) * m)
+        loss_err = float(((got_losses - ref_losses).abs() / ref_losses.abs().clamp_min(1e-6)).max())
+        g_err = max(float((got_di.float() - ref_di[sl].float()).norm() / ref_di[sl].float().norm()),
+                    float((got_dt.float() - ref_dt[sl].float()).norm() / ref_dt[sl].float().norm()))
+        ok = loss_err < 1e-5 and g_err < (2e-3 if path == "tensor" else 2e-5)
+        flag = torch.tensor([1 if ok else 0, ], device=dev)
+        errs = torch.tensor([loss_err, g_err], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+        parity = {"status": "ok" if int(flag) == 1 else "FAILED", "max_rel_loss_diff_vs_1gpu": float(errs[0]),
+                  "max_rel_grad_diff_vs_1gpu": float(errs[1]), "losses_sharded": [float(x) for x in got_losses.cpu()],
+                  "losses_1gpu": [float(x) for x in ref_losses.cpu()]}
+        del full_dev, ref_di, ref_dt
+
     graphed = None
     if not args.no_graph:
-        # the public API's CUDA-graph wrapper: one graph launch per step (kernels + NCCL collectives)
+        # the public API's CUDA-graph wrapper: one graph launch per step (kernels + peer-memory exchanges)
         graphed = L.GraphedStep(step_fn, resident)
         step_inputs = graphed.static_in           # the resident inputs ARE the graph's static inputs
     else:
@@ -265,16 +304,24 @@ def main():
         roof = kernel_roofline(L, _lib, resident, B, m, d, path, rank, load_peaks())
 
     extra = {}
+    if world > 1:
+        weak = weak_scaling_bench(L, dev, rank, world, d, tdtype, path, timed, args)
+        if rank == 0:
+            extra["weak_scaling"] = weak
     if not args.no_retrieval:
         big = sharded_gallery_bench(dev, rank, world, args.gallery, args.queries)     # every rank takes part
         if rank == 0:
             extra["retrieval"] = {"sharded_top10": big}
             if world == 1:
-                extra["retrieval"].update(retrieval_bench(dev))
+                extra["retrieval"].update(retrieval_bench(dev, not args.no_cpu_baseline))
+    if rank == 0 and world == 1 and not args.no_teacher:
+        extra["teacher_step"] = teacher_step_bench(dev, not args.no_cpu_baseline)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(B, d)
 
+    failed = (parity is not None and parity["status"] != "ok") or (
+        "retrieval" in extra and extra["retrieval"]["sharded_top10"].get("fp32_recheck", {}).get("status") == "FAILED")
     if rank == 0:
         line = {
             "metric": METRIC, "value": B / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -282,11 +329,10 @@ def main():
             "vs_baseline": None, "dtype": {"bf16": "bf16", "fp32": "f32", "fp16": "f16"}[args.dtype] +
             ("/f16-operands,f32-accumulate" if path == "tensor" else "/f32-math"),
             "data": "synthetic",
-            "config": {"workload": f"distill-loss fwd+bwd, global batch {B}, d={d}, tau={TEMPERATURE} (BASELINE configs[3])",
-                       "global_batch": B, "dim": d, "rows_per_gpu": m, "path": path, "l2_flush": "256 MiB write between timed steps",
-                       "launch": "python" if args.no_graph else "cuda-graph (dclip_b200.losses.GraphedStep)",
-                       "parallelism": f"dp{world} (batch-sharded, operand all-gather over NVLink peer memory)" if world > 1 else "single GPU",
-                       "start": "host barrier + device-side peer-memory gate before the start event" if gate is not None else "host barrier"},
+            "config": shared_config(B, d, world),
+            "details": {"path": path, "launch": "python" if args.no_graph else "cuda-graph (dclip_b200.losses.GraphedStep)",
+                        "parallelism": f"dp{world} (batch-sharded, operand exchange over NVLink peer memory)" if world > 1 else "single GPU",
+                        "start": "host barrier + device-side peer-memory gate before the start event" if gate is not None else "host barrier"},
             "clocks": clocks,
             "e2e": {"value": B / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in host) * world,
@@ -294,6 +340,9 @@ def main():
             "gpu_launches": int(launches_per_step) * args.steps,
             "roofline": roof, "cpu_baseline": cpu,
         }
+        if parity is not None:
+            line["parity_check"] = parity["status"]
+            line["parity"] = parity
         line.update(extra)
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -304,13 +353,14 @@ def main():
         dist.barrier()
         torch.cuda.synchronize()
         sys.stdout.flush()
-        os._exit(0)
+        os._exit(1 if failed else 0)
+    if failed:
+        raise SystemExit(1)
 
 
-# DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture of this very
-# launch shape (profiles/r1_ncu_full_loss_kernels.txt: dram__bytes_read.sum + dram__bytes_write.sum); the
-# operands (2 x 6.3 MB fp16) are read once, everything else lives in L2.
-NCU_DRAM_BYTES_PER_LAUNCH = {"tensor": 12.69e6}
+# DRAM traffic of the dominant kernel per launch comes from the committed ncu --set full capture of this very launch
+# shape (dram__bytes_read.sum + dram__bytes_write.sum); bench.py cannot read DRAM counters itself.
+NCU_TRAFFIC = {"tensor": {"bytes": 12.69e6, "source": "profiles/r1_ncu_full_loss_kernels.txt (ncu --set full of k_infonce_bwd_pair<6>, B=4096 d=768)"}}
 
 
 def kernel_roofline(L, _lib, resident, B, m, d, path, rank, peaks):
@@ -354,17 +404,38 @@ def kernel_roofline(L, _lib, resident, B, m, d, path, rank, peaks):
     flops = 4.0 * B * B * d
     achieved = flops / sec / 1e12
     peak = peaks["bf16_tflops"]
+    tr = NCU_TRAFFIC.get(path)
     return {"bound": "tensor", "kernel": "k_infonce_bwd_pair (CTA pairs, cta_group::2; both directions in one launch: dU = G V, dV = G^T U; score tiles recomputed)",
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "peak_source": peaks["source"] + " bf16 burst (kernel timed alone, back to back, L2-warm)",
             "algorithmic_flops_per_launch": flops, "executed_flops_per_launch": 2.0 * flops,
-            "tensor_cores": path == "tensor", "avg_launch_us": sec * 1e6, "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(path)}
+            "tensor_cores": path == "tensor", "avg_launch_us": sec * 1e6,
+            "traffic": tr["bytes"] if tr else None, "traffic_source": tr["source"] if tr else None}
+
+
+def weak_scaling_bench(L, dev, rank, world, d, tdtype, path, timed, args):
+    """N > 1 only: 4096 rows PER GPU (global batch 4096 N), the same sharded step.  Per-rank tile work is what one GPU
+    does at N = 1 times N in the column direction; reported so that the exchange is judged on a shape where the
+    compute can hide it.  Rank 0 returns the dict."""
+    from oracle import synthetic
+    m = 4096
+    Bw = m * world
+    inputs = [t.to(tdtype)[rank * m:(rank + 1) * m].contiguous().to(dev) for t in synthetic.loss_inputs(Bw, d, seed=43)]
+
+    def fn():
+        return L.sharded_distill_loss_fwd_bwd(*inputs, temperature=TEMPERATURE, path=path)
+
+    graphed = None if args.no_graph else L.GraphedStep(lambda *a: L.sharded_distill_loss_fwd_bwd(*a, temperature=TEMPERATURE, path=path), inputs)
+    ms = timed((lambda: graphed.graph.replay()) if graphed is not None else fn, max(5, args.steps // 2), 3)
+    return {"rows_per_gpu": m, "global_batch": Bw, "ms_per_step": ms, "pairs_per_s": Bw / (ms * 1e-3), "scaling": "weak",
+            "note": "ideal time grows with N (B^2 tiles / N per GPU = 4096 x 4096 N): compare pairs/s per GPU x B/4096"}
 
 
 def sharded_gallery_bench(dev, rank, world, n_gallery, n_query):
     """BASELINE configs[4]: cosine top-10 over an N x 768 fp16 gallery sharded over the ranks (rank r holds
     rows [r N/P, (r+1) N/P)), every rank scores all queries against its shard on the tcgen05 path, the
-    per-GPU exact top-10 lists are all-gathered and merged by (-score, +index).  Strong scaling."""
+    per-GPU exact top-10 lists are all-gathered and merged by (-score, +index).  Strong scaling.  256 sampled
+    queries are re-run on the exact FP32 path over the same shards: (score, index) must be bit-identical."""
     import math
 
     import torch.distributed as dist
@@ -390,25 +461,27 @@ def sharded_gallery_bench(dev, rank, world, n_gallery, n_query):
         q = torch.empty((n_query, d), dtype=torch.float16, device=dev)
     if world > 1:
         dist.broadcast(q, src=0)
+        dist.broadcast(planted, src=0)
     gallery = R.TensorGallery(g)
 
-    def search():
-        s, i = R.topk_ip(q, g, 10, g_index_offset=lo, path="tensor", gallery=gallery)
+    def search(queries, path):
+        s, i = R.topk_ip(queries, g, 10, g_index_offset=lo, path=path, gallery=gallery if path == "tensor" else None)
+        nq = queries.shape[0]
         if world > 1:
-            all_s = torch.empty((world * n_query, 10), dtype=s.dtype, device=dev)
-            all_i = torch.empty((world * n_query, 10), dtype=i.dtype, device=dev)
+            all_s = torch.empty((world * nq, 10), dtype=s.dtype, device=dev)
+            all_i = torch.empty((world * nq, 10), dtype=i.dtype, device=dev)
             dist.all_gather_into_tensor(all_s, s)
             dist.all_gather_into_tensor(all_i, i)
-            s, i = R.topk_merge(all_s.view(world, n_query, 10), all_i.view(world, n_query, 10))
+            s, i = R.topk_merge(all_s.view(world, nq, 10), all_i.view(world, nq, 10))
         return s, i
 
-    search()
+    search(q, "tensor")
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    s, i = search()
+    s, i = search(q, "tensor")
     e1.record()
     torch.cuda.synchronize()
     t = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -416,26 +489,40 @@ def sharded_gallery_bench(dev, rank, world, n_gallery, n_query):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     sec = float(t) * 1e-3
     r1 = float((i[:, 0] == planted).float().mean())
+    # exactness at scale: a fixed sample of the queries again on the FP32 CUDA-core path (every score the contract's fmaf chain)
+    nchk = min(256, n_query)
+    sel = torch.arange(0, n_query, max(1, n_query // nchk), device=dev)[:nchk]
+    s32, i32 = search(q[sel].contiguous(), "fp32")
+    same = bool(torch.equal(i32, i[sel]) and torch.equal(s32, s[sel]))
+    recheck = {"status": "ok" if same else "FAILED", "queries": int(sel.numel()),
+               "what": "tcgen05 path vs exact FP32 path over the same sharded gallery: top-10 scores and indices bit-identical"}
     del g, gallery
     torch.cuda.empty_cache()
     peaks = load_peaks()
     tflops = 2.0 * n_query * n_gallery * d / sec / 1e12
+    per_gpu = tflops / world
     return {"metric": "retrieval queries/sec top-10", "queries_per_s": n_query / sec, "ms": sec * 1e3, "planted_R@1": r1,
+            "fp32_recheck": recheck,
             "tflops_aggregate": tflops, "frac_of_bf16_sustained_peak": tflops / (world * peaks["bf16_tflops_sustained"]),
+            "roofline": {"bound": "tensor", "kernel": "k_stream_tc<2,*> (tcgen05 score tiles + fused top-32 candidate lists), per GPU",
+                         "achieved": per_gpu, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": per_gpu / peaks["bf16_tflops_sustained"],
+                         "peak_source": peaks["source"] + " bf16 sustained (a 0.1-1 s kernel under the power cap)",
+                         "algorithmic_flops_per_launch": 2.0 * n_query * n_gallery * d / world,
+                         "traffic": None, "traffic_source": "profiles/ (ncu capture of one shard; the gallery is read once per wave of CTAs)"},
             "workload": f"exact cosine top-10, {n_gallery} x {d} fp16 gallery sharded over {world} GPU(s), {n_query} queries "
                         "(BASELINE configs[4]); tcgen05 candidates + exact fp32 re-scoring, bit-exact contract"}
 
 
-def retrieval_bench(dev):
+def retrieval_bench(dev, with_cpu):
     """Second BASELINE metric: retrieval queries/s.  (a) Flickr-shaped Recall@K eval, 1k images x 5k
-    captions, d=512 (configs[1]; 6000 ranked queries per eval).  (b) exact top-10 over a 1M x 768
-    fp16 gallery slice, 1024 queries (configs[4] scaled to one GPU's slice of the bench budget)."""
+    captions, d=512 (configs[1]; 6000 ranked queries per eval), the reference's own evaluator timed beside it.
+    (b) exact top-10 over a 1M x 768 fp16 gallery slice, 4096 queries, with the host stand-in for faiss."""
     import numpy as np
 
     from dclip_b200 import retrieval as R
     from oracle import synthetic
     out = {}
-    cap, img, image_ids, cap_ids = synthetic.retrieval_inputs(1000, 5, 512, 1.0, seed=42)
+    cap, img, image_ids, cap_ids = synthetic.retrieval_inputs(1000, 5, 512, 7.0, seed=44)      # the tests/golden/retrieval_cfg2 recipe
     cap_d, img_d = torch.from_numpy(cap).to(dev), torch.from_numpy(img).to(dev)
     for _ in range(2):
         R.retrieval_metrics_from_embeddings(cap_d, img_d, image_ids, cap_ids)
@@ -447,7 +534,19 @@ def retrieval_bench(dev):
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / reps
     out["flickr_eval"] = {"queries_per_s": 6000 / dt, "ms_per_eval": dt * 1e3, "t2i_R@1": m["t2i"]["R@1"],
-                          "i2t_R@1": m["i2t"]["R@1"], "workload": "1k images x 5k captions, d=512, R@1/5/10 both directions"}
+                          "i2t_R@1": m["i2t"]["R@1"], "workload": "1k images x 5k captions, d=512, R@1/5/10 both directions (BASELINE configs[1])"}
+    if with_cpu:
+        from oracle import reference_arm
+        arm = reference_arm.load()
+        cores = os.cpu_count() or 1
+        arm.retrieval_eval(cap, img, image_ids, cap_ids)
+        t0 = time.perf_counter()
+        mc = arm.retrieval_eval(cap, img, image_ids, cap_ids)
+        ct = time.perf_counter() - t0
+        same = all(mc[dn][k] == m[dn][k] for dn in ("t2i", "i2t") for k in ("R@1", "R@5", "R@10"))
+        out["flickr_eval"]["cpu_baseline"] = {"value": 6000 / ct, "unit": "ranked queries/s", "cores": cores, "kind": arm.kind, "ms_per_eval": ct * 1e3,
+                                              "sample": "one full eval: normalise + chunked similarity + calculate_retrieval_metrics (eval_scripts/flickr30k_eval.py:16-88, :243-266)",
+                                              "recall_at_k_identical_to_gpu": same}
     ng, nq, dd = 1_000_000, 4096, 768
     g = torch.randn(ng, dd, device=dev, generator=torch.Generator(device=dev).manual_seed(42))
     g = (g / g.norm(dim=1, keepdim=True)).half()
@@ -467,25 +566,119 @@ def retrieval_bench(dev):
         out[name] = {"queries_per_s": nq / sec, "ms": sec * 1e3, "planted_R@1": float((i[:, 0] == idx).float().mean()),
                      "tflops": 2.0 * nq * ng * dd / sec / 1e12, "path": path,
                      "workload": f"exact IP top-10, {ng} x {dd} fp16 gallery, {nq} queries, 1 GPU"}
+    if with_cpu:
+        # faiss is absent and unpinned: the stand-in BASELINE.md names - Q @ G^T + top-k on the host cores over
+        # the same 1 M-row slice, 512 queries (a few seconds), extrapolated linearly to the 10 M-row gallery
+        from oracle import reference_arm
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        gq = q[:512].float().cpu().numpy()
+        gg = g.float().cpu().numpy()
+        reference_arm.topk_stand_in(gq[:32], gg, 10)
+        t0 = time.perf_counter()
+        reference_arm.topk_stand_in(gq, gg, 10)
+        ct = time.perf_counter() - t0
+        out["top10"]["cpu_baseline"] = {"value": 512 / ct, "unit": "queries/s at 1 M rows", "cores": cores, "kind": "port",
+                                        "extrapolated_to_10M_rows_queries_per_s": 512 / ct / 10.0,
+                                        "sample": f"512 queries x 1 M x 768 fp32, torch matmul + topk on {cores} threads, {ct:.1f} s (stand-in for faiss IndexFlatIP.search; extrapolated)"}
+    return out
+
+
+def teacher_flops(B, T, R, d):
+    """Algorithmic FLOPs of the meta-teacher step as the reference uses it (weight gradients only):
+    forward 8 d^2 N + 8 B T R d, backward 10 d^2 N + 16 B T R d, N = B (T + R)."""
+    n = B * (T + R)
+    return 18.0 * d * d * n + 24.0 * B * T * R * d
+
+
+def teacher_step_bench(dev, with_cpu):
+    """BASELINE configs[0] (B=32, R=8, T=77, d=512, fp32) and configs[2] (B=32, R=36, T=77, d=768, bf16): cross-attention ->
+    aggregation x2 -> combine -> InfoNCE -> backward to the 12 parameter tensors (train_contrastive_teacher.py:347-361),
+    replayed as ONE CUDA graph; the second figure adds the fused Adam step (:362)."""
+    from dclip_b200 import losses as L
+    from dclip_b200.optim import FusedAdam
+    from dclip_b200.patch_text_aggregation import GraphedTeacherStep, PatchTextAggregation
+    from oracle import reference_math as om
+    from oracle import synthetic
+    peaks = load_peaks()
+    out = {}
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    for name, (B, T, R, d, dtype) in (("cfg0", (32, 77, 8, 512, torch.float32)), ("cfg2", (32, 77, 36, 768, torch.bfloat16))):
+        params = om.perturbed_cross_attention_params(d, 8, 42)
+        text, image = synthetic.xattn_inputs(B, T, R, d, 42, ragged=True)
+        txt = torch.randn(B, d, generator=torch.Generator().manual_seed(43))
+
+        def loss_fn(mod, t, i, x):
+            return L.compute_contrastive_loss(mod.global_embedding(t, i), x, temperature=TEMPERATURE)
+
+        res = {}
+        for with_opt in (False, True):
+            mod = PatchTextAggregation(embed_dim=d, num_heads=8)
+            mod.cross_modal_attention.load_state_dict(params)
+            mod = mod.to(dev).to(dtype)
+            inputs = [text.to(dev).to(dtype), image.to(dev).to(dtype), txt.to(dev).to(dtype)]
+            opt = FusedAdam(mod.parameters(), lr=1e-5) if with_opt else None
+            gs = GraphedTeacherStep(mod, loss_fn, inputs, optimizer=opt)
+            for _ in range(3):
+                gs(*inputs)
+            torch.cuda.synchronize()
+            reps, tot = 20, 0.0
+            for _ in range(reps):
+                flush.zero_()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                loss = gs(*inputs)
+                e1.record()
+                torch.cuda.synchronize()
+                tot += e0.elapsed_time(e1)
+            res["us_per_step_with_adam" if with_opt else "us_per_step"] = tot / reps * 1e3
+            if not with_opt:
+                res["loss"] = float(loss)
+        us = res["us_per_step"]
+        fl = teacher_flops(B, T, R, d)
+        res.update({"pairs_per_s": B / (us * 1e-6), "algorithmic_gflop": fl / 1e9,
+                    "roofline": {"bound": "tensor" if dtype != torch.float32 else "launch latency (fp32 exact tier, CUDA cores)",
+                                 "achieved": fl / (us * 1e-6) / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                                 "frac": fl / (us * 1e-6) / 1e12 / peaks["bf16_tflops"], "peak_source": peaks["source"] + " bf16 burst",
+                                 "traffic": None},
+                    "workload": f"meta-teacher step fwd+bwd, B={B} T={T} R={R} d={d} {str(dtype).replace('torch.', '')} "
+                                f"(BASELINE configs[{0 if name == 'cfg0' else 2}]), one CUDA graph, L2 flushed between steps"})
+        if with_cpu:
+            from oracle import reference_arm
+            arm = reference_arm.load()
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            arm.teacher_step(params, text, image, txt)
+            n, t0 = 0, time.perf_counter()
+            while n < 10 and time.perf_counter() - t0 < 6.0:
+                arm.teacher_step(params, text, image, txt)
+                n += 1
+            ct = (time.perf_counter() - t0) / n
+            res["cpu_baseline"] = {"value": B / ct, "unit": "pairs/s", "ms_per_step": ct * 1e3, "cores": cores, "kind": arm.kind,
+                                   "sample": f"{n} steps of the reference CrossModalAttention + aggregation + contrastive loss + backward, torch fp32 on {cores} threads"}
+        out[name] = res
     return out
 
 
 def cpu_baseline(B, d):
-    from oracle import synthetic
+    from oracle import reference_arm, synthetic
+    arm = reference_arm.load()
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    s_img, s_txt, t_img, t_txt = synthetic.loss_inputs(B, d, seed=42)
-    cpu_reference_step(s_img, s_txt, t_img, t_txt)
+    inputs = synthetic.loss_inputs(B, d, seed=42)
+    arm.loss_step(*inputs, TEMPERATURE)
     n = 0
     t0 = time.perf_counter()
     while True:
-        cpu_reference_step(s_img, s_txt, t_img, t_txt)
+        arm.loss_step(*inputs, TEMPERATURE)
         n += 1
         el = time.perf_counter() - t0
         if el > 12.0 or n >= 40:
             break
-    return {"value": B * n / el, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{n} full steps (B={B}, d={d}) of the oracle port (torch fp32 CPU, {cores} threads), {el:.1f} s"}
+    what = "the reference's own loss functions + backward (oracle/_ref, unmodified)" if arm.kind == "reference" else "the oracle port"
+    return {"value": B * n / el, "unit": UNIT, "cores": cores, "kind": arm.kind,
+            "sample": f"{n} full steps (B={B}, d={d}) of {what} (torch fp32 CPU, {cores} threads), {el:.1f} s"}
 
 
 if __name__ == "__main__":

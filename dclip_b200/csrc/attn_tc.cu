@@ -29,7 +29,7 @@ using namespace tc;
 
 namespace at {
 constexpr int kThreads = 128;
-constexpr int kQAtom = 128 * 128;          // [128 rows x 64 cols] 16-bit = 16 KB
+constexpr int kQAtom = 128 * 128;          // what an M = 128 MMA reads from an A atom: [128 rows x 64 cols] 16-bit = 16 KB
 constexpr uint32_t kSpin = 1u << 22;
 constexpr float kLog2e = 1.4426950408889634f;
 }  // namespace at
@@ -47,6 +47,11 @@ struct AttnTcDev {
     int* error_flag;
 };
 
+__device__ __forceinline__ float ex2f(float x) {          // arguments are <= 0: ex2.approx.ftz, no range handling needed
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ uint32_t pack16(float a, float b, bool bf) {
     if (bf) {
         const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -83,14 +88,17 @@ __global__ void __launch_bounds__(at::kThreads) k_attn_fwd_tc(const __grid_const
     const AttnTcDirDev& D = a.dir[blockIdx.y];
     const int b = blockIdx.x / a.heads, h = blockIdx.x - b * a.heads;
     const int hd = a.hd, na = (hd + 63) >> 6;
-    const int Lq = D.Lq, Lk = D.Lk, LkP = D.LkP;
-    const int kvAtom = LkP * 128;
+    const int Lq = D.Lq, Lk = D.Lk, LkP = D.LkP, LqP = D.LqP;
+    const int kvAtom = LkP * 128, qAtom = LqP * 128;   // bytes of one [rows x 64 columns] SWIZZLE_128B atom
     const int nap = (LkP + 63) >> 6;
+    // Q and P are A operands of M = 128 MMAs but only LqP rows are loaded / written: the tensor core reads 16 KB from each
+    // atom base, i.e. into the buffers behind it (rows >= LqP of S / O are garbage and never used).  Q and P come first
+    // so that those reads stay inside this CTA's shared memory (the host pads the allocation).
     uint8_t* Qs = smem;
-    uint8_t* Ks = Qs + na * kQAtom;
+    uint8_t* Ps = Qs + na * qAtom;
+    uint8_t* Ks = Ps + nap * qAtom;
     uint8_t* Vs = Ks + na * kvAtom;
-    uint8_t* Ps = Vs + na * kvAtom;
-    uint64_t* bar_tma = reinterpret_cast<uint64_t*>(Ps + nap * kQAtom);
+    uint64_t* bar_tma = reinterpret_cast<uint64_t*>(Vs + na * kvAtom);
     uint64_t* bar_mma = bar_tma + 1;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_mma + 1);
     const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
@@ -107,9 +115,9 @@ __global__ void __launch_bounds__(at::kThreads) k_attn_fwd_tc(const __grid_const
 
     const uint64_t hiK = make_smem_desc_hi(0, 1024, kSwizzle128B);
     if (warp == 0 && elect_one()) {
-        mbar_arrive_expect_tx(bar_tma, (uint32_t)(na * (kQAtom + 2 * kvAtom)));
+        mbar_arrive_expect_tx(bar_tma, (uint32_t)(na * (qAtom + 2 * kvAtom)));
         for (int t = 0; t < na; ++t) {
-            tma_load_2d(Qs + t * kQAtom, &D.tq, bar_tma, h * hd + t * 64, b * Lq);
+            tma_load_2d(Qs + t * qAtom, &D.tq, bar_tma, h * hd + t * 64, b * Lq);
             tma_load_2d(Ks + t * kvAtom, &D.tkv, bar_tma, h * hd + t * 64, b * Lk);
             tma_load_2d(Vs + t * kvAtom, &D.tkv, bar_tma, a.d + h * hd + t * 64, b * Lk);
         }
@@ -119,7 +127,7 @@ __global__ void __launch_bounds__(at::kThreads) k_attn_fwd_tc(const __grid_const
         const uint32_t idesc = make_idesc_f16(128, (uint32_t)LkP, bf ? kFmtBF16 : kFmtF16, 0, 0);
         const uint32_t qa = smem_u32(Qs), ka = smem_u32(Ks);
         for (int ks = 0; ks < hd / 16; ++ks)
-            umma_f16(tmem, smem_desc(hiK, qa + (ks >> 2) * kQAtom + (ks & 3) * 32), smem_desc(hiK, ka + (ks >> 2) * kvAtom + (ks & 3) * 32), idesc,
+            umma_f16(tmem, smem_desc(hiK, qa + (ks >> 2) * qAtom + (ks & 3) * 32), smem_desc(hiK, ka + (ks >> 2) * kvAtom + (ks & 3) * 32), idesc,
                      ks != 0);
         umma_commit(bar_mma);
     }
@@ -127,7 +135,7 @@ __global__ void __launch_bounds__(at::kThreads) k_attn_fwd_tc(const __grid_const
     ok = mbar_wait(bar_mma, 0, kSpin) && ok;
     fence_after_thread_sync();
 
-    // ---- softmax of my row (three passes over TMEM: max, sum, write P) ----
+    // ---- softmax of my row (three passes over TMEM: max, sum, write P); rows >= LqP have no place in the P tile ----
     const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
     const float c = a.scale * kLog2e;
     float mx = -INFINITY;
@@ -139,6 +147,7 @@ __global__ void __launch_bounds__(at::kThreads) k_attn_fwd_tc(const __grid_const
         for (int i = 0; i < 16; ++i)
             if (c0 + i < Lk) mx = fmaxf(mx, __uint_as_float(r[i]));
     }
+    const float mc = mx * c;
     float sum = 0.f;
     for (int c0 = 0; c0 < LkP; c0 += 16) {
         uint32_t r[16];
@@ -146,21 +155,23 @@ __global__ void __launch_bounds__(at::kThreads) k_attn_fwd_tc(const __grid_const
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-            if (c0 + i < Lk) sum += exp2f((__uint_as_float(r[i]) - mx) * c);
+            if (c0 + i < Lk) sum += ex2f(fmaf(__uint_as_float(r[i]), c, -mc));
     }
     const float inv = 1.0f / sum;
     for (int c0 = 0; c0 < LkP; c0 += 16) {
         uint32_t r[16];
         tmem_ld_32x32b_x16(tmem + lane_addr + c0, r);
         tmem_ld_wait();
-        float p[16];
+        if (row < LqP) {
+            float p[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) p[i] = c0 + i < Lk ? exp2f((__uint_as_float(r[i]) - mx) * c) * inv : 0.f;
-        uint8_t* atom = Ps + (c0 >> 6) * kQAtom;
-        const int ch = (c0 & 63) >> 3;
-        *reinterpret_cast<uint4*>(atom + sw128_chunk(row, ch)) = make_uint4(pack16(p[0], p[1], bf), pack16(p[2], p[3], bf), pack16(p[4], p[5], bf), pack16(p[6], p[7], bf));
-        *reinterpret_cast<uint4*>(atom + sw128_chunk(row, ch + 1)) =
-            make_uint4(pack16(p[8], p[9], bf), pack16(p[10], p[11], bf), pack16(p[12], p[13], bf), pack16(p[14], p[15], bf));
+            for (int i = 0; i < 16; ++i) p[i] = c0 + i < Lk ? ex2f(fmaf(__uint_as_float(r[i]), c, -mc)) * inv : 0.f;
+            uint8_t* atom = Ps + (c0 >> 6) * qAtom;
+            const int ch = (c0 & 63) >> 3;
+            *reinterpret_cast<uint4*>(atom + sw128_chunk(row, ch)) = make_uint4(pack16(p[0], p[1], bf), pack16(p[2], p[3], bf), pack16(p[4], p[5], bf), pack16(p[6], p[7], bf));
+            *reinterpret_cast<uint4*>(atom + sw128_chunk(row, ch + 1)) =
+                make_uint4(pack16(p[8], p[9], bf), pack16(p[10], p[11], bf), pack16(p[12], p[13], bf), pack16(p[14], p[15], bf));
+        }
     }
     fence_proxy_async_smem();            // my generic-proxy stores of P -> visible to the tensor core (async proxy)
     fence_before_thread_sync();          // my TMEM reads of S are complete before O overwrites those columns
@@ -173,7 +184,7 @@ __global__ void __launch_bounds__(at::kThreads) k_attn_fwd_tc(const __grid_const
         const uint64_t hiV = make_smem_desc_hi((uint32_t)kvAtom, 1024, kSwizzle128B);
         const uint32_t pa = smem_u32(Ps), va = smem_u32(Vs);
         for (int ks = 0; ks < LkP / 16; ++ks)
-            umma_f16(tmem, smem_desc(hiK, pa + (ks >> 2) * kQAtom + (ks & 3) * 32), smem_desc(hiV, va + ks * 2048), idesc, ks != 0);
+            umma_f16(tmem, smem_desc(hiK, pa + (ks >> 2) * qAtom + (ks & 3) * 32), smem_desc(hiV, va + ks * 2048), idesc, ks != 0);
         umma_commit(bar_mma);
     }
     __syncwarp();
@@ -203,6 +214,13 @@ __global__ void __launch_bounds__(at::kThreads) k_attn_fwd_tc(const __grid_const
 // ------------------------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------------------------
+// Shared memory (all tiles hold only the rows that exist, padded to 16: two CTAs fit on an SM):
+//   Q, dO [LqP x hd] | dS, P [LqP x 128] | K, V [LkP x hd] | barriers;  the bias-gradient scratch aliases Q (dead by then).
+// Q, dO and dS are also A operands of M = 128 MMAs (S, dP, dQ): the tensor core reads 16 KB from each atom base, into the
+// buffers behind it - rows >= LqP of those products are garbage and never used; these tiles come first so that the
+// reads stay inside the CTA's allocation (the host pads it).
+// TMEM (256 columns): S -> [0, LkP), dP -> [128, 128 + LkP); then dQ -> [0, hd), dK -> [128, 128 + hd); dV re-uses
+// [0, hd) once every thread has read its dQ row (it is issued while the dK rows are being stored).
 __global__ void __launch_bounds__(at::kThreads) k_attn_bwd_tc(const __grid_constant__ AttnTcDev a) {
     using namespace at;
     extern __shared__ uint8_t smem_raw[];
@@ -211,23 +229,23 @@ __global__ void __launch_bounds__(at::kThreads) k_attn_bwd_tc(const __grid_const
     const int b = blockIdx.x / a.heads, h = blockIdx.x - b * a.heads;
     const int hd = a.hd, na = (hd + 63) >> 6;
     const int Lq = D.Lq, Lk = D.Lk, LkP = D.LkP, LqP = D.LqP;
-    const int kvAtom = LkP * 128;
+    const int kvAtom = LkP * 128, qAtom = LqP * 128;
     uint8_t* Qs = smem;
-    uint8_t* dOs = Qs + na * kQAtom;
-    uint8_t* Ks = dOs + na * kQAtom;
+    uint8_t* dOs = Qs + na * qAtom;
+    uint8_t* dSs = dOs + na * qAtom;                  // [LqP q x 128 j] = two atoms, always (MN-major A operand with M = 128 j)
+    uint8_t* Ps = dSs + 2 * qAtom;
+    uint8_t* Ks = Ps + 2 * qAtom;
     uint8_t* Vs = Ks + na * kvAtom;
-    uint8_t* Ps = Vs + na * kvAtom;                   // [128 q x 128 j] = two atoms, always (MN-major A operand with M = 128)
-    uint8_t* dSs = Ps + 2 * kQAtom;
-    float* red = reinterpret_cast<float*>(dSs + 2 * kQAtom);       // [4 warps][3 outputs][128 columns]
-    uint64_t* bar_tma = reinterpret_cast<uint64_t*>(red + 4 * 3 * 128);
+    uint64_t* bar_tma = reinterpret_cast<uint64_t*>(Vs + na * kvAtom);
     uint64_t* bar_mma = bar_tma + 1;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_mma + 1);
+    float* red = reinterpret_cast<float*>(tmem_ptr + 2);          // [4 warps][3 outputs][128 columns]
     const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const int row = threadIdx.x;
     const bool bf = a.bf16 != 0;
 
     if (threadIdx.x == 0) { mbar_init(bar_tma, 1); mbar_init(bar_mma, 1); fence_barrier_init(); }
-    if (warp == 0) tmem_alloc(tmem_ptr, 512);
+    if (warp == 0) tmem_alloc(tmem_ptr, 256);
     fence_before_thread_sync();
     __syncthreads();
     fence_after_thread_sync();
@@ -237,10 +255,10 @@ __global__ void __launch_bounds__(at::kThreads) k_attn_bwd_tc(const __grid_const
     const uint32_t fmt = bf ? kFmtBF16 : kFmtF16;
 
     if (warp == 0 && elect_one()) {
-        mbar_arrive_expect_tx(bar_tma, (uint32_t)(na * (2 * kQAtom + 2 * kvAtom)));
+        mbar_arrive_expect_tx(bar_tma, (uint32_t)(na * (2 * qAtom + 2 * kvAtom)));
         for (int t = 0; t < na; ++t) {
-            tma_load_2d(Qs + t * kQAtom, &D.tq, bar_tma, h * hd + t * 64, b * Lq);
-            tma_load_2d(dOs + t * kQAtom, &D.tdo, bar_tma, h * hd + t * 64, b * Lq);
+            tma_load_2d(Qs + t * qAtom, &D.tq, bar_tma, h * hd + t * 64, b * Lq);
+            tma_load_2d(dOs + t * qAtom, &D.tdo, bar_tma, h * hd + t * 64, b * Lq);
             tma_load_2d(Ks + t * kvAtom, &D.tkv, bar_tma, h * hd + t * 64, b * Lk);
             tma_load_2d(Vs + t * kvAtom, &D.tkv, bar_tma, a.d + h * hd + t * 64, b * Lk);
         }
@@ -249,7 +267,7 @@ __global__ void __launch_bounds__(at::kThreads) k_attn_bwd_tc(const __grid_const
         const uint32_t idesc = make_idesc_f16(128, (uint32_t)LkP, fmt, 0, 0);
         const uint32_t qa = smem_u32(Qs), doa = smem_u32(dOs), ka = smem_u32(Ks), va = smem_u32(Vs);
         for (int ks = 0; ks < hd / 16; ++ks) {       // S = Q K^T -> columns [0, LkP);  dP = dO V^T -> columns [128, 128 + LkP)
-            const uint32_t offq = (ks >> 2) * kQAtom + (ks & 3) * 32, offk = (ks >> 2) * kvAtom + (ks & 3) * 32;
+            const uint32_t offq = (ks >> 2) * qAtom + (ks & 3) * 32, offk = (ks >> 2) * kvAtom + (ks & 3) * 32;
             umma_f16(tmem, smem_desc(hiK, qa + offq), smem_desc(hiK, ka + offk), idesc, ks != 0);
             umma_f16(tmem + 128, smem_desc(hiK, doa + offq), smem_desc(hiK, va + offk), idesc, ks != 0);
         }
@@ -259,7 +277,7 @@ __global__ void __launch_bounds__(at::kThreads) k_attn_bwd_tc(const __grid_const
     ok = mbar_wait(bar_mma, 0, kSpin) && ok;
     fence_after_thread_sync();
 
-    // ---- recompute P, form dS (my row) ----
+    // ---- recompute P, form dS (my row): max; then sum and sum(e dP) in one pass; then write ----
     const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
     const float c = a.scale * kLog2e;
     float mx = -INFINITY;
@@ -271,17 +289,8 @@ __global__ void __launch_bounds__(at::kThreads) k_attn_bwd_tc(const __grid_const
         for (int i = 0; i < 16; ++i)
             if (c0 + i < Lk) mx = fmaxf(mx, __uint_as_float(r[i]));
     }
-    float sum = 0.f;
-    for (int c0 = 0; c0 < LkP; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld_32x32b_x16(tmem + lane_addr + c0, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-            if (c0 + i < Lk) sum += exp2f((__uint_as_float(r[i]) - mx) * c);
-    }
-    const float inv = 1.0f / sum;
-    float dot = 0.f;                                  // sum_j P_j dP_j
+    const float mc = mx * c;
+    float sum = 0.f, dot = 0.f;                       // sum_j e_j,  sum_j e_j dP_j
     for (int c0 = 0; c0 < LkP; c0 += 16) {
         uint32_t r[16], g[16];
         tmem_ld_32x32b_x16(tmem + lane_addr + c0, r);
@@ -289,57 +298,63 @@ __global__ void __launch_bounds__(at::kThreads) k_attn_bwd_tc(const __grid_const
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-            if (c0 + i < Lk) dot = fmaf(exp2f((__uint_as_float(r[i]) - mx) * c) * inv, __uint_as_float(g[i]), dot);
+            if (c0 + i < Lk) {
+                const float e = ex2f(fmaf(__uint_as_float(r[i]), c, -mc));
+                sum += e;
+                dot = fmaf(e, __uint_as_float(g[i]), dot);
+            }
     }
+    const float inv = 1.0f / sum;
+    dot *= inv;
     const bool row_ok = row < Lq;
     const float dsc = a.scale * a.ds_scale;
-    for (int c0 = 0; c0 < 128; c0 += 16) {
-        float p[16], ds[16];
-        if (c0 < LkP) {
-            uint32_t r[16], g[16];
-            tmem_ld_32x32b_x16(tmem + lane_addr + c0, r);
-            tmem_ld_32x32b_x16(tmem + lane_addr + 128 + c0, g);
-            tmem_ld_wait();
+    if (warp * 32 < LqP) {               // warp-uniform (the TMEM loads are warp-collective); rows >= LqP of a straddling warp only skip the stores
+        for (int c0 = 0; c0 < 128; c0 += 16) {
+            float p[16], ds[16];
+            if (c0 < LkP) {
+                uint32_t r[16], g[16];
+                tmem_ld_32x32b_x16(tmem + lane_addr + c0, r);
+                tmem_ld_32x32b_x16(tmem + lane_addr + 128 + c0, g);
+                tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const bool v = row_ok && c0 + i < Lk;
-                p[i] = v ? exp2f((__uint_as_float(r[i]) - mx) * c) * inv : 0.f;
-                ds[i] = v ? p[i] * (__uint_as_float(g[i]) - dot) * dsc : 0.f;
+                for (int i = 0; i < 16; ++i) {
+                    const bool v = row_ok && c0 + i < Lk;
+                    p[i] = v ? ex2f(fmaf(__uint_as_float(r[i]), c, -mc)) * inv : 0.f;
+                    ds[i] = v ? p[i] * (__uint_as_float(g[i]) - dot) * dsc : 0.f;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { p[i] = 0.f; ds[i] = 0.f; }
             }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) { p[i] = 0.f; ds[i] = 0.f; }
+            if (row >= LqP) continue;          // no such row in the P / dS tiles
+            const int ch = (c0 & 63) >> 3;
+            uint8_t* pa = Ps + (c0 >> 6) * qAtom;
+            uint8_t* da = dSs + (c0 >> 6) * qAtom;
+            *reinterpret_cast<uint4*>(pa + sw128_chunk(row, ch)) = make_uint4(pack16(p[0], p[1], bf), pack16(p[2], p[3], bf), pack16(p[4], p[5], bf), pack16(p[6], p[7], bf));
+            *reinterpret_cast<uint4*>(pa + sw128_chunk(row, ch + 1)) =
+                make_uint4(pack16(p[8], p[9], bf), pack16(p[10], p[11], bf), pack16(p[12], p[13], bf), pack16(p[14], p[15], bf));
+            *reinterpret_cast<uint4*>(da + sw128_chunk(row, ch)) =
+                make_uint4(pack16(ds[0], ds[1], bf), pack16(ds[2], ds[3], bf), pack16(ds[4], ds[5], bf), pack16(ds[6], ds[7], bf));
+            *reinterpret_cast<uint4*>(da + sw128_chunk(row, ch + 1)) =
+                make_uint4(pack16(ds[8], ds[9], bf), pack16(ds[10], ds[11], bf), pack16(ds[12], ds[13], bf), pack16(ds[14], ds[15], bf));
         }
-        const int ch = (c0 & 63) >> 3;
-        uint8_t* pa = Ps + (c0 >> 6) * kQAtom;
-        uint8_t* da = dSs + (c0 >> 6) * kQAtom;
-        *reinterpret_cast<uint4*>(pa + sw128_chunk(row, ch)) = make_uint4(pack16(p[0], p[1], bf), pack16(p[2], p[3], bf), pack16(p[4], p[5], bf), pack16(p[6], p[7], bf));
-        *reinterpret_cast<uint4*>(pa + sw128_chunk(row, ch + 1)) =
-            make_uint4(pack16(p[8], p[9], bf), pack16(p[10], p[11], bf), pack16(p[12], p[13], bf), pack16(p[14], p[15], bf));
-        *reinterpret_cast<uint4*>(da + sw128_chunk(row, ch)) =
-            make_uint4(pack16(ds[0], ds[1], bf), pack16(ds[2], ds[3], bf), pack16(ds[4], ds[5], bf), pack16(ds[6], ds[7], bf));
-        *reinterpret_cast<uint4*>(da + sw128_chunk(row, ch + 1)) =
-            make_uint4(pack16(ds[8], ds[9], bf), pack16(ds[10], ds[11], bf), pack16(ds[12], ds[13], bf), pack16(ds[14], ds[15], bf));
     }
     fence_proxy_async_smem();
     fence_before_thread_sync();
     __syncthreads();
 
+    const uint32_t qa = smem_u32(Qs), doa = smem_u32(dOs), ka = smem_u32(Ks), pa_ = smem_u32(Ps), dsa = smem_u32(dSs);
+    const uint32_t idesc_t = make_idesc_f16(128, (uint32_t)hd, fmt, 1, 1);     // A MN-major (dS^T / P^T), B MN-major (Q / dO)
+    const uint64_t hiQ = make_smem_desc_hi((uint32_t)qAtom, 1024, kSwizzle128B);         // MN-major, 64-column groups qAtom apart
     if (warp == 0 && elect_one()) {
         fence_after_thread_sync();
-        const uint32_t qa = smem_u32(Qs), doa = smem_u32(dOs), ka = smem_u32(Ks), pa = smem_u32(Ps), dsa = smem_u32(dSs);
         const uint32_t idesc_q = make_idesc_f16(128, (uint32_t)hd, fmt, 0, 1);     // A K-major (dS), B MN-major (K)
-        const uint32_t idesc_t = make_idesc_f16(128, (uint32_t)hd, fmt, 1, 1);     // A MN-major (dS^T / P^T), B MN-major (Q / dO)
         const uint64_t hiKV = make_smem_desc_hi((uint32_t)kvAtom, 1024, kSwizzle128B);   // MN-major, 64-column groups kvAtom apart
-        const uint64_t hiQ = make_smem_desc_hi((uint32_t)kQAtom, 1024, kSwizzle128B);    // MN-major, groups 16 KB apart
-        // dQ[128 q x hd] = dS K        (contraction over j, LkP / 16 steps)            -> columns [0, hd)
+        // dQ[128 q x hd] = dS K  (contraction over j, LkP / 16 steps) -> [0, hd);  dK[128 j x hd] = dS^T Q (over q) -> [128, 128 + hd)
         for (int ks = 0; ks < LkP / 16; ++ks)
-            umma_f16(tmem, smem_desc(hiK, dsa + (ks >> 2) * kQAtom + (ks & 3) * 32), smem_desc(hiKV, ka + ks * 2048), idesc_q, ks != 0);
-        // dK[128 j x hd] = dS^T Q,  dV[128 j x hd] = P^T dO   (contraction over q, LqP / 16 steps) -> [128, 128 + hd), [256, 256 + hd)
-        for (int ks = 0; ks < LqP / 16; ++ks) {
+            umma_f16(tmem, smem_desc(hiK, dsa + (ks >> 2) * qAtom + (ks & 3) * 32), smem_desc(hiKV, ka + ks * 2048), idesc_q, ks != 0);
+        for (int ks = 0; ks < LqP / 16; ++ks)
             umma_f16(tmem + 128, smem_desc(hiQ, dsa + ks * 2048), smem_desc(hiQ, qa + ks * 2048), idesc_t, ks != 0);
-            umma_f16(tmem + 256, smem_desc(hiQ, pa + ks * 2048), smem_desc(hiQ, doa + ks * 2048), idesc_t, ks != 0);
-        }
         umma_commit(bar_mma);
     }
     __syncwarp();
@@ -351,41 +366,54 @@ __global__ void __launch_bounds__(at::kThreads) k_attn_bwd_tc(const __grid_const
     uint16_t* dq = static_cast<uint16_t*>(D.dQ) + ((size_t)b * Lq + row) * a.d + h * hd;
     uint16_t* dk = static_cast<uint16_t*>(D.dKV) + ((size_t)b * Lk + row) * 2 * a.d + h * hd;
     uint16_t* dv = dk + a.d;
-#pragma unroll 1
-    for (int o = 0; o < 3; ++o) {
+    auto drain = [&](int o, uint32_t tcol) {
         uint16_t* dst = o == 0 ? dq : o == 1 ? dk : dv;
         const bool valid = o == 0 ? row < Lq : row < Lk;
         const float sc = o == 2 ? 1.0f : inv_ds;
         for (int c0 = 0; c0 < hd; c0 += 32) {
             uint32_t r[32];
-            tmem_ld_32x32b_x32(tmem + lane_addr + o * 128 + c0, r);
+            tmem_ld_32x32b_x32(tmem + lane_addr + tcol + c0, r);
             tmem_ld_wait();
             float v[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * sc;
+            for (int i = 0; i < 32; ++i) v[i] = valid ? __uint_as_float(r[i]) * sc : 0.f;     // rows past the sequence: garbage, masked
             if (valid) {
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4)
                     *reinterpret_cast<uint4*>(dst + c0 + q4 * 8) = make_uint4(pack16(v[q4 * 8], v[q4 * 8 + 1], bf), pack16(v[q4 * 8 + 2], v[q4 * 8 + 3], bf),
                                                                               pack16(v[q4 * 8 + 4], v[q4 * 8 + 5], bf), pack16(v[q4 * 8 + 6], v[q4 * 8 + 7], bf));
             }
-            // rows past the sequence are exact zeros by construction (zero rows / columns of dS and P): no masking needed
             red[(warp * 3 + o) * 128 + c0 + lane] = warp_colsum32(v, lane);
         }
+    };
+    drain(0, 0);                                       // dQ
+    fence_before_thread_sync();                        // every thread has read its dQ row: the columns may be overwritten
+    __syncthreads();
+    if (warp == 0 && elect_one()) {
+        fence_after_thread_sync();
+        // dV[128 j x hd] = P^T dO (contraction over q) -> [0, hd), issued while the dK rows drain
+        for (int ks = 0; ks < LqP / 16; ++ks)
+            umma_f16(tmem, smem_desc(hiQ, pa_ + ks * 2048), smem_desc(hiQ, doa + ks * 2048), idesc_t, ks != 0);
+        umma_commit(bar_mma);
     }
+    __syncwarp();
+    drain(1, 128);                                     // dK
+    ok = mbar_wait(bar_mma, 0, kSpin) && ok;           // third completion of the barrier: parity 0 again
+    fence_after_thread_sync();
+    drain(2, 0);                                       // dV
     __syncthreads();
     if (D.dbq) {
         for (int e = threadIdx.x; e < 3 * hd; e += kThreads) {
             const int o = e / hd, col = e - o * hd;
-            const float s = red[(0 * 3 + o) * 128 + col] + red[(1 * 3 + o) * 128 + col] + red[(2 * 3 + o) * 128 + col] + red[(3 * 3 + o) * 128 + col];
-            if (o == 0) D.dbq[(size_t)b * a.d + h * hd + col] = s;
-            else D.dbkv[(size_t)b * 2 * a.d + (o - 1) * a.d + h * hd + col] = s;
+            const float sv = red[(0 * 3 + o) * 128 + col] + red[(1 * 3 + o) * 128 + col] + red[(2 * 3 + o) * 128 + col] + red[(3 * 3 + o) * 128 + col];
+            if (o == 0) D.dbq[(size_t)b * a.d + h * hd + col] = sv;
+            else D.dbkv[(size_t)b * 2 * a.d + (o - 1) * a.d + h * hd + col] = sv;
         }
     }
     if (!__all_sync(0xffffffffu, ok) && lane == 0 && a.error_flag) atomicExch(a.error_flag, 1);
     fence_before_thread_sync();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 512);
+    if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
 int* tc_error_flag();   // loss_tc.cu
@@ -396,10 +424,18 @@ bool attn_tc_shape_ok(int64_t T, int64_t R, int64_t d, int heads) {
     return hd % 32 == 0 && hd >= 32 && hd <= 128 && d % 8 == 0 && T >= 1 && T <= 128 && R >= 1 && R <= 128;
 }
 
-static size_t attn_smem(int hd, int Lk, bool bwd) {
-    const int na = (hd + 63) / 64, LkP = (Lk + 15) / 16 * 16, kv = LkP * 128;
-    if (!bwd) return 1024 + (size_t)na * (at::kQAtom + 2 * kv) + (size_t)((LkP + 63) / 64) * at::kQAtom + 64;
-    return 1024 + (size_t)na * (2 * at::kQAtom + 2 * kv) + 4 * at::kQAtom + 4 * 3 * 128 * sizeof(float) + 64;
+static size_t attn_smem(int hd, int Lq, int Lk, bool bwd) {
+    const size_t na = (hd + 63) / 64, LkP = (Lk + 15) / 16 * 16, LqP = (Lq + 15) / 16 * 16, kv = LkP * 128, qa = LqP * 128;
+    size_t total, last_a;      // last_a: base of the last atom that is read as a 128-row A operand (16 KB from its base)
+    if (!bwd) {
+        const size_t nap = (LkP + 63) / 64;
+        total = (na + nap) * qa + 2 * na * kv + 64;
+        last_a = (na + nap - 1) * qa;
+    } else {
+        total = (2 * na + 4) * qa + 2 * na * kv + 64 + 4 * 3 * 128 * sizeof(float);
+        last_a = (2 * na + 1) * qa;
+    }
+    return 1024 + max(total, last_a + (size_t)at::kQAtom);
 }
 
 // text side: rows = B*T, image side: rows = B*R.  dir 0 = text queries over image keys, dir 1 = the reverse.
@@ -418,11 +454,11 @@ int launch_attn_tc(const AttnTcProblem& p, bool backward, cudaStream_t st) {
         D.Lq = Lq; D.Lk = Lk; D.LkP = (Lk + 15) / 16 * 16; D.LqP = (Lq + 15) / 16 * 16;
         const void* Q = dir == 0 ? p.Qt : p.Qi;
         const void* KV = dir == 0 ? p.KVi : p.KVt;
-        bool okm = make_tmap_2d_sw128_ld(&D.tq, Q, (uint64_t)p.B * Lq, (uint64_t)p.d, (uint64_t)p.d, 128, dt);
+        bool okm = make_tmap_2d_sw128_ld(&D.tq, Q, (uint64_t)p.B * Lq, (uint64_t)p.d, (uint64_t)p.d, (uint32_t)D.LqP, dt);
         okm = okm && make_tmap_2d_sw128_ld(&D.tkv, KV, (uint64_t)p.B * Lk, (uint64_t)2 * p.d, (uint64_t)2 * p.d, (uint32_t)D.LkP, dt);
         if (backward) {
             const void* dO = dir == 0 ? p.dOt : p.dOi;
-            okm = okm && make_tmap_2d_sw128_ld(&D.tdo, dO, (uint64_t)p.B * Lq, (uint64_t)p.d, (uint64_t)p.d, 128, dt);
+            okm = okm && make_tmap_2d_sw128_ld(&D.tdo, dO, (uint64_t)p.B * Lq, (uint64_t)p.d, (uint64_t)p.d, (uint32_t)D.LqP, dt);
             D.dQ = dir == 0 ? p.dQt : p.dQi;
             D.dKV = dir == 0 ? p.dKVi : p.dKVt;
             D.dbq = dir == 0 ? p.dbq_t2i : p.dbq_i2t;
@@ -435,7 +471,7 @@ int launch_attn_tc(const AttnTcProblem& p, bool backward, cudaStream_t st) {
         }
         if (!okm) return fail(DCLIP_ERR_CUDA, "attention: cuTensorMapEncodeTiled failed");
     }
-    const size_t smem = max(attn_smem(a.hd, p.R, backward), attn_smem(a.hd, p.T, backward));
+    const size_t smem = max(attn_smem(a.hd, p.T, p.R, backward), attn_smem(a.hd, p.R, p.T, backward));
     dim3 grid((unsigned)(p.B * p.heads), 2);
     if (backward) {
         DCLIP_CUDA_OK(cudaFuncSetAttribute(k_attn_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

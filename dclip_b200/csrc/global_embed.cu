@@ -50,7 +50,9 @@ __device__ __forceinline__ const T* ge_stage(const T* xb, int L, int d, void* st
     return reinterpret_cast<const T*>(stage);
 }
 
-// merge per-warp column accumulators: red[warp][d] -> dst[d] (sum over warps in order) * scale
+// Per-column fp32 vectors in shared memory (mean, dmean, the merged accumulators) are kept CHUNK-TRANSPOSED: element i of
+// 8-element chunk ch lives at [i * nch + ch], so the lanes of a warp (consecutive chunks) touch consecutive words.
+// merge per-warp column accumulators: red[warp][d] -> dst[d] (sum over warps in order) * scale, same layout
 template <int NC>
 __device__ __forceinline__ void ge_merge(float (&acc)[NC][8], float* red, float* dst, int d, float scale) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nch = d >> 3;
@@ -59,7 +61,7 @@ __device__ __forceinline__ void ge_merge(float (&acc)[NC][8], float* red, float*
     for (int k = 0; k < NC; ++k)
         if (lane + 32 * k < nch)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) red[(size_t)warp * d + (lane + 32 * k) * 8 + i] = acc[k][i];
+            for (int i = 0; i < 8; ++i) red[(size_t)warp * d + i * nch + lane + 32 * k] = acc[k][i];       // chunk-transposed: lanes hit consecutive words
     __syncthreads();
     for (int c = threadIdx.x; c < d; c += ge::kThreads) {
         float s = 0.f;
@@ -138,7 +140,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ge::kThreads) k_glob
                 float v[8];
                 load8<T>(xb + (size_t)l * d + ch * 8, v);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) dot = fmaf(v[i], mean[ch * 8 + i], dot);
+                for (int i = 0; i < 8; ++i) dot = fmaf(v[i], mean[i * nch + ch], dot);
             }
         }
         dot = warp_sum(dot);
@@ -189,7 +191,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ge::kThreads) k_glob
     bool bad = false;
     T* out = static_cast<T*>(a.out) + (size_t)b * d;
     for (int c = threadIdx.x; c < d; c += kThreads) {
-        const float v = 0.5f * mean[c] + 0.5f * vecb[c];
+        const int t = (c & 7) * nch + (c >> 3);              // chunk-transposed position of column c
+        const float v = 0.5f * mean[t] + 0.5f * vecb[t];
         bad |= !isfinite(v);
         out[c] = from_f32<T>(v);
     }
@@ -287,7 +290,7 @@ __global__ void __launch_bounds__(ge::kThreads) k_global_bwd(const __grid_consta
                 float v[8];
                 load8<T>(xb + (size_t)l * d + ch * 8, v);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) dot = fmaf(v[i], mean[ch * 8 + i], dot);
+                for (int i = 0; i < 8; ++i) dot = fmaf(v[i], mean[i * nch + ch], dot);
             }
         }
         dot = warp_sum(dot);
@@ -339,7 +342,7 @@ __global__ void __launch_bounds__(ge::kThreads) k_global_bwd(const __grid_consta
                 float v[8], o[8];
                 load8<T>(xb + (size_t)l * d + ch * 8, v);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) o[i] = fmaf(w, dg[k][i], fmaf(e, mean[ch * 8 + i], fmaf(-f, v[i], dmean[ch * 8 + i])));
+                for (int i = 0; i < 8; ++i) o[i] = fmaf(w, dg[k][i], fmaf(e, mean[i * nch + ch], fmaf(-f, v[i], dmean[i * nch + ch])));
                 store8<T>(dxb + (size_t)l * d + ch * 8, o);
             }
         }

@@ -373,7 +373,7 @@ static int distill_loss_impl(int phase, const void* s_img, const void* s_txt, co
 
     // small batches (the teacher step's B = 32, the reference's own distillation batch): the whole objective in ONE
     // launch of one 8-CTA cluster instead of six launch-latency-bound kernels (DCLIP_LOSS_SMALL=0: generic path)
-    if (phase == 0 && !tensor && small_loss_shape_ok(B, d) && (B * (ceil_div(ceil_div(d, 8), 8) * 8 + 1) * 16 + B * B * 12) < 200 * 1024) {
+    if (phase == 0 && !tensor && small_loss_shape_ok(B, d) && (B * (ceil_div(ceil_div(d, 8), 8) * 8 + 4) * 16 + B * (B + 1) * 16) < 200 * 1024) {
         static const bool off = [] { const char* e = getenv("DCLIP_LOSS_SMALL"); return e && e[0] == '0'; }();
         if (!off)
             return launch_distill_small(s_img, s_txt, t_img, t_txt, B, d, dtype, temperature, w_img, w_txt, w_con, grad_scale, losses, d_s_img,

@@ -136,13 +136,15 @@ __global__ void __launch_bounds__(256) k_ln_bwd16(const __grid_constant__ LnBwdA
         for (int k = 0; k < NC; ++k)
             if (lane + 32 * k < nch)
 #pragma unroll
-                for (int i = 0; i < 8; ++i) red[((size_t)warp * 3 + q) * d + (lane + 32 * k) * 8 + i] = acc[q][k][i];
+                for (int i = 0; i < 8; ++i) red[((size_t)warp * 3 + q) * d + i * nch + lane + 32 * k] = acc[q][k][i];   // chunk-transposed
     __syncthreads();
     float* out = a.part + (size_t)blockIdx.x * 3 * d;
     for (int e = threadIdx.x; e < 3 * d; e += 256) {
+        const int q = e / d, c = e - q * d;
+        const int t = q * d + (c & 7) * nch + (c >> 3);      // chunk-transposed position of column c
         float s = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) s += red[(size_t)w * 3 * d + e];
+        for (int w = 0; w < 8; ++w) s += red[(size_t)w * 3 * d + t];
         out[e] = s;
     }
 }

@@ -14,7 +14,8 @@ buf = (ctypes.c_longlong * 16)()
 lib.dclip_debug_small_prof.restype = ctypes.c_int
 lib.dclip_debug_small_prof(buf)
 t = list(buf)
-names = ["load", "partial S", "(sync wait)", "cluster.sync 1", "exchange 1", "inv + logits", "lse", "losses", "G + normalise", "grad slice", "proj dots", "cluster.sync 2", "exchange 2 + store", "cluster.sync 3"]
+names = ["load", "partial S + norms", "cluster.sync 1", "exchange 1", "inv + logits", "lse", "losses", "G + normalise", "grad slice", "proj dots", "cluster.sync 2", "exchange 2 + store", "cluster.sync 3"]
 for i in range(13):
     print(f"{names[i]:22s} {t[i + 1] - t[i]:8d} cycles")
 print("total", t[13] - t[0])
+
