@@ -12,8 +12,9 @@
 // (the MN-major canonical layout is the same bytes TMA writes for a [k rows x 64 columns] box; both
 // were validated against a CPU GEMM with tools/tc_probe).  Tile 128 x 256, K in 64-wide stages, 4-stage
 // ring, 4 producer warps, 1 MMA-issuer warp, 8 epilogue warps (thread = output row; two warps per TMEM lane
-// quadrant split the columns; bias / residual / conversion in registers, 16-byte stores straight from the row the
-// thread owns - the epilogue of a K = 768 tile must not cost more than its 12-stage main loop).  Persistent CTAs.
+// quadrant split the columns; bias / residual / conversion in registers, then a swizzled 4 KB staging buffer per warp so
+// that global stores are 128 contiguous bytes per row - the epilogue of a K = 768 tile must not cost more than its
+// 12-stage main loop).  Persistent CTAs.
 // bias / residual: fp32 or the operands' 16-bit type; outputs: fp32 C and / or 16-bit C16.
 #include "common.cuh"
 #include "gemm_tc.h"
@@ -47,6 +48,24 @@ struct TcGemmArgs {
     int* error_flag;
 };
 
+#ifdef DCLIP_GEMM_PROF
+__device__ long long g_gemm_prof[16];
+#define GPROF(k) do { if (blockIdx.x == 0) g_gemm_prof[k] = clock64(); } while (0)
+#else
+#define GPROF(k) do { } while (0)
+#endif
+
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) { const __nv_bfloat162 v = __floats2bfloat162_rn(a, b); return *reinterpret_cast<const uint32_t*>(&v); }
+__device__ __forceinline__ uint32_t pack_f16(float a, float b) { const __half2 v = __floats2half2_rn(a, b); return *reinterpret_cast<const uint32_t*>(&v); }
+
 struct TileCoord { int pi, m0, n0, nkb; };
 __device__ __forceinline__ TileCoord tile_coord(const TcGemmArgs& g, int tile) {
     int pi = 0;
@@ -72,6 +91,7 @@ __global__ void __launch_bounds__(kGThreads, 1) k_gemm_tc(const __grid_constant_
     const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const int total_tiles = g.total_tiles;
 
+    if (threadIdx.x == 0) GPROF(0);
     if (threadIdx.x == 0) {
         for (int i = 0; i < kGStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kGEpiWarps * 32); }
@@ -83,6 +103,7 @@ __global__ void __launch_bounds__(kGThreads, 1) k_gemm_tc(const __grid_constant_
     fence_after_thread_sync();
     const uint32_t tmem = *tmem_ptr;
     bool ok = true;
+    if (threadIdx.x == 0) GPROF(1);
 
     if (warp < kGStages) {
         // ---- TMA producers: warp w owns ring stage w; stage job q = running k-block index over all my tiles
@@ -101,6 +122,7 @@ __global__ void __launch_bounds__(kGThreads, 1) k_gemm_tc(const __grid_constant_
                 for (; kb < tc.nkb && ok; kb += kGStages, phase ^= 1) {
                     const int k0 = kb * GKS;
                     ok = mbar_wait(&empty[warp], phase ^ 1, kSpinG);
+                    if (warp == 0 && kb == 0 && tile == (int)blockIdx.x) GPROF(2);
                     mbar_arrive_expect_tx(&full[warp], kGStageBytes);
                     if (!P.a_mn) tma_load_2d(dst, ta, &full[warp], k0, tc.m0);                     // [128 m x 64 k]
                     else
@@ -130,6 +152,8 @@ __global__ void __launch_bounds__(kGThreads, 1) k_gemm_tc(const __grid_constant_
                 fence_after_thread_sync();
                 for (int kb = 0; kb < tc.nkb && ok; ++kb) {
                     ok = mbar_wait(&full[stage], phase, kSpinG);
+                    if (it == 0 && kb == 0) GPROF(3);
+                    if (it == 0 && kb == tc.nkb - 1) GPROF(4);
                     fence_after_thread_sync();
                     const uint64_t da0 = smem_desc(hiA, ring_addr + stage * kGStageBytes);
                     const uint64_t db0 = smem_desc(hiB, ring_addr + stage * kGStageBytes + kGAStage);
@@ -143,15 +167,20 @@ __global__ void __launch_bounds__(kGThreads, 1) k_gemm_tc(const __grid_constant_
             }
         }
     } else {
-        // ---- epilogue: TMEM hands each thread one output ROW (lane) and 32 consecutive columns per load; the thread
-        // adds bias / residual in registers and stores its 64 (16-bit) or 128 (fp32) contiguous bytes with 16-byte
-        // stores - no shared-memory transposition, ~70 instructions per 32 x 32 chunk.  Eight warps: warp % 4 is the
-        // TMEM lane quadrant it may read, the two warps of a quadrant split the tile's columns.  N % 8 == 0 (checked on
-        // the host), so every 8-column group is entirely inside or outside C.
+        // ---- epilogue.  TMEM hands each thread one output ROW (lane) and 32 consecutive columns per load; global memory
+        // wants a warp on few rows: a store in which every lane touches a different row costs ~32 memory-pipe cycles
+        // (4096 cycles for a 128 x 256 16-bit tile, more than the 12-stage main loop of a K = 768 tile).  So: bias /
+        // residual are added in registers, the 32 x 64 chunk is staged through a private 4 KB shared-memory buffer
+        // (16-byte chunks XOR-swizzled by the row: conflict-free both ways) and written back with 8 lanes per row =
+        // 128 contiguous bytes per row.  Eight warps: warp % 4 is the TMEM lane quadrant it may read, the two warps
+        // of a quadrant split the tile's columns.  N % 8 == 0 (host-checked): an 8-column group is inside C or not.
         const int qd = warp & 3;
-        const int half = (warp - (kGStages + 1)) >> 2;
+        const int we = warp - (kGStages + 1);
+        const int half = we >> 2;
         const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
+        const uint32_t stage_s = smem_u32(ring + kGStages * kGStageBytes + 256) + (uint32_t)we * 4096;
         const bool bf = g.ab_fmt == (int)kFmtBF16;
+        const int rb_row = lane >> 3, rb_chunk = lane & 7;           // read-back: 8 lanes per row, 4 rows per pass
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const TileCoord tc = tile_coord(g, tile);
@@ -160,23 +189,27 @@ __global__ void __launch_bounds__(kGThreads, 1) k_gemm_tc(const __grid_constant_
             ok = mbar_wait(&acc_full[b], (it >> 1) & 1, kSpinG);
             ok = __all_sync(0xffffffffu, ok);
             if (!ok) break;
+            if (it == 0 && warp == kGStages + 1 && lane == 0) GPROF(5);
             fence_after_thread_sync();
-            const int grow = tc.m0 + qd * 32 + lane;
+            const int rbase = tc.m0 + qd * 32;
+            const int grow = rbase + lane;
             const bool row_ok = grow < P.M;
 #pragma unroll 1
-            for (int c0 = half * (GN / 2); c0 < (half + 1) * (GN / 2); c0 += 32) {
+            for (int c0 = half * (GN / 2); c0 < (half + 1) * (GN / 2); c0 += 64) {
                 const int col = tc.n0 + c0;
                 if (col >= P.N) break;                        // warp-uniform
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(tmem + lane_addr + b * GN + c0, r);
-                tmem_ld_wait();
-                float v[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-                const int ngrp = min(4, (P.N - col) >> 3);      // 8-column groups of this chunk inside C (warp-uniform)
+                const int ngrp = min(8, (P.N - col) >> 3);      // 8-column groups of this chunk inside C (warp-uniform)
+                float v[64];
+                {
+                    uint32_t(&r)[64] = *reinterpret_cast<uint32_t(*)[64]>(v);
+                    tmem_ld_32x32b_x32(tmem + lane_addr + b * GN + c0, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+                    // (columns past N hold whatever the MMA left there - TMA zero-fills the operands, so zeros; never stored)
+                    tmem_ld_32x32b_x32(tmem + lane_addr + b * GN + c0 + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+                    tmem_ld_wait();
+                }
                 if (P.bias) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
+                    for (int q = 0; q < 8; ++q)
                         if (q < ngrp) {
                             float bv[8];
                             if (P.bias_kind == 0) load8<float>(static_cast<const float*>(P.bias) + col + q * 8, bv);
@@ -186,55 +219,85 @@ __global__ void __launch_bounds__(kGThreads, 1) k_gemm_tc(const __grid_constant_
                             for (int i = 0; i < 8; ++i) v[q * 8 + i] += bv[i];
                         }
                 }
-                if (row_ok) {
-                    if (P.residual) {
+                if (row_ok && P.residual) {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            if (q < ngrp) {
-                                float rv[8];
-                                const size_t off = (size_t)grow * P.ldr + col + q * 8;
-                                if (P.res_kind == 0) load8<float>(static_cast<const float*>(P.residual) + off, rv);
-                                else if (bf) load8<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(P.residual) + off, rv);
-                                else load8<__half>(static_cast<const __half*>(P.residual) + off, rv);
+                    for (int q = 0; q < 8; ++q)
+                        if (q < ngrp) {
+                            float rv[8];
+                            const size_t off = (size_t)grow * P.ldr + col + q * 8;
+                            if (P.res_kind == 0) load8<float>(static_cast<const float*>(P.residual) + off, rv);
+                            else if (bf) load8<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(P.residual) + off, rv);
+                            else load8<__half>(static_cast<const __half*>(P.residual) + off, rv);
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) v[q * 8 + i] += rv[i];
-                            }
+                            for (int i = 0; i < 8; ++i) v[q * 8 + i] += rv[i];
+                        }
+                }
+                if (row_ok && P.C && P.accumulate) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        if (q < ngrp) {
+                            float cv[8];
+                            load8<float>(P.C + (size_t)grow * P.ldc + col + q * 8, cv);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[q * 8 + i] += cv[i];
+                        }
+                }
+                if (P.C) {
+                    // fp32 output: two passes of 32 columns (128 B per row each)
+#pragma unroll
+                    for (int hsub = 0; hsub < 2; ++hsub) {
+                        if (hsub * 4 >= ngrp) break;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            sts128(stage_s + lane * 128 + ((q ^ (lane & 7)) << 4),
+                                   make_uint4(__float_as_uint(v[hsub * 32 + q * 4]), __float_as_uint(v[hsub * 32 + q * 4 + 1]),
+                                              __float_as_uint(v[hsub * 32 + q * 4 + 2]), __float_as_uint(v[hsub * 32 + q * 4 + 3])));
+                        __syncwarp();
+                        const int ccol = col + hsub * 32 + rb_chunk * 4;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const int rr = rb_row + 4 * k;
+                            const uint4 x = lds128(stage_s + rr * 128 + ((rb_chunk ^ (rr & 7)) << 4));
+                            if (rbase + rr < P.M && ccol < P.N) *reinterpret_cast<uint4*>(P.C + (size_t)(rbase + rr) * P.ldc + ccol) = x;
+                        }
+                        __syncwarp();
                     }
-                    if (P.C) {
-                        float* cp = P.C + (size_t)grow * P.ldc + col;
+                }
+                if (P.c16_kind) {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            if (q < ngrp) {
-                                if (P.accumulate) {
-                                    float cv[8];
-                                    load8<float>(cp + q * 8, cv);
-#pragma unroll
-                                    for (int i = 0; i < 8; ++i) v[q * 8 + i] += cv[i];
-                                }
-                                const float o[8] = {v[q * 8], v[q * 8 + 1], v[q * 8 + 2], v[q * 8 + 3], v[q * 8 + 4], v[q * 8 + 5], v[q * 8 + 6], v[q * 8 + 7]};
-                                store8<float>(cp + q * 8, o);
-                            }
+                    for (int q = 0; q < 8; ++q) {
+                        uint4 x;
+                        if (bf) {
+                            x = make_uint4(pack_bf16(v[q * 8], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]), pack_bf16(v[q * 8 + 4], v[q * 8 + 5]),
+                                           pack_bf16(v[q * 8 + 6], v[q * 8 + 7]));
+                        } else {
+                            x = make_uint4(pack_f16(v[q * 8], v[q * 8 + 1]), pack_f16(v[q * 8 + 2], v[q * 8 + 3]), pack_f16(v[q * 8 + 4], v[q * 8 + 5]),
+                                           pack_f16(v[q * 8 + 6], v[q * 8 + 7]));
+                        }
+                        sts128(stage_s + lane * 128 + ((q ^ (lane & 7)) << 4), x);
                     }
-                    if (P.c16_kind) {
+                    __syncwarp();
+                    const int ccol = col + rb_chunk * 8;
+                    uint16_t* c16 = static_cast<uint16_t*>(P.C16);
 #pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            if (q < ngrp) {
-                                const float o[8] = {v[q * 8], v[q * 8 + 1], v[q * 8 + 2], v[q * 8 + 3], v[q * 8 + 4], v[q * 8 + 5], v[q * 8 + 6], v[q * 8 + 7]};
-                                const size_t off = (size_t)grow * P.ldc16 + col + q * 8;
-                                if (bf) store8<__nv_bfloat16>(static_cast<__nv_bfloat16*>(P.C16) + off, o);
-                                else store8<__half>(static_cast<__half*>(P.C16) + off, o);
-                            }
+                    for (int k = 0; k < 8; ++k) {
+                        const int rr = rb_row + 4 * k;
+                        const uint4 x = lds128(stage_s + rr * 128 + ((rb_chunk ^ (rr & 7)) << 4));
+                        if (rbase + rr < P.M && ccol < P.N) *reinterpret_cast<uint4*>(c16 + (size_t)(rbase + rr) * P.ldc16 + ccol) = x;
                     }
+                    __syncwarp();
                 }
             }
             fence_before_thread_sync();
             mbar_arrive(&acc_empty[b]);
+            if (it == 0 && warp == kGStages + 1 && lane == 0) GPROF(6);
         }
     }
     if (!ok && lane == 0 && g.error_flag) atomicExch(g.error_flag, 1);
     fence_before_thread_sync();
     __syncthreads();
     if (warp == kGStages) tmem_dealloc(tmem, 512);
+    if (threadIdx.x == 0) GPROF(7);
 }
 
 int* tc_error_flag();   // loss_tc.cu
@@ -278,7 +341,7 @@ int launch_gemm_tc(const TcGemmProblem* probs, int count, int dtype16, cudaStrea
         tiles += ((q.M + GM - 1) / GM) * d.tiles_n;
     }
     g.total_tiles = tiles;
-    const size_t smem = 1024 + (size_t)kGStages * kGStageBytes + 256;
+    const size_t smem = 1024 + (size_t)kGStages * kGStageBytes + 256 + kGEpiWarps * 4096;
     DCLIP_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_gemm_tc<<<min(tiles, sm_count()), kGThreads, smem, st>>>(g);
     DCLIP_LAUNCH_OK("k_gemm_tc");
@@ -286,3 +349,10 @@ int launch_gemm_tc(const TcGemmProblem* probs, int count, int dtype16, cudaStrea
 }
 
 }  // namespace dclip
+
+#ifdef DCLIP_GEMM_PROF
+extern "C" int dclip_debug_gemm_prof(long long* out16) {
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    return cudaMemcpyFromSymbol(out16, dclip::g_gemm_prof, 16 * sizeof(long long)) == cudaSuccess ? 0 : -1;
+}
+#endif
