@@ -175,6 +175,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    # stdout carries exactly ONE JSON line: libraries that print to file descriptor 1 (NCCL's version banner) go to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     import torch.distributed as dist
@@ -344,7 +348,8 @@ def main():
             line["parity_check"] = parity["status"]
             line["parity"] = parity
         line.update(extra)
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         # tearing NCCL down while captured graphs still reference its streams can block: drop the graph,
         # drain the device, leave through a barrier and exit without the (optional) communicator destroy.
