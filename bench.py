@@ -62,7 +62,8 @@ def shared_config(B, d, world):
     """The `config` object: identical in the GPU arm and in the reference arm of the same invocation."""
     return {"workload": f"distill-loss fwd+bwd, global batch {B}, d={d}, tau={TEMPERATURE} (BASELINE configs[3])",
             "global_batch": B, "dim": d, "temperature": TEMPERATURE, "rows_per_gpu": B // max(world, 1),
-            "l2_flush": "256 MiB write between timed steps (GPU arm); none needed on the host arm"}
+            "l2_flush": "between timed steps: 256 MiB write, then a 256 MiB read of another buffer, so L2 is cold AND clean (no dirty "
+                        "flush lines to write back inside the timed step) - GPU arm; none needed on the host arm"}
 
 
 def load_peaks():
@@ -203,6 +204,7 @@ def main():
     host = [t[rank * m:(rank + 1) * m].contiguous().pin_memory() for t in full_cpu]
     resident = [t.to(dev) for t in host]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
+    flush_rd = torch.zeros(32 * 1024 * 1024, dtype=torch.int64, device=dev)   # 256 MiB, only ever read
     launches_per_step = lib.dclip_distill_loss_launch_count(m, B, d, _lib.path_code(path), 1 if world > 1 else 0)
 
     def step_fn(s_img, s_txt, t_img, t_txt):
@@ -279,7 +281,8 @@ def main():
         barrier()
         total_ms = 0.0
         for _ in range(steps):
-            flush.zero_()                                    # L2 flush between timed iterations (untimed)
+            flush.zero_()                                    # L2 flush between timed iterations (untimed) ...
+            flush_rd.sum()                                   # ... then fill L2 with clean lines of a read-only buffer
             barrier()
             if gate is not None:
                 gate.push([], -1, 3, wait_after=True)        # device-side start gate (untimed)
@@ -608,6 +611,7 @@ def teacher_step_bench(dev, with_cpu):
     peaks = load_peaks()
     out = {}
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    flush_rd = torch.zeros(32 * 1024 * 1024, dtype=torch.int64, device=dev)
     for name, (B, T, R, d, dtype) in (("cfg0", (32, 77, 8, 512, torch.float32)), ("cfg2", (32, 77, 36, 768, torch.bfloat16))):
         params = om.perturbed_cross_attention_params(d, 8, 42)
         text, image = synthetic.xattn_inputs(B, T, R, d, 42, ragged=True)
@@ -630,6 +634,7 @@ def teacher_step_bench(dev, with_cpu):
             reps, tot = 20, 0.0
             for _ in range(reps):
                 flush.zero_()
+                flush_rd.sum()
                 torch.cuda.synchronize()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()

@@ -70,6 +70,7 @@ SIGNATURES = {
     "dclip_pair_scores": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp]),
     "dclip_rank_counts_workspace_bytes": (_sz, [_i64, _i64, _i64, _i32]),
     "dclip_rank_counts": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _sz, _i32, _vp]),
+    "dclip_rank_counts_multi": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _i32, _i64, _vp, _vp]),
     "dclip_matrix_ranks": (_i32, [_vp, _i32, _i64, _i64, _vp, _vp, _i64, _i32, _vp, _vp]),
     "dclip_recall_metrics": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _sz, _vp]),
     "dclip_topk_ip_workspace_bytes": (_sz, [_i64, _i64, _i64, _i64, _i32, _i32, _i32]),

@@ -176,6 +176,69 @@ __global__ void __launch_bounds__(RThreads) k_rank_counts(const float* __restric
     }
 }
 
+// Several targets per query row (image -> text direction of the Recall@K evaluation, flickr30k_eval.py:48-64: the column of
+// image i is ranked once for each of its ground-truth captions).  The pairs of one query are contiguous (CSR tptr); the
+// score tile of a query row is computed ONCE and compared against all of its targets' scores - not once per pair as the
+// gather-by-qidx form does (5x fewer FLOPs on the Flickr shape).  Up to kMaxTargets targets per row (host-checked).
+constexpr int kMaxTargets = 8;
+__global__ void __launch_bounds__(RThreads) k_rank_counts_multi(const float* __restrict__ q, const float* __restrict__ g, int64_t nq,
+                                                                int64_t ng, int64_t d, const int64_t* __restrict__ tptr,
+                                                                const float* __restrict__ ts, const int64_t* __restrict__ tgt,
+                                                                int64_t goff, int tiles_per_split, int32_t* __restrict__ rank) {
+    __shared__ __align__(16) float As[RK][RLD];
+    __shared__ __align__(16) float Bs[RK][RLD];
+    __shared__ float ts_s[RT][kMaxTargets];
+    __shared__ long long tg_s[RT][kMaxTargets];
+    __shared__ int cnt_s[RT][kMaxTargets];
+    __shared__ int nt_s[RT];
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    const int64_t row0 = (int64_t)blockIdx.x * RT;
+    const unsigned half_mask = (threadIdx.x & 16) ? 0xffff0000u : 0x0000ffffu;     // the 16 lanes that share my rows
+    for (int e = threadIdx.x; e < RT * kMaxTargets; e += RThreads) {
+        const int r = e / kMaxTargets, k = e - r * kMaxTargets;
+        const int64_t row = row0 + r;
+        int n = 0;
+        int64_t p0 = 0;
+        if (row < nq) { p0 = tptr[row]; n = (int)(tptr[row + 1] - p0); }
+        if (k == 0) nt_s[r] = n;
+        ts_s[r][k] = k < n ? ts[p0 + k] : 0.f;
+        tg_s[r][k] = k < n ? tgt[p0 + k] : 0;
+        cnt_s[r][k] = 0;
+    }
+    __syncthreads();
+    const int64_t ntiles = (ng + RT - 1) / RT;
+    const int64_t t0 = (int64_t)blockIdx.y * tiles_per_split, t1 = min(ntiles, t0 + tiles_per_split);
+    ScoreTile<float, float> tile;
+    for (int64_t jt = t0; jt < t1; ++jt) {
+        const int64_t col0 = jt * RT;
+        tile.compute(As, Bs, q, nullptr, row0, nq, g, col0, ng, d);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = ty * 4 + i;
+            const int n = nt_s[r];                          // same for the 16 threads (half warp) that share the row
+            for (int k = 0; k < n; ++k) {
+                const float st = ts_s[r][k];
+                const long long tg = tg_s[r][k];
+                int c = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int64_t col = col0 + tx * 4 + j;
+                    const float sv = tile.acc[i][j];
+                    c += (col < ng && (sv > st || (sv == st && goff + col < tg))) ? 1 : 0;
+                }
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) c += __shfl_xor_sync(half_mask, c, o, 16);   // the other half-warp may run a different target count
+                if (tx == 0 && c) cnt_s[r][k] += c;         // one writer per (row, target)
+            }
+        }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < RT * kMaxTargets; e += RThreads) {
+        const int r = e / kMaxTargets, k = e - r * kMaxTargets;
+        if (k < nt_s[r] && cnt_s[r][k]) atomicAdd(&rank[tptr[row0 + r] + k], cnt_s[r][k]);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // warp-resident sorted list (lane l holds the l-th best), order (-score, +index)
 // ---------------------------------------------------------------------------------------------
@@ -414,6 +477,25 @@ int dclip_rank_counts(const float* q, const float* g, int64_t ng, int64_t d, con
     dim3 grid((unsigned)row_tiles, (unsigned)ceil_div(col_tiles, tps));
     k_rank_counts<<<grid, RThreads, 0, st>>>(q, g, ng, d, qidx, target_score, target_index, npairs, g_index_offset, tps, rank);
     DCLIP_LAUNCH_OK("k_rank_counts");
+    return DCLIP_OK;
+}
+
+int dclip_rank_counts_multi(const float* q, const float* g, int64_t nq, int64_t ng, int64_t d, const int64_t* target_ptr,
+                            const float* target_score, const int64_t* target_index, int64_t npairs, int max_targets,
+                            int64_t g_index_offset, int32_t* rank, void* stream) {
+    DCLIP_REQUIRE(q && g && target_ptr && target_score && target_index && rank, "rank_counts_multi: null pointer");
+    DCLIP_REQUIRE(d > 0 && d % 4 == 0 && nq >= 0 && ng >= 0 && npairs >= 0, "rank_counts_multi: bad shape (d must be a multiple of 4)");
+    if (max_targets > kMaxTargets) return fail(DCLIP_ERR_UNSUPPORTED, "rank_counts_multi: at most %d targets per query row (got %d)", kMaxTargets, max_targets);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (npairs == 0) return DCLIP_OK;
+    DCLIP_CUDA_OK(cudaMemsetAsync(rank, 0, sizeof(int32_t) * npairs, st));
+    if (ng == 0 || nq == 0) return DCLIP_OK;
+    const int64_t row_tiles = ceil_div(nq, RT), col_tiles = ceil_div(ng, RT);
+    const int nsplit = split_for(row_tiles, col_tiles);
+    const int tps = (int)ceil_div(col_tiles, nsplit);
+    dim3 grid((unsigned)row_tiles, (unsigned)ceil_div(col_tiles, tps));
+    k_rank_counts_multi<<<grid, RThreads, 0, st>>>(q, g, nq, ng, d, target_ptr, target_score, target_index, g_index_offset, tps, rank);
+    DCLIP_LAUNCH_OK("k_rank_counts_multi");
     return DCLIP_OK;
 }
 

@@ -214,6 +214,14 @@ int dclip_rank_counts(const float* q, const float* g, int64_t ng, int64_t d, con
                       int64_t g_index_offset, int32_t* rank, void* workspace, size_t workspace_bytes, int path,
                       void* stream);
 
+/* rank_counts for query rows with SEVERAL targets each (the image -> text direction of calculate_retrieval_metrics,
+ * eval_scripts/flickr30k_eval.py:48-64): the pairs of query row r are target_ptr[r] .. target_ptr[r + 1] (CSR over
+ * target_score / target_index / rank).  One score tile per unique query row, compared against all of its targets:
+ * same contract, same result as dclip_rank_counts with a gather index, a fraction of the FLOPs.
+ * max_targets (host-known maximum of targets per row) must be <= 8. */
+int dclip_rank_counts_multi(const float* q, const float* g, int64_t nq, int64_t ng, int64_t d, const int64_t* target_ptr,
+                            const float* target_score, const int64_t* target_index, int64_t npairs, int max_targets,
+                            int64_t g_index_offset, int32_t* rank, void* stream);
 /* Compatibility form of calculate_retrieval_metrics (flickr30k_eval.py:16), which receives a
  * MATERIALISED similarity matrix sim[n_rows, n_cols] (float32 if is_f64 == 0 else float64, the
  * reference stores fp32 products in a float64 buffer, :255).  Pair p ranks element

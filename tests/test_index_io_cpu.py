@@ -37,3 +37,25 @@ def test_empty_and_errors(tmp_path):
     trunc.write_bytes(p.read_bytes()[:20])
     with pytest.raises(ValueError, match="truncated"):
         index_io.read_index_arrays(trunc)
+
+
+def test_embeddings_json_round_trip(tmp_path):
+    """The reference's schema (compute_faiss.py:83-91): nested [1, d] embedding lists, optional positions, key order = row order."""
+    import json
+    rng = np.random.default_rng(1)
+    embs = rng.standard_normal((5, 16)).astype(np.float32)
+    pos = rng.uniform(0, 1, size=(5, 4)).astype(np.float32)
+    ids = [f"img{i // 2}.jpg_patch{i % 2}" for i in range(5)]
+    p = tmp_path / "embeddings.json"
+    index_io.write_embeddings_json(p, ids, embs, pos)
+    raw = json.load(open(p))
+    assert list(raw.keys()) == ids
+    first = raw[ids[0]]
+    assert set(first) == {"embedding", "position"} and len(first["embedding"]) == 1 and len(first["embedding"][0]) == 16
+    ids2, embs2, pos2 = index_io.read_embeddings_json(p)
+    assert ids2 == ids and np.array_equal(embs2, embs) and np.allclose(pos2, pos)
+    # the older bare-list form of an entry (compute_faiss.py:84) is read too
+    raw[ids[1]] = raw[ids[1]]["embedding"]
+    json.dump(raw, open(p, "w"))
+    ids3, embs3, pos3 = index_io.read_embeddings_json(p)
+    assert np.array_equal(embs3, embs) and np.isnan(pos3[1]).all() and not np.isnan(pos3[0]).any()

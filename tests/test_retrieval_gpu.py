@@ -80,6 +80,22 @@ def test_ranks_bit_exact(built_library, n_img, cpi, d):
     assert [best[i] for i in range(n_img)] == want_i2t
 
 
+def test_i2t_many_captions_falls_back_and_matches(built_library):
+    """Images with more than 8 captions take the per-pair kernel, fewer take the one-tile-per-image kernel: same ranks."""
+    from dclip_b200 import retrieval as R
+    for cpi in (9, 8, 2):
+        cap, img, image_ids, cap_ids = synthetic.retrieval_inputs(23, cpi, 64, 1.0, seed=cpi)
+        keep = [c for c in range(len(cap_ids)) if not (cap_ids[c] == 3 or (cap_ids[c] == 7 and c % 2))]     # an image without captions, a ragged one
+        cap, cap_ids = cap[keep], [cap_ids[c] for c in keep]
+        t2i, i2t_pairs, pair_img = R.retrieval_ranks(cap, img, image_ids, cap_ids)
+        want_t2i, want_i2t = orc.ranks_from_embeddings_c(cap, img, image_ids, cap_ids)
+        assert t2i.cpu().tolist() == want_t2i
+        best = {}
+        for o, r in zip(pair_img.cpu().tolist(), i2t_pairs.cpu().tolist()):
+            best[o] = min(best.get(o, 1 << 30), r)
+        assert [best[i] for i in sorted(best)] == want_i2t
+
+
 def test_ranks_with_exact_ties(built_library):
     from dclip_b200 import retrieval as R
     rng = np.random.default_rng(2)
