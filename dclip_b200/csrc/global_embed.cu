@@ -4,16 +4,15 @@
 //   whole-tensor NaN / Inf guard (-> zeros)                    :649-651
 // and the autograd backward of the same.
 //
-// Forward: one 2-CTA cluster per batch element (CTA 0 = text side, CTA 1 = image side).  A CTA stages its [L, d] block
-// in shared memory once (16-byte loads; straight from L2 when the block does not fit) and makes three passes over it with
-// one WARP PER ROW and lane-owned 8-element column chunks, so every pass is coalesced and the column reductions are
-// register accumulators merged across the 8 warps through shared memory:
-//   pass 1  column sums -> mean; row norms          pass 2  cos(x_l, mean) -> softmax over l (temperature 2.0)
+// Forward: one 8-CTA cluster per batch element: 4 CTAs share the rows of the text side, 4 those of the image side.  A CTA
+// stages its rows in shared memory once (16-byte loads) and makes three passes over them with one WARP PER ROW and
+// lane-owned 8-element column chunks, so every pass is coalesced and the column reductions are register accumulators
+// merged across the 8 warps through shared memory, then across the CTAs through distributed shared memory:
+//   pass 1  column sums -> mean; row norms          pass 2  cos(x_l, mean) -> softmax over ALL rows of the side
 //   pass 3  weighted column sum -> the side's global embedding
-// The image CTA hands its vector to the text CTA through distributed shared memory; the text CTA writes
-// 0.5 a + 0.5 b and the per-element non-finite flag.  The last cluster to finish zeroes the whole [B, d] output if any
-// flag is set (device-side: the reference's `.any()` is a host sync).
-// Backward: same cluster shape, no exchange: each side turns 0.5 * d_global (0 when the guard fired) into d_attended.
+// Rank 0 adds the eight weighted partials (0.5 text + 0.5 image), writes the element and its non-finite flag; the last
+// batch element to finish zeroes the whole [B, d] output if any flag is set (device-side: the reference's `.any()` is a
+// host sync).  Backward: one 4-CTA cluster per (batch element, side), two exchanges (mean + sum w dw; dmean + S2).
 #include <cooperative_groups.h>
 
 #include "common.cuh"
@@ -83,35 +82,60 @@ __device__ __forceinline__ float ge_block_sum(float v, float* scratch) {      //
     return t;
 }
 
-// shared memory (floats): mean[d] | vecb[d] | red[8][d] | rowv[4][L] | scratch[32] | stage
+// Row split: kParts CTAs share the rows of one (batch element, side); they meet three times through distributed shared
+// memory (column partials for the mean, the cosines for the softmax over all rows, the weighted column partials), every
+// cross-CTA sum taken in rank order by every CTA that needs it (bit-reproducible, identical in all of them).
+constexpr int kParts = 4;
+
+struct GePartition { int l0, l1; };
+__device__ __forceinline__ GePartition ge_rows(int L, int part) {
+    const int lc = (L + kParts - 1) / kParts;
+    return GePartition{min(L, part * lc), min(L, (part + 1) * lc)};
+}
+
+// dst[c] = scale * sum_p colpart_p[c] over the kParts CTAs of my side (cluster ranks base .. base + kParts - 1)
+__device__ __forceinline__ void ge_gather(cg::cluster_group& cluster, float* colpart, int base, float* dst, int d, float scale) {
+    for (int c = threadIdx.x; c < d; c += ge::kThreads) {
+        float s = 0.f;
+#pragma unroll
+        for (int p = 0; p < kParts; ++p) s += *cluster.map_shared_rank(colpart + c, base + p);
+        dst[c] = s * scale;
+    }
+    __syncthreads();
+}
+
+// shared memory (floats): mean[d] | cp1[d] | cp2[d] | red[8][d] | nx[Lc] cs_all[Lmax] | scratch[32] | stage (my rows)
 template <typename T, int NC>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ge::kThreads) k_global_fwd(const __grid_constant__ GlobalArgs a) {
+__global__ void __cluster_dims__(2 * kParts, 1, 1) __launch_bounds__(ge::kThreads) k_global_fwd(const __grid_constant__ GlobalArgs a) {
     using namespace ge;
     extern __shared__ __align__(16) float sm[];
     cg::cluster_group cluster = cg::this_cluster();
-    const int side = (int)cluster.block_rank();
-    const int b = blockIdx.x >> 1;
+    const int rank = (int)cluster.block_rank();
+    const int side = rank / kParts, part = rank - side * kParts;
+    const int b = blockIdx.x / (2 * kParts);
     const GlobalSide& S = a.s[side];
     const int L = S.L, d = a.d, nch = d >> 3;
-    const int Lmax = max(a.s[0].L, a.s[1].L);
+    const int Lmax = (max(a.s[0].L, a.s[1].L) + 3) & ~3;          // padded: the staging area behind the row vectors stays 16-byte aligned
+    const GePartition R = ge_rows(L, part);
+    const int nl = R.l1 - R.l0;
     float* mean = sm;
-    float* vecb = mean + d;                  // text CTA: the image side's vector lands here (DSMEM)
-    float* red = vecb + d;
-    float* rowv = red + (size_t)kWarps * d;  // nx[L], cs[L]
-    float* scratch = rowv + 4 * Lmax;
+    float* cp1 = mean + d;                   // my column partial (exchange 1), later the gathered side vectors on rank 0
+    float* cp2 = cp1 + d;                    // my weighted column partial (exchange 3)
+    float* red = cp2 + d;
+    float* nx = red + (size_t)kWarps * d;    // [rows of this CTA]
+    float* cs_all = nx + Lmax;               // [L] cosines / temperature of the whole side (exchange 2)
+    float* scratch = cs_all + Lmax;
     void* stage = scratch + 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const T* xb = ge_stage<T>(static_cast<const T*>(S.x) + (size_t)b * L * d, L, d, stage, a.staged[side] != 0);
-    float* nx = rowv;
-    float* cs = rowv + Lmax;
+    const T* xb = ge_stage<T>(static_cast<const T*>(S.x) + ((size_t)b * L + R.l0) * d, nl, d, stage, a.staged[side] != 0);
 
-    // pass 1: column sums and row norms
+    // pass 1: column sums and row norms of my rows
     float acc[NC][8];
 #pragma unroll
     for (int k = 0; k < NC; ++k)
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[k][i] = 0.f;
-    for (int l = warp; l < L; l += kWarps) {
+    for (int l = warp; l < nl; l += kWarps) {
         float q = 0.f;
 #pragma unroll
         for (int k = 0; k < NC; ++k) {
@@ -126,12 +150,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ge::kThreads) k_glob
         q = warp_sum(q);
         if (lane == 0) nx[l] = sqrtf(q);
     }
-    ge_merge<NC>(acc, red, mean, d, 1.0f / L);
-    float part = 0.f;
-    for (int c = threadIdx.x; c < d; c += kThreads) part = fmaf(mean[c], mean[c], part);
-    const float nm = fmaxf(sqrtf(ge_block_sum(part, scratch)), kCosEps);
-    // pass 2: cosine to the mean
-    for (int l = warp; l < L; l += kWarps) {
+    ge_merge<NC>(acc, red, cp1, d, 1.0f);
+    cluster.sync();                                                   // (1) column partials of every CTA are in place
+    ge_gather(cluster, cp1, side * kParts, mean, d, 1.0f / L);
+    float partn = 0.f;
+    for (int c = threadIdx.x; c < d; c += kThreads) partn = fmaf(mean[c], mean[c], partn);
+    const float nm = fmaxf(sqrtf(ge_block_sum(partn, scratch)), kCosEps);
+    // pass 2: cosine of my rows to the mean -> every CTA of my side
+    for (int l = warp; l < nl; l += kWarps) {
         float dot = 0.f;
 #pragma unroll
         for (int k = 0; k < NC; ++k) {
@@ -144,31 +170,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ge::kThreads) k_glob
             }
         }
         dot = warp_sum(dot);
-        if (lane == 0) cs[l] = dot / (fmaxf(nx[l], kCosEps) * nm) / a.temperature;
+        if (lane < kParts) *cluster.map_shared_rank(cs_all + R.l0 + l, side * kParts + lane) = dot / (fmaxf(nx[l], kCosEps) * nm) / a.temperature;
     }
-    __syncthreads();
-    // softmax over the L rows (warp 0)
-    if (warp == 0) {
-        float mx = -INFINITY;
-        for (int l = lane; l < L; l += 32) mx = fmaxf(mx, cs[l]);
-        mx = warp_max(mx);
-        float den = 0.f;
-        for (int l = lane; l < L; l += 32) den += expf(cs[l] - mx);
-        den = warp_sum(den);
-        for (int l = lane; l < L; l += 32) {
-            const float w = expf(cs[l] - mx) / den;
-            cs[l] = w;
-            if (S.w) S.w[(size_t)b * L + l] = w;
-        }
-    }
-    __syncthreads();
-    // pass 3: weighted column sum
+    cluster.sync();                                                   // (2) all cosines of the side have landed here
+    // softmax over the L rows of the side (every CTA, redundantly: a few hundred flops)
+    float mx = -INFINITY;
+    for (int l = lane; l < L; l += 32) mx = fmaxf(mx, cs_all[l]);
+    mx = warp_max(mx);
+    float den = 0.f;
+    for (int l = lane; l < L; l += 32) den += __expf(cs_all[l] - mx);
+    den = warp_sum(den);
+    // pass 3: weighted column sum of my rows
 #pragma unroll
     for (int k = 0; k < NC; ++k)
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[k][i] = 0.f;
-    for (int l = warp; l < L; l += kWarps) {
-        const float w = cs[l];
+    for (int l = warp; l < nl; l += kWarps) {
+        const float w = __expf(cs_all[R.l0 + l] - mx) / den;
+        if (lane == 0 && S.w) S.w[(size_t)b * L + R.l0 + l] = w;
 #pragma unroll
         for (int k = 0; k < NC; ++k) {
             const int ch = lane + 32 * k;
@@ -180,63 +199,72 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ge::kThreads) k_glob
             }
         }
     }
-    ge_merge<NC>(acc, red, mean, d, 1.0f);           // mean[] now holds this side's global embedding
-    // combine: image side -> text CTA's vecb
-    if (side == 1) {
-        float* remote = cluster.map_shared_rank(vecb, 0);
-        for (int c = threadIdx.x; c < d; c += kThreads) remote[c] = mean[c];
+    ge_merge<NC>(acc, red, cp2, d, 1.0f);
+    cluster.sync();                                                   // (3) weighted partials in place
+    if (rank == 0) {
+        // 0.5 * (text global) + 0.5 * (image global): partials added in rank order
+        bool bad = false;
+        T* out = static_cast<T*>(a.out) + (size_t)b * d;
+        for (int c = threadIdx.x; c < d; c += kThreads) {
+            const int t = (c & 7) * nch + (c >> 3);              // chunk-transposed position of column c
+            float st = 0.f, si = 0.f;
+#pragma unroll
+            for (int p = 0; p < kParts; ++p) { st += *cluster.map_shared_rank(cp2 + t, p); si += *cluster.map_shared_rank(cp2 + t, kParts + p); }
+            const float v = 0.5f * st + 0.5f * si;
+            bad |= !isfinite(v);
+            out[c] = from_f32<T>(v);
+        }
+        const int any_bad = __syncthreads_or(bad);
+        __shared__ int last;
+        if (threadIdx.x == 0) {
+            a.flags[b] = any_bad;
+            __threadfence();
+            last = atomicAdd(&a.flags[a.B], 1) == a.B - 1;
+        }
+        __syncthreads();
+        if (last) {
+            // the last batch element to finish: every output and flag is visible; zero everything if any flag is set
+            __threadfence();
+            int any = 0;
+            for (int i = threadIdx.x; i < a.B; i += kThreads) any |= __ldcg(a.flags + i);
+            any = __syncthreads_or(any);
+            if (any) {
+                T* all = static_cast<T*>(a.out);
+                for (size_t i = threadIdx.x; i < (size_t)a.B * d; i += kThreads) all[i] = from_f32<T>(0.f);
+            }
+            if (threadIdx.x == 0) a.flags[a.B] = 0;          // counter ready for the next launch
+        }
     }
-    cluster.sync();
-    if (side == 1) return;
-    bool bad = false;
-    T* out = static_cast<T*>(a.out) + (size_t)b * d;
-    for (int c = threadIdx.x; c < d; c += kThreads) {
-        const int t = (c & 7) * nch + (c >> 3);              // chunk-transposed position of column c
-        const float v = 0.5f * mean[t] + 0.5f * vecb[t];
-        bad |= !isfinite(v);
-        out[c] = from_f32<T>(v);
-    }
-    const int any_bad = __syncthreads_or(bad);
-    __shared__ int last;
-    if (threadIdx.x == 0) {
-        a.flags[b] = any_bad;
-        __threadfence();
-        last = atomicAdd(&a.flags[a.B], 1) == a.B - 1;
-    }
-    __syncthreads();
-    if (!last) return;
-    // the last text CTA: every element's output and flag is visible; zero everything if any flag is set
-    __threadfence();
-    int any = 0;
-    for (int i = threadIdx.x; i < a.B; i += kThreads) any |= __ldcg(a.flags + i);
-    any = __syncthreads_or(any);
-    if (any) {
-        T* all = static_cast<T*>(a.out);
-        for (size_t i = threadIdx.x; i < (size_t)a.B * d; i += kThreads) all[i] = from_f32<T>(0.f);
-    }
-    if (threadIdx.x == 0) a.flags[a.B] = 0;          // counter ready for the next launch
+    cluster.sync();                                                   // (4) nobody leaves while rank 0 reads its partials
 }
 
-// backward of one side: x [L, d], w [L] (saved softmax weights), dg = 0.5 * d_global (0 if guarded)
+// backward of one side, rows split over kParts CTAs: x [L, d], w [L] (saved softmax weights), dg = 0.5 * d_global (0 if guarded)
 //   dc_l = w_l / T (dw_l - sum w dw), dw_l = x_l . dg;  e_l = dc_l / (nx_l nm);  f_l = dc_l cos_l / nx_l^2 (0 if clamped)
 //   dmean = (sum_l e_l x_l - mean S2) / L,  S2 = sum_l dc_l cos_l / nm^2 (0 if the mean's norm is clamped)
 //   dx_l = w_l dg + e_l mean - f_l x_l + dmean
+// shared memory (floats): mean[d] | dmean[d] | cp1[d + 4] | cp2[d + 4] | red[8][d] | rowv[4][Lc] | scratch[32] | stage
 template <typename T, int NC>
-__global__ void __launch_bounds__(ge::kThreads) k_global_bwd(const __grid_constant__ GlobalArgs a) {
+__global__ void __cluster_dims__(kParts, 1, 1) __launch_bounds__(ge::kThreads) k_global_bwd(const __grid_constant__ GlobalArgs a) {
     using namespace ge;
     extern __shared__ __align__(16) float sm[];
-    const int side = blockIdx.x & 1, b = blockIdx.x >> 1;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int part = (int)cluster.block_rank();
+    const int side = (blockIdx.x / kParts) & 1, b = blockIdx.x / (2 * kParts);
     const GlobalSide& S = a.s[side];
     const int L = S.L, d = a.d, nch = d >> 3;
-    const int Lmax = max(a.s[0].L, a.s[1].L);
+    const int Lmax = (max(a.s[0].L, a.s[1].L) + 3) & ~3;          // padded: the staging area behind the row vectors stays 16-byte aligned
+    const GePartition R = ge_rows(L, part);
+    const int nl = R.l1 - R.l0;
     float* mean = sm;
     float* dmean = mean + d;
-    float* red = dmean + d;
-    float* rowv = red + (size_t)kWarps * d;  // nx[L] (negative = clamped), cosv[L], dcs[L], wl[L]
+    float* cp1 = dmean + d;                  // [d] column partial + [d] = my partial of sum w dw
+    float* cp2 = cp1 + d + 4;                // [d] sum e_l x_l partial + [d] = my partial of S2
+    float* red = cp2 + d + 4;
+    float* rowv = red + (size_t)kWarps * d;  // nx (negative = clamped), cosv, dcs, wl of my rows
     float* scratch = rowv + 4 * Lmax;
     void* stage = scratch + 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const T* xb = ge_stage<T>(static_cast<const T*>(S.x) + (size_t)b * L * d, L, d, stage, a.staged[side] != 0);
+    const T* xb = ge_stage<T>(static_cast<const T*>(S.x) + ((size_t)b * L + R.l0) * d, nl, d, stage, a.staged[side] != 0);
     float* nx = rowv; float* cosv = rowv + Lmax; float* dcs = rowv + 2 * Lmax; float* wl = rowv + 3 * Lmax;
     int guarded = 0;
     for (int i = threadIdx.x; i < a.B; i += kThreads) guarded |= a.flags[i];
@@ -253,14 +281,16 @@ __global__ void __launch_bounds__(ge::kThreads) k_global_bwd(const __grid_consta
             for (int i = 0; i < 8; ++i) dg[k][i] *= gscale;
         }
     }
-    for (int l = threadIdx.x; l < L; l += kThreads) wl[l] = S.w[(size_t)b * L + l];
+    for (int l = threadIdx.x; l < nl; l += kThreads) wl[l] = S.w[(size_t)b * L + R.l0 + l];
+    __syncthreads();
 
+    // pass 1: column sums, row norms, dw_l = x_l . dg
     float acc[NC][8];
 #pragma unroll
     for (int k = 0; k < NC; ++k)
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[k][i] = 0.f;
-    for (int l = warp; l < L; l += kWarps) {
+    for (int l = warp; l < nl; l += kWarps) {
         float q = 0.f, dw = 0.f;
 #pragma unroll
         for (int k = 0; k < NC; ++k) {
@@ -275,13 +305,23 @@ __global__ void __launch_bounds__(ge::kThreads) k_global_bwd(const __grid_consta
         q = warp_sum(q); dw = warp_sum(dw);
         if (lane == 0) { const float r = sqrtf(q); nx[l] = r < kCosEps ? -kCosEps : r; dcs[l] = dw; }
     }
-    ge_merge<NC>(acc, red, mean, d, 1.0f / L);
-    float part = 0.f;
-    for (int c = threadIdx.x; c < d; c += kThreads) part = fmaf(mean[c], mean[c], part);
-    const float nm_raw = sqrtf(ge_block_sum(part, scratch));
+    ge_merge<NC>(acc, red, cp1, d, 1.0f);
+    float sp = 0.f;
+    for (int l = threadIdx.x; l < nl; l += kThreads) sp = fmaf(wl[l], dcs[l], sp);
+    sp = ge_block_sum(sp, scratch);
+    if (threadIdx.x == 0) cp1[d] = sp;
+    cluster.sync();                                                   // (1)
+    ge_gather(cluster, cp1, 0, mean, d, 1.0f / L);
+    float sdot = 0.f;
+#pragma unroll
+    for (int p = 0; p < kParts; ++p) sdot += *cluster.map_shared_rank(cp1 + d, p);
+    float partn = 0.f;
+    for (int c = threadIdx.x; c < d; c += kThreads) partn = fmaf(mean[c], mean[c], partn);
+    const float nm_raw = sqrtf(ge_block_sum(partn, scratch));
     const float nm = fmaxf(nm_raw, kCosEps);
     const bool m_clamped = nm_raw < kCosEps;
-    for (int l = warp; l < L; l += kWarps) {
+    // pass 2: cosines of my rows
+    for (int l = warp; l < nl; l += kWarps) {
         float dot = 0.f;
 #pragma unroll
         for (int k = 0; k < NC; ++k) {
@@ -297,12 +337,9 @@ __global__ void __launch_bounds__(ge::kThreads) k_global_bwd(const __grid_consta
         if (lane == 0) cosv[l] = dot / (fabsf(nx[l]) * nm);
     }
     __syncthreads();
-    float sp = 0.f;
-    for (int l = threadIdx.x; l < L; l += kThreads) sp = fmaf(wl[l], dcs[l], sp);
-    const float sdot = ge_block_sum(sp, scratch);
     float s2p = 0.f;
-    // per-row coefficients; el -> nx[], fl -> cosv[] (reuse)
-    for (int l = threadIdx.x; l < L; l += kThreads) {
+    // per-row coefficients; e_l -> nx[], f_l -> cosv[] (reuse)
+    for (int l = threadIdx.x; l < nl; l += kThreads) {
         const float dc = wl[l] / a.temperature * (dcs[l] - sdot);
         const float n = fabsf(nx[l]);
         const bool row_ok = nx[l] > 0.f;
@@ -311,12 +348,13 @@ __global__ void __launch_bounds__(ge::kThreads) k_global_bwd(const __grid_consta
         nx[l] = dc / (n * nm);
         cosv[l] = row_ok ? dc * cl / (n * n) : 0.f;
     }
-    const float S2 = ge_block_sum(s2p, scratch);
+    s2p = ge_block_sum(s2p, scratch);
+    // pass 3: sum_l e_l x_l over my rows
 #pragma unroll
     for (int k = 0; k < NC; ++k)
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[k][i] = 0.f;
-    for (int l = warp; l < L; l += kWarps) {
+    for (int l = warp; l < nl; l += kWarps) {
         const float e = nx[l];
 #pragma unroll
         for (int k = 0; k < NC; ++k) {
@@ -329,11 +367,17 @@ __global__ void __launch_bounds__(ge::kThreads) k_global_bwd(const __grid_consta
             }
         }
     }
-    ge_merge<NC>(acc, red, dmean, d, 1.0f);
+    ge_merge<NC>(acc, red, cp2, d, 1.0f);
+    if (threadIdx.x == 0) cp2[d] = s2p;
+    cluster.sync();                                                   // (2)
+    ge_gather(cluster, cp2, 0, dmean, d, 1.0f);
+    float S2 = 0.f;
+#pragma unroll
+    for (int p = 0; p < kParts; ++p) S2 += *cluster.map_shared_rank(cp2 + d, p);
     for (int c = threadIdx.x; c < d; c += kThreads) dmean[c] = (dmean[c] - mean[c] * S2) / L;
     __syncthreads();
-    T* dxb = static_cast<T*>(S.dx) + (size_t)b * L * d;
-    for (int l = warp; l < L; l += kWarps) {
+    T* dxb = static_cast<T*>(S.dx) + ((size_t)b * L + R.l0) * d;
+    for (int l = warp; l < nl; l += kWarps) {
         const float w = wl[l], e = nx[l], f = cosv[l];
 #pragma unroll
         for (int k = 0; k < NC; ++k) {
@@ -347,18 +391,19 @@ __global__ void __launch_bounds__(ge::kThreads) k_global_bwd(const __grid_consta
             }
         }
     }
+    cluster.sync();                                                   // (3) peers may still be reading my partials
 }
 
-static size_t ge_smem_base(int d, int Lmax) { return ((size_t)2 * d + (size_t)ge::kWarps * d + 4 * Lmax + 32) * sizeof(float) + 16; }
+static size_t ge_smem_base(int d, int Lmax) { return ((size_t)4 * d + 8 + (size_t)ge::kWarps * d + 4 * Lmax + 32) * sizeof(float) + 16; }
 
 template <typename T, int NC>
 static int launch_ge(const GlobalArgs& a, size_t smem, bool bwd, cudaStream_t st) {
     if (bwd) {
         DCLIP_CUDA_OK(cudaFuncSetAttribute(k_global_bwd<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_global_bwd<T, NC><<<2 * a.B, ge::kThreads, smem, st>>>(a);
+        k_global_bwd<T, NC><<<2 * kParts * a.B, ge::kThreads, smem, st>>>(a);
     } else {
         DCLIP_CUDA_OK(cudaFuncSetAttribute(k_global_fwd<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_global_fwd<T, NC><<<2 * a.B, ge::kThreads, smem, st>>>(a);
+        k_global_fwd<T, NC><<<2 * kParts * a.B, ge::kThreads, smem, st>>>(a);
     }
     DCLIP_LAUNCH_OK("k_global_embedding");
     return DCLIP_OK;
@@ -374,11 +419,11 @@ static int launch_ge_nc(const GlobalArgs& a, size_t smem, bool bwd, cudaStream_t
 }
 
 static int global_embedding(GlobalArgs a, int dtype, bool bwd, cudaStream_t st) {
-    const int Lmax = max(a.s[0].L, a.s[1].L);
+    const int Lmax = (max(a.s[0].L, a.s[1].L) + 3) & ~3;
     const size_t base = ge_smem_base(a.d, Lmax);
     size_t stage = 0;
     for (int s = 0; s < 2; ++s) {
-        const size_t bytes = (size_t)a.s[s].L * a.d * dtype_size(dtype);
+        const size_t bytes = (size_t)ceil_div(a.s[s].L, kParts) * a.d * dtype_size(dtype);       // the rows of one CTA
         a.staged[s] = (bytes % 16 == 0 && aligned16(a.s[s].x) && base + bytes <= 220 * 1024) ? 1 : 0;
         if (a.staged[s]) stage = max(stage, bytes);
     }

@@ -132,13 +132,17 @@ class _DistillLossFn(torch.autograd.Function):
                                                     temperature, w_img, w_txt, w_con, 1.0, need, path)
         if need:
             ctx.save_for_backward(d_img, d_txt)
-        return losses
+        # (total, {total, L_img, L_txt, L_con}): the 0-dim total is an output of its own, so that autograd does not have to
+        # scatter its gradient back into a [4] tensor (a fill + a copy kernel per step); the components are for logging
+        ctx.mark_non_differentiable(losses)
+        return losses[0], losses
 
     @staticmethod
-    def backward(ctx, grad_losses):
+    def backward(ctx, g, _unused):
         d_img, d_txt = ctx.saved_tensors
-        g = grad_losses[0]            # only the total (index 0) carries gradient; components are for logging
-        return (d_img * g.to(d_img.dtype), d_txt * g.to(d_txt.dtype), None, None, None, None, None, None, None)
+        # a 0-dim fp32 factor does not promote a 16-bit tensor: one multiply kernel per input that needs a gradient
+        return (d_img * g if ctx.needs_input_grad[0] else None, d_txt * g if ctx.needs_input_grad[1] else None,
+                None, None, None, None, None, None, None)
 
 
 def _contig(t):
@@ -148,9 +152,9 @@ def _contig(t):
 def compute_contrastive_loss(image_embeddings, text_embeddings, temperature=0.05, path="auto"):
     """Symmetric InfoNCE over the B x B image-text logits (un-normalised [B, d] inputs).
     Returns a 0-dim tensor with an autograd graph, like the reference."""
-    losses = _DistillLossFn.apply(_contig(image_embeddings), _contig(text_embeddings), None, None, temperature,
-                                  0.0, 0.0, 1.0, path)
-    return losses[0]
+    total, _ = _DistillLossFn.apply(_contig(image_embeddings), _contig(text_embeddings), None, None, temperature,
+                                    0.0, 0.0, 1.0, path)
+    return total
 
 
 class _CosineLossFn(torch.autograd.Function):
@@ -208,12 +212,12 @@ class DistillationLoss(nn.Module):
 
     def forward(self, student_image_embeddings, student_text_embeddings, teacher_image_embeddings,
                 teacher_text_embeddings):
-        losses = _DistillLossFn.apply(_contig(student_image_embeddings), _contig(student_text_embeddings),
-                                      _contig(teacher_image_embeddings.detach()),
-                                      _contig(teacher_text_embeddings.detach()), self.temperature,
-                                      self.image_weight, self.text_weight, self.contrastive_weight, self.path)
+        total, losses = _DistillLossFn.apply(_contig(student_image_embeddings), _contig(student_text_embeddings),
+                                             _contig(teacher_image_embeddings.detach()),
+                                             _contig(teacher_text_embeddings.detach()), self.temperature,
+                                             self.image_weight, self.text_weight, self.contrastive_weight, self.path)
         self.last_components = losses.detach()
-        return losses[0]
+        return total
 
 
 # ------------------------------------------------------------------------------------------------
