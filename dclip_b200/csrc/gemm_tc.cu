@@ -39,6 +39,7 @@ struct TcGemmDev {
     int tiles_n, tile_begin;      // tiles of this problem occupy [tile_begin, tile_begin + tiles_m * tiles_n)
     int accumulate;
     void* C16; int c16_kind, ldc16;   // optional 16-bit copy of C (0 none, 1 bf16, 2 fp16); C itself may then be null
+    float alpha;
 };
 struct TcGemmArgs {
     CUtensorMap ta[kTcGemmMax], tb[kTcGemmMax];
@@ -207,6 +208,10 @@ __global__ void __launch_bounds__(kGThreads, 1) k_gemm_tc(const __grid_constant_
                     tmem_ld_32x32b_x32(tmem + lane_addr + b * GN + c0 + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
                     tmem_ld_wait();
                 }
+                if (P.alpha != 1.0f) {
+#pragma unroll
+                    for (int i = 0; i < 64; ++i) v[i] *= P.alpha;
+                }
                 if (P.bias) {
 #pragma unroll
                     for (int q = 0; q < 8; ++q)
@@ -336,6 +341,7 @@ int launch_gemm_tc(const TcGemmProblem* probs, int count, int dtype16, cudaStrea
         d.M = q.M; d.N = q.N; d.K = q.K; d.ldc = q.ldc; d.ldr = q.ldr;
         d.a_mn = q.a_mn; d.b_mn = q.b_mn; d.accumulate = q.accumulate;
         d.C16 = q.C16; d.c16_kind = q.C16 ? (dtype16 == DCLIP_BF16 ? 1 : 2) : 0; d.ldc16 = q.ldc16 > 0 ? q.ldc16 : q.ldc;
+        d.alpha = q.alpha == 0.f ? 1.0f : q.alpha;
         d.tiles_n = (q.N + GN - 1) / GN;
         d.tile_begin = tiles;
         tiles += ((q.M + GM - 1) / GM) * d.tiles_n;

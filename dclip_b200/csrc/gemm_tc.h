@@ -16,6 +16,7 @@ struct TcGemmProblem {
     int a_mn, b_mn, accumulate;
     int ldc16;      // row stride of C16 (0 = ldc); C may be null when only the 16-bit output is wanted
     int bias_kind, res_kind;
+    float alpha;    // C = alpha * A'B' + ... (0 = 1)
 };
 
 int launch_gemm_tc(const TcGemmProblem* probs, int count, int dtype16, cudaStream_t st);

@@ -228,6 +228,7 @@ int dclip_distill_loss_launch_count(int64_t m, int64_t n, int64_t d, int path, i
     if (path == DCLIP_PATH_FP32 && !sharded && small_loss_shape_ok(m, d) && m == n) return 1;      // k_distill_small
     if (path == DCLIP_PATH_FP32) return sharded ? 11 : 6;   // prep, rowlse+combine, sums, grad, tail (x2 sides when sharded)
     // tensor path, single GPU: prep_pair, one-pass forward tiles, finalize, backward tiles (+ partial combines), tail
+    if (!sharded && tc_gmat_ok(m, d)) return 6;   // prep_pair, forward tiles, finalize, G tiles, grouped GEMM (dU, dV), tail
     if (!sharded) return 5 + (tc_nsplit(m, n, d, 2) > 1 ? 2 : 0);
     // fused sharded phases: prep, forward tiles, finalize, global losses, backward tiles (+ combine), tail
     // + the three peer-memory pushes (operands, statistics, step-done) that replace the NCCL all-gathers
@@ -344,6 +345,7 @@ size_t dclip_distill_loss_workspace_bytes(int64_t B, int64_t d, int path) {
         if (tns > 1) total += align_up((size_t)2 * tns * B * d * 4, 256);
         // one-pass forward: row partials [stream_nsplit(1 side)][B] + column partials [ceil(B / 128)][B]
         total += align_up((size_t)stream_nsplit(B, B, 1) * B * 4, 256) + align_up((size_t)ceil_div(B, 128) * B * 4, 256);
+        if (tc_gmat_ok(B, d)) total += align_up(tc_gmat_bytes(B), 256);   // fp16 gradient coefficients G
     }
     return total + 1024;
 }
@@ -396,7 +398,7 @@ static int distill_loss_impl(int phase, const void* s_img, const void* s_txt, co
     float* dv_hat = static_cast<float*>(ws.take((size_t)B * d * 4));
     float* du_part = du_hat;
     float* dv_part = dv_hat;
-    if (tensor && nsb > 1 && (d_s_img || phase != 0)) {
+    if (tensor && nsb > 1 && (d_s_img || phase != 0) && !tc_gmat_ok(B, d)) {
         du_part = static_cast<float*>(ws.take((size_t)2 * nsb * B * d * 4));   // [side][split][B][d], sides contiguous
         dv_part = du_part + (size_t)nsb * B * d;
     }
@@ -405,6 +407,8 @@ static int distill_loss_impl(int phase, const void* s_img, const void* s_txt, co
     const int nib = (int)ceil_div(B, 128);
     float* rowpart = tensor ? static_cast<float*>(ws.take((size_t)ns1 * B * 4)) : nullptr;
     float* colpart = tensor ? static_cast<float*>(ws.take((size_t)nib * B * 4)) : nullptr;
+    const bool gmat = tensor && tc_gmat_ok(B, d);
+    void* g_buf = gmat ? ws.take(tc_gmat_bytes(B)) : nullptr;
     if (!ws.ok()) return fail(DCLIP_ERR_WORKSPACE, "distill_loss: workspace too small (%zu < %zu)", workspace_bytes, ws.used);
     if (stats) { lse_u = stats; lse_v = stats + B; }
 
@@ -463,6 +467,10 @@ static int distill_loss_impl(int phase, const void* s_img, const void* s_txt, co
     if (d_s_img || phase == 1) {
         const bool need_con = w_con != 0.f;
         if (!do_students) {
+        } else if (need_con && gmat) {
+            if (int e = launch_infonce_bwd_gmat(u_hat, v_hat, B, d, lse_u, lse_v, 1.0f / temperature,
+                                                w_con / (2.0f * (float)B) / temperature * (1.0f / 8192.0f), g_buf, du_hat, dv_hat, st))
+                return e;
         } else if (need_con && tensor) {
             TcArgs ga{};
             ga.s[0] = TcSide{lse_u, lse_v, du_part};

@@ -66,6 +66,8 @@ struct TcArgs {
     float* cand_s;        // retrieval mode: [nsplit][m][32] approximate scores (descending)
     int32_t* cand_i;      //                 [nsplit][m][32] gallery rows (-1 = empty)
     float* col_out;       // stream mode 1: partial column sums [ceil(m / 128)][n]
+    void* g_out;          // stream mode 3: fp16 gradient coefficients G * 2^13, [ceil(m / 128) * 128][ldg]
+    int64_t ldg;          //                row stride (elements), a multiple of 256 >= n
     // stream kernel: soft lockstep of concurrently running CTAs (keeps the Y tiles they share inside L2); null = off
     unsigned int* sync_ctr;   // [groups][sync_epochs], zeroed before the launch
     int sync_every, sync_group, sync_epochs;
@@ -84,6 +86,11 @@ int launch_tc_grad_combine2(const float* part, int nsplit, int64_t m, int64_t d,
 int launch_tc_diag(const void* x, const void* y, int64_t m, int64_t n, int64_t d, float inv_tau, int64_t row_offset, float* diag,
                    cudaStream_t st);
 int tc_check_error_flag(cudaStream_t st);
+// single-GPU backward through the materialised fp16 coefficient matrix G (stream mode 3 + two GEMMs); g_buf = tc_gmat_bytes(B)
+bool tc_gmat_ok(int64_t B, int64_t d);
+size_t tc_gmat_bytes(int64_t B);
+int launch_infonce_bwd_gmat(const void* u_hat, const void* v_hat, int64_t B, int64_t d, const float* lse_u, const float* lse_v, float inv_tau,
+                            float out_scale, void* g_buf, float* du_hat, float* dv_hat, cudaStream_t st);
 // streaming 128 x 256 score-tile kernel (stream_tc.cu): mode 0 = row sums, mode 2 = top-32 candidates
 int stream_nsplit(int64_t m, int64_t n, int nsides);
 int launch_stream_tc(int mode, int nsides, const void* const x[2], const void* const y[2], const TcArgs& args, int nsplit,

@@ -31,6 +31,7 @@
 #include "common.cuh"
 
 #include <mutex>
+#include "gemm_tc.h"
 #include "loss_internal.h"
 #include "tcgen05.cuh"
 
@@ -427,6 +428,40 @@ int launch_infonce_bwd_tc(int nsides, const void* const x[2], const void* const 
     k_infonce_bwd_tc<<<grid, kTcThreads, smem, st>>>(tmx[0], tmy[0], tmx[1], tmy[1], a);
     DCLIP_LAUNCH_OK("k_infonce_bwd_tc");
     return DCLIP_OK;
+}
+
+// ---- single-GPU backward through a MATERIALISED coefficient matrix ----------------------------------------------
+// G = softmax_row + softmax_col - 2 I (B x B, fp16, scaled by 2^13) is written once by the streaming kernel (mode 3:
+// the score tiles are recomputed once, 2 B^2 d) and both gradients are plain GEMMs over it,
+//     dU_hat = alpha G V_hat        (A = G K-major,  B = V_hat stored [K, N])
+//     dV_hat = alpha G^T U_hat      (A = G read MN-major, B = U_hat stored [K, N])
+// 6 B^2 d executed instead of the 8 B^2 d of the fused CTA-pair kernel, which recomputes every score tile per side
+// (and stays the kernel of the sharded path, where that recompute is what removes the [B, d] reduce-scatter).
+// G (32 MB at B = 4096) lives in L2 between its writer and its two readers.
+bool tc_gmat_ok(int64_t B, int64_t d) {
+    const char* e = getenv("DCLIP_BWD_GMAT");      // "0": keep the fused CTA-pair kernel (A/B measurements, tests); read per call
+    const bool off = e && e[0] == '0';
+    return !off && B > 128 && d % 8 == 0 && tc_gmat_bytes(B) <= ((size_t)1 << 30);
+}
+size_t tc_gmat_bytes(int64_t B) {
+    return (size_t)(ceil_div(B, 128) * 128) * (size_t)(ceil_div(B, 256) * 256) * 2;
+}
+int launch_infonce_bwd_gmat(const void* u_hat, const void* v_hat, int64_t B, int64_t d, const float* lse_u, const float* lse_v, float inv_tau,
+                            float out_scale, void* g_buf, float* du_hat, float* dv_hat, cudaStream_t st) {
+    const int64_t ldg = ceil_div(B, 256) * 256;
+    TcArgs a{};
+    a.s[0] = TcSide{lse_u, lse_v, nullptr};
+    a.m = B; a.n = B; a.d = d; a.inv_tau = inv_tau; a.row_offset = 0;
+    a.g_out = g_buf; a.ldg = ldg;
+    const void* xs[2] = {u_hat, u_hat};
+    const void* ys[2] = {v_hat, v_hat};
+    if (int e = launch_stream_tc(3, 1, xs, ys, a, stream_nsplit(B, B, 1), st)) return e;
+    TcGemmProblem pr[2] = {};
+    pr[0].A = g_buf; pr[0].lda = (int)ldg; pr[0].a_mn = 0; pr[0].B = v_hat; pr[0].ldb = (int)d; pr[0].b_mn = 1;
+    pr[0].C = du_hat; pr[0].ldc = (int)d; pr[0].M = (int)B; pr[0].N = (int)d; pr[0].K = (int)B; pr[0].alpha = out_scale;
+    pr[1] = pr[0];
+    pr[1].a_mn = 1; pr[1].B = u_hat; pr[1].C = dv_hat;
+    return launch_gemm_tc(pr, 2, DCLIP_F16, st);
 }
 
 int launch_tc_lse_combine(const float* part, int nsplit, int64_t m, float inv_tau, float* lse, cudaStream_t st) {

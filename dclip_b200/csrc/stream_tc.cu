@@ -50,10 +50,15 @@ constexpr int kStagesSingle = 4;          // single-CTA ring: X box + 256-row Y 
 constexpr int kStagesPair = 6;            // CTA-pair ring: X box + MY 128 rows of the Y tile = 32 KB per stage
 constexpr int kXStageBytes = SM_ROWS * 128;   // 16 KB
 constexpr int kYStageBytes = SN_COLS * 128;   // 32 KB
-constexpr int stream_stages(bool pair) { return pair ? kStagesPair : kStagesSingle; }
+// mode 3 gives one ring stage to the epilogue's staging buffers (8 warps x 4 KB)
+constexpr int stream_stages(int mode, bool pair) { return pair ? (mode == 3 ? kStagesPair - 1 : kStagesPair) : kStagesSingle; }
 constexpr int stream_stage_bytes(bool pair) { return kXStageBytes + (pair ? kYStageBytes / 2 : kYStageBytes); }
-constexpr int stream_epi_warps(int mode) { return mode == 1 ? 8 : 4; }   // mode 1: two warps per TMEM lane quadrant, 128 columns each
-constexpr int stream_threads(int mode, bool pair) { return (stream_stages(pair) + 1 + stream_epi_warps(mode)) * 32; }
+constexpr int stream_epi_warps(int mode) { return mode == 1 || mode == 3 ? 8 : 4; }   // modes 1, 3: two warps per TMEM lane quadrant, 128 columns each
+constexpr int stream_threads(int mode, bool pair) { return (stream_stages(mode, pair) + 1 + stream_epi_warps(mode)) * 32; }
+constexpr int kGStageWarpBytes = 4096;    // mode 3: per-warp staging buffer (32 rows x 128 B, 16-byte chunks XOR-swizzled by the row)
+constexpr int stream_extra_bytes(int mode) {   // shared memory between the ring and the barriers
+    return mode == 2 ? 2 * 32 * SM_ROWS * 4 : mode == 1 ? 2 * 4 * SN_COLS * 4 : mode == 3 ? 2 * SN_COLS * 4 + 8 * kGStageWarpBytes : 0;
+}
 constexpr int kListLen = 32;
 constexpr uint32_t kSpinS = 1u << 24;
 
@@ -85,13 +90,13 @@ k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CU
     const CUtensorMap* tmy = side ? &tmy1 : &tmy0;
     const TcSide S = a.s[side];
     const int nkb = (int)((a.d + 63) / 64);
-    constexpr int kStages = stream_stages(kPair);
+    constexpr int kStages = stream_stages(kMode, kPair);
     constexpr int kStageBytes = stream_stage_bytes(kPair);
     const uint32_t cr = kPair ? cluster_ctarank() : 0u;
 
     uint8_t* ring = smem;                                             // kStages x (48 | 32) KB
     uint8_t* lists = ring + kStages * kStageBytes;                    // mode 2: [32][128] float + [32][128] int32 = 32 KB
-    uint8_t* tail = lists + (kMode == 2 ? 2 * kListLen * SM_ROWS * 4 : kMode == 1 ? 2 * 4 * SN_COLS * 4 : 0);   // mode 1: colsum[2][4][256]
+    uint8_t* tail = lists + stream_extra_bytes(kMode);                // mode 1: colsum[2][4][256]; mode 3: b[2][256] + staging
     uint64_t* full = reinterpret_cast<uint64_t*>(tail);               // [kStages]
     uint64_t* empty = full + kStages;                                 // [kStages]
     uint64_t* s_full = empty + kStages;                               // [2]
@@ -215,7 +220,7 @@ k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CU
         float sum = 0.f;
         float* colsum = reinterpret_cast<float*>(lists);  // mode 1
         const float rowvalid = grow < a.m ? 1.f : 0.f;    // rows past m are TMA zero-filled: keep them out of the column sums
-        const int chalf = kMode == 1 ? (warp - (kStages + 1)) >> 2 : 0;     // mode 1: my 128-column half of the tile
+        const int chalf = (kMode == 1 || kMode == 3) ? (warp - (kStages + 1)) >> 2 : 0;     // modes 1, 3: my 128-column half of the tile
         (void)colsum; (void)rowvalid;
         // retrieval state: per X row an unsorted list of its 32 best approximate scores in shared memory,
         // laid out [row][32] so that a whole warp can work on one row's list without bank conflicts; the
@@ -223,6 +228,14 @@ k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CU
         float* ls = reinterpret_cast<float*>(lists);
         int32_t* li = reinterpret_cast<int32_t*>(lists + kListLen * SM_ROWS * 4);
         float mn = -INFINITY;
+        // mode 3 (gradient coefficients): a_i = 2^13 / rowsum_i of my row; b_j per tile in shared memory
+        constexpr float kLog2e = 1.4426950408889634f;
+        float a_i = 0.f;
+        float* bs = reinterpret_cast<float*>(lists);                                     // [2][256]
+        const int we = warp - (kStages + 1);
+        const uint32_t stage_s = smem_u32(lists + 2 * SN_COLS * 4) + (uint32_t)we * kGStageWarpBytes;
+        if (kMode == 3 && grow < a.m) a_i = exp2f((a.inv_tau - S.lse_x[grow]) * kLog2e + 13.0f);
+        (void)a_i; (void)bs; (void)stage_s;
         if (kMode == 2) {
             for (int e = 0; e < kListLen; ++e) { ls[et * kListLen + e] = -INFINITY; li[et * kListLen + e] = -1; }
             __syncwarp();
@@ -231,6 +244,14 @@ k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CU
             const int b = t & 1;
             const int64_t j0 = (t_begin + t) * SN_COLS;
             const int ncols = (int)min((int64_t)SN_COLS, a.n - j0);
+            if (kMode == 3) {
+                // column factors of this tile: b_j = 2^13 / colsum_j (buffer b is rewritten two tiles later, after every
+                // thread has passed the next tile's barrier)
+                const int idx = we * 32 + lane;
+                const int64_t gj = j0 + idx;
+                bs[b * SN_COLS + idx] = gj < a.n ? exp2f((a.inv_tau - S.lse_y[gj]) * kLog2e + 13.0f) : 0.f;
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+            }
             SPROF_BEGIN(p_sf);
             ok = mbar_wait(&s_full[b], (t >> 1) & 1, kSpinS);
             if (threadIdx.x == (kStages + 1) * 32) SPROF_END(p_sf, 3);
@@ -238,8 +259,63 @@ k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CU
             if (!ok) break;
             fence_after_thread_sync();
             SPROF_BEGIN(p_ep);
+            if (kMode == 3) {
+                // G tile: g_ij = p_ij (a_i + b_j) - 2 [i == j], scaled by 2^13, rounded to fp16 and written to the B x B
+                // coefficient matrix (row i, 64 columns = 128 contiguous bytes per chunk).  TMEM gives a thread one ROW;
+                // the chunk is staged through the warp's swizzled 4 KB buffer so that global stores are 8 lanes per row.
+                const int rb_row = lane >> 3, rb_chunk = lane & 7;
+                const int64_t rbase = row0 + qd * 32;
+                uint16_t* gout = static_cast<uint16_t*>(a.g_out);
 #pragma unroll 1
-            for (int c0 = chalf * 128; c0 < (kMode == 1 ? chalf * 128 + 128 : SN_COLS); c0 += 32) {
+                for (int c0 = chalf * 128; c0 < chalf * 128 + 128; c0 += 64) {
+                    uint32_t r[64];
+                    tmem_ld_32x32b_x32(tmem + lane_addr + b * SN_COLS + c0, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+                    tmem_ld_32x32b_x32(tmem + lane_addr + b * SN_COLS + c0 + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+                    tmem_ld_wait();
+                    const uint32_t b_addr = smem_u32(bs) + (uint32_t)(b * SN_COLS + c0) * 4;
+                    // the diagonal of S crosses this warp's 32 x 64 chunk? (warp-uniform; one chunk in 2 * B / 128 ... rare)
+                    const int64_t dc = a.row_offset + grow - (j0 + c0);       // my diagonal column inside the chunk, if in [0, 64)
+                    const bool has_diag = a.row_offset + rbase < j0 + c0 + 64 && a.row_offset + rbase + 32 > j0 + c0;
+                    uint32_t packed[32];
+#pragma unroll
+                    for (int q8 = 0; q8 < 8; ++q8) {
+                        float4 b0, b1;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b0.x), "=f"(b0.y), "=f"(b0.z), "=f"(b0.w) : "r"(b_addr + q8 * 32));
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b1.x), "=f"(b1.y), "=f"(b1.z), "=f"(b1.w) : "r"(b_addr + q8 * 32 + 16));
+                        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                        float gv[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) gv[i] = ex2_ftz(fmaf(__uint_as_float(r[q8 * 8 + i]), c, -c)) * (a_i + bv[i]);
+                        if (has_diag) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) gv[i] += (dc == q8 * 8 + i) ? -16384.0f : 0.f;
+                        }
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) {
+                            const __half2 hv = __floats2half2_rn(gv[2 * h], gv[2 * h + 1]);
+                            packed[q8 * 4 + h] = *reinterpret_cast<const uint32_t*>(&hv);
+                        }
+                    }
+#pragma unroll
+                    for (int q8 = 0; q8 < 8; ++q8)
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_s + lane * 128 + ((q8 ^ (lane & 7)) << 4)),
+                                     "r"(packed[q8 * 4]), "r"(packed[q8 * 4 + 1]), "r"(packed[q8 * 4 + 2]), "r"(packed[q8 * 4 + 3]) : "memory");
+                    __syncwarp();
+                    // rows / columns past m / n land in the padding of the coefficient matrix (ld and row count are rounded
+                    // up to whole tiles); its readers never look there (TMA bounds = m x n)
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int rr = rb_row + 4 * k;
+                        uint4 x;
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w)
+                                     : "r"(stage_s + rr * 128 + ((rb_chunk ^ (rr & 7)) << 4)) : "memory");
+                        *reinterpret_cast<uint4*>(gout + (size_t)(rbase + rr) * a.ldg + j0 + c0 + rb_chunk * 8) = x;
+                    }
+                    __syncwarp();
+                }
+            }
+#pragma unroll 1
+            for (int c0 = chalf * 128; kMode != 3 && c0 < (kMode == 1 ? chalf * 128 + 128 : SN_COLS); c0 += 32) {
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(tmem + lane_addr + b * SN_COLS + c0, r);
                 tmem_ld_wait();
@@ -362,6 +438,7 @@ k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CU
             if (chalf == 0 && grow < a.m) S.out[(int64_t)blockIdx.y * a.m + grow] = sum + colsum[et];
         } else if (kMode == 0) {
             if (grow < a.m) S.out[(int64_t)blockIdx.y * a.m + grow] = sum;
+        } else if (kMode == 3) {
         } else {
             __syncwarp();
             if (grow < a.m) {
@@ -458,8 +535,10 @@ int launch_stream_tc(int mode, int nsides, const void* const x[2], const void* c
         }
     }
     if (mode == 1 && (!a.col_out || nsides != 1)) return fail(DCLIP_ERR_INVALID, "stream_tc: mode 1 is single-sided and needs col_out");
-    const size_t smem = 1024 + (size_t)stream_stages(pair) * stream_stage_bytes(pair) +
-                        (mode == 2 ? 2 * kListLen * SM_ROWS * 4 : mode == 1 ? 2 * 4 * SN_COLS * 4 : 0) + 256;
+    if (mode == 3 && (!a.g_out || nsides != 1 || !pair || a.ldg % 8 || a.ldg < ceil_div(a.n, SN_COLS) * SN_COLS))
+        return fail(DCLIP_ERR_INVALID, "stream_tc: mode 3 is single-sided, needs more than 128 rows and a tile-padded coefficient matrix");
+    const size_t smem = 1024 + (size_t)stream_stages(mode, pair) * stream_stage_bytes(pair) +
+                        (mode == 3 ? stream_extra_bytes(3) : mode == 2 ? stream_extra_bytes(2) : mode == 1 ? stream_extra_bytes(1) : 0) + 256;
     const int64_t row_blocks = ceil_div(a.m, SM_ROWS);
     dim3 grid((unsigned)(pair ? (row_blocks + 1) / 2 * 2 : row_blocks), (unsigned)nsplit, (unsigned)nsides);
 #define DCLIP_STREAM_LAUNCH(MODE, PAIR)                                                                                   \
@@ -479,6 +558,7 @@ int launch_stream_tc(int mode, int nsides, const void* const x[2], const void* c
     } while (0)
     if (mode == 0) { if (pair) DCLIP_STREAM_LAUNCH(0, true); else DCLIP_STREAM_LAUNCH(0, false); }
     else if (mode == 1) { if (pair) DCLIP_STREAM_LAUNCH(1, true); else DCLIP_STREAM_LAUNCH(1, false); }
+    else if (mode == 3) DCLIP_STREAM_LAUNCH(3, true);
     else { if (pair) DCLIP_STREAM_LAUNCH(2, true); else DCLIP_STREAM_LAUNCH(2, false); }
 #undef DCLIP_STREAM_LAUNCH
     DCLIP_LAUNCH_OK("k_stream_tc");

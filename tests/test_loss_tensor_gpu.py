@@ -133,3 +133,22 @@ def test_host_step_split_matches_composite(built_library, B, d, dtype, path):
     assert torch.allclose(lh, ref_l.cpu(), rtol=1e-5, atol=1e-6), (lh, ref_l)
     assert _rel(di, ref_di) < 1e-5 + (2 ** -8 if dtype == torch.bfloat16 else 0)
     assert _rel(dt, ref_dt) < 1e-5 + (2 ** -8 if dtype == torch.bfloat16 else 0)
+
+
+@pytest.mark.parametrize("B,d", [(4096, 768), (1000, 512), (264, 256)])
+def test_materialised_g_backward_matches_fused_pair_kernel(built_library, B, d, monkeypatch):
+    """Single-GPU backward through the materialised fp16 coefficient matrix (stream mode 3 + two GEMMs, the default)
+    against the fused CTA-pair kernel (DCLIP_BWD_GMAT=0, the kernel of the sharded path): same G values, fp32
+    accumulation in a different order."""
+    from dclip_b200 import losses as L
+    dev = torch.device("cuda:0")
+    s_img, s_txt, t_img, t_txt = (t.to(dev) for t in synthetic.loss_inputs(B, d, seed=11))
+    monkeypatch.setenv("DCLIP_BWD_GMAT", "0")
+    l0, di0, dt0 = L.distill_loss_fwd_bwd(s_img, s_txt, t_img, t_txt, path="tensor")
+    monkeypatch.delenv("DCLIP_BWD_GMAT")
+    l1, di1, dt1 = L.distill_loss_fwd_bwd(s_img, s_txt, t_img, t_txt, path="tensor")
+    torch.cuda.synchronize()
+    assert _pipeline_ok(built_library)
+    assert torch.equal(l0, l1)
+    print(f"[gmat vs fused] B={B} d={d}: d_img {_rel(di1, di0):.3e} d_txt {_rel(dt1, dt0):.3e}")
+    assert _rel(di1, di0) < 1e-5 and _rel(dt1, dt0) < 1e-5
