@@ -40,6 +40,11 @@ SIGNATURES = {
     "dclip_infonce_grad": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _f32, _i64, _vp, _vp, _f32, _vp, _vp, _sz, _i32,
                                   _vp]),
     "dclip_infonce_grad_pair_workspace_bytes": (_sz, [_i64, _i64, _i32]),
+    "dclip_infonce_coeffs_bytes": (_sz, [_i64]),
+    "dclip_infonce_coeffs_ld": (_i64, [_i64]),
+    "dclip_infonce_coeffs_dot_bytes": (_sz, [_i64]),
+    "dclip_infonce_coeffs": (_i32, [_vp, _vp, _i64, _i64, _f32, _vp, _vp, _vp, _vp, _vp]),
+    "dclip_infonce_grad_from_coeffs": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _f32, _f32, _vp, _vp, _vp, _vp]),
     "dclip_infonce_grad_pair": (_i32, [_vp, _vp, _i64, _i64, _i32, _f32, _vp, _vp, _f32, _vp, _vp, _vp, _sz, _i32, _vp]),
     "dclip_loss_grad_tail": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _f32, _f32, _vp, _vp]),
     "dclip_loss_partial_sums": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),

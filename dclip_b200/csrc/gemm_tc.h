@@ -20,5 +20,17 @@ struct TcGemmProblem {
 };
 
 int launch_gemm_tc(const TcGemmProblem* probs, int count, int dtype16, cudaStream_t st);
+// CTA-pair kernel with 256 x 384 tiles (gemm_pair.cu): plain fp32 outputs only, at most 2 problems
+bool gemm_pair_ok(const TcGemmProblem& q);
+// Optional fused epilogue of the distillation gradients (normalise backward + cosine-term gradient, per problem):
+//   out[i, :] = ((alpha acc[i, :] + ts_i t[i, :]) - x[i, :] inv_i dot_i) inv_i grad_scale,   ts_i = -w t_inv_i,
+//   dot_i = alpha sum_q dot_part[q][i] - w cos_i   (0 when the norm was clamped);  x / t / out are [M, N] in `io_dtype`.
+struct GemmPairTail {
+    const void* x; const void* t; const float* inv_norm; const float* cos; const float* t_inv;
+    const float* dot_part; int dot_count; long long dot_stride;
+    void* out; float w_cos_over_B;
+};
+int launch_gemm_pair(const TcGemmProblem* probs, int count, int dtype16, cudaStream_t st, const GemmPairTail* tails = nullptr,
+                     float grad_scale = 1.0f, int io_dtype = 0);
 
 }  // namespace dclip

@@ -199,6 +199,40 @@ int dclip_infonce_grad_pair(const void* u_hat, const void* v_hat, int64_t B, int
     return DCLIP_OK;
 }
 
+size_t dclip_infonce_coeffs_bytes(int64_t B) { return B > 0 ? tc_gmat_bytes(B) : 0; }
+int64_t dclip_infonce_coeffs_ld(int64_t B) { return tc_gmat_ld(B); }
+size_t dclip_infonce_coeffs_dot_bytes(int64_t B) { return B > 0 ? tc_gmat_dot_floats(B) * sizeof(float) : 0; }
+
+int dclip_infonce_coeffs(const void* u_hat, const void* v_hat, int64_t B, int64_t d, float temperature, const float* lse_u,
+                         const float* lse_v, void* coeffs, float* dots, void* stream) {
+    if (int e = check_common(B, d)) return e;
+    DCLIP_REQUIRE(u_hat && v_hat && lse_u && lse_v && coeffs && dots, "infonce_coeffs: null pointer");
+    DCLIP_REQUIRE(B > 128, "infonce_coeffs: needs more than 128 rows (got %lld)", (long long)B);
+    if (!tc_loss_shape_ok(d, temperature))
+        return fail(DCLIP_ERR_UNSUPPORTED, "infonce_coeffs: tensor path needs d %% 128 == 0, 128 <= d <= 768 and temperature >= 0.025 (d=%lld tau=%g)", (long long)d, temperature);
+    DCLIP_REQUIRE(aligned16(u_hat) && aligned16(v_hat) && aligned16(coeffs), "infonce_coeffs: pointers must be 16-byte aligned");
+    return launch_gmat_coeffs(u_hat, v_hat, B, d, lse_u, lse_v, 1.0f / temperature, coeffs, dots, static_cast<cudaStream_t>(stream));
+}
+
+int dclip_infonce_grad_from_coeffs(const void* coeffs, const float* dots, const void* u_hat, const void* v_hat, int64_t B, int64_t d,
+                                   float temperature, float coef, float* du_hat, float* dv_hat, const dclip_grad_tail* tail, void* stream) {
+    if (int e = check_common(B, d)) return e;
+    DCLIP_REQUIRE(coeffs && u_hat && v_hat && B > 128 && temperature > 0.f, "infonce_grad_from_coeffs: bad arguments");
+    DCLIP_REQUIRE(tail || (du_hat && dv_hat), "infonce_grad_from_coeffs: give du_hat / dv_hat or a gradient tail");
+    const float alpha = coef / temperature * (1.0f / 8192.0f);
+    if (!tail) return launch_gmat_gemms(coeffs, dots, u_hat, v_hat, B, d, alpha, du_hat, dv_hat, nullptr, static_cast<cudaStream_t>(stream));
+    DCLIP_REQUIRE(dots && tail->s_img && tail->s_txt && tail->inv_u && tail->inv_v && tail->d_s_img && tail->d_s_txt,
+                  "infonce_grad_from_coeffs: incomplete gradient tail");
+    DCLIP_REQUIRE((tail->t_img == nullptr) == (tail->t_txt == nullptr), "infonce_grad_from_coeffs: give both teachers or neither");
+    DCLIP_REQUIRE(!tail->t_img || (tail->cos_img && tail->cos_txt && tail->tinv_img && tail->tinv_txt),
+                  "infonce_grad_from_coeffs: teachers need their cosine terms and inverse norms");
+    GmatTail gt{};
+    gt.s[0] = GmatTailSide{tail->s_img, tail->t_img, tail->inv_u, tail->cos_img, tail->tinv_img, tail->d_s_img, tail->w_img_over_B};
+    gt.s[1] = GmatTailSide{tail->s_txt, tail->t_txt, tail->inv_v, tail->cos_txt, tail->tinv_txt, tail->d_s_txt, tail->w_txt_over_B};
+    gt.grad_scale = tail->grad_scale; gt.dtype = tail->dtype;
+    return launch_gmat_gemms(coeffs, dots, u_hat, v_hat, B, d, alpha, nullptr, nullptr, &gt, static_cast<cudaStream_t>(stream));
+}
+
 int dclip_loss_grad_tail(const void* x, const void* teacher, const float* inv_norm, const float* dx_hat, int64_t m,
                          int64_t d, int dtype, float w_cos_over_B, float grad_scale, void* d_x, void* stream) {
     if (int e = check_common(m, d)) return e;
@@ -228,7 +262,7 @@ int dclip_distill_loss_launch_count(int64_t m, int64_t n, int64_t d, int path, i
     if (path == DCLIP_PATH_FP32 && !sharded && small_loss_shape_ok(m, d) && m == n) return 1;      // k_distill_small
     if (path == DCLIP_PATH_FP32) return sharded ? 11 : 6;   // prep, rowlse+combine, sums, grad, tail (x2 sides when sharded)
     // tensor path, single GPU: prep_pair, one-pass forward tiles, finalize, backward tiles (+ partial combines), tail
-    if (!sharded && tc_gmat_ok(m, d)) return 6;   // prep_pair, forward tiles, finalize, G tiles, grouped GEMM (dU, dV), tail
+    if (!sharded && tc_gmat_ok(m, d)) return 5;   // prep_pair, forward tiles, finalize, G tiles, pair GEMM (dU, dV) with the fused tail
     if (!sharded) return 5 + (tc_nsplit(m, n, d, 2) > 1 ? 2 : 0);
     // fused sharded phases: prep, forward tiles, finalize, global losses, backward tiles (+ combine), tail
     // + the three peer-memory pushes (operands, statistics, step-done) that replace the NCCL all-gathers
@@ -345,7 +379,8 @@ size_t dclip_distill_loss_workspace_bytes(int64_t B, int64_t d, int path) {
         if (tns > 1) total += align_up((size_t)2 * tns * B * d * 4, 256);
         // one-pass forward: row partials [stream_nsplit(1 side)][B] + column partials [ceil(B / 128)][B]
         total += align_up((size_t)stream_nsplit(B, B, 1) * B * 4, 256) + align_up((size_t)ceil_div(B, 128) * B * 4, 256);
-        if (tc_gmat_ok(B, d)) total += align_up(tc_gmat_bytes(B), 256);   // fp16 gradient coefficients G
+        if (tc_gmat_ok(B, d))     // fp16 gradient coefficients G + row / column sums of g * s + the teachers' inverse norms
+            total += align_up(tc_gmat_bytes(B), 256) + align_up(tc_gmat_dot_floats(B) * 4, 256) + 2 * align_up((size_t)B * 4, 256);
     }
     return total + 1024;
 }
@@ -409,6 +444,12 @@ static int distill_loss_impl(int phase, const void* s_img, const void* s_txt, co
     float* colpart = tensor ? static_cast<float*>(ws.take((size_t)nib * B * 4)) : nullptr;
     const bool gmat = tensor && tc_gmat_ok(B, d);
     void* g_buf = gmat ? ws.take(tc_gmat_bytes(B)) : nullptr;
+    float* dot_ws = gmat ? static_cast<float*>(ws.take(tc_gmat_dot_floats(B) * 4)) : nullptr;
+    float* tinv_u = gmat ? static_cast<float*>(ws.take((size_t)B * 4)) : nullptr;
+    float* tinv_v = gmat ? static_cast<float*>(ws.take((size_t)B * 4)) : nullptr;
+    // one-call objective: the GEMM epilogue finishes the gradients (no fp32 dX_hat round trip, no tail launch)
+    const char* ft_env = getenv("DCLIP_GMAT_FUSED_TAIL");      // "0": fp32 dX_hat + the tail kernel (A/B measurements, tests)
+    const bool fused_tail = gmat && phase == 0 && d_s_img && w_con != 0.f && !(ft_env && ft_env[0] == '0');
     if (!ws.ok()) return fail(DCLIP_ERR_WORKSPACE, "distill_loss: workspace too small (%zu < %zu)", workspace_bytes, ws.used);
     if (stats) { lse_u = stats; lse_v = stats + B; }
 
@@ -426,8 +467,8 @@ static int distill_loss_impl(int phase, const void* s_img, const void* s_txt, co
         if (int e = launch_loss_sums(sa, st)) return e;
     }
     PrepArgs pa{};
-    pa.s[0] = PrepSide{s_img, phase == 1 ? nullptr : t_img, u_hat, inv_u, cos_img};
-    pa.s[1] = PrepSide{s_txt, phase == 1 ? nullptr : t_txt, v_hat, inv_v, cos_txt};
+    pa.s[0] = PrepSide{s_img, phase == 1 ? nullptr : t_img, u_hat, inv_u, cos_img, tinv_u};
+    pa.s[1] = PrepSide{s_txt, phase == 1 ? nullptr : t_txt, v_hat, inv_v, cos_txt, tinv_v};
     pa.m = B; pa.d = d;
     if (!do_students) {
     } else if (tensor) {
@@ -468,9 +509,15 @@ static int distill_loss_impl(int phase, const void* s_img, const void* s_txt, co
         const bool need_con = w_con != 0.f;
         if (!do_students) {
         } else if (need_con && gmat) {
+            GmatTail gt{};
+            gt.s[0] = GmatTailSide{s_img, t_img, inv_u, cos_img, tinv_u, d_s_img, w_img / (float)B};
+            gt.s[1] = GmatTailSide{s_txt, t_txt, inv_v, cos_txt, tinv_v, d_s_txt, w_txt / (float)B};
+            gt.grad_scale = grad_scale; gt.dtype = dtype;
             if (int e = launch_infonce_bwd_gmat(u_hat, v_hat, B, d, lse_u, lse_v, 1.0f / temperature,
-                                                w_con / (2.0f * (float)B) / temperature * (1.0f / 8192.0f), g_buf, du_hat, dv_hat, st))
+                                                w_con / (2.0f * (float)B) / temperature * (1.0f / 8192.0f), g_buf, dot_ws, du_hat, dv_hat,
+                                                fused_tail ? &gt : nullptr, st))
                 return e;
+            if (fused_tail) return DCLIP_OK;
         } else if (need_con && tensor) {
             TcArgs ga{};
             ga.s[0] = TcSide{lse_u, lse_v, du_part};

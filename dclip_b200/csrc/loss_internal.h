@@ -8,7 +8,7 @@ namespace dclip {
 // A "side" is one direction of the symmetric objective: side 0 = image rows against all text
 // rows, side 1 = text rows against all image rows.  Kernels take both sides in one launch
 // (blockIdx.z / .y selects) so the single-GPU step is 6 launches.
-struct PrepSide { const void* x; const void* t; void* xhat; float* inv_norm; float* cos; };
+struct PrepSide { const void* x; const void* t; void* xhat; float* inv_norm; float* cos; float* t_inv; };   // t_inv: 1 / max(|t|, eps), optional
 struct PrepArgs { PrepSide s[2]; int64_t m, d; float* diag; float inv_tau; };   // diag: pair kernel only
 
 // cosine terms of the rows against the teacher, students' inverse norms given (phase 2 of the split objective)
@@ -89,8 +89,19 @@ int tc_check_error_flag(cudaStream_t st);
 // single-GPU backward through the materialised fp16 coefficient matrix G (stream mode 3 + two GEMMs); g_buf = tc_gmat_bytes(B)
 bool tc_gmat_ok(int64_t B, int64_t d);
 size_t tc_gmat_bytes(int64_t B);
+// Gradient tail fused into the GEMM epilogue (normalise backward + cosine-term gradient, k_loss_grad_tail's math): per side
+// the raw student / teacher rows, the prep kernel's per-row vectors and the output gradient; null `tail` = fp32 dX_hat outputs.
+struct GmatTailSide { const void* x; const void* t; const float* inv_norm; const float* cos; const float* t_inv; void* d_x; float w_cos_over_B; };
+struct GmatTail { GmatTailSide s[2]; float grad_scale; int dtype; };
+// workspace for the row / column sums of g * s: floats
+size_t tc_gmat_dot_floats(int64_t B);
+int64_t tc_gmat_ld(int64_t B);
+int launch_gmat_coeffs(const void* u_hat, const void* v_hat, int64_t B, int64_t d, const float* lse_u, const float* lse_v, float inv_tau,
+                       void* g_buf, float* dot_ws, cudaStream_t st);
+int launch_gmat_gemms(const void* g_buf, const float* dot_ws, const void* u_hat, const void* v_hat, int64_t B, int64_t d, float out_scale,
+                      float* du_hat, float* dv_hat, const GmatTail* tail, cudaStream_t st);
 int launch_infonce_bwd_gmat(const void* u_hat, const void* v_hat, int64_t B, int64_t d, const float* lse_u, const float* lse_v, float inv_tau,
-                            float out_scale, void* g_buf, float* du_hat, float* dv_hat, cudaStream_t st);
+                            float out_scale, void* g_buf, float* dot_ws, float* du_hat, float* dv_hat, const GmatTail* tail, cudaStream_t st);
 // streaming 128 x 256 score-tile kernel (stream_tc.cu): mode 0 = row sums, mode 2 = top-32 candidates
 int stream_nsplit(int64_t m, int64_t n, int nsides);
 int launch_stream_tc(int mode, int nsides, const void* const x[2], const void* const y[2], const TcArgs& args, int nsplit,

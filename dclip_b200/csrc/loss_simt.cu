@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(kThreads) k_loss_prep_pair(PrepArgs a) {
         if (lane == 0) {
             s.inv_norm[row] = 1.0f / nx;
             if (s.cos) s.cos[row] = t ? xt / (nx * fmaxf(sqrtf(tt), kNormEps)) : 0.f;
+            if (s.t_inv) s.t_inv[row] = t ? 1.0f / fmaxf(sqrtf(tt), kNormEps) : 0.f;
         }
     }
     const T* x0 = static_cast<const T*>(a.s[0].x) + row * d;
@@ -163,6 +164,7 @@ __global__ void __launch_bounds__(128) k_loss_prep_pair_nc(PrepArgs a) {
         if (lane == 0) {
             a.s[sd].inv_norm[row] = 1.0f / nx;
             if (a.s[sd].cos) a.s[sd].cos[row] = has_t ? xt / (nx * fmaxf(sqrtf(tt), kNormEps)) : 0.f;
+            if (a.s[sd].t_inv) a.s[sd].t_inv[row] = has_t ? 1.0f / fmaxf(sqrtf(tt), kNormEps) : 0.f;
         }
     }
     OT* o0 = static_cast<OT*>(a.s[0].xhat) + row * d;

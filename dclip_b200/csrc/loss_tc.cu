@@ -446,22 +446,51 @@ bool tc_gmat_ok(int64_t B, int64_t d) {
 size_t tc_gmat_bytes(int64_t B) {
     return (size_t)(ceil_div(B, 128) * 128) * (size_t)(ceil_div(B, 256) * 256) * 2;
 }
-int launch_infonce_bwd_gmat(const void* u_hat, const void* v_hat, int64_t B, int64_t d, const float* lse_u, const float* lse_v, float inv_tau,
-                            float out_scale, void* g_buf, float* du_hat, float* dv_hat, cudaStream_t st) {
-    const int64_t ldg = ceil_div(B, 256) * 256;
+size_t tc_gmat_dot_floats(int64_t B) { return (size_t)(stream_nsplit(B, B, 1) + ceil_div(B, 128)) * (size_t)B; }
+int64_t tc_gmat_ld(int64_t B) { return ceil_div(B, 256) * 256; }
+// stage 1: G and the row / column sums of g * s.  dot_ws: [ns][B] partial row sums (u side: x_hat_i . dU_hat_i / alpha),
+// then [ceil(B / 128)][B] partial column sums (v side)
+int launch_gmat_coeffs(const void* u_hat, const void* v_hat, int64_t B, int64_t d, const float* lse_u, const float* lse_v, float inv_tau,
+                       void* g_buf, float* dot_ws, cudaStream_t st) {
+    const int ns = stream_nsplit(B, B, 1);
     TcArgs a{};
-    a.s[0] = TcSide{lse_u, lse_v, nullptr};
+    a.s[0] = TcSide{lse_u, lse_v, dot_ws};
+    a.col_out = dot_ws + (size_t)ns * B;
     a.m = B; a.n = B; a.d = d; a.inv_tau = inv_tau; a.row_offset = 0;
-    a.g_out = g_buf; a.ldg = ldg;
+    a.g_out = g_buf; a.ldg = tc_gmat_ld(B);
     const void* xs[2] = {u_hat, u_hat};
     const void* ys[2] = {v_hat, v_hat};
-    if (int e = launch_stream_tc(3, 1, xs, ys, a, stream_nsplit(B, B, 1), st)) return e;
+    return launch_stream_tc(3, 1, xs, ys, a, ns, st);
+}
+// stage 2: dU_hat = alpha G V_hat, dV_hat = alpha G^T U_hat; with `tail` the epilogue finishes the gradients (needs dot_ws)
+int launch_gmat_gemms(const void* g_buf, const float* dot_ws, const void* u_hat, const void* v_hat, int64_t B, int64_t d, float out_scale,
+                      float* du_hat, float* dv_hat, const GmatTail* tail, cudaStream_t st) {
+    const int64_t ldg = tc_gmat_ld(B);
+    const int ns = stream_nsplit(B, B, 1), nib = (int)ceil_div(B, 128);
     TcGemmProblem pr[2] = {};
     pr[0].A = g_buf; pr[0].lda = (int)ldg; pr[0].a_mn = 0; pr[0].B = v_hat; pr[0].ldb = (int)d; pr[0].b_mn = 1;
     pr[0].C = du_hat; pr[0].ldc = (int)d; pr[0].M = (int)B; pr[0].N = (int)d; pr[0].K = (int)B; pr[0].alpha = out_scale;
     pr[1] = pr[0];
     pr[1].a_mn = 1; pr[1].B = u_hat; pr[1].C = dv_hat;
-    return launch_gemm_tc(pr, 2, DCLIP_F16, st);
+    const char* e = getenv("DCLIP_GEMM_PAIR");      // "0": the 128 x 256 single-CTA grouped GEMM (A/B measurements; no fused tail)
+    if (e && e[0] == '0') {
+        if (tail) return fail(DCLIP_ERR_INVALID, "bwd_gmat: the fused gradient tail needs the CTA-pair GEMM");
+        return launch_gemm_tc(pr, 2, DCLIP_F16, st);
+    }
+    if (!tail) return launch_gemm_pair(pr, 2, DCLIP_F16, st);
+    GemmPairTail gt[2];
+    for (int sd = 0; sd < 2; ++sd) {
+        const GmatTailSide& t = tail->s[sd];
+        gt[sd] = GemmPairTail{t.x, t.t, t.inv_norm, t.cos, t.t_inv, sd == 0 ? dot_ws : dot_ws + (size_t)ns * B, sd == 0 ? ns : nib, (long long)B,
+                              t.d_x, t.w_cos_over_B};
+        pr[sd].C = nullptr;
+    }
+    return launch_gemm_pair(pr, 2, DCLIP_F16, st, gt, tail->grad_scale, tail->dtype);
+}
+int launch_infonce_bwd_gmat(const void* u_hat, const void* v_hat, int64_t B, int64_t d, const float* lse_u, const float* lse_v, float inv_tau,
+                            float out_scale, void* g_buf, float* dot_ws, float* du_hat, float* dv_hat, const GmatTail* tail, cudaStream_t st) {
+    if (int e = launch_gmat_coeffs(u_hat, v_hat, B, d, lse_u, lse_v, inv_tau, g_buf, dot_ws, st)) return e;
+    return launch_gmat_gemms(g_buf, dot_ws, u_hat, v_hat, B, d, out_scale, du_hat, dv_hat, tail, st);
 }
 
 int launch_tc_lse_combine(const float* part, int nsplit, int64_t m, float inv_tau, float* lse, cudaStream_t st) {

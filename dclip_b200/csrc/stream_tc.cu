@@ -38,7 +38,7 @@ using namespace tc;
 #ifdef DCLIP_PAIR_PROF
 __device__ unsigned long long g_stream_prof[16];
 #define SPROF_BEGIN(v) const long long v = clock64()
-#define SPROF_END(v, slot) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) atomicAdd(&g_stream_prof[slot], (unsigned long long)(clock64() - v)); } while (0)
+#define SPROF_END(v, slot) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) atomicAdd(&g_stream_prof[(slot) + (kMode == 3 ? 8 : 0)], (unsigned long long)(clock64() - v)); } while (0)
 #else
 #define SPROF_BEGIN(v) do { } while (0)
 #define SPROF_END(v, slot) do { } while (0)
@@ -53,11 +53,13 @@ constexpr int kYStageBytes = SN_COLS * 128;   // 32 KB
 // mode 3 gives one ring stage to the epilogue's staging buffers (8 warps x 4 KB)
 constexpr int stream_stages(int mode, bool pair) { return pair ? (mode == 3 ? kStagesPair - 1 : kStagesPair) : kStagesSingle; }
 constexpr int stream_stage_bytes(bool pair) { return kXStageBytes + (pair ? kYStageBytes / 2 : kYStageBytes); }
-constexpr int stream_epi_warps(int mode) { return mode == 1 || mode == 3 ? 8 : 4; }   // modes 1, 3: two warps per TMEM lane quadrant, 128 columns each
+// mode 1: two warps per TMEM lane quadrant, 128 columns each; mode 3: four per quadrant, 64 columns each
+constexpr int stream_epi_warps(int mode) { return mode == 3 ? 16 : mode == 1 ? 8 : 4; }
 constexpr int stream_threads(int mode, bool pair) { return (stream_stages(mode, pair) + 1 + stream_epi_warps(mode)) * 32; }
-constexpr int kGStageWarpBytes = 4096;    // mode 3: per-warp staging buffer (32 rows x 128 B, 16-byte chunks XOR-swizzled by the row)
+constexpr int kGStageWarpBytes = 2048;    // mode 3: per-warp staging buffer (32 rows x 64 B, 16-byte chunks XOR-swizzled by the row pair)
+constexpr int kGStageWarps = 16;
 constexpr int stream_extra_bytes(int mode) {   // shared memory between the ring and the barriers
-    return mode == 2 ? 2 * 32 * SM_ROWS * 4 : mode == 1 ? 2 * 4 * SN_COLS * 4 : mode == 3 ? 2 * SN_COLS * 4 + 8 * kGStageWarpBytes : 0;
+    return mode == 2 ? 2 * 32 * SM_ROWS * 4 : mode == 1 ? 2 * 4 * SN_COLS * 4 : mode == 3 ? 2 * SN_COLS * 4 + kGStageWarps * kGStageWarpBytes + 2 * 4 * SN_COLS * 4 : 0;
 }
 constexpr int kListLen = 32;
 constexpr uint32_t kSpinS = 1u << 24;
@@ -104,6 +106,7 @@ k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CU
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(s_empty + 2);
 
     const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+    SPROF_BEGIN(p_kernel);
     const int64_t row0 = (int64_t)blockIdx.x * SM_ROWS;
     const int64_t ntiles = (a.n + SN_COLS - 1) / SN_COLS;
     const int64_t t_begin = (int64_t)blockIdx.y * a.tiles_per_split;
@@ -123,6 +126,7 @@ k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CU
     fence_after_thread_sync();
     const uint32_t tmem = *tmem_ptr;
     bool ok = true;
+    if (threadIdx.x == 0) SPROF_END(p_kernel, 6);
 
     if (warp < kStages) {
         // ===================== TMA producers: warp w owns ring stage w =====================
@@ -220,7 +224,8 @@ k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CU
         float sum = 0.f;
         float* colsum = reinterpret_cast<float*>(lists);  // mode 1
         const float rowvalid = grow < a.m ? 1.f : 0.f;    // rows past m are TMA zero-filled: keep them out of the column sums
-        const int chalf = (kMode == 1 || kMode == 3) ? (warp - (kStages + 1)) >> 2 : 0;     // modes 1, 3: my 128-column half of the tile
+        const int chalf = kMode == 1 ? (warp - (kStages + 1)) >> 2 : 0;     // mode 1: my 128-column half of the tile
+        const int cpart = kMode == 3 ? (warp - (kStages + 1)) >> 2 : 0;     // mode 3: my 64-column quarter of the tile
         (void)colsum; (void)rowvalid;
         // retrieval state: per X row an unsorted list of its 32 best approximate scores in shared memory,
         // laid out [row][32] so that a whole warp can work on one row's list without bank conflicts; the
@@ -235,7 +240,8 @@ k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CU
         const int we = warp - (kStages + 1);
         const uint32_t stage_s = smem_u32(lists + 2 * SN_COLS * 4) + (uint32_t)we * kGStageWarpBytes;
         if (kMode == 3 && grow < a.m) a_i = exp2f((a.inv_tau - S.lse_x[grow]) * kLog2e + 13.0f);
-        (void)a_i; (void)bs; (void)stage_s;
+        float* csum3 = reinterpret_cast<float*>(lists + 2 * SN_COLS * 4 + kGStageWarps * kGStageWarpBytes);     // [2][4][256] column sums of g * s
+        (void)a_i; (void)bs; (void)stage_s; (void)csum3; (void)cpart;
         if (kMode == 2) {
             for (int e = 0; e < kListLen; ++e) { ls[et * kListLen + e] = -INFINITY; li[et * kListLen + e] = -1; }
             __syncwarp();
@@ -249,8 +255,8 @@ k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CU
                 // thread has passed the next tile's barrier)
                 const int idx = we * 32 + lane;
                 const int64_t gj = j0 + idx;
-                bs[b * SN_COLS + idx] = gj < a.n ? exp2f((a.inv_tau - S.lse_y[gj]) * kLog2e + 13.0f) : 0.f;
-                asm volatile("bar.sync 2, 256;" ::: "memory");
+                if (idx < SN_COLS) bs[b * SN_COLS + idx] = gj < a.n ? exp2f((a.inv_tau - S.lse_y[gj]) * kLog2e + 13.0f) : 0.f;
+                asm volatile("bar.sync 2, 512;" ::: "memory");
             }
             SPROF_BEGIN(p_sf);
             ok = mbar_wait(&s_full[b], (t >> 1) & 1, kSpinS);
@@ -261,24 +267,25 @@ k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CU
             SPROF_BEGIN(p_ep);
             if (kMode == 3) {
                 // G tile: g_ij = p_ij (a_i + b_j) - 2 [i == j], scaled by 2^13, rounded to fp16 and written to the B x B
-                // coefficient matrix (row i, 64 columns = 128 contiguous bytes per chunk).  TMEM gives a thread one ROW;
-                // the chunk is staged through the warp's swizzled 4 KB buffer so that global stores are 8 lanes per row.
-                const int rb_row = lane >> 3, rb_chunk = lane & 7;
+                // coefficient matrix.  TMEM gives a thread one ROW; 32-column chunks (64 B of fp16 per row) are staged through
+                // the warp's swizzled 2 KB buffer so that global stores are 4 lanes per row (two full sectors).  Sixteen
+                // warps: the tile's epilogue (exp, scaling, rounding, the sums below) must stay under its 12 k-blocks of MMAs.
+                const int rb_row = lane >> 2, rb_chunk = lane & 3;
                 const int64_t rbase = row0 + qd * 32;
                 uint16_t* gout = static_cast<uint16_t*>(a.g_out);
 #pragma unroll 1
-                for (int c0 = chalf * 128; c0 < chalf * 128 + 128; c0 += 64) {
-                    uint32_t r[64];
-                    tmem_ld_32x32b_x32(tmem + lane_addr + b * SN_COLS + c0, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
-                    tmem_ld_32x32b_x32(tmem + lane_addr + b * SN_COLS + c0 + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+                for (int c0 = cpart * 64; c0 < cpart * 64 + 64; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(tmem + lane_addr + b * SN_COLS + c0, r);
                     tmem_ld_wait();
                     const uint32_t b_addr = smem_u32(bs) + (uint32_t)(b * SN_COLS + c0) * 4;
-                    // the diagonal of S crosses this warp's 32 x 64 chunk? (warp-uniform; one chunk in 2 * B / 128 ... rare)
-                    const int64_t dc = a.row_offset + grow - (j0 + c0);       // my diagonal column inside the chunk, if in [0, 64)
-                    const bool has_diag = a.row_offset + rbase < j0 + c0 + 64 && a.row_offset + rbase + 32 > j0 + c0;
-                    uint32_t packed[32];
+                    // the diagonal of S crosses this warp's 32 x 32 chunk? (warp-uniform, rare)
+                    const int64_t dc = a.row_offset + grow - (j0 + c0);       // my diagonal column inside the chunk, if in [0, 32)
+                    const bool has_diag = a.row_offset + rbase < j0 + c0 + 32 && a.row_offset + rbase + 32 > j0 + c0;
+                    float v[32];
+                    uint32_t packed[16];
 #pragma unroll
-                    for (int q8 = 0; q8 < 8; ++q8) {
+                    for (int q8 = 0; q8 < 4; ++q8) {
                         float4 b0, b1;
                         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b0.x), "=f"(b0.y), "=f"(b0.z), "=f"(b0.w) : "r"(b_addr + q8 * 32));
                         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b1.x), "=f"(b1.y), "=f"(b1.z), "=f"(b1.w) : "r"(b_addr + q8 * 32 + 16));
@@ -290,28 +297,47 @@ k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CU
 #pragma unroll
                             for (int i = 0; i < 8; ++i) gv[i] += (dc == q8 * 8 + i) ? -16384.0f : 0.f;
                         }
+                        // g * s with the ROUNDED coefficient (what the gradient GEMMs read): its row / column sums are the
+                        // radial components x_hat_i . dX_hat_i of the two gradients (normalise backward, fused GEMM epilogue)
 #pragma unroll
                         for (int h = 0; h < 4; ++h) {
                             const __half2 hv = __floats2half2_rn(gv[2 * h], gv[2 * h + 1]);
                             packed[q8 * 4 + h] = *reinterpret_cast<const uint32_t*>(&hv);
+                            const float2 gr = __half22float2(hv);
+                            v[q8 * 8 + 2 * h] = gr.x * __uint_as_float(r[q8 * 8 + 2 * h]);
+                            v[q8 * 8 + 2 * h + 1] = gr.y * __uint_as_float(r[q8 * 8 + 2 * h + 1]);
+                            sum += v[q8 * 8 + 2 * h] + v[q8 * 8 + 2 * h + 1];
                         }
                     }
 #pragma unroll
-                    for (int q8 = 0; q8 < 8; ++q8)
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_s + lane * 128 + ((q8 ^ (lane & 7)) << 4)),
-                                     "r"(packed[q8 * 4]), "r"(packed[q8 * 4 + 1]), "r"(packed[q8 * 4 + 2]), "r"(packed[q8 * 4 + 3]) : "memory");
+                    for (int q4 = 0; q4 < 4; ++q4)
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_s + lane * 64 + ((q4 ^ ((lane >> 1) & 3)) << 4)),
+                                     "r"(packed[q4 * 4]), "r"(packed[q4 * 4 + 1]), "r"(packed[q4 * 4 + 2]), "r"(packed[q4 * 4 + 3]) : "memory");
                     __syncwarp();
                     // rows / columns past m / n land in the padding of the coefficient matrix (ld and row count are rounded
                     // up to whole tiles); its readers never look there (TMA bounds = m x n)
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const int rr = rb_row + 4 * k;
+                    for (int k = 0; k < 4; ++k) {
+                        const int rr = rb_row + 8 * k;
                         uint4 x;
                         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w)
-                                     : "r"(stage_s + rr * 128 + ((rb_chunk ^ (rr & 7)) << 4)) : "memory");
-                        *reinterpret_cast<uint4*>(gout + (size_t)(rbase + rr) * a.ldg + j0 + c0 + rb_chunk * 8) = x;
+                                     : "r"(stage_s + rr * 64 + ((rb_chunk ^ ((rr >> 1) & 3)) << 4)) : "memory");
+                        if (row0 < a.m)      // (the padded CTA of an odd pair owns no rows of the matrix at all)
+                            *reinterpret_cast<uint4*>(gout + (size_t)(rbase + rr) * a.ldg + j0 + c0 + rb_chunk * 8) = x;
                     }
                     __syncwarp();
+                    // column sums of g * s over my warp's 32 rows: a 32 x 32 transpose-reduce (as in mode 1)
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) {
+                        const bool upper = (lane & off) != 0;
+#pragma unroll
+                        for (int i = 0; i < off; ++i) {
+                            const float send = upper ? v[i] : v[i + off];
+                            const float keep = upper ? v[i + off] : v[i];
+                            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                        }
+                    }
+                    csum3[(b * 4 + qd) * SN_COLS + c0 + lane] = v[0];
                 }
             }
 #pragma unroll 1
@@ -419,6 +445,14 @@ k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CU
                 mbar_arrive(&s_empty[b]);                 // all of this thread's TMEM reads of buffer b are done
             }
             if (threadIdx.x == (kStages + 1) * 32) SPROF_END(p_ep, 4);
+            if (kMode == 3) {
+                asm volatile("bar.sync 2, 512;" ::: "memory");
+                const int col = we * 32 + lane;
+                if (col < ncols && row0 < a.m) {
+                    const float* cs = csum3 + b * 4 * SN_COLS + col;
+                    a.col_out[(int64_t)blockIdx.x * a.n + j0 + col] = (cs[0] + cs[SN_COLS]) + (cs[2 * SN_COLS] + cs[3 * SN_COLS]);
+                }
+            }
             if (kMode == 1) {
                 // the four warps' partial column sums meet here (buffer b is rewritten two tiles later, after
                 // every thread has passed the next tile's barrier)
@@ -439,6 +473,11 @@ k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CU
         } else if (kMode == 0) {
             if (grow < a.m) S.out[(int64_t)blockIdx.y * a.m + grow] = sum;
         } else if (kMode == 3) {
+            // the four column quarters of a row meet in shared memory
+            asm volatile("bar.sync 2, 512;" ::: "memory");
+            if (cpart > 0) csum3[(cpart - 1) * SM_ROWS + et] = sum;
+            asm volatile("bar.sync 2, 512;" ::: "memory");
+            if (cpart == 0 && grow < a.m) S.out[(int64_t)blockIdx.y * a.m + grow] = (sum + csum3[et]) + (csum3[SM_ROWS + et] + csum3[2 * SM_ROWS + et]);
         } else {
             __syncwarp();
             if (grow < a.m) {
@@ -460,6 +499,7 @@ k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CU
     __syncthreads();
     if (kPair) cluster_sync_all();          // no CTA leaves while its peer can still signal its barriers / read its operands
     if (warp == kStages) { if (kPair) tmem_dealloc_pair(tmem, 512); else tmem_dealloc(tmem, 512); }
+    if (threadIdx.x == 0) SPROF_END(p_kernel, 7);
 }
 
 // Column splits: enough CTAs to fill the SMs when there are few row blocks; with many row blocks the
@@ -535,7 +575,7 @@ int launch_stream_tc(int mode, int nsides, const void* const x[2], const void* c
         }
     }
     if (mode == 1 && (!a.col_out || nsides != 1)) return fail(DCLIP_ERR_INVALID, "stream_tc: mode 1 is single-sided and needs col_out");
-    if (mode == 3 && (!a.g_out || nsides != 1 || !pair || a.ldg % 8 || a.ldg < ceil_div(a.n, SN_COLS) * SN_COLS))
+    if (mode == 3 && (!a.g_out || !a.col_out || !a.s[0].out || nsides != 1 || !pair || a.ldg % 8 || a.ldg < ceil_div(a.n, SN_COLS) * SN_COLS))
         return fail(DCLIP_ERR_INVALID, "stream_tc: mode 3 is single-sided, needs more than 128 rows and a tile-padded coefficient matrix");
     const size_t smem = 1024 + (size_t)stream_stages(mode, pair) * stream_stage_bytes(pair) +
                         (mode == 3 ? stream_extra_bytes(3) : mode == 2 ? stream_extra_bytes(2) : mode == 1 ? stream_extra_bytes(1) : 0) + 256;

@@ -134,6 +134,28 @@ size_t dclip_infonce_grad_pair_workspace_bytes(int64_t B, int64_t d, int path);
 int dclip_infonce_grad_pair(const void* u_hat, const void* v_hat, int64_t B, int64_t d, int op_dtype, float temperature,
                             const float* lse_u, const float* lse_v, float coef, float* du_hat, float* dv_hat,
                             void* workspace, size_t workspace_bytes, int path, void* stream);
+/* (3c) (3b) in two stages through a MATERIALISED coefficient matrix (tensor path; what the single-GPU composite runs
+ *      for B > 128): the score tiles are recomputed once instead of once per side.
+ *      stage 1: coeffs[i][j] = 2^13 * (exp(S_ij - lse_u[i]) + exp(S_ij - lse_v[j]) - 2 [i == j]) in float16, row stride
+ *               dclip_infonce_coeffs_ld(B), dclip_infonce_coeffs_bytes(B) bytes; dots (dclip_infonce_coeffs_dot_bytes)
+ *               receives partial row / column sums of coeffs * S = the radial components u_hat_i . du_hat_i, v_hat_j . dv_hat_j.
+ *      stage 2: du_hat = coef/tau * 2^-13 * coeffs . v_hat,  dv_hat = coef/tau * 2^-13 * coeffs^T . u_hat  (fp32 [B, d]) as one
+ *               launch of a CTA-pair GEMM; with `tail` its epilogue applies step (4) to both sides instead and writes
+ *               d_s_img / d_s_txt in `dtype` (du_hat / dv_hat may then be NULL).  tinv_* = 1 / max(|t_i|, 1e-12). */
+typedef struct dclip_grad_tail {
+    const void* s_img; const void* s_txt; const void* t_img; const void* t_txt;       /* raw rows [B, d] in `dtype`; teachers may be NULL */
+    const float* inv_u; const float* inv_v; const float* cos_img; const float* cos_txt; const float* tinv_img; const float* tinv_txt;
+    float w_img_over_B, w_txt_over_B, grad_scale;
+    int dtype;
+    void* d_s_img; void* d_s_txt;
+} dclip_grad_tail;
+size_t dclip_infonce_coeffs_bytes(int64_t B);
+int64_t dclip_infonce_coeffs_ld(int64_t B);
+size_t dclip_infonce_coeffs_dot_bytes(int64_t B);
+int dclip_infonce_coeffs(const void* u_hat, const void* v_hat, int64_t B, int64_t d, float temperature, const float* lse_u,
+                         const float* lse_v, void* coeffs, float* dots, void* stream);
+int dclip_infonce_grad_from_coeffs(const void* coeffs, const float* dots, const void* u_hat, const void* v_hat, int64_t B, int64_t d,
+                                   float temperature, float coef, float* du_hat, float* dv_hat, const dclip_grad_tail* tail, void* stream);
 /* (4) row-local tail: adds the cosine-distillation gradient (-w_cos/B_global * t_hat), applies the
  *     normalise backward  dx = (g - x_hat (x_hat . g)) * inv_norm  and writes d_x in `dtype`.
  *     dx_hat may be NULL (cosine term only).  teacher may be NULL. */
