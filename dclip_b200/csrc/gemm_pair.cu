@@ -19,6 +19,8 @@
 // Warps: 0-4 TMA producers (one ring stage each, both CTAs), 5 MMA issuer (leader) + TMEM alloc, 6-21 epilogue
 // (TMEM lane quadrant = warp & 3, the four warps of a quadrant take 96 columns each; output staged through the
 // idle ring so that global stores are 128 contiguous bytes per row).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "gemm_tc.h"
 #include "tcgen05.cuh"
@@ -47,6 +49,7 @@ struct GemmPairArgs {
     GemmPairDev p[2];
     int count, total_tiles, ab_fmt;
     float grad_scale; int io_dtype;      // fused tail: dclip_dtype of x / t / out
+    int debug_skip;                      // stall-accounting build only (results are garbage): 1 no x / t loads, 2 no stores, 4 no L2 prefetch
     int* error_flag;
 };
 
@@ -85,9 +88,12 @@ __device__ __forceinline__ void store4_io(void* base, size_t idx, int io, const 
 }
 
 #ifdef DCLIP_GEMM_PROF
+#define GP_SKIP(bit) (g.debug_skip & (bit))
 __device__ long long g_gpair_prof[16];
-#define PPROF(k) do { if (blockIdx.x == 0) g_gpair_prof[k] = clock64(); } while (0)
+__device__ __forceinline__ long long gtimer_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define PPROF(k) do { if (blockIdx.x == 0) { g_gpair_prof[k] = clock64(); if ((k) == 0 || (k) == 6) g_gpair_prof[8 + (k)] = gtimer_ns(); } } while (0)
 #else
+#define GP_SKIP(bit) false
 #define PPROF(k) do { } while (0)
 #endif
 
@@ -192,6 +198,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gp::kThreads, 1) k_g
         const GemmPairTail& T = P.tail;
         const bool fused = T.out != nullptr;
         if (fused) {
+            // my tile of the raw student / teacher rows was last touched by the prep kernel, four kernels and > 100 MB of L2
+            // traffic ago: pull it back into L2 while the main loop runs (128 rows x 384 columns x 2 arrays, one 128-byte line
+            // per request), so that the epilogue's loads are L2 hits instead of a DRAM burst from every CTA at once
+            {
+                const int esz = g.io_dtype == DCLIP_F32 ? 4 : 2;
+                const int lines_per_row = (min(TN, P.N - n0) * esz + 127) / 128;
+                const int total = 128 * lines_per_row;
+                for (int i = we * 32 + lane; i < total; i += kEpiWarps * 32) {
+                    const int r = i / lines_per_row, l = i - r * lines_per_row;
+                    if (m0 + r < P.M && !GP_SKIP(4)) {
+                        const size_t off = ((size_t)(m0 + r) * P.N + n0) * esz + (size_t)l * 128;
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(static_cast<const char*>(T.x) + off));
+                        if (T.t) asm volatile("prefetch.global.L2 [%0];" ::"l"(static_cast<const char*>(T.t) + off));
+                    }
+                }
+            }
             // per-row scalars of my 128 rows while the main loop runs (k_loss_grad_tail's math, loss_simt.cu):
             //   g = alpha acc + ts t,  dot = x_hat . g = alpha sum_j g_ij s_ij - w cos_i,  out = (g - x inv dot) inv grad_scale
             const int idx = we * 32 + lane;
@@ -211,39 +233,39 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gp::kThreads, 1) k_g
             }
             asm volatile("bar.sync 1, 512;" ::: "memory");
         }
+        const uint32_t stage_s = smem_u32(ring) + (uint32_t)we * 4096;
+        const int rb_row = lane >> 3, rb_chunk = lane & 7;
+        const int rbase = m0 + qd * 32;
+        const bool io16 = g.io_dtype != DCLIP_F32;
+        const uint16_t* x16 = static_cast<const uint16_t*>(T.x);
+        const uint16_t* t16 = static_cast<const uint16_t*>(T.t);
+        // fused tail, 16-bit I/O: the student / teacher elements of a chunk (8 rows x 8 B per lane and operand) are requested
+        // before the chunk's TMEM load and staging; loads issued where they are used would serialise one L2 round trip per
+        // 4 rows (measured: +40 us)
+        uint2 xq[8], tq[8];
+        auto prefetch = [&](int c0, uint2 (&xo)[8], uint2 (&to)[8]) {
+            const int ccol = n0 + c0 + rb_chunk * 4;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int row = rbase + rb_row + 4 * k;
+                xo[k] = make_uint2(0u, 0u); to[k] = make_uint2(0u, 0u);
+                if (row < P.M && ccol < P.N && !GP_SKIP(1)) {
+                    const size_t off = (size_t)row * P.N + ccol;
+                    xo[k] = __ldg(reinterpret_cast<const uint2*>(x16 + off));
+                    if (t16) to[k] = __ldg(reinterpret_cast<const uint2*>(t16 + off));
+                }
+            }
+        };
+        if (fused && io16) prefetch(part * 96, xq, tq);      // first chunk: in flight while the accumulator completes
         ok = mbar_wait(acc_full, 0, kSpin);
         ok = __all_sync(0xffffffffu, ok);
         if (we == 0 && lane == 0) PPROF(4);
         if (ok) {
             fence_after_thread_sync();
-            const uint32_t stage_s = smem_u32(ring) + (uint32_t)we * 4096;
-            const int rb_row = lane >> 3, rb_chunk = lane & 7;
-            const int rbase = m0 + qd * 32;
-            const bool io16 = g.io_dtype != DCLIP_F32;
-            const uint16_t* x16 = static_cast<const uint16_t*>(T.x);
-            const uint16_t* t16 = static_cast<const uint16_t*>(T.t);
-            // fused tail, 16-bit I/O: the student / teacher elements of a chunk (8 rows x 8 B per lane and operand) are requested
-            // before the chunk's TMEM load and staging; loads issued where they are used would serialise one L2 round trip per
-            // 4 rows (measured: +40 us)
-            uint2 xq[8], tq[8];
-            auto prefetch = [&](int c0, uint2 (&xo)[8], uint2 (&to)[8]) {
-                const int ccol = n0 + c0 + rb_chunk * 4;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int row = rbase + rb_row + 4 * k;
-                    xo[k] = make_uint2(0u, 0u); to[k] = make_uint2(0u, 0u);
-                    if (row < P.M && ccol < P.N) {
-                        const size_t off = (size_t)row * P.N + ccol;
-                        xo[k] = __ldg(reinterpret_cast<const uint2*>(x16 + off));
-                        if (t16) to[k] = __ldg(reinterpret_cast<const uint2*>(t16 + off));
-                    }
-                }
-            };
 #pragma unroll 1
             for (int c0 = part * 96; c0 < part * 96 + 96; c0 += 32) {
                 const int col = n0 + c0;
                 if (col >= P.N) break;
-                if (fused && io16) prefetch(c0, xq, tq);      // in flight across the TMEM load and the staging below
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(tmem + lane_addr + c0, r);
                 tmem_ld_wait();
@@ -286,11 +308,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gp::kThreads, 1) k_g
                             }
 #pragma unroll
                             for (int i = 0; i < 4; ++i) o[i] = (fmaf(ts, tv[i], acc[i]) - xv[i] * dx) * sc;      // (ts = 0, tv = 0 without teachers)
-                            store4_io(T.out, off, g.io_dtype, o);
+                            if (!GP_SKIP(2)) store4_io(T.out, off, g.io_dtype, o);
                         }
                     }
                 }
                 __syncwarp();
+                if (fused && io16 && c0 + 32 < part * 96 + 96 && n0 + c0 + 32 < P.N) prefetch(c0 + 32, xq, tq);      // next chunk (L2 hits)
             }
         }
     }
@@ -344,6 +367,9 @@ int launch_gemm_pair(const TcGemmProblem* probs, int count, int dtype16, cudaStr
     }
     g.total_tiles = tiles;
     g.grad_scale = grad_scale; g.io_dtype = io_dtype;
+#ifdef DCLIP_GEMM_PROF
+    { const char* e = getenv("DCLIP_GPAIR_SKIP"); g.debug_skip = e ? atoi(e) : 0; }
+#endif
     const size_t smem = 1024 + (size_t)kStages * kStageBytes + 256 + 3 * 128 * 4;
     DCLIP_CUDA_OK(cudaFuncSetAttribute(k_gemm_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_gemm_pair<<<2 * tiles, kThreads, smem, st>>>(g);

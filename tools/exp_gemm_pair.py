@@ -60,3 +60,4 @@ v = list(buf)
 names = ["entry", "setup done", "first stage full", "last stage full", "accumulator complete (epilogue sees it)", "epilogue done", "exit"]
 for i in range(1, 7):
     print(f"  {names[i]:42s} +{v[i] - v[0]:8d} cyc  (step {v[i] - v[i - 1]:8d})")
+print(f"  CTA 0 lifetime {v[14] - v[8]} ns for {v[6] - v[0]} cycles -> effective SM clock {(v[6] - v[0]) / max(1, v[14] - v[8]):.3f} GHz")
