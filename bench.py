@@ -371,7 +371,9 @@ def main():
 
 # DRAM traffic of the dominant kernel per launch comes from the committed ncu --set full capture of this very launch
 # shape (dram__bytes_read.sum + dram__bytes_write.sum); bench.py cannot read DRAM counters itself.
-NCU_TRAFFIC = {"tensor": {"bytes": 12.69e6, "source": "profiles/r1_ncu_full_loss_kernels.txt (ncu --set full of k_infonce_bwd_pair<6>, B=4096 d=768)"}}
+NCU_TRAFFIC = {"tensor": {"bytes": 89.75e6, "source": "profiles/r2_ncu_full_loss_kernels.txt (ncu --set full of k_gemm_pair, B=4096 d=768; caches flushed before "
+                                                       "the kernel, so G 33.5 MB + operands 12.6 MB + raw student / teacher rows 25.2 MB are all DRAM reads "
+                                                       "there: algorithmic bytes 71.3 MB read + 12.6 MB written; inside the step G and the operands are L2 hits)"}}
 
 
 def kernel_roofline(L, _lib, resident, B, m, d, path, rank, peaks):
