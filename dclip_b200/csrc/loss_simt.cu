@@ -125,6 +125,25 @@ __global__ void __launch_bounds__(kThreads) k_loss_prep_pair(PrepArgs a) {
 // Same, for d <= 1024: every load of the row (both students, both teachers) is issued before the first use, so a warp has
 // 4 NC 16-byte loads in flight instead of one dependent round trip per chunk (the generic kernel runs at ~40 % of the HBM
 // rate for exactly that reason), and the second pass works on registers.
+// (rows are held as the RAW 16-byte words they were loaded as - 4 NC of them per lane, all requested before the first use;
+// keeping fp32 copies instead costs 2 x the registers and makes the compiler serialise load -> convert -> load)
+template <typename T> __device__ __forceinline__ void unpack8(const uint4& raw, float (&v)[8]);
+template <> __device__ __forceinline__ void unpack8<__nv_bfloat16>(const uint4& raw, float (&v)[8]) {
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+template <> __device__ __forceinline__ void unpack8<__half>(const uint4& raw, float (&v)[8]) {
+    const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+__device__ __forceinline__ uint4 ldg_nc16(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
 template <typename T, typename OT, int NC>
 __global__ void __launch_bounds__(128) k_loss_prep_pair_nc(PrepArgs a) {
     const int lane = threadIdx.x & 31;
@@ -133,15 +152,16 @@ __global__ void __launch_bounds__(128) k_loss_prep_pair_nc(PrepArgs a) {
     const int64_t d = a.d;
     const int nch = (int)(d >> 3);
     const bool has_t = a.s[0].t != nullptr;
-    float x[2][NC][8], t[2][NC][8];
+    uint4 xr[2][NC], tr[2][NC];
 #pragma unroll
     for (int sd = 0; sd < 2; ++sd)
 #pragma unroll
         for (int k = 0; k < NC; ++k) {
             const int ch = lane + 32 * k;
+            xr[sd][k] = make_uint4(0u, 0u, 0u, 0u); tr[sd][k] = make_uint4(0u, 0u, 0u, 0u);
             if (ch < nch) {
-                load8<T>(static_cast<const T*>(a.s[sd].x) + row * d + ch * 8, x[sd][k]);
-                if (has_t) load8<T>(static_cast<const T*>(a.s[sd].t) + row * d + ch * 8, t[sd][k]);
+                xr[sd][k] = ldg_nc16(static_cast<const T*>(a.s[sd].x) + row * d + ch * 8);
+                if (has_t) tr[sd][k] = ldg_nc16(static_cast<const T*>(a.s[sd].t) + row * d + ch * 8);
             }
         }
     float nrm[2];
@@ -151,10 +171,13 @@ __global__ void __launch_bounds__(128) k_loss_prep_pair_nc(PrepArgs a) {
 #pragma unroll
         for (int k = 0; k < NC; ++k)
             if (lane + 32 * k < nch) {
+                float x[8], t[8];
+                unpack8<T>(xr[sd][k], x);
+                unpack8<T>(tr[sd][k], t);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    ss = fmaf(x[sd][k][i], x[sd][k][i], ss);
-                    if (has_t) { tt = fmaf(t[sd][k][i], t[sd][k][i], tt); xt = fmaf(x[sd][k][i], t[sd][k][i], xt); }
+                    ss = fmaf(x[i], x[i], ss);
+                    if (has_t) { tt = fmaf(t[i], t[i], tt); xt = fmaf(x[i], t[i], xt); }
                 }
             }
         ss = warp_sum(ss);
@@ -175,10 +198,12 @@ __global__ void __launch_bounds__(128) k_loss_prep_pair_nc(PrepArgs a) {
         const int ch = lane + 32 * k;
         if (ch < nch) {
             float u[8], v[8];
+            unpack8<T>(xr[0][k], u);
+            unpack8<T>(xr[1][k], v);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                u[i] = to_f32<OT>(from_f32<OT>(x[0][k][i] / nrm[0]));
-                v[i] = to_f32<OT>(from_f32<OT>(x[1][k][i] / nrm[1]));
+                u[i] = to_f32<OT>(from_f32<OT>(u[i] / nrm[0]));
+                v[i] = to_f32<OT>(from_f32<OT>(v[i] / nrm[1]));
                 dot = fmaf(u[i], v[i], dot);
             }
             store8<OT>(o0 + ch * 8, u);
@@ -549,7 +574,8 @@ __global__ void __launch_bounds__(kThreads) k_loss_grad_tail(TailArgs a) {
     }
 }
 
-// Same for d <= 1024: all loads of the row up front, the projection and the store on registers.
+// Same for d <= 1024 and 16-bit I/O: all loads of the row up front (raw 16-byte words, see k_loss_prep_pair_nc), the projection
+// and the store on registers.
 template <typename T, int NC>
 __global__ void __launch_bounds__(128) k_loss_grad_tail_nc(TailArgs a) {
     const TailSide s = a.s[blockIdx.y];
@@ -559,44 +585,51 @@ __global__ void __launch_bounds__(128) k_loss_grad_tail_nc(TailArgs a) {
     const int64_t d = a.d;
     const int nch = (int)(d >> 3);
     const bool has_t = s.t != nullptr, has_g = s.dx_hat != nullptr;
-    float x[NC][8], g[NC][8];
+    uint4 xr[NC], tr[NC];
+    float g[NC][8];
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
         const int ch = lane + 32 * k;
-        if (ch < nch) {
-            load8<T>(static_cast<const T*>(s.x) + row * d + ch * 8, x[k]);
-            if (has_g) load8<float>(s.dx_hat + row * d + ch * 8, g[k]);
-            else {
+        xr[k] = make_uint4(0u, 0u, 0u, 0u); tr[k] = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) g[k][i] = 0.f;
-            }
+        for (int i = 0; i < 8; ++i) g[k][i] = 0.f;
+        if (ch < nch) {
+            xr[k] = ldg_nc16(static_cast<const T*>(s.x) + row * d + ch * 8);
+            if (has_t) tr[k] = ldg_nc16(static_cast<const T*>(s.t) + row * d + ch * 8);
+            if (has_g) load8<float>(s.dx_hat + row * d + ch * 8, g[k]);
         }
     }
     const float inv = s.inv_norm[row];
     if (has_t) {
-        float t[NC][8];
         float tt = 0.f;
 #pragma unroll
         for (int k = 0; k < NC; ++k)
             if (lane + 32 * k < nch) {
-                load8<T>(static_cast<const T*>(s.t) + row * d + (lane + 32 * k) * 8, t[k]);
+                float t[8];
+                unpack8<T>(tr[k], t);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) tt = fmaf(t[k][i], t[k][i], tt);
+                for (int i = 0; i < 8; ++i) tt = fmaf(t[i], t[i], tt);
             }
         tt = warp_sum(tt);
         const float t_scale = -a.w_cos_over_B[blockIdx.y] / fmaxf(sqrtf(tt), kNormEps);
 #pragma unroll
         for (int k = 0; k < NC; ++k)
-            if (lane + 32 * k < nch)
+            if (lane + 32 * k < nch) {
+                float t[8];
+                unpack8<T>(tr[k], t);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) g[k][i] = fmaf(t_scale, t[k][i], g[k][i]);
+                for (int i = 0; i < 8; ++i) g[k][i] = fmaf(t_scale, t[i], g[k][i]);
+            }
     }
     float dot = 0.f;
 #pragma unroll
     for (int k = 0; k < NC; ++k)
-        if (lane + 32 * k < nch)
+        if (lane + 32 * k < nch) {
+            float x[8];
+            unpack8<T>(xr[k], x);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) dot = fmaf(x[k][i] * inv, g[k][i], dot);
+            for (int i = 0; i < 8; ++i) dot = fmaf(x[i] * inv, g[k][i], dot);
+        }
     dot = warp_sum(dot);
     if (inv >= 1.0f / kNormEps) dot = 0.f;           // clamped norm: F.normalize has no projection term
     const float scale = inv * a.grad_scale;
@@ -605,9 +638,10 @@ __global__ void __launch_bounds__(128) k_loss_grad_tail_nc(TailArgs a) {
     for (int k = 0; k < NC; ++k) {
         const int ch = lane + 32 * k;
         if (ch < nch) {
-            float o[8];
+            float x[8], o[8];
+            unpack8<T>(xr[k], x);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = (g[k][i] - x[k][i] * inv * dot) * scale;
+            for (int i = 0; i < 8; ++i) o[i] = (g[k][i] - x[i] * inv * dot) * scale;
             store8<T>(out + ch * 8, o);
         }
     }
