@@ -58,10 +58,10 @@ SIGNATURES = {
     "dclip_combine_guard_fwd": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "dclip_combine_guard_bwd": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "dclip_sharded_loss_workspace_bytes": (_sz, [_i64, _i64, _i64]),
-    "dclip_sharded_loss_prep": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _f32, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "dclip_sharded_loss_fwd": (_i32, [_vp, _vp, _i64, _i64, _i64, _f32, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "dclip_sharded_loss_prep": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _f32, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dclip_sharded_loss_fwd": (_i32, [_vp, _vp, _i64, _i64, _i64, _f32, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "dclip_sharded_loss_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _f32, _i64, _i32, _i32, _vp, _vp, _vp,
-                                      _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _sz, _vp]),
+                                      _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "dclip_p2p_flags_bytes": (_sz, []),
     "dclip_p2p_alloc": (_i32, [_sz, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p]),
     "dclip_p2p_init_flags": (_i32, [_vp, _sz, _i32]),

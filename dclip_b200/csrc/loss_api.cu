@@ -6,7 +6,9 @@
 
 using namespace dclip;
 
+namespace dclip { int* tc_error_flag(); }
 namespace {
+int* tc_error_flag_api() { return dclip::tc_error_flag(); }
 
 #ifndef DCLIP_TENSOR_PATH_READY
 #define DCLIP_TENSOR_PATH_READY 1   // validated on B200 (tests/test_loss_tensor_gpu.py)
@@ -25,6 +27,23 @@ int resolve_loss_path(int path, int dtype, int64_t B, int64_t d, float temperatu
 int resolve_block_path(int path, int op_dtype) {
     if (path != DCLIP_PATH_AUTO) return path;
     return op_dtype == DCLIP_F16 ? DCLIP_PATH_TENSOR : DCLIP_PATH_FP32;
+}
+
+// C-ABI peer description -> device-side context (world <= 1 or NULL: no in-kernel exchange)
+int make_peer_ctx(const dclip_peers* peers, PeerCtx* out) {
+    *out = PeerCtx{};
+    if (!peers || peers->world <= 1) return DCLIP_OK;
+    DCLIP_REQUIRE(peers->bases && peers->world <= kP2PMaxWorld && peers->rank >= 0 && peers->rank < peers->world, "peers: bad world / rank");
+    for (int r = 0; r < peers->world; ++r) {
+        DCLIP_REQUIRE(peers->bases[r] != nullptr, "peers: null base for rank %d", r);
+        out->base[r] = static_cast<char*>(peers->bases[r]);
+    }
+    out->world = peers->world; out->rank = peers->rank; out->flags_offset = peers->flags_offset;
+    return DCLIP_OK;
+}
+bool inside(const PeerCtx& pc, const void* p) {      // p lies inside this rank's symmetric buffer (below the flag block)
+    const char* c = static_cast<const char*>(p);
+    return c >= pc.base[pc.rank] && c < pc.base[pc.rank] + pc.flags_offset;
 }
 
 int check_common(int64_t m, int64_t d) {
@@ -280,7 +299,7 @@ size_t dclip_sharded_loss_workspace_bytes(int64_t m, int64_t n, int64_t d) {
 
 int dclip_sharded_loss_prep(const void* s_img, const void* s_txt, const void* t_img, const void* t_txt, int64_t m, int64_t d, int dtype,
                             float temperature, void* u_all, void* v_all, int64_t row_offset, float* inv_u, float* inv_v, float* cos_img,
-                            float* cos_txt, float* diag, void* stream) {
+                            float* cos_txt, float* diag, const dclip_peers* peers, void* stream) {
     if (int e = check_common(m, d)) return e;
     DCLIP_REQUIRE(s_img && s_txt && u_all && v_all && inv_u && inv_v && cos_img && cos_txt && diag, "sharded_loss_prep: null pointer");
     DCLIP_REQUIRE((t_img == nullptr) == (t_txt == nullptr), "sharded_loss_prep: give both teachers or neither");
@@ -288,12 +307,17 @@ int dclip_sharded_loss_prep(const void* s_img, const void* s_txt, const void* t_
     pa.s[0] = PrepSide{s_img, t_img, static_cast<char*>(u_all) + (size_t)row_offset * d * 2, inv_u, cos_img};
     pa.s[1] = PrepSide{s_txt, t_txt, static_cast<char*>(v_all) + (size_t)row_offset * d * 2, inv_v, cos_txt};
     pa.m = m; pa.d = d; pa.diag = diag; pa.inv_tau = 1.0f / temperature;
+    if (int e = make_peer_ctx(peers, &pa.peers)) return e;
+    if (pa.peers.world > 1) {
+        DCLIP_REQUIRE(inside(pa.peers, u_all) && inside(pa.peers, v_all), "sharded_loss_prep: u_all / v_all must live in the symmetric buffer");
+        pa.error_flag = tc_error_flag_api();
+    }
     return launch_loss_prep_pair(pa, dtype, DCLIP_F16, static_cast<cudaStream_t>(stream));
 }
 
 int dclip_sharded_loss_fwd(const void* u_all, const void* v_all, int64_t m, int64_t n, int64_t d, float temperature, int64_t row_offset,
                            const float* cos_img, const float* cos_txt, const float* diag, float* stat_row, void* workspace,
-                           size_t workspace_bytes, void* stream) {
+                           size_t workspace_bytes, const dclip_peers* peers, void* stream) {
     if (int e = check_common(m, d)) return e;
     DCLIP_REQUIRE(u_all && v_all && diag && stat_row && n >= m && m > 0, "sharded_loss_fwd: bad arguments");
     if (!tc_loss_shape_ok(d, temperature))
@@ -310,11 +334,14 @@ int dclip_sharded_loss_fwd(const void* u_all, const void* v_all, int64_t m, int6
     fa.s[0] = TcSide{nullptr, nullptr, pu};
     fa.s[1] = TcSide{nullptr, nullptr, pv};
     fa.m = m; fa.n = n; fa.d = d; fa.inv_tau = 1.0f / temperature; fa.row_offset = row_offset;
+    if (int e = make_peer_ctx(peers, &fa.peers)) return e;
+    if (fa.peers.world > 1) DCLIP_REQUIRE(inside(fa.peers, stat_row), "sharded_loss_fwd: stat_row must live in the symmetric buffer");
     const void* xs[2] = {ul, vl};
     const void* ys[2] = {v_all, u_all};
     if (int e = launch_stream_tc(0, 2, xs, ys, fa, nf, st)) return e;
     FinalizeArgs fz{pu, pv, nf, m, fa.inv_tau, stat_row, stat_row + m,
                     SumsArgs{stat_row, stat_row + m, diag, cos_img, cos_txt, m, stat_row + 2 * m, nullptr, 0.f, 0.f, 0.f}};
+    fz.peers = fa.peers;
     return launch_tc_finalize(fz, st);
 }
 
@@ -322,14 +349,17 @@ int dclip_sharded_loss_bwd(const void* s_img, const void* s_txt, const void* t_i
                            int64_t m, int64_t n, int64_t d, int dtype, float temperature, int64_t row_offset, int rank, int world,
                            const float* stat_all, const float* inv_u, const float* inv_v, float w_img, float w_txt, float w_con,
                            float grad_scale, float* losses, void* d_s_img, void* d_s_txt, void* workspace, size_t workspace_bytes,
-                           void* stream) {
+                           const dclip_peers* peers, void* stream) {
     if (int e = check_common(m, d)) return e;
     DCLIP_REQUIRE(s_img && s_txt && u_all && v_all && stat_all && inv_u && inv_v && losses, "sharded_loss_bwd: null pointer");
     DCLIP_REQUIRE(world >= 1 && rank >= 0 && rank < world && n == m * world, "sharded_loss_bwd: n must equal m * world");
     DCLIP_REQUIRE((d_s_img == nullptr) == (d_s_txt == nullptr), "sharded_loss_bwd: give both gradients or neither");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int64_t stride = 2 * m + 4;
-    if (int e = launch_sharded_losses(stat_all, world, stride, 2 * m, n, t_img != nullptr, t_txt != nullptr, w_img, w_txt, w_con, losses, st)) return e;
+    PeerCtx pc;
+    if (int e = make_peer_ctx(peers, &pc)) return e;
+    DCLIP_REQUIRE(pc.world <= 1 || d_s_img, "sharded_loss_bwd: the in-kernel peer exchange needs the gradient pass (its tail signals \"step done\")");
+    if (int e = launch_sharded_losses(stat_all, world, stride, 2 * m, n, t_img != nullptr, t_txt != nullptr, w_img, w_txt, w_con, losses, st, &pc)) return e;
     if (!d_s_img) return DCLIP_OK;
     const int nb = tc_nsplit(m, n, d, 2);
     Workspace ws(workspace, workspace_bytes);
@@ -358,6 +388,7 @@ int dclip_sharded_loss_bwd(const void* s_img, const void* s_txt, const void* t_i
     ta.s[1] = TailSide{s_txt, t_txt, inv_v, need_con ? dv_hat : nullptr, d_s_txt};
     ta.w_cos_over_B[0] = w_img / (float)n;
     ta.w_cos_over_B[1] = w_txt / (float)n;
+    ta.peers = pc;
     return launch_grad_tail(ta, 2, dtype, st);
 }
 

@@ -3,13 +3,19 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "p2p.h"
+
 namespace dclip {
 
 // A "side" is one direction of the symmetric objective: side 0 = image rows against all text
 // rows, side 1 = text rows against all image rows.  Kernels take both sides in one launch
 // (blockIdx.z / .y selects) so the single-GPU step is 6 launches.
 struct PrepSide { const void* x; const void* t; void* xhat; float* inv_norm; float* cos; float* t_inv; };   // t_inv: 1 / max(|t|, eps), optional
-struct PrepArgs { PrepSide s[2]; int64_t m, d; float* diag; float inv_tau; };   // diag: pair kernel only
+struct PrepArgs {
+    PrepSide s[2]; int64_t m, d; float* diag; float inv_tau;   // diag: pair kernel only
+    PeerCtx peers; int* error_flag;      // peers.world > 1 (register-resident pair kernel): the operand rows are also written into every peer's
+                                         // buffer (after its "step done" credit) and the last block signals kP2PKindOperands
+};
 
 // cosine terms of the rows against the teacher, students' inverse norms given (phase 2 of the split objective)
 struct CosSide { const void* x; const void* t; const float* inv_norm; float* cos; };
@@ -38,7 +44,10 @@ struct GradArgs {
 };
 
 struct TailSide { const void* x; const void* t; const float* inv_norm; const float* dx_hat; void* d_x; };
-struct TailArgs { TailSide s[2]; int64_t m, d; float w_cos_over_B[2]; float grad_scale; };
+struct TailArgs {
+    TailSide s[2]; int64_t m, d; float w_cos_over_B[2]; float grad_scale;
+    PeerCtx peers;                       // peers.world > 1: the last block tells every peer that this rank is done with the step's buffers
+};
 
 struct SumsArgs {
     const float* lse_u; const float* lse_v; const float* diag; const float* cos_img; const float* cos_txt;
@@ -71,6 +80,7 @@ struct TcArgs {
     // stream kernel: soft lockstep of concurrently running CTAs (keeps the Y tiles they share inside L2); null = off
     unsigned int* sync_ctr;   // [groups][sync_epochs], zeroed before the launch
     int sync_every, sync_group, sync_epochs;
+    PeerCtx peers;        // stream mode 0, peers.world > 1: the producers wait for every peer's operand rows before the first load
     int debug_skip;       // timing experiments only (results are garbage): 1 = no phase-1 MMAs, 2 = no phase-2 MMAs, 4 = no G stores
 };
 
@@ -118,11 +128,14 @@ struct FinalizeArgs {
     const float* part_u; const float* part_v; int nsplit; int64_t m; float inv_tau;
     float* lse_u; float* lse_v; SumsArgs sums;
     int nsplit_v;         // partial count of part_v when it differs from part_u's (0 = nsplit): column-sum partials
+    PeerCtx peers;        // peers.world > 1: lse_u / lse_v / out3 live in the symmetric buffer and are also written to every peer, then
+                          // kP2PKindStats is signalled; the kernel also retires this step's operand / done waits (expected[] += 1)
 };
 int launch_tc_finalize(const FinalizeArgs& a, cudaStream_t st);
 // global losses {total, img, txt, con} from the all-gathered per-rank raw sums stat[r * stride + off + 0..2]
+// peers (optional, world > 1): wait for every peer's statistics first (kP2PKindStats) and retire that wait
 int launch_sharded_losses(const float* stat, int world, int64_t stride, int64_t off, int64_t B, int has_img, int has_txt,
-                          float w_img, float w_txt, float w_con, float* losses, cudaStream_t st);
+                          float w_img, float w_txt, float w_con, float* losses, cudaStream_t st, const PeerCtx* peers = nullptr);
 int simt_rowlse_nsplit(int64_t m, int64_t n, int64_t d);
 int launch_rowlse_simt(LseArgs a, int nsides, cudaStream_t st);
 int launch_grad_simt(const GradArgs& a, int nsides, cudaStream_t st);

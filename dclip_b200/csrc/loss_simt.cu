@@ -148,9 +148,10 @@ template <typename T, typename OT, int NC>
 __global__ void __launch_bounds__(128) k_loss_prep_pair_nc(PrepArgs a) {
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (row >= a.m) return;
+    const bool px = a.peers.world > 1;
+    if (row >= a.m && !px) return;
     const int64_t d = a.d;
-    const int nch = (int)(d >> 3);
+    const int nch = row < a.m ? (int)(d >> 3) : 0;       // (a warp past the last row only takes part in the block's signalling)
     const bool has_t = a.s[0].t != nullptr;
     uint4 xr[2][NC], tr[2][NC];
 #pragma unroll
@@ -164,6 +165,11 @@ __global__ void __launch_bounds__(128) k_loss_prep_pair_nc(PrepArgs a) {
                 if (has_t) tr[sd][k] = ldg_nc16(static_cast<const T*>(a.s[sd].t) + row * d + ch * 8);
             }
         }
+    if (px) {
+        // my rows go straight into every peer's operand buffer: not before the peer has finished reading the previous step's
+        const unsigned int target = p2p_ld_volatile(&p2p_flags(a.peers, a.peers.rank)->expected[kP2PKindDone]) + 1;
+        p2p_wait_all_warp(a.peers, kP2PKindDone, target, a.error_flag, lane);
+    }
     float nrm[2];
 #pragma unroll
     for (int sd = 0; sd < 2; ++sd) {
@@ -184,7 +190,7 @@ __global__ void __launch_bounds__(128) k_loss_prep_pair_nc(PrepArgs a) {
         const float nx = fmaxf(sqrtf(ss), kNormEps);
         nrm[sd] = nx;
         if (has_t) { tt = warp_sum(tt); xt = warp_sum(xt); }
-        if (lane == 0) {
+        if (lane == 0 && row < a.m) {
             a.s[sd].inv_norm[row] = 1.0f / nx;
             if (a.s[sd].cos) a.s[sd].cos[row] = has_t ? xt / (nx * fmaxf(sqrtf(tt), kNormEps)) : 0.f;
             if (a.s[sd].t_inv) a.s[sd].t_inv[row] = has_t ? 1.0f / fmaxf(sqrtf(tt), kNormEps) : 0.f;
@@ -208,10 +214,21 @@ __global__ void __launch_bounds__(128) k_loss_prep_pair_nc(PrepArgs a) {
             }
             store8<OT>(o0 + ch * 8, u);
             store8<OT>(o1 + ch * 8, v);
+            if (px)
+                for (int r = 0; r < a.peers.world; ++r)
+                    if (r != a.peers.rank) {         // 512 contiguous bytes per warp and store: full NVLink write packets
+                        store8<OT>(p2p_remote(a.peers, o0 + ch * 8, r), u);
+                        store8<OT>(p2p_remote(a.peers, o1 + ch * 8, r), v);
+                    }
         }
     }
     dot = warp_sum(dot);
-    if (lane == 0 && a.diag) a.diag[row] = dot * a.inv_tau;
+    if (lane == 0 && a.diag && row < a.m) a.diag[row] = dot * a.inv_tau;
+    if (px) {
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0 && p2p_last_block(a.peers, gridDim.x)) p2p_signal_all(a.peers, kP2PKindOperands);
+    }
 }
 
 // cos(x_i, t_i) for both sides with the students' clamped inverse norms from the prep kernel (one warp per row)
@@ -247,6 +264,13 @@ __global__ void __cluster_dims__(kFinCtas, 1, 1) __launch_bounds__(kFinThreads) 
     const SumsArgs& a = f.sums;
     const uint32_t rank = tc::cluster_ctarank();
     const int nsv = f.nsplit_v > 0 ? f.nsplit_v : f.nsplit;
+    const bool px = f.peers.world > 1;
+    if (px && rank == 0 && threadIdx.x == 0) {
+        // the kernels before this one have read their targets: retire this step's "operands" and "step done" waits
+        P2PFlags* fl = p2p_flags(f.peers, f.peers.rank);
+        fl->expected[kP2PKindOperands] += 1;
+        fl->expected[kP2PKindDone] += 1;
+    }
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
     for (int64_t i = (int64_t)rank * kFinThreads + threadIdx.x; i < f.m; i += kFinCtas * kFinThreads) {
         float su = 0.f, sv = 0.f;
@@ -271,11 +295,31 @@ __global__ void __cluster_dims__(kFinCtas, 1, 1) __launch_bounds__(kFinThreads) 
         __syncthreads();
     }
     if (threadIdx.x < 3) tc::st_shared_cluster_f32(tc::mapa_u32(tc::smem_u32(&gather[rank][threadIdx.x]), 0), red[threadIdx.x][0]);
+    if (px) __threadfence();               // my lse stores are visible to the CTAs that forward them
     tc::cluster_sync_all();
+    if (px) {
+        // the statistics row {lse_u[m], lse_v[m]} (contiguous in the symmetric buffer) goes to every peer as 16-byte stores, 512
+        // contiguous bytes per warp (scattered 4-byte remote stores cost one NVLink packet each): CTA c forwards to peers c, c + 8
+        const int64_t n16 = (2 * f.m * 4) / 16, tail4 = (2 * f.m) - n16 * 4;
+        for (int r = (int)rank; r < f.peers.world; r += kFinCtas) {
+            if (r == f.peers.rank) continue;
+            const uint4* src = reinterpret_cast<const uint4*>(f.lse_u);
+            uint4* dst = reinterpret_cast<uint4*>(p2p_remote(f.peers, f.lse_u, r));
+            for (int64_t i = threadIdx.x; i < n16; i += kFinThreads) dst[i] = __ldcg(src + i);
+            if ((int64_t)threadIdx.x < tail4) p2p_remote(f.peers, f.lse_u, r)[n16 * 4 + threadIdx.x] = __ldcg(f.lse_u + n16 * 4 + threadIdx.x);
+        }
+        __threadfence_system();
+        tc::cluster_sync_all();
+    }
     if (rank == 0 && threadIdx.x == 0) {
         float t0 = 0.f, t1 = 0.f, t2 = 0.f;
         for (int r = 0; r < kFinCtas; ++r) { t0 += gather[r][0]; t1 += gather[r][1]; t2 += gather[r][2]; }
         if (a.out3) { a.out3[0] = t0; a.out3[1] = t1; a.out3[2] = t2; }   // sharded: raw local sums
+        if (px && a.out3) {
+            for (int r = 0; r < f.peers.world; ++r)
+                if (r != f.peers.rank) { float* o = p2p_remote(f.peers, a.out3, r); o[0] = t0; o[1] = t1; o[2] = t2; }
+            p2p_signal_all(f.peers, kP2PKindStats);      // (fences first) every CTA's row copies were fenced before the second cluster barrier
+        }
         if (a.losses) {
             const float l_con = t0 / (2.0f * (float)f.m);
             const float l_img = a.cos_img ? t1 / (float)f.m : 0.f;
@@ -287,11 +331,22 @@ __global__ void __cluster_dims__(kFinCtas, 1, 1) __launch_bounds__(kFinThreads) 
 }
 
 // global losses from the per-rank raw sums (fixed rank order: every rank gets the same bits)
-__global__ void k_sharded_losses(const float* __restrict__ stat, int world, int64_t stride, int64_t off, float B, int has_img, int has_txt,
-                                 float w_img, float w_txt, float w_con, float* __restrict__ losses) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__global__ void k_sharded_losses(const float* stat, int world, int64_t stride, int64_t off, float B, int has_img, int has_txt,
+                                 float w_img, float w_txt, float w_con, float* __restrict__ losses, const PeerCtx peers, int* error_flag) {
+    if (blockIdx.x != 0) return;
+    if (peers.world > 1) {
+        // one warp: lane r waits for rank r's statistics (written into my buffer by its finalize kernel), then the wait is retired
+        P2PFlags* fl = p2p_flags(peers, peers.rank);
+        const unsigned int target = p2p_ld_volatile(&fl->expected[kP2PKindStats]) + 1;
+        p2p_wait_all_warp(peers, kP2PKindStats, target, error_flag, (int)threadIdx.x);
+        if (threadIdx.x == 0) fl->expected[kP2PKindStats] = target;
+    }
+    if (threadIdx.x != 0) return;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-    for (int r = 0; r < world; ++r) { s0 += stat[r * stride + off]; s1 += stat[r * stride + off + 1]; s2 += stat[r * stride + off + 2]; }
+    for (int r = 0; r < world; ++r) {
+        const volatile float* q = stat + r * stride + off;
+        s0 += q[0]; s1 += q[1]; s2 += q[2];
+    }
     const float l_con = s0 / (2.0f * B), l_img = has_img ? s1 / B : 0.f, l_txt = has_txt ? s2 / B : 0.f;
     losses[0] = w_img * l_img + w_txt * l_txt + w_con * l_con;
     losses[1] = l_img; losses[2] = l_txt; losses[3] = l_con;
@@ -506,12 +561,22 @@ __global__ void __launch_bounds__(kThreads) k_infonce_grad(GradArgs a) {
 // ---------------------------------------------------------------------------------------------
 // tail: cosine-term gradient + normalise backward, one warp per row
 // ---------------------------------------------------------------------------------------------
+
+// sharded step with in-kernel exchange: the gradient tail is the last reader of this step's peer-written buffers (stream order) -
+// its last block tells every peer that they may be overwritten ("step done" credit of the next step's operand rows)
+__device__ __forceinline__ void tail_signal_done(const TailArgs& a) {
+    __syncthreads();                     // (nothing is published to the peers here: no per-thread system fence; p2p_signal_all fences once)
+    if (threadIdx.x == 0 && p2p_last_block(a.peers, gridDim.x * gridDim.y)) p2p_signal_all(a.peers, kP2PKindDone);
+}
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_loss_grad_tail(TailArgs a) {
     const TailSide s = a.s[blockIdx.y];
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-    if (row >= a.m) return;
+    if (row >= a.m) {
+        if (a.peers.world > 1) tail_signal_done(a);
+        return;
+    }
     const int64_t d = a.d;
     const T* x = static_cast<const T*>(s.x) + row * d;
     const T* t = s.t ? static_cast<const T*>(s.t) + row * d : nullptr;
@@ -572,6 +637,7 @@ __global__ void __launch_bounds__(kThreads) k_loss_grad_tail(TailArgs a) {
         for (int i = 0; i < 8; ++i) g[i] = (g[i] - xv[i] * inv * dot) * scale;
         store8<T>(out + k, g);
     }
+    if (a.peers.world > 1) tail_signal_done(a);
 }
 
 // Same for d <= 1024 and 16-bit I/O: all loads of the row up front (raw 16-byte words, see k_loss_prep_pair_nc), the projection
@@ -581,7 +647,10 @@ __global__ void __launch_bounds__(128) k_loss_grad_tail_nc(TailArgs a) {
     const TailSide s = a.s[blockIdx.y];
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (row >= a.m) return;
+    if (row >= a.m) {
+        if (a.peers.world > 1) tail_signal_done(a);
+        return;
+    }
     const int64_t d = a.d;
     const int nch = (int)(d >> 3);
     const bool has_t = s.t != nullptr, has_g = s.dx_hat != nullptr;
@@ -645,6 +714,7 @@ __global__ void __launch_bounds__(128) k_loss_grad_tail_nc(TailArgs a) {
             store8<T>(out + ch * 8, o);
         }
     }
+    if (a.peers.world > 1) tail_signal_done(a);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -710,8 +780,12 @@ static void launch_prep_pair_nc(const PrepArgs& a, cudaStream_t st) {
     }
 }
 
+bool loss_prep_pair_pushes(int64_t d, int dtype, int op_dtype) { return d <= 1024 && op_dtype == DCLIP_F16 && dtype != DCLIP_F32; }
+
 int launch_loss_prep_pair(const PrepArgs& a, int dtype, int op_dtype, cudaStream_t st) {
     if (a.m == 0) return DCLIP_OK;
+    if (a.peers.world > 1 && !loss_prep_pair_pushes(a.d, dtype, op_dtype))
+        return fail(DCLIP_ERR_UNSUPPORTED, "loss_prep_pair: the in-kernel peer exchange needs 16-bit inputs and d <= 1024");
     if (a.d <= 1024 && op_dtype == DCLIP_F16 && dtype != DCLIP_F32) {        // the tensor tier's shapes: register-resident rows
         if (dtype == DCLIP_BF16) launch_prep_pair_nc<__nv_bfloat16, __half>(a, st);
         else launch_prep_pair_nc<__half, __half>(a, st);
@@ -738,9 +812,13 @@ int launch_cos_rows(const CosArgs& a, int dtype, cudaStream_t st) {
     return DCLIP_OK;
 }
 
+int* tc_error_flag();   // loss_tc.cu
+
 int launch_sharded_losses(const float* stat, int world, int64_t stride, int64_t off, int64_t B, int has_img, int has_txt, float w_img,
-                          float w_txt, float w_con, float* losses, cudaStream_t st) {
-    k_sharded_losses<<<1, 32, 0, st>>>(stat, world, stride, off, (float)B, has_img, has_txt, w_img, w_txt, w_con, losses);
+                          float w_txt, float w_con, float* losses, cudaStream_t st, const PeerCtx* peers) {
+    PeerCtx pc{};
+    if (peers) pc = *peers;
+    k_sharded_losses<<<1, 32, 0, st>>>(stat, world, stride, off, (float)B, has_img, has_txt, w_img, w_txt, w_con, losses, pc, tc_error_flag());
     DCLIP_LAUNCH_OK("k_sharded_losses");
     return DCLIP_OK;
 }

@@ -17,19 +17,11 @@
 // the library's pipeline error flag and executes `trap`, so the stream never continues on stale operands and the
 // next CUDA call on this context raises (expected[] is not advanced, nothing of the next step is published).
 #include "common.cuh"
+#include "p2p.h"
 
 namespace dclip {
 
-constexpr int kP2PMaxWorld = 16;
-constexpr int kP2PKinds = 4;
 constexpr int kP2PMaxRanges = 4;
-constexpr unsigned long long kP2PTimeoutNs = 120000000000ull;
-
-struct P2PFlags {
-    unsigned int arrive[kP2PKinds][kP2PMaxWorld];
-    unsigned int expected[kP2PKinds];
-    unsigned int done_ctr;
-};
 
 struct PushArgs {
     char* base[kP2PMaxWorld];

@@ -133,6 +133,13 @@ k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CU
         if (T > 0 && elect_one()) {
             tma_prefetch_desc(tmx);
             tma_prefetch_desc(tmy);
+            if (kMode == 0 && a.peers.world > 1) {
+                // sharded forward: the Y rows of the other ranks are written into my buffer by THEIR prep kernels; wait for every
+                // peer's arrival (system-scope), then order those generic-proxy writes before my async-proxy (TMA) reads
+                const unsigned int target = p2p_ld_volatile(&p2p_flags(a.peers, a.peers.rank)->expected[kP2PKindOperands]) + 1;
+                p2p_wait_all(a.peers, kP2PKindOperands, target, a.error_flag);
+                fence_proxy_async_all();
+            }
             const int njobs = T * nkb;
             uint8_t* dst = ring + (size_t)warp * kStageBytes;
             uint32_t phase = 0;

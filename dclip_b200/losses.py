@@ -446,12 +446,20 @@ def _sharded_fused(s_img, s_txt, t_img, t_txt, temperature, w_img, w_txt, w_con,
     d_txt = torch.empty_like(s_txt) if need_grad else None
     ws = workspace(lib.dclip_sharded_loss_workspace_bytes(m, n, d), dev)
     has_t = t_img is not None
+    # in-kernel exchange: the prep / finalize / tail kernels write to the peers and signal, their consumers wait in their
+    # prologues - no push kernels, nothing between the three calls (16-bit inputs, gradients requested; DCLIP_SHARDED_PUSH=1
+    # keeps the separate push kernels)
+    fused_x = (pb is not None and need_grad and s_img.dtype != torch.float32 and d <= 1024
+               and os.environ.get("DCLIP_SHARDED_PUSH", "0") != "1")
+    peers = pb.peers_arg() if fused_x else None
     with torch.cuda.device(dev):
         st = stream_ptr(dev)
         check(lib.dclip_sharded_loss_prep(ptr(s_img), ptr(s_txt), ptr(t_img), ptr(t_txt), m, d, dtype_code(s_img),
                                           float(temperature), p_u, p_v, row_offset, ptr(vecs[0]), ptr(vecs[1]),
-                                          ptr(vecs[2]), ptr(vecs[3]), ptr(vecs[4]), st), "sharded_loss_prep")
-        if pb is not None:
+                                          ptr(vecs[2]), ptr(vecs[3]), ptr(vecs[4]), peers, st), "sharded_loss_prep")
+        if fused_x:
+            pass
+        elif pb is not None:
             rows = (row_offset * d * 2, m * d * 2)
             # my rows -> every peer (after the peers have finished reading the previous step's operands)
             pb.push([rows, (ops_bytes + rows[0], rows[1])], KIND_DONE, KIND_OPERANDS, wait_after=True)
@@ -460,16 +468,18 @@ def _sharded_fused(s_img, s_txt, t_img, t_txt, temperature, w_img, w_txt, w_con,
             dist.all_gather_into_tensor(v_all, v_all[row_offset:row_offset + m], group=group)
         check(lib.dclip_sharded_loss_fwd(p_u, p_v, m, n, d, float(temperature), row_offset,
                                          ptr(vecs[2]) if has_t else None, ptr(vecs[3]) if has_t else None, ptr(vecs[4]),
-                                         p_stat_row, ptr(ws), ws.numel(), st), "sharded_loss_fwd")
-        if pb is not None:
+                                         p_stat_row, ptr(ws), ws.numel(), peers, st), "sharded_loss_fwd")
+        if fused_x:
+            pass
+        elif pb is not None:
             pb.push([(2 * ops_bytes + rank * stride * 4, stride * 4)], -1, KIND_STATS, wait_after=True)
         elif world > 1:
             dist.all_gather_into_tensor(stat.view(-1), stat[rank], group=group)
         check(lib.dclip_sharded_loss_bwd(ptr(s_img), ptr(s_txt), ptr(t_img), ptr(t_txt), p_u, p_v, m, n, d,
                                          dtype_code(s_img), float(temperature), row_offset, rank, world, p_stat, ptr(vecs[0]),
                                          ptr(vecs[1]), float(w_img), float(w_txt), float(w_con), float(grad_scale), ptr(losses),
-                                         ptr(d_img), ptr(d_txt), ptr(ws), ws.numel(), st), "sharded_loss_bwd")
-        if pb is not None:
+                                         ptr(d_img), ptr(d_txt), ptr(ws), ws.numel(), peers, st), "sharded_loss_bwd")
+        if pb is not None and not fused_x:
             pb.push([], -1, KIND_DONE)           # my reads of this step's operands / statistics are stream-ordered before this
     return losses, d_img, d_txt
 

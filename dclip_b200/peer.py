@@ -15,6 +15,11 @@ from ._lib import check, stream_ptr
 KIND_OPERANDS, KIND_STATS, KIND_DONE = 0, 1, 2
 
 
+class _Peers(ctypes.Structure):
+    """dclip_peers (include/dclip_b200.h): the ranks' buffers as mapped into this process."""
+    _fields_ = [("bases", ctypes.POINTER(ctypes.c_void_p)), ("world", ctypes.c_int), ("rank", ctypes.c_int), ("flags_offset", ctypes.c_size_t)]
+
+
 class PeerSetupError(RuntimeError):
     """The symmetric buffer could not be set up; raised on EVERY rank of the group together."""
 
@@ -72,6 +77,7 @@ class PeerBuffer:
                 err = str(e)
             agree(err is None, err)          # doubles as the barrier: every rank has initialised its flags and mapped its peers
         self._peer_arr = (ctypes.c_void_p * self.world)(*self.peers)
+        self._peers_struct = _Peers(ctypes.cast(self._peer_arr, ctypes.POINTER(ctypes.c_void_p)), self.world, self.rank, self.flags_offset)
         self._closed = False
 
     def _release(self):
@@ -86,6 +92,10 @@ class PeerBuffer:
 
     def ptr(self, offset=0):
         return ctypes.c_void_p(self.base + offset)
+
+    def peers_arg(self):
+        """Pointer to the dclip_peers struct of this buffer (for the entry points that do their exchange in-kernel)."""
+        return ctypes.cast(ctypes.pointer(self._peers_struct), ctypes.c_void_p)
 
     def push(self, ranges, wait_kind, signal_kind, wait_after=False):
         """ranges: [(offset, nbytes), ...] of the local buffer, written to the same offsets of every peer.

@@ -171,19 +171,28 @@ int dclip_loss_partial_sums(const float* lse_u, const float* lse_v, const float*
  * host's all-gathers in between.  u_all / v_all: float16 [n, d] gather buffers (this rank writes rows
  * [row_offset, row_offset + m) in _prep, the host all-gathers them in place).  stat: float [world][2m + 4]
  * gather buffer; _fwd fills this rank's row {lse_u[m], lse_v[m], 3 raw loss sums}, the host all-gathers it,
- * _bwd reads every rank's row (blocked lse lookup inside the kernel, global losses from the raw sums). */
+ * _bwd reads every rank's row (blocked lse lookup inside the kernel, global losses from the raw sums).
+ *
+ * `peers` (NULL or world <= 1: none): the exchanges happen INSIDE these kernels over NVLink peer memory and the host does
+ * nothing between the calls.  u_all / v_all / stat then live in the rank's symmetric buffer (dclip_p2p_alloc; same layout on
+ * every rank; bases[r] = rank r's buffer as mapped here, bases[rank] = the local one; flag block at flags_offset):
+ *   _prep  waits for every peer's "step done" credit, writes its normalised rows into EVERY rank's u_all / v_all and signals;
+ *   _fwd   waits (TMA producers) for every peer's rows, writes its statistics row into every rank's stat and signals;
+ *   _bwd   waits for every peer's statistics, and its gradient tail signals "step done" (gradients are mandatory here).
+ * 16-bit inputs with d <= 1024 only.  A peer that never arrives is fatal (see the push / wait kernels below). */
+typedef struct dclip_peers { void* const* bases; int world; int rank; size_t flags_offset; } dclip_peers;
 size_t dclip_sharded_loss_workspace_bytes(int64_t m, int64_t n, int64_t d);
 int dclip_sharded_loss_prep(const void* s_img, const void* s_txt, const void* t_img, const void* t_txt, int64_t m, int64_t d,
                             int dtype, float temperature, void* u_all, void* v_all, int64_t row_offset, float* inv_u,
-                            float* inv_v, float* cos_img, float* cos_txt, float* diag, void* stream);
+                            float* inv_v, float* cos_img, float* cos_txt, float* diag, const dclip_peers* peers, void* stream);
 int dclip_sharded_loss_fwd(const void* u_all, const void* v_all, int64_t m, int64_t n, int64_t d, float temperature,
                            int64_t row_offset, const float* cos_img, const float* cos_txt, const float* diag, float* stat_row,
-                           void* workspace, size_t workspace_bytes, void* stream);
+                           void* workspace, size_t workspace_bytes, const dclip_peers* peers, void* stream);
 int dclip_sharded_loss_bwd(const void* s_img, const void* s_txt, const void* t_img, const void* t_txt, const void* u_all,
                            const void* v_all, int64_t m, int64_t n, int64_t d, int dtype, float temperature, int64_t row_offset,
                            int rank, int world, const float* stat_all, const float* inv_u, const float* inv_v, float w_img,
                            float w_txt, float w_con, float grad_scale, float* losses, void* d_s_img, void* d_s_txt,
-                           void* workspace, size_t workspace_bytes, void* stream);
+                           void* workspace, size_t workspace_bytes, const dclip_peers* peers, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Push-based exchange over NVLink peer memory (replaces NCCL's all-gathers in the data-parallel objective;

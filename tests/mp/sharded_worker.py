@@ -31,6 +31,13 @@ def main():
             l3, di3, dt3 = L.sharded_distill_loss_fwd_bwd(*loc, path=path, comm="nccl")
             torch.cuda.synchronize()
             assert torch.equal(l3, losses) and torch.equal(di3, di) and torch.equal(dt3, dt), "p2p vs nccl exchange differ"
+            # the separate push / wait kernels instead of the exchange inside the prep / finalize / tail kernels: bit-identical
+            os.environ["DCLIP_SHARDED_PUSH"] = "1"
+            for _ in range(3):
+                l6, di6, dt6 = L.sharded_distill_loss_fwd_bwd(*loc, path=path)
+            os.environ.pop("DCLIP_SHARDED_PUSH")
+            torch.cuda.synchronize()
+            assert torch.equal(l6, losses) and torch.equal(di6, di) and torch.equal(dt6, dt), "push kernels vs in-kernel exchange differ"
             for _ in range(20):                                                  # flag counters over many steps
                 l4, di4, dt4 = L.sharded_distill_loss_fwd_bwd(*loc, path=path)
             torch.cuda.synchronize()
