@@ -127,11 +127,23 @@ def test_16bit_tensor_tier_forward_backward(built_library, dtype):
     b64 = image.double().requires_grad_(True)
     ref = om.global_embedding(p64, a64, b64, heads)
     (ref * w.double()).sum().backward()
-    tol = 2e-2 if dtype == torch.bfloat16 else 4e-3
-    assert _rel(glob, ref) < tol
-    assert _rel(a.grad, a64.grad) < tol and _rel(b.grad, b64.grad) < tol
-    for k, p in m.cross_modal_attention.named_parameters():
-        assert _rel(p.grad, p64[k].grad) < tol, (k, _rel(p.grad, p64[k].grad))
+    # measured on B200: ours 2.5e-3 .. 4.1e-3 (bf16) / 3.0e-4 .. 5.1e-4 (fp16), torch eager in the same dtype 4.8e-3 .. 6.6e-3 /
+    # 6.5e-4 .. 8.3e-4 (fp32 statistics and fp32 accumulation in TMEM are why ours is the smaller one)
+    tol = 8e-3 if dtype == torch.bfloat16 else 1.5e-3
+    # What does a 16-bit tier cost at all?  The SAME reference math (torch ops, nn.MultiheadAttention's formulas) run by torch
+    # in this dtype on the GPU, against the same fp64 oracle: our error must stay within 2x of torch's own for every tensor.
+    p16 = {k: v.to(dtype).to(DEV).requires_grad_(True) for k, v in params.items()}
+    a16 = text.to(DEV).requires_grad_(True)
+    b16 = image.to(DEV).requires_grad_(True)
+    ref16 = om.global_embedding(p16, a16, b16, heads)
+    (ref16.float() * w.to(DEV)).sum().backward()
+    checks = [("global", glob, ref16, ref), ("d_text", a.grad, a16.grad, a64.grad), ("d_image", b.grad, b16.grad, b64.grad)]
+    checks += [(k, p.grad, p16[k].grad, p64[k].grad) for k, p in m.cross_modal_attention.named_parameters()]
+    for name, ours, torch16, want in checks:
+        e_ours, e_torch = _rel(ours, want), _rel(torch16, want)
+        print(f"[xattn 16-bit tier] {dtype} {name}: ours {e_ours:.3e}  torch in the same dtype {e_torch:.3e}")
+        assert e_ours < tol, (name, e_ours)
+        assert e_ours < 2.0 * e_torch + 1e-3, (name, e_ours, e_torch)
 
 
 def test_nan_guard_zeroes_whole_tensor(built_library):
