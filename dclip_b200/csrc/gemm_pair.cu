@@ -38,6 +38,7 @@ constexpr int kStageBytes = kAStage + kBStage;   // 40 KB
 constexpr int kEpiWarps = 16;               // four per TMEM lane quadrant, 96 columns each
 constexpr int kThreads = (kStages + 1 + kEpiWarps) * 32;
 constexpr uint32_t kSpin = 1u << 24;
+constexpr int kLateBlocks = 12;                  // ~10 k cycles of MMAs: long enough to pull 196 KB per SM from DRAM with every SM asking
 }  // namespace gp
 
 struct GemmPairDev {
@@ -87,6 +88,101 @@ __device__ __forceinline__ void store4_io(void* base, size_t idx, int io, const 
     }
 }
 
+
+// 4 consecutive 16-bit elements (bf16 or fp16) of a row <-> fp32
+template <bool kBf16> __device__ __forceinline__ void unpack4_16(const uint2& q, float (&v)[4]) {
+    if (kBf16) {
+        v[0] = __uint_as_float(q.x << 16); v[1] = __uint_as_float(q.x & 0xffff0000u);
+        v[2] = __uint_as_float(q.y << 16); v[3] = __uint_as_float(q.y & 0xffff0000u);
+    } else {
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&q.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    }
+}
+template <bool kBf16> __device__ __forceinline__ uint2 pack4_16(const float (&v)[4]) {
+    uint2 q;
+    if (kBf16) {
+        const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+        q.x = *reinterpret_cast<const uint32_t*>(&a); q.y = *reinterpret_cast<const uint32_t*>(&b);
+    } else {
+        const __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+        q.x = *reinterpret_cast<const uint32_t*>(&a); q.y = *reinterpret_cast<const uint32_t*>(&b);
+    }
+    return q;
+}
+
+// Fused gradient tail for 16-bit I/O, one warp: 96 columns of 32 rows in three 32-column chunks.
+//   out = acc * A_r + t * T_r - x * X_r     with the per-row float4 {A, T, X, -} = {alpha, ts, inv dot} * inv * grad_scale in shared memory
+// The accumulator chunk goes through the warp's swizzled 4 KB staging buffer (thread = row on the way in, 8 lanes per row on
+// the way out); the student / teacher elements a lane needs (8 rows x 8 B per operand and chunk) are requested BEFORE the chunk's
+// TMEM load - loads issued where they are used serialise one L2 round trip per 4 rows (measured: +40 us).
+template <bool kBf16>
+__device__ __forceinline__ void fused_tail_epilogue16(uint32_t tmem_rows, uint32_t stage_s, const float4* row_sc4, int qd, int lane, int rbase, int n0,
+                                                      int c_begin, int M, int N, const uint16_t* __restrict__ x16, const uint16_t* __restrict__ t16,
+                                                      uint16_t* __restrict__ out16, bool skip_loads, bool skip_stores, bool skip_tmem = false,
+                                                      bool skip_stage = false) {
+    const int rb_row = lane >> 3, rb_chunk = lane & 7;
+    int rowoff[8];          // element offset of my 8 rows (row k of a pass = rb_row + 4 k); -1 = past M
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int row = rbase + rb_row + 4 * k;
+        rowoff[k] = row < M ? row * N : -1;
+    }
+    uint2 xq[8], tq[8];
+    auto prefetch = [&](int c0) {
+        const int ccol = n0 + c0 + rb_chunk * 4;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            xq[k] = make_uint2(0u, 0u); tq[k] = make_uint2(0u, 0u);
+            if (rowoff[k] >= 0 && ccol < N && !skip_loads) {
+                xq[k] = __ldg(reinterpret_cast<const uint2*>(x16 + rowoff[k] + ccol));
+                if (t16) tq[k] = __ldg(reinterpret_cast<const uint2*>(t16 + rowoff[k] + ccol));
+            }
+        }
+    };
+    prefetch(c_begin);
+#pragma unroll 1
+    for (int c0 = c_begin; c0 < c_begin + 96; c0 += 32) {
+        if (n0 + c0 >= N) break;
+        uint32_t r[32];
+        if (!skip_tmem) {
+            tmem_ld_32x32b_x32(tmem_rows + c0, r);
+            tmem_ld_wait();
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = (uint32_t)(c0 + i + lane);
+        }
+        if (!skip_stage) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_s + lane * 128 + ((q ^ (lane & 7)) << 4)), "r"(r[q * 4]), "r"(r[q * 4 + 1]),
+                         "r"(r[q * 4 + 2]), "r"(r[q * 4 + 3]) : "memory");
+        }
+        __syncwarp();
+        const int ccol = n0 + c0 + rb_chunk * 4;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int rr = rb_row + 4 * k;
+            uint4 a4;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a4.x), "=r"(a4.y), "=r"(a4.z), "=r"(a4.w)
+                         : "r"(stage_s + rr * 128 + ((rb_chunk ^ (rr & 7)) << 4)) : "memory");
+            if (rowoff[k] >= 0 && ccol < N) {
+                const float4 sc = row_sc4[qd * 32 + rr];
+                float xv[4], tv[4], o[4];
+                unpack4_16<kBf16>(xq[k], xv);
+                unpack4_16<kBf16>(tq[k], tv);
+                o[0] = fmaf(__uint_as_float(a4.x), sc.x, fmaf(tv[0], sc.y, -xv[0] * sc.z));
+                o[1] = fmaf(__uint_as_float(a4.y), sc.x, fmaf(tv[1], sc.y, -xv[1] * sc.z));
+                o[2] = fmaf(__uint_as_float(a4.z), sc.x, fmaf(tv[2], sc.y, -xv[2] * sc.z));
+                o[3] = fmaf(__uint_as_float(a4.w), sc.x, fmaf(tv[3], sc.y, -xv[3] * sc.z));
+                if (!skip_stores) *reinterpret_cast<uint2*>(out16 + rowoff[k] + ccol) = pack4_16<kBf16>(o);
+            }
+        }
+        __syncwarp();
+        if (c0 + 32 < c_begin + 96 && n0 + c0 + 32 < N) prefetch(c0 + 32);      // next chunk (L2 hits: the tile was prefetched at kernel start)
+    }
+}
+
 #ifdef DCLIP_GEMM_PROF
 #define GP_SKIP(bit) (g.debug_skip & (bit))
 __device__ long long g_gpair_prof[16];
@@ -104,8 +200,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gp::kThreads, 1) k_g
     uint64_t* full = reinterpret_cast<uint64_t*>(ring + kStages * kStageBytes);   // (leader) bytes of both CTAs
     uint64_t* empty = full + kStages;                                            // both CTAs (multicast commit)
     uint64_t* acc_full = empty + kStages;                                        // both CTAs
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 1);
-    float* row_sc = reinterpret_cast<float*>(ring + kStages * kStageBytes + 256);   // fused tail: [3][128] per-row scalars
+    uint64_t* late = acc_full + 1;                                               // both CTAs: kLateBlocks k-blocks before the end of the K loop
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(late + 1);
+    float* row_sc = reinterpret_cast<float*>(ring + kStages * kStageBytes + 256);   // fused tail: float4[128] per-row scalars
     const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const uint32_t cr = cluster_ctarank();
 
@@ -122,6 +219,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gp::kThreads, 1) k_g
     if (threadIdx.x == 0) {
         for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         mbar_init(acc_full, 1);
+        mbar_init(late, 1);
         fence_barrier_init();
     }
     if (warp == kStages) tmem_alloc_pair(tmem_ptr, 512);
@@ -183,6 +281,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gp::kThreads, 1) k_g
                     umma_f16_pair(tmem + 256, da0 + (uint64_t)(ks * stepA), db2 + (uint64_t)(ks * stepB), idesc2, (kb | ks) != 0);
                 }
                 umma_commit_pair(&empty[stage]);
+                if (kb == max(0, nkb - 1 - kLateBlocks)) umma_commit_pair(late);      // wakes the epilogue warps' L2 prefetch (below)
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
             umma_commit_pair(acc_full);
@@ -198,9 +297,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gp::kThreads, 1) k_g
         const GemmPairTail& T = P.tail;
         const bool fused = T.out != nullptr;
         if (fused) {
-            // my tile of the raw student / teacher rows was last touched by the prep kernel, four kernels and > 100 MB of L2
-            // traffic ago: pull it back into L2 while the main loop runs (128 rows x 384 columns x 2 arrays, one 128-byte line
-            // per request), so that the epilogue's loads are L2 hits instead of a DRAM burst from every CTA at once
+            // per-row scalars of my 128 rows while the main loop runs (k_loss_grad_tail's math, loss_simt.cu):
+            //   g = alpha acc + ts t,  dot = x_hat . g = alpha sum_j g_ij s_ij - w cos_i,  out = (g - x inv dot) inv grad_scale
+            const int idx = we * 32 + lane;
+            if (idx < 128) {
+                const int row = m0 + idx;
+                float sc = 0.f, ts = 0.f, dx = 0.f;      // inv grad_scale, -w / |t|, inv dot
+                if (row < P.M) {
+                    float r = 0.f;
+                    for (int q = 0; q < T.dot_count; ++q) r += T.dot_part[(size_t)q * T.dot_stride + row];
+                    const float inv = T.inv_norm[row];
+                    float dot = P.alpha * r;
+                    if (T.t) { ts = -T.w_cos_over_B * T.t_inv[row]; dot -= T.w_cos_over_B * T.cos[row]; }
+                    if (inv >= 1.0f / kPairNormEps) dot = 0.f;      // clamped norm: F.normalize has no projection term
+                    sc = inv * g.grad_scale; dx = inv * dot;
+                }
+                // out = acc * (alpha sc) + t * (ts sc) - x * (dx sc): three FMAs per element in the epilogue
+                reinterpret_cast<float4*>(row_sc)[idx] = make_float4(P.alpha * sc, ts * sc, dx * sc, 0.f);
+            }
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            // my tile of the raw student / teacher rows was last touched by the prep kernel, four kernels and > 300 MB of L2 traffic
+            // ago, and a prefetch issued at kernel start is evicted again by the operand stream (measured: no gain).  Pull it into
+            // L2 when the K loop is kLateBlocks k-blocks from its end (128 rows x 384 columns x 2 arrays, one 128-byte line per
+            // request): the epilogue's loads are then L2 hits instead of a 25 MB DRAM burst from every CTA at once.
+            ok = mbar_wait(late, 0, kSpin);
             {
                 const int esz = g.io_dtype == DCLIP_F32 ? 4 : 2;
                 const int lines_per_row = (min(TN, P.N - n0) * esz + 127) / 128;
@@ -214,106 +334,68 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gp::kThreads, 1) k_g
                     }
                 }
             }
-            // per-row scalars of my 128 rows while the main loop runs (k_loss_grad_tail's math, loss_simt.cu):
-            //   g = alpha acc + ts t,  dot = x_hat . g = alpha sum_j g_ij s_ij - w cos_i,  out = (g - x inv dot) inv grad_scale
-            const int idx = we * 32 + lane;
-            if (idx < 128) {
-                const int row = m0 + idx;
-                float sc = 0.f, ts = 0.f, dx = 0.f;
-                if (row < P.M) {
-                    float r = 0.f;
-                    for (int q = 0; q < T.dot_count; ++q) r += T.dot_part[(size_t)q * T.dot_stride + row];
-                    const float inv = T.inv_norm[row];
-                    float dot = P.alpha * r;
-                    if (T.t) { ts = -T.w_cos_over_B * T.t_inv[row]; dot -= T.w_cos_over_B * T.cos[row]; }
-                    if (inv >= 1.0f / kPairNormEps) dot = 0.f;      // clamped norm: F.normalize has no projection term
-                    sc = inv * g.grad_scale; dx = inv * dot;
-                }
-                row_sc[idx] = sc; row_sc[128 + idx] = ts; row_sc[256 + idx] = dx;
-            }
-            asm volatile("bar.sync 1, 512;" ::: "memory");
         }
         const uint32_t stage_s = smem_u32(ring) + (uint32_t)we * 4096;
         const int rb_row = lane >> 3, rb_chunk = lane & 7;
         const int rbase = m0 + qd * 32;
         const bool io16 = g.io_dtype != DCLIP_F32;
-        const uint16_t* x16 = static_cast<const uint16_t*>(T.x);
-        const uint16_t* t16 = static_cast<const uint16_t*>(T.t);
-        // fused tail, 16-bit I/O: the student / teacher elements of a chunk (8 rows x 8 B per lane and operand) are requested
-        // before the chunk's TMEM load and staging; loads issued where they are used would serialise one L2 round trip per
-        // 4 rows (measured: +40 us)
-        uint2 xq[8], tq[8];
-        auto prefetch = [&](int c0, uint2 (&xo)[8], uint2 (&to)[8]) {
-            const int ccol = n0 + c0 + rb_chunk * 4;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int row = rbase + rb_row + 4 * k;
-                xo[k] = make_uint2(0u, 0u); to[k] = make_uint2(0u, 0u);
-                if (row < P.M && ccol < P.N && !GP_SKIP(1)) {
-                    const size_t off = (size_t)row * P.N + ccol;
-                    xo[k] = __ldg(reinterpret_cast<const uint2*>(x16 + off));
-                    if (t16) to[k] = __ldg(reinterpret_cast<const uint2*>(t16 + off));
-                }
-            }
-        };
-        if (fused && io16) prefetch(part * 96, xq, tq);      // first chunk: in flight while the accumulator completes
-        ok = mbar_wait(acc_full, 0, kSpin);
+        ok = mbar_wait(acc_full, 0, kSpin) && ok;
         ok = __all_sync(0xffffffffu, ok);
         if (we == 0 && lane == 0) PPROF(4);
         if (ok) {
             fence_after_thread_sync();
+            if (fused && io16) {
+                // (16-bit I/O: the epilogue that matters - the first chunk's loads could sit above the accumulator wait, but they are
+                //  L2 hits by now and the wait is short: measured no difference)
+                const float4* sc4 = reinterpret_cast<const float4*>(row_sc);
+                if (g.io_dtype == DCLIP_BF16)
+                    fused_tail_epilogue16<true>(tmem + lane_addr, stage_s, sc4, qd, lane, rbase, n0, part * 96, P.M, P.N, static_cast<const uint16_t*>(T.x),
+                                                static_cast<const uint16_t*>(T.t), static_cast<uint16_t*>(T.out), GP_SKIP(1), GP_SKIP(2), GP_SKIP(8), GP_SKIP(16));
+                else
+                    fused_tail_epilogue16<false>(tmem + lane_addr, stage_s, sc4, qd, lane, rbase, n0, part * 96, P.M, P.N, static_cast<const uint16_t*>(T.x),
+                                                 static_cast<const uint16_t*>(T.t), static_cast<uint16_t*>(T.out), GP_SKIP(1), GP_SKIP(2));
+            } else {
+                // plain fp32 C (alpha applied), or the fused tail with fp32 I/O (rare: tests)
 #pragma unroll 1
-            for (int c0 = part * 96; c0 < part * 96 + 96; c0 += 32) {
-                const int col = n0 + c0;
-                if (col >= P.N) break;
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(tmem + lane_addr + c0, r);
-                tmem_ld_wait();
+                for (int c0 = part * 96; c0 < part * 96 + 96; c0 += 32) {
+                    const int col = n0 + c0;
+                    if (col >= P.N) break;
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(tmem + lane_addr + c0, r);
+                    tmem_ld_wait();
+                    const float al = fused ? 1.0f : P.alpha;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const uint4 v = make_uint4(__float_as_uint(__uint_as_float(r[q * 4]) * P.alpha), __float_as_uint(__uint_as_float(r[q * 4 + 1]) * P.alpha),
-                                               __float_as_uint(__uint_as_float(r[q * 4 + 2]) * P.alpha), __float_as_uint(__uint_as_float(r[q * 4 + 3]) * P.alpha));
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_s + lane * 128 + ((q ^ (lane & 7)) << 4)), "r"(v.x), "r"(v.y),
-                                 "r"(v.z), "r"(v.w) : "memory");
-                }
-                __syncwarp();
-                const int ccol = col + rb_chunk * 4;
+                    for (int q = 0; q < 8; ++q) {
+                        const uint4 v = make_uint4(__float_as_uint(__uint_as_float(r[q * 4]) * al), __float_as_uint(__uint_as_float(r[q * 4 + 1]) * al),
+                                                   __float_as_uint(__uint_as_float(r[q * 4 + 2]) * al), __float_as_uint(__uint_as_float(r[q * 4 + 3]) * al));
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_s + lane * 128 + ((q ^ (lane & 7)) << 4)), "r"(v.x), "r"(v.y),
+                                     "r"(v.z), "r"(v.w) : "memory");
+                    }
+                    __syncwarp();
+                    const int ccol = col + rb_chunk * 4;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int rr = rb_row + 4 * k;
-                    uint4 x;
-                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w)
-                                 : "r"(stage_s + rr * 128 + ((rb_chunk ^ (rr & 7)) << 4)) : "memory");
-                    if (rbase + rr < P.M && ccol < P.N) {
-                        if (!fused) *reinterpret_cast<uint4*>(P.C + (size_t)(rbase + rr) * P.ldc + ccol) = x;
-                        else {
-                            const int lr = qd * 32 + rr;
-                            const float sc = row_sc[lr], ts = row_sc[128 + lr], dx = row_sc[256 + lr];
-                            const size_t off = (size_t)(rbase + rr) * P.N + ccol;
-                            const float acc[4] = {__uint_as_float(x.x), __uint_as_float(x.y), __uint_as_float(x.z), __uint_as_float(x.w)};
-                            float xv[4], tv[4] = {0.f, 0.f, 0.f, 0.f}, o[4];
-                            if (io16) {
-                                if (g.io_dtype == DCLIP_BF16) {
-                                    const float2 a0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xq[k].x)), a1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xq[k].y));
-                                    const float2 b0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&tq[k].x)), b1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&tq[k].y));
-                                    xv[0] = a0.x; xv[1] = a0.y; xv[2] = a1.x; xv[3] = a1.y; tv[0] = b0.x; tv[1] = b0.y; tv[2] = b1.x; tv[3] = b1.y;
-                                } else {
-                                    const float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(&xq[k].x)), a1 = __half22float2(*reinterpret_cast<const __half2*>(&xq[k].y));
-                                    const float2 b0 = __half22float2(*reinterpret_cast<const __half2*>(&tq[k].x)), b1 = __half22float2(*reinterpret_cast<const __half2*>(&tq[k].y));
-                                    xv[0] = a0.x; xv[1] = a0.y; xv[2] = a1.x; xv[3] = a1.y; tv[0] = b0.x; tv[1] = b0.y; tv[2] = b1.x; tv[3] = b1.y;
-                                }
-                            } else {
+                    for (int k = 0; k < 8; ++k) {
+                        const int rr = rb_row + 4 * k;
+                        uint4 x;
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w)
+                                     : "r"(stage_s + rr * 128 + ((rb_chunk ^ (rr & 7)) << 4)) : "memory");
+                        if (rbase + rr < P.M && ccol < P.N) {
+                            if (!fused) *reinterpret_cast<uint4*>(P.C + (size_t)(rbase + rr) * P.ldc + ccol) = x;
+                            else {
+                                const float4 sc = reinterpret_cast<const float4*>(row_sc)[qd * 32 + rr];
+                                const size_t off = (size_t)(rbase + rr) * P.N + ccol;
+                                const float acc[4] = {__uint_as_float(x.x), __uint_as_float(x.y), __uint_as_float(x.z), __uint_as_float(x.w)};
+                                float xv[4], tv[4] = {0.f, 0.f, 0.f, 0.f}, o[4];
                                 load4_io(T.x, off, g.io_dtype, xv);
                                 if (T.t) load4_io(T.t, off, g.io_dtype, tv);
-                            }
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) o[i] = (fmaf(ts, tv[i], acc[i]) - xv[i] * dx) * sc;      // (ts = 0, tv = 0 without teachers)
-                            if (!GP_SKIP(2)) store4_io(T.out, off, g.io_dtype, o);
+                                for (int i = 0; i < 4; ++i) o[i] = fmaf(acc[i], sc.x, fmaf(tv[i], sc.y, -xv[i] * sc.z));
+                                store4_io(T.out, off, g.io_dtype, o);
+                            }
                         }
                     }
+                    __syncwarp();
                 }
-                __syncwarp();
-                if (fused && io16 && c0 + 32 < part * 96 + 96 && n0 + c0 + 32 < P.N) prefetch(c0 + 32, xq, tq);      // next chunk (L2 hits)
             }
         }
     }
@@ -356,6 +438,7 @@ int launch_gemm_pair(const TcGemmProblem* probs, int count, int dtype16, cudaStr
         GemmPairDev& d = g.p[i];
         d.C = q.C; d.M = q.M; d.N = q.N; d.K = q.K; d.ldc = q.ldc; d.a_mn = q.a_mn; d.b_mn = q.b_mn;
         d.alpha = q.alpha == 0.f ? 1.0f : q.alpha;
+        if (tails && (long long)q.M * q.N >= (1ll << 31)) return fail(DCLIP_ERR_UNSUPPORTED, "gemm_pair: fused tail needs M * N < 2^31");
         if (tails) {
             d.tail = tails[i];
             if (!d.tail.out || !d.tail.x || !d.tail.inv_norm || !d.tail.dot_part || (d.tail.t && (!d.tail.cos || !d.tail.t_inv)))
@@ -370,7 +453,7 @@ int launch_gemm_pair(const TcGemmProblem* probs, int count, int dtype16, cudaStr
 #ifdef DCLIP_GEMM_PROF
     { const char* e = getenv("DCLIP_GPAIR_SKIP"); g.debug_skip = e ? atoi(e) : 0; }
 #endif
-    const size_t smem = 1024 + (size_t)kStages * kStageBytes + 256 + 3 * 128 * 4;
+    const size_t smem = 1024 + (size_t)kStages * kStageBytes + 256 + 4 * 128 * 4;
     DCLIP_CUDA_OK(cudaFuncSetAttribute(k_gemm_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_gemm_pair<<<2 * tiles, kThreads, smem, st>>>(g);
     DCLIP_LAUNCH_OK("k_gemm_pair");
