@@ -205,7 +205,14 @@ def main():
     resident = [t.to(dev) for t in host]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
     flush_rd = torch.zeros(32 * 1024 * 1024, dtype=torch.int64, device=dev)   # 256 MiB, only ever read
-    launches_per_step = lib.dclip_distill_loss_launch_count(m, B, d, _lib.path_code(path), 1 if world > 1 else 0)
+    def launches_per_step_now():
+        # N > 1: 2 = the peer exchange runs inside the kernels (a peer buffer was mapped, 16-bit inputs), 1 = separate push kernels / NCCL
+        sharded = 0
+        if world > 1:
+            in_kernel = (any(b is not None for b, _ in L._PEER_BUFFERS.values()) and args.dtype != "fp32"
+                         and os.environ.get("DCLIP_SHARDED_PUSH", "0") != "1")
+            sharded = 2 if in_kernel else 1
+        return lib.dclip_distill_loss_launch_count(m, B, d, _lib.path_code(path), sharded)
 
     def step_fn(s_img, s_txt, t_img, t_txt):
         if world == 1:
@@ -347,7 +354,7 @@ def main():
             "e2e": {"value": B / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in host) * world,
                     "d2h_bytes_per_step": 16 * world},
-            "gpu_launches": int(launches_per_step) * args.steps,
+            "gpu_launches": int(launches_per_step_now()) * args.steps,
             "roofline": roof, "cpu_baseline": cpu,
         }
         if parity is not None:

@@ -284,8 +284,9 @@ int dclip_distill_loss_launch_count(int64_t m, int64_t n, int64_t d, int path, i
     if (!sharded && tc_gmat_ok(m, d)) return 5;   // prep_pair, forward tiles, finalize, G tiles, pair GEMM (dU, dV) with the fused tail
     if (!sharded) return 5 + (tc_nsplit(m, n, d, 2) > 1 ? 2 : 0);
     // fused sharded phases: prep, forward tiles, finalize, global losses, backward tiles (+ combine), tail
-    // + the three peer-memory pushes (operands, statistics, step-done) that replace the NCCL all-gathers
-    return 6 + (tc_nsplit(m, n, d, 2) > 1 ? 1 : 0) + 3;
+    // + the three peer-memory pushes (operands, statistics, step-done) that replace the NCCL all-gathers - unless the exchange
+    // happens inside the kernels (sharded == 2: the `peers` argument of the three phases)
+    return 6 + (tc_nsplit(m, n, d, 2) > 1 ? 1 : 0) + (sharded == 2 ? 0 : 3);
 }
 
 // ---- fused per-rank phases of the sharded objective (tensor path) -----------------------------

@@ -82,7 +82,8 @@ int dclip_distill_loss_fwd_bwd(const void* s_img, const void* s_txt, const void*
                                float* stats, void* workspace, size_t workspace_bytes, int path, void* stream);
 
 /* Number of kernels of this library one step launches (single-GPU composite when sharded == 0, the
- * per-rank building blocks (1)-(5) when sharded != 0); used by bench.py for "gpu_launches". */
+ * per-rank building blocks (1)-(5) when sharded != 0; sharded == 2: the fused phases with the peer exchange inside the
+ * kernels, no push launches); used by bench.py for "gpu_launches". */
 /* The same objective split where the TEACHER embeddings are first needed, for callers whose inputs arrive over
  * PCIe: _students (normalise, forward tiles, log-sum-exp, backward tiles) needs only the student rows and can run
  * while the teachers are still being copied; _teachers (cosine terms, the four losses, gradient tail) finishes
