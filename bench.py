@@ -568,17 +568,22 @@ def retrieval_bench(dev, with_cpu):
     out = {}
     cap, img, image_ids, cap_ids = synthetic.retrieval_inputs(1000, 5, 512, 7.0, seed=44)      # the tests/golden/retrieval_cfg2 recipe
     cap_d, img_d = torch.from_numpy(cap).to(dev), torch.from_numpy(img).to(dev)
-    for _ in range(2):
-        R.retrieval_metrics_from_embeddings(cap_d, img_d, image_ids, cap_ids)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    reps = 5
-    for _ in range(reps):
-        m = R.retrieval_metrics_from_embeddings(cap_d, img_d, image_ids, cap_ids)
-    torch.cuda.synchronize()
-    dt = (time.perf_counter() - t0) / reps
-    out["flickr_eval"] = {"queries_per_s": 6000 / dt, "ms_per_eval": dt * 1e3, "t2i_R@1": m["t2i"]["R@1"],
-                          "i2t_R@1": m["i2t"]["R@1"], "workload": "1k images x 5k captions, d=512, R@1/5/10 both directions (BASELINE configs[1])"}
+    res = {}
+    for rank_path in ("fp32", "tensor"):
+        for _ in range(2):
+            R.retrieval_metrics_from_embeddings(cap_d, img_d, image_ids, cap_ids, path=rank_path)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        reps = 5
+        for _ in range(reps):
+            m = R.retrieval_metrics_from_embeddings(cap_d, img_d, image_ids, cap_ids, path=rank_path)
+        torch.cuda.synchronize()
+        res[rank_path] = ((time.perf_counter() - t0) / reps, m)
+    (dt32, m32), (dt, m) = res["fp32"], res["tensor"]
+    out["flickr_eval"] = {"queries_per_s": 6000 / dt, "ms_per_eval": dt * 1e3, "ms_per_eval_fp32_path": dt32 * 1e3, "t2i_R@1": m["t2i"]["R@1"],
+                          "i2t_R@1": m["i2t"]["R@1"], "metrics_identical_on_both_paths": m == m32,
+                          "path": "tensor (tcgen05 score tiles, exact re-scoring of the band around each target score; ranks bit-exact)",
+                          "workload": "1k images x 5k captions, d=512, R@1/5/10 both directions (BASELINE configs[1])"}
     if with_cpu:
         from oracle import reference_arm
         arm = reference_arm.load()

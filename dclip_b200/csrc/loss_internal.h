@@ -80,6 +80,10 @@ struct TcArgs {
     // stream kernel: soft lockstep of concurrently running CTAs (keeps the Y tiles they share inside L2); null = off
     unsigned int* sync_ctr;   // [groups][sync_epochs], zeroed before the launch
     int sync_every, sync_group, sync_epochs;
+    // stream mode 4 (Recall@K rank counting): exact target score / global target index per row, rank accumulator, band list
+    const float* rk_thr; const int64_t* rk_tgt; int32_t* rk_rank; int2* rk_band; unsigned int* rk_ctr; unsigned int rk_cap;
+    float rk_eps; int64_t rk_goff;
+    const float* rk_norms;   // {max |q|, max |g|} (device): the band half-width is rk_eps * |q|max * |g|max
     PeerCtx peers;        // stream mode 0, peers.world > 1: the producers wait for every peer's operand rows before the first load
     int debug_skip;       // timing experiments only (results are garbage): 1 = no phase-1 MMAs, 2 = no phase-2 MMAs, 4 = no G stores
 };
@@ -116,6 +120,10 @@ int launch_infonce_bwd_gmat(const void* u_hat, const void* v_hat, int64_t B, int
 int stream_nsplit(int64_t m, int64_t n, int nsides);
 int launch_stream_tc(int mode, int nsides, const void* const x[2], const void* const y[2], const TcArgs& args, int nsplit,
                      cudaStream_t st);
+// Recall@K rank counting on the tensor path (retrieval_tc.cu)
+size_t rank_counts_tc_workspace_bytes(int64_t npairs, int64_t ng, int64_t d);
+int launch_rank_counts_tc(const float* q, const float* g, int64_t ng, int64_t d, const int64_t* qidx, const float* ts, const int64_t* tgt,
+                          int64_t npairs, int64_t goff, int32_t* rank, void* workspace, size_t workspace_bytes, int** gate_out, cudaStream_t st);
 // lockstep counters the streaming kernel wants for this problem (0 = lockstep not used); see stream_tc.cu
 size_t stream_sync_bytes(int64_t m, int64_t n, int64_t d, int nsplit);
 

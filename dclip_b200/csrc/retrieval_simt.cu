@@ -11,6 +11,7 @@
 // output, k-chunks visited in ascending order), so ranks and top-k lists are bit-exact,
 // ties included.  The score matrix never leaves registers / shared memory.
 #include "common.cuh"
+#include "loss_internal.h"
 
 namespace dclip {
 
@@ -35,50 +36,65 @@ template <> __device__ __forceinline__ float4 ld4<__nv_bfloat16>(const __nv_bflo
 }
 
 // ---------------------------------------------------------------------------------------------
-// row normalisation with the contract's sequential sum of squares (numpy semantics: no eps)
-// 32 rows per CTA; chunks of 128 columns staged through smem so global loads stay coalesced
+// The contract's score is a strictly SEQUENTIAL fp32 fmaf chain over k, so one thread has to walk it - but nothing says that
+// thread must also wait for every load.  A warp stages 512-element chunks of the two rows in its slice of shared memory with
+// coalesced 16-byte loads; lane 0 then walks the chunk out of shared memory (LDS.128 + 4 dependent FMAs).  One thread doing
+// both was latency-bound: 17 us for 5000 pairs of d = 512, 31 us to normalise them.
 // ---------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(256) k_normalize_rows(const T* __restrict__ x, int64_t n, int64_t d, float* __restrict__ out) {
-    __shared__ float tile[32][129];
-    __shared__ float nrm[32];
-    const int64_t row0 = (int64_t)blockIdx.x * 32;
-    float ss = 0.f;
-    for (int64_t c0 = 0; c0 < d; c0 += 128) {
-        const int cw = (int)min((int64_t)128, d - c0);
-        __syncthreads();
-        for (int idx = threadIdx.x; idx < 32 * 128; idx += 256) {
-            const int r = idx >> 7, c = idx & 127;
-            tile[r][c] = (row0 + r < n && c < cw) ? to_f32<T>(x[(row0 + r) * d + c0 + c]) : 0.f;
+constexpr int kChainChunk = 512;                 // elements per staged chunk
+constexpr int kChainWarps = 8;                   // warps per CTA (2 x 512 floats of shared memory each)
+
+// returns (in lane 0) fmaf-chain sum_k a[k] * b[k];  `sa`, `sb`: this warp's two kChainChunk-float buffers (sb == sa when b == a)
+template <typename TA, typename TB>
+__device__ __forceinline__ float warp_chain_dot(const TA* __restrict__ a, const TB* __restrict__ b, int64_t d, float* sa, float* sb, int lane) {
+    float acc = 0.f;
+    const bool same = (const void*)a == (const void*)b;
+    for (int64_t c0 = 0; c0 < d; c0 += kChainChunk) {
+        const int cw = (int)min((int64_t)kChainChunk, d - c0);       // multiple of 4 (host-checked)
+        __syncwarp();
+        for (int k = lane * 4; k < cw; k += 128) {
+            *reinterpret_cast<float4*>(sa + k) = ld4<TA>(a + c0 + k);
+            if (!same) *reinterpret_cast<float4*>(sb + k) = ld4<TB>(b + c0 + k);
         }
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            for (int c = 0; c < cw; ++c) ss = fmaf(tile[threadIdx.x][c], tile[threadIdx.x][c], ss);
+        __syncwarp();
+        if (lane == 0) {
+            const float* pb = same ? sa : sb;
+#pragma unroll 4
+            for (int k = 0; k < cw; k += 4) {
+                const float4 x = *reinterpret_cast<const float4*>(sa + k), y = *reinterpret_cast<const float4*>(pb + k);
+                acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+            }
         }
     }
-    if (threadIdx.x < 32) nrm[threadIdx.x] = sqrtf(ss);
-    __syncthreads();
-    for (int64_t idx = threadIdx.x; idx < 32 * d; idx += 256) {
-        const int r = (int)(idx / d);
-        const int64_t c = idx - (int64_t)r * d;
-        if (row0 + r < n) out[(row0 + r) * d + c] = to_f32<T>(x[(row0 + r) * d + c]) / nrm[r];
+    return acc;
+}
+
+// row normalisation with the contract's sequential sum of squares (numpy semantics: no eps): one warp per row
+template <typename T>
+__global__ void __launch_bounds__(kChainWarps * 32) k_normalize_rows(const T* __restrict__ x, int64_t n, int64_t d, float* __restrict__ out) {
+    __shared__ __align__(16) float buf[kChainWarps][kChainChunk];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t row = (int64_t)blockIdx.x * kChainWarps + w;
+    if (row >= n) return;
+    const T* xr = x + row * d;
+    float ss = warp_chain_dot<T, T>(xr, xr, d, buf[w], buf[w], lane);
+    const float nrm = sqrtf(__shfl_sync(0xffffffffu, ss, 0));
+    for (int64_t k = lane * 4; k < d; k += 128) {
+        const float4 v = ld4<T>(xr + k);
+        *reinterpret_cast<float4*>(out + row * d + k) = make_float4(v.x / nrm, v.y / nrm, v.z / nrm, v.w / nrm);
     }
 }
 
-// one thread per pair; float4 loads, strictly sequential fma chain
-__global__ void k_pair_scores(const float* __restrict__ q, const float* __restrict__ g, int64_t d,
-                              const int64_t* __restrict__ qidx, const int64_t* __restrict__ gidx, int64_t npairs,
-                              float* __restrict__ out) {
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per pair (staged chunks, lane 0 walks the chain)
+__global__ void __launch_bounds__(kChainWarps * 32) k_pair_scores(const float* __restrict__ q, const float* __restrict__ g, int64_t d,
+                                                                  const int64_t* __restrict__ qidx, const int64_t* __restrict__ gidx, int64_t npairs,
+                                                                  float* __restrict__ out) {
+    __shared__ __align__(16) float buf[kChainWarps][2][kChainChunk];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t p = (int64_t)blockIdx.x * kChainWarps + w;
     if (p >= npairs) return;
-    const float* qr = q + (qidx ? qidx[p] : p) * d;
-    const float* gr = g + gidx[p] * d;
-    float acc = 0.f;
-    for (int64_t k = 0; k < d; k += 4) {
-        const float4 a = ld4<float>(qr + k), b = ld4<float>(gr + k);
-        acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
-    }
-    out[p] = acc;
+    const float acc = warp_chain_dot<float, float>(q + (qidx ? qidx[p] : p) * d, g + gidx[p] * d, d, buf[w][0], buf[w][1], lane);
+    if (lane == 0) out[p] = acc;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -134,9 +150,10 @@ __global__ void __launch_bounds__(RThreads) k_rank_counts(const float* __restric
                                                           int64_t ng, int64_t d, const int64_t* __restrict__ qidx,
                                                           const float* __restrict__ ts, const int64_t* __restrict__ tgt,
                                                           int64_t npairs, int64_t goff, int tiles_per_split,
-                                                          int32_t* __restrict__ rank) {
+                                                          int32_t* __restrict__ rank, const int* __restrict__ gate) {
     __shared__ __align__(16) float As[RK][RLD];
     __shared__ __align__(16) float Bs[RK][RLD];
+    if (gate && *gate == 0) return;      // fallback launch of the tensor path: only runs when its band list overflowed
     const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
     const int64_t row0 = (int64_t)blockIdx.x * RT;
     float tsr[4];
@@ -369,10 +386,8 @@ __global__ void k_group_min(const int32_t* __restrict__ rank, const int64_t* __r
 }
 __global__ void __launch_bounds__(1024) k_recall_metrics(const int32_t* __restrict__ rank, int64_t n, double* out4) {
     __shared__ double red[1024];
-    __shared__ unsigned long long cnt[4];
-    if (threadIdx.x < 4) cnt[threadIdx.x] = 0ull;
-    __syncthreads();
-    unsigned long long c1 = 0, c5 = 0, c10 = 0, cv = 0;
+    __shared__ int cnt[4][32];
+    int c1 = 0, c5 = 0, c10 = 0, cv = 0;
     double rr = 0.0;
     for (int64_t i = threadIdx.x; i < n; i += 1024) {
         const int32_t r = rank[i];
@@ -380,7 +395,13 @@ __global__ void __launch_bounds__(1024) k_recall_metrics(const int32_t* __restri
         ++cv; c1 += r < 1; c5 += r < 5; c10 += r < 10;
         rr += 1.0 / ((double)r + 1.0);
     }
-    atomicAdd(&cnt[0], c1); atomicAdd(&cnt[1], c5); atomicAdd(&cnt[2], c10); atomicAdd(&cnt[3], cv);
+    // integer counts: warp reductions, then 32 partials per counter (4096 serialised 64-bit shared atomics cost 45 us here)
+    c1 = __reduce_add_sync(0xffffffffu, c1); c5 = __reduce_add_sync(0xffffffffu, c5);
+    c10 = __reduce_add_sync(0xffffffffu, c10); cv = __reduce_add_sync(0xffffffffu, cv);
+    if ((threadIdx.x & 31) == 0) {
+        const int w = threadIdx.x >> 5;
+        cnt[0][w] = c1; cnt[1][w] = c5; cnt[2][w] = c10; cnt[3][w] = cv;
+    }
     red[threadIdx.x] = rr;
     __syncthreads();
     for (int o = 512; o > 0; o >>= 1) {
@@ -388,8 +409,11 @@ __global__ void __launch_bounds__(1024) k_recall_metrics(const int32_t* __restri
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        const double nv = (double)cnt[3];
-        out4[0] = (double)cnt[0] / nv; out4[1] = (double)cnt[1] / nv; out4[2] = (double)cnt[2] / nv;
+        long long t[4] = {0, 0, 0, 0};
+        for (int k = 0; k < 4; ++k)
+            for (int w = 0; w < 32; ++w) t[k] += cnt[k][w];
+        const double nv = (double)t[3];
+        out4[0] = (double)t[0] / nv; out4[1] = (double)t[1] / nv; out4[2] = (double)t[2] / nv;
         out4[3] = red[0] / nv;
     }
 }
@@ -440,7 +464,8 @@ int dclip_normalize_rows(const void* x, int64_t n, int64_t d, int dtype, float* 
     DCLIP_REQUIRE(x && out && n >= 0 && d > 0, "normalize_rows: bad arguments");
     if (n == 0) return DCLIP_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    DCLIP_DISPATCH_DTYPE(dtype, (k_normalize_rows<T><<<(unsigned)ceil_div(n, 32), 256, 0, st>>>(static_cast<const T*>(x), n, d, out)));
+    DCLIP_REQUIRE(d % 4 == 0, "normalize_rows: d must be a multiple of 4");
+    DCLIP_DISPATCH_DTYPE(dtype, (k_normalize_rows<T><<<(unsigned)ceil_div(n, kChainWarps), kChainWarps * 32, 0, st>>>(static_cast<const T*>(x), n, d, out)));
     DCLIP_LAUNCH_OK("k_normalize_rows");
     return DCLIP_OK;
 }
@@ -450,32 +475,40 @@ int dclip_pair_scores(const float* q, const float* g, int64_t d, const int64_t* 
     DCLIP_REQUIRE(q && g && gidx && out && npairs >= 0, "pair_scores: bad arguments");
     DCLIP_REQUIRE(d > 0 && d % 4 == 0, "pair_scores: d must be a multiple of 4");
     if (npairs == 0) return DCLIP_OK;
-    k_pair_scores<<<(unsigned)ceil_div(npairs, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(q, g, d, qidx, gidx, npairs, out);
+    k_pair_scores<<<(unsigned)ceil_div(npairs, kChainWarps), kChainWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(q, g, d, qidx, gidx, npairs, out);
     DCLIP_LAUNCH_OK("k_pair_scores");
     return DCLIP_OK;
 }
 
 size_t dclip_rank_counts_workspace_bytes(int64_t npairs, int64_t ng, int64_t d, int path) {
-    (void)npairs; (void)ng; (void)d; (void)path;
+    if (path == DCLIP_PATH_TENSOR) return rank_counts_tc_workspace_bytes(npairs, ng, d);
     return 256;
 }
 
 int dclip_rank_counts(const float* q, const float* g, int64_t ng, int64_t d, const int64_t* qidx, const float* target_score,
                       const int64_t* target_index, int64_t npairs, int64_t g_index_offset, int32_t* rank, void* workspace,
                       size_t workspace_bytes, int path, void* stream) {
-    (void)workspace; (void)workspace_bytes;
     DCLIP_REQUIRE(q && g && target_score && target_index && rank, "rank_counts: null pointer");
     DCLIP_REQUIRE(d > 0 && d % 4 == 0 && ng >= 0 && npairs >= 0, "rank_counts: bad shape (d must be a multiple of 4)");
-    if (path == DCLIP_PATH_TENSOR) return fail(DCLIP_ERR_UNSUPPORTED, "rank_counts: tensor path not available");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (npairs == 0) return DCLIP_OK;
     DCLIP_CUDA_OK(cudaMemsetAsync(rank, 0, sizeof(int32_t) * npairs, st));
     if (ng == 0) return DCLIP_OK;
+    const int* gate = nullptr;
+    if (path == DCLIP_PATH_TENSOR) {
+        // tcgen05 score tiles decide everything the fp16 operands can decide, the band around every target score is re-scored
+        // exactly (retrieval_tc.cu); `gate` is set only when the band list overflowed, and then the exact kernel below redoes it all
+        int* g_dev = nullptr;
+        if (int e = launch_rank_counts_tc(q, g, ng, d, qidx, target_score, target_index, npairs, g_index_offset, rank, workspace, workspace_bytes,
+                                          &g_dev, st))
+            return e;
+        gate = g_dev;
+    }
     const int64_t row_tiles = ceil_div(npairs, RT), col_tiles = ceil_div(ng, RT);
     const int nsplit = split_for(row_tiles, col_tiles);
     const int tps = (int)ceil_div(col_tiles, nsplit);
     dim3 grid((unsigned)row_tiles, (unsigned)ceil_div(col_tiles, tps));
-    k_rank_counts<<<grid, RThreads, 0, st>>>(q, g, ng, d, qidx, target_score, target_index, npairs, g_index_offset, tps, rank);
+    k_rank_counts<<<grid, RThreads, 0, st>>>(q, g, ng, d, qidx, target_score, target_index, npairs, g_index_offset, tps, rank, gate);
     DCLIP_LAUNCH_OK("k_rank_counts");
     return DCLIP_OK;
 }

@@ -202,6 +202,127 @@ __global__ void __launch_bounds__(256) k_topk_rescore(const TQ* __restrict__ q, 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Recall@K rank counting on the tensor path (flickr30k_eval.py:29-64 via dclip_rank_counts):
+//   rank[p] = #{ j : s_pj > ts_p  or  (s_pj == ts_p and goff + j < tgt_p) }      with s the contract's fp32 fmaf chain
+// The fp16-operand score tiles (stream mode 4) differ from s by at most eps = 1.1e-3 |q|max |g|max (two operand roundings of
+// 2^-11 each + both fp32 accumulations + fp16 subnormals), so every entry outside [ts - eps, ts + eps] is decided by the tile
+// and the few inside are decided here by the exact chain - the ranks are bit-identical to the FP32 path.
+// ---------------------------------------------------------------------------------------------
+struct RankTcMisc { unsigned int band_ctr; int overflow; float qmax, gmax; };
+
+// out[p][:] = fp16(x[idx ? idx[p] : p][:]) and the maximum row norm (non-negative floats order like their bit patterns)
+__global__ void __launch_bounds__(256) k_rows_to_f16_norm(const float* __restrict__ x, const int64_t* __restrict__ idx, int64_t n, int64_t d,
+                                                          __half* __restrict__ out, float* __restrict__ max_norm) {
+    const int lane = threadIdx.x & 31;
+    const int64_t p = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (p >= n) return;
+    const float* src = x + (idx ? idx[p] : p) * d;
+    float ss = 0.f;
+    for (int64_t k = lane * 4; k < d; k += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(src + k);
+        ss = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, ss))));
+        const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+        *reinterpret_cast<uint2*>(out + p * d + k) = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+    }
+    ss = warp_sum(ss);
+    if (lane == 0) atomicMax(reinterpret_cast<int*>(max_norm), __float_as_int(sqrtf(ss) * 1.000001f));
+}
+
+// exact decision of the band entries.  The chain is sequential by contract, so ONE lane walks an entry - but a warp takes 8
+// entries at a time: all 32 lanes stage 128-element chunks of the 16 rows in shared memory (coalesced 512-byte segments, rows
+// padded by 16 B against bank conflicts), lanes 0-7 walk one entry each.  (One thread per entry waits on every load itself: 64 us
+// for the 30 k entries of the Flickr-shaped evaluation; one warp per entry leaves 31 lanes idle: 37 us.)  An overflowed list means
+// the data defeats the band (e.g. a gallery of identical rows): the ranks are zeroed and the gated exact kernel recomputes them.
+constexpr int kBandWarps = 4, kBandGroup = 8, kBandChunk = 128, kBandLd = kBandChunk + 4;
+__global__ void __launch_bounds__(kBandWarps * 32) k_rank_band(const float* __restrict__ q, const float* __restrict__ g, int64_t d,
+                                                               const int64_t* __restrict__ qidx, const float* __restrict__ ts,
+                                                               const int64_t* __restrict__ tgt, int64_t goff, const int2* __restrict__ band,
+                                                               RankTcMisc* misc, unsigned int cap, int64_t npairs, int32_t* __restrict__ rank) {
+    __shared__ __align__(16) float buf[kBandWarps][kBandGroup][2][kBandLd];
+    const unsigned int n = misc->band_ctr;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (n > cap) {
+        const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (e == 0) misc->overflow = 1;
+        for (int64_t i = e; i < npairs; i += (int64_t)gridDim.x * blockDim.x) rank[i] = 0;
+        return;
+    }
+    const int64_t ngroups = ((int64_t)n + kBandGroup - 1) / kBandGroup;
+    for (int64_t grp = (int64_t)blockIdx.x * kBandWarps + w; grp < ngroups; grp += (int64_t)gridDim.x * kBandWarps) {
+        const int64_t e = grp * kBandGroup + lane;                 // lanes 0-7 own one entry each
+        const bool mine = lane < kBandGroup && e < n;
+        int2 b = make_int2(0, 0);
+        const float* qr = q;                                       // (a lane without an entry stages row 0: never read back)
+        const float* gr = g;
+        if (mine) {
+            b = band[e];
+            qr = q + (qidx ? qidx[b.x] : (int64_t)b.x) * d;
+            gr = g + (int64_t)b.y * d;
+        }
+        float acc = 0.f;
+        for (int64_t c0 = 0; c0 < d; c0 += kBandChunk) {
+            const int cw = (int)min((int64_t)kBandChunk, d - c0);                // multiple of 4
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 2 * kBandGroup; ++j) {                           // row j of the group: entry j >> 1, operand j & 1
+                const float* src = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>((j & 1) ? gr : qr), j >> 1));
+                if (lane * 4 < cw) *reinterpret_cast<float4*>(&buf[w][j >> 1][j & 1][lane * 4]) = __ldg(reinterpret_cast<const float4*>(src + c0 + lane * 4));
+            }
+            __syncwarp();
+            if (mine) {
+#pragma unroll 4
+                for (int k = 0; k < cw; k += 4) {
+                    const float4 x = *reinterpret_cast<const float4*>(&buf[w][lane][0][k]), y = *reinterpret_cast<const float4*>(&buf[w][lane][1][k]);
+                    acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+                }
+            }
+        }
+        if (mine) {
+            const float t = ts[b.x];
+            if (acc > t || (acc == t && goff + b.y < tgt[b.x])) atomicAdd(&rank[b.x], 1);
+        }
+    }
+}
+
+static unsigned int rank_band_cap(int64_t npairs) { return (unsigned int)min((int64_t)1 << 26, 8 * npairs + 8192); }
+
+size_t rank_counts_tc_workspace_bytes(int64_t npairs, int64_t ng, int64_t d) {
+    return align_up((size_t)npairs * d * 2, 256) + align_up((size_t)ng * d * 2, 256) + align_up((size_t)rank_band_cap(npairs) * sizeof(int2), 256) +
+           256 + 1024;
+}
+
+// rank must be zeroed by the caller (stream-ordered).  *gate_out = device int that is 1 iff the exact fallback has to run.
+int launch_rank_counts_tc(const float* q, const float* g, int64_t ng, int64_t d, const int64_t* qidx, const float* ts, const int64_t* tgt,
+                          int64_t npairs, int64_t goff, int32_t* rank, void* workspace, size_t workspace_bytes, int** gate_out, cudaStream_t st) {
+    if (!device_is_sm100()) return fail(DCLIP_ERR_ARCH, "tensor path needs an sm_100 device");
+    if (d % 8 != 0 || d < 64 || d > 1024) return fail(DCLIP_ERR_UNSUPPORTED, "rank_counts: tensor path needs d %% 8 == 0 and 64 <= d <= 1024 (got %lld)", (long long)d);
+    if (npairs >= (1ll << 31) || ng >= (1ll << 31)) return fail(DCLIP_ERR_UNSUPPORTED, "rank_counts: tensor path needs fewer than 2^31 pairs / gallery rows");
+    DCLIP_REQUIRE(aligned16(q) && aligned16(g) && aligned16(workspace), "rank_counts: pointers must be 16-byte aligned");
+    const unsigned int cap = rank_band_cap(npairs);
+    Workspace ws(workspace, workspace_bytes);
+    __half* q16 = static_cast<__half*>(ws.take((size_t)npairs * d * 2));
+    __half* g16 = static_cast<__half*>(ws.take((size_t)ng * d * 2));
+    int2* band = static_cast<int2*>(ws.take((size_t)cap * sizeof(int2)));
+    RankTcMisc* misc = static_cast<RankTcMisc*>(ws.take(256));
+    if (!ws.ok()) return fail(DCLIP_ERR_WORKSPACE, "rank_counts: workspace too small (%zu < %zu)", workspace_bytes, ws.used);
+    DCLIP_CUDA_OK(cudaMemsetAsync(misc, 0, sizeof(RankTcMisc), st));
+    k_rows_to_f16_norm<<<(unsigned)ceil_div(npairs, 8), 256, 0, st>>>(q, qidx, npairs, d, q16, &misc->qmax);
+    k_rows_to_f16_norm<<<(unsigned)ceil_div(ng, 8), 256, 0, st>>>(g, nullptr, ng, d, g16, &misc->gmax);
+    DCLIP_LAUNCH_OK("k_rows_to_f16_norm");
+    TcArgs a{};
+    a.m = npairs; a.n = ng; a.d = d; a.inv_tau = 1.f;
+    a.rk_thr = ts; a.rk_tgt = tgt; a.rk_rank = rank; a.rk_band = band; a.rk_ctr = &misc->band_ctr; a.rk_cap = cap; a.rk_goff = goff;
+    a.rk_eps = 1.1e-3f; a.rk_norms = &misc->qmax;
+    const void* xs[2] = {q16, q16};
+    const void* ys[2] = {g16, g16};
+    if (int e = launch_stream_tc(4, 1, xs, ys, a, stream_nsplit(npairs, ng, 1), st)) return e;
+    k_rank_band<<<(unsigned)(8 * sm_count()), kBandWarps * 32, 0, st>>>(q, g, d, qidx, ts, tgt, goff, band, misc, cap, npairs, rank);
+    DCLIP_LAUNCH_OK("k_rank_band");
+    *gate_out = &misc->overflow;
+    return DCLIP_OK;
+}
+
 int tc_topk_nsplit(int64_t nq, int64_t ng) { return stream_nsplit(nq, ng, 1); }
 
 }  // namespace dclip

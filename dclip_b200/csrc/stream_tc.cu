@@ -22,6 +22,9 @@
 //                           sum of column l over the warp's 32 rows, the four warps meet in shared memory and
 //                           the tile's 256 column sums go to col_out[row block][j] (summed over row blocks,
 //                           in fixed order, by the finalize kernel)
+//   mode 4 (Recall@K ranks): thread i holds the EXACT score ts_i of its query's target; a score tile entry counts when it beats
+//                           ts_i by more than the operand-rounding bound eps, entries inside [ts_i - eps, ts_i + eps] go to a
+//                           global band list and are decided by exact re-scoring (retrieval_tc.cu): ranks stay bit-exact
 //   mode 2 (retrieval):     thread i caches the admission threshold of its query; a warp-wide max test
 //                           rejects whole 32-score chunks, the rare hits are inserted warp-cooperatively
 //                           into that query's 32-entry list in shared memory -> cand_s / cand_i[i][32]
@@ -249,6 +252,17 @@ k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CU
         if (kMode == 3 && grow < a.m) a_i = exp2f((a.inv_tau - S.lse_x[grow]) * kLog2e + 13.0f);
         float* csum3 = reinterpret_cast<float*>(lists + 2 * SN_COLS * 4 + kGStageWarps * kGStageWarpBytes);     // [2][4][256] column sums of g * s
         (void)a_i; (void)bs; (void)stage_s; (void)csum3; (void)cpart;
+        // mode 4: my query's exact target score, the band around it and the (local) column of the target itself
+        float rk_hi = INFINITY, rk_lo = INFINITY;
+        int64_t rk_tcol = -1;
+        int rk_cnt = 0;
+        if (kMode == 4 && grow < a.m) {
+            const float ts = a.rk_thr[grow];
+            const float eps = a.rk_eps * (a.rk_norms ? a.rk_norms[0] * a.rk_norms[1] : 1.f);
+            rk_hi = ts + eps; rk_lo = ts - eps;
+            rk_tcol = a.rk_tgt[grow] - a.rk_goff;
+        }
+        (void)rk_hi; (void)rk_lo; (void)rk_tcol; (void)rk_cnt;
         if (kMode == 2) {
             for (int e = 0; e < kListLen; ++e) { ls[et * kListLen + e] = -INFINITY; li[et * kListLen + e] = -1; }
             __syncwarp();
@@ -382,6 +396,25 @@ k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CU
                         }
                     }
                     colsum[(b * 4 + qd) * SN_COLS + c0 + lane] = v[0];     // column c0 + lane over my warp's 32 rows
+                } else if (kMode == 4) {
+                    // definite wins are counted; anything the fp16 operands cannot decide is listed for the exact pass
+                    const int lim = min(32, ncols - c0);
+                    unsigned inband = 0u;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float sv = __uint_as_float(r[i]);
+                        const bool valid = i < lim;
+                        rk_cnt += (valid && sv > rk_hi) ? 1 : 0;
+                        inband |= (valid && sv >= rk_lo && sv <= rk_hi) ? (1u << i) : 0u;
+                    }
+                    while (inband) {                          // rare (the target itself + ~0.2 neighbours per query on Flickr-shaped data)
+                        const int i = __ffs(inband) - 1;
+                        inband &= inband - 1;
+                        const int64_t col = j0 + c0 + i;
+                        if (col == rk_tcol) continue;         // the target never outranks itself
+                        const unsigned pos = atomicAdd(a.rk_ctr, 1u);
+                        if (pos < a.rk_cap) a.rk_band[pos] = make_int2((int)grow, (int)col);
+                    }
                 } else if (kMode == 0) {
                     if (c0 + 32 <= ncols) {
 #pragma unroll
@@ -479,6 +512,8 @@ k_stream_tc(const __grid_constant__ CUtensorMap tmx0, const __grid_constant__ CU
             if (chalf == 0 && grow < a.m) S.out[(int64_t)blockIdx.y * a.m + grow] = sum + colsum[et];
         } else if (kMode == 0) {
             if (grow < a.m) S.out[(int64_t)blockIdx.y * a.m + grow] = sum;
+        } else if (kMode == 4) {
+            if (grow < a.m && rk_cnt) atomicAdd(&a.rk_rank[grow], rk_cnt);      // (integer: the order of the column splits does not matter)
         } else if (kMode == 3) {
             // the four column quarters of a row meet in shared memory
             asm volatile("bar.sync 2, 512;" ::: "memory");
@@ -581,6 +616,8 @@ int launch_stream_tc(int mode, int nsides, const void* const x[2], const void* c
             a.sync_epochs = (int)ceil_div(a.tiles_per_split, sync_every());
         }
     }
+    if (mode == 4 && (!a.rk_thr || !a.rk_tgt || !a.rk_rank || !a.rk_band || !a.rk_ctr || nsides != 1))
+        return fail(DCLIP_ERR_INVALID, "stream_tc: mode 4 is single-sided and needs thresholds, targets, the rank output and a band list");
     if (mode == 1 && (!a.col_out || nsides != 1)) return fail(DCLIP_ERR_INVALID, "stream_tc: mode 1 is single-sided and needs col_out");
     if (mode == 3 && (!a.g_out || !a.col_out || !a.s[0].out || nsides != 1 || !pair || a.ldg % 8 || a.ldg < ceil_div(a.n, SN_COLS) * SN_COLS))
         return fail(DCLIP_ERR_INVALID, "stream_tc: mode 3 is single-sided, needs more than 128 rows and a tile-padded coefficient matrix");
@@ -606,6 +643,7 @@ int launch_stream_tc(int mode, int nsides, const void* const x[2], const void* c
     if (mode == 0) { if (pair) DCLIP_STREAM_LAUNCH(0, true); else DCLIP_STREAM_LAUNCH(0, false); }
     else if (mode == 1) { if (pair) DCLIP_STREAM_LAUNCH(1, true); else DCLIP_STREAM_LAUNCH(1, false); }
     else if (mode == 3) DCLIP_STREAM_LAUNCH(3, true);
+    else if (mode == 4) { if (pair) DCLIP_STREAM_LAUNCH(4, true); else DCLIP_STREAM_LAUNCH(4, false); }
     else { if (pair) DCLIP_STREAM_LAUNCH(2, true); else DCLIP_STREAM_LAUNCH(2, false); }
 #undef DCLIP_STREAM_LAUNCH
     DCLIP_LAUNCH_OK("k_stream_tc");

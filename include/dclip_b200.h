@@ -239,7 +239,11 @@ int dclip_pair_scores(const float* q, const float* g, int64_t d, const int64_t* 
 /* Partial ranks over one gallery shard g[0..ng) whose rows have global indices
  * g_index_offset + j:   rank[p] = #{ j : s_pj > ts[p]  or (s_pj == ts[p] and g_index_offset + j < tgt[p]) }
  * with s_pj = score(q[qidx[p]], g[j]), ts = target scores from dclip_pair_scores, tgt = global
- * target index.  Ranks of shards add up (all-reduce sum) to the stable-argsort rank. */
+ * target index.  Ranks of shards add up (all-reduce sum) to the stable-argsort rank.
+ * path = DCLIP_PATH_TENSOR (sm_100, d % 8 == 0, 64 <= d <= 1024): the score tiles run on tcgen05 with fp16 copies of the rows;
+ * they differ from the fp32 chain by at most 1.1e-3 |q|max |g|max, so every entry outside that band around ts[p] is decided by the
+ * tile and the few inside are re-scored with the exact chain - same ranks, bit for bit; data that defeats the band (its list
+ * overflows) is recomputed by the exact kernel inside the same call. */
 size_t dclip_rank_counts_workspace_bytes(int64_t npairs, int64_t ng, int64_t d, int path);
 int dclip_rank_counts(const float* q, const float* g, int64_t ng, int64_t d, const int64_t* qidx,
                       const float* target_score, const int64_t* target_index, int64_t npairs,

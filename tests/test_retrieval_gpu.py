@@ -10,7 +10,7 @@ from oracle import synthetic
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-RANK_PATHS = ("fp32",)
+RANK_PATHS = ("fp32", "tensor")     # tensor: tcgen05 score tiles + exact re-scoring of the band around every target score
 
 
 def _d(a):
@@ -67,11 +67,12 @@ def test_normalize_and_scores_bit_exact(built_library):
     assert np.array_equal(ps.cpu().numpy(), want)
 
 
-@pytest.mark.parametrize("n_img,cpi,d", [(1000, 5, 512), (37, 3, 40), (130, 1, 768)])
-def test_ranks_bit_exact(built_library, n_img, cpi, d):
+@pytest.mark.parametrize("n_img,cpi,d,path", [(1000, 5, 512, "fp32"), (37, 3, 40, "fp32"), (130, 1, 768, "fp32"),
+                                                (1000, 5, 512, "tensor"), (37, 3, 64, "tensor"), (130, 1, 768, "tensor"), (301, 4, 256, "tensor")])
+def test_ranks_bit_exact(built_library, n_img, cpi, d, path):
     from dclip_b200 import retrieval as R
     cap, img, image_ids, cap_ids = synthetic.retrieval_inputs(n_img, cpi, d, 1.0, seed=n_img)
-    t2i, i2t_pairs, pair_img = R.retrieval_ranks(cap, img, image_ids, cap_ids)
+    t2i, i2t_pairs, pair_img = R.retrieval_ranks(cap, img, image_ids, cap_ids, path=path)
     want_t2i, want_i2t = orc.ranks_from_embeddings_c(cap, img, image_ids, cap_ids)
     assert t2i.cpu().tolist() == want_t2i
     best = {}
@@ -108,6 +109,33 @@ def test_ranks_with_exact_ties(built_library):
     # gallery sharding: partial ranks add up
     parts = [R.rank_counts(_d(q), _d(g[a:b]), ts, _d(tgt), g_index_offset=a) for a, b in ((0, 64), (64, 65), (65, 150))]
     assert (parts[0] + parts[1] + parts[2]).cpu().tolist() == r.cpu().tolist()
+
+
+def test_tensor_ranks_with_ties_shards_and_band_overflow(built_library):
+    """Tensor-path rank counting stays bit-exact where the fp16 score tiles cannot decide: exact ties (small-integer rows: every
+    score is a tie candidate and lands in the band), gallery shards with an index offset, and a gallery of identical rows, whose
+    band list overflows and hands the whole problem to the gated exact kernel."""
+    from dclip_b200 import retrieval as R
+    rng = np.random.default_rng(5)
+    g = rng.integers(-1, 2, size=(700, 64)).astype(np.float32)
+    q = rng.integers(-1, 2, size=(300, 64)).astype(np.float32)
+    tgt = rng.integers(0, 700, size=300)
+    ts = R.pair_scores(_d(q), _d(g), _d(tgt))
+    want = orc.c_ranks(q, g, np.arange(300), tgt).tolist()
+    r = R.rank_counts(_d(q), _d(g), ts, _d(tgt), path="tensor")
+    assert r.cpu().tolist() == want
+    parts = [R.rank_counts(_d(q), _d(g[a:b]), ts, _d(tgt), g_index_offset=a, path="tensor") for a, b in ((0, 256), (256, 257), (257, 700))]
+    assert (parts[0] + parts[1] + parts[2]).cpu().tolist() == want
+    # unit rows, every gallery row identical: all 40000 x 129 scores sit inside the band -> overflow -> exact fallback
+    row = rng.standard_normal(128).astype(np.float32)
+    row /= np.linalg.norm(row)
+    g2 = np.tile(row, (40000, 1)).astype(np.float32)
+    q2 = rng.standard_normal((129, 128)).astype(np.float32)
+    q2 /= np.linalg.norm(q2, axis=1, keepdims=True)
+    tgt2 = rng.integers(0, 40000, size=129)
+    ts2 = R.pair_scores(_d(q2), _d(g2), _d(tgt2))
+    r2 = R.rank_counts(_d(q2), _d(g2), ts2, _d(tgt2), path="tensor")
+    assert r2.cpu().tolist() == R.rank_counts(_d(q2), _d(g2), ts2, _d(tgt2), path="fp32").cpu().tolist() == tgt2.tolist()
 
 
 @pytest.mark.parametrize("ng,nq,d,k", [(5000, 33, 128, 10), (64, 1, 512, 3), (100000, 16, 64, 10), (5, 4, 16, 10), (777, 70, 768, 32)])
