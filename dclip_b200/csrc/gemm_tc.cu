@@ -47,13 +47,20 @@ struct TcGemmArgs {
     int count, total_tiles;
     int ab_fmt;                   // kFmtBF16 / kFmtF16
     int* error_flag;
+    int prof_slot, debug_skip;    // stall-accounting build only (debug_skip: 1 no global stores, 2 no staging, 4 no TMEM load; results are garbage)
 };
 
 #ifdef DCLIP_GEMM_PROF
 __device__ long long g_gemm_prof[16];
-#define GPROF(k) do { if (blockIdx.x == 0) g_gemm_prof[k] = clock64(); } while (0)
+__device__ long long g_gemm_prof_ring[8][16];      // the last eight launches (slot = launch counter % 8), CTA 0
+#define GPROF(k) do { if (blockIdx.x == 0) { const long long c_ = clock64(); g_gemm_prof[k] = c_; g_gemm_prof_ring[g.prof_slot][k] = c_; } } while (0)
 #else
 #define GPROF(k) do { } while (0)
+#endif
+#ifdef DCLIP_GEMM_PROF
+#define GSKIPV (g.debug_skip)
+#else
+#define GSKIPV 0
 #endif
 
 __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
@@ -68,6 +75,150 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) { const __nv_bfl
 __device__ __forceinline__ uint32_t pack_f16(float a, float b) { const __half2 v = __floats2half2_rn(a, b); return *reinterpret_cast<const uint32_t*>(&v); }
 
 struct TileCoord { int pi, m0, n0, nkb; };
+
+// ---- epilogue.  TMEM hands each thread one output ROW (lane) and 32 consecutive columns per load; global memory wants a
+// warp on few rows (a store in which every lane touches a different row costs ~32 memory-pipe cycles).  So a chunk goes
+// through a private 4 KB shared-memory buffer (16-byte chunks XOR-swizzled by the row: conflict-free both ways) and comes
+// back with 8 lanes per row = 128 contiguous bytes per row and store.  The epilogue is INSTRUCTION-bound (8 warps, ~13 k
+// cycles per tile for a first version that tested the problem's optional features inside the store loop, against 5.6 k
+// of main loop at K = 768), so it is specialised per tile:
+//   MODE 0  16-bit output (+ bias)                          64-column chunks, packed to 16-bit BEFORE staging
+//   MODE 1  fp32 output + bias + 16-bit residual            32-column passes staged as fp32; the residual is added at
+//           (out-projection -> pre-LayerNorm sum)           read-back from coalesced 8-byte loads requested a pass ahead
+//   MODE 2  anything else (accumulate, fp32 residual, both outputs): the general form of mode 1
+// N % 8 == 0 (host-checked): a 4-/8-column group is inside C or not.
+struct EpiCtx { int qd, we, half, lane; uint32_t stage_s, bias_s; };
+
+__device__ __forceinline__ void epi_load_res16(const TcGemmDev& P, int row0, int ccol, uint2 (&raw)[8]) {
+    // rows row0 + 4k, columns ccol .. ccol + 3 of a 16-bit residual
+    const uint16_t* src = static_cast<const uint16_t*>(P.residual) + (size_t)row0 * P.ldr + ccol;
+    const int rows_left = ccol < P.N ? P.M - row0 : 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        raw[k] = make_uint2(0u, 0u);
+        if (4 * k < rows_left) raw[k] = *reinterpret_cast<const uint2*>(src + (size_t)(4 * k) * P.ldr);
+    }
+}
+template <bool BF> __device__ __forceinline__ void widen2(uint32_t w, float& lo, float& hi) {
+    if (BF) { lo = __uint_as_float(w << 16); hi = __uint_as_float(w & 0xffff0000u); }
+    else { const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w)); lo = f.x; hi = f.y; }
+}
+template <bool BF> __device__ __forceinline__ uint32_t pack2(float a, float b) { return BF ? pack_bf16(a, b) : pack_f16(a, b); }
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) { const uint4 v = lds128(addr); return make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w)); }
+
+template <int MODE, bool BF>
+__device__ __forceinline__ void epilogue_tile(const TcGemmDev& P, const TileCoord& tc, const EpiCtx& E, uint32_t tacc, uint2 (&res0)[8], int skip) {
+    const int lane = E.lane;
+    const int rb_row = lane >> 3, rb_chunk = lane & 7;           // read-back: 8 lanes per row, 4 rows per store
+    const int row0 = tc.m0 + E.qd * 32 + rb_row;                 // my first read-back row
+    const int col0 = tc.n0 + E.half * (GN / 2);                  // first column of this warp
+    const bool has_bias = P.bias != nullptr;
+    const uint32_t st_wr = E.stage_s + lane * 128, st_sw = (uint32_t)(lane & 7);
+    if (MODE == 0) {
+        uint16_t* c16 = static_cast<uint16_t*>(P.C16);
+#pragma unroll 1
+        for (int ch = 0; ch < 2; ++ch) {
+            const int col = col0 + ch * 64;
+            if (col >= P.N) break;                               // warp-uniform
+            float v[64];
+            tmem_ld_32x32b_x32(tacc + ch * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+            tmem_ld_32x32b_x32(tacc + ch * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+            // (columns past N hold whatever the MMA left there - TMA zero-fills the operands, so zeros; never stored)
+            tmem_ld_wait();
+            if (P.alpha != 1.0f) {
+#pragma unroll
+                for (int i = 0; i < 64; ++i) v[i] *= P.alpha;
+            }
+            if (has_bias) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const float4 bq = lds_f4(E.bias_s + (uint32_t)(E.half * (GN / 2) + ch * 64 + q * 4) * 4);      // broadcast
+                    v[q * 4] += bq.x; v[q * 4 + 1] += bq.y; v[q * 4 + 2] += bq.z; v[q * 4 + 3] += bq.w;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                sts128(st_wr + ((q ^ st_sw) << 4), make_uint4(pack2<BF>(v[q * 8], v[q * 8 + 1]), pack2<BF>(v[q * 8 + 2], v[q * 8 + 3]),
+                                                                pack2<BF>(v[q * 8 + 4], v[q * 8 + 5]), pack2<BF>(v[q * 8 + 6], v[q * 8 + 7])));
+            __syncwarp();
+            const int ccol = col + rb_chunk * 8;
+            const int rows_left = (ccol < P.N && !(skip & 1)) ? P.M - row0 : 0;
+            uint16_t* dst = c16 + (size_t)row0 * P.ldc16 + ccol;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int rr = rb_row + 4 * k;
+                const uint4 x = lds128(E.stage_s + rr * 128 + ((rb_chunk ^ (rr & 7)) << 4));
+                if (4 * k < rows_left) *reinterpret_cast<uint4*>(dst + (size_t)(4 * k) * P.ldc16) = x;
+            }
+            __syncwarp();
+        }
+        return;
+    }
+    // MODE 1 / 2: 32-column passes staged as fp32; lane (r, c) owns columns 4c .. 4c+3 of the rows r, r + 4, ...
+    constexpr int kPasses = GN / 2 / 32;
+    const bool res16 = MODE == 1 || (P.residual != nullptr && P.res_kind != 0);
+#pragma unroll 1
+    for (int ps = 0; ps < kPasses; ++ps) {
+        const int col = col0 + ps * 32;
+        if (col >= P.N) break;                                   // warp-uniform
+        const int ccol = col + rb_chunk * 4;
+        float v[32];
+        tmem_ld_32x32b_x32(tacc + ps * 32, *reinterpret_cast<uint32_t(*)[32]>(v));
+        tmem_ld_wait();
+        if (P.alpha != 1.0f) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] *= P.alpha;
+        }
+        if (has_bias) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 bq = lds_f4(E.bias_s + (uint32_t)(E.half * (GN / 2) + ps * 32 + q * 4) * 4);      // broadcast
+                v[q * 4] += bq.x; v[q * 4 + 1] += bq.y; v[q * 4 + 2] += bq.z; v[q * 4 + 3] += bq.w;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            sts128(st_wr + ((q ^ st_sw) << 4), make_uint4(__float_as_uint(v[q * 4]), __float_as_uint(v[q * 4 + 1]), __float_as_uint(v[q * 4 + 2]), __float_as_uint(v[q * 4 + 3])));
+        __syncwarp();
+        uint2 cur[8];
+        if (res16) {
+            if (MODE == 1) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) cur[k] = res0[k];
+                if (ps + 1 < kPasses && col + 32 < P.N) epi_load_res16(P, row0, ccol + 32, res0);      // next pass: in flight under this one
+            } else epi_load_res16(P, row0, ccol, cur);
+        }
+        const int rows_left = (ccol < P.N && !(skip & 1)) ? P.M - row0 : 0;
+        float* dst = MODE == 1 || P.C ? P.C + (size_t)row0 * P.ldc + ccol : nullptr;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int rr = rb_row + 4 * k;
+            float4 o = lds_f4(E.stage_s + rr * 128 + ((rb_chunk ^ (rr & 7)) << 4));
+            if (res16) {
+                float r0, r1, r2, r3;
+                widen2<BF>(cur[k].x, r0, r1); widen2<BF>(cur[k].y, r2, r3);
+                o.x += r0; o.y += r1; o.z += r2; o.w += r3;
+            }
+            if (4 * k < rows_left) {
+                if (MODE == 2) {
+                    if (P.residual && P.res_kind == 0) {
+                        const float4 r = *reinterpret_cast<const float4*>(static_cast<const float*>(P.residual) + (size_t)(row0 + 4 * k) * P.ldr + ccol);
+                        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+                    }
+                    if (P.C && P.accumulate) {
+                        const float4 r = *reinterpret_cast<const float4*>(dst + (size_t)(4 * k) * P.ldc);
+                        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+                    }
+                    if (P.c16_kind)
+                        *reinterpret_cast<uint2*>(static_cast<uint16_t*>(P.C16) + (size_t)(row0 + 4 * k) * P.ldc16 + ccol) = make_uint2(pack2<BF>(o.x, o.y), pack2<BF>(o.z, o.w));
+                }
+                if (MODE == 1 || P.C) *reinterpret_cast<float4*>(dst + (size_t)(4 * k) * P.ldc) = o;
+            }
+        }
+        __syncwarp();
+    }
+}
+
 __device__ __forceinline__ TileCoord tile_coord(const TcGemmArgs& g, int tile) {
     int pi = 0;
     for (int i = 1; i < g.count; ++i)
@@ -168,131 +319,47 @@ __global__ void __launch_bounds__(kGThreads, 1) k_gemm_tc(const __grid_constant_
             }
         }
     } else {
-        // ---- epilogue.  TMEM hands each thread one output ROW (lane) and 32 consecutive columns per load; global memory
-        // wants a warp on few rows: a store in which every lane touches a different row costs ~32 memory-pipe cycles
-        // (4096 cycles for a 128 x 256 16-bit tile, more than the 12-stage main loop of a K = 768 tile).  So: bias /
-        // residual are added in registers, the 32 x 64 chunk is staged through a private 4 KB shared-memory buffer
-        // (16-byte chunks XOR-swizzled by the row: conflict-free both ways) and written back with 8 lanes per row =
-        // 128 contiguous bytes per row.  Eight warps: warp % 4 is the TMEM lane quadrant it may read, the two warps
-        // of a quadrant split the tile's columns.  N % 8 == 0 (host-checked): an 8-column group is inside C or not.
-        const int qd = warp & 3;
-        const int we = warp - (kGStages + 1);
-        const int half = we >> 2;
-        const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
-        const uint32_t stage_s = smem_u32(ring + kGStages * kGStageBytes + 256) + (uint32_t)we * 4096;
+        // ---- epilogue (epilogue_tile above), eight warps: warp % 4 is the TMEM lane quadrant it may read, the two warps of a
+        // quadrant split the tile's columns.  The tile's bias row is staged once per tile in shared memory (before the
+        // accumulator barrier: hidden under the main loop).
+        EpiCtx E;
+        E.qd = warp & 3;
+        E.we = warp - (kGStages + 1);
+        E.half = E.we >> 2;
+        E.lane = lane;
+        E.stage_s = smem_u32(ring + kGStages * kGStageBytes + 256) + (uint32_t)E.we * 4096;
+        E.bias_s = smem_u32(ring + kGStages * kGStageBytes + 256 + kGEpiWarps * 4096);
         const bool bf = g.ab_fmt == (int)kFmtBF16;
-        const int rb_row = lane >> 3, rb_chunk = lane & 7;           // read-back: 8 lanes per row, 4 rows per pass
+        const int et = (int)threadIdx.x - (kGStages + 1) * 32;       // 0 .. 255: my bias column
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const TileCoord tc = tile_coord(g, tile);
             const TcGemmDev P = g.p[tc.pi];
             const int b = it & 1;
+            if (P.bias) {      // uniform over the CTA's epilogue warps (same tile)
+                float bv = 0.f;
+                if (tc.n0 + et < P.N) {
+                    if (P.bias_kind == 0) bv = static_cast<const float*>(P.bias)[tc.n0 + et];
+                    else if (bf) bv = __bfloat162float(static_cast<const __nv_bfloat16*>(P.bias)[tc.n0 + et]);
+                    else bv = __half2float(static_cast<const __half*>(P.bias)[tc.n0 + et]);
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");      // the previous tile's readers are done
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(E.bias_s + et * 4), "f"(bv) : "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
+            const int mode = (!P.C && P.c16_kind && !P.residual) ? 0 : (P.C && !P.c16_kind && P.residual && P.res_kind != 0 && !P.accumulate) ? 1 : 2;
+            // mode 1: the first pass's residual words are requested before the accumulator barrier
+            uint2 res0[8];
+            if (mode == 1) epi_load_res16(P, tc.m0 + E.qd * 32 + (lane >> 3), tc.n0 + E.half * (GN / 2) + (lane & 7) * 4, res0);
             ok = mbar_wait(&acc_full[b], (it >> 1) & 1, kSpinG);
             ok = __all_sync(0xffffffffu, ok);
             if (!ok) break;
             if (it == 0 && warp == kGStages + 1 && lane == 0) GPROF(5);
             fence_after_thread_sync();
-            const int rbase = tc.m0 + qd * 32;
-            const int grow = rbase + lane;
-            const bool row_ok = grow < P.M;
-#pragma unroll 1
-            for (int c0 = half * (GN / 2); c0 < (half + 1) * (GN / 2); c0 += 64) {
-                const int col = tc.n0 + c0;
-                if (col >= P.N) break;                        // warp-uniform
-                const int ngrp = min(8, (P.N - col) >> 3);      // 8-column groups of this chunk inside C (warp-uniform)
-                float v[64];
-                {
-                    uint32_t(&r)[64] = *reinterpret_cast<uint32_t(*)[64]>(v);
-                    tmem_ld_32x32b_x32(tmem + lane_addr + b * GN + c0, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
-                    // (columns past N hold whatever the MMA left there - TMA zero-fills the operands, so zeros; never stored)
-                    tmem_ld_32x32b_x32(tmem + lane_addr + b * GN + c0 + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
-                    tmem_ld_wait();
-                }
-                if (P.alpha != 1.0f) {
-#pragma unroll
-                    for (int i = 0; i < 64; ++i) v[i] *= P.alpha;
-                }
-                if (P.bias) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        if (q < ngrp) {
-                            float bv[8];
-                            if (P.bias_kind == 0) load8<float>(static_cast<const float*>(P.bias) + col + q * 8, bv);
-                            else if (bf) load8<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(P.bias) + col + q * 8, bv);
-                            else load8<__half>(static_cast<const __half*>(P.bias) + col + q * 8, bv);
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) v[q * 8 + i] += bv[i];
-                        }
-                }
-                if (row_ok && P.residual) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        if (q < ngrp) {
-                            float rv[8];
-                            const size_t off = (size_t)grow * P.ldr + col + q * 8;
-                            if (P.res_kind == 0) load8<float>(static_cast<const float*>(P.residual) + off, rv);
-                            else if (bf) load8<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(P.residual) + off, rv);
-                            else load8<__half>(static_cast<const __half*>(P.residual) + off, rv);
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) v[q * 8 + i] += rv[i];
-                        }
-                }
-                if (row_ok && P.C && P.accumulate) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        if (q < ngrp) {
-                            float cv[8];
-                            load8<float>(P.C + (size_t)grow * P.ldc + col + q * 8, cv);
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) v[q * 8 + i] += cv[i];
-                        }
-                }
-                if (P.C) {
-                    // fp32 output: two passes of 32 columns (128 B per row each)
-#pragma unroll
-                    for (int hsub = 0; hsub < 2; ++hsub) {
-                        if (hsub * 4 >= ngrp) break;
-#pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            sts128(stage_s + lane * 128 + ((q ^ (lane & 7)) << 4),
-                                   make_uint4(__float_as_uint(v[hsub * 32 + q * 4]), __float_as_uint(v[hsub * 32 + q * 4 + 1]),
-                                              __float_as_uint(v[hsub * 32 + q * 4 + 2]), __float_as_uint(v[hsub * 32 + q * 4 + 3])));
-                        __syncwarp();
-                        const int ccol = col + hsub * 32 + rb_chunk * 4;
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            const int rr = rb_row + 4 * k;
-                            const uint4 x = lds128(stage_s + rr * 128 + ((rb_chunk ^ (rr & 7)) << 4));
-                            if (rbase + rr < P.M && ccol < P.N) *reinterpret_cast<uint4*>(P.C + (size_t)(rbase + rr) * P.ldc + ccol) = x;
-                        }
-                        __syncwarp();
-                    }
-                }
-                if (P.c16_kind) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        uint4 x;
-                        if (bf) {
-                            x = make_uint4(pack_bf16(v[q * 8], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]), pack_bf16(v[q * 8 + 4], v[q * 8 + 5]),
-                                           pack_bf16(v[q * 8 + 6], v[q * 8 + 7]));
-                        } else {
-                            x = make_uint4(pack_f16(v[q * 8], v[q * 8 + 1]), pack_f16(v[q * 8 + 2], v[q * 8 + 3]), pack_f16(v[q * 8 + 4], v[q * 8 + 5]),
-                                           pack_f16(v[q * 8 + 6], v[q * 8 + 7]));
-                        }
-                        sts128(stage_s + lane * 128 + ((q ^ (lane & 7)) << 4), x);
-                    }
-                    __syncwarp();
-                    const int ccol = col + rb_chunk * 8;
-                    uint16_t* c16 = static_cast<uint16_t*>(P.C16);
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const int rr = rb_row + 4 * k;
-                        const uint4 x = lds128(stage_s + rr * 128 + ((rb_chunk ^ (rr & 7)) << 4));
-                        if (rbase + rr < P.M && ccol < P.N) *reinterpret_cast<uint4*>(c16 + (size_t)(rbase + rr) * P.ldc16 + ccol) = x;
-                    }
-                    __syncwarp();
-                }
-            }
+            const uint32_t tacc = tmem + (static_cast<uint32_t>(E.qd * 32) << 16) + b * GN + E.half * (GN / 2);
+            if (mode == 0) { if (bf) epilogue_tile<0, true>(P, tc, E, tacc, res0, GSKIPV); else epilogue_tile<0, false>(P, tc, E, tacc, res0, GSKIPV); }
+            else if (mode == 1) { if (bf) epilogue_tile<1, true>(P, tc, E, tacc, res0, GSKIPV); else epilogue_tile<1, false>(P, tc, E, tacc, res0, GSKIPV); }
+            else { if (bf) epilogue_tile<2, true>(P, tc, E, tacc, res0, GSKIPV); else epilogue_tile<2, false>(P, tc, E, tacc, res0, GSKIPV); }
             fence_before_thread_sync();
             mbar_arrive(&acc_empty[b]);
             if (it == 0 && warp == kGStages + 1 && lane == 0) GPROF(6);
@@ -347,7 +414,10 @@ int launch_gemm_tc(const TcGemmProblem* probs, int count, int dtype16, cudaStrea
         tiles += ((q.M + GM - 1) / GM) * d.tiles_n;
     }
     g.total_tiles = tiles;
-    const size_t smem = 1024 + (size_t)kGStages * kGStageBytes + 256 + kGEpiWarps * 4096;
+#ifdef DCLIP_GEMM_PROF
+    { static int launches = 0; g.prof_slot = launches++ & 7; const char* e = getenv("DCLIP_GEMM_SKIP"); g.debug_skip = e ? atoi(e) : 0; }
+#endif
+    const size_t smem = 1024 + (size_t)kGStages * kGStageBytes + 256 + kGEpiWarps * 4096 + GN * sizeof(float);
     DCLIP_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_gemm_tc<<<min(tiles, sm_count()), kGThreads, smem, st>>>(g);
     DCLIP_LAUNCH_OK("k_gemm_tc");
@@ -360,5 +430,9 @@ int launch_gemm_tc(const TcGemmProblem* probs, int count, int dtype16, cudaStrea
 extern "C" int dclip_debug_gemm_prof(long long* out16) {
     if (cudaDeviceSynchronize() != cudaSuccess) return -1;
     return cudaMemcpyFromSymbol(out16, dclip::g_gemm_prof, 16 * sizeof(long long)) == cudaSuccess ? 0 : -1;
+}
+extern "C" int dclip_debug_gemm_prof_ring(long long* out128) {
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    return cudaMemcpyFromSymbol(out128, dclip::g_gemm_prof_ring, 128 * sizeof(long long)) == cudaSuccess ? 0 : -1;
 }
 #endif

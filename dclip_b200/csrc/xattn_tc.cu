@@ -8,9 +8,9 @@
 //     k_ln_fwd16       LayerNorm of both sides, 16-bit module outputs + (mean, rstd)                           (K4)
 //   backward (autograd of the same, training/train_contrastive_teacher.py:361), 5 launches (+2 for input gradients):
 //     k_ln_bwd16       dZ (16-bit) + per-block column partials of dgamma, dbeta and the out-projection bias gradient
-//     k_gemm_tc        dWo = dZ^T O (straight into the 16-bit parameter gradients), dO = dZ Wo                4 problems
+//     k_gemm_tc        dO = dZ Wo                                                                              2 problems
 //     k_attn_bwd_tc    dQ, dK|dV (16-bit) + per-batch column partials of the in-projection bias gradients
-//     k_gemm_tc        dWq = dQ^T X, dWkv = dKV^T X (straight into the parameter gradients)                   4 problems
+//     k_gemm_tc        dWq = dQ^T X, dWkv = dKV^T X, dWo = dZ^T O (straight into the parameter gradients)      6 problems
 //     k_vec_finalize   the eight small gradient vectors from their partials (fixed order: bit-reproducible)
 // Statistics (softmax, LayerNorm, all partial sums) are fp32.  Nothing is widened to fp32 in HBM except Z.
 #include "attn_tc.h"
@@ -316,13 +316,13 @@ int xattn_bwd_tc(const void* text, const void* image, int64_t B, int64_t T, int6
     lb.d = D; lb.nblk0 = W.nblk_t; lb.part = reinterpret_cast<float*>(X + W.lnpart);
     if (dtype == DCLIP_BF16) { if (int e = launch_ln_bwd<__nv_bfloat16>(lb, W.nblk_t + W.nblk_i, st)) return e; }
     else { if (int e = launch_ln_bwd<__half>(lb, W.nblk_t + W.nblk_i, st)) return e; }
-    // (3') out-projection backward: dWo = dZ^T O (into the parameter gradients), dO = dZ Wo
-    TcGemmProblem pr[4];
-    pr[0] = out16(tcg(X + W.dZt, D, true, S + L.Ot, D, true, D, D, nt), grads[2], D);
-    pr[1] = out16(tcg(X + W.dZi, D, true, S + L.Oi, D, true, D, D, ni), grads[6], D);
-    pr[2] = out16(tcg(X + W.dZt, D, false, params[2], D, true, nt, D, D), X + W.dOt, D);
-    pr[3] = out16(tcg(X + W.dZi, D, false, params[6], D, true, ni, D, D), X + W.dOi, D);
-    if (int e = launch_gemm_tc(pr, 4, dtype, st)) return e;
+    // (3') out-projection backward: dO = dZ Wo.  The weight gradients dWo = dZ^T O are leaves of the dependency graph with a long
+    // contraction (K = B T rows: a tile takes 3x as long as a dO tile and would set this launch's critical path), so they ride
+    // with the in-projection weight gradients below, whose tiles are as long and leave SMs idle (108 of 148).
+    TcGemmProblem pr[2];
+    pr[0] = out16(tcg(X + W.dZt, D, false, params[2], D, true, nt, D, D), X + W.dOt, D);
+    pr[1] = out16(tcg(X + W.dZi, D, false, params[6], D, true, ni, D, D), X + W.dOi, D);
+    if (int e = launch_gemm_tc(pr, 2, dtype, st)) return e;
     // (2') attention cores backward (+ in-projection bias gradient partials per batch element)
     AttnTcProblem ap{};
     ap.B = (int)B; ap.T = (int)T; ap.R = (int)R; ap.d = D; ap.heads = heads; ap.dtype16 = dtype;
@@ -335,12 +335,14 @@ int xattn_bwd_tc(const void* text, const void* image, int64_t B, int64_t T, int6
     // (1') in-projection weight gradients (rows 0..d = q, d..3d = k|v), straight into the parameter gradients
     char* g_t2i = static_cast<char*>(grads[0]);
     char* g_i2t = static_cast<char*>(grads[4]);
-    TcGemmProblem pw[4];
+    TcGemmProblem pw[6];
     pw[0] = out16(tcg(X + W.dQt, D, true, text, D, true, D, D, nt), g_t2i, D);
-    pw[1] = out16(tcg(X + W.dKVi, 2 * D, true, image, D, true, 2 * D, D, ni), g_t2i + dd2, D);
-    pw[2] = out16(tcg(X + W.dQi, D, true, image, D, true, D, D, ni), g_i2t, D);
-    pw[3] = out16(tcg(X + W.dKVt, 2 * D, true, text, D, true, 2 * D, D, nt), g_i2t + dd2, D);
-    if (int e = launch_gemm_tc(pw, 4, dtype, st)) return e;
+    pw[1] = out16(tcg(X + W.dKVt, 2 * D, true, text, D, true, 2 * D, D, nt), g_i2t + dd2, D);
+    pw[2] = out16(tcg(X + W.dZt, D, true, S + L.Ot, D, true, D, D, nt), grads[2], D);              // dWo (text side)
+    pw[3] = out16(tcg(X + W.dKVi, 2 * D, true, image, D, true, 2 * D, D, ni), g_t2i + dd2, D);
+    pw[4] = out16(tcg(X + W.dQi, D, true, image, D, true, D, D, ni), g_i2t, D);
+    pw[5] = out16(tcg(X + W.dZi, D, true, S + L.Oi, D, true, D, D, ni), grads[6], D);              // dWo (image side)
+    if (int e = launch_gemm_tc(pw, 6, dtype, st)) return e;      // long contractions first: a persistent CTA that gets two tiles gets a short second one
     if (d_text) {
         // input gradients: residual path (dZ) + query projection, then + key/value projection of the other direction
         const char* w_t2i = static_cast<const char*>(params[0]);
