@@ -54,6 +54,22 @@ int check_common(int64_t m, int64_t d) {
 
 }  // namespace
 
+namespace dclip {
+// out = x * (*scale): the upstream gradient of the scalar loss (loss.backward(), training/train_contrastive_teacher.py:361) applied to
+// the gradients the fused forward+backward call already produced; the factor stays on the device (no host sync, graph-capturable).
+template <typename T>
+__global__ void __launch_bounds__(256) k_scale_grad(const T* __restrict__ x, int64_t groups, const float* __restrict__ scale, T* __restrict__ out) {
+    const int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (g >= groups) return;
+    const float s = *scale;
+    float v[8];
+    load8<T>(x + g * 8, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] *= s;
+    store8<T>(out + g * 8, v);
+}
+}  // namespace dclip
+
 extern "C" {
 
 int dclip_loss_prep(const void* x, const void* teacher, int64_t m, int64_t d, int dtype, void* x_hat, int op_dtype,
@@ -600,6 +616,18 @@ int dclip_distill_loss_teachers(const void* s_img, const void* s_txt, const void
                                 void* d_s_img, void* d_s_txt, void* workspace, size_t workspace_bytes, int path, void* stream) {
     return distill_loss_impl(2, s_img, s_txt, t_img, t_txt, B, d, dtype, temperature, w_img, w_txt, w_con, grad_scale, losses, d_s_img,
                              d_s_txt, nullptr, workspace, workspace_bytes, path, stream);
+}
+
+int dclip_scale_grad(const void* x, int64_t n, int dtype, const float* scale, void* out, void* stream) {
+    DCLIP_REQUIRE(x && scale && out && n > 0 && n % 8 == 0, "scale_grad: bad arguments (n must be a positive multiple of 8)");
+    DCLIP_REQUIRE(dclip::aligned16(x) && dclip::aligned16(out), "scale_grad: pointers must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t groups = n / 8;
+    DCLIP_DISPATCH_DTYPE(dtype, {
+        dclip::k_scale_grad<T><<<(unsigned)dclip::ceil_div(groups, 256), 256, 0, st>>>(static_cast<const T*>(x), groups, scale, static_cast<T*>(out));
+    });
+    DCLIP_LAUNCH_OK("k_scale_grad");
+    return DCLIP_OK;
 }
 
 }  // extern "C"

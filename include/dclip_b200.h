@@ -326,6 +326,12 @@ int dclip_xattn_bwd(const void* text, const void* image, int64_t B, int64_t T, i
                     const void* const* params, const void* saved, const void* d_text_out, const void* d_image_out,
                     void* const* grads, void* d_text, void* d_image, void* scratch, size_t scratch_bytes, void* stream);
 
+/* out[i] = x[i] * (*scale), scale a float on the DEVICE: the upstream gradient of the scalar loss
+ * (`loss.backward()`, training/train_contrastive_teacher.py:361; CLIP_image_distillation.py:634 through Lightning) applied to
+ * the gradients that dclip_distill_loss_fwd_bwd already produced - no host read of the factor, graph-capturable.
+ * n % 8 == 0; x / out of `dtype`, 16-byte aligned; out may alias x. */
+int dclip_scale_grad(const void* x, int64_t n, int dtype, const float* scale, void* out, void* stream);
+
 /* aggregation(attended [B, L, d], temperature = 2.0) -> [B, d]; weights: float[B, L] softmax weights
  * saved for the backward (may be NULL for inference). */
 int dclip_aggregate_fwd(const void* x, int64_t B, int64_t L, int64_t d, int dtype, float temperature, void* out,

@@ -63,6 +63,15 @@ def test_pure_infonce_and_autograd_wrappers(built_library):
     assert abs(float(loss) - float(ref)) < FP32_TOL * abs(float(ref)) + 1e-7
     assert _rel(a.grad, 3.0 * ga) < FP32_TOL and _rel(b.grad, 3.0 * gb) < FP32_TOL
 
+    # 16-bit gradients scaled by a device-side upstream factor (dclip_scale_grad): exact 0.5 x, so bit-identical halves
+    a16 = s_img.to(dev).bfloat16().requires_grad_(True)
+    b16 = s_txt.to(dev).bfloat16().requires_grad_(True)
+    L.compute_contrastive_loss(a16, b16, temperature=0.05, path="fp32").backward()
+    g1 = a16.grad.clone()
+    a16.grad = None
+    (0.5 * L.compute_contrastive_loss(a16, b16, temperature=0.05, path="fp32")).backward()
+    assert torch.equal(a16.grad.float(), 0.5 * g1.float())
+
     a2 = s_img.to(dev).requires_grad_(True)
     cl = L.cosine_distillation_loss(a2, t_img.to(dev))
     cl.backward()
