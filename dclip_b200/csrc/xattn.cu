@@ -121,6 +121,147 @@ static GemmProblem gemm(const float* A, int lda, bool tA, const float* B, int ld
 }
 
 // ---------------------------------------------------------------------------------------------
+// The same grouped fp32 GEMM on tcgen05: bf16 x 3 operand splitting.
+// An fp32 value is x = h + m + l with three bf16 terms (8 + 8 + 8 mantissa bits: exact to 2^-27 |x|, fp32's full exponent
+// range - gradients of 1e-8 keep their precision, which an fp16 split would lose).  The product of two split operands
+// needs six of the nine term products (h l, l h, m m, h m, m h, h h; the rest is below 2^-26), and a sum of products over k
+// of six term pairs is ONE contraction over 6 K: the terms are written side by side along K,
+//     A' = [h | l | m | h | m | h],   B' = [l | h | m | m | h | h]      (smallest products first: they are accumulated
+//                                                                         before the large h h term can swamp them)
+// and the 16-bit grouped tcgen05 kernel (gemm_tc.cu) runs unchanged on [M, 6 K] x [N, 6 K] with fp32 accumulation in TMEM.
+// Measured against an fp64 product (tools/exp_split_gemm.py, N(0,1) operands): 4.7e-7 at K = 512, 7.3e-7 at K = 768, 2.6e-6 at
+// K = 2464, torch's fp32 matmul (TF32 off) 4.1e-7 / 5.0e-7 / 8.9e-7 - inside the FP32 tier's 1e-5, at 6x the MMA work of a
+// 16-bit GEMM instead of CUDA-core FFMA (configs[0] teacher step: 1287 us of k_gemm_group per step).
+// This is what stands in for the TF32 tier north_star mentions: kind::tf32 keeps 10 mantissa bits (1e-3); the reference trains
+// its teacher in fp32 with TF32 off (torch default), so the drop-in keeps fp32 accuracy.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSplitSegs = 6;
+struct SplitJob {
+    const float* src; __nv_bfloat16* dst;
+    int rows, cols, ld;        // source matrix [rows, cols], row stride ld
+    int out_rows, out_cols;    // iteration space: K-major operand rows x Kp;  MN-major operand Kp x ldd
+    int ldd, Kp, kmajor, role; // role 0 = A operand, 1 = B operand
+};
+struct SplitGroup { SplitJob j[16]; int count; };
+
+__global__ void __launch_bounds__(256) k_split_bf16x3(const __grid_constant__ SplitGroup g) {
+    const SplitJob& J = g.j[blockIdx.y];
+    const int ncg = J.out_cols >> 3;
+    const long long total = (long long)J.out_rows * ncg;
+    const bool vec = (J.ld & 3) == 0 && (reinterpret_cast<uintptr_t>(J.src) & 15) == 0;
+    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+        const int r = (int)(e / ncg), c = (int)(e - (long long)r * ncg) * 8;
+        float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (r < J.rows) {
+            const float* sp = J.src + (size_t)r * J.ld + c;
+            if (vec && c + 8 <= J.cols) {
+                const float4 a = *reinterpret_cast<const float4*>(sp), b = *reinterpret_cast<const float4*>(sp + 4);
+                x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) if (c + i < J.cols) x[i] = sp[i];
+            }
+        }
+        uint32_t t[3][4];      // terms h, m, l: 8 bf16 each
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+            float r0 = x[i], r1 = x[i + 1];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const __nv_bfloat16 b0 = __float2bfloat16_rn(r0), b1 = __float2bfloat16_rn(r1);
+                r0 -= __bfloat162float(b0); r1 -= __bfloat162float(b1);       // exact: the remainder of a rounding fits fp32
+                t[q][i >> 1] = (uint32_t)__bfloat16_as_ushort(b0) | ((uint32_t)__bfloat16_as_ushort(b1) << 16);
+            }
+        }
+        // A' = [h l m h m h], B' = [l h m m h h]  (0 = h, 1 = m, 2 = l)
+        const int seqA[kSplitSegs] = {0, 2, 1, 0, 1, 0}, seqB[kSplitSegs] = {2, 0, 1, 1, 0, 0};
+#pragma unroll
+        for (int sgi = 0; sgi < kSplitSegs; ++sgi) {
+            const int q = J.role ? seqB[sgi] : seqA[sgi];
+            const size_t off = J.kmajor ? (size_t)r * J.ldd + (size_t)sgi * J.Kp + c : ((size_t)sgi * J.Kp + r) * J.ldd + c;
+            *reinterpret_cast<uint4*>(J.dst + off) = make_uint4(t[q][0], t[q][1], t[q][2], t[q][3]);
+        }
+    }
+}
+
+struct SplitScratch { char* base; size_t bytes; };
+
+// fp32 tier on tensor cores?  (sm_100 device; DCLIP_XATTN_SPLIT=0 keeps the CUDA-core GEMM for A/B timing and tests)
+static bool gemm_split_enabled() {
+    if (!device_is_sm100()) return false;
+    const char* e = getenv("DCLIP_XATTN_SPLIT");
+    return !(e && e[0] == '0');
+}
+static size_t split_fwd_bytes(int64_t B, int64_t T, int64_t R, int64_t d) {
+    const size_t dp = (size_t)(d + 7) / 8 * 8;
+    return ((size_t)B * (T + R) + 6 * d + 16) * kSplitSegs * dp * 2 + 16 * 256;
+}
+static size_t split_bwd_bytes(int64_t B, int64_t T, int64_t R, int64_t d) {
+    const size_t dp = (size_t)(d + 7) / 8 * 8;
+    return (((size_t)B * (T + R) + 32) * 24 * dp + 24 * dp * dp) * 2 + 16 * 256;
+}
+
+static int launch_gemm_group_split(const GemmGroup& g, const SplitScratch& sc, cudaStream_t st) {
+    SplitGroup sg{};
+    TcGemmProblem pr[8];
+    size_t used = 0;
+    auto operand = [&](const float* src, bool kmajor, int role, int mn, int K, int ld, int Kp, const __nv_bfloat16** out, int* ldd) -> int {
+        const int rows = kmajor ? mn : K, cols = kmajor ? K : mn;
+        for (int i = 0; i < sg.count; ++i) {
+            const SplitJob& J = sg.j[i];
+            if (J.src == src && J.kmajor == (int)kmajor && J.role == role && J.rows == rows && J.cols == cols && J.ld == ld) { *out = J.dst; *ldd = J.ldd; return DCLIP_OK; }
+        }
+        if (sg.count == 16) return fail(DCLIP_ERR_INVALID, "gemm split: too many distinct operands");
+        SplitJob J{};
+        J.src = src; J.rows = rows; J.cols = cols; J.ld = ld; J.Kp = Kp; J.kmajor = kmajor; J.role = role;
+        if (kmajor) { J.ldd = kSplitSegs * Kp; J.out_rows = mn; J.out_cols = Kp; }
+        else { J.ldd = (mn + 7) / 8 * 8; J.out_rows = Kp; J.out_cols = J.ldd; }
+        const size_t bytes = (kmajor ? (size_t)mn * J.ldd : (size_t)kSplitSegs * Kp * J.ldd) * 2;
+        if (used + bytes > sc.bytes) return fail(DCLIP_ERR_WORKSPACE, "gemm split: scratch too small (%zu + %zu > %zu)", used, bytes, sc.bytes);
+        J.dst = reinterpret_cast<__nv_bfloat16*>(sc.base + used);
+        used += align_up(bytes, 256);
+        sg.j[sg.count++] = J;
+        *out = J.dst; *ldd = J.ldd;
+        return DCLIP_OK;
+    };
+    for (int i = 0; i < g.count; ++i) {
+        const GemmProblem& P = g.p[i];
+        const int Kp = (P.K + 7) / 8 * 8;
+        const __nv_bfloat16* A2 = nullptr; const __nv_bfloat16* B2 = nullptr;
+        int lda2 = 0, ldb2 = 0;
+        if (int e = operand(P.A, !P.transA, 0, P.M, P.K, P.lda, Kp, &A2, &lda2)) return e;
+        if (int e = operand(P.B, P.transB != 0, 1, P.N, P.K, P.ldb, Kp, &B2, &ldb2)) return e;
+        TcGemmProblem q{};
+        q.A = A2; q.B = B2; q.C = P.C; q.bias = P.bias; q.residual = P.residual; q.C16 = nullptr;
+        q.M = P.M; q.N = P.N; q.K = kSplitSegs * Kp; q.lda = lda2; q.ldb = ldb2; q.ldc = P.ldc; q.ldr = P.ldr;
+        q.a_mn = P.transA ? 1 : 0; q.b_mn = P.transB ? 0 : 1; q.accumulate = P.accumulate; q.alpha = P.alpha;
+        q.bias_kind = 0; q.res_kind = 0;
+        pr[i] = q;
+    }
+    long long mx = 0;
+    for (int i = 0; i < sg.count; ++i) mx = max(mx, (long long)sg.j[i].out_rows * (sg.j[i].out_cols >> 3));
+    if (mx > 0) {
+        k_split_bf16x3<<<dim3((unsigned)min((long long)1184, (mx + 255) / 256), (unsigned)sg.count), 256, 0, st>>>(sg);
+        DCLIP_LAUNCH_OK("k_split_bf16x3");
+    }
+    return launch_gemm_tc(pr, g.count, DCLIP_BF16, st);
+}
+
+// the fp32 grouped GEMM: tcgen05 through operand splitting where a scratch area was provided, CUDA cores otherwise
+static int run_gemm_group(const GemmGroup& g, const SplitScratch& sc, cudaStream_t st) {
+    if (sc.base) {
+        bool ok = true;
+        for (int i = 0; i < g.count; ++i) {
+            const GemmProblem& P = g.p[i];
+            ok = ok && P.N % 8 == 0 && P.ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(P.C) & 15) == 0 && (!P.residual || (P.ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(P.residual) & 15) == 0)) &&
+                 (!P.bias || (reinterpret_cast<uintptr_t>(P.bias) & 15) == 0);
+        }
+        if (ok) return launch_gemm_group_split(g, sc, st);
+    }
+    return launch_gemm_group(g, st);
+}
+
+// ---------------------------------------------------------------------------------------------
 // casts and column sums
 // ---------------------------------------------------------------------------------------------
 template <typename T>
@@ -654,7 +795,8 @@ extern "C" {
 
 size_t dclip_xattn_saved_bytes(int64_t B, int64_t T, int64_t R, int64_t d, int dtype) {
     const size_t base = xlayout(B, T, R, d, dtype != DCLIP_F32).total * sizeof(float) + 256;
-    return dtype != DCLIP_F32 ? max(base, xattn_tc_saved_bytes(B, T, R, d)) : base;     // either 16-bit tier may be chosen at call time
+    if (dtype == DCLIP_F32) return base + 256 + split_fwd_bytes(B, T, R, d);      // + the split operands of the tensor-core fp32 GEMMs
+    return max(base, xattn_tc_saved_bytes(B, T, R, d));     // either 16-bit tier may be chosen at call time
 }
 // scratch for the backward: dZ, zhat, dO (text+image), dQ, dKV (both) + widened output grads
 size_t dclip_xattn_bwd_scratch_bytes(int64_t B, int64_t T, int64_t R, int64_t d, int dtype) {
@@ -662,7 +804,8 @@ size_t dclip_xattn_bwd_scratch_bytes(int64_t B, int64_t T, int64_t R, int64_t d,
     size_t f = (nt + ni) * d * 6 + (nt + ni) * 2 * d + 1024;       // dY, dZ, zhat, dO, dQ, dX + dKV
     if (dtype != DCLIP_F32) { f += (nt + ni) * d; for (int i = 0; i < kParamCount; ++i) f += param_numel(i, d) + 64; f += (nt + ni) * d * 2 + 1024; }
     const size_t base = f * sizeof(float) + 4096;
-    return dtype != DCLIP_F32 ? max(base, xattn_tc_scratch_bytes(B, T, R, d)) : base;
+    if (dtype == DCLIP_F32) return base + 256 + split_bwd_bytes(B, T, R, d);
+    return max(base, xattn_tc_scratch_bytes(B, T, R, d));
 }
 
 int dclip_xattn_fwd(const void* text, const void* image, int64_t B, int64_t T, int64_t R, int64_t d, int heads, int dtype,
@@ -676,6 +819,12 @@ int dclip_xattn_fwd(const void* text, const void* image, int64_t B, int64_t T, i
     const XLayout L = xlayout(B, T, R, d, wide);
     if (saved_bytes < L.total * sizeof(float)) return fail(DCLIP_ERR_WORKSPACE, "xattn_fwd: saved buffer too small (%zu < %zu)", saved_bytes, L.total * sizeof(float));
     const int hd = (int)(d / heads);
+    // fp32 inputs on an sm_100 device: the four GEMM launches run on tcgen05 through bf16 x 3 operand splitting (scratch behind the saved tensors)
+    SplitScratch sc{nullptr, 0};
+    if (!wide && d % 8 == 0 && gemm_split_enabled()) {
+        const size_t off = align_up(L.total * sizeof(float), 256);
+        if (saved_bytes >= off + split_fwd_bytes(B, T, R, d)) sc = SplitScratch{static_cast<char*>(saved) + off, split_fwd_bytes(B, T, R, d)};
+    }
     const size_t sm_t2i = attn_fwd_smem((int)T, (int)R, hd), sm_i2t = attn_fwd_smem((int)R, (int)T, hd);
     if (max(sm_t2i, sm_i2t) > 220 * 1024) return fail(DCLIP_ERR_UNSUPPORTED, "xattn_fwd: sequence x head_dim too large for shared memory");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -724,7 +873,7 @@ int dclip_xattn_fwd(const void* text, const void* image, int64_t B, int64_t T, i
         g.p[2] = gemm(Xi, D, false, Wp[4], D, true, S + L.Qi, D, ni, D, D, Wp[5]);
         g.p[3] = gemm(Xt, D, false, Wp[4] + (size_t)d * d, D, true, S + L.KVt, 2 * D, nt, 2 * D, D, Wp[5] + d);
         g.count = 4;
-        if (int e = launch_gemm_group(g, st)) return e;
+        if (int e = run_gemm_group(g, sc, st)) return e;
     }
     // (2) attention cores
     AttnArgs a{};
@@ -752,7 +901,7 @@ int dclip_xattn_fwd(const void* text, const void* image, int64_t B, int64_t T, i
         g2.p[0] = gemm(S + L.Ot, D, false, Wp[2], D, true, S + L.Zt, D, nt, D, D, Wp[3], Xt, D);
         g2.p[1] = gemm(S + L.Oi, D, false, Wp[6], D, true, S + L.Zi, D, ni, D, D, Wp[7], Xi, D);
         g2.count = 2;
-        if (int e = launch_gemm_group(g2, st)) return e;
+        if (int e = run_gemm_group(g2, sc, st)) return e;
     }
     // (4) LayerNorm
     if (!wide) {
@@ -833,6 +982,11 @@ int dclip_xattn_bwd(const void* text, const void* image, int64_t B, int64_t T, i
         for (int i = 0; i < kParamCount; ++i) { G[i] = static_cast<float*>(grads[i]); Wp[i] = static_cast<const float*>(params[i]); }
     }
     if (o * sizeof(float) > scratch_bytes) return fail(DCLIP_ERR_WORKSPACE, "xattn_bwd: scratch too small (%zu < %zu)", scratch_bytes, o * sizeof(float));
+    SplitScratch sc{nullptr, 0};      // fp32 inputs: tensor-core GEMMs through operand splitting (see run_gemm_group)
+    if (!wide && d % 8 == 0 && gemm_split_enabled()) {
+        const size_t off = align_up(o * sizeof(float), 256);
+        if (scratch_bytes >= off + split_bwd_bytes(B, T, R, d)) sc = SplitScratch{static_cast<char*>(scratch) + off, split_bwd_bytes(B, T, R, d)};
+    }
 
     // (4') LayerNorm backward: dZ, zhat; dgamma = colsum(dY * zhat), dbeta = colsum(dY)
     k_ln_bwd<<<(unsigned)ceil_div(nt, 8), 256, 0, st>>>(dyt, S + L.Zt, Wp[8], S + L.St, nt, D, dZt, zht);
@@ -864,7 +1018,7 @@ int dclip_xattn_bwd(const void* text, const void* image, int64_t B, int64_t T, i
         g.p[2] = gemm(dZt, D, false, Wp[2], D, false, dOt, D, nt, D, D);
         g.p[3] = gemm(dZi, D, false, Wp[6], D, false, dOi, D, ni, D, D);
         g.count = 4;
-        if (int e = launch_gemm_group(g, st)) return e;
+        if (int e = run_gemm_group(g, sc, st)) return e;
     }
     // (2') attention cores backward
     AttnArgs a{};
@@ -914,19 +1068,19 @@ int dclip_xattn_bwd(const void* text, const void* image, int64_t B, int64_t T, i
         g2.p[2] = gemm(dQi, D, true, Xi, D, false, G[4], D, D, D, ni);
         g2.p[3] = gemm(dKVt, 2 * D, true, Xt, D, false, G[4] + (size_t)d * d, D, 2 * D, D, nt);
         g2.count = 4;
-        if (int e = launch_gemm_group(g2, st)) return e;
+        if (int e = run_gemm_group(g2, sc, st)) return e;
         if (d_text) {
             // input gradients: residual path + query projection + key/value projection of the other direction
             GemmGroup g3{};
             g3.p[0] = gemm(dQt, D, false, Wp[0], D, false, dXt, D, nt, D, D, nullptr, dZt, D);
             g3.p[1] = gemm(dQi, D, false, Wp[4], D, false, dXi, D, ni, D, D, nullptr, dZi, D);
             g3.count = 2;
-            if (int e = launch_gemm_group(g3, st)) return e;
+            if (int e = run_gemm_group(g3, sc, st)) return e;
             GemmGroup g4{};
             g4.p[0] = gemm(dKVt, 2 * D, false, Wp[4] + (size_t)d * d, D, false, dXt, D, nt, D, 2 * D, nullptr, nullptr, 0, true);
             g4.p[1] = gemm(dKVi, 2 * D, false, Wp[0] + (size_t)d * d, D, false, dXi, D, ni, D, 2 * D, nullptr, nullptr, 0, true);
             g4.count = 2;
-            if (int e = launch_gemm_group(g4, st)) return e;
+            if (int e = run_gemm_group(g4, sc, st)) return e;
         }
     }
     if (d_text) {
