@@ -36,7 +36,9 @@ struct TcGemmDev {
     float* C; const void* bias; const void* residual; int bias_kind, res_kind;
     int M, N, K, ldc, ldr;
     int a_mn, b_mn;
-    int tiles_n, tile_begin;      // tiles of this problem occupy [tile_begin, tile_begin + tiles_m * tiles_n)
+    int tiles_n, tile_begin;      // tiles of this problem occupy [tile_begin, tile_begin + slices * tiles_m * tiles_n)
+    int tiles_mn, kb_per_slice;   // split-K: slice = local tile / tiles_mn, k-blocks [slice * kb_per_slice, ...)
+    long long split_stride;
     int accumulate;
     void* C16; int c16_kind, ldc16;   // optional 16-bit copy of C (0 none, 1 bf16, 2 fp16); C itself may then be null
     float alpha;
@@ -74,7 +76,7 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) { const __nv_bfloat162 v = __floats2bfloat162_rn(a, b); return *reinterpret_cast<const uint32_t*>(&v); }
 __device__ __forceinline__ uint32_t pack_f16(float a, float b) { const __half2 v = __floats2half2_rn(a, b); return *reinterpret_cast<const uint32_t*>(&v); }
 
-struct TileCoord { int pi, m0, n0, nkb; };
+struct TileCoord { int pi, m0, n0, nkb, kb0; long long c_off; };      // k-blocks [kb0, kb0 + nkb); c_off: split-K partial offset
 
 // ---- epilogue.  TMEM hands each thread one output ROW (lane) and 32 consecutive columns per load; global memory wants a
 // warp on few rows (a store in which every lane touches a different row costs ~32 memory-pipe cycles).  So a chunk goes
@@ -224,9 +226,13 @@ __device__ __forceinline__ TileCoord tile_coord(const TcGemmArgs& g, int tile) {
     for (int i = 1; i < g.count; ++i)
         if (tile >= g.p[i].tile_begin) pi = i;
     const TcGemmDev& P = g.p[pi];
-    const int local = tile - P.tile_begin;
+    int local = tile - P.tile_begin;
+    const int slice = local / P.tiles_mn;
+    local -= slice * P.tiles_mn;
     const int tm = local / P.tiles_n, tn = local - tm * P.tiles_n;
-    return TileCoord{pi, tm * GM, tn * GN, (P.K + GKS - 1) / GKS};
+    const int nkb_all = (P.K + GKS - 1) / GKS;
+    const int kb0 = slice * P.kb_per_slice;
+    return TileCoord{pi, tm * GM, tn * GN, min(P.kb_per_slice, nkb_all - kb0), kb0, (long long)slice * P.split_stride};
 }
 
 // Persistent: gridDim.x CTAs walk the tile list with stride gridDim.x.  The TMA ring keeps flowing across
@@ -272,7 +278,7 @@ __global__ void __launch_bounds__(kGThreads, 1) k_gemm_tc(const __grid_constant_
                 // my k-blocks of this tile: those with (q0 + kb) % kGStages == warp
                 int kb = (warp - q0 % kGStages + kGStages) % kGStages;
                 for (; kb < tc.nkb && ok; kb += kGStages, phase ^= 1) {
-                    const int k0 = kb * GKS;
+                    const int k0 = (tc.kb0 + kb) * GKS;
                     ok = mbar_wait(&empty[warp], phase ^ 1, kSpinG);
                     if (warp == 0 && kb == 0 && tile == (int)blockIdx.x) GPROF(2);
                     mbar_arrive_expect_tx(&full[warp], kGStageBytes);
@@ -334,7 +340,8 @@ __global__ void __launch_bounds__(kGThreads, 1) k_gemm_tc(const __grid_constant_
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const TileCoord tc = tile_coord(g, tile);
-            const TcGemmDev P = g.p[tc.pi];
+            TcGemmDev P = g.p[tc.pi];
+            if (P.C) P.C += tc.c_off;            // split-K: this slice's partial product
             const int b = it & 1;
             if (P.bias) {      // uniform over the CTA's epilogue warps (same tile)
                 float bv = 0.f;
@@ -374,6 +381,13 @@ __global__ void __launch_bounds__(kGThreads, 1) k_gemm_tc(const __grid_constant_
 
 int* tc_error_flag();   // loss_tc.cu
 
+int gemm_tc_slices(int K, int ksplit) {
+    const int nkb = (K + GKS - 1) / GKS;
+    const int ks = ksplit > 1 ? min(ksplit, nkb) : 1;
+    const int per = (nkb + ks - 1) / ks;
+    return (nkb + per - 1) / per;
+}
+
 // dtype16: 1 = bf16, 2 = fp16 (dclip_dtype values)
 int launch_gemm_tc(const TcGemmProblem* probs, int count, int dtype16, cudaStream_t st) {
     if (count < 1 || count > kTcGemmMax) return fail(DCLIP_ERR_INVALID, "gemm_tc: 1..%d problems per launch", kTcGemmMax);
@@ -411,7 +425,14 @@ int launch_gemm_tc(const TcGemmProblem* probs, int count, int dtype16, cudaStrea
         d.alpha = q.alpha == 0.f ? 1.0f : q.alpha;
         d.tiles_n = (q.N + GN - 1) / GN;
         d.tile_begin = tiles;
-        tiles += ((q.M + GM - 1) / GM) * d.tiles_n;
+        d.tiles_mn = ((q.M + GM - 1) / GM) * d.tiles_n;
+        const int nkb = (q.K + GKS - 1) / GKS;
+        int ks = q.ksplit > 1 ? min(q.ksplit, nkb) : 1;
+        if (ks > 1 && (q.bias || q.residual || q.accumulate || q.C16 || !q.C)) return fail(DCLIP_ERR_INVALID, "gemm_tc: split-K problem %d must be a plain fp32 product", i);
+        d.kb_per_slice = (nkb + ks - 1) / ks;
+        ks = (nkb + d.kb_per_slice - 1) / d.kb_per_slice;            // no empty slice
+        d.split_stride = ks > 1 ? q.split_stride : 0;
+        tiles += ks * d.tiles_mn;
     }
     g.total_tiles = tiles;
 #ifdef DCLIP_GEMM_PROF

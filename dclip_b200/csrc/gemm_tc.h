@@ -17,9 +17,13 @@ struct TcGemmProblem {
     int ldc16;      // row stride of C16 (0 = ldc); C may be null when only the 16-bit output is wanted
     int bias_kind, res_kind;
     float alpha;    // C = alpha * A'B' + ... (0 = 1)
+    int ksplit;     // > 1: the contraction is cut into `ksplit` slices of whole 64-wide k-blocks, slice s writes its partial
+    long long split_stride;   // product to C + s * split_stride (fp32 output only, no bias / residual / accumulate); the caller sums
 };
 
 int launch_gemm_tc(const TcGemmProblem* probs, int count, int dtype16, cudaStream_t st);
+// number of slices a problem with contraction length K and a requested `ksplit` is actually cut into (the partials to sum)
+int gemm_tc_slices(int K, int ksplit);
 // CTA-pair kernel with 256 x 384 tiles (gemm_pair.cu): plain fp32 outputs only, at most 2 problems
 bool gemm_pair_ok(const TcGemmProblem& q);
 // Optional fused epilogue of the distillation gradients (normalise backward + cosine-term gradient, per problem):

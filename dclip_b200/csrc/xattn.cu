@@ -136,6 +136,8 @@ static GemmProblem gemm(const float* A, int lda, bool tA, const float* B, int ld
 // its teacher in fp32 with TF32 off (torch default), so the drop-in keeps fp32 accuracy.
 // ---------------------------------------------------------------------------------------------
 constexpr int kSplitSegs = 6;
+constexpr int kSplitK = 6;           // slices of a long contraction (weight gradients)
+constexpr int kSplitKMinBlocks = 96; // ... when it has at least this many 64-wide k-blocks
 struct SplitJob {
     const float* src; __nv_bfloat16* dst;
     int rows, cols, ld;        // source matrix [rows, cols], row stride ld
@@ -184,6 +186,31 @@ __global__ void __launch_bounds__(256) k_split_bf16x3(const __grid_constant__ Sp
     }
 }
 
+// split-K partial products summed in slice order; bias / residual / the accumulate input of the problem are applied here.
+// Two kinds of problem are cut: weight gradients (d x d outputs = a handful of tiles under a contraction over every row of the
+// batch) and launches whose tiles would fill less than half of the SMs (out-projections at d = 512: 44 tiles of 48 k-blocks).
+struct SumJob { const float* part; float* out; const float* bias; const float* residual; int M, N, ldc, ldr, count, accumulate; long long stride; };
+struct SumGroup { SumJob j[8]; int count; };
+__global__ void __launch_bounds__(256) k_sum_partials(const __grid_constant__ SumGroup g) {
+    const SumJob& J = g.j[blockIdx.y];
+    const int n4 = J.N >> 2;
+    const long long total = (long long)J.M * n4;
+    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+        const int m = (int)(e / n4), n = (int)(e - (long long)m * n4) * 4;
+        const float* p = J.part + (size_t)m * J.N + n;
+        float4 s = *reinterpret_cast<const float4*>(p);
+        for (int q = 1; q < J.count; ++q) {
+            const float4 v = *reinterpret_cast<const float4*>(p + (size_t)q * J.stride);
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        if (J.bias) { const float4 v = *reinterpret_cast<const float4*>(J.bias + n); s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
+        if (J.residual) { const float4 v = *reinterpret_cast<const float4*>(J.residual + (size_t)m * J.ldr + n); s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
+        float* o = J.out + (size_t)m * J.ldc + n;
+        if (J.accumulate) { const float4 v = *reinterpret_cast<const float4*>(o); s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
+        *reinterpret_cast<float4*>(o) = s;
+    }
+}
+
 struct SplitScratch { char* base; size_t bytes; };
 
 // fp32 tier on tensor cores?  (sm_100 device; DCLIP_XATTN_SPLIT=0 keeps the CUDA-core GEMM for A/B timing and tests)
@@ -194,16 +221,17 @@ static bool gemm_split_enabled() {
 }
 static size_t split_fwd_bytes(int64_t B, int64_t T, int64_t R, int64_t d) {
     const size_t dp = (size_t)(d + 7) / 8 * 8;
-    return ((size_t)B * (T + R) + 6 * d + 16) * kSplitSegs * dp * 2 + 16 * 256;
+    return ((size_t)B * (T + R) + 6 * d + 16) * kSplitSegs * dp * 2 + 16 * 256 + ((size_t)B * (T + R) + 256) * 3 * dp * kSplitK * 4 + 8 * 256;      // operands + split-K partials
 }
 static size_t split_bwd_bytes(int64_t B, int64_t T, int64_t R, int64_t d) {
     const size_t dp = (size_t)(d + 7) / 8 * 8;
-    return (((size_t)B * (T + R) + 32) * 24 * dp + 24 * dp * dp) * 2 + 16 * 256;
+    return (((size_t)B * (T + R) + 32) * 24 * dp + 24 * dp * dp) * 2 + 16 * 256 + (size_t)kSplitK * 6 * dp * dp * 4 + ((size_t)B * (T + R) + 256) * 2 * dp * kSplitK * 4 + 8 * 256;      // operands + split-K partials
 }
 
 static int launch_gemm_group_split(const GemmGroup& g, const SplitScratch& sc, cudaStream_t st) {
     SplitGroup sg{};
-    TcGemmProblem pr[8];
+    SumGroup sums{};
+    TcGemmProblem pr[8] = {};
     size_t used = 0;
     auto operand = [&](const float* src, bool kmajor, int role, int mn, int K, int ld, int Kp, const __nv_bfloat16** out, int* ldd) -> int {
         const int rows = kmajor ? mn : K, cols = kmajor ? K : mn;
@@ -238,13 +266,41 @@ static int launch_gemm_group_split(const GemmGroup& g, const SplitScratch& sc, c
         q.bias_kind = 0; q.res_kind = 0;
         pr[i] = q;
     }
+    // split-K (see k_sum_partials): long contractions always, everything when the launch would leave most SMs idle
+    int total_tiles = 0;      // with the long contractions already cut
+    for (int i = 0; i < g.count; ++i)
+        total_tiles += ((g.p[i].M + 127) / 128) * ((g.p[i].N + 255) / 256) * ((pr[i].K + 63) / 64 >= kSplitKMinBlocks ? gemm_tc_slices(pr[i].K, kSplitK) : 1);
+    const int fill = total_tiles > 0 ? sm_count() / total_tiles : 1;
+    for (int i = 0; i < g.count; ++i) {
+        const GemmProblem& P = g.p[i];
+        TcGemmProblem& q = pr[i];
+        const int nkb = (q.K + 63) / 64;
+        int want = nkb >= kSplitKMinBlocks ? kSplitK : 1;
+        if (want == 1 && fill >= 2) want = min(min(fill, kSplitK), nkb / 8);
+        if (want < 2 || sums.count == 8) continue;
+        const int ks = gemm_tc_slices(q.K, want);
+        const size_t bytes = (size_t)ks * P.M * P.N * sizeof(float);
+        if (ks < 2 || used + bytes > sc.bytes) continue;
+        float* part = reinterpret_cast<float*>(sc.base + used);
+        used += align_up(bytes, 256);
+        sums.j[sums.count++] = SumJob{part, P.C, P.bias, P.residual, P.M, P.N, P.ldc, P.ldr, ks, P.accumulate, (long long)P.M * P.N};
+        q.C = part; q.ldc = P.N; q.bias = nullptr; q.residual = nullptr; q.accumulate = 0; q.ksplit = want; q.split_stride = (long long)P.M * P.N;
+    }
+
     long long mx = 0;
     for (int i = 0; i < sg.count; ++i) mx = max(mx, (long long)sg.j[i].out_rows * (sg.j[i].out_cols >> 3));
     if (mx > 0) {
         k_split_bf16x3<<<dim3((unsigned)min((long long)1184, (mx + 255) / 256), (unsigned)sg.count), 256, 0, st>>>(sg);
         DCLIP_LAUNCH_OK("k_split_bf16x3");
     }
-    return launch_gemm_tc(pr, g.count, DCLIP_BF16, st);
+    if (int e = launch_gemm_tc(pr, g.count, DCLIP_BF16, st)) return e;
+    if (sums.count) {
+        long long mxn = 0;
+        for (int i = 0; i < sums.count; ++i) mxn = max(mxn, (long long)sums.j[i].M * sums.j[i].N);
+        k_sum_partials<<<dim3((unsigned)min((long long)592, (mxn / 4 + 255) / 256), (unsigned)sums.count), 256, 0, st>>>(sums);
+        DCLIP_LAUNCH_OK("k_sum_partials");
+    }
+    return DCLIP_OK;
 }
 
 // the fp32 grouped GEMM: tcgen05 through operand splitting where a scratch area was provided, CUDA cores otherwise
@@ -304,7 +360,8 @@ __global__ void __launch_bounds__(1024) k_colsum(const __grid_constant__ ColsumG
     const int c = blockIdx.x * 32 + lane;
     float s1 = 0.f, s2 = 0.f;
     if (c < P.cols)
-        for (int r = grp; r < P.rows; r += 32) {
+#pragma unroll 8
+        for (int r = grp; r < P.rows; r += 32) {      // unrolled: the loads of eight rows are in flight together (the loop is L2-latency bound)
             const float v = P.Mx[(size_t)r * P.ld + c];
             s1 += v;
             if (P.W) s2 = fmaf(v, P.W[(size_t)r * P.ldw + c], s2);
