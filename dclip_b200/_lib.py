@@ -87,7 +87,7 @@ SIGNATURES = {
                                 _vp]),
     "dclip_topk_merge": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
     "dclip_global_embedding_flags_bytes": (_sz, [_i64]),
-    "dclip_global_embedding_fwd": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _f32, _vp, _vp, _vp, _vp, _vp]),
+    "dclip_global_embedding_fwd": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dclip_global_embedding_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i32, _f32, _vp, _vp, _vp]),
     "dclip_token_select": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     "dclip_cu_seqlens": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp]),

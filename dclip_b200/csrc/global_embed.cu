@@ -34,7 +34,8 @@ struct GlobalArgs {
     float temperature;
     void* out;                 // fwd: [B, d]
     const void* dout;          // bwd: [B, d]
-    int* flags;                // [B] per-element non-finite flags, [B] = completion counter
+    int* flags;                // [B] per-element non-finite flags
+    int* counter;              // completion counter: zero on entry, left zero
     int staged[2];             // side's [L, d] block fits in shared memory
 };
 
@@ -219,7 +220,7 @@ __global__ void __cluster_dims__(2 * kParts, 1, 1) __launch_bounds__(ge::kThread
         if (threadIdx.x == 0) {
             a.flags[b] = any_bad;
             __threadfence();
-            last = atomicAdd(&a.flags[a.B], 1) == a.B - 1;
+            last = atomicAdd(a.counter, 1) == a.B - 1;
         }
         __syncthreads();
         if (last) {
@@ -232,7 +233,7 @@ __global__ void __cluster_dims__(2 * kParts, 1, 1) __launch_bounds__(ge::kThread
                 T* all = static_cast<T*>(a.out);
                 for (size_t i = threadIdx.x; i < (size_t)a.B * d; i += kThreads) all[i] = from_f32<T>(0.f);
             }
-            if (threadIdx.x == 0) a.flags[a.B] = 0;          // counter ready for the next launch
+            if (threadIdx.x == 0) *a.counter = 0;            // counter ready for the next launch
         }
     }
     cluster.sync();                                                   // (4) nobody leaves while rank 0 reads its partials
@@ -441,17 +442,19 @@ extern "C" {
 size_t dclip_global_embedding_flags_bytes(int64_t B) { return (size_t)(B + 1) * sizeof(int); }
 
 int dclip_global_embedding_fwd(const void* attended_text, const void* attended_image, int64_t B, int64_t T, int64_t R, int64_t d, int dtype,
-                               float temperature, void* out, float* w_text, float* w_image, int* flags, void* stream) {
+                               float temperature, void* out, float* w_text, float* w_image, int* flags, int* zeroed_counter, void* stream) {
     DCLIP_REQUIRE(attended_text && attended_image && out && flags && B > 0 && T > 0 && R > 0 && d > 0 && temperature > 0.f,
                   "global_embedding_fwd: bad arguments");
     DCLIP_REQUIRE(d % 8 == 0 && d <= 1024 && aligned16(attended_text) && aligned16(attended_image) && aligned16(out),
                   "global_embedding_fwd: d must be a multiple of 8, <= 1024, pointers 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    DCLIP_CUDA_OK(cudaMemsetAsync(flags + B, 0, sizeof(int), st));       // completion counter (the flags themselves are always written)
+    // completion counter (the flags themselves are always written): the caller's persistent zeroed word, which every launch leaves
+    // zero again, or flags[B] cleared here (a memset node costs ~8 us of launch gaps inside a CUDA graph)
+    if (!zeroed_counter) DCLIP_CUDA_OK(cudaMemsetAsync(flags + B, 0, sizeof(int), st));
     GlobalArgs a{};
     a.s[0] = GlobalSide{attended_text, (int)T, w_text, nullptr};
     a.s[1] = GlobalSide{attended_image, (int)R, w_image, nullptr};
-    a.B = (int)B; a.d = (int)d; a.temperature = temperature; a.out = out; a.flags = flags;
+    a.B = (int)B; a.d = (int)d; a.temperature = temperature; a.out = out; a.flags = flags; a.counter = zeroed_counter ? zeroed_counter : flags + B;
     return global_embedding(a, dtype, false, st);
 }
 

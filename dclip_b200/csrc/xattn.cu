@@ -19,10 +19,14 @@
 //
 // Row layout: text rows = b*T + t, image rows = b*R + r (batch-first, as the callers hold them; the
 // reference's transpose to [L, B, d] only permutes rows of the same per-(b, head) problems).
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "gemm_tc.h"
 
 #include <cstdlib>
+
+namespace cg = cooperative_groups;
 
 namespace dclip {
 
@@ -352,34 +356,53 @@ __global__ void k_narrow_group(const __grid_constant__ CastGroup g) {
 // Up to 8 problems per launch (blockIdx.y); a block owns 32 columns, 32 row lanes.
 struct ColsumProblem { const float* Mx; const float* W; int rows, cols, ld, ldw; float* out; float* out2; };
 struct ColsumGroup { ColsumProblem p[8]; int count; };
-__global__ void __launch_bounds__(1024) k_colsum(const __grid_constant__ ColsumGroup g) {
+// The rows are split over the 8 CTAs of a cluster (blockIdx.z): a thread walks ~rows / 256 of them instead of rows / 32 (the loop
+// is a chain of L2 round trips), the per-CTA sums meet in CTA 0 through distributed shared memory, rank order: deterministic.
+constexpr int kColsumCluster = 8;
+__global__ void __cluster_dims__(1, 1, kColsumCluster) __launch_bounds__(1024) k_colsum(const __grid_constant__ ColsumGroup g) {
     const ColsumProblem& P = g.p[blockIdx.y];
-    if ((int)blockIdx.x * 32 >= P.cols) return;
+    if ((int)blockIdx.x * 32 >= P.cols) return;        // the whole cluster (same x, y) leaves together
+    cg::cluster_group cluster = cg::this_cluster();
     __shared__ float r1[32][33], r2[32][33];
+    __shared__ float fin[2][32];
     const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + lane;
+    const int rank = (int)blockIdx.z;
+    const int per = (P.rows + kColsumCluster - 1) / kColsumCluster;
+    const int r_begin = rank * per, r_end = min(P.rows, r_begin + per);
     float s1 = 0.f, s2 = 0.f;
-    if (c < P.cols)
-#pragma unroll 8
-        for (int r = grp; r < P.rows; r += 32) {      // unrolled: the loads of eight rows are in flight together (the loop is L2-latency bound)
+    if (c < P.cols) {
+#pragma unroll 4
+        for (int r = r_begin + grp; r < r_end; r += 32) {
             const float v = P.Mx[(size_t)r * P.ld + c];
             s1 += v;
             if (P.W) s2 = fmaf(v, P.W[(size_t)r * P.ldw + c], s2);
         }
+    }
     r1[grp][lane] = s1; r2[grp][lane] = s2;
     __syncthreads();
-    if (grp == 0 && c < P.cols) {
+    if (grp == 0) {
         float a = 0.f, b = 0.f;
         for (int i = 0; i < 32; ++i) { a += r1[i][lane]; b += r2[i][lane]; }
+        fin[0][lane] = a; fin[1][lane] = b;
+    }
+    cluster.sync();
+    if (rank == 0 && grp == 0 && c < P.cols) {
+        float a = 0.f, b = 0.f;
+        for (int q = 0; q < kColsumCluster; ++q) {
+            const float* f = cluster.map_shared_rank(&fin[0][0], q);
+            a += f[lane]; b += f[32 + lane];
+        }
         if (P.out) P.out[c] = a;
         if (P.out2) P.out2[c] = b;
     }
+    cluster.sync();        // nobody leaves while CTA 0 still reads its shared memory
 }
 static int launch_colsum(const ColsumGroup& g, cudaStream_t st) {
     int maxc = 0;
     for (int i = 0; i < g.count; ++i) maxc = max(maxc, g.p[i].cols);
     if (maxc == 0) return DCLIP_OK;
-    k_colsum<<<dim3((maxc + 31) / 32, g.count), 1024, 0, st>>>(g);
+    k_colsum<<<dim3((maxc + 31) / 32, g.count, kColsumCluster), 1024, 0, st>>>(g);
     DCLIP_LAUNCH_OK("k_colsum");
     return DCLIP_OK;
 }

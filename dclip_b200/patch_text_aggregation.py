@@ -14,6 +14,7 @@ training/patch_text_aggregation.py.
       (SURVEY.md §8): callers hand the padded [B,T,d] / [B,R,d] tensors it produces.
 """
 import ctypes
+import threading
 
 import torch
 import torch.nn as nn
@@ -130,6 +131,24 @@ class _CombineGuardFn(torch.autograd.Function):
         return da, db
 
 
+_COUNTERS = {}
+_CAPTURE = threading.local()
+
+
+def _zeroed_counter(dev):
+    """A persistent zero-initialised device word: the completion counter of the fused global-embedding kernel, which every
+    launch leaves zero again.  One per (device, stream) - stream order keeps the launches that share it apart; while a CUDA
+    graph is being captured, the word its owner registered (GraphedTeacherStep), else None (the library then clears a
+    per-call word with a memset node)."""
+    if torch.cuda.is_current_stream_capturing():
+        return getattr(_CAPTURE, "counter", None)
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    c = _COUNTERS.get(key)
+    if c is None:
+        c = _COUNTERS[key] = torch.zeros(1, dtype=torch.int32, device=dev)
+    return c
+
+
 class _GlobalEmbeddingFn(torch.autograd.Function):
     """aggregation(text) + aggregation(image) + 0.5 / 0.5 combine + whole-tensor NaN / Inf guard: one launch each way."""
 
@@ -145,7 +164,8 @@ class _GlobalEmbeddingFn(torch.autograd.Function):
         flags = torch.empty(B + 1, dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
             check(lib.dclip_global_embedding_fwd(ptr(attended_text), ptr(attended_image), B, T, R, d, dtype_code(attended_text),
-                                                 float(temperature), ptr(out), ptr(w_t), ptr(w_i), ptr(flags), stream_ptr(dev)),
+                                                 float(temperature), ptr(out), ptr(w_t), ptr(w_i), ptr(flags), ptr(_zeroed_counter(dev)),
+                                                 stream_ptr(dev)),
                   "global_embedding_fwd")
         ctx.save_for_backward(attended_text, attended_image, w_t, w_i, flags)
         ctx.temperature = float(temperature)
@@ -255,6 +275,8 @@ class GraphedTeacherStep:
     ``zero_grad(set_to_none=True)`` afterwards (every replay overwrites the gradients anyway).
 
     loss_fn(module, *inputs) -> scalar loss tensor; shapes and dtypes are fixed at construction.
+    ``step.static_in`` are the graph's input buffers: a caller that fills them in place (the target of its host-to-device
+    copies) and calls ``step(*step.static_in)`` skips the device-to-device staging copies of ``step(text, patches, txt)``.
     optimizer: an optional dclip_b200.optim.FusedAdam over the same parameters; its step (two launches for all 12
     tensors, step counter and clip coefficient in device memory) is captured at the end of the graph, so one replay
     is the reference's whole ``backward(); optimizer.step()`` (train_contrastive_teacher.py:361-362).  The warm-up
@@ -278,12 +300,21 @@ class GraphedTeacherStep:
         torch.cuda.synchronize()
         for p in self.params:
             p.grad = None
+        dev = self.static_in[0].device
+        self._counter = torch.zeros(1, dtype=torch.int32, device=dev)      # the graph's own completion counter (see _zeroed_counter)
+        self._one = torch.ones((), dtype=torch.float32, device=dev)          # root gradient: no ones_like fill kernel per replay
+        torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.static_loss = loss_fn(module, *self.static_in)
-            self.static_loss.backward()
-            if optimizer is not None:
-                optimizer.step()
+        _CAPTURE.counter = self._counter
+        try:
+            with torch.cuda.graph(self.graph):
+                self.static_loss = loss_fn(module, *self.static_in)
+                root = self._one if self.static_loss.dtype == torch.float32 and self.static_loss.dim() == 0 else None
+                self.static_loss.backward(gradient=root)
+                if optimizer is not None:
+                    optimizer.step()
+        finally:
+            _CAPTURE.counter = None
 
     def __call__(self, *inputs):
         for dst, src in zip(self.static_in, inputs):

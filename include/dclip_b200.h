@@ -349,11 +349,12 @@ int dclip_combine_guard_bwd(const void* d_out, int64_t n, int dtype, const int* 
  * backward of the same in one launch.  attended_text [B, T, d], attended_image [B, R, d], out [B, d]; d % 8 == 0,
  * d <= 1024.  w_text [B, T] / w_image [B, R]: the softmax weights (saved for the backward).  flags: int[B + 1]
  * (dclip_global_embedding_flags_bytes): per-element non-finite flags + a completion counter; device-side decision,
- * no host synchronisation. */
+ * no host synchronisation.  zeroed_counter: optional device int that is ZERO on entry and is left zero by every launch
+ * (a persistent word per stream owned by the caller); NULL: flags[B] is used and cleared by a memset on the stream. */
 size_t dclip_global_embedding_flags_bytes(int64_t B);
 int dclip_global_embedding_fwd(const void* attended_text, const void* attended_image, int64_t B, int64_t T, int64_t R,
                                int64_t d, int dtype, float temperature, void* out, float* w_text, float* w_image,
-                               int* flags, void* stream);
+                               int* flags, int* zeroed_counter, void* stream);
 int dclip_global_embedding_bwd(const void* attended_text, const void* attended_image, const float* w_text,
                                const float* w_image, const void* d_out, const int* flags, int64_t B, int64_t T,
                                int64_t R, int64_t d, int dtype, float temperature, void* d_attended_text,
