@@ -146,6 +146,46 @@ def test_16bit_tensor_tier_forward_backward(built_library, dtype):
         assert e_ours < 2.0 * e_torch + 1e-3, (name, e_ours, e_torch)
 
 
+def test_fp32_tier_tensor_core_gemms_match_cuda_core_gemms(built_library, monkeypatch):
+    """fp32 inputs run their GEMMs on tcgen05 through bf16 x 3 operand splitting (csrc/xattn.cu: run_gemm_group); with
+    DCLIP_XATTN_SPLIT=0 the CUDA-core fp32 GEMM of round 1 runs instead.  Both must sit inside the FP32 tier against the
+    fp64 oracle, at the configs[0] shape (split-K for the weight gradients and the out-projections) with input gradients,
+    and when the upstream gradient is tiny (1e-8: an fp16 split would flush it; bf16 terms keep fp32's exponent range)."""
+    B, T, R, d, heads = 32, 77, 8, 512, 8
+    params = om.perturbed_cross_attention_params(d, heads, 11)
+    text, image = synthetic.xattn_inputs(B, T, R, d, 11, ragged=True)
+    gt = torch.randn(B, T, d, generator=torch.Generator().manual_seed(5))
+    gi = torch.randn(B, R, d, generator=torch.Generator().manual_seed(6))
+    p64 = {k: v.double().requires_grad_(True) for k, v in params.items()}
+    t64, i64 = text.double().requires_grad_(True), image.double().requires_grad_(True)
+    to64, io64 = om.cross_modal_attention(p64, t64, i64, heads)
+    ((to64 * gt.double()).sum() + (io64 * gi.double()).sum()).backward()
+
+    def run(scale):
+        m = _module(d, heads, params)
+        t = text.to(DEV).requires_grad_(True)
+        i = image.to(DEV).requires_grad_(True)
+        to, io = m.cross_attention(t, i)
+        ((to * gt.to(DEV)).sum() * scale + (io * gi.to(DEV)).sum() * scale).backward()
+        g = {k: p.grad.clone() for k, p in m.cross_modal_attention.named_parameters()}
+        return to.detach(), io.detach(), t.grad.clone(), i.grad.clone(), g
+
+    for scale in (1.0, 1e-8):
+        monkeypatch.setenv("DCLIP_XATTN_SPLIT", "0")
+        ref = run(scale)
+        monkeypatch.delenv("DCLIP_XATTN_SPLIT")
+        got = run(scale)
+        worst = {"split": 0.0, "simt": 0.0}
+        for name, res in (("split", got), ("simt", ref)):
+            assert _rel(res[0], to64.detach()) < 1e-5 and _rel(res[1], io64.detach()) < 1e-5, name
+            worst[name] = max(_rel(res[2] / scale, t64.grad), _rel(res[3] / scale, i64.grad))
+            for k in om.PARAM_KEYS:
+                worst[name] = max(worst[name], _rel(res[4][k] / scale, p64[k].grad))
+        print(f"fp32 tier vs the fp64 oracle, upstream scale {scale:g}: worst gradient error, tensor-core GEMMs {worst['split']:.2e}, "
+              f"CUDA-core GEMMs {worst['simt']:.2e}")
+        assert worst["split"] < 1e-4 and worst["simt"] < 1e-4
+
+
 def test_nan_guard_zeroes_whole_tensor(built_library):
     from dclip_b200.patch_text_aggregation import combine_global
     a = torch.randn(4, 16, device=DEV, requires_grad=True)
