@@ -690,7 +690,7 @@ def teacher_step_bench(dev, with_cpu):
         us = res["us_per_step"]
         fl = teacher_flops(B, T, R, d)
         res.update({"pairs_per_s": B / (us * 1e-6), "algorithmic_gflop": fl / 1e9,
-                    "roofline": {"bound": "tensor" if dtype != torch.float32 else "launch latency (fp32 exact tier, CUDA cores)",
+                    "roofline": {"bound": "tensor" if dtype != torch.float32 else "tensor (fp32 tier: GEMMs on tcgen05 through bf16 x 3 operand splitting = 6x the MMA work; attention cores on CUDA cores)",
                                  "achieved": fl / (us * 1e-6) / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                                  "frac": fl / (us * 1e-6) / 1e12 / peaks["bf16_tflops"], "peak_source": peaks["source"] + " bf16 burst",
                                  "traffic": None},

@@ -1,4 +1,4 @@
-"""Runs N eager meta-teacher steps (configs[2] shape by default) - the target of ncu captures."""
+"""Runs N eager meta-teacher steps (configs[2] shape by default, `N fp32` = configs[0]) - the target of ncu captures."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -8,8 +8,9 @@ from oracle import reference_math as om
 from oracle import synthetic
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 4
-dtype = torch.bfloat16
-B, T, R, d = 32, 77, 36, 768
+fp32 = len(sys.argv) > 2 and sys.argv[2] == "fp32"            # fp32: BASELINE configs[0] (B=32, T=77, R=8, d=512)
+dtype = torch.float32 if fp32 else torch.bfloat16
+B, T, R, d = (32, 77, 8, 512) if fp32 else (32, 77, 36, 768)
 dev = torch.device("cuda:0")
 m = PatchTextAggregation(embed_dim=d, num_heads=8)
 m.cross_modal_attention.load_state_dict(om.perturbed_cross_attention_params(d, 8, 3))
