@@ -76,20 +76,18 @@ struct LnBwdSide { const void* dY; const float* Z; const void* gamma; const floa
 struct LnBwdArgs { LnBwdSide s[2]; int d, nblk0; float* part; };
 
 template <typename T, int NC>
-__global__ void __launch_bounds__(256) k_ln_bwd16(const __grid_constant__ LnBwdArgs a) {
-    extern __shared__ float red[];                     // [8 warps][3][d]
+__global__ void __launch_bounds__(256, 2) k_ln_bwd16(const __grid_constant__ LnBwdArgs a) {
+    // The column sums of a warp's rows are accumulated in the warp's own slice of shared memory, not in registers (72 of them:
+    // 171 registers = one block per SM = 226 blocks in two waves at the configs[2] shape; now two blocks per SM, one wave,
+    // twice the rows in flight per SM for a kernel that is a chain of global-memory round trips).
+    extern __shared__ float red[];                     // [8 warps][3][d], chunk-transposed columns
     const int side = (int)blockIdx.x >= a.nblk0 ? 1 : 0;
     const LnBwdSide& S = a.s[side];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int row0 = ((int)blockIdx.x - (side ? a.nblk0 : 0)) * kLnRowsPerBlock;
     const int d = a.d, nch = d >> 3;
-    float gam[NC][8], acc[3][NC][8];
-#pragma unroll
-    for (int k = 0; k < NC; ++k) {
-        if (lane + 32 * k < nch) load8<T>(static_cast<const T*>(S.gamma) + (lane + 32 * k) * 8, gam[k]);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { acc[0][k][i] = 0.f; acc[1][k][i] = 0.f; acc[2][k][i] = 0.f; }
-    }
+    float* mine = red + (size_t)warp * 3 * d;
+    bool first = true;
     for (int r = warp; r < kLnRowsPerBlock; r += 8) {
         const int row = row0 + r;
         if (row >= S.rows) break;
@@ -102,17 +100,19 @@ __global__ void __launch_bounds__(256) k_ln_bwd16(const __grid_constant__ LnBwdA
         for (int k = 0; k < NC; ++k) {
             const int ch = lane + 32 * k;
             if (ch < nch) {
-                float dv[8];
+                float dv[8], gam[8];
                 load8<float>(z + ch * 8, zh[k]);
                 load8<T>(dy + ch * 8, dv);
+                load8<T>(static_cast<const T*>(S.gamma) + ch * 8, gam);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     zh[k][i] = (zh[k][i] - mu) * rstd;
-                    g[k][i] = dv[i] * gam[k][i];
+                    g[k][i] = dv[i] * gam[i];
                     s1 += g[k][i];
                     s2 = fmaf(g[k][i], zh[k][i], s2);
-                    acc[0][k][i] += dv[i];
-                    acc[1][k][i] = fmaf(dv[i], zh[k][i], acc[1][k][i]);
+                    float* p0 = mine + i * nch + ch;             // column sums of dy (-> dbeta) and dy zhat (-> dgamma)
+                    const float c1 = dv[i] * zh[k][i];
+                    if (first) { p0[0] = dv[i]; p0[d] = c1; } else { p0[0] += dv[i]; p0[d] += c1; }
                 }
             }
         }
@@ -125,18 +125,18 @@ __global__ void __launch_bounds__(256) k_ln_bwd16(const __grid_constant__ LnBwdA
             if (ch < nch) {
                 float o[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) { o[i] = rstd * (g[k][i] - s1 - zh[k][i] * s2); acc[2][k][i] += o[i]; }
+                for (int i = 0; i < 8; ++i) {
+                    o[i] = rstd * (g[k][i] - s1 - zh[k][i] * s2);
+                    float* p2 = mine + 2 * d + i * nch + ch;     // column sums of dz (-> out-projection bias gradient)
+                    if (first) p2[0] = o[i]; else p2[0] += o[i];
+                }
                 store8<T>(dz + ch * 8, o);
             }
         }
+        first = false;
     }
-#pragma unroll
-    for (int q = 0; q < 3; ++q)
-#pragma unroll
-        for (int k = 0; k < NC; ++k)
-            if (lane + 32 * k < nch)
-#pragma unroll
-                for (int i = 0; i < 8; ++i) red[((size_t)warp * 3 + q) * d + i * nch + lane + 32 * k] = acc[q][k][i];   // chunk-transposed
+    if (first)                                         // no row for this warp: its slice still takes part in the block sum
+        for (int e = lane; e < 3 * d; e += 32) mine[e] = 0.f;
     __syncthreads();
     float* out = a.part + (size_t)blockIdx.x * 3 * d;
     for (int e = threadIdx.x; e < 3 * d; e += 256) {
