@@ -223,13 +223,16 @@ static bool gemm_split_enabled() {
     const char* e = getenv("DCLIP_XATTN_SPLIT");
     return !(e && e[0] == '0');
 }
+// scratch of the split path: the six-term operands of the largest launch + split-K partials.  Partials exist for weight gradients
+// (d x d outputs, always cut) and for launches of fewer than sm_count() / 2 tiles (<= 74 tiles of 128 x 256 outputs, cut up to 6 ways).
+static size_t split_partial_cap(size_t out_elems) { return (out_elems < (size_t)74 * 128 * 256 ? out_elems : (size_t)74 * 128 * 256) * kSplitK * sizeof(float); }
 static size_t split_fwd_bytes(int64_t B, int64_t T, int64_t R, int64_t d) {
-    const size_t dp = (size_t)(d + 7) / 8 * 8;
-    return ((size_t)B * (T + R) + 6 * d + 16) * kSplitSegs * dp * 2 + 16 * 256 + ((size_t)B * (T + R) + 256) * 3 * dp * kSplitK * 4 + 8 * 256;      // operands + split-K partials
+    const size_t dp = (size_t)(d + 7) / 8 * 8, rows = (size_t)B * (T + R);
+    return (rows + 6 * d + 16) * kSplitSegs * dp * 2 + 16 * 256 + split_partial_cap((rows + 256) * 3 * dp) + 8 * 256;
 }
 static size_t split_bwd_bytes(int64_t B, int64_t T, int64_t R, int64_t d) {
-    const size_t dp = (size_t)(d + 7) / 8 * 8;
-    return (((size_t)B * (T + R) + 32) * 24 * dp + 24 * dp * dp) * 2 + 16 * 256 + (size_t)kSplitK * 6 * dp * dp * 4 + ((size_t)B * (T + R) + 256) * 2 * dp * kSplitK * 4 + 8 * 256;      // operands + split-K partials
+    const size_t dp = (size_t)(d + 7) / 8 * 8, rows = (size_t)B * (T + R);
+    return ((rows + 32) * 24 * dp + 24 * dp * dp) * 2 + 16 * 256 + (size_t)kSplitK * 6 * dp * dp * sizeof(float) + split_partial_cap((rows + 256) * 2 * dp) + 8 * 256;
 }
 
 static int launch_gemm_group_split(const GemmGroup& g, const SplitScratch& sc, cudaStream_t st) {
