@@ -89,6 +89,27 @@ def test_project_text_tokens(built_library, B, L, width, d, dtype, tol):
     assert max(0.0, rel * rel - rounding * rounding) ** 0.5 < tol, (rel, rounding)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_linear_rows_odd_shapes(built_library, dtype):
+    """The grouped tcgen05 GEMM behind dclip_linear_rows at shapes that do not fill its 128 x 256 tiles, 64-wide k-blocks or
+    the 64- / 32-column chunks of its specialised epilogue (16-bit output + fp32 bias), against an fp64 product of the same
+    16-bit operands: only the output rounding separates the two."""
+    from dclip_b200 import assembly as A
+    g = torch.Generator().manual_seed(7)
+    for n, k, m in ((1, 8, 8), (33, 72, 24), (129, 200, 40), (300, 64, 264), (257, 136, 328), (128, 768, 256)):
+        x = torch.randn(n, k, generator=g).to(dtype)
+        w = (torch.randn(m, k, generator=g) / k ** 0.5).to(dtype)
+        b = torch.randn(m, generator=g)
+        for bias in (None, b):
+            got = A.linear_rows(x.to(DEV), w.to(DEV), None if bias is None else bias.to(DEV)).double().cpu()
+            want = x.double() @ w.double().T + (0 if bias is None else bias.double())
+            rounded = want.to(dtype).double()
+            # fp32 accumulation: the result is the correctly rounded fp64 value except where fp32 summation error crosses a rounding boundary
+            err = float((got - want).abs().max() / want.abs().max())
+            rnd = float((rounded - want).abs().max() / want.abs().max())
+            assert got.shape == want.shape and err <= 1.05 * rnd + 1e-6, (n, k, m, bias is not None, err, rnd)
+
+
 def _clone_params(shapes, dtype, seed):
     g = torch.Generator().manual_seed(seed)
     return [torch.randn(s, generator=g).to(dtype) for s in shapes]
