@@ -333,6 +333,8 @@ def main():
                 extra["retrieval"].update(retrieval_bench(dev, not args.no_cpu_baseline))
     if rank == 0 and world == 1 and not args.no_teacher:
         extra["teacher_step"] = teacher_step_bench(dev, not args.no_cpu_baseline)
+    if rank == 0 and world == 1 and args.dtype == "bf16" and not args.no_teacher:
+        extra["fp32_inputs"] = fp32_input_bench(L, dev, B, d)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(B, d)
@@ -630,6 +632,38 @@ def retrieval_bench(dev, with_cpu):
         out["top10"]["cpu_baseline"] = {"value": 512 / ct, "unit": "queries/s at 1 M rows", "cores": cores, "kind": "port",
                                         "extrapolated_to_10M_rows_queries_per_s": 512 / ct / 10.0,
                                         "sample": f"512 queries x 1 M x 768 fp32, torch matmul + topk on {cores} threads, {ct:.1f} s (stand-in for faiss IndexFlatIP.search; extrapolated)"}
+    return out
+
+
+def fp32_input_bench(L, dev, B, d):
+    """The same objective for fp32 inputs (the reference's own dtype): `path="tensor"` rounds the L2-normalised rows to fp16
+    operands once (fp32 accumulate, fp32 gradients: the 1e-3 tier), `path="fp32"` is the exact CUDA-core tier (1e-5) that
+    `path="auto"` selects for fp32 inputs.  Device-timed, eager launches, L2 flushed between steps."""
+    from oracle import synthetic
+    inp = [t.to(dev) for t in synthetic.loss_inputs(B, d, seed=42)]
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    out = {"workload": f"distill-loss fwd+bwd, B={B}, d={d}, fp32 inputs and gradients"}
+    ref = None
+    for path, reps in (("tensor", 10), ("fp32", 4)):
+        for _ in range(2):
+            res = L.distill_loss_fwd_bwd(*inp, temperature=TEMPERATURE, path=path)
+        torch.cuda.synchronize()
+        tot = 0.0
+        for _ in range(reps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            res = L.distill_loss_fwd_bwd(*inp, temperature=TEMPERATURE, path=path)
+            e1.record()
+            torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        out[f"ms_per_step_{path}_path"] = tot / reps
+        if path == "tensor":
+            ref = res
+        else:
+            out["tensor_vs_fp32_path_rel_grad_diff"] = float((ref[1] - res[1]).norm() / res[1].norm())
+            out["tensor_vs_fp32_path_rel_loss_diff"] = float(((ref[0] - res[0]).abs() / res[0].abs().clamp_min(1e-6)).max())
     return out
 
 
