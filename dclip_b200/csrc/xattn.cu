@@ -432,10 +432,22 @@ template <bool TA, bool TB, typename F>
 __device__ __forceinline__ void smem_gemm(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, int M, int N, int K,
                                           F&& store) {
     const int tiles_m = (M + 3) >> 2, tiles_n = (N + 3) >> 2;
-    const int blocks_n = (tiles_n + 7) >> 3, blocks_m = (tiles_m + 3) >> 2;
+    // a warp covers (32 / TN) x TN micro-tiles; 4 x 8 is the conflict-free default, but an 8-region image side (N = 8: two tile
+    // columns, or M = 8: two tile rows) would leave 75 % / 50 % of the lanes without a tile: take the shape that pads least
+    int tn_shift = 3;
+    {
+        int best = ((tiles_m + 3) >> 2) * ((tiles_n + 7) >> 3);
+        for (int sh = 0; sh <= 5; ++sh) {
+            const int TNc = 1 << sh, TMc = 32 >> sh;
+            const int cost = ((tiles_m + TMc - 1) / TMc) * ((tiles_n + TNc - 1) / TNc);
+            if (cost < best) { best = cost; tn_shift = sh; }
+        }
+    }
+    const int TN = 1 << tn_shift, TM = 32 >> tn_shift;
+    const int blocks_n = (tiles_n + TN - 1) >> tn_shift, blocks_m = (tiles_m + TM - 1) / TM;
     for (int t = threadIdx.x; t < blocks_m * blocks_n * 32; t += kAttnThreads) {
         const int blk = t >> 5, inb = t & 31;
-        const int tm = (blk / blocks_n) * 4 + (inb >> 3), tn = (blk % blocks_n) * 8 + (inb & 7);
+        const int tm = (blk / blocks_n) * TM + (inb >> tn_shift), tn = (blk % blocks_n) * TN + (inb & (TN - 1));
         if (tm >= tiles_m || tn >= tiles_n) continue;
         const int m0 = tm * 4, n0 = tn * 4;
         float acc[4][4];
