@@ -39,6 +39,7 @@ struct TcGemmDev {
     int tiles_n, tile_begin;      // tiles of this problem occupy [tile_begin, tile_begin + slices * tiles_m * tiles_n)
     int tiles_mn, kb_per_slice;   // split-K: slice = local tile / tiles_mn, k-blocks [slice * kb_per_slice, ...)
     long long split_stride;
+    int seg_len; unsigned seg_map_a, seg_map_b;      // segmented contraction (gemm_tc.h)
     int accumulate;
     void* C16; int c16_kind, ldc16;   // optional 16-bit copy of C (0 none, 1 bf16, 2 fp16); C itself may then be null
     float alpha;
@@ -279,15 +280,21 @@ __global__ void __launch_bounds__(kGThreads, 1) k_gemm_tc(const __grid_constant_
                 int kb = (warp - q0 % kGStages + kGStages) % kGStages;
                 for (; kb < tc.nkb && ok; kb += kGStages, phase ^= 1) {
                     const int k0 = (tc.kb0 + kb) * GKS;
+                    int ka = k0, kbb = k0;                 // physical k of the two operands
+                    if (P.seg_len) {
+                        const int sidx = k0 / P.seg_len, off = k0 - sidx * P.seg_len;
+                        ka = (int)((P.seg_map_a >> (4 * sidx)) & 15u) * P.seg_len + off;
+                        kbb = (int)((P.seg_map_b >> (4 * sidx)) & 15u) * P.seg_len + off;
+                    }
                     ok = mbar_wait(&empty[warp], phase ^ 1, kSpinG);
                     if (warp == 0 && kb == 0 && tile == (int)blockIdx.x) GPROF(2);
                     mbar_arrive_expect_tx(&full[warp], kGStageBytes);
-                    if (!P.a_mn) tma_load_2d(dst, ta, &full[warp], k0, tc.m0);                     // [128 m x 64 k]
+                    if (!P.a_mn) tma_load_2d(dst, ta, &full[warp], ka, tc.m0);                     // [128 m x 64 k]
                     else
-                        for (int h = 0; h < 2; ++h) tma_load_2d(dst + h * 8192, ta, &full[warp], tc.m0 + h * 64, k0);   // [64 k x 64 m]
-                    if (!P.b_mn) tma_load_2d(dst + kGAStage, tb, &full[warp], k0, tc.n0);           // [256 n x 64 k]
+                        for (int h = 0; h < 2; ++h) tma_load_2d(dst + h * 8192, ta, &full[warp], tc.m0 + h * 64, ka);   // [64 k x 64 m]
+                    if (!P.b_mn) tma_load_2d(dst + kGAStage, tb, &full[warp], kbb, tc.n0);          // [256 n x 64 k]
                     else
-                        for (int h = 0; h < 4; ++h) tma_load_2d(dst + kGAStage + h * 8192, tb, &full[warp], tc.n0 + h * 64, k0);
+                        for (int h = 0; h < 4; ++h) tma_load_2d(dst + kGAStage + h * 8192, tb, &full[warp], tc.n0 + h * 64, kbb);
                 }
                 q0 += tc.nkb;
             }
@@ -411,10 +418,13 @@ int launch_gemm_tc(const TcGemmProblem* probs, int count, int dtype16, cudaStrea
             return fail(DCLIP_ERR_INVALID, "gemm_tc: bias / residual must be 16-byte aligned");
         bool okm;
         // A: K-major stored [M, K] (rows = M, cols = K); MN-major stored [K, M]
-        if (!q.a_mn) okm = make_tmap_2d_sw128_ld(&g.ta[i], q.A, (uint64_t)q.M, (uint64_t)q.K, (uint64_t)q.lda, GM, dt);
-        else okm = make_tmap_2d_sw128_ld(&g.ta[i], q.A, (uint64_t)q.K, (uint64_t)q.M, (uint64_t)q.lda, GKS, dt);
-        if (!q.b_mn) okm = okm && make_tmap_2d_sw128_ld(&g.tb[i], q.B, (uint64_t)q.N, (uint64_t)q.K, (uint64_t)q.ldb, GN, dt);
-        else okm = okm && make_tmap_2d_sw128_ld(&g.tb[i], q.B, (uint64_t)q.K, (uint64_t)q.N, (uint64_t)q.ldb, GKS, dt);
+        if (q.seg_len && (q.seg_len % GKS || q.K % q.seg_len || q.K / q.seg_len > 8 || q.k_phys <= 0 || q.k_phys % q.seg_len))
+            return fail(DCLIP_ERR_INVALID, "gemm_tc: problem %d: bad segmented contraction (seg_len %d, K %d, k_phys %d)", i, q.seg_len, q.K, q.k_phys);
+        const uint64_t kext = q.seg_len ? (uint64_t)q.k_phys : (uint64_t)q.K;      // K extent of the STORED operands
+        if (!q.a_mn) okm = make_tmap_2d_sw128_ld(&g.ta[i], q.A, (uint64_t)q.M, kext, (uint64_t)q.lda, GM, dt);
+        else okm = make_tmap_2d_sw128_ld(&g.ta[i], q.A, kext, (uint64_t)q.M, (uint64_t)q.lda, GKS, dt);
+        if (!q.b_mn) okm = okm && make_tmap_2d_sw128_ld(&g.tb[i], q.B, (uint64_t)q.N, kext, (uint64_t)q.ldb, GN, dt);
+        else okm = okm && make_tmap_2d_sw128_ld(&g.tb[i], q.B, kext, (uint64_t)q.N, (uint64_t)q.ldb, GKS, dt);
         if (!okm) return fail(DCLIP_ERR_CUDA, "gemm_tc: cuTensorMapEncodeTiled failed for problem %d", i);
         TcGemmDev& d = g.p[i];
         d.C = q.C; d.bias = q.bias; d.residual = q.residual; d.bias_kind = q.bias_kind; d.res_kind = q.res_kind;
@@ -423,6 +433,7 @@ int launch_gemm_tc(const TcGemmProblem* probs, int count, int dtype16, cudaStrea
         d.a_mn = q.a_mn; d.b_mn = q.b_mn; d.accumulate = q.accumulate;
         d.C16 = q.C16; d.c16_kind = q.C16 ? (dtype16 == DCLIP_BF16 ? 1 : 2) : 0; d.ldc16 = q.ldc16 > 0 ? q.ldc16 : q.ldc;
         d.alpha = q.alpha == 0.f ? 1.0f : q.alpha;
+        d.seg_len = q.seg_len; d.seg_map_a = q.seg_map_a; d.seg_map_b = q.seg_map_b;
         d.tiles_n = (q.N + GN - 1) / GN;
         d.tile_begin = tiles;
         d.tiles_mn = ((q.M + GM - 1) / GM) * d.tiles_n;

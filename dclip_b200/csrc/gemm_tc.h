@@ -19,6 +19,11 @@ struct TcGemmProblem {
     float alpha;    // C = alpha * A'B' + ... (0 = 1)
     int ksplit;     // > 1: the contraction is cut into `ksplit` slices of whole 64-wide k-blocks, slice s writes its partial
     long long split_stride;   // product to C + s * split_stride (fp32 output only, no bias / residual / accumulate); the caller sums
+    // Segmented contraction (fp32 operands split into 16-bit terms, xattn.cu): the logical K axis is `K / seg_len` segments of
+    // seg_len (a multiple of 64) and segment s reads PHYSICAL segment (seg_map >> 4 s) & 15 of the stored operand, whose K extent
+    // is k_phys - one stored term serves several term products.  seg_len = 0: plain contraction.
+    int seg_len, k_phys;
+    unsigned seg_map_a, seg_map_b;
 };
 
 int launch_gemm_tc(const TcGemmProblem* probs, int count, int dtype16, cudaStream_t st);

@@ -129,24 +129,27 @@ static GemmProblem gemm(const float* A, int lda, bool tA, const float* B, int ld
 // An fp32 value is x = h + m + l with three bf16 terms (8 + 8 + 8 mantissa bits: exact to 2^-27 |x|, fp32's full exponent
 // range - gradients of 1e-8 keep their precision, which an fp16 split would lose).  The product of two split operands
 // needs six of the nine term products (h l, l h, m m, h m, m h, h h; the rest is below 2^-26), and a sum of products over k
-// of six term pairs is ONE contraction over 6 K: the terms are written side by side along K,
-//     A' = [h | l | m | h | m | h],   B' = [l | h | m | m | h | h]      (smallest products first: they are accumulated
-//                                                                         before the large h h term can swamp them)
-// and the 16-bit grouped tcgen05 kernel (gemm_tc.cu) runs unchanged on [M, 6 K] x [N, 6 K] with fp32 accumulation in TMEM.
+// of six term pairs is ONE contraction over 6 K.  Every operand is stored once as [h | m | l] along K (segments of Kp = K
+// rounded up to the 64-wide k-block) and the grouped tcgen05 kernel (gemm_tc.cu, "segmented contraction") walks the six
+// logical segments
+//     A: h l m h m h      B: l h m m h h      (smallest products first: they are accumulated before the large h h term
+//                                              can swamp them)
+// by mapping each to the stored term it reads - 16-bit MMAs, fp32 accumulation in TMEM, nothing else changes.
 // Measured against an fp64 product (tools/exp_split_gemm.py, N(0,1) operands): 4.7e-7 at K = 512, 7.3e-7 at K = 768, 2.6e-6 at
 // K = 2464, torch's fp32 matmul (TF32 off) 4.1e-7 / 5.0e-7 / 8.9e-7 - inside the FP32 tier's 1e-5, at 6x the MMA work of a
 // 16-bit GEMM instead of CUDA-core FFMA (configs[0] teacher step: 1287 us of k_gemm_group per step).
 // This is what stands in for the TF32 tier north_star mentions: kind::tf32 keeps 10 mantissa bits (1e-3); the reference trains
 // its teacher in fp32 with TF32 off (torch default), so the drop-in keeps fp32 accuracy.
 // ---------------------------------------------------------------------------------------------
-constexpr int kSplitSegs = 6;
+constexpr int kSplitSegs = 6;          // logical segments of the contraction (term products)
+constexpr int kSplitTerms = 3;         // stored terms per operand: h | m | l
 constexpr int kSplitK = 6;           // slices of a long contraction (weight gradients)
 constexpr int kSplitKMinBlocks = 96; // ... when it has at least this many 64-wide k-blocks
 struct SplitJob {
     const float* src; __nv_bfloat16* dst;
     int rows, cols, ld;        // source matrix [rows, cols], row stride ld
     int out_rows, out_cols;    // iteration space: K-major operand rows x Kp;  MN-major operand Kp x ldd
-    int ldd, Kp, kmajor, role; // role 0 = A operand, 1 = B operand
+    int ldd, Kp, kmajor;
 };
 struct SplitGroup { SplitJob j[16]; int count; };
 
@@ -179,12 +182,9 @@ __global__ void __launch_bounds__(256) k_split_bf16x3(const __grid_constant__ Sp
                 t[q][i >> 1] = (uint32_t)__bfloat16_as_ushort(b0) | ((uint32_t)__bfloat16_as_ushort(b1) << 16);
             }
         }
-        // A' = [h l m h m h], B' = [l h m m h h]  (0 = h, 1 = m, 2 = l)
-        const int seqA[kSplitSegs] = {0, 2, 1, 0, 1, 0}, seqB[kSplitSegs] = {2, 0, 1, 1, 0, 0};
 #pragma unroll
-        for (int sgi = 0; sgi < kSplitSegs; ++sgi) {
-            const int q = J.role ? seqB[sgi] : seqA[sgi];
-            const size_t off = J.kmajor ? (size_t)r * J.ldd + (size_t)sgi * J.Kp + c : ((size_t)sgi * J.Kp + r) * J.ldd + c;
+        for (int q = 0; q < kSplitTerms; ++q) {
+            const size_t off = J.kmajor ? (size_t)r * J.ldd + (size_t)q * J.Kp + c : ((size_t)q * J.Kp + r) * J.ldd + c;
             *reinterpret_cast<uint4*>(J.dst + off) = make_uint4(t[q][0], t[q][1], t[q][2], t[q][3]);
         }
     }
@@ -227,12 +227,13 @@ static bool gemm_split_enabled() {
 // (d x d outputs, always cut) and for launches of fewer than sm_count() / 2 tiles (<= 74 tiles of 128 x 256 outputs, cut up to 6 ways).
 static size_t split_partial_cap(size_t out_elems) { return (out_elems < (size_t)74 * 128 * 256 ? out_elems : (size_t)74 * 128 * 256) * kSplitK * sizeof(float); }
 static size_t split_fwd_bytes(int64_t B, int64_t T, int64_t R, int64_t d) {
-    const size_t dp = (size_t)(d + 7) / 8 * 8, rows = (size_t)B * (T + R);
-    return (rows + 6 * d + 16) * kSplitSegs * dp * 2 + 16 * 256 + split_partial_cap((rows + 256) * 3 * dp) + 8 * 256;
+    const size_t dp = (size_t)(d + 63) / 64 * 64, rows = (size_t)B * (T + R);
+    return (rows + 6 * d + 16) * kSplitTerms * dp * 2 + 16 * 256 + split_partial_cap((rows + 256) * 3 * dp) + 8 * 256;
 }
 static size_t split_bwd_bytes(int64_t B, int64_t T, int64_t R, int64_t d) {
-    const size_t dp = (size_t)(d + 7) / 8 * 8, rows = (size_t)B * (T + R);
-    return ((rows + 32) * 24 * dp + 24 * dp * dp) * 2 + 16 * 256 + (size_t)kSplitK * 6 * dp * dp * sizeof(float) + split_partial_cap((rows + 256) * 2 * dp) + 8 * 256;
+    // the largest launch: weight gradients (contraction over the rows, padded to 64 per side) with their 4 + 2 operand matrices
+    const size_t dp = (size_t)(d + 63) / 64 * 64, rows = (size_t)B * (T + R) + 128;
+    return ((rows + 32) * 12 * dp + 12 * dp * dp) * 2 + 16 * 256 + (size_t)kSplitK * 6 * dp * dp * sizeof(float) + split_partial_cap((rows + 256) * 2 * dp) + 8 * 256;
 }
 
 static int launch_gemm_group_split(const GemmGroup& g, const SplitScratch& sc, cudaStream_t st) {
@@ -240,18 +241,18 @@ static int launch_gemm_group_split(const GemmGroup& g, const SplitScratch& sc, c
     SumGroup sums{};
     TcGemmProblem pr[8] = {};
     size_t used = 0;
-    auto operand = [&](const float* src, bool kmajor, int role, int mn, int K, int ld, int Kp, const __nv_bfloat16** out, int* ldd) -> int {
+    auto operand = [&](const float* src, bool kmajor, int mn, int K, int ld, int Kp, const __nv_bfloat16** out, int* ldd) -> int {
         const int rows = kmajor ? mn : K, cols = kmajor ? K : mn;
-        for (int i = 0; i < sg.count; ++i) {
+        for (int i = 0; i < sg.count; ++i) {        // a matrix that feeds several problems (either operand side) is split once
             const SplitJob& J = sg.j[i];
-            if (J.src == src && J.kmajor == (int)kmajor && J.role == role && J.rows == rows && J.cols == cols && J.ld == ld) { *out = J.dst; *ldd = J.ldd; return DCLIP_OK; }
+            if (J.src == src && J.kmajor == (int)kmajor && J.rows == rows && J.cols == cols && J.ld == ld) { *out = J.dst; *ldd = J.ldd; return DCLIP_OK; }
         }
         if (sg.count == 16) return fail(DCLIP_ERR_INVALID, "gemm split: too many distinct operands");
         SplitJob J{};
-        J.src = src; J.rows = rows; J.cols = cols; J.ld = ld; J.Kp = Kp; J.kmajor = kmajor; J.role = role;
-        if (kmajor) { J.ldd = kSplitSegs * Kp; J.out_rows = mn; J.out_cols = Kp; }
+        J.src = src; J.rows = rows; J.cols = cols; J.ld = ld; J.Kp = Kp; J.kmajor = kmajor;
+        if (kmajor) { J.ldd = kSplitTerms * Kp; J.out_rows = mn; J.out_cols = Kp; }
         else { J.ldd = (mn + 7) / 8 * 8; J.out_rows = Kp; J.out_cols = J.ldd; }
-        const size_t bytes = (kmajor ? (size_t)mn * J.ldd : (size_t)kSplitSegs * Kp * J.ldd) * 2;
+        const size_t bytes = (kmajor ? (size_t)mn * J.ldd : (size_t)kSplitTerms * Kp * J.ldd) * 2;
         if (used + bytes > sc.bytes) return fail(DCLIP_ERR_WORKSPACE, "gemm split: scratch too small (%zu + %zu > %zu)", used, bytes, sc.bytes);
         J.dst = reinterpret_cast<__nv_bfloat16*>(sc.base + used);
         used += align_up(bytes, 256);
@@ -259,18 +260,22 @@ static int launch_gemm_group_split(const GemmGroup& g, const SplitScratch& sc, c
         *out = J.dst; *ldd = J.ldd;
         return DCLIP_OK;
     };
+    // logical segment -> stored term (0 = h, 1 = m, 2 = l):  A: h l m h m h,  B: l h m m h h
+    constexpr unsigned kMapA = 0u | (2u << 4) | (1u << 8) | (0u << 12) | (1u << 16) | (0u << 20);
+    constexpr unsigned kMapB = 2u | (0u << 4) | (1u << 8) | (1u << 12) | (0u << 16) | (0u << 20);
     for (int i = 0; i < g.count; ++i) {
         const GemmProblem& P = g.p[i];
-        const int Kp = (P.K + 7) / 8 * 8;
+        const int Kp = (P.K + 63) / 64 * 64;          // segments are whole k-blocks
         const __nv_bfloat16* A2 = nullptr; const __nv_bfloat16* B2 = nullptr;
         int lda2 = 0, ldb2 = 0;
-        if (int e = operand(P.A, !P.transA, 0, P.M, P.K, P.lda, Kp, &A2, &lda2)) return e;
-        if (int e = operand(P.B, P.transB != 0, 1, P.N, P.K, P.ldb, Kp, &B2, &ldb2)) return e;
+        if (int e = operand(P.A, !P.transA, P.M, P.K, P.lda, Kp, &A2, &lda2)) return e;
+        if (int e = operand(P.B, P.transB != 0, P.N, P.K, P.ldb, Kp, &B2, &ldb2)) return e;
         TcGemmProblem q{};
         q.A = A2; q.B = B2; q.C = P.C; q.bias = P.bias; q.residual = P.residual; q.C16 = nullptr;
         q.M = P.M; q.N = P.N; q.K = kSplitSegs * Kp; q.lda = lda2; q.ldb = ldb2; q.ldc = P.ldc; q.ldr = P.ldr;
         q.a_mn = P.transA ? 1 : 0; q.b_mn = P.transB ? 0 : 1; q.accumulate = P.accumulate; q.alpha = P.alpha;
         q.bias_kind = 0; q.res_kind = 0;
+        q.seg_len = Kp; q.k_phys = kSplitTerms * Kp; q.seg_map_a = kMapA; q.seg_map_b = kMapB;
         pr[i] = q;
     }
     // split-K (see k_sum_partials): long contractions always, everything when the launch would leave most SMs idle
