@@ -279,15 +279,23 @@ static int launch_gemm_group_split(const GemmGroup& g, const SplitScratch& sc, c
         pr[i] = q;
     }
     // split-K (see k_sum_partials): long contractions always, everything when the launch would leave most SMs idle
+    // long contractions: as many slices (<= kSplitK) as still leave the launch within one wave of CTAs
+    auto tiles_of = [&](int i) { return ((g.p[i].M + 127) / 128) * ((g.p[i].N + 255) / 256); };
+    auto is_long = [&](int i) { return (pr[i].K + 63) / 64 >= kSplitKMinBlocks; };
+    int long_slices = kSplitK;
+    for (int ks = kSplitK; ks >= 2; --ks) {
+        int tot = 0;
+        for (int i = 0; i < g.count; ++i) tot += tiles_of(i) * (is_long(i) ? gemm_tc_slices(pr[i].K, ks) : 1);
+        if (tot <= sm_count()) { long_slices = ks; break; }
+    }
     int total_tiles = 0;      // with the long contractions already cut
-    for (int i = 0; i < g.count; ++i)
-        total_tiles += ((g.p[i].M + 127) / 128) * ((g.p[i].N + 255) / 256) * ((pr[i].K + 63) / 64 >= kSplitKMinBlocks ? gemm_tc_slices(pr[i].K, kSplitK) : 1);
+    for (int i = 0; i < g.count; ++i) total_tiles += tiles_of(i) * (is_long(i) ? gemm_tc_slices(pr[i].K, long_slices) : 1);
     const int fill = total_tiles > 0 ? sm_count() / total_tiles : 1;
     for (int i = 0; i < g.count; ++i) {
         const GemmProblem& P = g.p[i];
         TcGemmProblem& q = pr[i];
         const int nkb = (q.K + 63) / 64;
-        int want = nkb >= kSplitKMinBlocks ? kSplitK : 1;
+        int want = nkb >= kSplitKMinBlocks ? long_slices : 1;
         if (want == 1 && fill >= 2) want = min(min(fill, kSplitK), nkb / 8);
         if (want < 2 || sums.count == 8) continue;
         const int ks = gemm_tc_slices(q.K, want);
