@@ -579,44 +579,66 @@ __global__ void __launch_bounds__(kAttnThreads) k_attn_bwd(const __grid_constant
 // LayerNorm (eps 1e-5, biased variance, affine): one warp per row, d <= 4096
 // ---------------------------------------------------------------------------------------------
 constexpr float kLnEps = 1e-5f;
-__global__ void __launch_bounds__(256) k_ln_fwd(const float* __restrict__ z, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                int rows, int d, float* __restrict__ out, float* __restrict__ stats) {
+// both sides (text rows, image rows) in one launch: blocks [0, nblk0) serve side 0
+struct LnFwdSide32 { const float* z; const float* gamma; const float* beta; int rows; float* out; float* stats; };
+struct LnFwdArgs32 { LnFwdSide32 s[2]; int d, nblk0; };
+__global__ void __launch_bounds__(256) k_ln_fwd(const __grid_constant__ LnFwdArgs32 a) {
+    const int side = (int)blockIdx.x >= a.nblk0 ? 1 : 0;
+    const LnFwdSide32& S = a.s[side];
+    const int d = a.d;
     const int lane = threadIdx.x & 31;
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (row >= rows) return;
-    const float* zr = z + (size_t)row * d;
+    const int row = ((int)blockIdx.x - (side ? a.nblk0 : 0)) * 8 + (threadIdx.x >> 5);
+    if (row >= S.rows) return;
+    const float* zr = S.z + (size_t)row * d;
     float s = 0.f;
     for (int c = lane; c < d; c += 32) s += zr[c];
     const float mu = warp_sum(s) / d;
     float v = 0.f;
     for (int c = lane; c < d; c += 32) { const float t = zr[c] - mu; v = fmaf(t, t, v); }
     const float rstd = rsqrtf(warp_sum(v) / d + kLnEps);
-    for (int c = lane; c < d; c += 32) out[(size_t)row * d + c] = (zr[c] - mu) * rstd * gamma[c] + beta[c];
-    if (lane == 0) { stats[2 * row] = mu; stats[2 * row + 1] = rstd; }
+    for (int c = lane; c < d; c += 32) S.out[(size_t)row * d + c] = (zr[c] - mu) * rstd * S.gamma[c] + S.beta[c];
+    if (lane == 0) { S.stats[2 * row] = mu; S.stats[2 * row + 1] = rstd; }
+}
+static int launch_ln_fwd32(const LnFwdSide32& s0, const LnFwdSide32& s1, int d, cudaStream_t st) {
+    LnFwdArgs32 a{};
+    a.s[0] = s0; a.s[1] = s1; a.d = d; a.nblk0 = (int)ceil_div(s0.rows, 8);
+    k_ln_fwd<<<(unsigned)(a.nblk0 + ceil_div(s1.rows, 8)), 256, 0, st>>>(a);
+    DCLIP_LAUNCH_OK("k_ln_fwd");
+    return DCLIP_OK;
 }
 // dz = rstd (dy g - mean(dy g) - zhat mean(dy g zhat));  also writes zhat for the dgamma column sums
-__global__ void __launch_bounds__(256) k_ln_bwd(const float* __restrict__ dy, const float* __restrict__ z, const float* __restrict__ gamma,
-                                                const float* __restrict__ stats, int rows, int d, float* __restrict__ dz,
-                                                float* __restrict__ zhat) {
+struct LnBwdSide32 { const float* dy; const float* z; const float* gamma; const float* stats; int rows; float* dz; float* zhat; };
+struct LnBwdArgs32 { LnBwdSide32 s[2]; int d, nblk0; };
+__global__ void __launch_bounds__(256) k_ln_bwd(const __grid_constant__ LnBwdArgs32 a) {
+    const int side = (int)blockIdx.x >= a.nblk0 ? 1 : 0;
+    const LnBwdSide32& S = a.s[side];
+    const int d = a.d;
     const int lane = threadIdx.x & 31;
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (row >= rows) return;
-    const float mu = stats[2 * row], rstd = stats[2 * row + 1];
-    const float* zr = z + (size_t)row * d;
-    const float* dyr = dy + (size_t)row * d;
+    const int row = ((int)blockIdx.x - (side ? a.nblk0 : 0)) * 8 + (threadIdx.x >> 5);
+    if (row >= S.rows) return;
+    const float mu = S.stats[2 * row], rstd = S.stats[2 * row + 1];
+    const float* zr = S.z + (size_t)row * d;
+    const float* dyr = S.dy + (size_t)row * d;
     float s1 = 0.f, s2 = 0.f;
     for (int c = lane; c < d; c += 32) {
-        const float zh = (zr[c] - mu) * rstd, g = dyr[c] * gamma[c];
+        const float zh = (zr[c] - mu) * rstd, g = dyr[c] * S.gamma[c];
         s1 += g;
         s2 = fmaf(g, zh, s2);
     }
     s1 = warp_sum(s1) / d;
     s2 = warp_sum(s2) / d;
     for (int c = lane; c < d; c += 32) {
-        const float zh = (zr[c] - mu) * rstd, g = dyr[c] * gamma[c];
-        dz[(size_t)row * d + c] = rstd * (g - s1 - zh * s2);
-        zhat[(size_t)row * d + c] = zh;
+        const float zh = (zr[c] - mu) * rstd, g = dyr[c] * S.gamma[c];
+        S.dz[(size_t)row * d + c] = rstd * (g - s1 - zh * s2);
+        S.zhat[(size_t)row * d + c] = zh;
     }
+}
+static int launch_ln_bwd32(const LnBwdSide32& s0, const LnBwdSide32& s1, int d, cudaStream_t st) {
+    LnBwdArgs32 a{};
+    a.s[0] = s0; a.s[1] = s1; a.d = d; a.nblk0 = (int)ceil_div(s0.rows, 8);
+    k_ln_bwd<<<(unsigned)(a.nblk0 + ceil_div(s1.rows, 8)), 256, 0, st>>>(a);
+    DCLIP_LAUNCH_OK("k_ln_bwd");
+    return DCLIP_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1013,14 +1035,12 @@ int dclip_xattn_fwd(const void* text, const void* image, int64_t B, int64_t T, i
     }
     // (4) LayerNorm
     if (!wide) {
-        k_ln_fwd<<<(unsigned)ceil_div(nt, 8), 256, 0, st>>>(S + L.Zt, Wp[8], Wp[9], nt, D, static_cast<float*>(text_out), S + L.St);
-        k_ln_fwd<<<(unsigned)ceil_div(ni, 8), 256, 0, st>>>(S + L.Zi, Wp[10], Wp[11], ni, D, static_cast<float*>(image_out), S + L.Si);
-        DCLIP_LAUNCH_OK("k_ln_fwd");
+        if (int e = launch_ln_fwd32(LnFwdSide32{S + L.Zt, Wp[8], Wp[9], nt, static_cast<float*>(text_out), S + L.St},
+                                    LnFwdSide32{S + L.Zi, Wp[10], Wp[11], ni, static_cast<float*>(image_out), S + L.Si}, D, st)) return e;
     } else {
         // fp32 result staged in the widened-input slots (X copies are re-derived in the backward from the originals)
-        k_ln_fwd<<<(unsigned)ceil_div(nt, 8), 256, 0, st>>>(S + L.Zt, Wp[8], Wp[9], nt, D, S + L.Xt, S + L.St);
-        k_ln_fwd<<<(unsigned)ceil_div(ni, 8), 256, 0, st>>>(S + L.Zi, Wp[10], Wp[11], ni, D, S + L.Xi, S + L.Si);
-        DCLIP_LAUNCH_OK("k_ln_fwd");
+        if (int e = launch_ln_fwd32(LnFwdSide32{S + L.Zt, Wp[8], Wp[9], nt, S + L.Xt, S + L.St},
+                                    LnFwdSide32{S + L.Zi, Wp[10], Wp[11], ni, S + L.Xi, S + L.Si}, D, st)) return e;
         CastGroup cy{};
         cast_add(cy, S + L.Xt, text_out, (size_t)nt * d);
         cast_add(cy, S + L.Xi, image_out, (size_t)ni * d);
@@ -1097,9 +1117,8 @@ int dclip_xattn_bwd(const void* text, const void* image, int64_t B, int64_t T, i
     }
 
     // (4') LayerNorm backward: dZ, zhat; dgamma = colsum(dY * zhat), dbeta = colsum(dY)
-    k_ln_bwd<<<(unsigned)ceil_div(nt, 8), 256, 0, st>>>(dyt, S + L.Zt, Wp[8], S + L.St, nt, D, dZt, zht);
-    k_ln_bwd<<<(unsigned)ceil_div(ni, 8), 256, 0, st>>>(dyi, S + L.Zi, Wp[10], S + L.Si, ni, D, dZi, zhi);
-    DCLIP_LAUNCH_OK("k_ln_bwd");
+    if (int e = launch_ln_bwd32(LnBwdSide32{dyt, S + L.Zt, Wp[8], S + L.St, nt, dZt, zht}, LnBwdSide32{dyi, S + L.Zi, Wp[10], S + L.Si, ni, dZi, zhi}, D, st))
+        return e;
     ColsumGroup cg{};
     cg.p[0] = ColsumProblem{dyt, zht, nt, D, D, D, G[9], G[8]};       // dbeta = colsum(dY), dgamma = colsum(dY * zhat)
     cg.p[1] = ColsumProblem{dyi, zhi, ni, D, D, D, G[11], G[10]};
