@@ -51,6 +51,13 @@ struct SmallLossArgs {
 //   logits / G           [B][B + 1]: row walks and column walks are both conflict-free
 // partial block (exchange #1, floats): S[B*B] | nu[B] nv[B] ntu[B] ntv[B] dut[B] dvt[B];  exchange #2: ru[B] rv[B]
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+// e / n for the index splits of the phase loops: the kernel is instruction-bound on its 8 SMs and a run-time integer division is
+// ~30 instructions (ncu source view: 19 % of all executed instructions were these splits) - batch sizes are powers of two in practice
+struct FastDiv {      // exact for 0 <= e < 2^16, 1 <= n < 2^16 (multiply-high by ceil(2^32 / n))
+    int n; unsigned magic;
+    __device__ __forceinline__ explicit FastDiv(int n_) : n(n_), magic(n_ > 1 ? 0xFFFFFFFFu / (unsigned)n_ + 1u : 0u) {}
+    __device__ __forceinline__ int div(int e) const { return n > 1 ? (int)__umulhi((unsigned)e, magic) : e; }
+};
 
 template <typename T>
 __global__ void __cluster_dims__(sm::kCluster, 1, 1) __launch_bounds__(sm::kThreads) k_distill_small(const SmallLossArgs a) {
@@ -80,7 +87,7 @@ __global__ void __cluster_dims__(sm::kCluster, 1, 1) __launch_bounds__(sm::kThre
     // 1. load my slice (8 columns per thread and tensor; columns past d are zeros)
 #pragma unroll 1
     for (int e = tid; e < B * (w >> 3); e += kThreads) {
-        const int i = e / (w >> 3), c = (e - i * (w >> 3)) * 8;
+        const int i = FastDiv(w >> 3).div(e), c = (e - i * (w >> 3)) * 8;
         const bool in = c < wc;          // wc is a multiple of 8 (d % 8 == 0, w % 8 == 0)
         const size_t g = (size_t)i * d + c0 + c;
 #pragma unroll
@@ -98,7 +105,7 @@ __global__ void __cluster_dims__(sm::kCluster, 1, 1) __launch_bounds__(sm::kThre
     // 2. partial raw logits: thread (ti, tj) owns rows {ti, ti + hB} x columns {tj, tj + hB}
 #pragma unroll 1
     for (int e = tid; e < hB * hB; e += kThreads) {
-        const int ti = e / hB, tj = e - ti * hB;
+        const int ti = FastDiv(hB).div(e), tj = e - ti * hB;
         const int i1 = min(ti + hB, B - 1), j1 = min(tj + hB, B - 1);
         const float* u0 = U + (size_t)ti * ws; const float* u1 = U + (size_t)i1 * ws;
         const float* v0 = V + (size_t)tj * ws; const float* v1 = V + (size_t)j1 * ws;
@@ -119,19 +126,27 @@ __global__ void __cluster_dims__(sm::kCluster, 1, 1) __launch_bounds__(sm::kThre
         }
     }
     // squared norms and student-teacher dots: one warp per (quantity, row)
+    const FastDiv divB(B);
 #pragma unroll 1
-    for (int e = warp; e < 6 * B; e += kWarps) {
-        const int q = e / B, i = e - q * B;
-        const float* x = ((q == 0 || q == 4) ? U : (q == 1 || q == 5) ? V : q == 2 ? TU : TV) + (size_t)i * ws;
-        const float* y = q == 4 ? TU + (size_t)i * ws : q == 5 ? TV + (size_t)i * ws : x;
-        float s = 0.f;
-        if (has_t || q < 2)
+    for (int q = 0; q < 6; ++q) {
+        const float* xq = (q == 0 || q == 4) ? U : (q == 1 || q == 5) ? V : q == 2 ? TU : TV;
+        const float* yq = q == 4 ? TU : q == 5 ? TV : xq;
+        if (!has_t && q >= 2) {                        // no teachers: those sums are zero (no warp walks them)
+            for (int i = tid; i < B; i += kThreads) part[B * B + q * B + i] = 0.f;
+            continue;
+        }
+#pragma unroll 1
+        for (int i = warp; i < B; i += kWarps) {
+            const float* x = xq + (size_t)i * ws;
+            const float* y = yq + (size_t)i * ws;
+            float s = 0.f;
             for (int c = lane * 4; c < w; c += 128) {
                 const float4 p = lds4(x + c), r = lds4(y + c);
                 s = fmaf(p.x, r.x, fmaf(p.y, r.y, fmaf(p.z, r.z, fmaf(p.w, r.w, s))));
             }
-        s = warp_sum(s);
-        if (lane == 0) part[B * B + e] = s;
+            s = warp_sum(s);
+            if (lane == 0) part[B * B + q * B + i] = s;
+        }
     }
     SPROF(2);
     cluster.sync();
@@ -154,14 +169,14 @@ __global__ void __cluster_dims__(sm::kCluster, 1, 1) __launch_bounds__(sm::kThre
     // 4. logits, statistics, G
 #pragma unroll 1
     for (int e = tid; e < B * B; e += kThreads) {
-        const int i = e / B, j = e - i * B;
+        const int i = divB.div(e), j = e - i * B;
         Sg[i * BP + j] = full[e] * inv_u[i] * inv_v[j] * a.inv_tau;
     }
     __syncthreads();
     SPROF(5);
 #pragma unroll 1
     for (int e = warp; e < 2 * B; e += kWarps) {        // row / column log-sum-exp: one warp per (side, row), fixed-order reductions
-        const int side = e / B, i = e - side * B;
+        const int side = e >= B ? 1 : 0, i = e - side * B;
         float mx = -INFINITY;
         for (int j = lane; j < B; j += 32) mx = fmaxf(mx, side ? Sg[j * BP + i] : Sg[i * BP + j]);
         mx = warp_max(mx);
@@ -197,14 +212,14 @@ __global__ void __cluster_dims__(sm::kCluster, 1, 1) __launch_bounds__(sm::kThre
     const float coef = a.w_con / (2.0f * B);
 #pragma unroll 1
     for (int e = tid; e < B * B; e += kThreads) {
-        const int i = e / B, j = e - i * B;
+        const int i = divB.div(e), j = e - i * B;
         const float s = Sg[i * BP + j];
         G[i * BP + j] = coef * (__expf(s - lse_r[i]) + __expf(s - lse_c[j]) - (i == j ? 2.0f : 0.f));
     }
     // normalised rows of my slice (in place)
 #pragma unroll 1
     for (int e = tid; e < B * (w >> 2); e += kThreads) {
-        const int i = e / (w >> 2), c = (e - i * (w >> 2)) * 4;
+        const int i = FastDiv(w >> 2).div(e), c = (e - i * (w >> 2)) * 4;
         float4 x = lds4(U + (size_t)i * ws + c), y = lds4(V + (size_t)i * ws + c);
         const float su = inv_u[i], sv = inv_v[i];
         *reinterpret_cast<float4*>(U + (size_t)i * ws + c) = make_float4(x.x * su, x.y * su, x.z * su, x.w * su);
@@ -217,10 +232,11 @@ __global__ void __cluster_dims__(sm::kCluster, 1, 1) __launch_bounds__(sm::kThre
     float* DU = TU;                       // the teacher slices are consumed on the fly and overwritten with the gradients
     float* DV = TV;
     const int ncg = w >> 2, nrb = (B + 31) >> 5;
+    const FastDiv divR(nrb);
 #pragma unroll 1
     for (int e = warp; e < 2 * ncg * nrb; e += kWarps) {
-        const int side = e / (ncg * nrb), r = e - side * ncg * nrb;
-        const int cgi = r / nrb, i = (r - cgi * nrb) * 32 + lane;
+        const int side = e >= ncg * nrb ? 1 : 0, r = e - side * ncg * nrb;
+        const int cgi = divR.div(r), i = (r - cgi * nrb) * 32 + lane;
         const int c = cgi * 4;
         const int ic = min(i, B - 1);
         const float* Y = (side ? U : V) + c;
@@ -247,7 +263,7 @@ __global__ void __cluster_dims__(sm::kCluster, 1, 1) __launch_bounds__(sm::kThre
     // partial projection dots u_hat_i . d_u_hat_i over my slice: one warp per (side, row)
 #pragma unroll 1
     for (int e = warp; e < 2 * B; e += kWarps) {
-        const int side = e / B, i = e - side * B;
+        const int side = e >= B ? 1 : 0, i = e - side * B;
         const float* x = (side ? V : U) + (size_t)i * ws;
         const float* gq = (side ? DV : DU) + (size_t)i * ws;
         float s = 0.f;
@@ -273,8 +289,8 @@ __global__ void __cluster_dims__(sm::kCluster, 1, 1) __launch_bounds__(sm::kThre
     const int nch = w >> 3;
 #pragma unroll 1
     for (int e = tid; e < 2 * B * nch; e += kThreads) {
-        const int side = e / (B * nch), r = e - side * B * nch;
-        const int i = r / nch, c = (r - i * nch) * 8;
+        const int side = e >= B * nch ? 1 : 0, r = e - side * B * nch;
+        const int i = FastDiv(nch).div(r), c = (r - i * nch) * 8;
         if (c >= wc) continue;
         const float* x = (side ? V : U) + (size_t)i * ws + c;
         const float* gq = (side ? DV : DU) + (size_t)i * ws + c;
