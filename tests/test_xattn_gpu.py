@@ -146,6 +146,31 @@ def test_16bit_tensor_tier_forward_backward(built_library, dtype):
         assert e_ours < 2.0 * e_torch + 1e-3, (name, e_ours, e_torch)
 
 
+@pytest.mark.parametrize("B,T,R,d,heads", [(3, 5, 3, 72, 8), (2, 9, 4, 136, 8), (5, 13, 7, 64, 4)])
+def test_fp32_tier_split_gemms_odd_shapes(built_library, monkeypatch, B, T, R, d, heads):
+    """The bf16 x 3 split path at shapes whose contraction lengths (d, B T, B R) are not multiples of the 64-wide k-block
+    (zero-padded segments) and whose outputs do not fill a tile: same results as the CUDA-core GEMMs to fp32 accuracy."""
+    params = om.perturbed_cross_attention_params(d, heads, 21)
+    text, image = synthetic.xattn_inputs(B, T, R, d, 21, ragged=True)
+    gt = torch.randn(B, T, d, generator=torch.Generator().manual_seed(8))
+    gi = torch.randn(B, R, d, generator=torch.Generator().manual_seed(9))
+
+    def run():
+        m = _module(d, heads, params)
+        t = text.to(DEV).requires_grad_(True)
+        i = image.to(DEV).requires_grad_(True)
+        to, io = m.cross_attention(t, i)
+        ((to * gt.to(DEV)).sum() + (io * gi.to(DEV)).sum()).backward()
+        return [to.detach(), io.detach(), t.grad, i.grad] + [p.grad for _, p in sorted(m.cross_modal_attention.named_parameters())]
+
+    monkeypatch.setenv("DCLIP_XATTN_SPLIT", "0")
+    ref = run()
+    monkeypatch.delenv("DCLIP_XATTN_SPLIT")
+    got = run()
+    for a, b in zip(got, ref):
+        assert _rel(a, b) < 2e-5
+
+
 def test_fp32_tier_tensor_core_gemms_match_cuda_core_gemms(built_library, monkeypatch):
     """fp32 inputs run their GEMMs on tcgen05 through bf16 x 3 operand splitting (csrc/xattn.cu: run_gemm_group); with
     DCLIP_XATTN_SPLIT=0 the CUDA-core fp32 GEMM of round 1 runs instead.  Both must sit inside the FP32 tier against the
