@@ -515,6 +515,19 @@ __device__ __forceinline__ void smem_softmax_rows(float* P, int lp, int Lq, int 
 }
 
 __device__ __forceinline__ void load_head(float* dst, int ld, const float* src, int64_t row0, int rows, int64_t ldsrc, int col0, int hd) {
+    const int q4 = hd >> 2;
+    if ((hd & 3) == 0 && (ldsrc & 3) == 0 && (col0 & 3) == 0 && q4 <= kAttnThreads && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        // a thread keeps its 4-column group and walks rows: one index split per call instead of one per element (the per-element
+        // idx / hd was as many instructions as the FMAs of the five micro-GEMMs together), 16-byte global loads
+        const int c = (threadIdx.x % q4) * 4, r0 = threadIdx.x / q4, rstep = kAttnThreads / q4;
+        if (r0 < rstep)            // threads past the last whole row group (hd / 4 does not divide the block) sit out
+            for (int r = r0; r < rows; r += rstep) {
+                const float4 v = *reinterpret_cast<const float4*>(src + (row0 + r) * ldsrc + col0 + c);
+                float* o = dst + r * ld + c;
+                o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+            }
+        return;
+    }
     for (int idx = threadIdx.x; idx < rows * hd; idx += kAttnThreads) {
         const int r = idx / hd, e = idx - r * hd;
         dst[r * ld + e] = src[(row0 + r) * ldsrc + col0 + e];
