@@ -107,7 +107,8 @@ def test_linear_rows_odd_shapes(built_library, dtype):
             # fp32 accumulation: the result is the correctly rounded fp64 value except where fp32 summation error crosses a rounding boundary
             err = float((got - want).abs().max() / want.abs().max())
             rnd = float((rounded - want).abs().max() / want.abs().max())
-            assert got.shape == want.shape and err <= 1.05 * rnd + 1e-6, (n, k, m, bias is not None, err, rnd)
+            # (an element whose fp32 sum lands across a rounding boundary is off by one ulp instead of half: 2 x, never more)
+            assert got.shape == want.shape and err <= 2.1 * rnd + 1e-6, (n, k, m, bias is not None, err, rnd)
 
 
 def _clone_params(shapes, dtype, seed):
