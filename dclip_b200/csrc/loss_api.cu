@@ -618,6 +618,37 @@ int dclip_distill_loss_teachers(const void* s_img, const void* s_txt, const void
                              d_s_txt, nullptr, workspace, workspace_bytes, path, stream);
 }
 
+int dclip_host_distill_step(const void* h_s_img, const void* h_s_txt, const void* h_t_img, const void* h_t_txt, void* const* d_in,
+                            int64_t B, int64_t d, int dtype, float temperature, float w_img, float w_txt, float w_con, float grad_scale,
+                            float* d_losses, float* h_losses, void* d_s_img, void* d_s_txt, void* workspace, size_t workspace_bytes, int path,
+                            void* compute_stream, void* copy_stream, void* ev_students, void* ev_teachers, void* ev_done) {
+    DCLIP_REQUIRE(h_s_img && h_s_txt && h_t_img && h_t_txt && d_in && d_in[0] && d_in[1] && d_in[2] && d_in[3] && d_losses && h_losses,
+                  "host_distill_step: null pointer");
+    DCLIP_REQUIRE(copy_stream && ev_students && ev_teachers && ev_done && copy_stream != compute_stream,
+                  "host_distill_step: needs a copy stream of its own and three events");
+    cudaStream_t cs = static_cast<cudaStream_t>(compute_stream), xs = static_cast<cudaStream_t>(copy_stream);
+    cudaEvent_t es = static_cast<cudaEvent_t>(ev_students), et = static_cast<cudaEvent_t>(ev_teachers), ed = static_cast<cudaEvent_t>(ev_done);
+    const size_t bytes = (size_t)B * d * dclip::dtype_size(dtype);
+    // the device input buffers are free again once the previous step's kernels are done
+    DCLIP_CUDA_OK(cudaStreamWaitEvent(xs, ed, 0));
+    DCLIP_CUDA_OK(cudaMemcpyAsync(d_in[0], h_s_img, bytes, cudaMemcpyHostToDevice, xs));
+    DCLIP_CUDA_OK(cudaMemcpyAsync(d_in[1], h_s_txt, bytes, cudaMemcpyHostToDevice, xs));
+    DCLIP_CUDA_OK(cudaEventRecord(es, xs));
+    DCLIP_CUDA_OK(cudaMemcpyAsync(d_in[2], h_t_img, bytes, cudaMemcpyHostToDevice, xs));
+    DCLIP_CUDA_OK(cudaMemcpyAsync(d_in[3], h_t_txt, bytes, cudaMemcpyHostToDevice, xs));
+    DCLIP_CUDA_OK(cudaEventRecord(et, xs));
+    DCLIP_CUDA_OK(cudaStreamWaitEvent(cs, es, 0));
+    if (int e = distill_loss_impl(1, d_in[0], d_in[1], nullptr, nullptr, B, d, dtype, temperature, 0.f, 0.f, w_con, 1.f, nullptr, nullptr, nullptr,
+                                  nullptr, workspace, workspace_bytes, path, compute_stream)) return e;
+    DCLIP_CUDA_OK(cudaStreamWaitEvent(cs, et, 0));
+    if (int e = distill_loss_impl(2, d_in[0], d_in[1], d_in[2], d_in[3], B, d, dtype, temperature, w_img, w_txt, w_con, grad_scale, d_losses,
+                                  d_s_img, d_s_txt, nullptr, workspace, workspace_bytes, path, compute_stream)) return e;
+    DCLIP_CUDA_OK(cudaMemcpyAsync(h_losses, d_losses, 4 * sizeof(float), cudaMemcpyDeviceToHost, cs));
+    DCLIP_CUDA_OK(cudaEventRecord(ed, cs));
+    DCLIP_CUDA_OK(cudaStreamSynchronize(cs));
+    return DCLIP_OK;
+}
+
 int dclip_scale_grad(const void* x, int64_t n, int dtype, const float* scale, void* out, void* stream) {
     DCLIP_REQUIRE(x && scale && out && n > 0 && n % 8 == 0, "scale_grad: bad arguments (n must be a positive multiple of 8)");
     DCLIP_REQUIRE(dclip::aligned16(x) && dclip::aligned16(out), "scale_grad: pointers must be 16-byte aligned");

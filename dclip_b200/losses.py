@@ -11,6 +11,8 @@ All arithmetic runs in the CUDA library behind include/dclip_b200.h; the B x B l
 never materialised.  `distill_loss_fwd_bwd` is the raw fused call (forward + backward in
 one pass over the library), the autograd wrappers are thin shells around it.
 """
+import ctypes
+
 import torch
 import torch.nn as nn
 
@@ -88,34 +90,27 @@ class HostDistillStep:
         self.copy_stream = torch.cuda.Stream(self.dev)
         self.ev_students = torch.cuda.Event()
         self.ev_teachers = torch.cuda.Event()
+        self.ev_done = torch.cuda.Event()
+        with torch.cuda.device(self.dev):
+            for ev in (self.ev_students, self.ev_teachers, self.ev_done):      # creates the CUDA events (torch makes them lazily)
+                ev.record(torch.cuda.current_stream(self.dev))
+        self._d_in = (ctypes.c_void_p * 4)(*[t.data_ptr() for t in self.bufs])
+        self._shape = (self.B, self.d)
 
     def __call__(self, s_img, s_txt, t_img, t_txt):
+        """One step = ONE library call (dclip_host_distill_step): the four copies on the copy stream, students first; the contrastive
+        part on the current stream behind the students' event, overlapped with the teachers' copy; the teachers' part; the read of the
+        four losses and the one host wait."""
         for t in (s_img, s_txt, t_img, t_txt):
-            if t.is_cuda or tuple(t.shape) != (self.B, self.d) or t.dtype != self.dtype:
-                raise ValueError(f"HostDistillStep: expected four host [{self.B}, {self.d}] {self.dtype} tensors")
+            if t.is_cuda or tuple(t.shape) != self._shape or t.dtype != self.dtype or not t.is_contiguous():
+                raise ValueError(f"HostDistillStep: expected four contiguous host [{self.B}, {self.d}] {self.dtype} tensors")
         temperature, w_img, w_txt, w_con, grad_scale = self.hyper
-        cur = torch.cuda.current_stream(self.dev)
-        b = self.bufs
-        self.copy_stream.wait_stream(cur)                  # the previous step has finished with the device buffers
-        with torch.cuda.stream(self.copy_stream):
-            b[0].copy_(s_img, non_blocking=True)
-            b[1].copy_(s_txt, non_blocking=True)
-            self.ev_students.record()
-            b[2].copy_(t_img, non_blocking=True)
-            b[3].copy_(t_txt, non_blocking=True)
-            self.ev_teachers.record()
-        dt = dtype_code(b[0])
         with torch.cuda.device(self.dev):
-            cur.wait_event(self.ev_students)
-            check(self.lib.dclip_distill_loss_students(ptr(b[0]), ptr(b[1]), self.B, self.d, dt, temperature, w_con, ptr(self.ws),
-                                                       self.ws.numel(), self.pc, stream_ptr(self.dev)), "distill_loss_students")
-            cur.wait_event(self.ev_teachers)
-            check(self.lib.dclip_distill_loss_teachers(ptr(b[0]), ptr(b[1]), ptr(b[2]), ptr(b[3]), self.B, self.d, dt, temperature, w_img,
-                                                       w_txt, w_con, grad_scale, ptr(self.losses), ptr(self.d_img), ptr(self.d_txt),
-                                                       ptr(self.ws), self.ws.numel(), self.pc, stream_ptr(self.dev)),
-                  "distill_loss_teachers")
-            self.losses_host.copy_(self.losses, non_blocking=True)
-            cur.synchronize()
+            check(self.lib.dclip_host_distill_step(
+                s_img.data_ptr(), s_txt.data_ptr(), t_img.data_ptr(), t_txt.data_ptr(), self._d_in, self.B, self.d, dtype_code(self.bufs[0]),
+                temperature, w_img, w_txt, w_con, grad_scale, ptr(self.losses), self.losses_host.data_ptr(), ptr(self.d_img), ptr(self.d_txt),
+                ptr(self.ws), self.ws.numel(), self.pc, stream_ptr(self.dev), self.copy_stream.cuda_stream, self.ev_students.cuda_event,
+                self.ev_teachers.cuda_event, self.ev_done.cuda_event), "host_distill_step")
         return self.losses_host, self.d_img, self.d_txt
 
 

@@ -326,6 +326,19 @@ int dclip_xattn_bwd(const void* text, const void* image, int64_t B, int64_t T, i
                     const void* const* params, const void* saved, const void* d_text_out, const void* d_image_out,
                     void* const* grads, void* d_text, void* d_image, void* scratch, size_t scratch_bytes, void* stream);
 
+/* One whole step for inputs in PINNED HOST memory, issued by ONE call (the per-step Python between the pieces - stream contexts,
+ * event objects, four tensor copies - was 56 us of a 0.56 ms step): waits for ev_done of the previous step on the copy stream, copies
+ * the four [B, d] inputs to d_in[0..3] there (students first, ev_students / ev_teachers recorded behind each pair), runs
+ * dclip_distill_loss_students / _teachers on the compute stream behind those events (the contrastive part overlaps the teachers'
+ * copy), copies the four losses to h_losses (pinned), records ev_done and synchronises the compute stream - the one host wait of the
+ * reference's `loss.item()` (training/train_contrastive_teacher.py:364).  The caller owns streams and events (created once, ev_done
+ * recorded once before the first call); gradients stay on the device in d_s_img / d_s_txt. */
+int dclip_host_distill_step(const void* h_s_img, const void* h_s_txt, const void* h_t_img, const void* h_t_txt, void* const* d_in,
+                            int64_t B, int64_t d, int dtype, float temperature, float w_img, float w_txt, float w_con,
+                            float grad_scale, float* d_losses, float* h_losses, void* d_s_img, void* d_s_txt, void* workspace,
+                            size_t workspace_bytes, int path, void* compute_stream, void* copy_stream, void* ev_students,
+                            void* ev_teachers, void* ev_done);
+
 /* out[i] = x[i] * (*scale), scale a float on the DEVICE: the upstream gradient of the scalar loss
  * (`loss.backward()`, training/train_contrastive_teacher.py:361; CLIP_image_distillation.py:634 through Lightning) applied to
  * the gradients that dclip_distill_loss_fwd_bwd already produced - no host read of the factor, graph-capturable.
