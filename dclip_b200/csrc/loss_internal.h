@@ -43,7 +43,8 @@ struct GradArgs {
     float coef_over_tau;
 };
 
-struct TailSide { const void* x; const void* t; const float* inv_norm; const float* dx_hat; void* d_x; };
+struct TailSide { const void* x; const void* t; const float* inv_norm; const float* dx_hat; void* d_x;
+                  float* cos_out; };      // optional: cos(x, t) of the row (the split host-buffer step: saves the separate cosine pass)
 struct TailArgs {
     TailSide s[2]; int64_t m, d; float w_cos_over_B[2]; float grad_scale;
     PeerCtx peers;                       // peers.world > 1: the last block tells every peer that this rank is done with the step's buffers

@@ -593,6 +593,18 @@ __global__ void __launch_bounds__(kThreads) k_loss_grad_tail(TailArgs a) {
         }
         tt = warp_sum(tt);
         t_scale = -a.w_cos_over_B[blockIdx.y] / fmaxf(sqrtf(tt), kNormEps);
+        if (s.cos_out) {          // the row's cosine term, exactly as k_cos_rows forms it
+            float xt = 0.f;
+            for (int64_t k = lane * 8; k < d; k += 256) {
+                float xv[8], tv[8];
+                load8<T>(x + k, xv);
+                load8<T>(t + k, tv);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) xt = fmaf(xv[i], tv[i], xt);
+            }
+            xt = warp_sum(xt);
+            if (lane == 0) s.cos_out[row] = xt * inv / fmaxf(sqrtf(tt), kNormEps);
+        }
     }
     // pass 1: dot = x_hat . g
     float dot = 0.f;
@@ -681,6 +693,20 @@ __global__ void __launch_bounds__(128) k_loss_grad_tail_nc(TailArgs a) {
             }
         tt = warp_sum(tt);
         const float t_scale = -a.w_cos_over_B[blockIdx.y] / fmaxf(sqrtf(tt), kNormEps);
+        if (s.cos_out) {          // the row's cosine term, exactly as k_cos_rows forms it (same chunk order per lane)
+            float xt = 0.f;
+#pragma unroll
+            for (int k = 0; k < NC; ++k)
+                if (lane + 32 * k < nch) {
+                    float x[8], t[8];
+                    unpack8<T>(xr[k], x);
+                    unpack8<T>(tr[k], t);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) xt = fmaf(x[i], t[i], xt);
+                }
+            xt = warp_sum(xt);
+            if (lane == 0) s.cos_out[row] = xt * inv / fmaxf(sqrtf(tt), kNormEps);
+        }
 #pragma unroll
         for (int k = 0; k < NC; ++k)
             if (lane + 32 * k < nch) {
