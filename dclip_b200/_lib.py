@@ -59,7 +59,7 @@ SIGNATURES = {
     "dclip_combine_guard_bwd": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "dclip_scale_grad": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp]),
     "dclip_host_distill_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _sz, _i32,
-                                       _vp, _vp, _vp, _vp, _vp]),
+                                       _vp, _vp, _vp, _vp, _vp, _vp]),
     "dclip_sharded_loss_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "dclip_sharded_loss_prep": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _f32, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dclip_sharded_loss_fwd": (_i32, [_vp, _vp, _i64, _i64, _i64, _f32, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),

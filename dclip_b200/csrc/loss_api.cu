@@ -430,7 +430,7 @@ size_t dclip_distill_loss_workspace_bytes(int64_t B, int64_t d, int path) {
         if (tc_gmat_ok(B, d))     // fp16 gradient coefficients G + row / column sums of g * s + the teachers' inverse norms
             total += align_up(tc_gmat_bytes(B), 256) + align_up(tc_gmat_dot_floats(B) * 4, 256) + 2 * align_up((size_t)B * 4, 256);
     }
-    return total + 1024;
+    return total + 256 + 1024;     // + the split objective's sums / block counter
 }
 
 // phase 0: the whole objective.  Phases 1 / 2 split it at the point where the TEACHER embeddings are first
@@ -438,10 +438,13 @@ size_t dclip_distill_loss_workspace_bytes(int64_t B, int64_t d, int path) {
 // part (dclip_distill_loss_students / _teachers; both phases carve the same workspace):
 //   phase 1 (students only): normalise, forward tiles, log-sum-exp, backward tiles -> du_hat, dv_hat, lse, diag
 //   phase 2 (teachers):      cosine terms, the four losses, gradient tail (normalise backward + cosine gradient)
+// The teachers phase of the host-buffer step is issued per side (TailCtl::sides): the image side's tail runs while the text teacher is
+// still crossing PCIe, the text side's tail finishes the losses and stores them into host memory (TailSums).
+struct TailCtl { int sides; float* losses_host; unsigned int seq; };      // sides: 0 both (one launch), 1 image side only, 2 text side + losses
 static int distill_loss_impl(int phase, const void* s_img, const void* s_txt, const void* t_img, const void* t_txt, int64_t B,
                              int64_t d, int dtype, float temperature, float w_img, float w_txt, float w_con,
                              float grad_scale, float* losses, void* d_s_img, void* d_s_txt, float* stats,
-                             void* workspace, size_t workspace_bytes, int path, void* stream) {
+                             void* workspace, size_t workspace_bytes, int path, void* stream, TailCtl ctl = TailCtl{0, nullptr, 0u}) {
     if (int e = check_common(B, d)) return e;
     DCLIP_REQUIRE(B > 0, "distill_loss: empty batch");
     DCLIP_REQUIRE(s_img && s_txt && (losses || phase == 1), "distill_loss: null pointer");
@@ -495,6 +498,9 @@ static int distill_loss_impl(int phase, const void* s_img, const void* s_txt, co
     float* dot_ws = gmat ? static_cast<float*>(ws.take(tc_gmat_dot_floats(B) * 4)) : nullptr;
     float* tinv_u = gmat ? static_cast<float*>(ws.take((size_t)B * 4)) : nullptr;
     float* tinv_v = gmat ? static_cast<float*>(ws.take((size_t)B * 4)) : nullptr;
+    // split objective: raw contrastive sum of the students phase [0..2] and the teachers phase's block counter [4]
+    float* split_sums = static_cast<float*>(ws.take(64));
+    unsigned int* tail_counter = reinterpret_cast<unsigned int*>(split_sums + 4);
     // one-call objective: the GEMM epilogue finishes the gradients (no fp32 dX_hat round trip, no tail launch)
     const char* ft_env = getenv("DCLIP_GMAT_FUSED_TAIL");      // "0": fp32 dX_hat + the tail kernel (A/B measurements, tests)
     const bool fused_tail = gmat && phase == 0 && d_s_img && w_con != 0.f && !(ft_env && ft_env[0] == '0');
@@ -503,7 +509,7 @@ static int distill_loss_impl(int phase, const void* s_img, const void* s_txt, co
 
     const bool do_students = phase != 2, do_teachers = phase != 1;
     // phase 2 with gradients: the gradient tail reads the raw student / teacher rows anyway and leaves the cosine terms (TailSide::cos_out);
-    // the losses are summed behind it - one pass over the 4 x B x d rows instead of two behind the teachers' copy (12 us of a host step)
+    // its last block finishes the losses (TailSums) - one pass over the 4 x B x d rows and ONE launch behind the teachers' copy
     const bool cos_in_tail = phase == 2 && d_s_img && t_img;
     if (phase == 2 && !cos_in_tail) {
         // cosine terms of the rows (the norms of the students are phase 1's), then the four losses
@@ -539,8 +545,8 @@ static int distill_loss_impl(int phase, const void* s_img, const void* s_txt, co
         fa.m = B; fa.n = B; fa.d = d; fa.inv_tau = 1.0f / temperature; fa.row_offset = 0;
         if (int e = launch_stream_tc(1, 1, xs2, ys2, fa, ns1, st)) return e;
         FinalizeArgs fz{rowpart, colpart, ns1, B, fa.inv_tau, lse_u, lse_v,
-                        SumsArgs{lse_u, lse_v, diag, t_img ? cos_img : nullptr, t_txt ? cos_txt : nullptr, B, nullptr, phase == 0 ? losses : nullptr,
-                                 w_img, w_txt, w_con},
+                        SumsArgs{lse_u, lse_v, diag, t_img ? cos_img : nullptr, t_txt ? cos_txt : nullptr, B, phase == 1 ? split_sums : nullptr,
+                                 phase == 0 ? losses : nullptr, w_img, w_txt, w_con, phase == 1 ? tail_counter : nullptr},
                         nib};
         if (int e = launch_tc_finalize(fz, st)) return e;
     } else {
@@ -553,6 +559,9 @@ static int distill_loss_impl(int phase, const void* s_img, const void* s_txt, co
 
     if (!tensor && phase == 0) {
         SumsArgs sa{lse_u, lse_v, diag, t_img ? cos_img : nullptr, t_txt ? cos_txt : nullptr, B, nullptr, losses, w_img, w_txt, w_con};
+        if (int e = launch_loss_sums(sa, st)) return e;
+    } else if (!tensor && phase == 1) {      // raw contrastive sum for the teachers phase (the tensor path's finalize kernel leaves it)
+        SumsArgs sa{lse_u, lse_v, diag, nullptr, nullptr, B, split_sums, nullptr, 0.f, 0.f, 0.f, tail_counter};
         if (int e = launch_loss_sums(sa, st)) return e;
     }
 
@@ -595,11 +604,14 @@ static int distill_loss_impl(int phase, const void* s_img, const void* s_txt, co
         ta.s[1] = TailSide{s_txt, t_txt, inv_v, need_con ? dv_hat : nullptr, d_s_txt, cos_in_tail ? cos_txt : nullptr};
         ta.w_cos_over_B[0] = w_img / (float)B;
         ta.w_cos_over_B[1] = w_txt / (float)B;
-        if (int e = launch_grad_tail(ta, 2, dtype, st)) return e;
-        if (cos_in_tail) {
-            SumsArgs sa{lse_u, lse_v, diag, cos_img, cos_txt, B, nullptr, losses, w_img, w_txt, w_con};
-            if (int e = launch_loss_sums(sa, st)) return e;
+        if (cos_in_tail && ctl.sides == 1) return launch_grad_tail(ta, 1, dtype, st);      // image side only; the text side's launch finishes the losses
+        if (cos_in_tail) ta.sums = TailSums{tail_counter, split_sums, cos_img, cos_txt, losses, ctl.losses_host, ctl.seq, w_img, w_txt, w_con};
+        if (cos_in_tail && ctl.sides == 2) {
+            ta.s[0] = ta.s[1];
+            ta.w_cos_over_B[0] = ta.w_cos_over_B[1];
+            return launch_grad_tail(ta, 1, dtype, st);
         }
+        if (int e = launch_grad_tail(ta, 2, dtype, st)) return e;
     }
     return DCLIP_OK;
 }
@@ -628,31 +640,72 @@ int dclip_distill_loss_teachers(const void* s_img, const void* s_txt, const void
 int dclip_host_distill_step(const void* h_s_img, const void* h_s_txt, const void* h_t_img, const void* h_t_txt, void* const* d_in,
                             int64_t B, int64_t d, int dtype, float temperature, float w_img, float w_txt, float w_con, float grad_scale,
                             float* d_losses, float* h_losses, void* d_s_img, void* d_s_txt, void* workspace, size_t workspace_bytes, int path,
-                            void* compute_stream, void* copy_stream, void* ev_students, void* ev_teachers, void* ev_done) {
+                            void* compute_stream, void* copy_stream, void* ev_students, void* ev_teacher_img, void* ev_teachers, void* ev_done) {
     DCLIP_REQUIRE(h_s_img && h_s_txt && h_t_img && h_t_txt && d_in && d_in[0] && d_in[1] && d_in[2] && d_in[3] && d_losses && h_losses,
                   "host_distill_step: null pointer");
-    DCLIP_REQUIRE(copy_stream && ev_students && ev_teachers && ev_done && copy_stream != compute_stream,
-                  "host_distill_step: needs a copy stream of its own and three events");
+    DCLIP_REQUIRE(copy_stream && ev_students && ev_teacher_img && ev_teachers && ev_done && copy_stream != compute_stream,
+                  "host_distill_step: needs a copy stream of its own and four events");
     cudaStream_t cs = static_cast<cudaStream_t>(compute_stream), xs = static_cast<cudaStream_t>(copy_stream);
-    cudaEvent_t es = static_cast<cudaEvent_t>(ev_students), et = static_cast<cudaEvent_t>(ev_teachers), ed = static_cast<cudaEvent_t>(ev_done);
+    cudaEvent_t es = static_cast<cudaEvent_t>(ev_students), ei = static_cast<cudaEvent_t>(ev_teacher_img),
+                et = static_cast<cudaEvent_t>(ev_teachers), ed = static_cast<cudaEvent_t>(ev_done);
     const size_t bytes = (size_t)B * d * dclip::dtype_size(dtype);
+    // with gradients the teachers phase runs per side and its last block stores the losses straight into h_losses (mapped pinned
+    // memory), sequence word last: the host waits on that word instead of a D2H copy + stream synchronisation
+    const bool direct = d_s_img != nullptr;
+    DCLIP_REQUIRE(!direct || dclip::aligned16(h_losses), "host_distill_step: h_losses must be 16-byte aligned");
+    float* h_dev = nullptr;
+    unsigned int seq = 0;
+    if (direct) {
+        if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&h_dev), h_losses, 0) != cudaSuccess || !h_dev) {
+            (void)cudaGetLastError();
+            return dclip::fail(DCLIP_ERR_INVALID, "host_distill_step: h_losses must be pinned host memory (cudaHostAlloc / cudaHostRegister), 8 floats");
+        }
+        seq = __atomic_load_n(reinterpret_cast<unsigned int*>(h_losses + 4), __ATOMIC_RELAXED) + 1u;
+    }
     // the device input buffers are free again once the previous step's kernels are done
     DCLIP_CUDA_OK(cudaStreamWaitEvent(xs, ed, 0));
     DCLIP_CUDA_OK(cudaMemcpyAsync(d_in[0], h_s_img, bytes, cudaMemcpyHostToDevice, xs));
     DCLIP_CUDA_OK(cudaMemcpyAsync(d_in[1], h_s_txt, bytes, cudaMemcpyHostToDevice, xs));
     DCLIP_CUDA_OK(cudaEventRecord(es, xs));
     DCLIP_CUDA_OK(cudaMemcpyAsync(d_in[2], h_t_img, bytes, cudaMemcpyHostToDevice, xs));
+    DCLIP_CUDA_OK(cudaEventRecord(ei, xs));
     DCLIP_CUDA_OK(cudaMemcpyAsync(d_in[3], h_t_txt, bytes, cudaMemcpyHostToDevice, xs));
     DCLIP_CUDA_OK(cudaEventRecord(et, xs));
     DCLIP_CUDA_OK(cudaStreamWaitEvent(cs, es, 0));
     if (int e = distill_loss_impl(1, d_in[0], d_in[1], nullptr, nullptr, B, d, dtype, temperature, 0.f, 0.f, w_con, 1.f, nullptr, nullptr, nullptr,
                                   nullptr, workspace, workspace_bytes, path, compute_stream)) return e;
+    if (!direct) {
+        DCLIP_CUDA_OK(cudaStreamWaitEvent(cs, et, 0));
+        if (int e = distill_loss_impl(2, d_in[0], d_in[1], d_in[2], d_in[3], B, d, dtype, temperature, w_img, w_txt, w_con, grad_scale, d_losses,
+                                      nullptr, nullptr, nullptr, workspace, workspace_bytes, path, compute_stream)) return e;
+        DCLIP_CUDA_OK(cudaMemcpyAsync(h_losses, d_losses, 4 * sizeof(float), cudaMemcpyDeviceToHost, cs));
+        DCLIP_CUDA_OK(cudaEventRecord(ed, cs));
+        DCLIP_CUDA_OK(cudaStreamSynchronize(cs));
+        return DCLIP_OK;
+    }
+    DCLIP_CUDA_OK(cudaStreamWaitEvent(cs, ei, 0));
+    if (int e = distill_loss_impl(2, d_in[0], d_in[1], d_in[2], d_in[3], B, d, dtype, temperature, w_img, w_txt, w_con, grad_scale, d_losses,
+                                  d_s_img, d_s_txt, nullptr, workspace, workspace_bytes, path, compute_stream, TailCtl{1, nullptr, 0u})) return e;
     DCLIP_CUDA_OK(cudaStreamWaitEvent(cs, et, 0));
     if (int e = distill_loss_impl(2, d_in[0], d_in[1], d_in[2], d_in[3], B, d, dtype, temperature, w_img, w_txt, w_con, grad_scale, d_losses,
-                                  d_s_img, d_s_txt, nullptr, workspace, workspace_bytes, path, compute_stream)) return e;
-    DCLIP_CUDA_OK(cudaMemcpyAsync(h_losses, d_losses, 4 * sizeof(float), cudaMemcpyDeviceToHost, cs));
+                                  d_s_img, d_s_txt, nullptr, workspace, workspace_bytes, path, compute_stream, TailCtl{2, h_dev, seq})) return e;
     DCLIP_CUDA_OK(cudaEventRecord(ed, cs));
-    DCLIP_CUDA_OK(cudaStreamSynchronize(cs));
+    // the one host wait of the step: the sequence word behind the losses (the stream is queried now and then so that a failed launch
+    // or a device fault ends the wait with its error instead of hanging)
+    const unsigned int* flag = reinterpret_cast<const unsigned int*>(h_losses + 4);
+    for (unsigned int spins = 1; __atomic_load_n(flag, __ATOMIC_ACQUIRE) != seq; ++spins) {
+        if ((spins & 0xfffu) == 0u) {
+            const cudaError_t q = cudaStreamQuery(cs);
+            if (q == cudaSuccess) {
+                if (__atomic_load_n(flag, __ATOMIC_ACQUIRE) == seq) break;
+                return dclip::fail(DCLIP_ERR_CUDA, "host_distill_step: the step finished without delivering its losses");
+            }
+            if (q != cudaErrorNotReady) return dclip::fail(DCLIP_ERR_CUDA, "host_distill_step: %s", cudaGetErrorString(q));
+        }
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+    }
     return DCLIP_OK;
 }
 

@@ -45,9 +45,22 @@ struct GradArgs {
 
 struct TailSide { const void* x; const void* t; const float* inv_norm; const float* dx_hat; void* d_x;
                   float* cos_out; };      // optional: cos(x, t) of the row (the split host-buffer step: saves the separate cosine pass)
+// Teachers phase of the split objective: the LAST block of the (last) tail launch finishes the four losses from the cosine terms the
+// tail launches left (TailSide::cos_out) and the contrastive sum of the students phase - no k_loss_sums launch behind the tail - and,
+// for the host-buffer step, also stores them into mapped pinned host memory followed by a sequence word (no D2H copy, no event wait).
+struct TailSums {
+    unsigned int* counter;               // blocks done; zero on entry (cleared by the students phase), left zero
+    const float* con_sum;                // raw sum of lse_u + lse_v - 2 diag (students phase)
+    const float* cos_img; const float* cos_txt;      // [m]
+    float* losses;                       // device {total, img, txt, con}
+    float* losses_host;                  // optional: device-visible address of a pinned host float[8]; [4] receives seq after the losses
+    unsigned int seq;
+    float w_img, w_txt, w_con;
+};
 struct TailArgs {
     TailSide s[2]; int64_t m, d; float w_cos_over_B[2]; float grad_scale;
     PeerCtx peers;                       // peers.world > 1: the last block tells every peer that this rank is done with the step's buffers
+    TailSums sums;                       // sums.counter != nullptr: see TailSums
 };
 
 struct SumsArgs {
@@ -56,6 +69,7 @@ struct SumsArgs {
     float* out3;      // raw partial sums (sharded API) or nullptr
     float* losses;    // finished {total, img, txt, con} (single-GPU composite) or nullptr
     float w_img, w_txt, w_con;
+    unsigned int* zero_counter;   // optional: cleared by the thread that writes the sums (TailSums::counter of the teachers phase)
 };
 
 // ---- tensor path (loss_tc.cu) ----

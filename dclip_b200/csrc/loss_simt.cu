@@ -314,7 +314,8 @@ __global__ void __cluster_dims__(kFinCtas, 1, 1) __launch_bounds__(kFinThreads) 
     if (rank == 0 && threadIdx.x == 0) {
         float t0 = 0.f, t1 = 0.f, t2 = 0.f;
         for (int r = 0; r < kFinCtas; ++r) { t0 += gather[r][0]; t1 += gather[r][1]; t2 += gather[r][2]; }
-        if (a.out3) { a.out3[0] = t0; a.out3[1] = t1; a.out3[2] = t2; }   // sharded: raw local sums
+        if (a.out3) { a.out3[0] = t0; a.out3[1] = t1; a.out3[2] = t2; }   // sharded / students phase: raw local sums
+        if (a.zero_counter) *a.zero_counter = 0u;
         if (px && a.out3) {
             for (int r = 0; r < f.peers.world; ++r)
                 if (r != f.peers.rank) { float* o = p2p_remote(f.peers, a.out3, r); o[0] = t0; o[1] = t1; o[2] = t2; }
@@ -568,6 +569,54 @@ __device__ __forceinline__ void tail_signal_done(const TailArgs& a) {
     __syncthreads();                     // (nothing is published to the peers here: no per-thread system fence; p2p_signal_all fences once)
     if (threadIdx.x == 0 && p2p_last_block(a.peers, gridDim.x * gridDim.y)) p2p_signal_all(a.peers, kP2PKindDone);
 }
+// teachers phase of the split objective (TailSums): the last block to finish sums the cosine terms in a fixed order (thread-strided,
+// shuffle tree, warps in order) and writes the four losses; the host-buffer step gets them straight into mapped pinned memory,
+// sequence word last
+__device__ __forceinline__ void tail_finish_losses(const TailArgs& a) {
+    __shared__ float red[2][32];
+    __shared__ int is_last;
+    const TailSums& q = a.sums;
+    __syncthreads();                     // this block's cosine terms are stored (thread 0's fence below is cumulative)
+    if (threadIdx.x == 0) {
+        __threadfence();
+        is_last = atomicAdd(q.counter, 1u) == gridDim.x * gridDim.y - 1u;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const float con_sum = threadIdx.x == 0 ? __ldcg(q.con_sum) : 0.f;      // requested ahead of the sums
+    float s1 = 0.f, s2 = 0.f;
+    const int64_t m4 = a.m >> 2;
+    if (q.cos_img) {
+        const float4* c = reinterpret_cast<const float4*>(q.cos_img);
+#pragma unroll 8
+        for (int64_t i = threadIdx.x; i < m4; i += blockDim.x) { const float4 v = __ldcg(c + i); s1 += (1.0f - v.x) + (1.0f - v.y) + (1.0f - v.z) + (1.0f - v.w); }
+        for (int64_t i = m4 * 4 + threadIdx.x; i < a.m; i += blockDim.x) s1 += 1.0f - __ldcg(q.cos_img + i);
+    }
+    if (q.cos_txt) {
+        const float4* c = reinterpret_cast<const float4*>(q.cos_txt);
+#pragma unroll 8
+        for (int64_t i = threadIdx.x; i < m4; i += blockDim.x) { const float4 v = __ldcg(c + i); s2 += (1.0f - v.x) + (1.0f - v.y) + (1.0f - v.z) + (1.0f - v.w); }
+        for (int64_t i = m4 * 4 + threadIdx.x; i < a.m; i += blockDim.x) s2 += 1.0f - __ldcg(q.cos_txt + i);
+    }
+    s1 = warp_sum(s1); s2 = warp_sum(s2);
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s1; red[1][threadIdx.x >> 5] = s2; }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    float t1 = 0.f, t2 = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { t1 += red[0][w]; t2 += red[1][w]; }
+    const float l_con = con_sum / (2.0f * (float)a.m);
+    const float l_img = q.cos_img ? t1 / (float)a.m : 0.f;
+    const float l_txt = q.cos_txt ? t2 / (float)a.m : 0.f;
+    const float total = q.w_img * l_img + q.w_txt * l_txt + q.w_con * l_con;
+    if (q.losses_host) *reinterpret_cast<float4*>(q.losses_host) = make_float4(total, l_img, l_txt, l_con);
+    q.losses[0] = total; q.losses[1] = l_img; q.losses[2] = l_txt; q.losses[3] = l_con;
+    *q.counter = 0u;
+    if (q.losses_host) {
+        __threadfence_system();          // (also orders this step's gradient stores before the word the host waits for)
+        *reinterpret_cast<volatile unsigned int*>(q.losses_host + 4) = q.seq;
+    }
+}
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_loss_grad_tail(TailArgs a) {
     const TailSide s = a.s[blockIdx.y];
@@ -575,6 +624,7 @@ __global__ void __launch_bounds__(kThreads) k_loss_grad_tail(TailArgs a) {
     const int64_t row = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
     if (row >= a.m) {
         if (a.peers.world > 1) tail_signal_done(a);
+        if (a.sums.counter) tail_finish_losses(a);
         return;
     }
     const int64_t d = a.d;
@@ -650,6 +700,7 @@ __global__ void __launch_bounds__(kThreads) k_loss_grad_tail(TailArgs a) {
         store8<T>(out + k, g);
     }
     if (a.peers.world > 1) tail_signal_done(a);
+    if (a.sums.counter) tail_finish_losses(a);
 }
 
 // Same for d <= 1024 and 16-bit I/O: all loads of the row up front (raw 16-byte words, see k_loss_prep_pair_nc), the projection
@@ -661,6 +712,7 @@ __global__ void __launch_bounds__(128) k_loss_grad_tail_nc(TailArgs a) {
     const int64_t row = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (row >= a.m) {
         if (a.peers.world > 1) tail_signal_done(a);
+        if (a.sums.counter) tail_finish_losses(a);
         return;
     }
     const int64_t d = a.d;
@@ -741,6 +793,7 @@ __global__ void __launch_bounds__(128) k_loss_grad_tail_nc(TailArgs a) {
         }
     }
     if (a.peers.world > 1) tail_signal_done(a);
+    if (a.sums.counter) tail_finish_losses(a);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -766,6 +819,7 @@ __global__ void __launch_bounds__(1024) k_loss_sums(SumsArgs a) {
     }
     if (threadIdx.x == 0) {
         if (a.out3) { a.out3[0] = red[0][0]; a.out3[1] = red[1][0]; a.out3[2] = red[2][0]; }
+        if (a.zero_counter) *a.zero_counter = 0u;
         if (a.losses) {   // single-GPU composite: finished losses {total, img, txt, con}
             const float l_con = red[0][0] / (2.0f * (float)a.m);
             const float l_img = a.cos_img ? red[1][0] / (float)a.m : 0.f;

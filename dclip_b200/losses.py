@@ -83,34 +83,47 @@ class HostDistillStep:
         self.bufs = [torch.empty((B, d), dtype=dtype, device=self.dev) for _ in range(4)]
         self.pc = _lib.resolve_loss_path(path, self.bufs[0], temperature)
         self.losses = torch.empty(4, dtype=torch.float32, device=self.dev)
-        self.losses_host = torch.empty(4, dtype=torch.float32).pin_memory()
+        # pinned float[8]: the device stores the four losses and then a sequence word [4] through the buffer's mapped address
+        self._losses_host8 = torch.zeros(8, dtype=torch.float32).pin_memory()
+        self.losses_host = self._losses_host8[:4]
         self.d_img = torch.empty((B, d), dtype=dtype, device=self.dev)
         self.d_txt = torch.empty((B, d), dtype=dtype, device=self.dev)
         self.ws = workspace(self.lib.dclip_distill_loss_workspace_bytes(B, d, self.pc), self.dev)
         self.copy_stream = torch.cuda.Stream(self.dev)
         self.ev_students = torch.cuda.Event()
+        self.ev_teacher_img = torch.cuda.Event()
         self.ev_teachers = torch.cuda.Event()
         self.ev_done = torch.cuda.Event()
         with torch.cuda.device(self.dev):
-            for ev in (self.ev_students, self.ev_teachers, self.ev_done):      # creates the CUDA events (torch makes them lazily)
+            for ev in (self.ev_students, self.ev_teacher_img, self.ev_teachers, self.ev_done):      # creates the CUDA events (torch makes them lazily)
                 ev.record(torch.cuda.current_stream(self.dev))
         self._d_in = (ctypes.c_void_p * 4)(*[t.data_ptr() for t in self.bufs])
-        self._shape = (self.B, self.d)
+        self._size = torch.Size((self.B, self.d))
+        # everything but the four host pointers and the current stream is fixed: converted once (the per-call Python sits between
+        # two steps, where nothing overlaps it)
+        self._fn = self.lib.dclip_host_distill_step
+        self._fixed = (self._d_in, self.B, self.d, dtype_code(self.bufs[0]), *self.hyper, ptr(self.losses),
+                       ctypes.c_void_p(self._losses_host8.data_ptr()), ptr(self.d_img), ptr(self.d_txt), ptr(self.ws), self.ws.numel(), self.pc)
+        self._sync = tuple(ctypes.c_void_p(h) for h in (self.copy_stream.cuda_stream, self.ev_students.cuda_event, self.ev_teacher_img.cuda_event,
+                                                        self.ev_teachers.cuda_event, self.ev_done.cuda_event))
+        self._index = self.dev.index if self.dev.index is not None else torch.cuda.current_device()
 
     def __call__(self, s_img, s_txt, t_img, t_txt):
         """One step = ONE library call (dclip_host_distill_step): the four copies on the copy stream, students first; the contrastive
-        part on the current stream behind the students' event, overlapped with the teachers' copy; the teachers' part; the read of the
-        four losses and the one host wait."""
+        part on the current stream behind the students' event, overlapped with the teachers' copies; the image side's gradient tail
+        behind the image teacher, the text side's behind the text teacher - its last block stores the four losses into the pinned
+        host buffer, which is the one host wait of the step."""
+        size, dtype = self._size, self.dtype
         for t in (s_img, s_txt, t_img, t_txt):
-            if t.is_cuda or tuple(t.shape) != self._shape or t.dtype != self.dtype or not t.is_contiguous():
+            if t.shape != size or t.dtype is not dtype or t.is_cuda or not t.is_contiguous():
                 raise ValueError(f"HostDistillStep: expected four contiguous host [{self.B}, {self.d}] {self.dtype} tensors")
-        temperature, w_img, w_txt, w_con, grad_scale = self.hyper
-        with torch.cuda.device(self.dev):
-            check(self.lib.dclip_host_distill_step(
-                s_img.data_ptr(), s_txt.data_ptr(), t_img.data_ptr(), t_txt.data_ptr(), self._d_in, self.B, self.d, dtype_code(self.bufs[0]),
-                temperature, w_img, w_txt, w_con, grad_scale, ptr(self.losses), self.losses_host.data_ptr(), ptr(self.d_img), ptr(self.d_txt),
-                ptr(self.ws), self.ws.numel(), self.pc, stream_ptr(self.dev), self.copy_stream.cuda_stream, self.ev_students.cuda_event,
-                self.ev_teachers.cuda_event, self.ev_done.cuda_event), "host_distill_step")
+        if torch.cuda.current_device() != self._index:
+            with torch.cuda.device(self._index):
+                return self.__call__(s_img, s_txt, t_img, t_txt)
+        status = self._fn(s_img.data_ptr(), s_txt.data_ptr(), t_img.data_ptr(), t_txt.data_ptr(), *self._fixed,
+                          torch.cuda.current_stream(self._index).cuda_stream, *self._sync)
+        if status:
+            check(status, "host_distill_step")
         return self.losses_host, self.d_img, self.d_txt
 
 

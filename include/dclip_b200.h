@@ -328,16 +328,21 @@ int dclip_xattn_bwd(const void* text, const void* image, int64_t B, int64_t T, i
 
 /* One whole step for inputs in PINNED HOST memory, issued by ONE call (the per-step Python between the pieces - stream contexts,
  * event objects, four tensor copies - was 56 us of a 0.56 ms step): waits for ev_done of the previous step on the copy stream, copies
- * the four [B, d] inputs to d_in[0..3] there (students first, ev_students / ev_teachers recorded behind each pair), runs
- * dclip_distill_loss_students / _teachers on the compute stream behind those events (the contrastive part overlaps the teachers'
- * copy), copies the four losses to h_losses (pinned), records ev_done and synchronises the compute stream - the one host wait of the
- * reference's `loss.item()` (training/train_contrastive_teacher.py:364).  The caller owns streams and events (created once, ev_done
- * recorded once before the first call); gradients stay on the device in d_s_img / d_s_txt. */
+ * the four [B, d] inputs to d_in[0..3] there (students first; ev_students, ev_teacher_img, ev_teachers recorded behind the student
+ * pair, the image teacher and the text teacher), runs dclip_distill_loss_students on the compute stream behind ev_students (the
+ * contrastive part overlaps the teachers' copies), the image side's gradient tail behind ev_teacher_img and the text side's behind
+ * ev_teachers; the last block of that launch finishes the four losses and stores them into h_losses - PINNED host memory of 8
+ * floats, 16-byte aligned, written by the device through its mapped address: [0..3] = {total, img, txt, con}, [4] = a sequence word
+ * stored last, which is what the call waits for (the one host wait of the reference's `loss.item()`,
+ * training/train_contrastive_teacher.py:364; no D2H copy, no stream synchronisation).  d_losses receives the same four values.
+ * Without gradients (d_s_img == d_s_txt == NULL) the teachers phase is one dclip_distill_loss_teachers call followed by a 16-byte
+ * D2H copy and a stream synchronisation.  The caller owns streams and events (created once, ev_done recorded once before the first
+ * call); gradients stay on the device in d_s_img / d_s_txt. */
 int dclip_host_distill_step(const void* h_s_img, const void* h_s_txt, const void* h_t_img, const void* h_t_txt, void* const* d_in,
                             int64_t B, int64_t d, int dtype, float temperature, float w_img, float w_txt, float w_con,
                             float grad_scale, float* d_losses, float* h_losses, void* d_s_img, void* d_s_txt, void* workspace,
                             size_t workspace_bytes, int path, void* compute_stream, void* copy_stream, void* ev_students,
-                            void* ev_teachers, void* ev_done);
+                            void* ev_teacher_img, void* ev_teachers, void* ev_done);
 
 /* out[i] = x[i] * (*scale), scale a float on the DEVICE: the upstream gradient of the scalar loss
  * (`loss.backward()`, training/train_contrastive_teacher.py:361; CLIP_image_distillation.py:634 through Lightning) applied to

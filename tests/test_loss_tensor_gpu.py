@@ -118,21 +118,69 @@ def test_pair_backward_is_bit_reproducible(built_library):
     assert _pipeline_ok(built_library)
 
 
-@pytest.mark.parametrize("B,d,dtype,path", [(512, 768, torch.bfloat16, "tensor"), (96, 256, torch.float32, "fp32")])
+@pytest.mark.parametrize("B,d,dtype,path", [(512, 768, torch.bfloat16, "tensor"), (96, 256, torch.float32, "fp32"),
+                                            (4096, 768, torch.bfloat16, "tensor"), (250, 256, torch.float16, "tensor"),
+                                            (101, 512, torch.float32, "fp32"), (203, 384, torch.bfloat16, "fp32")])
 def test_host_step_split_matches_composite(built_library, B, d, dtype, path):
-    """HostDistillStep (students / teachers phases, copies overlapped) against the one-call composite."""
+    """HostDistillStep (students phase, then the teachers phase per side; the last block of the text side's gradient tail stores the
+    losses into the pinned host buffer the call waits on) against the one-call composite, incl. batches that do not fill the tail's
+    row blocks."""
     from dclip_b200 import losses as L
     dev = torch.device("cuda:0")
     host = [t.to(dtype).contiguous().pin_memory() for t in synthetic.loss_inputs(B, d, seed=3)]
-    step = L.HostDistillStep(B, d, dtype, dev, path=path)
-    for _ in range(3):
+    gs = 1024.0 if dtype == torch.float16 else 1.0      # fp16 gradients of magnitude 1e-5 are subnormal: loss scale, as AMP does
+    step = L.HostDistillStep(B, d, dtype, dev, path=path, grad_scale=gs)
+    for i in range(4):
         lh, di, dt = step(*host)
-    ref_l, ref_di, ref_dt = L.distill_loss_fwd_bwd(*(t.to(dev) for t in host), path=path)
+        assert torch.equal(lh, step.losses.cpu())        # the host copy is the device's result of THIS step
+        if i == 1:      # other inputs in between: every call must deliver its own losses (sequence word), not a stale buffer
+            other = [t.to(dtype).contiguous().pin_memory() for t in synthetic.loss_inputs(B, d, seed=4)]
+            lo, _, _ = step(*other)
+            ref_o, _, _ = L.distill_loss_fwd_bwd(*(t.to(dev) for t in other), path=path)
+            assert torch.allclose(lo, ref_o.cpu(), rtol=1e-5, atol=1e-6), (lo, ref_o)
+    ref_l, ref_di, ref_dt = L.distill_loss_fwd_bwd(*(t.to(dev) for t in host), path=path, grad_scale=gs)
     torch.cuda.synchronize()
     assert _pipeline_ok(built_library)
     assert torch.allclose(lh, ref_l.cpu(), rtol=1e-5, atol=1e-6), (lh, ref_l)
-    assert _rel(di, ref_di) < 1e-5 + (2 ** -8 if dtype == torch.bfloat16 else 0)
-    assert _rel(dt, ref_dt) < 1e-5 + (2 ** -8 if dtype == torch.bfloat16 else 0)
+    # (the composite finishes its gradients in the GEMM epilogue, the split step in the tail kernel: same fp32 math in another order,
+    # so 16-bit outputs may round the other way here and there)
+    slack = {torch.bfloat16: 2 ** -8, torch.float16: 2 ** -11}.get(dtype, 0)
+    assert _rel(di, ref_di) < 1e-5 + slack
+    assert _rel(dt, ref_dt) < 1e-5 + slack
+
+
+@pytest.mark.parametrize("B,d,dtype,path", [(1000, 512, torch.bfloat16, "tensor"), (77, 256, torch.float32, "fp32")])
+def test_split_objective_through_the_c_abi(built_library, B, d, dtype, path):
+    """dclip_distill_loss_students + dclip_distill_loss_teachers (one tail launch for both sides, its last block finishes the losses)
+    against the one-call composite; twice over the same workspace (the block counter must be left clear), and without gradients."""
+    from dclip_b200 import _lib, losses as L
+    from dclip_b200._lib import check, dtype_code, ptr, stream_ptr
+    lib = built_library
+    dev = torch.device("cuda:0")
+    s_img, s_txt, t_img, t_txt = (t.to(dtype).to(dev) for t in synthetic.loss_inputs(B, d, seed=9))
+    ref_l, ref_di, ref_dt = L.distill_loss_fwd_bwd(s_img, s_txt, t_img, t_txt, w_img=0.7, w_txt=1.3, w_con=0.9, path=path)
+    pc = _lib.resolve_loss_path(path, s_img, 0.05)
+    ws = _lib.workspace(lib.dclip_distill_loss_workspace_bytes(B, d, pc), dev)
+    ws.fill_(0xA5)                                   # no reliance on a zeroed workspace
+    losses = torch.empty(4, dtype=torch.float32, device=dev)
+    di, dt = torch.empty_like(s_img), torch.empty_like(s_txt)
+    st = stream_ptr(dev)
+    for rep in range(2):
+        losses.fill_(-1.0)
+        check(lib.dclip_distill_loss_students(ptr(s_img), ptr(s_txt), B, d, dtype_code(s_img), 0.05, 0.9, ptr(ws), ws.numel(), pc, st), "students")
+        check(lib.dclip_distill_loss_teachers(ptr(s_img), ptr(s_txt), ptr(t_img), ptr(t_txt), B, d, dtype_code(s_img), 0.05, 0.7, 1.3, 0.9, 1.0,
+                                              ptr(losses), ptr(di), ptr(dt), ptr(ws), ws.numel(), pc, st), "teachers")
+        torch.cuda.synchronize()
+        assert torch.allclose(losses, ref_l, rtol=1e-5, atol=1e-6), (rep, losses, ref_l)
+        tol = 1e-5 + (2 ** -8 if dtype == torch.bfloat16 else 0)
+        assert _rel(di, ref_di) < tol and _rel(dt, ref_dt) < tol
+    losses.fill_(-1.0)          # loss only: cosine rows + loss sums kernels
+    check(lib.dclip_distill_loss_students(ptr(s_img), ptr(s_txt), B, d, dtype_code(s_img), 0.05, 0.9, ptr(ws), ws.numel(), pc, st), "students")
+    check(lib.dclip_distill_loss_teachers(ptr(s_img), ptr(s_txt), ptr(t_img), ptr(t_txt), B, d, dtype_code(s_img), 0.05, 0.7, 1.3, 0.9, 1.0,
+                                          ptr(losses), None, None, ptr(ws), ws.numel(), pc, st), "teachers (loss only)")
+    torch.cuda.synchronize()
+    assert torch.allclose(losses, ref_l, rtol=1e-5, atol=1e-6), (losses, ref_l)
+    assert _pipeline_ok(lib)
 
 
 @pytest.mark.parametrize("B,d", [(4096, 768), (1000, 512), (264, 256)])
