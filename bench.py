@@ -259,7 +259,8 @@ def main():
     def step_e2e():
         if host_step is not None:
             # public host-buffer API: pinned host -> device copies (students first), the contrastive part overlapped
-            # with the teachers' copy, device -> host read of the four losses; all inside the timed region
+            # with the teachers' copies, the four losses delivered into pinned host memory (returned as a CPU tensor);
+            # all inside the timed region
             return host_step(*host)[0]
         for dst, src in zip(step_inputs, host):
             dst.copy_(src, non_blocking=True)       # pinned host -> device, inside the timed region
@@ -355,7 +356,9 @@ def main():
             "clocks": clocks,
             "e2e": {"value": B / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in host) * world,
-                    "d2h_bytes_per_step": 16 * world},
+                    # N = 1: the four losses + a sequence word, stored by the last block of the step's last kernel into the pinned
+                    # host buffer the call waits on (HostDistillStep); N > 1: a 16-byte D2H copy of the losses
+                    "d2h_bytes_per_step": 20 if world == 1 else 16 * world},
             "gpu_launches": int(launches_per_step_now()) * args.steps,
             "roofline": roof, "cpu_baseline": cpu,
         }
