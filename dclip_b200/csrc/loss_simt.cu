@@ -24,6 +24,12 @@ constexpr float kNormEps = 1e-12f;  // F.normalize eps
 // prep: one warp per row.  x_hat = x / max(|x|, eps); cos = x_hat . t_hat
 // ---------------------------------------------------------------------------------------------
 
+// x / max(|x|, eps): the FP32 tier divides like F.normalize (1e-5 parity); 16-bit OPERANDS (rounded to 2^-11 right after) take the
+// reciprocal the kernel stores as inv_norm anyway - an fp32 division is ~12 instructions with a branch, and the register-resident
+// prep kernel was bound by exactly those (48 per lane and row pair: 17 -> see DESIGN 4.3)
+template <typename OT> __device__ __forceinline__ float unit_component(float x, float nx, float inv_nx) { return x * inv_nx; }
+template <> __device__ __forceinline__ float unit_component<float>(float x, float nx, float inv_nx) { return x / nx; }
+
 template <typename T, typename OT>
 __global__ void __launch_bounds__(kThreads) k_loss_prep(PrepArgs a) {
     const PrepSide s = a.s[blockIdx.y];
@@ -54,11 +60,12 @@ __global__ void __launch_bounds__(kThreads) k_loss_prep(PrepArgs a) {
         if (s.cos) s.cos[row] = t ? xt / (nx * fmaxf(sqrtf(tt), kNormEps)) : 0.f;
     }
     OT* out = static_cast<OT*>(s.xhat) + row * d;
+    const float inv_nx = 1.0f / nx;
     for (int64_t k = lane * 8; k < d; k += 256) {
         float xv[8];
         load8<T>(x + k, xv);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) xv[i] = xv[i] / nx;
+        for (int i = 0; i < 8; ++i) xv[i] = unit_component<OT>(xv[i], nx, inv_nx);
         store8<OT>(out + k, xv);
     }
 }
@@ -71,7 +78,7 @@ __global__ void __launch_bounds__(kThreads) k_loss_prep_pair(PrepArgs a) {
     const int64_t row = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
     if (row >= a.m) return;
     const int64_t d = a.d;
-    float nrm[2];
+    float nrm[2], inv_nrm[2];
 #pragma unroll
     for (int sd = 0; sd < 2; ++sd) {
         const PrepSide s = a.s[sd];
@@ -92,7 +99,7 @@ __global__ void __launch_bounds__(kThreads) k_loss_prep_pair(PrepArgs a) {
         }
         ss = warp_sum(ss);
         const float nx = fmaxf(sqrtf(ss), kNormEps);
-        nrm[sd] = nx;
+        nrm[sd] = nx; inv_nrm[sd] = 1.0f / nx;
         if (t) { tt = warp_sum(tt); xt = warp_sum(xt); }
         if (lane == 0) {
             s.inv_norm[row] = 1.0f / nx;
@@ -111,8 +118,8 @@ __global__ void __launch_bounds__(kThreads) k_loss_prep_pair(PrepArgs a) {
         load8<T>(x1 + k, v);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            u[i] = to_f32<OT>(from_f32<OT>(u[i] / nrm[0]));
-            v[i] = to_f32<OT>(from_f32<OT>(v[i] / nrm[1]));
+            u[i] = to_f32<OT>(from_f32<OT>(unit_component<OT>(u[i], nrm[0], inv_nrm[0])));
+            v[i] = to_f32<OT>(from_f32<OT>(unit_component<OT>(v[i], nrm[1], inv_nrm[1])));
             dot = fmaf(u[i], v[i], dot);
         }
         store8<OT>(o0 + k, u);
@@ -170,7 +177,7 @@ __global__ void __launch_bounds__(128) k_loss_prep_pair_nc(PrepArgs a) {
         const unsigned int target = p2p_ld_volatile(&p2p_flags(a.peers, a.peers.rank)->expected[kP2PKindDone]) + 1;
         p2p_wait_all_warp(a.peers, kP2PKindDone, target, a.error_flag, lane);
     }
-    float nrm[2];
+    float nrm[2], inv_nrm[2];
 #pragma unroll
     for (int sd = 0; sd < 2; ++sd) {
         float ss = 0.f, tt = 0.f, xt = 0.f;
@@ -188,7 +195,7 @@ __global__ void __launch_bounds__(128) k_loss_prep_pair_nc(PrepArgs a) {
             }
         ss = warp_sum(ss);
         const float nx = fmaxf(sqrtf(ss), kNormEps);
-        nrm[sd] = nx;
+        nrm[sd] = nx; inv_nrm[sd] = 1.0f / nx;
         if (has_t) { tt = warp_sum(tt); xt = warp_sum(xt); }
         if (lane == 0 && row < a.m) {
             a.s[sd].inv_norm[row] = 1.0f / nx;
@@ -208,8 +215,8 @@ __global__ void __launch_bounds__(128) k_loss_prep_pair_nc(PrepArgs a) {
             unpack8<T>(xr[1][k], v);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                u[i] = to_f32<OT>(from_f32<OT>(u[i] / nrm[0]));
-                v[i] = to_f32<OT>(from_f32<OT>(v[i] / nrm[1]));
+                u[i] = to_f32<OT>(from_f32<OT>(unit_component<OT>(u[i], nrm[0], inv_nrm[0])));
+                v[i] = to_f32<OT>(from_f32<OT>(unit_component<OT>(v[i], nrm[1], inv_nrm[1])));
                 dot = fmaf(u[i], v[i], dot);
             }
             store8<OT>(o0 + ch * 8, u);
