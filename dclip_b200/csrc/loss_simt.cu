@@ -280,16 +280,25 @@ __global__ void __cluster_dims__(kFinCtas, 1, 1) __launch_bounds__(kFinThreads) 
     }
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
     for (int64_t i = (int64_t)rank * kFinThreads + threadIdx.x; i < f.m; i += kFinCtas * kFinThreads) {
+        // a thread has one or two rows: every load of the row is requested before the first add (a batch of 8 at a time was four
+        // dependent L2 round trips for the 32 column partials of B = 4096); the sums keep their order
+        const float dg = a.diag[i];
+        const float c_img = a.cos_img ? a.cos_img[i] : 0.f, c_txt = a.cos_txt ? a.cos_txt[i] : 0.f;
         float su = 0.f, sv = 0.f;
 #pragma unroll 4
         for (int p = 0; p < f.nsplit; ++p) su += f.part_u[(int64_t)p * f.m + i];
-#pragma unroll 8
-        for (int p = 0; p < nsv; ++p) sv += f.part_v[(int64_t)p * f.m + i];
+        for (int p0 = 0; p0 < nsv; p0 += 32) {
+            float pv[32];
+#pragma unroll
+            for (int p = 0; p < 32; ++p) pv[p] = p0 + p < nsv ? __ldg(f.part_v + (int64_t)(p0 + p) * f.m + i) : 0.f;
+#pragma unroll
+            for (int p = 0; p < 32; ++p) sv += pv[p];
+        }
         const float lu = f.inv_tau + logf(su), lv = f.inv_tau + logf(sv);
         f.lse_u[i] = lu; f.lse_v[i] = lv;
-        s0 += lu + lv - 2.0f * a.diag[i];
-        if (a.cos_img) s1 += 1.0f - a.cos_img[i];
-        if (a.cos_txt) s2 += 1.0f - a.cos_txt[i];
+        s0 += lu + lv - 2.0f * dg;
+        if (a.cos_img) s1 += 1.0f - c_img;
+        if (a.cos_txt) s2 += 1.0f - c_txt;
     }
     red[0][threadIdx.x] = s0; red[1][threadIdx.x] = s1; red[2][threadIdx.x] = s2;
     __syncthreads();
