@@ -134,7 +134,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import reference_arm, synthetic
+    import workloads as synthetic
+    from oracle import reference_arm
     arm = reference_arm.load()
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -188,7 +189,7 @@ def main():
 
     from dclip_b200 import _lib
     from dclip_b200 import losses as L
-    from oracle import synthetic          # synthetic input recipe only (not the checker, not timed)
+    import workloads as synthetic          # seeded input recipes (neutral module: the GPU arm never imports oracle/)
 
     lib = _lib.load_library()
     tdtype = {"bf16": torch.bfloat16, "fp32": torch.float32, "fp16": torch.float16}[args.dtype]
@@ -466,7 +467,7 @@ def weak_scaling_bench(L, dev, rank, world, d, tdtype, path, timed, args):
     """N > 1 only: 4096 rows PER GPU (global batch 4096 N), the same sharded step.  Per-rank tile work is what one GPU
     does at N = 1 times N in the column direction; reported so that the exchange is judged on a shape where the
     compute can hide it.  Rank 0 returns the dict."""
-    from oracle import synthetic
+    import workloads as synthetic
     m = 4096
     Bw = m * world
     inputs = [t.to(tdtype)[rank * m:(rank + 1) * m].contiguous().to(dev) for t in synthetic.loss_inputs(Bw, d, seed=43)]
@@ -569,7 +570,7 @@ def retrieval_bench(dev, with_cpu):
     import numpy as np
 
     from dclip_b200 import retrieval as R
-    from oracle import synthetic
+    import workloads as synthetic
     out = {}
     cap, img, image_ids, cap_ids = synthetic.retrieval_inputs(1000, 5, 512, 7.0, seed=44)      # the tests/golden/retrieval_cfg2 recipe
     cap_d, img_d = torch.from_numpy(cap).to(dev), torch.from_numpy(img).to(dev)
@@ -642,7 +643,7 @@ def fp32_input_bench(L, dev, B, d):
     """The same objective for fp32 inputs (the reference's own dtype): `path="tensor"` rounds the L2-normalised rows to fp16
     operands once (fp32 accumulate, fp32 gradients: the 1e-3 tier), `path="fp32"` is the exact CUDA-core tier (1e-5) that
     `path="auto"` selects for fp32 inputs.  Device-timed, eager launches, L2 flushed between steps."""
-    from oracle import synthetic
+    import workloads as synthetic
     inp = [t.to(dev) for t in synthetic.loss_inputs(B, d, seed=42)]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     out = {"workload": f"distill-loss fwd+bwd, B={B}, d={d}, fp32 inputs and gradients"}
@@ -684,14 +685,13 @@ def teacher_step_bench(dev, with_cpu):
     from dclip_b200 import losses as L
     from dclip_b200.optim import FusedAdam
     from dclip_b200.patch_text_aggregation import GraphedTeacherStep, PatchTextAggregation
-    from oracle import reference_math as om
-    from oracle import synthetic
+    import workloads as synthetic
     peaks = load_peaks()
     out = {}
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     flush_rd = torch.zeros(32 * 1024 * 1024, dtype=torch.int64, device=dev)
     for name, (B, T, R, d, dtype) in (("cfg0", (32, 77, 8, 512, torch.float32)), ("cfg2", (32, 77, 36, 768, torch.bfloat16))):
-        params = om.perturbed_cross_attention_params(d, 8, 42)
+        params = synthetic.perturbed_cross_attention_params(d, 8, 42)
         text, image = synthetic.xattn_inputs(B, T, R, d, 42, ragged=True)
         txt = torch.randn(B, d, generator=torch.Generator().manual_seed(43))
 
@@ -752,7 +752,8 @@ def teacher_step_bench(dev, with_cpu):
 
 
 def cpu_baseline(B, d):
-    from oracle import reference_arm, synthetic
+    import workloads as synthetic
+    from oracle import reference_arm
     arm = reference_arm.load()
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)

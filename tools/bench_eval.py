@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from torch.profiler import ProfilerActivity, profile
 from dclip_b200 import retrieval as R
-from oracle import synthetic
+import workloads as synthetic
 dev = torch.device("cuda:0")
 cap, img, image_ids, cap_ids = synthetic.retrieval_inputs(1000, 5, 512, 7.0, seed=44)
 cap_d, img_d = torch.from_numpy(cap).to(dev), torch.from_numpy(img).to(dev)

@@ -6,7 +6,7 @@ import torch
 from dclip_b200 import losses as L
 from dclip_b200.patch_text_aggregation import PatchTextAggregation
 from oracle import reference_math as om
-from oracle import synthetic
+import workloads as synthetic
 
 def run(B, T, R, d, dtype, cpu=False):
     dev = torch.device("cuda:0")

@@ -2,7 +2,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from dclip_b200 import losses as L
-from oracle import synthetic
+import workloads as synthetic
 dev = torch.device("cuda:0")
 for B, d in ((1024, 768), (4096, 256), (640, 512), (4096, 768)):
     x = [t.to(torch.bfloat16).to(dev) for t in synthetic.loss_inputs(B, d, seed=7)]

@@ -7,7 +7,7 @@ os.environ.setdefault("DCLIP_B200_LIB", os.path.join(ROOT, "build", "prof", "lib
 import torch
 from dclip_b200 import _lib, losses as L
 from dclip_b200._lib import check, dtype_code, ptr, stream_ptr
-from oracle import synthetic
+import workloads as synthetic
 lib = _lib.load_library()
 dev = torch.device("cuda:0")
 B, d = 4096, 768

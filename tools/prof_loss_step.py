@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from torch.profiler import ProfilerActivity, profile
 from dclip_b200 import losses as L
-from oracle import synthetic
+import workloads as synthetic
 dev = torch.device("cuda:0")
 B, d = 4096, 768
 x = [t.to(torch.bfloat16).to(dev) for t in synthetic.loss_inputs(B, d, seed=42)]

@@ -6,7 +6,7 @@ import torch
 import torch.distributed as dist
 from torch.profiler import ProfilerActivity, profile
 from dclip_b200 import losses as L
-from oracle import synthetic
+import workloads as synthetic
 
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))

@@ -6,7 +6,7 @@ sys.path.insert(0, ROOT)
 os.environ.setdefault("DCLIP_B200_LIB", os.path.join(ROOT, "build", "prof", "libdclip_b200_prof.so"))
 import torch
 from dclip_b200 import _lib, losses as L
-from oracle import synthetic
+import workloads as synthetic
 lib = _lib.load_library()
 dev = torch.device("cuda:0")
 B, d = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (4096, 768)

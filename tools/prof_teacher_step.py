@@ -6,14 +6,13 @@ import torch
 from torch.profiler import ProfilerActivity, profile
 from dclip_b200 import losses as L
 from dclip_b200.patch_text_aggregation import PatchTextAggregation
-from oracle import reference_math as om
-from oracle import synthetic
+import workloads as synthetic
 
 dtype = torch.bfloat16 if (len(sys.argv) < 2 or sys.argv[1] == "bf16") else torch.float32
 B, T, R, d = (int(x) for x in sys.argv[2:6]) if len(sys.argv) >= 6 else (32, 77, 36, 768)
 dev = torch.device("cuda:0")
 m = PatchTextAggregation(embed_dim=d, num_heads=8)
-m.cross_modal_attention.load_state_dict(om.perturbed_cross_attention_params(d, 8, 3))
+m.cross_modal_attention.load_state_dict(synthetic.perturbed_cross_attention_params(d, 8, 3))
 m = m.to(dev).to(dtype)
 text, image = synthetic.xattn_inputs(B, T, R, d, 3, ragged=True)
 txt = torch.randn(B, d, generator=torch.Generator().manual_seed(1))

@@ -6,13 +6,12 @@ import torch
 from torch.profiler import ProfilerActivity, profile
 from dclip_b200 import losses as L
 from dclip_b200.patch_text_aggregation import GraphedTeacherStep, PatchTextAggregation
-from oracle import reference_math as om
-from oracle import synthetic
+import workloads as synthetic
 dev = torch.device("cuda:0")
 fp32 = len(sys.argv) > 1 and sys.argv[1] == "fp32"
 B, T, R, d, dtype = (32, 77, 8, 512, torch.float32) if fp32 else (32, 77, 36, 768, torch.bfloat16)
 mod = PatchTextAggregation(embed_dim=d, num_heads=8)
-mod.cross_modal_attention.load_state_dict(om.perturbed_cross_attention_params(d, 8, 42))
+mod.cross_modal_attention.load_state_dict(synthetic.perturbed_cross_attention_params(d, 8, 42))
 mod = mod.to(dev).to(dtype)
 text, image = synthetic.xattn_inputs(B, T, R, d, 42, ragged=True)
 txt = torch.randn(B, d, generator=torch.Generator().manual_seed(43))
