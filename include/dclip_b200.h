@@ -207,7 +207,8 @@ int dclip_sharded_loss_bwd(const void* s_img, const void* s_txt, const void* t_i
  *          wait_after = 1 also performs the wait below for `signal_kind` inside the same launch (all-gather)
  *   wait:  block the stream until every peer has pushed `kind` once more than this rank has consumed so far
  * Kinds are small integers (0..3) chosen by the caller.  Everything is asynchronous on `stream` and can be
- * captured in a CUDA graph.  Waits time out after 10 s (dclip_debug_pipeline_error reports it).
+ * captured in a CUDA graph.  A peer that never arrives is FATAL, as with NCCL's watchdog: after 120 s the waiting kernel sets the
+ * error flag (dclip_debug_pipeline_error) and traps, so the next CUDA call of the process fails.
  */
 size_t dclip_p2p_flags_bytes(void);
 int dclip_p2p_alloc(size_t bytes, void** dev_ptr, unsigned char* handle64);
